@@ -1,0 +1,196 @@
+/*
+ * mzb200 - C ABI of the B200-native self-play search library (libmzb200.so).
+ *
+ * The reference (werner-duvaud/muzero-general) is pure Python and has no FFI; the drop-in
+ * boundary is therefore the set of Python call sites listed next to each entry point below
+ * (file:line in the reference).  A maintainer binds these symbols with ctypes
+ * (see INTEGRATION.md and muzero_general_b200/_lib.py); nothing here mentions torch.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative MZ_E* code on failure; the message is
+ *     available from mz_last_error(handle) (or mz_last_error(NULL) for mz_create failures);
+ *     the library never aborts the process;
+ *   - the caller owns every buffer passed in; the library borrows it for the duration of the
+ *     call.  `mem` says whether the IO pointers of that call are HOST or DEVICE pointers
+ *     (device = the handle's device).  Host buffers are staged through library-owned pinned
+ *     memory, copies included in the call;
+ *   - a handle is NOT thread-safe: one host thread per handle, one handle per GPU process
+ *     (mirrors the reference's one-thread-per-actor model, self_play.py:11-29);
+ *   - all library-owned scratch (node pool, hidden-state pool, staging) is allocated in
+ *     mz_create, sized from max_games, num_simulations, action_space and the net shape.
+ */
+#ifndef MZB200_H
+#define MZB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MZ_ABI_VERSION 1
+#define MZ_MAX_LAYERS 8          /* hidden layers per MLP head */
+#define MZ_MAX_ACTIONS 32        /* |action_space| supported by the tree kernels */
+
+enum { MZ_OK = 0, MZ_EINVAL = -1, MZ_ECUDA = -2, MZ_EUNSUPPORTED = -3, MZ_ESTATE = -4, MZ_ENOMEM = -5 };
+enum { MZ_NET_FC = 0, MZ_NET_RESNET = 1 };
+enum { MZ_MEM_HOST = 0, MZ_MEM_DEVICE = 1 };
+
+/* Shape of the networks built by models.MuZeroNetwork(config)  (models.py:7-41). */
+typedef struct MzNetDesc {
+    int32_t kind;                 /* MZ_NET_FC (models.py:80-195) or MZ_NET_RESNET (models.py:436-623) */
+    int32_t obs_c, obs_h, obs_w;  /* stacked input: C*(s+1)+s channels, H, W (self_play.py:513-550) */
+    int32_t action_space;         /* len(config.action_space); actions are 0..A-1 */
+    int32_t support_size;         /* config.support_size; heads emit 2S+1 logits */
+    /* fully connected */
+    int32_t encoding;
+    int32_t n_fc_representation, fc_representation[MZ_MAX_LAYERS];
+    int32_t n_fc_dynamics, fc_dynamics[MZ_MAX_LAYERS];
+    int32_t n_fc_reward, fc_reward[MZ_MAX_LAYERS];
+    int32_t n_fc_value, fc_value[MZ_MAX_LAYERS];
+    int32_t n_fc_policy, fc_policy[MZ_MAX_LAYERS];
+    /* residual */
+    int32_t blocks, channels;
+    int32_t reduced_reward, reduced_value, reduced_policy;
+    int32_t n_res_fc_reward, res_fc_reward[MZ_MAX_LAYERS];
+    int32_t n_res_fc_value, res_fc_value[MZ_MAX_LAYERS];
+    int32_t n_res_fc_policy, res_fc_policy[MZ_MAX_LAYERS];
+    int32_t downsample;           /* 0 = none, 1 = "resnet" (models.py:233-275) */
+} MzNetDesc;
+
+/* The MuZeroConfig attributes MCTS reads (self_play.py:249-430). */
+typedef struct MzSearchDesc {
+    int32_t max_games;            /* capacity B: games searched in lockstep by one call */
+    int32_t num_simulations;      /* config.num_simulations */
+    int32_t num_players;          /* len(config.players); 1 or 2 (self_play.py:411-430) */
+    int32_t reserved;
+    double discount;              /* config.discount */
+    double pb_c_base, pb_c_init;  /* self_play.py:384-390 */
+    double root_dirichlet_alpha;  /* used only when noise is generated on the device */
+    double root_exploration_fraction; /* self_play.py:476 */
+    uint64_t seed;                /* key of the counter-based tie-break / noise stream */
+    /* log((n+base+1)/base)+init and sqrt(n) for n = 0..num_simulations+1, computed by the
+     * caller with the host language's libm so the device reproduces math.log / math.sqrt
+     * (self_play.py:385-390) exactly.  NULL: the library computes them with C log()/sqrt(). */
+    const double* pb_c_table;
+    const double* sqrt_table;
+} MzSearchDesc;
+
+/* One named tensor of the reference state_dict (models.py:69-73), fp32 host memory. */
+typedef struct MzTensor {
+    const char* name;             /* e.g. "dynamics_encoded_state_network.module.0.weight" */
+    const float* data;
+    int64_t numel;
+} MzTensor;
+
+/* Optional per-simulation record of what the device did (student forcing). */
+typedef struct MzTrace {
+    int32_t max_depth;            /* D: entries kept per path */
+    int32_t reserved;
+    int32_t* depth;               /* [n, N]      number of select_child calls of simulation i */
+    uint8_t* actions;             /* [n, N, D]   actions chosen root->leaf */
+    float* value;                 /* [n, N]      scalarised value of the expanded leaf */
+    float* reward;                /* [n, N]      scalarised reward of the expanded leaf */
+    float* priors;                /* [n, N, A]   fp32 softmax priors of the expanded leaf */
+    float* root_priors_raw;       /* [n, A]      root priors before noise (0 for illegal) */
+    float* root_reward;           /* [n] */
+} MzTrace;
+
+/* Teacher forcing: bypass the networks, feed the tree these per-simulation outputs instead. */
+typedef struct MzTeacher {
+    const float* root_value;      /* [n] */
+    const float* root_reward;     /* [n] */
+    const float* root_priors;     /* [n, A] by action id (illegal entries ignored) */
+    const float* value;           /* [n, N] */
+    const float* reward;          /* [n, N] */
+    const float* priors;          /* [n, N, A] */
+} MzTeacher;
+
+/* Arguments of one batched MCTS.run (self_play.py:260-361) over n games. */
+typedef struct MzSearchIO {
+    int32_t n_games;              /* <= max_games */
+    int32_t mem;                  /* MZ_MEM_HOST or MZ_MEM_DEVICE for every pointer below */
+    /* inputs */
+    const float* obs;             /* [n, obs_c*obs_h*obs_w] fp32 (torch.tensor(obs).float(), self_play.py:281-282) */
+    const uint8_t* legal_mask;    /* [n, A] non-zero = legal (self_play.py:296-308); NULL = all legal */
+    const int32_t* to_play;       /* [n] game.to_play(); NULL = 0 */
+    int32_t add_exploration_noise;/* self_play.py:310-314 */
+    int32_t flags;                /* MZ_FLAG_* */
+    const double* noise;          /* [n, A] Dirichlet draw by action id (host draws); NULL = device Philox */
+    const int32_t* first_index;   /* [n] index into the legal list picked at the first simulation's
+                                     all-way tie (self_play.py:371); NULL = device Philox */
+    const int64_t* game_id;       /* [n] global game ids keying the Philox stream; NULL = 0..n-1 */
+    const int32_t* move_index;    /* [n] move number keying the Philox stream; NULL = 0 */
+    /* outputs (any may be NULL) */
+    int32_t* visit_counts;        /* [n, A] child.visit_count by action id, 0 if illegal */
+    double* root_value;           /* [n] root.value() (self_play.py:509) */
+    float* root_predicted_value;  /* [n] mcts_info["root_predicted_value"] */
+    int32_t* max_tree_depth;      /* [n] mcts_info["max_tree_depth"] */
+    int32_t* tie_count;           /* [n] exact UCB ties met after the first simulation */
+    double* root_priors;          /* [n, A] root priors after noise */
+    double* value_range;          /* [n, 2] MinMaxStats minimum, maximum */
+    const MzTeacher* teacher;     /* NULL = use the networks */
+    const MzTrace* trace;         /* NULL = no trace */
+} MzSearchIO;
+
+#define MZ_FLAG_KEEP_TREE 1       /* leave the full tree in the HBM node pool for mz_export_tree */
+#define MZ_FLAG_STEPWISE  2       /* force the generic select/infer/expand+backup pipeline */
+
+/* Full tree of one game after a search with MZ_FLAG_KEEP_TREE (host pointers). Slot layout:
+ * expansion e (0 = root, e = i+1 for simulation i) owns child slots [e*A, e*A+A). */
+typedef struct MzTreeExport {
+    int32_t n_expansions;         /* out */
+    int32_t* child_visit;         /* [(N+1)*A] */
+    double* child_value_sum;      /* [(N+1)*A] */
+    float* child_reward;          /* [(N+1)*A] */
+    double* child_prior;          /* [(N+1)*A] */
+    int32_t* child_expansion;     /* [(N+1)*A] expansion id of the child, -1 if not expanded */
+    float* hidden;                /* [(N+1), hidden_elems] or NULL */
+    int32_t root_visit;           /* out */
+    double root_value_sum;        /* out */
+} MzTreeExport;
+
+/* Results of a batched network call, all DEVICE or all HOST per `mem`; any pointer may be NULL. */
+typedef struct MzInferenceOut {
+    float* value_logits;          /* [n, 2S+1] */
+    float* reward_logits;         /* [n, 2S+1] */
+    float* policy_logits;         /* [n, A] */
+    float* hidden;                /* [n, hidden_elems] (rescaled state) */
+    float* value;                 /* [n] support_to_scalar(value_logits)  (models.py:645-666) */
+    float* reward;                /* [n] support_to_scalar(reward_logits) */
+} MzInferenceOut;
+
+typedef struct MzHandle MzHandle;
+
+/* replaces SelfPlay.__init__ model construction (self_play.py:25-29) + MCTS(config) (self_play.py:257-258) */
+int mz_create(const MzNetDesc* net, const MzSearchDesc* search, int device, MzHandle** out);
+int mz_destroy(MzHandle* h);
+const char* mz_last_error(const MzHandle* h);
+int mz_abi_version(void);
+
+/* replaces model.set_weights(state_dict) (models.py:72-73, self_play.py:27,37) */
+int mz_load_weights(MzHandle* h, const MzTensor* tensors, int32_t n_tensors);
+
+/* replaces MCTS.run for a batch of games (self_play.py:260-361; called from self_play.py:144-150) */
+int mz_search(MzHandle* h, const MzSearchIO* io);
+
+/* replaces model.initial_inference / recurrent_inference (models.py:172-195, 601-623) */
+int mz_initial_inference(MzHandle* h, int32_t n, int32_t mem, const float* obs, const MzInferenceOut* out);
+int mz_recurrent_inference(MzHandle* h, int32_t n, int32_t mem, const float* hidden, const int32_t* action,
+                           const MzInferenceOut* out);
+
+/* Node graph access for callers that walk the tree (self_play.py:229-232,499-509; diagnose_model.py:164,222-255) */
+int mz_export_tree(MzHandle* h, int32_t game, MzTreeExport* out);
+
+/* sizes derived from the descriptors */
+int64_t mz_hidden_elems(const MzHandle* h);
+int64_t mz_obs_elems(const MzHandle* h);
+/* number of kernels this handle has launched so far (bench.py's gpu_launches) */
+int64_t mz_launch_count(const MzHandle* h);
+/* device time of the search kernels of the last mz_search call, ms (CUDA events on the library stream) */
+double mz_last_search_ms(const MzHandle* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MZB200_H */

@@ -1,0 +1,578 @@
+// Host side of libmzb200.so: the C ABI declared in include/mzb200.h.
+//
+// Owns the device allocations (node pool, hidden-state pool, IO arenas, weight blobs), turns a
+// reference state_dict into kernel layouts, and dispatches a batched MCTS.run to
+//   - the fused persistent kernel (fc_search.cu) for fully-connected nets, or
+//   - the step-wise pipeline select -> network -> expand+backup (tree_kernels.cu + the network
+//     kernels) for residual nets, for teacher-forced tree tests and on MZ_FLAG_STEPWISE.
+// No torch types, no exceptions across the boundary, never aborts.
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <map>
+#include <string>
+#include <vector>
+
+#include "kernels.h"
+#include "pipeline.h"
+
+using namespace mz;
+
+static thread_local std::string g_create_error;
+
+struct MzHandle {
+    MzNetDesc net;
+    MzSearchDesc search;
+    int device = 0;
+    int sm_count = 0;
+    size_t smem_cap = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    std::string err;
+    int64_t launches = 0;
+    double last_ms = 0.0;
+    // tables
+    double* d_pbc = nullptr;
+    double* d_sqrt = nullptr;
+    // fully-connected weights
+    FcNet fc{};
+    float* d_fc_blob = nullptr;
+    bool weights_loaded = false;
+    int fc_group = 16;
+    // residual weights + workspace
+    ResNetDevice* res = nullptr;
+    // pool
+    NodePool pool{};
+    int64_t hidden_elems = 0, obs_elems = 0;
+    // IO arenas
+    unsigned char* d_in = nullptr;
+    unsigned char* d_out = nullptr;
+    unsigned char* h_in = nullptr;
+    unsigned char* h_out = nullptr;
+    size_t in_cap = 0, out_cap = 0;
+    // lazily allocated debug buffers
+    std::vector<void*> debug_allocs;
+    std::map<std::string, std::pair<void*, size_t>> named;
+};
+
+static int fail(MzHandle* h, int code, const std::string& msg) {
+    if (h) h->err = msg; else g_create_error = msg;
+    return code;
+}
+
+#define MZ_CUDA(h, expr)                                                                          \
+    do {                                                                                          \
+        cudaError_t _e = (expr);                                                                  \
+        if (_e != cudaSuccess)                                                                    \
+            return fail(h, MZ_ECUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));          \
+    } while (0)
+
+template <typename T>
+static cudaError_t dev_alloc(T** p, size_t count) { return cudaMalloc(reinterpret_cast<void**>(p), count * sizeof(T) + 16); }
+
+static void* named_buffer(MzHandle* h, const char* name, size_t bytes) {
+    auto it = h->named.find(name);
+    if (it != h->named.end() && it->second.second >= bytes) return it->second.first;
+    if (it != h->named.end()) cudaFree(it->second.first);
+    void* p = nullptr;
+    if (cudaMalloc(&p, bytes + 16) != cudaSuccess) return nullptr;
+    h->named[name] = {p, bytes};
+    return p;
+}
+
+extern "C" int mz_abi_version(void) { return MZ_ABI_VERSION; }
+
+extern "C" const char* mz_last_error(const MzHandle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+static int mlp_dims(const int32_t* hidden, int n_hidden, int in, int out, std::vector<int>& sizes) {
+    if (n_hidden < 0 || n_hidden > MZ_MAX_LAYERS) return -1;
+    sizes.clear();
+    sizes.push_back(in);
+    for (int i = 0; i < n_hidden; ++i) sizes.push_back(hidden[i]);
+    sizes.push_back(out);
+    return 0;
+}
+
+extern "C" int mz_create(const MzNetDesc* net, const MzSearchDesc* search, int device, MzHandle** out) {
+    if (!net || !search || !out) return fail(nullptr, MZ_EINVAL, "mz_create: null argument");
+    *out = nullptr;
+    if (search->num_players > 2)       // self_play.py:429-430
+        return fail(nullptr, MZ_EUNSUPPORTED, "More than two player mode not implemented.");
+    if (search->num_players < 1 || search->max_games < 1 || search->num_simulations < 0)
+        return fail(nullptr, MZ_EINVAL, "mz_create: bad search descriptor");
+    if (net->action_space < 1 || net->action_space > MZ_MAX_ACTIONS)
+        return fail(nullptr, MZ_EUNSUPPORTED, "mz_create: action_space must be in [1, 32]");
+    if (net->kind != MZ_NET_FC && net->kind != MZ_NET_RESNET)
+        return fail(nullptr, MZ_EUNSUPPORTED, "The network parameter should be \"fullyconnected\" or \"resnet\".");
+    if (net->kind == MZ_NET_RESNET && net->downsample > 1)
+        return fail(nullptr, MZ_EUNSUPPORTED, "downsample=\"CNN\" is not supported");
+
+    int n_dev = 0;
+    if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev <= device)
+        return fail(nullptr, MZ_ECUDA, "mz_create: no such CUDA device (this library has no CPU fallback)");
+    MzHandle* h = new (std::nothrow) MzHandle();
+    if (!h) return fail(nullptr, MZ_ENOMEM, "mz_create: out of host memory");
+    h->net = *net;
+    h->search = *search;
+    h->search.pb_c_table = nullptr;
+    h->search.sqrt_table = nullptr;
+    h->device = device;
+#define MZ_CREATE_CUDA(expr)                                                                      \
+    do {                                                                                          \
+        cudaError_t _e = (expr);                                                                  \
+        if (_e != cudaSuccess) {                                                                  \
+            fail(nullptr, MZ_ECUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));           \
+            mz_destroy(h);                                                                        \
+            return MZ_ECUDA;                                                                      \
+        }                                                                                         \
+    } while (0)
+    MZ_CREATE_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    MZ_CREATE_CUDA(cudaGetDeviceProperties(&prop, device));
+    h->sm_count = prop.multiProcessorCount;
+    h->smem_cap = prop.sharedMemPerBlockOptin;
+    MZ_CREATE_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    MZ_CREATE_CUDA(cudaEventCreate(&h->ev0));
+    MZ_CREATE_CUDA(cudaEventCreate(&h->ev1));
+
+    const int B = search->max_games, N = search->num_simulations, A = net->action_space;
+    // ---- UCB tables (self_play.py:385-390)
+    std::vector<double> pbc(N + 2), sq(N + 2);
+    for (int n = 0; n < N + 2; ++n) {
+        pbc[n] = search->pb_c_table ? search->pb_c_table[n]
+                                    : log(((double)n + search->pb_c_base + 1) / search->pb_c_base) + search->pb_c_init;
+        sq[n] = search->sqrt_table ? search->sqrt_table[n] : sqrt((double)n);
+    }
+    MZ_CREATE_CUDA(dev_alloc(&h->d_pbc, N + 2));
+    MZ_CREATE_CUDA(dev_alloc(&h->d_sqrt, N + 2));
+    MZ_CREATE_CUDA(cudaMemcpy(h->d_pbc, pbc.data(), (N + 2) * 8, cudaMemcpyHostToDevice));
+    MZ_CREATE_CUDA(cudaMemcpy(h->d_sqrt, sq.data(), (N + 2) * 8, cudaMemcpyHostToDevice));
+
+    // ---- sizes
+    h->obs_elems = (int64_t)net->obs_c * net->obs_h * net->obs_w;
+    if (net->kind == MZ_NET_FC) {
+        h->hidden_elems = net->encoding;
+    } else {
+        const int hh = net->downsample ? (net->obs_h + 15) / 16 : net->obs_h;
+        const int hw = net->downsample ? (net->obs_w + 15) / 16 : net->obs_w;
+        h->hidden_elems = (int64_t)net->channels * hh * hw;
+    }
+    // ---- node pool
+    const size_t slots = (size_t)B * (N + 1) * A;
+    NodePool& p = h->pool;
+    MZ_CREATE_CUDA(dev_alloc(&p.visit, slots));
+    MZ_CREATE_CUDA(dev_alloc(&p.vsum, slots));
+    MZ_CREATE_CUDA(dev_alloc(&p.reward, slots));
+    MZ_CREATE_CUDA(dev_alloc(&p.prior, slots));
+    MZ_CREATE_CUDA(dev_alloc(&p.expansion, slots));
+    MZ_CREATE_CUDA(dev_alloc(&p.root_prior, (size_t)B * A));
+    MZ_CREATE_CUDA(dev_alloc(&p.hidden, (size_t)B * (N + 1) * h->hidden_elems));
+    MZ_CREATE_CUDA(dev_alloc(&p.root_visit, B));
+    MZ_CREATE_CUDA(dev_alloc(&p.root_vsum, B));
+    MZ_CREATE_CUDA(dev_alloc(&p.root_reward, B));
+    MZ_CREATE_CUDA(dev_alloc(&p.range, (size_t)B * 2));
+    MZ_CREATE_CUDA(dev_alloc(&p.n_expanded, B));
+    MZ_CREATE_CUDA(dev_alloc(&p.ties, B));
+    MZ_CREATE_CUDA(dev_alloc(&p.max_depth, B));
+    MZ_CREATE_CUDA(dev_alloc(&p.legal, B));
+    MZ_CREATE_CUDA(dev_alloc(&p.path, (size_t)B * (N + 2)));
+    MZ_CREATE_CUDA(dev_alloc(&p.leaf_depth, B));
+    MZ_CREATE_CUDA(dev_alloc(&p.leaf_parent, B));
+    MZ_CREATE_CUDA(dev_alloc(&p.leaf_action, B));
+    MZ_CREATE_CUDA(dev_alloc(&p.leaf_slot, B));
+    MZ_CREATE_CUDA(dev_alloc(&p.net_value, B));
+    MZ_CREATE_CUDA(dev_alloc(&p.net_reward, B));
+    MZ_CREATE_CUDA(dev_alloc(&p.net_policy, (size_t)B * A));
+    MZ_CREATE_CUDA(cudaMemset(p.n_expanded, 0, B * sizeof(int)));
+
+    // ---- IO arenas (sized for max_games)
+    h->in_cap = (size_t)B * (h->obs_elems * 4 + A * 1 + 4 + A * 8 + 4 + 8 + 4) + 16 * 256;
+    h->out_cap = (size_t)B * (A * 4 + 8 + 4 + 4 + 4 + A * 8 + 16) + 16 * 256;
+    MZ_CREATE_CUDA(cudaMalloc(&h->d_in, h->in_cap));
+    MZ_CREATE_CUDA(cudaMalloc(&h->d_out, h->out_cap));
+    MZ_CREATE_CUDA(cudaMallocHost(&h->h_in, h->in_cap));
+    MZ_CREATE_CUDA(cudaMallocHost(&h->h_out, h->out_cap));
+
+    const char* genv = getenv("MZ_FC_GROUP");
+    if (genv) h->fc_group = atoi(genv);
+    else {
+        int g = 8;
+        while (g < A) g <<= 1;
+        if (g < 16) g = 16;
+        h->fc_group = g;
+    }
+    if (h->fc_group < A || (h->fc_group != 4 && h->fc_group != 8 && h->fc_group != 16 && h->fc_group != 32)) {
+        fail(nullptr, MZ_EINVAL, "mz_create: MZ_FC_GROUP must be 4, 8, 16 or 32 and >= action_space");
+        mz_destroy(h);
+        return MZ_EINVAL;
+    }
+    if (net->kind == MZ_NET_RESNET) {
+        std::string e;
+        h->res = resnet_create(*net, B, h->sm_count, &e);
+        if (!h->res) { fail(nullptr, MZ_ECUDA, "resnet_create: " + e); mz_destroy(h); return MZ_ECUDA; }
+    }
+    *out = h;
+    return MZ_OK;
+}
+
+extern "C" int mz_destroy(MzHandle* h) {
+    if (!h) return MZ_OK;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    NodePool& p = h->pool;
+    void* ptrs[] = {p.visit, p.vsum, p.reward, p.prior, p.expansion, p.root_prior, p.hidden, p.root_visit, p.root_vsum,
+                    p.root_reward, p.range, p.n_expanded, p.ties, p.max_depth, p.legal, p.path, p.leaf_depth,
+                    p.leaf_parent, p.leaf_action, p.leaf_slot, p.net_value, p.net_reward, p.net_policy, h->d_pbc, h->d_sqrt, h->d_fc_blob, h->d_in, h->d_out};
+    for (void* q : ptrs) if (q) cudaFree(q);
+    for (auto& kv : h->named) cudaFree(kv.second.first);
+    if (h->h_in) cudaFreeHost(h->h_in);
+    if (h->h_out) cudaFreeHost(h->h_out);
+    if (h->res) resnet_destroy(h->res);
+    if (h->ev0) cudaEventDestroy(h->ev0);
+    if (h->ev1) cudaEventDestroy(h->ev1);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+    return MZ_OK;
+}
+
+extern "C" int64_t mz_hidden_elems(const MzHandle* h) { return h ? h->hidden_elems : 0; }
+extern "C" int64_t mz_obs_elems(const MzHandle* h) { return h ? h->obs_elems : 0; }
+extern "C" int64_t mz_launch_count(const MzHandle* h) { return h ? h->launches : 0; }
+extern "C" double mz_last_search_ms(const MzHandle* h) { return h ? h->last_ms : 0.0; }
+
+// ------------------------------------------------------------------------------------------
+// weights
+// ------------------------------------------------------------------------------------------
+static const MzTensor* find_tensor(const MzTensor* t, int n, const std::string& name) {
+    for (int i = 0; i < n; ++i) if (t[i].name && name == t[i].name) return &t[i];
+    return nullptr;
+}
+
+// Appends one mlp (models.py:630-642) to the blob: per Linear W^T [in][out] then bias.
+static int pack_mlp(MzHandle* h, const MzTensor* t, int n, const std::string& prefix, const std::vector<int>& sizes,
+                    MlpDesc& d, std::vector<float>& blob) {
+    d.n = (int)sizes.size() - 1;
+    for (int l = 0; l < d.n; ++l) {
+        const int in = sizes[l], out = sizes[l + 1];
+        const MzTensor* w = find_tensor(t, n, prefix + "." + std::to_string(2 * l) + ".weight");
+        const MzTensor* b = find_tensor(t, n, prefix + "." + std::to_string(2 * l) + ".bias");
+        if (!w || !b) return fail(h, MZ_EINVAL, "mz_load_weights: missing tensor " + prefix + "." + std::to_string(2 * l));
+        if (w->numel != (int64_t)in * out || b->numel != out)
+            return fail(h, MZ_EINVAL, "mz_load_weights: shape mismatch for " + prefix + "." + std::to_string(2 * l));
+        d.in[l] = in; d.out[l] = out;
+        d.w_off[l] = (int)blob.size();
+        blob.resize(blob.size() + (size_t)in * out);
+        float* dst = blob.data() + d.w_off[l];
+        for (int o = 0; o < out; ++o)
+            for (int i = 0; i < in; ++i) dst[(size_t)i * out + o] = w->data[(size_t)o * in + i];   // torch Linear: [out][in]
+        d.b_off[l] = (int)blob.size();
+        blob.insert(blob.end(), b->data, b->data + out);
+    }
+    return MZ_OK;
+}
+
+static int load_fc_weights(MzHandle* h, const MzTensor* t, int n) {
+    const MzNetDesc& nd = h->net;
+    const int E = nd.encoding, A = nd.action_space, F = 2 * nd.support_size + 1;
+    FcNet fc{};
+    std::vector<float> blob;
+    std::vector<int> sz;
+    int rc;
+    if (mlp_dims(nd.fc_representation, nd.n_fc_representation, (int)h->obs_elems, E, sz)) return fail(h, MZ_EINVAL, "bad layers");
+    if ((rc = pack_mlp(h, t, n, "representation_network.module", sz, fc.rep, blob))) return rc;
+    if (mlp_dims(nd.fc_dynamics, nd.n_fc_dynamics, E + A, E, sz)) return fail(h, MZ_EINVAL, "bad layers");
+    if ((rc = pack_mlp(h, t, n, "dynamics_encoded_state_network.module", sz, fc.dyn, blob))) return rc;
+    if (mlp_dims(nd.fc_reward, nd.n_fc_reward, E, F, sz)) return fail(h, MZ_EINVAL, "bad layers");
+    if ((rc = pack_mlp(h, t, n, "dynamics_reward_network.module", sz, fc.rew, blob))) return rc;
+    if (mlp_dims(nd.fc_value, nd.n_fc_value, E, F, sz)) return fail(h, MZ_EINVAL, "bad layers");
+    if ((rc = pack_mlp(h, t, n, "prediction_value_network.module", sz, fc.val, blob))) return rc;
+    if (mlp_dims(nd.fc_policy, nd.n_fc_policy, E, A, sz)) return fail(h, MZ_EINVAL, "bad layers");
+    if ((rc = pack_mlp(h, t, n, "prediction_policy_network.module", sz, fc.pol, blob))) return rc;
+    fc.blob_floats = (int)blob.size();
+    fc.obs_elems = (int)h->obs_elems; fc.E = E; fc.A = A; fc.S = nd.support_size; fc.F = F;
+    int maxw = E > F ? E : F;
+    if (A > maxw) maxw = A;
+    const MlpDesc* all[] = {&fc.rep, &fc.dyn, &fc.rew, &fc.val, &fc.pol};
+    for (const MlpDesc* d : all) for (int l = 0; l < d->n; ++l) if (d->out[l] > maxw) maxw = d->out[l];
+    fc.maxw = (maxw + 3) & ~3;
+    if (h->d_fc_blob) cudaFree(h->d_fc_blob);
+    h->d_fc_blob = nullptr;
+    MZ_CUDA(h, dev_alloc(&h->d_fc_blob, blob.size()));
+    MZ_CUDA(h, cudaMemcpy(h->d_fc_blob, blob.data(), blob.size() * 4, cudaMemcpyHostToDevice));
+    h->fc = fc;
+    return MZ_OK;
+}
+
+extern "C" int mz_load_weights(MzHandle* h, const MzTensor* tensors, int32_t n) {
+    if (!h || !tensors || n <= 0) return fail(h, MZ_EINVAL, "mz_load_weights: null argument");
+    MZ_CUDA(h, cudaSetDevice(h->device));
+    MZ_CUDA(h, cudaStreamSynchronize(h->stream));
+    int rc;
+    if (h->net.kind == MZ_NET_FC) {
+        rc = load_fc_weights(h, tensors, n);
+    } else {
+        std::string e;
+        rc = resnet_load_weights(h->res, tensors, n, &e);
+        if (rc) return fail(h, rc, "mz_load_weights: " + e);
+    }
+    if (rc == MZ_OK) h->weights_loaded = true;
+    return rc;
+}
+
+// ------------------------------------------------------------------------------------------
+// search
+// ------------------------------------------------------------------------------------------
+struct Arena {
+    size_t off = 0;
+    size_t take(size_t bytes) { size_t o = off; off = (off + bytes + 255) & ~(size_t)255; return o; }
+};
+
+template <typename T>
+static const T* stage_in(MzHandle* h, Arena& ar, const T* src, size_t count) {
+    if (!src) return nullptr;
+    const size_t o = ar.take(count * sizeof(T));
+    memcpy(h->h_in + o, src, count * sizeof(T));
+    return reinterpret_cast<const T*>(h->d_in + o);
+}
+
+struct OutSlot { void* user; size_t off, bytes; };
+template <typename T>
+static T* stage_out(MzHandle* h, Arena& ar, T* user, size_t count, std::vector<OutSlot>& slots) {
+    if (!user) return nullptr;
+    const size_t o = ar.take(count * sizeof(T));
+    slots.push_back({user, o, count * sizeof(T)});
+    return reinterpret_cast<T*>(h->d_out + o);
+}
+
+template <typename T>
+static int debug_in(MzHandle* h, const char* name, const T* src, size_t count, int mem, const T** out) {
+    *out = nullptr;
+    if (!src) return MZ_OK;
+    if (mem == MZ_MEM_DEVICE) { *out = src; return MZ_OK; }
+    void* d = named_buffer(h, name, count * sizeof(T));
+    if (!d) return fail(h, MZ_ENOMEM, std::string("out of device memory for ") + name);
+    MZ_CUDA(h, cudaMemcpyAsync(d, src, count * sizeof(T), cudaMemcpyHostToDevice, h->stream));
+    *out = reinterpret_cast<const T*>(d);
+    return MZ_OK;
+}
+
+struct DebugOut { void* user; void* dev; size_t bytes; };
+template <typename T>
+static int debug_out(MzHandle* h, const char* name, T* user, size_t count, int mem, T** out, std::vector<DebugOut>& outs) {
+    *out = nullptr;
+    if (!user) return MZ_OK;
+    if (mem == MZ_MEM_DEVICE) { *out = user; return MZ_OK; }
+    void* d = named_buffer(h, name, count * sizeof(T));
+    if (!d) return fail(h, MZ_ENOMEM, std::string("out of device memory for ") + name);
+    outs.push_back({user, d, count * sizeof(T)});
+    *out = reinterpret_cast<T*>(d);
+    return MZ_OK;
+}
+
+extern "C" int mz_search(MzHandle* h, const MzSearchIO* io) {
+    if (!h || !io) return fail(h, MZ_EINVAL, "mz_search: null argument");
+    const int n = io->n_games, N = h->search.num_simulations, A = h->net.action_space;
+    if (n < 1 || n > h->search.max_games) return fail(h, MZ_EINVAL, "mz_search: n_games out of range");
+    const bool teacher = io->teacher != nullptr;
+    if (!teacher && !h->weights_loaded) return fail(h, MZ_ESTATE, "mz_search: weights not loaded");
+    if (!teacher && !io->obs) return fail(h, MZ_EINVAL, "mz_search: obs is null");
+    MZ_CUDA(h, cudaSetDevice(h->device));
+
+    SearchCall call{};
+    call.n = n;
+    std::vector<OutSlot> outs;
+    std::vector<DebugOut> dbg_outs;
+    const bool host = io->mem == MZ_MEM_HOST;
+    if (host) {
+        Arena ai, ao;
+        call.obs = teacher ? nullptr : stage_in(h, ai, io->obs, (size_t)n * h->obs_elems);
+        call.legal_mask = stage_in(h, ai, io->legal_mask, (size_t)n * A);
+        call.to_play = stage_in(h, ai, io->to_play, n);
+        call.noise = stage_in(h, ai, io->add_exploration_noise ? io->noise : nullptr, (size_t)n * A);
+        call.first_index = stage_in(h, ai, io->first_index, n);
+        call.game_id = stage_in(h, ai, io->game_id, n);
+        call.move_index = stage_in(h, ai, io->move_index, n);
+        if (ai.off > h->in_cap) return fail(h, MZ_EINVAL, "mz_search: input arena overflow");
+        if (ai.off) MZ_CUDA(h, cudaMemcpyAsync(h->d_in, h->h_in, ai.off, cudaMemcpyHostToDevice, h->stream));
+        call.visit_counts = stage_out(h, ao, io->visit_counts, (size_t)n * A, outs);
+        call.root_value = stage_out(h, ao, io->root_value, n, outs);
+        call.root_predicted_value = stage_out(h, ao, io->root_predicted_value, n, outs);
+        call.max_tree_depth = stage_out(h, ao, io->max_tree_depth, n, outs);
+        call.tie_count = stage_out(h, ao, io->tie_count, n, outs);
+        call.root_priors = stage_out(h, ao, io->root_priors, (size_t)n * A, outs);
+        call.value_range = stage_out(h, ao, io->value_range, (size_t)n * 2, outs);
+        if (ao.off > h->out_cap) return fail(h, MZ_EINVAL, "mz_search: output arena overflow");
+        call.out_bytes = ao.off;
+    } else {
+        call.obs = io->obs; call.legal_mask = io->legal_mask; call.to_play = io->to_play;
+        call.noise = io->add_exploration_noise ? io->noise : nullptr;
+        call.first_index = io->first_index; call.game_id = io->game_id; call.move_index = io->move_index;
+        call.visit_counts = io->visit_counts; call.root_value = io->root_value;
+        call.root_predicted_value = io->root_predicted_value; call.max_tree_depth = io->max_tree_depth;
+        call.tie_count = io->tie_count; call.root_priors = io->root_priors; call.value_range = io->value_range;
+    }
+    call.add_noise = io->add_exploration_noise;
+    if (call.add_noise && !call.noise)
+        return fail(h, MZ_EUNSUPPORTED, "mz_search: device-generated Dirichlet noise is not implemented yet; pass `noise`");
+    int rc;
+    if (teacher) {
+        const MzTeacher& t = *io->teacher;
+        if ((rc = debug_in(h, "t.root_value", t.root_value, n, io->mem, &call.teacher.root_value))) return rc;
+        if ((rc = debug_in(h, "t.root_reward", t.root_reward, n, io->mem, &call.teacher.root_reward))) return rc;
+        if ((rc = debug_in(h, "t.root_priors", t.root_priors, (size_t)n * A, io->mem, &call.teacher.root_priors))) return rc;
+        if ((rc = debug_in(h, "t.value", t.value, (size_t)n * N, io->mem, &call.teacher.value))) return rc;
+        if ((rc = debug_in(h, "t.reward", t.reward, (size_t)n * N, io->mem, &call.teacher.reward))) return rc;
+        if ((rc = debug_in(h, "t.priors", t.priors, (size_t)n * N * A, io->mem, &call.teacher.priors))) return rc;
+        if (!call.teacher.root_value || !call.teacher.root_reward || !call.teacher.root_priors ||
+            (N > 0 && (!call.teacher.value || !call.teacher.reward || !call.teacher.priors)))
+            return fail(h, MZ_EINVAL, "mz_search: incomplete teacher table");
+    }
+    if (io->trace) {
+        const MzTrace& t = *io->trace;
+        const int D = t.max_depth;
+        call.trace.max_depth = D;
+        if ((rc = debug_out(h, "r.depth", t.depth, (size_t)n * N, io->mem, &call.trace.depth, dbg_outs))) return rc;
+        if ((rc = debug_out(h, "r.actions", t.actions, (size_t)n * N * D, io->mem, &call.trace.actions, dbg_outs))) return rc;
+        if ((rc = debug_out(h, "r.value", t.value, (size_t)n * N, io->mem, &call.trace.value, dbg_outs))) return rc;
+        if ((rc = debug_out(h, "r.reward", t.reward, (size_t)n * N, io->mem, &call.trace.reward, dbg_outs))) return rc;
+        if ((rc = debug_out(h, "r.priors", t.priors, (size_t)n * N * A, io->mem, &call.trace.priors, dbg_outs))) return rc;
+        if ((rc = debug_out(h, "r.root_priors_raw", t.root_priors_raw, (size_t)n * A, io->mem, &call.trace.root_priors_raw, dbg_outs))) return rc;
+        if ((rc = debug_out(h, "r.root_reward", t.root_reward, n, io->mem, &call.trace.root_reward, dbg_outs))) return rc;
+        if (call.trace.depth && (!call.trace.actions || !call.trace.value || !call.trace.reward || !call.trace.priors))
+            return fail(h, MZ_EINVAL, "mz_search: trace needs depth, actions, value, reward and priors together");
+    }
+    call.keep_tree = (io->flags & MZ_FLAG_KEEP_TREE) != 0;
+
+    MZ_CUDA(h, cudaEventRecord(h->ev0, h->stream));
+    const bool fused = (h->net.kind == MZ_NET_FC || teacher) && !(io->flags & MZ_FLAG_STEPWISE);
+    if (fused) {
+        FcSearchArgs a{};
+        a.n_games = n; a.N = N; a.A = A; a.P = h->search.num_players;
+        a.discount = h->search.discount; a.noise_frac = h->search.root_exploration_fraction; a.seed = h->search.seed;
+        a.pbc = h->d_pbc; a.sqrtn = h->d_sqrt;
+        a.net = h->fc; a.blob = h->d_fc_blob;
+        if (teacher) { a.net.E = 1; a.net.maxw = 4; a.net.blob_floats = 0; a.net.A = A; }
+        a.obs = call.obs; a.legal_mask = call.legal_mask; a.to_play = call.to_play; a.add_noise = call.add_noise;
+        a.noise = call.noise; a.first_index = call.first_index; a.game_id = call.game_id; a.move_index = call.move_index;
+        a.visit_counts = call.visit_counts; a.root_value = call.root_value; a.root_predicted_value = call.root_predicted_value;
+        a.max_tree_depth = call.max_tree_depth; a.tie_count = call.tie_count; a.root_priors = call.root_priors;
+        a.value_range = call.value_range; a.teacher = call.teacher; a.trace = call.trace;
+        if (call.keep_tree) a.pool = h->pool;
+        FcLaunchInfo info{};
+        cudaError_t e = launch_fc_search(a, h->fc_group, teacher, h->sm_count, h->smem_cap, h->stream, &info);
+        if (e == cudaErrorInvalidConfiguration) {
+            // the tree does not fit in shared memory next to the weights: use the HBM node pool
+            (void)cudaGetLastError();
+            rc = run_stepwise_search(h->net, h->search, h->pool, h->d_pbc, h->d_sqrt, h->fc, h->d_fc_blob, h->res, call,
+                                     h->sm_count, h->stream, &h->launches, &h->err);
+            if (rc) return rc;
+        } else if (e != cudaSuccess) {
+            return fail(h, MZ_ECUDA, std::string("fc_search launch: ") + cudaGetErrorString(e));
+        } else {
+            h->launches += 1;
+        }
+    } else {
+        rc = run_stepwise_search(h->net, h->search, h->pool, h->d_pbc, h->d_sqrt, h->fc, h->d_fc_blob, h->res, call,
+                                 h->sm_count, h->stream, &h->launches, &h->err);
+        if (rc) return rc;
+    }
+    MZ_CUDA(h, cudaEventRecord(h->ev1, h->stream));
+    if (host && call.out_bytes)
+        MZ_CUDA(h, cudaMemcpyAsync(h->h_out, h->d_out, call.out_bytes, cudaMemcpyDeviceToHost, h->stream));
+    for (const DebugOut& d : dbg_outs)
+        MZ_CUDA(h, cudaMemcpyAsync(d.user, d.dev, d.bytes, cudaMemcpyDeviceToHost, h->stream));
+    MZ_CUDA(h, cudaStreamSynchronize(h->stream));
+    for (const OutSlot& s : outs) memcpy(s.user, h->h_out + s.off, s.bytes);
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, h->ev0, h->ev1) == cudaSuccess) h->last_ms = ms;
+    return MZ_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// network entry points
+// ------------------------------------------------------------------------------------------
+static int run_inference(MzHandle* h, int n, int mem, const float* in, const int32_t* action, const MzInferenceOut* out,
+                         bool recurrent) {
+    if (!h || !in || !out) return fail(h, MZ_EINVAL, "inference: null argument");
+    if (!h->weights_loaded) return fail(h, MZ_ESTATE, "inference: weights not loaded");
+    if (n < 1) return fail(h, MZ_EINVAL, "inference: n < 1");
+    if (recurrent && !action) return fail(h, MZ_EINVAL, "recurrent_inference: action is null");
+    MZ_CUDA(h, cudaSetDevice(h->device));
+    const int A = h->net.action_space, F = 2 * h->net.support_size + 1;
+    const size_t in_elems = recurrent ? (size_t)h->hidden_elems : (size_t)h->obs_elems;
+    std::vector<DebugOut> outs;
+    InferCall c{};
+    c.n = n; c.recurrent = recurrent;
+    int rc;
+    if ((rc = debug_in(h, "i.in", in, (size_t)n * in_elems, mem, &c.in))) return rc;
+    if ((rc = debug_in(h, "i.action", action, n, mem, &c.action))) return rc;
+    if ((rc = debug_out(h, "i.vl", out->value_logits, (size_t)n * F, mem, &c.value_logits, outs))) return rc;
+    if ((rc = debug_out(h, "i.rl", out->reward_logits, (size_t)n * F, mem, &c.reward_logits, outs))) return rc;
+    if ((rc = debug_out(h, "i.pl", out->policy_logits, (size_t)n * A, mem, &c.policy_logits, outs))) return rc;
+    if ((rc = debug_out(h, "i.h", out->hidden, (size_t)n * h->hidden_elems, mem, &c.hidden, outs))) return rc;
+    if ((rc = debug_out(h, "i.v", out->value, n, mem, &c.value, outs))) return rc;
+    if ((rc = debug_out(h, "i.r", out->reward, n, mem, &c.reward, outs))) return rc;
+    if (h->net.kind == MZ_NET_FC) {
+        FcInferArgs a{};
+        a.n = n; a.recurrent = recurrent; a.net = h->fc; a.blob = h->d_fc_blob; a.in = c.in; a.action = c.action;
+        a.value_logits = c.value_logits; a.reward_logits = c.reward_logits; a.policy_logits = c.policy_logits;
+        a.hidden = c.hidden; a.value = c.value; a.reward = c.reward;
+        cudaError_t e = launch_fc_inference(a, h->sm_count, h->stream);
+        if (e != cudaSuccess) return fail(h, MZ_ECUDA, std::string("fc_inference launch: ") + cudaGetErrorString(e));
+        h->launches += 1;
+    } else {
+        std::string e;
+        rc = resnet_inference(h->res, c, h->stream, &h->launches, &e);
+        if (rc) return fail(h, rc, "resnet_inference: " + e);
+    }
+    for (const DebugOut& d : outs)
+        MZ_CUDA(h, cudaMemcpyAsync(d.user, d.dev, d.bytes, cudaMemcpyDeviceToHost, h->stream));
+    MZ_CUDA(h, cudaStreamSynchronize(h->stream));
+    return MZ_OK;
+}
+
+extern "C" int mz_initial_inference(MzHandle* h, int32_t n, int32_t mem, const float* obs, const MzInferenceOut* out) {
+    return run_inference(h, n, mem, obs, nullptr, out, false);
+}
+
+extern "C" int mz_recurrent_inference(MzHandle* h, int32_t n, int32_t mem, const float* hidden, const int32_t* action,
+                                      const MzInferenceOut* out) {
+    return run_inference(h, n, mem, hidden, action, out, true);
+}
+
+// ------------------------------------------------------------------------------------------
+// tree export
+// ------------------------------------------------------------------------------------------
+extern "C" int mz_export_tree(MzHandle* h, int32_t game, MzTreeExport* out) {
+    if (!h || !out) return fail(h, MZ_EINVAL, "mz_export_tree: null argument");
+    if (game < 0 || game >= h->search.max_games) return fail(h, MZ_EINVAL, "mz_export_tree: game out of range");
+    MZ_CUDA(h, cudaSetDevice(h->device));
+    MZ_CUDA(h, cudaStreamSynchronize(h->stream));
+    const int N = h->search.num_simulations, A = h->net.action_space;
+    const size_t S = (size_t)(N + 1) * A, base = (size_t)game * S;
+    const NodePool& p = h->pool;
+    int nexp = 0;
+    MZ_CUDA(h, cudaMemcpy(&nexp, p.n_expanded + game, 4, cudaMemcpyDeviceToHost));
+    if (nexp < 1) return fail(h, MZ_ESTATE, "mz_export_tree: no tree kept for this game (use MZ_FLAG_KEEP_TREE)");
+    out->n_expansions = nexp;
+    const size_t used = (size_t)nexp * A;
+    if (out->child_visit) MZ_CUDA(h, cudaMemcpy(out->child_visit, p.visit + base, used * 4, cudaMemcpyDeviceToHost));
+    if (out->child_value_sum) MZ_CUDA(h, cudaMemcpy(out->child_value_sum, p.vsum + base, used * 8, cudaMemcpyDeviceToHost));
+    if (out->child_reward) MZ_CUDA(h, cudaMemcpy(out->child_reward, p.reward + base, used * 4, cudaMemcpyDeviceToHost));
+    if (out->child_expansion) MZ_CUDA(h, cudaMemcpy(out->child_expansion, p.expansion + base, used * 4, cudaMemcpyDeviceToHost));
+    if (out->child_prior) {
+        std::vector<float> pf(used);
+        std::vector<double> rp(A);
+        MZ_CUDA(h, cudaMemcpy(pf.data(), p.prior + base, used * 4, cudaMemcpyDeviceToHost));
+        MZ_CUDA(h, cudaMemcpy(rp.data(), p.root_prior + (size_t)game * A, A * 8, cudaMemcpyDeviceToHost));
+        for (size_t i = 0; i < used; ++i) out->child_prior[i] = (i < (size_t)A) ? rp[i] : (double)pf[i];
+    }
+    if (out->hidden)
+        MZ_CUDA(h, cudaMemcpy(out->hidden, p.hidden + (size_t)game * (N + 1) * h->hidden_elems,
+                              (size_t)nexp * h->hidden_elems * 4, cudaMemcpyDeviceToHost));
+    MZ_CUDA(h, cudaMemcpy(&out->root_visit, p.root_visit + game, 4, cudaMemcpyDeviceToHost));
+    MZ_CUDA(h, cudaMemcpy(&out->root_value_sum, p.root_vsum + game, 8, cudaMemcpyDeviceToHost));
+    return MZ_OK;
+}

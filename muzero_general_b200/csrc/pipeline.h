@@ -1,0 +1,86 @@
+// Step-wise search pipeline over the HBM node pool + the residual-network interface.
+#pragma once
+#include <string>
+
+#include "kernels.h"
+
+namespace mz {
+
+// One mz_search call after host staging: every pointer is a device pointer.
+struct SearchCall {
+    int n;
+    const float* obs;
+    const uint8_t* legal_mask;
+    const int32_t* to_play;
+    int add_noise;
+    const double* noise;
+    const int32_t* first_index;
+    const int64_t* game_id;
+    const int32_t* move_index;
+    int32_t* visit_counts;
+    double* root_value;
+    float* root_predicted_value;
+    int32_t* max_tree_depth;
+    int32_t* tie_count;
+    double* root_priors;
+    double* value_range;
+    DevTeacher teacher;
+    DevTrace trace;
+    bool keep_tree;
+    size_t out_bytes;
+};
+
+// One batched network call. Plain mode: sample g reads in[g*in_elems...] and writes hidden[g*H...].
+// Pool mode (gather_parent != nullptr): sample g reads pool_hidden[(g*pool_stride + gather_parent[g])*H...]
+// and writes its new state to pool_hidden[(g*pool_stride + out_slot)*H...].
+struct InferCall {
+    int n, recurrent;
+    const float* in;
+    const int32_t* action;
+    const int32_t* gather_parent;
+    float* pool_hidden;
+    int pool_stride, out_slot;
+    float *value_logits, *reward_logits, *policy_logits, *hidden, *value, *reward;
+};
+
+// One launch of the step-wise tree kernel (tree_kernels.cu).
+struct TreeStepArgs {
+    int n, N, A, P;
+    int sim;                       // simulation selected by this launch (do_select); do_update handles sim-1
+    int do_root, do_update, do_select, do_final;
+    double discount, noise_frac;
+    uint64_t seed;
+    const double* pbc;
+    const double* sqrtn;
+    NodePool pool;
+    const uint8_t* legal_mask;
+    const double* noise;
+    int add_noise;
+    const int32_t* first_index;
+    const int64_t* game_id;
+    const int32_t* move_index;
+    // outputs of the network (or teacher table) for the node being expanded
+    const float* net_value;        // [g*value_stride]
+    const float* net_reward;       // [g*value_stride]; nullptr at the root = log(one-hot centre)
+    const float* net_policy;       // [g*policy_stride + k] logits, or priors if policy_is_prior
+    int value_stride, policy_stride, policy_is_prior;
+    // final outputs
+    int32_t* visit_counts; double* root_value; float* root_predicted_value; int32_t* max_tree_depth;
+    int32_t* tie_count; double* root_priors; double* value_range;
+    DevTrace trace;
+};
+cudaError_t launch_tree_step(const TreeStepArgs& a, cudaStream_t stream);
+
+struct ResNetDevice;
+ResNetDevice* resnet_create(const MzNetDesc& net, int max_batch, int sm_count, std::string* err);
+void resnet_destroy(ResNetDevice* r);
+int resnet_load_weights(ResNetDevice* r, const MzTensor* tensors, int n, std::string* err);
+int resnet_inference(ResNetDevice* r, const InferCall& c, cudaStream_t stream, int64_t* launches, std::string* err);
+
+cudaError_t launch_fc_inference_pool(const FcNet& net, const float* blob, const InferCall& c, int sm_count, cudaStream_t stream);
+
+int run_stepwise_search(const MzNetDesc& net, const MzSearchDesc& search, const NodePool& pool, const double* d_pbc,
+                        const double* d_sqrt, const FcNet& fc, const float* d_fc_blob, ResNetDevice* res,
+                        const SearchCall& call, int sm_count, cudaStream_t stream, int64_t* launches, std::string* err);
+
+}  // namespace mz

@@ -1,0 +1,255 @@
+// Tree arithmetic of one game, executed by a group of G lanes.
+//
+// Restates, for the device, the reference's per-simulation tree work:
+//   select_child / ucb_score   self_play.py:363-404
+//   Node.expand                self_play.py:451-465
+//   add_exploration_noise      self_play.py:467-476
+//   backpropagate              self_play.py:406-430
+//   MinMaxStats                self_play.py:553-570
+// All statistics are IEEE fp64 evaluated in the reference's operation order with explicit
+// round-to-nearest intrinsics (never contracted into FMAs), so that visit counts, paths and
+// root values are bit-identical to the Python implementation when the network outputs are
+// the same (teacher / student forcing, tests/test_tree_parity_gpu.py).
+//
+// Storage (same layout in shared memory for the fused FC kernel and in the HBM node pool):
+// expansion e (0 = root, e = i+1 for simulation i) owns the child slots [e*A, e*A+A);
+// child k of a non-root expansion is action k; root children are indexed by action id and
+// masked by the legal bitmask.  Per slot: visit i32, value_sum f64, reward f32, prior f32,
+// expansion id i32 (-1 = leaf).  Root priors after noise are kept in fp64 separately
+// (they are not fp32-representable, self_play.py:476).
+#pragma once
+#include "common.cuh"
+
+namespace mz {
+
+struct TreeConst {
+    int A;                 // |action_space|
+    int N;                 // num_simulations
+    int P;                 // number of players (1 or 2)
+    double discount;
+    double noise_frac;     // root_exploration_fraction
+    uint64_t seed;
+    const double* pbc;     // [N+2]  log((n+base+1)/base)+init
+    const double* sqrtn;   // [N+2]  sqrt(n)
+};
+
+// Pointers to ONE game's tree (shared or global memory).
+struct GameTree {
+    int* visit;            // [(N+1)*A]
+    double* vsum;          // [(N+1)*A]
+    float* reward;         // [(N+1)*A]
+    float* prior;          // [(N+1)*A]
+    int* expansion;        // [(N+1)*A]
+    double* root_prior;    // [A]
+    int* path;             // [N+2] slots of the current simulation, path[0] = -1 (root)
+    // scalars of the game
+    int root_visit;
+    double root_vsum;
+    float root_reward;
+    double lo, hi;         // MinMaxStats
+    unsigned legal;        // bitmask of legal root actions
+    int n_expanded;        // expansions so far (>= 1 after the root expansion)
+    int ties;              // exact ties after the first simulation
+};
+
+struct Leaf {
+    int depth;             // number of select_child calls
+    int parent_exp;        // expansion id of the leaf's parent (its hidden state feeds dynamics)
+    int action;            // action leading to the leaf
+    int slot;              // child slot of the leaf
+};
+
+MZ_DEVINL double value_range_normalize(double v, double lo, double hi) {
+    // MinMaxStats.normalize, self_play.py:566-570
+    if (hi > lo) return __ddiv_rn(__dsub_rn(v, lo), __dsub_rn(hi, lo));
+    return v;
+}
+
+// n-th (0-based) set bit of m
+MZ_DEVINL int nth_set_bit(unsigned m, int n) { return (int)__fns(m, 0, n + 1); }
+
+// ------------------------------------------------------------------------------------------
+// Root: fp32 softmax over the legal logits, optional Dirichlet mixing.  (self_play.py:460-476)
+// `logit` is this lane's policy logit (lane k <-> action k); returns this lane's fp32 prior.
+// ------------------------------------------------------------------------------------------
+template <int G>
+MZ_DEVINL float group_softmax_masked(float logit, bool valid) {
+    const float m = group_max_f32<G>(valid ? logit : -INFINITY);
+    const float e = valid ? expf(logit - m) : 0.0f;
+    const float s = group_sum_f32<G>(e);
+    return __fdiv_rn(e, s);
+}
+
+template <int G>
+MZ_DEVINL void tree_init_root(const TreeConst& c, GameTree& t, float prior_f32, float root_reward,
+                              const double* noise /* [A] by action or nullptr */) {
+    const int k = LaneGroup<G>::lane();
+    if (k < c.A) {
+        const bool legal = (t.legal >> k) & 1u;
+        double p = (double)prior_f32;
+        if (legal && noise != nullptr) {
+            // prior * (1 - frac) + n * frac       (self_play.py:476)
+            p = __dadd_rn(__dmul_rn(p, __dsub_rn(1.0, c.noise_frac)), __dmul_rn(noise[k], c.noise_frac));
+        }
+        t.root_prior[k] = legal ? p : 0.0;
+        t.visit[k] = 0;
+        t.vsum[k] = 0.0;
+        t.reward[k] = 0.0f;
+        t.prior[k] = legal ? prior_f32 : 0.0f;
+        t.expansion[k] = -1;
+    }
+    t.root_visit = 0;
+    t.root_vsum = 0.0;
+    t.root_reward = root_reward;
+    t.lo = INFINITY;
+    t.hi = -INFINITY;
+    t.n_expanded = 1;
+    t.ties = 0;
+    LaneGroup<G>::sync();
+}
+
+// ------------------------------------------------------------------------------------------
+// Selection: descend from the root until an unexpanded child is reached.
+// first_index >= 0: host-supplied pick (index into the tied list) for the all-way tie of the
+// first simulation (self_play.py:371-377 with sqrt(0) = 0).
+// ------------------------------------------------------------------------------------------
+template <int G>
+MZ_DEVINL Leaf tree_select(const TreeConst& c, GameTree& t, int sim, int64_t game_id, int move, int first_index) {
+    const int k = LaneGroup<G>::lane();
+    const int width = pow2_ceil(c.A);
+    int e = 0;
+    int n_parent = t.root_visit;
+    int depth = 0;
+    Leaf leaf;
+    if (k == 0) t.path[0] = -1;
+    while (true) {
+        const int base = e * c.A;
+        const bool valid = (k < c.A) && (e != 0 || ((t.legal >> k) & 1u));
+        double score = -INFINITY;
+        if (valid) {
+            const int nc = t.visit[base + k];
+            const double pr = (e == 0) ? t.root_prior[k] : (double)t.prior[base + k];
+            // pb_c = (log(...) + init) * (sqrt(n_p) / (n_c + 1))     self_play.py:384-390
+            const double q = __ddiv_rn(c.sqrtn[n_parent], (double)(nc + 1));
+            const double pbc = __dmul_rn(c.pbc[n_parent], q);
+            score = __dmul_rn(pbc, pr);
+            if (nc > 0) {
+                const double mean = __ddiv_rn(t.vsum[base + k], (double)nc);
+                const double signed_mean = (c.P == 1) ? mean : -mean;
+                double v = __dadd_rn((double)t.reward[base + k], __dmul_rn(c.discount, signed_mean));
+                v = value_range_normalize(v, t.lo, t.hi);
+                score = __dadd_rn(score, v);
+            } else {
+                score = __dadd_rn(score, 0.0);     // prior_score + 0
+            }
+        }
+        const double best = group_max_f64<G>(score, width > G ? G : width);
+        const unsigned tied = LaneGroup<G>::ballot(valid && score == best);
+        const int n_tied = __popc(tied);
+        int pick;
+        if (n_tied == 1) {
+            pick = __ffs(tied) - 1;
+        } else {
+            int idx;
+            if (sim == 0 && depth == 0 && first_index >= 0) {
+                idx = first_index < n_tied ? first_index : n_tied - 1;
+            } else {
+                idx = philox_tie_index(c.seed, game_id, move, sim, depth, n_tied);
+                if (!(sim == 0 && depth == 0)) t.ties += 1;
+            }
+            pick = nth_set_bit(tied, idx);
+        }
+        const int slot = base + pick;
+        depth += 1;
+        if (k == 0) t.path[depth] = slot;
+        const int child_exp = t.expansion[slot];
+        if (child_exp < 0) {
+            leaf.depth = depth;
+            leaf.parent_exp = e;
+            leaf.action = pick;
+            leaf.slot = slot;
+            break;
+        }
+        n_parent = t.visit[slot];
+        e = child_exp;
+    }
+    LaneGroup<G>::sync();
+    return leaf;
+}
+
+// ------------------------------------------------------------------------------------------
+// Expansion of the selected leaf with the network outputs (self_play.py:345-351, 451-465).
+// prior_f32: this lane's fp32 softmax prior (lane k <-> action k).
+// ------------------------------------------------------------------------------------------
+template <int G>
+MZ_DEVINL int tree_expand(const TreeConst& c, GameTree& t, const Leaf& leaf, float reward, float prior_f32) {
+    const int k = LaneGroup<G>::lane();
+    const int e = t.n_expanded;
+    if (k == 0) {
+        t.expansion[leaf.slot] = e;
+        t.reward[leaf.slot] = reward;
+    }
+    if (k < c.A) {
+        const int s = e * c.A + k;
+        t.visit[s] = 0;
+        t.vsum[s] = 0.0;
+        t.reward[s] = 0.0f;
+        t.prior[s] = prior_f32;
+        t.expansion[s] = -1;
+    }
+    t.n_expanded = e + 1;
+    LaneGroup<G>::sync();
+    return e;
+}
+
+// ------------------------------------------------------------------------------------------
+// Backup along path[0..depth] (self_play.py:406-430).  The discounted value recurrence is a
+// serial chain (2 fp64 ops per level, run redundantly by every lane); the per-node updates
+// (value_sum, visit, running min/max) are independent and spread over the lanes.
+// ------------------------------------------------------------------------------------------
+template <int G>
+MZ_DEVINL void tree_backup(const TreeConst& c, GameTree& t, const Leaf& leaf, float leaf_value) {
+    const int k = LaneGroup<G>::lane();
+    const int L = leaf.depth;                         // path indices 0..L
+    double lo = INFINITY, hi = -INFINITY;
+    double v = (double)leaf_value;                    // value seen by node j, starting at j = L
+    double root_vsum = t.root_vsum;
+    for (int j = L; j >= 0; --j) {
+        const int slot = t.path[j];                   // -1 = root (shared-memory broadcast read)
+        const double r = (j == 0) ? (double)t.root_reward : (double)t.reward[slot];
+        // node.to_play == to_play  <=>  (L - j) even (players alternate every level)
+        const bool same = (c.P == 1) || (((L - j) & 1) == 0);
+        if ((j % G) == k) {
+            const double add = same ? v : -v;
+            double q;
+            if (j == 0) {
+                root_vsum = __dadd_rn(t.root_vsum, add);
+                q = __ddiv_rn(root_vsum, (double)(t.root_visit + 1));
+            } else {
+                const double s = __dadd_rn(t.vsum[slot], add);
+                const int n = t.visit[slot] + 1;
+                t.vsum[slot] = s;
+                t.visit[slot] = n;
+                q = __ddiv_rn(s, (double)n);
+            }
+            const double m = __dadd_rn(r, __dmul_rn(c.discount, (c.P == 1) ? q : -q));
+            lo = fmin(lo, m);
+            hi = fmax(hi, m);
+        }
+        // value = (same ? -reward : reward) + discount * value     (P == 2)
+        // value = reward + discount * value                        (P == 1)
+        const double rr = (c.P == 1) ? r : (same ? -r : r);
+        v = __dadd_rn(rr, __dmul_rn(c.discount, v));
+    }
+    // lane 0 always owns j = 0 (the root)
+    root_vsum = shfl_f64(LaneGroup<G>::mask(), root_vsum, 0, G);
+    lo = group_min_f64<G>(lo, G);
+    hi = group_max_f64<G>(hi, G);
+    t.root_vsum = root_vsum;
+    t.root_visit += 1;
+    t.lo = fmin(t.lo, lo);
+    t.hi = fmax(t.hi, hi);
+    LaneGroup<G>::sync();
+}
+
+}  // namespace mz

@@ -1,0 +1,295 @@
+"""Python face of the C ABI: one ``SearchEngine`` per GPU process.
+
+``SearchEngine`` owns an ``MzHandle`` and exposes, for a whole batch of games,
+what the reference does for one game at a time:
+
+* ``load_weights(state_dict)``          <- ``model.set_weights`` (models.py:72-73)
+* ``search(...)``                       <- ``MCTS(config).run`` (self_play.py:260-361)
+* ``initial_inference / recurrent_inference``  (models.py:172-195, 601-623)
+* ``export_tree(game)``                 <- walking ``Node.children`` (self_play.py:433-449)
+
+All numerical work happens in libmzb200.so; this file only marshals buffers.  Inputs may be
+numpy arrays (host memory, copies are part of the call) or CUDA torch tensors (device memory).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from dataclasses import dataclass
+from typing import Optional
+
+import numpy
+
+from . import _lib
+from .netspec import FC, NetSpec, netspec_from_config, weights_spec
+
+
+def _is_torch(x):
+    return x is not None and type(x).__module__.startswith("torch")
+
+
+def _fill_layers(desc, prefix, layers):
+    if len(layers) > _lib.MZ_MAX_LAYERS:
+        raise ValueError(f"at most {_lib.MZ_MAX_LAYERS} hidden layers per head are supported")
+    setattr(desc, "n_" + prefix, len(layers))
+    arr = getattr(desc, prefix)
+    for i, v in enumerate(layers):
+        arr[i] = int(v)
+
+
+def net_desc(spec: NetSpec) -> _lib.MzNetDesc:
+    d = _lib.MzNetDesc()
+    d.kind = spec.kind
+    d.obs_c, d.obs_h, d.obs_w = spec.in_channels, spec.obs_shape[1], spec.obs_shape[2]
+    d.action_space = spec.action_space
+    d.support_size = spec.support_size
+    d.encoding = spec.encoding
+    _fill_layers(d, "fc_representation", spec.fc_representation)
+    _fill_layers(d, "fc_dynamics", spec.fc_dynamics)
+    _fill_layers(d, "fc_reward", spec.fc_reward)
+    _fill_layers(d, "fc_value", spec.fc_value)
+    _fill_layers(d, "fc_policy", spec.fc_policy)
+    d.blocks, d.channels = spec.blocks, spec.channels
+    d.reduced_reward, d.reduced_value, d.reduced_policy = spec.reduced_reward, spec.reduced_value, spec.reduced_policy
+    _fill_layers(d, "res_fc_reward", spec.res_fc_reward)
+    _fill_layers(d, "res_fc_value", spec.res_fc_value)
+    _fill_layers(d, "res_fc_policy", spec.res_fc_policy)
+    d.downsample = spec.downsample
+    return d
+
+
+@dataclass
+class SearchOutput:
+    visit_counts: numpy.ndarray          # [n, A] int32
+    root_value: numpy.ndarray            # [n] float64
+    root_predicted_value: numpy.ndarray  # [n] float32
+    max_tree_depth: numpy.ndarray        # [n] int32
+    tie_count: numpy.ndarray             # [n] int32
+    root_priors: numpy.ndarray           # [n, A] float64
+    value_range: numpy.ndarray           # [n, 2] float64
+    trace: Optional[dict] = None
+    device_ms: float = 0.0
+
+
+class SearchEngine:
+    def __init__(self, config, max_games: int = 1, device: int = 0, seed: Optional[int] = None,
+                 num_simulations: Optional[int] = None):
+        self.lib = _lib.load_library()
+        self.config = config
+        self.spec = netspec_from_config(config)
+        if list(config.action_space) != list(range(len(config.action_space))):
+            raise ValueError("action_space must be list(range(n)) (every reference game file is)")
+        if list(config.players) != list(range(len(config.players))):
+            raise ValueError("players must be list(range(n))")
+        self.A = self.spec.action_space
+        self.N = int(config.num_simulations if num_simulations is None else num_simulations)
+        self.max_games = int(max_games)
+        self.device = int(device)
+        s = _lib.MzSearchDesc()
+        s.max_games = self.max_games
+        s.num_simulations = self.N
+        s.num_players = len(config.players)
+        s.discount = float(config.discount)
+        s.pb_c_base = float(config.pb_c_base)
+        s.pb_c_init = float(config.pb_c_init)
+        s.root_dirichlet_alpha = float(config.root_dirichlet_alpha)
+        s.root_exploration_fraction = float(config.root_exploration_fraction)
+        s.seed = int(config.seed if seed is None else seed) & 0xFFFFFFFFFFFFFFFF
+        # math.log / math.sqrt exactly as the reference evaluates them (self_play.py:385-390)
+        n = self.N + 2
+        self._pbc = (C.c_double * n)(*[math.log((i + config.pb_c_base + 1) / config.pb_c_base) + config.pb_c_init
+                                       for i in range(n)])
+        self._sqrt = (C.c_double * n)(*[math.sqrt(i) for i in range(n)])
+        s.pb_c_table = C.cast(self._pbc, C.POINTER(C.c_double))
+        s.sqrt_table = C.cast(self._sqrt, C.POINTER(C.c_double))
+        self._net_desc = net_desc(self.spec)
+        handle = C.c_void_p()
+        rc = self.lib.mz_create(C.byref(self._net_desc), C.byref(s), self.device, C.byref(handle))
+        if rc != 0:
+            msg = self.lib.mz_last_error(None).decode()
+            if rc == _lib.MZ_EUNSUPPORTED:
+                raise NotImplementedError(msg)
+            raise _lib.MzError(rc, msg)
+        self._h = handle
+        self.hidden_elems = int(self.lib.mz_hidden_elems(self._h))
+        self.obs_elems = int(self.lib.mz_obs_elems(self._h))
+
+    # ------------------------------------------------------------------ plumbing
+    def close(self):
+        if getattr(self, "_h", None):
+            self.lib.mz_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != 0:
+            raise _lib.MzError(rc, self.lib.mz_last_error(self._h).decode())
+
+    @property
+    def launch_count(self):
+        return int(self.lib.mz_launch_count(self._h))
+
+    @property
+    def last_search_ms(self):
+        return float(self.lib.mz_last_search_ms(self._h))
+
+    @staticmethod
+    def _ptr(x, dtype, keep):
+        """Pointer of a numpy array (made contiguous, right dtype) or of a CUDA torch tensor."""
+        if x is None:
+            return None
+        if _is_torch(x):
+            import torch
+            want = {numpy.float32: torch.float32, numpy.float64: torch.float64, numpy.int32: torch.int32,
+                    numpy.int64: torch.int64, numpy.uint8: torch.uint8}[dtype]
+            if x.dtype != want or not x.is_contiguous():
+                x = x.to(want).contiguous()
+            keep.append(x)
+            return x.data_ptr()
+        a = numpy.ascontiguousarray(x, dtype=dtype)
+        keep.append(a)
+        return a.ctypes.data
+
+    # ------------------------------------------------------------------ weights
+    def load_weights(self, state_dict):
+        """Accepts the reference ``state_dict`` (torch tensors or numpy arrays, CPU)."""
+        tensors, keep = [], []
+        for key, shape in weights_spec(self.spec):
+            if key.endswith("num_batches_tracked"):
+                continue
+            if key not in state_dict:
+                raise KeyError(f"state_dict is missing {key}")
+            v = state_dict[key]
+            if _is_torch(v):
+                v = v.detach().cpu().numpy()
+            a = numpy.ascontiguousarray(v, dtype=numpy.float32)
+            if tuple(a.shape) != tuple(shape):
+                raise ValueError(f"{key}: expected shape {tuple(shape)}, got {tuple(a.shape)}")
+            keep.append(a)
+            tensors.append((key.encode(), a))
+        arr = (_lib.MzTensor * len(tensors))()
+        for i, (name, a) in enumerate(tensors):
+            arr[i].name = name
+            arr[i].data = a.ctypes.data
+            arr[i].numel = a.size
+        self._check(self.lib.mz_load_weights(self._h, arr, len(tensors)))
+
+    # ------------------------------------------------------------------ search
+    def search(self, obs=None, legal_mask=None, to_play=None, add_exploration_noise=False, noise=None,
+               first_index=None, game_id=None, move_index=None, teacher=None, trace=False, trace_depth=None,
+               keep_tree=False, stepwise=False, n_games=None) -> SearchOutput:
+        A, N = self.A, self.N
+        keep = []
+        if n_games is None:
+            src = obs if obs is not None else (teacher["root_value"] if teacher else legal_mask)
+            n_games = int(src.shape[0])
+        n = n_games
+        device_mem = _is_torch(obs)
+        io = _lib.MzSearchIO()
+        io.n_games = n
+        io.mem = _lib.MZ_MEM_DEVICE if device_mem else _lib.MZ_MEM_HOST
+        if obs is not None:
+            if not device_mem:
+                obs = numpy.asarray(obs, dtype=numpy.float32).reshape(n, -1)
+                if obs.shape[1] != self.obs_elems:
+                    raise ValueError(f"observation has {obs.shape[1]} elements, expected {self.obs_elems}")
+            io.obs = self._ptr(obs, numpy.float32, keep)
+        io.legal_mask = self._ptr(legal_mask, numpy.uint8, keep)
+        io.to_play = self._ptr(to_play, numpy.int32, keep)
+        io.add_exploration_noise = int(bool(add_exploration_noise))
+        io.flags = (_lib.MZ_FLAG_KEEP_TREE if keep_tree else 0) | (_lib.MZ_FLAG_STEPWISE if stepwise else 0)
+        io.noise = self._ptr(noise, numpy.float64, keep)
+        io.first_index = self._ptr(first_index, numpy.int32, keep)
+        io.game_id = self._ptr(game_id, numpy.int64, keep)
+        io.move_index = self._ptr(move_index, numpy.int32, keep)
+
+        if device_mem:
+            import torch
+            dev = obs.device
+            mk = lambda shape, dt: torch.empty(shape, dtype=dt, device=dev)
+            out = SearchOutput(mk((n, A), torch.int32), mk((n,), torch.float64), mk((n,), torch.float32),
+                               mk((n,), torch.int32), mk((n,), torch.int32), mk((n, A), torch.float64),
+                               mk((n, 2), torch.float64))
+            p = lambda t: t.data_ptr()
+        else:
+            out = SearchOutput(numpy.empty((n, A), numpy.int32), numpy.empty(n, numpy.float64),
+                               numpy.empty(n, numpy.float32), numpy.empty(n, numpy.int32), numpy.empty(n, numpy.int32),
+                               numpy.empty((n, A), numpy.float64), numpy.empty((n, 2), numpy.float64))
+            p = lambda a: a.ctypes.data
+        io.visit_counts, io.root_value, io.root_predicted_value = p(out.visit_counts), p(out.root_value), p(out.root_predicted_value)
+        io.max_tree_depth, io.tie_count, io.root_priors = p(out.max_tree_depth), p(out.tie_count), p(out.root_priors)
+        io.value_range = p(out.value_range)
+
+        if teacher is not None:
+            t = _lib.MzTeacher()
+            for f in ("root_value", "root_reward", "root_priors", "value", "reward", "priors"):
+                setattr(t, f, self._ptr(teacher[f], numpy.float32, keep))
+            keep.append(t)
+            io.teacher = C.pointer(t)
+        if trace:
+            if device_mem:
+                raise ValueError("trace is only available with host buffers")
+            D = int(trace_depth or max(1, N))
+            tr = dict(depth=numpy.zeros((n, N), numpy.int32), actions=numpy.zeros((n, N, D), numpy.uint8),
+                      value=numpy.zeros((n, N), numpy.float32), reward=numpy.zeros((n, N), numpy.float32),
+                      priors=numpy.zeros((n, N, A), numpy.float32), root_priors_raw=numpy.zeros((n, A), numpy.float32),
+                      root_reward=numpy.zeros(n, numpy.float32))
+            t = _lib.MzTrace()
+            t.max_depth = D
+            for k, v in tr.items():
+                setattr(t, k, v.ctypes.data)
+            keep.append(t)
+            io.trace = C.pointer(t)
+            out.trace = tr
+        self._check(self.lib.mz_search(self._h, C.byref(io)))
+        out.device_ms = self.last_search_ms
+        return out
+
+    # ------------------------------------------------------------------ networks
+    def _inference(self, fn, n, x, action):
+        A, F, H = self.A, self.spec.full_support, self.hidden_elems
+        keep = []
+        res = dict(value_logits=numpy.empty((n, F), numpy.float32), reward_logits=numpy.empty((n, F), numpy.float32),
+                   policy_logits=numpy.empty((n, A), numpy.float32), hidden=numpy.empty((n, H), numpy.float32),
+                   value=numpy.empty(n, numpy.float32), reward=numpy.empty(n, numpy.float32))
+        o = _lib.MzInferenceOut()
+        for k, v in res.items():
+            setattr(o, k, v.ctypes.data)
+        xp = self._ptr(numpy.asarray(x, dtype=numpy.float32).reshape(n, -1), numpy.float32, keep)
+        if action is None:
+            self._check(fn(self._h, n, _lib.MZ_MEM_HOST, xp, C.byref(o)))
+        else:
+            ap = self._ptr(numpy.asarray(action).reshape(n), numpy.int32, keep)
+            self._check(fn(self._h, n, _lib.MZ_MEM_HOST, xp, ap, C.byref(o)))
+        return res
+
+    def initial_inference(self, obs):
+        obs = numpy.asarray(obs, dtype=numpy.float32)
+        return self._inference(self.lib.mz_initial_inference, obs.shape[0], obs, None)
+
+    def recurrent_inference(self, hidden, action):
+        hidden = numpy.asarray(hidden, dtype=numpy.float32)
+        return self._inference(self.lib.mz_recurrent_inference, hidden.shape[0], hidden, action)
+
+    # ------------------------------------------------------------------ tree
+    def export_tree(self, game: int, with_hidden: bool = False):
+        S = (self.N + 1) * self.A
+        out = dict(child_visit=numpy.zeros(S, numpy.int32), child_value_sum=numpy.zeros(S, numpy.float64),
+                   child_reward=numpy.zeros(S, numpy.float32), child_prior=numpy.zeros(S, numpy.float64),
+                   child_expansion=numpy.full(S, -1, numpy.int32))
+        e = _lib.MzTreeExport()
+        for k, v in out.items():
+            setattr(e, k, v.ctypes.data)
+        if with_hidden:
+            out["hidden"] = numpy.zeros((self.N + 1, self.hidden_elems), numpy.float32)
+            e.hidden = out["hidden"].ctypes.data
+        self._check(self.lib.mz_export_tree(self._h, int(game), C.byref(e)))
+        out["n_expansions"] = int(e.n_expansions)
+        out["root_visit"] = int(e.root_visit)
+        out["root_value_sum"] = float(e.root_value_sum)
+        return out
