@@ -1,0 +1,629 @@
+"""Drop-in self-play surface of the reference (``self_play.py``), backed by libmzb200.so.
+
+Same class names, method names, argument meaning and output format as the reference:
+
+* ``SelfPlay(initial_checkpoint, Game, config, seed)`` with ``continuous_self_play``,
+  ``play_game``, ``close_game``, ``select_opponent_action`` and the static
+  ``select_action``                                              (self_play.py:11-245)
+* ``MCTS(config).run(model, observation, legal_actions, to_play, add_exploration_noise)``
+  returning ``(root Node, {"max_tree_depth", "root_predicted_value"})``   (self_play.py:249-361)
+* ``Node`` with ``children / visit_count / value_sum / prior / reward / hidden_state /
+  to_play / expanded() / value()``                               (self_play.py:433-476)
+* ``GameHistory`` with the exact attribute set ``ReplayBuffer.save_game`` and
+  ``Trainer`` consume (self_play.py:479-550; replay_buffer.py:33-65,85-111,230-303)
+* ``MinMaxStats``                                                (self_play.py:553-570)
+
+What changes is HOW a move is computed: every search is a call into the CUDA library, and
+``config.num_parallel_games`` games can be searched in lockstep by one process
+(``SelfPlay.play_games`` / ``self_play_stream``).  With one game and ``rng_mode="numpy"`` the
+draw order on the legacy global ``numpy.random`` stream is the reference's: Dirichlet noise,
+then the first simulation's uniform pick, then the action sample.
+"""
+from __future__ import annotations
+
+import time
+from collections import deque
+
+import numpy
+
+from .engine import SearchEngine
+
+
+# ----------------------------------------------------------------------------------------
+# remote-or-local call helpers: the reference talks to Ray actors (self_play.py:32-37);
+# plain objects with the same methods work too.
+# ----------------------------------------------------------------------------------------
+def _call(obj, method, *args):
+    fn = getattr(obj, method)
+    if hasattr(fn, "remote"):
+        import ray
+        return ray.get(fn.remote(*args))
+    return fn(*args)
+
+
+def _fire(obj, method, *args):
+    fn = getattr(obj, method)
+    if hasattr(fn, "remote"):
+        return fn.remote(*args)
+    return fn(*args)
+
+
+# ----------------------------------------------------------------------------------------
+# model facade
+# ----------------------------------------------------------------------------------------
+class DeviceModel:
+    """Stands where ``models.MuZeroNetwork(config)`` stood in ``SelfPlay`` (self_play.py:25-29).
+
+    Holds the CUDA search engine; ``set_weights`` / ``get_weights`` keep the reference's
+    state_dict format (models.py:69-73).
+    """
+
+    def __init__(self, config, max_games=1, device=0, seed=None, num_simulations=None):
+        self.config = config
+        self.engine = SearchEngine(config, max_games=max_games, device=device, seed=seed,
+                                   num_simulations=num_simulations)
+        self._weights = None
+
+    def set_weights(self, weights):
+        self.engine.load_weights(weights)
+        self._weights = weights
+
+    def get_weights(self):
+        return self._weights
+
+    def eval(self):
+        return self
+
+    def to(self, device):
+        return self
+
+    def initial_inference(self, observation):
+        """[B,C',H,W] -> (value_logits, reward_logits, policy_logits, hidden) as torch tensors."""
+        import torch
+        obs = numpy.asarray(observation.cpu() if hasattr(observation, "cpu") else observation, dtype=numpy.float32)
+        r = self.engine.initial_inference(obs)
+        return (torch.from_numpy(r["value_logits"]), torch.from_numpy(r["reward_logits"]),
+                torch.from_numpy(r["policy_logits"]), torch.from_numpy(r["hidden"]))
+
+    def recurrent_inference(self, encoded_state, action):
+        import torch
+        h = numpy.asarray(encoded_state.cpu() if hasattr(encoded_state, "cpu") else encoded_state, dtype=numpy.float32)
+        a = numpy.asarray(action.cpu() if hasattr(action, "cpu") else action).reshape(-1)
+        r = self.engine.recurrent_inference(h.reshape(h.shape[0], -1), a)
+        return (torch.from_numpy(r["value_logits"]), torch.from_numpy(r["reward_logits"]),
+                torch.from_numpy(r["policy_logits"]), torch.from_numpy(r["hidden"]))
+
+
+# ----------------------------------------------------------------------------------------
+# tree view
+# ----------------------------------------------------------------------------------------
+class Node:
+    """Read-only mirror of the reference ``Node`` (self_play.py:433-449) built from the device tree."""
+
+    def __init__(self, prior):
+        self.visit_count = 0
+        self.to_play = -1
+        self.prior = prior
+        self.value_sum = 0
+        self.children = {}
+        self.hidden_state = None
+        self.reward = 0
+
+    def expanded(self):
+        return len(self.children) > 0
+
+    def value(self):
+        if self.visit_count == 0:
+            return 0
+        return self.value_sum / self.visit_count
+
+
+def _node_graph(tree, legal_actions, to_play, num_players, A):
+    """Rebuild the ``Node`` graph of one game from ``SearchEngine.export_tree``."""
+    root = Node(0)
+    root.visit_count = tree["root_visit"]
+    root.value_sum = tree["root_value_sum"]
+    root.to_play = to_play
+    root.reward = -0.0
+    hidden = tree.get("hidden")
+    if hidden is not None:
+        root.hidden_state = hidden[0]
+    stack = [(root, 0, to_play)]
+    while stack:
+        node, e, tp = stack.pop()
+        actions = legal_actions if e == 0 else range(A)
+        nxt = (tp + 1) % num_players
+        for a in actions:
+            s = e * A + a
+            child = Node(float(tree["child_prior"][s]))
+            child.visit_count = int(tree["child_visit"][s])
+            child.value_sum = float(tree["child_value_sum"][s])
+            node.children[a] = child
+            ce = int(tree["child_expansion"][s])
+            if ce >= 0:
+                child.reward = float(tree["child_reward"][s])
+                child.to_play = nxt
+                if hidden is not None:
+                    child.hidden_state = hidden[ce]
+                stack.append((child, ce, nxt))
+    return root
+
+
+class MCTS:
+    """``MCTS(config).run`` for ONE game through the batched engine (self_play.py:249-361)."""
+
+    def __init__(self, config):
+        self.config = config
+
+    def run(self, model, observation, legal_actions, to_play, add_exploration_noise, override_root_with=None):
+        if override_root_with:
+            raise NotImplementedError("override_root_with (diagnose_model.py:70-72) is not supported yet")
+        config = self.config
+        assert legal_actions, f"Legal actions should not be an empty array. Got {legal_actions}."
+        assert set(legal_actions).issubset(set(config.action_space)), \
+            "Legal actions should be a subset of the action space."
+        assert list(legal_actions) == sorted(legal_actions), "legal_actions must be ascending"
+        engine = model.engine
+        A = engine.A
+        mask = numpy.zeros((1, A), numpy.uint8)
+        mask[0, list(legal_actions)] = 1
+        noise = None
+        if add_exploration_noise:
+            draw = numpy.random.dirichlet([config.root_dirichlet_alpha] * len(legal_actions))   # self_play.py:473
+            noise = numpy.zeros((1, A))
+            noise[0, list(legal_actions)] = draw
+        # first simulation: every root child scores exactly 0 -> uniform pick (self_play.py:371)
+        first = list(legal_actions).index(numpy.random.choice(list(legal_actions)))
+        obs = numpy.asarray(observation, dtype=numpy.float32)[None]
+        out = engine.search(obs=obs, legal_mask=mask, to_play=numpy.array([to_play], numpy.int32),
+                            add_exploration_noise=add_exploration_noise, noise=noise,
+                            first_index=numpy.array([first], numpy.int32), keep_tree=True)
+        tree = engine.export_tree(0, with_hidden=True)
+        root = _node_graph(tree, list(legal_actions), to_play, len(config.players), A)
+        return root, {"max_tree_depth": int(out.max_tree_depth[0]),
+                      "root_predicted_value": float(out.root_predicted_value[0])}
+
+
+# ----------------------------------------------------------------------------------------
+# output format
+# ----------------------------------------------------------------------------------------
+class GameHistory:
+    """Same attributes and helpers as the reference's (self_play.py:479-550)."""
+
+    def __init__(self):
+        self.observation_history = []
+        self.action_history = []
+        self.reward_history = []
+        self.to_play_history = []
+        self.child_visits = []
+        self.root_values = []
+        self.reanalysed_predicted_root_values = None
+        # For PER
+        self.priorities = None
+        self.game_priority = None
+
+    def store_search_statistics(self, root, action_space):
+        if root is not None:
+            total = sum(child.visit_count for child in root.children.values())
+            self.child_visits.append(
+                [root.children[a].visit_count / total if a in root.children else 0 for a in action_space])
+            self.root_values.append(root.value())
+        else:
+            self.root_values.append(None)
+
+    def store_visit_counts(self, visit_counts, legal_mask, root_value, action_space):
+        """Batched equivalent of ``store_search_statistics``: one row of the engine's output."""
+        total = int(visit_counts.sum())
+        self.child_visits.append([int(visit_counts[a]) / total if legal_mask[a] else 0 for a in action_space])
+        self.root_values.append(float(root_value))
+
+    def get_stacked_observations(self, index, num_stacked_observations, action_space_size):
+        index = index % len(self.observation_history)
+        planes = [self.observation_history[index].copy()]
+        like = planes[0][0]
+        for past in range(index - 1, index - num_stacked_observations - 1, -1):
+            if past >= 0:
+                planes.append(self.observation_history[past])
+                planes.append([numpy.ones_like(like) * self.action_history[past + 1] / action_space_size])
+            else:
+                planes.append(numpy.zeros_like(self.observation_history[index]))
+                planes.append([numpy.zeros_like(like)])
+        return numpy.concatenate(planes) if len(planes) > 1 else planes[0]
+
+
+class MinMaxStats:
+    """self_play.py:553-570 (the device keeps the same two doubles per game)."""
+
+    def __init__(self):
+        self.maximum = -float("inf")
+        self.minimum = float("inf")
+
+    def update(self, value):
+        self.maximum = max(self.maximum, value)
+        self.minimum = min(self.minimum, value)
+
+    def normalize(self, value):
+        if self.maximum > self.minimum:
+            return (value - self.minimum) / (self.maximum - self.minimum)
+        return value
+
+
+def register_as_reference_module():
+    """Make pickles of ``GameHistory`` interchangeable with the reference's replay_buffer.pkl
+    (muzero.py:338-346,444-446): the class is published under the module name ``self_play``."""
+    import sys
+    import types
+    mod = sys.modules.get("self_play")
+    if mod is None:
+        mod = types.ModuleType("self_play")
+        sys.modules["self_play"] = mod
+    for cls in (GameHistory, MinMaxStats, Node, MCTS, SelfPlay):
+        setattr(mod, cls.__name__, cls)
+    GameHistory.__module__ = "self_play"
+
+
+# ----------------------------------------------------------------------------------------
+# the actor
+# ----------------------------------------------------------------------------------------
+class SelfPlay:
+    """Plays games and saves them to the replay buffer (self_play.py:11-245)."""
+
+    def __init__(self, initial_checkpoint, Game, config, seed, device=0):
+        self.config = config
+        self.Game = Game
+        self.seed = seed
+        self.num_parallel_games = int(getattr(config, "num_parallel_games", 1) or 1)
+        self.rng_mode = getattr(config, "rng_mode", "numpy")
+        self.game = Game(seed)
+
+        # Fix random generator seed (self_play.py:22-23)
+        numpy.random.seed(seed)
+
+        self.model = DeviceModel(config, max_games=self.num_parallel_games, device=device, seed=seed)
+        self.model.set_weights(initial_checkpoint["weights"])
+        self._stream = None
+        self.played_games = 0
+        self.played_steps = 0
+
+    # ------------------------------------------------------------------ reference loop
+    def continuous_self_play(self, shared_storage, replay_buffer, test_mode=False):
+        cfg = self.config
+        while (_call(shared_storage, "get_info", "training_step") < cfg.training_steps
+               and not _call(shared_storage, "get_info", "terminate")):
+            self.model.set_weights(_call(shared_storage, "get_info", "weights"))
+            if not test_mode:
+                temperature = cfg.visit_softmax_temperature_fn(
+                    trained_steps=_call(shared_storage, "get_info", "training_step"))
+                if self.num_parallel_games > 1:
+                    # one lockstep batch per weight refresh; every finished game goes to the buffer
+                    for game_history in self.play_games(self.num_parallel_games, temperature,
+                                                        cfg.temperature_threshold):
+                        _fire(replay_buffer, "save_game", game_history, shared_storage)
+                else:
+                    game_history = self.play_game(temperature, cfg.temperature_threshold, False, "self", 0)
+                    _fire(replay_buffer, "save_game", game_history, shared_storage)
+            else:
+                # Take the best action (no exploration) in test mode
+                game_history = self.play_game(
+                    0, cfg.temperature_threshold, False,
+                    "self" if len(cfg.players) == 1 else cfg.opponent, cfg.muzero_player)
+                _fire(shared_storage, "set_info", {
+                    "episode_length": len(game_history.action_history) - 1,
+                    "total_reward": sum(game_history.reward_history),
+                    "mean_value": numpy.mean([value for value in game_history.root_values if value]),
+                })
+                if 1 < len(cfg.players):
+                    _fire(shared_storage, "set_info", {
+                        "muzero_reward": sum(
+                            reward for i, reward in enumerate(game_history.reward_history)
+                            if game_history.to_play_history[i - 1] == cfg.muzero_player),
+                        "opponent_reward": sum(
+                            reward for i, reward in enumerate(game_history.reward_history)
+                            if game_history.to_play_history[i - 1] != cfg.muzero_player),
+                    })
+
+            # Managing the self-play / training ratio
+            if not test_mode and cfg.self_play_delay:
+                time.sleep(cfg.self_play_delay)
+            if not test_mode and cfg.ratio:
+                while (_call(shared_storage, "get_info", "training_step")
+                       / max(1, _call(shared_storage, "get_info", "num_played_steps")) < cfg.ratio
+                       and _call(shared_storage, "get_info", "training_step") < cfg.training_steps
+                       and not _call(shared_storage, "get_info", "terminate")):
+                    time.sleep(0.5)
+        self.close_game()
+
+    def play_game(self, temperature, temperature_threshold, render, opponent, muzero_player):
+        """One game, one search per move (self_play.py:110-183)."""
+        cfg = self.config
+        game_history = GameHistory()
+        observation = self.game.reset()
+        game_history.action_history.append(0)
+        game_history.observation_history.append(observation)
+        game_history.reward_history.append(0)
+        game_history.to_play_history.append(self.game.to_play())
+        done = False
+        if render:
+            self.game.render()
+        while not done and len(game_history.action_history) <= cfg.max_moves:
+            assert len(numpy.array(observation).shape) == 3, \
+                f"Observation should be 3 dimensionnal instead of {len(numpy.array(observation).shape)} dimensionnal. Got observation of shape: {numpy.array(observation).shape}"
+            assert numpy.array(observation).shape == cfg.observation_shape, \
+                f"Observation should match the observation_shape defined in MuZeroConfig. Expected {cfg.observation_shape} but got {numpy.array(observation).shape}."
+            stacked_observations = game_history.get_stacked_observations(
+                -1, cfg.stacked_observations, len(cfg.action_space))
+
+            # Choose the action
+            if opponent == "self" or muzero_player == self.game.to_play():
+                root, mcts_info = MCTS(cfg).run(self.model, stacked_observations, self.game.legal_actions(),
+                                                self.game.to_play(), True)
+                action = self.select_action(
+                    root,
+                    temperature if not temperature_threshold
+                    or len(game_history.action_history) < temperature_threshold else 0)
+                if render:
+                    print(f'Tree depth: {mcts_info["max_tree_depth"]}')
+                    print(f"Root value for player {self.game.to_play()}: {root.value():.2f}")
+            else:
+                action, root = self.select_opponent_action(opponent, stacked_observations)
+
+            observation, reward, done = self.game.step(action)
+            if render:
+                print(f"Played action: {self.game.action_to_string(action)}")
+                self.game.render()
+            game_history.store_search_statistics(root, cfg.action_space)
+
+            # Next batch
+            game_history.action_history.append(action)
+            game_history.observation_history.append(observation)
+            game_history.reward_history.append(reward)
+            game_history.to_play_history.append(self.game.to_play())
+        self.played_games += 1
+        self.played_steps += len(game_history.action_history) - 1
+        return game_history
+
+    def close_game(self):
+        self.game.close()
+
+    def select_opponent_action(self, opponent, stacked_observations):
+        """Opponent move for evaluation games (self_play.py:188-220)."""
+        if opponent == "human":
+            root, mcts_info = MCTS(self.config).run(self.model, stacked_observations, self.game.legal_actions(),
+                                                    self.game.to_play(), True)
+            print(f'Tree depth: {mcts_info["max_tree_depth"]}')
+            print(f"Root value for player {self.game.to_play()}: {root.value():.2f}")
+            print(f"Player {self.game.to_play()} turn. MuZero suggests "
+                  f"{self.game.action_to_string(self.select_action(root, 0))}")
+            return self.game.human_to_action(), root
+        elif opponent == "expert":
+            return self.game.expert_agent(), None
+        elif opponent == "random":
+            assert self.game.legal_actions(), \
+                f"Legal actions should not be an empty array. Got {self.game.legal_actions()}."
+            assert set(self.game.legal_actions()).issubset(set(self.config.action_space)), \
+                "Legal actions should be a subset of the action space."
+            return numpy.random.choice(self.game.legal_actions()), None
+        raise NotImplementedError(
+            'Wrong argument: "opponent" argument should be "self", "human", "expert" or "random"')
+
+    @staticmethod
+    def select_action(node, temperature):
+        """Visit-count sampling (self_play.py:222-245)."""
+        visit_counts = numpy.array([child.visit_count for child in node.children.values()], dtype="int32")
+        actions = [action for action in node.children.keys()]
+        return _sample_action(actions, visit_counts, temperature, numpy.random)
+
+    # ------------------------------------------------------------------ batched play
+    def play_games(self, num_games, temperature, temperature_threshold=None, max_total_moves=None):
+        """Play ``num_games`` games, ``num_parallel_games`` at a time in lockstep; returns the histories."""
+        out = []
+        for gh in self.self_play_stream(temperature, temperature_threshold):
+            out.append(gh)
+            if len(out) >= num_games:
+                break
+            if max_total_moves is not None and self.played_steps >= max_total_moves:
+                break
+        self._stream = None
+        return out
+
+    def self_play_stream(self, temperature, temperature_threshold=None):
+        """Generator over finished ``GameHistory`` objects; B games advance one move per iteration."""
+        return BatchedSelfPlay(self, temperature, temperature_threshold).run()
+
+
+def _sample_action(actions, visit_counts, temperature, rng):
+    if temperature == 0:
+        return actions[numpy.argmax(visit_counts)]
+    if temperature == float("inf"):
+        return rng.choice(actions)
+    # See paper appendix Data Generation
+    dist = visit_counts ** (1 / temperature)
+    dist = dist / sum(dist)
+    return rng.choice(actions, p=dist)
+
+
+class _ObjectVector:
+    """Adapter giving ``num_games`` ordinary ``Game`` objects the ``VectorGame`` interface."""
+
+    def __init__(self, Game, num_games, seed, A):
+        self.games = [Game(seed + g) for g in range(num_games)]
+        self.num_games = num_games
+        self.A = A
+        self._obs = [None] * num_games
+
+    def reset(self, which=None):
+        idx = range(self.num_games) if which is None else numpy.nonzero(which)[0]
+        for g in idx:
+            self._obs[g] = numpy.asarray(self.games[g].reset())
+        return self._obs
+
+    def observations(self):
+        return self._obs
+
+    def step(self, actions):
+        rewards, dones = [], []
+        for g, game in enumerate(self.games):
+            o, r, d = game.step(actions[g])
+            self._obs[g] = numpy.asarray(o)
+            rewards.append(r)
+            dones.append(d)
+        return self._obs, rewards, numpy.array(dones, dtype=bool)
+
+    def legal_mask(self):
+        m = numpy.zeros((self.num_games, self.A), numpy.uint8)
+        for g, game in enumerate(self.games):
+            m[g, game.legal_actions()] = 1
+        return m
+
+    def to_play(self):
+        return numpy.array([game.to_play() for game in self.games], dtype=numpy.int32)
+
+
+class BatchedSelfPlay:
+    """Lockstep self-play of B games: one ``mz_search`` call per move for the whole batch.
+
+    Per move the host only (1) gathers observations / legal masks from the environments,
+    (2) draws the root noise, (3) samples actions from the returned visit counts and
+    (4) appends one struct-of-arrays record; ``GameHistory`` objects are materialised only when
+    a game ends.  Game slot g keeps the global id ``seed*0 + g`` for its RNG streams so results do
+    not depend on how many games share the batch (world-size invariance).
+    """
+
+    def __init__(self, worker: SelfPlay, temperature, temperature_threshold, first_game_id=0):
+        self.w = worker
+        self.cfg = worker.config
+        self.B = worker.num_parallel_games
+        self.A = len(self.cfg.action_space)
+        self.temperature = temperature
+        self.temperature_threshold = temperature_threshold
+        self.first_game_id = first_game_id
+        Game = worker.Game
+        if hasattr(Game, "vector"):
+            self.env = Game.vector(self.B, worker.seed)
+        else:
+            self.env = _ObjectVector(Game, self.B, worker.seed, self.A)
+        self.numpy_mode = worker.rng_mode == "numpy"
+        if self.numpy_mode:
+            self.streams = [numpy.random.RandomState(worker.seed + first_game_id + g) for g in range(self.B)]
+        else:
+            self.fast = numpy.random.RandomState(worker.seed + first_game_id)
+
+    def _noise_and_first(self, legal):
+        cfg, B, A = self.cfg, self.B, self.A
+        noise = numpy.zeros((B, A))
+        if self.numpy_mode:
+            first = numpy.zeros(B, numpy.int32)
+            for g in range(B):
+                idx = numpy.nonzero(legal[g])[0]
+                noise[g, idx] = self.streams[g].dirichlet([cfg.root_dirichlet_alpha] * len(idx))
+                first[g] = self.streams[g].choice(len(idx))
+            return noise, first
+        gam = self.fast.standard_gamma(cfg.root_dirichlet_alpha, size=(B, A)) * (legal > 0)
+        noise = gam / gam.sum(1, keepdims=True)
+        return noise, None
+
+    def _actions(self, visit_counts, legal, moves_played):
+        B = self.B
+        actions = numpy.zeros(B, numpy.int64)
+        thr = self.temperature_threshold
+        if self.numpy_mode:
+            for g in range(B):
+                idx = numpy.nonzero(legal[g])[0]
+                t = self.temperature if not thr or moves_played[g] + 1 < thr else 0
+                actions[g] = _sample_action([int(a) for a in idx], visit_counts[g, idx].astype("int32"), t,
+                                            self.streams[g])
+            return actions
+        t = numpy.full(B, float(self.temperature))
+        if thr:
+            t[moves_played + 1 >= thr] = 0
+        greedy = t == 0
+        with numpy.errstate(divide="ignore"):
+            p = visit_counts.astype(numpy.float64) ** (1.0 / numpy.where(greedy, 1.0, t))[:, None]
+        cdf = numpy.cumsum(p / p.sum(1, keepdims=True), axis=1)
+        u = self.fast.random_sample(B)
+        sampled = (u[:, None] >= cdf).sum(1).clip(0, self.A - 1)
+        return numpy.where(greedy, visit_counts.argmax(1), sampled).astype(numpy.int64)
+
+    def run(self):
+        cfg, B, A, w = self.cfg, self.B, self.A, self.w
+        env = self.env
+        engine = w.model.engine
+        obs = env.reset()
+        # per-slot bookkeeping
+        start = numpy.zeros(B, numpy.int64)        # index into `records` of the slot's first move
+        moves = numpy.zeros(B, numpy.int64)        # moves played in the current game
+        first_obs = [numpy.asarray(obs[g]).copy() for g in range(B)]
+        first_to_play = numpy.asarray(env.to_play()).copy()
+        game_ids = (self.first_game_id + numpy.arange(B)).astype(numpy.int64)
+        records = deque()                          # one dict of [B,...] arrays per move
+        base = 0                                   # absolute index of records[0]
+        stacked = cfg.stacked_observations
+        partial = [None] * B                       # GameHistory under construction (only if stacking)
+        t_abs = 0
+        while True:
+            legal = numpy.asarray(env.legal_mask(), dtype=numpy.uint8)
+            to_play = numpy.asarray(env.to_play(), dtype=numpy.int32)
+            if stacked:
+                batch = numpy.stack([self._stacked(g, obs, records, base, start, first_obs) for g in range(B)])
+            else:
+                batch = numpy.stack([numpy.asarray(o, dtype=numpy.float32) for o in obs]) \
+                    if not isinstance(obs, numpy.ndarray) else obs
+            noise, first = self._noise_and_first(legal)
+            out = engine.search(obs=numpy.asarray(batch, dtype=numpy.float32).reshape(B, -1), legal_mask=legal,
+                                to_play=to_play, add_exploration_noise=True, noise=noise, first_index=first,
+                                game_id=game_ids, move_index=moves.astype(numpy.int32))
+            actions = self._actions(out.visit_counts, legal, moves)
+            obs, reward, done = env.step(actions)
+            records.append(dict(visits=out.visit_counts, legal=legal, root_value=out.root_value, action=actions,
+                                obs=[numpy.asarray(o).copy() for o in obs] if not isinstance(obs, numpy.ndarray) else obs.copy(),
+                                reward=numpy.asarray(reward).copy() if isinstance(reward, numpy.ndarray) else list(reward),
+                                to_play=numpy.asarray(env.to_play()).copy()))
+            t_abs += 1
+            moves += 1
+            w.played_steps += B
+            finished = numpy.asarray(done, dtype=bool) | (moves >= cfg.max_moves)
+            if finished.any():
+                for g in numpy.nonzero(finished)[0]:
+                    yield self._materialise(g, records, base, int(start[g]), t_abs, first_obs[g], first_to_play[g])
+                    w.played_games += 1
+                obs = env.reset(finished)
+                tp = numpy.asarray(env.to_play())
+                for g in numpy.nonzero(finished)[0]:
+                    first_obs[g] = numpy.asarray(obs[g]).copy()
+                    first_to_play[g] = tp[g]
+                    start[g] = t_abs
+                    moves[g] = 0
+                    game_ids[g] += B           # a fresh global game id for the slot's next game
+                    if self.numpy_mode:
+                        self.streams[g] = numpy.random.RandomState(self.w.seed + int(game_ids[g]))
+            drop = int(start.min()) - base
+            for _ in range(drop):
+                records.popleft()
+            base += drop
+
+    def _stacked(self, g, obs, records, base, start, first_obs):
+        gh = GameHistory()
+        gh.observation_history.append(first_obs[g])
+        gh.action_history.append(0)
+        for r in list(records)[int(start[g]) - base:]:
+            gh.observation_history.append(numpy.asarray(r["obs"][g]))
+            gh.action_history.append(r["action"][g])
+        return gh.get_stacked_observations(-1, self.cfg.stacked_observations, self.A)
+
+    def _materialise(self, g, records, base, first, last, obs0, to_play0):
+        """Column g of the per-move records [first, last) -> one reference-format GameHistory."""
+        cfg = self.cfg
+        gh = GameHistory()
+        gh.action_history.append(0)
+        gh.observation_history.append(obs0)
+        gh.reward_history.append(0)
+        gh.to_play_history.append(int(to_play0))
+        for i in range(first - base, last - base):
+            r = records[i]
+            gh.store_visit_counts(r["visits"][g], r["legal"][g], r["root_value"][g], cfg.action_space)
+            gh.action_history.append(r["action"][g])
+            gh.observation_history.append(numpy.asarray(r["obs"][g]))
+            rew = r["reward"][g]
+            gh.reward_history.append(rew.item() if hasattr(rew, "item") else rew)
+            gh.to_play_history.append(int(r["to_play"][g]))
+        return gh

@@ -103,7 +103,7 @@ class InjectedDraws:
         sim, depth = ctx
         if sim == 0 and depth == 0 and self.first_index is not None:
             return int(self.first_index)
-        if n_tied > 1:
+        if n_tied > 1 and not (sim == 0 and depth == 0):     # the first simulation's all-way tie is expected
             self.later_ties += 1
         if self.tie_fn is None:
             assert n_tied == 1, "unexpected exact tie and no tie_fn supplied"
