@@ -1,9 +1,638 @@
-// placeholder until the residual-network kernels land
+// Residual MuZero networks (models.py:206-623) on the device - fp32 CUDA-core path.
+//
+//   representation  models.py:339-349 (+ DownSample models.py:233-275), rescale models.py:526-553
+//   dynamics        models.py:379-389, action plane + rescale models.py:555-599
+//   prediction      models.py:424-433
+//   support_to_scalar models.py:645-666 fused behind the value / reward heads
+//
+// Layout: activations NCHW fp32 in HBM workspaces; BatchNorm (eval mode, self_play.py:29) is
+// folded into the conv weights/bias at load time; the dynamics input plane action/|A|
+// (models.py:557-572) is synthesised while staging the input tile, never materialised.
+// conv3x3 is a register-tiled direct convolution: a CTA stages the (padded) input planes of
+// one or more samples plus the [cin][tap][cout] weights of a cout tile in shared memory; each
+// thread owns 4 output channels x P consecutive pixels of one row.
+// This is the exact-fp32 path ("strict" numerics, also the validation reference for the
+// tensor-core path).
+#include <math.h>
+
+#include <map>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
 #include "pipeline.h"
+
 namespace mz {
-struct ResNetDevice { int dummy; };
-ResNetDevice* resnet_create(const MzNetDesc&, int, int, std::string*) { return new ResNetDevice(); }
-void resnet_destroy(ResNetDevice* r) { delete r; }
-int resnet_load_weights(ResNetDevice*, const MzTensor*, int, std::string* err) { *err = "resnet kernels not built yet"; return MZ_EUNSUPPORTED; }
-int resnet_inference(ResNetDevice*, const InferCall&, cudaStream_t, int64_t*, std::string* err) { *err = "resnet kernels not built yet"; return MZ_EUNSUPPORTED; }
+
+// ------------------------------------------------------------------------------------------
+// conv3x3 (+folded BN bias, +residual, +ReLU), stride 1 or 2, pad 1
+// ------------------------------------------------------------------------------------------
+struct ConvArgs {
+    const float* in;          // [n, Cin_real, Hin, Win]   (or gathered from the hidden pool)
+    float* out;               // [n, Cout, Ho, Wo]
+    const float* residual;    // same shape as out or nullptr
+    const float* w;           // [Cin][9][Cout]
+    const float* bias;        // [Cout] or nullptr
+    const int32_t* gather_parent;   // pool mode: sample g reads in + (g*pool_stride + gather_parent[g]) * sample_elems
+    const int32_t* action;    // extra constant input plane action/A as channel Cin-1 (dynamics), or nullptr
+    int pool_stride;
+    int n, Cin, Cout, Hin, Win, Ho, Wo, stride, relu, A;
+    int boards_per_cta, cin_chunk;
+};
+
+template <int P, int STRIDE, int MAX_ITEMS>
+__global__ void __launch_bounds__(256) conv3x3_kernel(const __grid_constant__ ConvArgs a) {
+    extern __shared__ __align__(16) float smem[];
+    constexpr int IN_SPAN = (P - 1) * STRIDE + 3;              // input columns feeding P outputs
+    const int Hp = a.Hin + 2, Wp = a.Win + 2;                   // padded plane
+    const int plane = Hp * Wp;
+    const int ct = a.Cout < 64 ? a.Cout : 64;                   // cout tile of this CTA
+    const int cout0 = blockIdx.y * ct;
+    const int cgs = ct / 4;
+    const int segs = a.Wo / P;
+    const int items_per_board = cgs * a.Ho * segs;
+    const int b0 = blockIdx.x * a.boards_per_cta;
+    const int nb = min(a.boards_per_cta, a.n - b0);
+    float* s_w = smem;                                          // [cin_chunk][9][ct]
+    float* s_in = smem + a.cin_chunk * 9 * ct;                  // [boards][cin_chunk][Hp][Wp]
+    const int cin_real = a.action ? a.Cin - 1 : a.Cin;
+    const size_t sample_elems = (size_t)cin_real * a.Hin * a.Win;
+
+    const int total_items = nb * items_per_board;
+    // each thread may own several items (big images): MAX_ITEMS accumulator tiles
+    float acc[MAX_ITEMS][4][P];
+#pragma unroll
+    for (int it = 0; it < MAX_ITEMS; ++it)
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+#pragma unroll
+            for (int p = 0; p < P; ++p) acc[it][c][p] = 0.0f;
+
+    for (int c0 = 0; c0 < a.Cin; c0 += a.cin_chunk) {
+        const int cc = min(a.cin_chunk, a.Cin - c0);
+        __syncthreads();
+        // ---- stage weights of this cin chunk / cout tile
+        for (int i = threadIdx.x; i < cc * 9 * ct; i += blockDim.x) {
+            const int co = i % ct, r = i / ct;                  // r = ci*9 + tap
+            s_w[i] = a.w[((size_t)(c0 * 9 + r)) * a.Cout + cout0 + co];
+        }
+        // ---- stage padded input planes
+        for (int i = threadIdx.x; i < nb * cc * plane; i += blockDim.x) {
+            const int x = i % Wp, y = (i / Wp) % Hp, ci = (i / plane) % cc, b = i / (plane * cc);
+            const int g = b0 + b, cg = c0 + ci;
+            float v = 0.0f;
+            if (x >= 1 && x <= a.Win && y >= 1 && y <= a.Hin) {
+                if (a.action && cg == a.Cin - 1) {
+                    v = __fdiv_rn((float)a.action[g], (float)a.A);       // action / |A| plane
+                } else {
+                    const float* src = a.gather_parent
+                        ? a.in + ((size_t)g * a.pool_stride + a.gather_parent[g]) * sample_elems
+                        : a.in + (size_t)g * sample_elems;
+                    v = src[((size_t)cg * a.Hin + (y - 1)) * a.Win + (x - 1)];
+                }
+            }
+            s_in[i] = v;
+        }
+        __syncthreads();
+        // ---- accumulate
+#pragma unroll
+        for (int it = 0; it < MAX_ITEMS; ++it) {
+            const int item = threadIdx.x + it * blockDim.x;
+            if (item >= total_items) break;
+            const int cgi = item % cgs;
+            const int rest = item / cgs;
+            const int seg = rest % segs, y = (rest / segs) % a.Ho, b = rest / (segs * a.Ho);
+            const float* ib = s_in + (size_t)b * cc * plane + (y * STRIDE) * Wp + seg * P * STRIDE;
+            const float* wb = s_w + cgi * 4;
+            for (int ci = 0; ci < cc; ++ci) {
+#pragma unroll
+                for (int dy = 0; dy < 3; ++dy) {
+                    float v[IN_SPAN];
+#pragma unroll
+                    for (int j = 0; j < IN_SPAN; ++j) v[j] = ib[ci * plane + dy * Wp + j];
+#pragma unroll
+                    for (int dx = 0; dx < 3; ++dx) {
+                        const float4 w4 = *reinterpret_cast<const float4*>(wb + (ci * 9 + dy * 3 + dx) * ct);
+#pragma unroll
+                        for (int p = 0; p < P; ++p) {
+                            const float xv = v[p * STRIDE + dx];
+                            acc[it][0][p] = fmaf(xv, w4.x, acc[it][0][p]);
+                            acc[it][1][p] = fmaf(xv, w4.y, acc[it][1][p]);
+                            acc[it][2][p] = fmaf(xv, w4.z, acc[it][2][p]);
+                            acc[it][3][p] = fmaf(xv, w4.w, acc[it][3][p]);
+                        }
+                    }
+                }
+            }
+        }
+    }
+    // ---- epilogue
+#pragma unroll
+    for (int it = 0; it < MAX_ITEMS; ++it) {
+        const int item = threadIdx.x + it * blockDim.x;
+        if (item >= total_items) break;
+        const int cgi = item % cgs;
+        const int rest = item / cgs;
+        const int seg = rest % segs, y = (rest / segs) % a.Ho, b = rest / (segs * a.Ho);
+        const int g = b0 + b;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const int co = cout0 + cgi * 4 + c;
+            const float bias = a.bias ? a.bias[co] : 0.0f;
+            const size_t o = (((size_t)g * a.Cout + co) * a.Ho + y) * a.Wo + seg * P;
+#pragma unroll
+            for (int p = 0; p < P; ++p) {
+                float r = acc[it][c][p] + bias;
+                if (a.residual) r += a.residual[o + p];
+                if (a.relu) r = fmaxf(r, 0.0f);
+                a.out[o + p] = r;
+            }
+        }
+    }
 }
+
+// ------------------------------------------------------------------------------------------
+// AvgPool2d(kernel 3, stride 2, padding 1), count_include_pad (always / 9)   models.py:258,262
+// ------------------------------------------------------------------------------------------
+__global__ void avgpool3x3s2_kernel(const float* in, float* out, int planes, int H, int W, int Ho, int Wo) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (size_t)planes * Ho * Wo) return;
+    const int x = i % Wo, y = (i / Wo) % Ho;
+    const size_t pl = i / ((size_t)Wo * Ho);
+    const float* p = in + pl * H * W;
+    float s = 0.0f;
+    for (int dy = -1; dy <= 1; ++dy)
+        for (int dx = -1; dx <= 1; ++dx) {
+            const int yy = 2 * y + dy, xx = 2 * x + dx;
+            if (yy >= 0 && yy < H && xx >= 0 && xx < W) s += p[yy * W + xx];
+        }
+    out[i] = __fdiv_rn(s, 9.0f);
+}
+
+// ------------------------------------------------------------------------------------------
+// Heads: conv1x1(+bias) -> flatten (c,h,w) -> MLP -> logits (-> support_to_scalar), plus the
+// per-(sample, channel) min-max rescale of the state (models.py:530-553).  One CTA per sample.
+// ------------------------------------------------------------------------------------------
+struct HeadDesc {
+    int rc;                    // reduced channels
+    int w1_off, b1_off;        // conv1x1 weight [rc][C], bias [rc]
+    MlpDesc mlp;               // transposed layers in the same blob
+    int n_out;                 // logits
+};
+
+struct HeadsArgs {
+    const float* x;            // [n, C, HW] input state (raw trunk output)
+    const float* blob;
+    int n, C, HW, S;
+    int n_heads;
+    HeadDesc head[2];
+    float* logits[2];          // [n, n_out] or nullptr
+    float* scalar[2];          // [n] support_to_scalar or nullptr
+    // optional rescale of x into the hidden pool / a plain buffer
+    float* rescaled;           // [n, C*HW] or nullptr
+    float* pool_hidden;        // pool mode target
+    int pool_stride, out_slot;
+    int smem_floats;
+};
+
+__global__ void __launch_bounds__(128) heads_kernel(const __grid_constant__ HeadsArgs a) {
+    extern __shared__ __align__(16) float sm[];
+    const int g = blockIdx.x;
+    const int C = a.C, HW = a.HW;
+    float* s_x = sm;                              // [C*HW]
+    float* s_a = s_x + C * HW;                    // activations ping
+    float* s_b = s_a + a.smem_floats;             // activations pong
+    const float* x = a.x + (size_t)g * C * HW;
+    for (int i = threadIdx.x; i < C * HW; i += blockDim.x) s_x[i] = x[i];
+    __syncthreads();
+
+    if (a.rescaled || a.pool_hidden) {
+        // one warp per channel: min / max over HW, then (x - min) / scale
+        const int warp = threadIdx.x / 32, lane = threadIdx.x % 32, nw = blockDim.x / 32;
+        for (int c = warp; c < C; c += nw) {
+            float lo = INFINITY, hi = -INFINITY;
+            for (int i = lane; i < HW; i += 32) { lo = fminf(lo, s_x[c * HW + i]); hi = fmaxf(hi, s_x[c * HW + i]); }
+            lo = -group_max_f32<32>(-lo);
+            hi = group_max_f32<32>(hi);
+            float sc = __fsub_rn(hi, lo);
+            if (sc < 1e-5f) sc = __fadd_rn(sc, 1e-5f);
+            for (int i = lane; i < HW; i += 32) {
+                const float v = __fdiv_rn(__fsub_rn(s_x[c * HW + i], lo), sc);
+                if (a.rescaled) a.rescaled[(size_t)g * C * HW + c * HW + i] = v;
+                if (a.pool_hidden) a.pool_hidden[((size_t)g * a.pool_stride + a.out_slot) * C * HW + c * HW + i] = v;
+            }
+        }
+    }
+
+    for (int h = 0; h < a.n_heads; ++h) {
+        const HeadDesc& d = a.head[h];
+        __syncthreads();
+        // conv1x1: r[c][p] = b[c] + sum_k W[c][k] x[k][p]
+        for (int i = threadIdx.x; i < d.rc * HW; i += blockDim.x) {
+            const int c = i / HW, p = i % HW;
+            float acc = a.blob[d.b1_off + c];
+            const float* w = a.blob + d.w1_off + c * C;
+            for (int k = 0; k < C; ++k) acc = fmaf(w[k], s_x[k * HW + p], acc);
+            s_a[i] = acc;                         // flatten order (c, h, w) = NCHW view(-1, ...)
+        }
+        __syncthreads();
+        float* cur = s_a;
+        float* nxt = s_b;
+        for (int l = 0; l < d.mlp.n; ++l) {
+            const int in = d.mlp.in[l], out = d.mlp.out[l];
+            const float* W = a.blob + d.mlp.w_off[l];
+            const float* b = a.blob + d.mlp.b_off[l];
+            const bool last = l == d.mlp.n - 1;
+            for (int o = threadIdx.x; o < out; o += blockDim.x) {
+                float acc = b[o];
+                for (int i = 0; i < in; ++i) acc = fmaf(cur[i], W[(size_t)i * out + o], acc);
+                nxt[o] = last ? acc : elu1(acc);
+            }
+            __syncthreads();
+            float* t = cur; cur = nxt; nxt = t;
+        }
+        if (a.logits[h])
+            for (int o = threadIdx.x; o < d.n_out; o += blockDim.x) a.logits[h][(size_t)g * d.n_out + o] = cur[o];
+        if (a.scalar[h] && threadIdx.x < 32) {
+            const float v = support_to_scalar_group<32>(cur, a.S);
+            if (threadIdx.x == 0) a.scalar[h][g] = v;
+        }
+    }
+}
+
+__global__ void fill_root_reward_logits_kernel(float* out, int n, int F, int S) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n * F) out[i] = (i % F == S) ? 0.0f : -INFINITY;
+}
+__global__ void fill_root_reward_kernel(float* out, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = inverse_value_transform(0.0f);
+}
+__global__ void copy_from_pool_kernel(const float* pool, float* out, int n, int pool_stride, int slot, int elems) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (size_t)n * elems) return;
+    const size_t g = i / elems, e = i % elems;
+    out[i] = pool[(g * pool_stride + slot) * elems + e];
+}
+
+// ------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------
+struct ConvLayer {
+    int cin, cout, stride;
+    size_t w_off;             // into the conv blob: [cin][9][cout]
+    long b_off;               // folded BN bias [cout], -1 = none
+};
+
+struct ResNetDevice {
+    MzNetDesc net;
+    int max_batch, sm_count;
+    int C, hh, hw;            // hidden state geometry
+    // layers in execution order
+    std::vector<ConvLayer> rep_down;   // conv1, rb1 x2 (2 convs each), conv2, rb2 x3, rb3 x3   (downsample only)
+    std::vector<ConvLayer> rep_trunk;  // [stem conv if no downsample] + blocks x 2
+    std::vector<ConvLayer> dyn;        // conv + blocks x 2
+    std::vector<ConvLayer> pred;       // blocks x 2
+    HeadDesc reward_head, value_head, policy_head;
+    float* d_conv = nullptr;           // conv weights + biases
+    float* d_head = nullptr;           // head blob
+    float* ws[3] = {nullptr, nullptr, nullptr};
+    size_t ws_elems = 0;
+    float* scratch_hidden = nullptr;   // [B, C*hh*hw] rescaled state when no pool is given
+    bool loaded = false;
+};
+
+static int conv_out(int h, int stride) { return (h - 1) / stride + 1; }
+
+ResNetDevice* resnet_create(const MzNetDesc& net, int max_batch, int sm_count, std::string* err) {
+    ResNetDevice* r = new ResNetDevice();
+    r->net = net; r->max_batch = max_batch; r->sm_count = sm_count;
+    r->C = net.channels;
+    if (net.channels % 4 != 0 || (net.downsample && (net.channels / 2) % 4 != 0)) {
+        *err = "channels must be a multiple of 4 (8 with downsample)";
+        delete r; return nullptr;
+    }
+    int H = net.obs_h, W = net.obs_w;
+    size_t max_elems = (size_t)net.obs_c * H * W;
+    if (net.downsample) {
+        int h1 = conv_out(H, 2), w1 = conv_out(W, 2);
+        int h2 = conv_out(h1, 2), w2 = conv_out(w1, 2);
+        int h3 = conv_out(h2, 2), w3 = conv_out(w2, 2);
+        int h4 = conv_out(h3, 2), w4 = conv_out(w3, 2);
+        max_elems = std::max(max_elems, (size_t)(net.channels / 2) * h1 * w1);
+        max_elems = std::max(max_elems, (size_t)net.channels * h2 * w2);
+        r->hh = h4; r->hw = w4;
+        if (h4 != (H + 15) / 16 || w4 != (W + 15) / 16) {
+            *err = "downsample geometry does not match ceil(H/16) x ceil(W/16) (models.py:456-484)";
+            delete r; return nullptr;
+        }
+    } else {
+        r->hh = H; r->hw = W;
+        max_elems = std::max(max_elems, (size_t)net.channels * H * W);
+    }
+    max_elems = std::max(max_elems, (size_t)(net.channels + 1) * r->hh * r->hw);
+    r->ws_elems = max_elems * (size_t)max_batch;
+    for (int i = 0; i < 3; ++i)
+        if (cudaMalloc(&r->ws[i], r->ws_elems * 4 + 64) != cudaSuccess) { *err = "workspace allocation failed"; resnet_destroy(r); return nullptr; }
+    if (cudaMalloc(&r->scratch_hidden, (size_t)max_batch * r->C * r->hh * r->hw * 4 + 64) != cudaSuccess) {
+        *err = "workspace allocation failed"; resnet_destroy(r); return nullptr;
+    }
+    return r;
+}
+
+void resnet_destroy(ResNetDevice* r) {
+    if (!r) return;
+    for (int i = 0; i < 3; ++i) if (r->ws[i]) cudaFree(r->ws[i]);
+    if (r->scratch_hidden) cudaFree(r->scratch_hidden);
+    if (r->d_conv) cudaFree(r->d_conv);
+    if (r->d_head) cudaFree(r->d_head);
+    delete r;
+}
+
+namespace {
+struct Loader {
+    const MzTensor* t; int n; std::string* err; bool ok = true;
+    const MzTensor* get(const std::string& name, int64_t numel) {
+        for (int i = 0; i < n; ++i)
+            if (t[i].name && name == t[i].name) {
+                if (t[i].numel != numel) { ok = false; *err = "shape mismatch for " + name; return nullptr; }
+                return &t[i];
+            }
+        ok = false; *err = "missing tensor " + name;
+        return nullptr;
+    }
+};
+
+// conv3x3 [cout][cin][3][3] (+ optional BN prefix) -> [cin][9][cout] with the BN scale folded in
+bool pack_conv(Loader& L, const std::string& conv, const std::string& bn, int cin, int cout, int stride,
+               std::vector<float>& blob, std::vector<ConvLayer>& layers) {
+    const MzTensor* w = L.get(conv + ".weight", (int64_t)cout * cin * 9);
+    if (!w) return false;
+    std::vector<double> scale(cout, 1.0), shift(cout, 0.0);
+    if (!bn.empty()) {
+        const MzTensor* g = L.get(bn + ".weight", cout);
+        const MzTensor* b = L.get(bn + ".bias", cout);
+        const MzTensor* m = L.get(bn + ".running_mean", cout);
+        const MzTensor* v = L.get(bn + ".running_var", cout);
+        if (!g || !b || !m || !v) return false;
+        for (int c = 0; c < cout; ++c) {
+            scale[c] = (double)g->data[c] / sqrt((double)v->data[c] + 1e-5);
+            shift[c] = (double)b->data[c] - (double)m->data[c] * scale[c];
+        }
+    }
+    ConvLayer l;
+    l.cin = cin; l.cout = cout; l.stride = stride;
+    l.w_off = blob.size();
+    blob.resize(blob.size() + (size_t)cin * 9 * cout);
+    float* dst = blob.data() + l.w_off;
+    for (int co = 0; co < cout; ++co)
+        for (int ci = 0; ci < cin; ++ci)
+            for (int tap = 0; tap < 9; ++tap)
+                dst[((size_t)ci * 9 + tap) * cout + co] = (float)((double)w->data[((size_t)co * cin + ci) * 9 + tap] * scale[co]);
+    if (!bn.empty()) {
+        l.b_off = (long)blob.size();
+        for (int c = 0; c < cout; ++c) blob.push_back((float)shift[c]);
+    } else {
+        l.b_off = -1;
+    }
+    while (blob.size() % 4) blob.push_back(0.0f);           // keep every layer 16-byte aligned
+    layers.push_back(l);
+    return true;
+}
+
+bool pack_resblock(Loader& L, const std::string& p, int ch, std::vector<float>& blob, std::vector<ConvLayer>& layers) {
+    return pack_conv(L, p + ".conv1", p + ".bn1", ch, ch, 1, blob, layers) &&
+           pack_conv(L, p + ".conv2", p + ".bn2", ch, ch, 1, blob, layers);
+}
+
+bool pack_head(Loader& L, const std::string& conv, const std::string& fc, int C, int rc, int HW, const int32_t* hidden,
+               int n_hidden, int n_out, std::vector<float>& blob, HeadDesc& d) {
+    const MzTensor* w = L.get(conv + ".weight", (int64_t)rc * C);
+    const MzTensor* b = L.get(conv + ".bias", rc);
+    if (!w || !b) return false;
+    d.rc = rc; d.n_out = n_out;
+    d.w1_off = (int)blob.size(); blob.insert(blob.end(), w->data, w->data + (size_t)rc * C);
+    d.b1_off = (int)blob.size(); blob.insert(blob.end(), b->data, b->data + rc);
+    std::vector<int> sz;
+    sz.push_back(rc * HW);
+    for (int i = 0; i < n_hidden; ++i) sz.push_back(hidden[i]);
+    sz.push_back(n_out);
+    d.mlp.n = (int)sz.size() - 1;
+    for (int l = 0; l < d.mlp.n; ++l) {
+        const int in = sz[l], out = sz[l + 1];
+        const MzTensor* lw = L.get(fc + "." + std::to_string(2 * l) + ".weight", (int64_t)in * out);
+        const MzTensor* lb = L.get(fc + "." + std::to_string(2 * l) + ".bias", out);
+        if (!lw || !lb) return false;
+        d.mlp.in[l] = in; d.mlp.out[l] = out;
+        d.mlp.w_off[l] = (int)blob.size();
+        blob.resize(blob.size() + (size_t)in * out);
+        float* dst = blob.data() + d.mlp.w_off[l];
+        for (int o = 0; o < out; ++o)
+            for (int i = 0; i < in; ++i) dst[(size_t)i * out + o] = lw->data[(size_t)o * in + i];
+        d.mlp.b_off[l] = (int)blob.size();
+        blob.insert(blob.end(), lb->data, lb->data + out);
+    }
+    return true;
+}
+}  // namespace
+
+int resnet_load_weights(ResNetDevice* r, const MzTensor* tensors, int n, std::string* err) {
+    const MzNetDesc& nd = r->net;
+    const int C = nd.channels, HW = r->hh * r->hw, F = 2 * nd.support_size + 1;
+    Loader L{tensors, n, err};
+    std::vector<float> conv, head;
+    r->rep_down.clear(); r->rep_trunk.clear(); r->dyn.clear(); r->pred.clear();
+    const std::string rp = "representation_network.module";
+    bool ok = true;
+    if (nd.downsample) {
+        const std::string dp = rp + ".downsample_net";
+        ok = ok && pack_conv(L, dp + ".conv1", "", nd.obs_c, C / 2, 2, conv, r->rep_down);
+        for (int i = 0; ok && i < 2; ++i) ok = pack_resblock(L, dp + ".resblocks1." + std::to_string(i), C / 2, conv, r->rep_down);
+        ok = ok && pack_conv(L, dp + ".conv2", "", C / 2, C, 2, conv, r->rep_down);
+        for (int i = 0; ok && i < 3; ++i) ok = pack_resblock(L, dp + ".resblocks2." + std::to_string(i), C, conv, r->rep_down);
+        for (int i = 0; ok && i < 3; ++i) ok = pack_resblock(L, dp + ".resblocks3." + std::to_string(i), C, conv, r->rep_down);
+    } else {
+        ok = ok && pack_conv(L, rp + ".conv", rp + ".bn", nd.obs_c, C, 1, conv, r->rep_trunk);
+    }
+    for (int i = 0; ok && i < nd.blocks; ++i) ok = pack_resblock(L, rp + ".resblocks." + std::to_string(i), C, conv, r->rep_trunk);
+    const std::string dp = "dynamics_network.module";
+    ok = ok && pack_conv(L, dp + ".conv", dp + ".bn", C + 1, C, 1, conv, r->dyn);
+    for (int i = 0; ok && i < nd.blocks; ++i) ok = pack_resblock(L, dp + ".resblocks." + std::to_string(i), C, conv, r->dyn);
+    const std::string pp = "prediction_network.module";
+    for (int i = 0; ok && i < nd.blocks; ++i) ok = pack_resblock(L, pp + ".resblocks." + std::to_string(i), C, conv, r->pred);
+    ok = ok && pack_head(L, dp + ".conv1x1_reward", dp + ".fc", C, nd.reduced_reward, HW, nd.res_fc_reward, nd.n_res_fc_reward, F, head, r->reward_head);
+    ok = ok && pack_head(L, pp + ".conv1x1_value", pp + ".fc_value", C, nd.reduced_value, HW, nd.res_fc_value, nd.n_res_fc_value, F, head, r->value_head);
+    ok = ok && pack_head(L, pp + ".conv1x1_policy", pp + ".fc_policy", C, nd.reduced_policy, HW, nd.res_fc_policy, nd.n_res_fc_policy, nd.action_space, head, r->policy_head);
+    if (!ok || !L.ok) return MZ_EINVAL;
+    if (r->d_conv) cudaFree(r->d_conv);
+    if (r->d_head) cudaFree(r->d_head);
+    r->d_conv = r->d_head = nullptr;
+    if (cudaMalloc(&r->d_conv, conv.size() * 4 + 64) != cudaSuccess || cudaMalloc(&r->d_head, head.size() * 4 + 64) != cudaSuccess) {
+        *err = "weight allocation failed"; return MZ_ENOMEM;
+    }
+    cudaMemcpy(r->d_conv, conv.data(), conv.size() * 4, cudaMemcpyHostToDevice);
+    cudaMemcpy(r->d_head, head.data(), head.size() * 4, cudaMemcpyHostToDevice);
+    r->loaded = true;
+    return MZ_OK;
+}
+
+namespace {
+struct Runner {
+    ResNetDevice* r; cudaStream_t stream; int64_t* launches; std::string* err; int n;
+    bool fail(const char* what, cudaError_t e) { *err = std::string(what) + ": " + cudaGetErrorString(e); return false; }
+
+    // conv: in -> out. `in` may be gathered from the pool; action adds the constant plane.
+    bool conv(const ConvLayer& l, const float* in, float* out, const float* residual, bool relu, int Hin, int Win,
+              const int32_t* gather_parent = nullptr, int pool_stride = 0, const int32_t* action = nullptr) {
+        ConvArgs a{};
+        a.in = in; a.out = out; a.residual = residual; a.w = r->d_conv + l.w_off;
+        a.bias = l.b_off >= 0 ? r->d_conv + l.b_off : nullptr;
+        a.gather_parent = gather_parent; a.pool_stride = pool_stride; a.action = action;
+        a.n = n; a.Cin = l.cin; a.Cout = l.cout; a.Hin = Hin; a.Win = Win; a.stride = l.stride;
+        a.Ho = conv_out(Hin, l.stride); a.Wo = conv_out(Win, l.stride); a.relu = relu; a.A = r->net.action_space;
+        int P = 1;
+        for (int cand : {8, 7, 6, 4, 3, 2}) if (a.Wo % cand == 0) { P = cand; break; }
+        const int ct = l.cout < 64 ? l.cout : 64;
+        const int items_per_board = (ct / 4) * a.Ho * (a.Wo / P);
+        const int threads = 256;
+        int boards = 1;
+        if (items_per_board < threads) boards = threads / items_per_board;
+        if (boards > 32) boards = 32;
+        if (boards > n) boards = n;
+        if (items_per_board * boards > threads * 4) { *err = "conv3x3: image too large for the item budget"; return false; }
+        const size_t plane = (size_t)(Hin + 2) * (Win + 2);
+        // pick the cin chunk so weights + planes fit comfortably
+        const size_t budget = 200 * 1024 / 4;
+        int chunk = l.cin;
+        while (chunk > 1 && (size_t)chunk * 9 * ct + (size_t)boards * chunk * plane > budget) chunk = (chunk + 1) / 2;
+        if ((size_t)chunk * 9 * ct + (size_t)boards * chunk * plane > budget) { *err = "conv3x3: tile does not fit in shared memory"; return false; }
+        a.boards_per_cta = boards; a.cin_chunk = chunk;
+        const size_t smem = ((size_t)chunk * 9 * ct + (size_t)boards * chunk * plane) * 4;
+        dim3 grid((n + boards - 1) / boards, l.cout / ct);
+        const bool multi = items_per_board * boards > threads;
+#define MZ_CONV(PP, SS)                                                                                         \
+        if (P == PP && l.stride == SS) {                                                                        \
+            auto kern = multi ? conv3x3_kernel<PP, SS, 4> : conv3x3_kernel<PP, SS, 1>;                          \
+            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+            if (e != cudaSuccess) return fail("conv attr", e);                                                  \
+            kern<<<grid, threads, smem, stream>>>(a);                                                           \
+        }
+        MZ_CONV(8, 1) MZ_CONV(7, 1) MZ_CONV(6, 1) MZ_CONV(4, 1) MZ_CONV(3, 1) MZ_CONV(2, 1) MZ_CONV(1, 1)
+        MZ_CONV(8, 2) MZ_CONV(6, 2) MZ_CONV(4, 2) MZ_CONV(3, 2) MZ_CONV(2, 2) MZ_CONV(1, 2) MZ_CONV(7, 2)
+#undef MZ_CONV
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return fail("conv3x3 launch", e);
+        *launches += 1;
+        return true;
+    }
+
+    // residual tower: layers[2k], layers[2k+1] are one block; x ends up in `*cur`
+    bool blocks(const std::vector<ConvLayer>& layers, size_t first, size_t count, float** cur, float** tmp, float** spare, int H, int W) {
+        for (size_t b = 0; b < count; ++b) {
+            if (!conv(layers[first + 2 * b], *cur, *tmp, nullptr, true, H, W)) return false;
+            if (!conv(layers[first + 2 * b + 1], *tmp, *spare, *cur, true, H, W)) return false;
+            float* t = *cur; *cur = *spare; *spare = t;
+        }
+        return true;
+    }
+
+    bool heads(const float* x, int n_heads, const HeadDesc* h0, const HeadDesc* h1, float* l0, float* l1, float* s0, float* s1,
+               float* rescaled, float* pool_hidden, int pool_stride, int out_slot) {
+        HeadsArgs a{};
+        a.x = x; a.blob = r->d_head; a.n = n; a.C = r->C; a.HW = r->hh * r->hw; a.S = r->net.support_size;
+        a.n_heads = n_heads;
+        int maxw = 32;
+        const HeadDesc* hs[2] = {h0, h1};
+        for (int i = 0; i < n_heads; ++i) {
+            a.head[i] = *hs[i];
+            maxw = std::max(maxw, hs[i]->rc * a.HW);
+            for (int l = 0; l < hs[i]->mlp.n; ++l) maxw = std::max(maxw, hs[i]->mlp.out[l]);
+        }
+        a.logits[0] = l0; a.logits[1] = l1; a.scalar[0] = s0; a.scalar[1] = s1;
+        a.rescaled = rescaled; a.pool_hidden = pool_hidden; a.pool_stride = pool_stride; a.out_slot = out_slot;
+        a.smem_floats = (maxw + 3) & ~3;
+        const size_t smem = ((size_t)a.C * a.HW + 2 * a.smem_floats) * 4;
+        cudaError_t e = cudaFuncSetAttribute(heads_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return fail("heads attr", e);
+        heads_kernel<<<n, 128, smem, stream>>>(a);
+        e = cudaGetLastError();
+        if (e != cudaSuccess) return fail("heads launch", e);
+        *launches += 1;
+        return true;
+    }
+};
+}  // namespace
+
+int resnet_inference(ResNetDevice* r, const InferCall& c, cudaStream_t stream, int64_t* launches, std::string* err) {
+    if (!r->loaded) { *err = "weights not loaded"; return MZ_ESTATE; }
+    if (c.n > r->max_batch) { *err = "batch larger than max_games"; return MZ_EINVAL; }
+    const MzNetDesc& nd = r->net;
+    const int n = c.n, C = r->C, hh = r->hh, hw = r->hw, F = 2 * nd.support_size + 1;
+    Runner R{r, stream, launches, err, n};
+    float *cur = r->ws[0], *tmp = r->ws[1], *spare = r->ws[2];
+    float* hidden_out = c.hidden ? c.hidden : r->scratch_hidden;
+
+    if (!c.recurrent) {
+        int H = nd.obs_h, W = nd.obs_w;
+        if (nd.downsample) {
+            const auto& d = r->rep_down;
+            if (!R.conv(d[0], c.in, cur, nullptr, false, H, W)) return MZ_ECUDA;
+            H = conv_out(H, 2); W = conv_out(W, 2);
+            if (!R.blocks(d, 1, 2, &cur, &tmp, &spare, H, W)) return MZ_ECUDA;
+            if (!R.conv(d[5], cur, tmp, nullptr, false, H, W)) return MZ_ECUDA;
+            { float* t = cur; cur = tmp; tmp = t; }
+            H = conv_out(H, 2); W = conv_out(W, 2);
+            if (!R.blocks(d, 6, 3, &cur, &tmp, &spare, H, W)) return MZ_ECUDA;
+            for (int pool = 0; pool < 2; ++pool) {
+                const int Ho = conv_out(H, 2), Wo = conv_out(W, 2);
+                const size_t total = (size_t)n * C * Ho * Wo;
+                avgpool3x3s2_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(cur, tmp, n * C, H, W, Ho, Wo);
+                *launches += 1;
+                { float* t = cur; cur = tmp; tmp = t; }
+                H = Ho; W = Wo;
+                if (pool == 0 && !R.blocks(d, 12, 3, &cur, &tmp, &spare, H, W)) return MZ_ECUDA;
+            }
+            if (!R.blocks(r->rep_trunk, 0, nd.blocks, &cur, &tmp, &spare, H, W)) return MZ_ECUDA;
+        } else {
+            if (!R.conv(r->rep_trunk[0], c.in, cur, nullptr, true, H, W)) return MZ_ECUDA;
+            if (!R.blocks(r->rep_trunk, 1, nd.blocks, &cur, &tmp, &spare, H, W)) return MZ_ECUDA;
+        }
+        // rescale -> hidden (no heads on the raw state at the root)
+        if (!R.heads(cur, 0, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, hidden_out, c.pool_hidden, c.pool_stride, c.out_slot))
+            return MZ_ECUDA;
+        if (c.reward_logits) {
+            fill_root_reward_logits_kernel<<<(n * F + 255) / 256, 256, 0, stream>>>(c.reward_logits, n, F, nd.support_size);
+            *launches += 1;
+        }
+        if (c.reward) {
+            fill_root_reward_kernel<<<(n + 255) / 256, 256, 0, stream>>>(c.reward, n);
+            *launches += 1;
+        }
+    } else {
+        const float* in = c.gather_parent ? c.pool_hidden : c.in;
+        if (!R.conv(r->dyn[0], in, cur, nullptr, true, hh, hw, c.gather_parent, c.pool_stride, c.action)) return MZ_ECUDA;
+        if (!R.blocks(r->dyn, 1, nd.blocks, &cur, &tmp, &spare, hh, hw)) return MZ_ECUDA;
+        // reward head on the raw state + rescale -> hidden
+        if (!R.heads(cur, 1, &r->reward_head, nullptr, c.reward_logits, nullptr, c.reward, nullptr, hidden_out, c.pool_hidden,
+                     c.pool_stride, c.out_slot))
+            return MZ_ECUDA;
+    }
+    // prediction on the rescaled state
+    {
+        float* x = hidden_out;
+        // the tower must not overwrite the hidden state: first conv reads it, writes workspace
+        float *pc = cur, *pt = tmp, *ps = spare;
+        if (nd.blocks > 0) {
+            if (!R.conv(r->pred[0], x, pt, nullptr, true, hh, hw)) return MZ_ECUDA;
+            if (!R.conv(r->pred[1], pt, ps, x, true, hh, hw)) return MZ_ECUDA;
+            { float* t = pc; pc = ps; ps = t; }
+            if (!R.blocks(r->pred, 2, nd.blocks - 1, &pc, &pt, &ps, hh, hw)) return MZ_ECUDA;
+            x = pc;
+        }
+        if (!R.heads(x, 2, &r->value_head, &r->policy_head, c.value_logits, c.policy_logits, c.value, nullptr, nullptr, nullptr, 0, 0))
+            return MZ_ECUDA;
+    }
+    return MZ_OK;
+}
+
+}  // namespace mz

@@ -205,3 +205,37 @@ def test_full_size_invariants(game_configs):
                    game_id=numpy.arange(n)[::-1].astype(numpy.int64))
     assert (c.visit_counts[::-1] == a.visit_counts).all() and (c.root_value[::-1] == a.root_value).all()
     eng.close()
+
+
+@pytest.mark.parametrize("stepwise", [False, True])
+@pytest.mark.parametrize("game,n,N", [("cartpole", 4096, 50), ("tictactoe", 2048, 50), ("connect4", 1024, 200)])
+def test_teacher_forced_full_size_vs_c_oracle(game, n, N, stepwise, game_configs):
+    """BASELINE-sized batches, injected outputs: every game's visit counts, root value, depth,
+    tie count, value range and every selected path equal the C oracle's, bit for bit."""
+    from oracle import build_c
+    cfg = game_configs[game]
+    A, P = len(cfg.action_space), len(cfg.players)
+    rs = numpy.random.RandomState(99)
+    legal = (rs.uniform(size=(n, A)) < 0.8).astype(numpy.uint8)
+    legal[numpy.arange(n), rs.randint(0, A, n)] = 1
+    t = random_teacher(rs, n, N, A, reward_scale=1.0 if P == 1 else 0.0, legal=legal)
+    noise = rs.dirichlet([cfg.root_dirichlet_alpha] * A, size=n)
+    to_play = rs.randint(0, P, n).astype(numpy.int32)
+    gid = rs.randint(0, 1 << 40, n).astype(numpy.int64)
+    mv = rs.randint(0, 400, n).astype(numpy.int32)
+    D = 64
+    ref = build_c.tree_search(n, N, A, P, cfg.discount, cfg.pb_c_base, cfg.pb_c_init, cfg.root_exploration_fraction,
+                              legal, to_play, noise, None, cfg.seed, gid, mv, t, D=D)
+    eng = _engine(cfg, n, N)
+    out = eng.search(legal_mask=legal, to_play=to_play, add_exploration_noise=True, noise=noise, game_id=gid,
+                     move_index=mv, teacher=t, trace=True, trace_depth=D, stepwise=stepwise, n_games=n)
+    assert (out.visit_counts == ref["visit_counts"]).all()
+    assert (out.root_value == ref["root_value"]).all()
+    assert (out.max_tree_depth == ref["max_depth"]).all()
+    assert (out.tie_count == ref["ties"]).all()
+    assert (out.value_range == ref["range"]).all()
+    assert (out.trace["depth"] == ref["depth"]).all()
+    assert ref["max_depth"].max() <= D
+    mask = numpy.arange(D)[None, None, :] < ref["depth"][:, :, None]
+    assert (numpy.where(mask, out.trace["actions"], 0) == numpy.where(mask, ref["actions"], 0)).all()
+    eng.close()
