@@ -41,6 +41,7 @@ struct MzHandle {
     float* d_fc_blob = nullptr;
     bool weights_loaded = false;
     int fc_group = 16;
+    int fc_threads = 64;
     // residual weights + workspace
     ResNetDevice* res = nullptr;
     // pool
@@ -203,6 +204,9 @@ extern "C" int mz_create(const MzNetDesc* net, const MzSearchDesc* search, int d
         if (g < 16) g = 16;
         h->fc_group = g;
     }
+    const char* tenv = getenv("MZ_FC_THREADS");
+    if (tenv) h->fc_threads = atoi(tenv);
+    if (h->fc_threads < 32 || h->fc_threads > kFcMaxThreads || h->fc_threads % 32) h->fc_threads = 64;
     if (h->fc_group < A || (h->fc_group != 4 && h->fc_group != 8 && h->fc_group != 16 && h->fc_group != 32)) {
         fail(nullptr, MZ_EINVAL, "mz_create: MZ_FC_GROUP must be 4, 8, 16 or 32 and >= action_space");
         mz_destroy(h);
@@ -250,9 +254,10 @@ static const MzTensor* find_tensor(const MzTensor* t, int n, const std::string& 
     return nullptr;
 }
 
-// Appends one mlp (models.py:630-642) to the blob: per Linear W^T [in][out] then bias.
+// Appends one mlp (models.py:630-642) to the blob: per Linear the weights packed [i/4][out][i%4]
+// (zero padded), the bias, and - for the first dynamics layer - the one-hot rows [A][out].
 static int pack_mlp(MzHandle* h, const MzTensor* t, int n, const std::string& prefix, const std::vector<int>& sizes,
-                    MlpDesc& d, std::vector<float>& blob) {
+                    MlpDesc& d, std::vector<float>& blob, int onehot_rows) {
     d.n = (int)sizes.size() - 1;
     for (int l = 0; l < d.n; ++l) {
         const int in = sizes[l], out = sizes[l + 1];
@@ -261,14 +266,24 @@ static int pack_mlp(MzHandle* h, const MzTensor* t, int n, const std::string& pr
         if (!w || !b) return fail(h, MZ_EINVAL, "mz_load_weights: missing tensor " + prefix + "." + std::to_string(2 * l));
         if (w->numel != (int64_t)in * out || b->numel != out)
             return fail(h, MZ_EINVAL, "mz_load_weights: shape mismatch for " + prefix + "." + std::to_string(2 * l));
-        d.in[l] = in; d.out[l] = out;
+        const int extra = (l == 0) ? onehot_rows : 0;
+        const int dense = in - extra, in4 = (dense + 3) / 4;
+        d.in[l] = in; d.out[l] = out; d.in_dense[l] = dense;
+        while (blob.size() % 4) blob.push_back(0.0f);
         d.w_off[l] = (int)blob.size();
-        blob.resize(blob.size() + (size_t)in * out);
+        blob.resize(blob.size() + (size_t)in4 * out * 4, 0.0f);
         float* dst = blob.data() + d.w_off[l];
         for (int o = 0; o < out; ++o)
-            for (int i = 0; i < in; ++i) dst[(size_t)i * out + o] = w->data[(size_t)o * in + i];   // torch Linear: [out][in]
+            for (int i = 0; i < dense; ++i)
+                dst[((size_t)(i / 4) * out + o) * 4 + (i % 4)] = w->data[(size_t)o * in + i];     // torch Linear: [out][in]
         d.b_off[l] = (int)blob.size();
         blob.insert(blob.end(), b->data, b->data + out);
+        d.x_off[l] = -1;
+        if (extra > 0) {
+            d.x_off[l] = (int)blob.size();
+            for (int a = 0; a < extra; ++a)
+                for (int o = 0; o < out; ++o) blob.push_back(w->data[(size_t)o * in + dense + a]);
+        }
     }
     return MZ_OK;
 }
@@ -281,19 +296,21 @@ static int load_fc_weights(MzHandle* h, const MzTensor* t, int n) {
     std::vector<int> sz;
     int rc;
     if (mlp_dims(nd.fc_representation, nd.n_fc_representation, (int)h->obs_elems, E, sz)) return fail(h, MZ_EINVAL, "bad layers");
-    if ((rc = pack_mlp(h, t, n, "representation_network.module", sz, fc.rep, blob))) return rc;
+    if ((rc = pack_mlp(h, t, n, "representation_network.module", sz, fc.rep, blob, 0))) return rc;
     if (mlp_dims(nd.fc_dynamics, nd.n_fc_dynamics, E + A, E, sz)) return fail(h, MZ_EINVAL, "bad layers");
-    if ((rc = pack_mlp(h, t, n, "dynamics_encoded_state_network.module", sz, fc.dyn, blob))) return rc;
+    if ((rc = pack_mlp(h, t, n, "dynamics_encoded_state_network.module", sz, fc.dyn, blob, A))) return rc;
     if (mlp_dims(nd.fc_reward, nd.n_fc_reward, E, F, sz)) return fail(h, MZ_EINVAL, "bad layers");
-    if ((rc = pack_mlp(h, t, n, "dynamics_reward_network.module", sz, fc.rew, blob))) return rc;
+    if ((rc = pack_mlp(h, t, n, "dynamics_reward_network.module", sz, fc.rew, blob, 0))) return rc;
     if (mlp_dims(nd.fc_value, nd.n_fc_value, E, F, sz)) return fail(h, MZ_EINVAL, "bad layers");
-    if ((rc = pack_mlp(h, t, n, "prediction_value_network.module", sz, fc.val, blob))) return rc;
+    if ((rc = pack_mlp(h, t, n, "prediction_value_network.module", sz, fc.val, blob, 0))) return rc;
     if (mlp_dims(nd.fc_policy, nd.n_fc_policy, E, A, sz)) return fail(h, MZ_EINVAL, "bad layers");
-    if ((rc = pack_mlp(h, t, n, "prediction_policy_network.module", sz, fc.pol, blob))) return rc;
+    if ((rc = pack_mlp(h, t, n, "prediction_policy_network.module", sz, fc.pol, blob, 0))) return rc;
     fc.blob_floats = (int)blob.size();
     fc.obs_elems = (int)h->obs_elems; fc.E = E; fc.A = A; fc.S = nd.support_size; fc.F = F;
     int maxw = E > F ? E : F;
     if (A > maxw) maxw = A;
+    if ((int)h->obs_elems > maxw) maxw = (int)h->obs_elems;
+    while (blob.size() % 4) blob.push_back(0.0f);
     const MlpDesc* all[] = {&fc.rep, &fc.dyn, &fc.rew, &fc.val, &fc.pol};
     for (const MlpDesc* d : all) for (int l = 0; l < d->n; ++l) if (d->out[l] > maxw) maxw = d->out[l];
     fc.maxw = (maxw + 3) & ~3;
@@ -449,7 +466,7 @@ extern "C" int mz_search(MzHandle* h, const MzSearchIO* io) {
     const bool fused = (h->net.kind == MZ_NET_FC || teacher) && !(io->flags & MZ_FLAG_STEPWISE);
     if (fused) {
         FcSearchArgs a{};
-        a.n_games = n; a.N = N; a.A = A; a.P = h->search.num_players;
+        a.n_games = n; a.N = N; a.A = A; a.P = h->search.num_players; a.threads = h->fc_threads;
         a.discount = h->search.discount; a.noise_frac = h->search.root_exploration_fraction; a.seed = h->search.seed;
         a.pbc = h->d_pbc; a.sqrtn = h->d_sqrt;
         a.net = h->fc; a.blob = h->d_fc_blob;
@@ -466,7 +483,7 @@ extern "C" int mz_search(MzHandle* h, const MzSearchIO* io) {
             // the tree does not fit in shared memory next to the weights: use the HBM node pool
             (void)cudaGetLastError();
             rc = run_stepwise_search(h->net, h->search, h->pool, h->d_pbc, h->d_sqrt, h->fc, h->d_fc_blob, h->res, call,
-                                     h->sm_count, h->stream, &h->launches, &h->err);
+                                     h->fc_group, h->sm_count, h->stream, &h->launches, &h->err);
             if (rc) return rc;
         } else if (e != cudaSuccess) {
             return fail(h, MZ_ECUDA, std::string("fc_search launch: ") + cudaGetErrorString(e));
@@ -475,7 +492,7 @@ extern "C" int mz_search(MzHandle* h, const MzSearchIO* io) {
         }
     } else {
         rc = run_stepwise_search(h->net, h->search, h->pool, h->d_pbc, h->d_sqrt, h->fc, h->d_fc_blob, h->res, call,
-                                 h->sm_count, h->stream, &h->launches, &h->err);
+                                 h->fc_group, h->sm_count, h->stream, &h->launches, &h->err);
         if (rc) return rc;
     }
     MZ_CUDA(h, cudaEventRecord(h->ev1, h->stream));
@@ -519,7 +536,7 @@ static int run_inference(MzHandle* h, int n, int mem, const float* in, const int
         a.n = n; a.recurrent = recurrent; a.net = h->fc; a.blob = h->d_fc_blob; a.in = c.in; a.action = c.action;
         a.value_logits = c.value_logits; a.reward_logits = c.reward_logits; a.policy_logits = c.policy_logits;
         a.hidden = c.hidden; a.value = c.value; a.reward = c.reward;
-        cudaError_t e = launch_fc_inference(a, h->sm_count, h->stream);
+        cudaError_t e = launch_fc_inference(a, h->fc_group, h->sm_count, h->stream);
         if (e != cudaSuccess) return fail(h, MZ_ECUDA, std::string("fc_inference launch: ") + cudaGetErrorString(e));
         h->launches += 1;
     } else {

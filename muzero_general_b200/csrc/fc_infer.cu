@@ -19,7 +19,7 @@ __global__ void __launch_bounds__(kFcThreads) fc_inference_kernel(const __grid_c
     const int lane = LaneGroup<G>::lane();
     const int E = a.net.E, A = a.net.A, F = a.net.F, S = a.net.S, maxw = a.net.maxw;
     float* base = s_blob + ((a.net.blob_floats + 3) & ~3) + (size_t)gi * (4 * maxw + 4);
-    float *s0 = base, *s1 = base + maxw, *s2 = base + 2 * maxw, *sh = base + 3 * maxw;
+    float *s0 = base, *s1 = base + maxw, *s2 = base + 2 * maxw, *sh = base + 3 * maxw;   // maxw % 4 == 0
 
     for (int g = blockIdx.x * groups_per_cta + gi; g < a.n; g += gridDim.x * groups_per_cta) {
         float reward = 0.0f;
@@ -28,14 +28,16 @@ __global__ void __launch_bounds__(kFcThreads) fc_inference_kernel(const __grid_c
             const float* hin = a.gather_parent
                 ? a.pool_hidden + ((size_t)g * a.pool_stride + a.gather_parent[g]) * E
                 : a.in + (size_t)g * E;
-            float* raw = mlp_forward<G>(a.net.dyn, s_blob, hin, s0, s1, s2, E, E + act);
+            load_vector<G>(hin, s1, E);
+            float* raw = mlp_forward<G>(a.net.dyn, s_blob, s1, s0, s1, s2, act);
             float* rl = mlp_forward<G>(a.net.rew, s_blob, raw, s0, s1, nullptr);
             if (a.reward_logits) for (int i = lane; i < F; i += G) a.reward_logits[(size_t)g * F + i] = rl[i];
             reward = support_to_scalar_group<G>(rl, S);
             LaneGroup<G>::sync();
             rescale_unit_range<G>(raw, sh, E);
         } else {
-            float* raw = mlp_forward<G>(a.net.rep, s_blob, a.in + (size_t)g * a.net.obs_elems, s0, s1, s2);
+            load_vector<G>(a.in + (size_t)g * a.net.obs_elems, s1, a.net.obs_elems);
+            float* raw = mlp_forward<G>(a.net.rep, s_blob, s1, s0, s1, s2);
             rescale_unit_range<G>(raw, sh, E);
             if (a.reward_logits)        // log(one-hot at the centre), models.py:176-183
                 for (int i = lane; i < F; i += G) a.reward_logits[(size_t)g * F + i] = (i == S) ? 0.0f : -INFINITY;
@@ -58,8 +60,8 @@ __global__ void __launch_bounds__(kFcThreads) fc_inference_kernel(const __grid_c
     }
 }
 
-cudaError_t launch_fc_inference(const FcInferArgs& a, int sm_count, cudaStream_t stream) {
-    constexpr int G = 32;
+template <int G>
+static cudaError_t launch_infer(const FcInferArgs& a, int sm_count, cudaStream_t stream) {
     const int groups = kFcThreads / G;
     const size_t smem = (((size_t)a.net.blob_floats + 3) & ~(size_t)3) * 4 + (size_t)groups * (4 * a.net.maxw + 4) * 4;
     auto kern = fc_inference_kernel<G>;
@@ -72,13 +74,25 @@ cudaError_t launch_fc_inference(const FcInferArgs& a, int sm_count, cudaStream_t
     return cudaGetLastError();
 }
 
-cudaError_t launch_fc_inference_pool(const FcNet& net, const float* blob, const InferCall& c, int sm_count, cudaStream_t stream) {
+// The lane-group width must equal the fused search kernel's: the fp32 reductions (softmax and
+// support sums) are shuffle trees over G lanes, so the same G gives bit-identical outputs.
+cudaError_t launch_fc_inference(const FcInferArgs& a, int group, int sm_count, cudaStream_t stream) {
+    switch (group) {
+        case 4: return launch_infer<4>(a, sm_count, stream);
+        case 8: return launch_infer<8>(a, sm_count, stream);
+        case 16: return launch_infer<16>(a, sm_count, stream);
+        case 32: return launch_infer<32>(a, sm_count, stream);
+    }
+    return cudaErrorInvalidValue;
+}
+
+cudaError_t launch_fc_inference_pool(const FcNet& net, const float* blob, const InferCall& c, int group, int sm_count, cudaStream_t stream) {
     FcInferArgs a{};
     a.n = c.n; a.recurrent = c.recurrent; a.net = net; a.blob = blob; a.in = c.in; a.action = c.action;
     a.gather_parent = c.gather_parent; a.pool_hidden = c.pool_hidden; a.pool_stride = c.pool_stride; a.out_slot = c.out_slot;
     a.value_logits = c.value_logits; a.reward_logits = c.reward_logits; a.policy_logits = c.policy_logits;
     a.hidden = c.hidden; a.value = c.value; a.reward = c.reward;
-    return launch_fc_inference(a, sm_count, stream);
+    return launch_fc_inference(a, group, sm_count, stream);
 }
 
 }  // namespace mz

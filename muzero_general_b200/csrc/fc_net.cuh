@@ -17,54 +17,83 @@ namespace mz {
 
 struct MlpDesc {
     int n;                               // number of Linear layers
-    int in[MZ_MAX_LAYERS + 1];
+    int in[MZ_MAX_LAYERS + 1];           // logical input width (for the dynamics net: dense part + |A|)
     int out[MZ_MAX_LAYERS + 1];
-    int w_off[MZ_MAX_LAYERS + 1];        // float offset of W^T [in][out] in the blob
+    int w_off[MZ_MAX_LAYERS + 1];        // float offset of the packed weights [ceil(in_dense/4)][out][4]
     int b_off[MZ_MAX_LAYERS + 1];        // float offset of bias [out]
+    int in_dense[MZ_MAX_LAYERS + 1];     // rows that multiply the activation vector
+    int x_off[MZ_MAX_LAYERS + 1];        // float offset of the one-hot rows [n_extra][out] (first layer of dynamics), or -1
 };
 
 struct FcNet {
     MlpDesc rep, dyn, rew, val, pol;
     int blob_floats;
     int obs_elems, E, A, S, F;           // F = 2S+1
-    int maxw;                            // widest activation vector
+    int maxw;                            // widest activation vector, multiple of 4
 };
 
-// y[o] = act(b[o] + sum_i x[i] W[i][o] (+ W[extra_row][o]))   for o striding over the lanes
+// y[o] = act(b[o] + sum_i x[i] W[i][o] (+ Wx[extra][o]))   for o striding over the lanes.
+// Weights are packed [i/4][o][i%4] (zero padded) so a lane fetches four weights with one 128-bit
+// shared load, and x (shared, 16-byte aligned, zero padded to a multiple of 4) is read as float4
+// broadcasts: 2 LDS.128 + 4 FFMA per four inputs.  Entries out..round4(out) of y are zeroed so y
+// can feed the next layer's float4 reads.
 template <int G>
-MZ_DEVINL void linear_layer(const float* __restrict__ W, const float* __restrict__ b, int in, int out,
-                            const float* x, float* y, bool elu, int extra_row) {
+MZ_DEVINL void linear_layer(const float* __restrict__ W, const float* __restrict__ b, const float* __restrict__ Wx,
+                            int in_dense, int out, const float* x, float* y, bool elu, int extra_row) {
     const int lane = LaneGroup<G>::lane();
-    for (int o = lane; o < out; o += G) {
-        float acc = b[o];
-        const float* w = W + o;
-#pragma unroll 4
-        for (int i = 0; i < in; ++i) acc = fmaf(x[i], w[i * out], acc);
-        if (extra_row >= 0) acc += w[extra_row * out];
-        y[o] = elu ? elu1(acc) : acc;
+    const int in4 = (in_dense + 3) >> 2;
+    const float4* x4 = reinterpret_cast<const float4*>(x);
+    const float4* W4 = reinterpret_cast<const float4*>(W);
+    const int out4 = (out + 3) & ~3;
+    for (int o = lane; o < out4; o += G) {
+        float r = 0.0f;
+        if (o < out) {
+            float acc = b[o];
+            const float4* w = W4 + o;
+#pragma unroll 2
+            for (int i = 0; i < in4; ++i) {
+                const float4 xv = x4[i];
+                const float4 wv = w[i * out];
+                acc = fmaf(xv.x, wv.x, acc);
+                acc = fmaf(xv.y, wv.y, acc);
+                acc = fmaf(xv.z, wv.z, acc);
+                acc = fmaf(xv.w, wv.w, acc);
+            }
+            if (extra_row >= 0) acc += Wx[extra_row * out + o];
+            r = elu ? elu1(acc) : acc;
+        }
+        y[o] = r;
     }
     LaneGroup<G>::sync();
 }
 
-// Runs a whole MLP. x may be global or shared; s0/s1 are per-game ping-pong scratch (shared).
-// For the dynamics net the first layer's input is [x | one_hot(action)]: `dense_in0` is the
-// length of x and `extra_row` = dense_in0 + action selects the one-hot column (models.py:149-155).
+// Runs a whole MLP. x must be in shared memory (16-byte aligned, zero padded to a multiple of 4);
+// s0/s1 are per-game ping-pong scratch.  For the dynamics net the first layer's input is
+// [x | one_hot(action)]: `action` >= 0 selects the one-hot row (models.py:149-155).
 // Returns the pointer holding the output (s0, s1 or `final_out` if given).
 template <int G>
 MZ_DEVINL float* mlp_forward(const MlpDesc& d, const float* blob, const float* x, float* s0, float* s1,
-                             float* final_out, int dense_in0 = -1, int extra_row = -1) {
+                             float* final_out, int action = -1) {
     const float* cur = x;
     float* dst = s0;
     for (int l = 0; l < d.n; ++l) {
         const bool last = (l == d.n - 1);
         float* y = (last && final_out) ? final_out : dst;
-        const int in = (l == 0 && dense_in0 >= 0) ? dense_in0 : d.in[l];
-        linear_layer<G>(blob + d.w_off[l], blob + d.b_off[l], in, d.out[l], cur, y, !last,
-                        (l == 0) ? extra_row : -1);
+        linear_layer<G>(blob + d.w_off[l], blob + d.b_off[l], d.x_off[l] >= 0 ? blob + d.x_off[l] : nullptr,
+                        d.in_dense[l], d.out[l], cur, y, !last, (l == 0) ? action : -1);
         cur = y;
         dst = (y == s0) ? s1 : s0;
     }
     return const_cast<float*>(cur);
+}
+
+// copies n floats from global memory into a zero-padded shared vector
+template <int G>
+MZ_DEVINL void load_vector(const float* __restrict__ src, float* dst, int n) {
+    const int lane = LaneGroup<G>::lane();
+    const int n4 = (n + 3) & ~3;
+    for (int i = lane; i < n4; i += G) dst[i] = (i < n) ? src[i] : 0.0f;
+    LaneGroup<G>::sync();
 }
 
 // Per-sample min-max rescale over n values held in shared memory (models.py:138-145,161-168):
@@ -78,7 +107,8 @@ MZ_DEVINL void rescale_unit_range(const float* x, float* out, int n) {
     hi = group_max_f32<G>(hi);
     float sc = __fsub_rn(hi, lo);
     if (sc < 1e-5f) sc = __fadd_rn(sc, 1e-5f);
-    for (int i = lane; i < n; i += G) out[i] = __fdiv_rn(__fsub_rn(x[i], lo), sc);
+    const int n4 = (n + 3) & ~3;
+    for (int i = lane; i < n4; i += G) out[i] = (i < n) ? __fdiv_rn(__fsub_rn(x[i], lo), sc) : 0.0f;
     LaneGroup<G>::sync();
 }
 

@@ -21,24 +21,25 @@ struct GameSmem {
 __host__ __device__ inline GameSmem game_smem_layout(int N, int A, int E, int maxw, bool keep_hidden) {
     GameSmem L;
     const int S = (N + 1) * A;
+    const int Epad = (E + 3) & ~3;
     int off = 0;
-    L.vsum = off;       off += S * 8;
-    L.root_prior = off; off += A * 8;
-    L.visit = off;      off += S * 4;
-    L.expansion = off;  off += S * 4;
-    L.reward = off;     off += S * 4;
-    L.prior = off;      off += S * 4;
-    L.path = off;       off += (N + 2) * 4;
-    L.hidden = off;     off += (keep_hidden ? (N + 1) * E : 0) * 4;
-    L.act = off;        off += 3 * maxw * 4;
-    off = (off + 15) & ~15;
+    auto take = [&](int bytes) { int o = off; off = (off + bytes + 15) & ~15; return o; };
+    L.vsum = take(S * 8);
+    L.root_prior = take(A * 8);
+    L.visit = take(S * 4);
+    L.expansion = take(S * 4);
+    L.reward = take(S * 4);
+    L.prior = take(S * 4);
+    L.path = take((N + 2) * 4);
+    L.hidden = take((keep_hidden ? (N + 1) * Epad : 0) * 4);
+    L.act = take(3 * maxw * 4);
     off += 16;          // odd multiple of 16 B between games: spreads games over banks
     L.bytes = off;
     return L;
 }
 
 template <int G, bool kTeacher>
-__global__ void __launch_bounds__(kFcThreads) fc_search_kernel(const __grid_constant__ FcSearchArgs a) {
+__global__ void __launch_bounds__(kFcMaxThreads) fc_search_kernel(const __grid_constant__ FcSearchArgs a) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int N = a.N, A = a.A;
     // ---- CTA-shared: tables + weights
@@ -72,6 +73,7 @@ __global__ void __launch_bounds__(kFcThreads) fc_search_kernel(const __grid_cons
     float* s_hidden = reinterpret_cast<float*>(mine + L.hidden);
     float* s_act = reinterpret_cast<float*>(mine + L.act);
     const int E = a.net.E, F = a.net.F, S = a.net.S, maxw = a.net.maxw;
+    const int Epad = (E + 3) & ~3;
     float* s0 = s_act;
     float* s1 = s_act + maxw;
     float* s2 = s_act + 2 * maxw;
@@ -93,7 +95,8 @@ __global__ void __launch_bounds__(kFcThreads) fc_search_kernel(const __grid_cons
             root_reward = a.teacher.root_reward[g];
         } else {
             // representation (models.py:133-145) -> hidden[0]
-            float* raw = mlp_forward<G>(a.net.rep, s_blob, a.obs + (size_t)g * a.net.obs_elems, s0, s1, s2);
+            load_vector<G>(a.obs + (size_t)g * a.net.obs_elems, s1, a.net.obs_elems);
+            float* raw = mlp_forward<G>(a.net.rep, s_blob, s1, s0, s1, s2);
             rescale_unit_range<G>(raw, s_hidden, E);
             // prediction (models.py:128-131)
             float* pol = mlp_forward<G>(a.net.pol, s_blob, s_hidden, s0, s1, s2);
@@ -123,13 +126,13 @@ __global__ void __launch_bounds__(kFcThreads) fc_search_kernel(const __grid_cons
                 prior = (lane < A) ? a.teacher.priors[((size_t)g * N + sim) * A + lane] : 0.0f;
             } else {
                 // dynamics (models.py:147-170)
-                const float* h = s_hidden + (size_t)leaf.parent_exp * E;
-                float* raw = mlp_forward<G>(a.net.dyn, s_blob, h, s0, s1, s2, E, E + leaf.action);
+                const float* h = s_hidden + (size_t)leaf.parent_exp * Epad;
+                float* raw = mlp_forward<G>(a.net.dyn, s_blob, h, s0, s1, s2, leaf.action);
                 // reward head reads the un-normalised next state
                 float* rl = mlp_forward<G>(a.net.rew, s_blob, raw, s0, s1, nullptr);
                 reward = support_to_scalar_group<G>(rl, S);
                 LaneGroup<G>::sync();
-                float* hn = s_hidden + (size_t)t.n_expanded * E;
+                float* hn = s_hidden + (size_t)t.n_expanded * Epad;
                 rescale_unit_range<G>(raw, hn, E);
                 float* pol = mlp_forward<G>(a.net.pol, s_blob, hn, s0, s1, s2);
                 logit = (lane < A) ? pol[lane] : 0.0f;
@@ -177,7 +180,7 @@ __global__ void __launch_bounds__(kFcThreads) fc_search_kernel(const __grid_cons
             if (lane < A) a.pool.root_prior[(size_t)g * A + lane] = t.root_prior[lane];
             if (!kTeacher && a.pool.hidden)
                 for (int i = lane; i < t.n_expanded * E; i += G)
-                    a.pool.hidden[(size_t)g * (N + 1) * E + i] = s_hidden[i];
+                    a.pool.hidden[(size_t)g * (N + 1) * E + i] = s_hidden[(i / E) * Epad + (i % E)];
             if (lane == 0) {
                 a.pool.root_visit[g] = t.root_visit;
                 a.pool.root_vsum[g] = t.root_vsum;
@@ -196,20 +199,22 @@ template <int G, bool T>
 static cudaError_t launch_one(const FcSearchArgs& a, int sm_count, size_t smem_cap, cudaStream_t stream, FcLaunchInfo* info) {
     const GameSmem L = game_smem_layout(a.N, a.A, a.net.E, a.net.maxw, !T);
     const size_t shared_bytes = ((2 * (size_t)(a.N + 2) * 8 + (T ? 0 : (size_t)a.net.blob_floats) * 4) + 15) & ~(size_t)15;
-    const int groups = kFcThreads / G;
+    const int threads = a.threads;
+    const int groups = threads / G;
+    if (groups < 1) return cudaErrorInvalidValue;
     const size_t smem = shared_bytes + (size_t)groups * L.bytes;
     if (smem > smem_cap) return cudaErrorInvalidConfiguration;
     auto kern = fc_search_kernel<G, T>;
     cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (err != cudaSuccess) return err;
     int per_sm = 0;
-    err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kFcThreads, smem);
+    err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem);
     if (err != cudaSuccess) return err;
     if (per_sm < 1) return cudaErrorInvalidConfiguration;
     const int want = (a.n_games + groups - 1) / groups;
     const int grid = want < per_sm * sm_count ? want : per_sm * sm_count;
-    if (info) { info->grid = grid; info->block = kFcThreads; info->smem = smem; info->ctas_per_sm = per_sm; info->group = G; }
-    kern<<<grid, kFcThreads, smem, stream>>>(a);
+    if (info) { info->grid = grid; info->block = threads; info->smem = smem; info->ctas_per_sm = per_sm; info->group = G; }
+    kern<<<grid, threads, smem, stream>>>(a);
     return cudaGetLastError();
 }
 
@@ -232,7 +237,7 @@ cudaError_t launch_fc_search(const FcSearchArgs& a, int group, bool teacher, int
 size_t fc_search_smem_bytes(const FcSearchArgs& a, int group, bool teacher) {
     const GameSmem L = game_smem_layout(a.N, a.A, a.net.E, a.net.maxw, !teacher);
     const size_t shared_bytes = ((2 * (size_t)(a.N + 2) * 8 + (teacher ? 0 : (size_t)a.net.blob_floats) * 4) + 15) & ~(size_t)15;
-    return shared_bytes + (size_t)(kFcThreads / group) * L.bytes;
+    return shared_bytes + (size_t)(a.threads / group) * L.bytes;
 }
 
 }  // namespace mz

@@ -9,7 +9,8 @@
 
 namespace mz {
 
-constexpr int kFcThreads = 128;
+constexpr int kFcThreads = 128;      // fc_inference_kernel block
+constexpr int kFcMaxThreads = 256;   // upper bound of the fused search kernel's block
 
 // HBM node pool, game-major: game g owns slots [g*(N+1)*A, (g+1)*(N+1)*A).
 struct NodePool {
@@ -48,6 +49,7 @@ struct DevTrace {
 
 struct FcSearchArgs {
     int n_games, N, A, P;
+    int threads;           // block size of the launch (multiple of 32)
     double discount, noise_frac;
     uint64_t seed;
     const double* pbc;
@@ -89,7 +91,7 @@ struct FcInferArgs {
     int pool_stride, out_slot;
     float *value_logits, *reward_logits, *policy_logits, *hidden, *value, *reward;
 };
-cudaError_t launch_fc_inference(const FcInferArgs& a, int sm_count, cudaStream_t stream);
+cudaError_t launch_fc_inference(const FcInferArgs& a, int group, int sm_count, cudaStream_t stream);
 
 struct FcLaunchInfo { int grid, block, ctas_per_sm, group; size_t smem; };
 

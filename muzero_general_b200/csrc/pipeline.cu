@@ -6,7 +6,7 @@ namespace mz {
 
 int run_stepwise_search(const MzNetDesc& net, const MzSearchDesc& search, const NodePool& pool, const double* d_pbc,
                         const double* d_sqrt, const FcNet& fc, const float* d_fc_blob, ResNetDevice* res,
-                        const SearchCall& call, int sm_count, cudaStream_t stream, int64_t* launches, std::string* err) {
+                        const SearchCall& call, int fc_group, int sm_count, cudaStream_t stream, int64_t* launches, std::string* err) {
     const int n = call.n, N = search.num_simulations, A = net.action_space;
     const bool teacher = call.teacher.root_value != nullptr;
     auto cuda_fail = [&](const char* what, cudaError_t e) {
@@ -15,7 +15,7 @@ int run_stepwise_search(const MzNetDesc& net, const MzSearchDesc& search, const 
     };
     auto infer = [&](const InferCall& c) -> int {
         if (net.kind == MZ_NET_FC) {
-            cudaError_t e = launch_fc_inference_pool(fc, d_fc_blob, c, sm_count, stream);
+            cudaError_t e = launch_fc_inference_pool(fc, d_fc_blob, c, fc_group, sm_count, stream);
             if (e != cudaSuccess) return cuda_fail("fc_inference", e);
             *launches += 1;
             return MZ_OK;

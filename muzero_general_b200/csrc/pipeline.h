@@ -77,10 +77,10 @@ void resnet_destroy(ResNetDevice* r);
 int resnet_load_weights(ResNetDevice* r, const MzTensor* tensors, int n, std::string* err);
 int resnet_inference(ResNetDevice* r, const InferCall& c, cudaStream_t stream, int64_t* launches, std::string* err);
 
-cudaError_t launch_fc_inference_pool(const FcNet& net, const float* blob, const InferCall& c, int sm_count, cudaStream_t stream);
+cudaError_t launch_fc_inference_pool(const FcNet& net, const float* blob, const InferCall& c, int group, int sm_count, cudaStream_t stream);
 
 int run_stepwise_search(const MzNetDesc& net, const MzSearchDesc& search, const NodePool& pool, const double* d_pbc,
                         const double* d_sqrt, const FcNet& fc, const float* d_fc_blob, ResNetDevice* res,
-                        const SearchCall& call, int sm_count, cudaStream_t stream, int64_t* launches, std::string* err);
+                        const SearchCall& call, int fc_group, int sm_count, cudaStream_t stream, int64_t* launches, std::string* err);
 
 }  // namespace mz

@@ -242,9 +242,14 @@ MZ_DEVINL void tree_backup(const TreeConst& c, GameTree& t, const Leaf& leaf, fl
         v = __dadd_rn(rr, __dmul_rn(c.discount, v));
     }
     // lane 0 always owns j = 0 (the root)
-    root_vsum = shfl_f64(LaneGroup<G>::mask(), root_vsum, 0, G);
-    lo = group_min_f64<G>(lo, G);
-    hi = group_max_f64<G>(hi, G);
+    // only lanes 0..L hold candidates: reduce over the smallest power of two covering them,
+    // then broadcast lane 0's result (lanes beyond the reduced width hold partial values)
+    const int width = (L + 1 >= G) ? G : pow2_ceil(L + 1);
+    lo = group_min_f64<G>(lo, width);
+    hi = group_max_f64<G>(hi, width);
+    const unsigned gm = LaneGroup<G>::mask();
+    root_vsum = shfl_f64(gm, root_vsum, 0, G);
+    if (width < G) { lo = shfl_f64(gm, lo, 0, G); hi = shfl_f64(gm, hi, 0, G); }
     t.root_vsum = root_vsum;
     t.root_visit += 1;
     t.lo = fmin(t.lo, lo);
