@@ -190,6 +190,12 @@ int64_t mz_launch_count(const MzHandle* h);
 /* device time of the search kernels of the last mz_search call, ms (CUDA events on the library stream) */
 double mz_last_search_ms(const MzHandle* h);
 
+/* Debug / parity: one conv3x3 (C -> C, stride 1, pad 1; models.py:206-209) with optional bias, residual and
+ * ReLU on host NCHW fp32 data, through the CUDA-core kernel (use_tensor_cores = 0) or the tcgen05 implicit
+ * GEMM (1; C = 64, H <= 6, W <= 7).  w is [C][C][3][3] as in the reference state_dict. */
+int mz_debug_conv3x3(int device, int32_t n, int32_t C, int32_t H, int32_t W, const float* x, const float* w,
+                     const float* bias, const float* residual, int32_t relu, int32_t use_tensor_cores, float* out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -47,6 +47,7 @@ struct MzHandle {
     // pool
     NodePool pool{};
     int64_t hidden_elems = 0, obs_elems = 0;
+    int64_t pool_state_elems = 0;      // floats per hidden state as stored in the pool (layout dependent)
     // IO arenas
     unsigned char* d_in = nullptr;
     unsigned char* d_out = nullptr;
@@ -160,6 +161,13 @@ extern "C" int mz_create(const MzNetDesc* net, const MzSearchDesc* search, int d
         const int hw = net->downsample ? (net->obs_w + 15) / 16 : net->obs_w;
         h->hidden_elems = (int64_t)net->channels * hh * hw;
     }
+    h->pool_state_elems = h->hidden_elems;
+    if (net->kind == MZ_NET_RESNET) {
+        std::string e;
+        h->res = resnet_create(*net, B, h->sm_count, &e);
+        if (!h->res) { fail(nullptr, MZ_ECUDA, "resnet_create: " + e); mz_destroy(h); return MZ_ECUDA; }
+        h->pool_state_elems = resnet_state_elems(h->res);
+    }
     // ---- node pool
     const size_t slots = (size_t)B * (N + 1) * A;
     NodePool& p = h->pool;
@@ -169,7 +177,8 @@ extern "C" int mz_create(const MzNetDesc* net, const MzSearchDesc* search, int d
     MZ_CREATE_CUDA(dev_alloc(&p.prior, slots));
     MZ_CREATE_CUDA(dev_alloc(&p.expansion, slots));
     MZ_CREATE_CUDA(dev_alloc(&p.root_prior, (size_t)B * A));
-    MZ_CREATE_CUDA(dev_alloc(&p.hidden, (size_t)B * (N + 1) * h->hidden_elems));
+    MZ_CREATE_CUDA(dev_alloc(&p.hidden, (size_t)B * (N + 1) * h->pool_state_elems));
+    MZ_CREATE_CUDA(cudaMemset(p.hidden, 0, (size_t)B * (N + 1) * h->pool_state_elems * 4));   // layout padding reads as zero
     MZ_CREATE_CUDA(dev_alloc(&p.root_visit, B));
     MZ_CREATE_CUDA(dev_alloc(&p.root_vsum, B));
     MZ_CREATE_CUDA(dev_alloc(&p.root_reward, B));
@@ -211,11 +220,6 @@ extern "C" int mz_create(const MzNetDesc* net, const MzSearchDesc* search, int d
         fail(nullptr, MZ_EINVAL, "mz_create: MZ_FC_GROUP must be 4, 8, 16 or 32 and >= action_space");
         mz_destroy(h);
         return MZ_EINVAL;
-    }
-    if (net->kind == MZ_NET_RESNET) {
-        std::string e;
-        h->res = resnet_create(*net, B, h->sm_count, &e);
-        if (!h->res) { fail(nullptr, MZ_ECUDA, "resnet_create: " + e); mz_destroy(h); return MZ_ECUDA; }
     }
     *out = h;
     return MZ_OK;
@@ -586,10 +590,33 @@ extern "C" int mz_export_tree(MzHandle* h, int32_t game, MzTreeExport* out) {
         MZ_CUDA(h, cudaMemcpy(rp.data(), p.root_prior + (size_t)game * A, A * 8, cudaMemcpyDeviceToHost));
         for (size_t i = 0; i < used; ++i) out->child_prior[i] = (i < (size_t)A) ? rp[i] : (double)pf[i];
     }
-    if (out->hidden)
-        MZ_CUDA(h, cudaMemcpy(out->hidden, p.hidden + (size_t)game * (N + 1) * h->hidden_elems,
-                              (size_t)nexp * h->hidden_elems * 4, cudaMemcpyDeviceToHost));
+    if (out->hidden) {
+        const float* src = p.hidden + (size_t)game * (N + 1) * h->pool_state_elems;
+        if (h->net.kind == MZ_NET_RESNET) {
+            void* tmp = named_buffer(h, "x.hidden", (size_t)nexp * h->hidden_elems * 4);
+            if (!tmp) return fail(h, MZ_ENOMEM, "mz_export_tree: out of device memory");
+            if (resnet_states_to_nchw(h->res, src, nexp, (float*)tmp, h->stream)) return fail(h, MZ_ECUDA, "mz_export_tree: layout conversion failed");
+            MZ_CUDA(h, cudaStreamSynchronize(h->stream));
+            src = (const float*)tmp;
+        }
+        MZ_CUDA(h, cudaMemcpy(out->hidden, src, (size_t)nexp * h->hidden_elems * 4, cudaMemcpyDeviceToHost));
+    }
     MZ_CUDA(h, cudaMemcpy(&out->root_visit, p.root_visit + game, 4, cudaMemcpyDeviceToHost));
     MZ_CUDA(h, cudaMemcpy(&out->root_value_sum, p.root_vsum + game, 8, cudaMemcpyDeviceToHost));
+    return MZ_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// debug: one conv3x3 through either implementation (host NCHW in / out)
+// ------------------------------------------------------------------------------------------
+extern "C" int mz_debug_conv3x3(int device, int32_t n, int32_t C, int32_t H, int32_t W, const float* x, const float* w,
+                                const float* bias, const float* residual, int32_t relu, int32_t use_tensor_cores, float* out) {
+    if (!x || !w || !out || n < 1) return fail(nullptr, MZ_EINVAL, "mz_debug_conv3x3: bad argument");
+    if (cudaSetDevice(device) != cudaSuccess) return fail(nullptr, MZ_ECUDA, "mz_debug_conv3x3: no such device");
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return fail(nullptr, MZ_ECUDA, "mz_debug_conv3x3: device query failed");
+    std::string e;
+    int rc = resnet_debug_conv(n, C, H, W, x, w, bias, residual, relu, use_tensor_cores, out, prop.multiProcessorCount, &e);
+    if (rc) return fail(nullptr, rc, "mz_debug_conv3x3: " + e);
     return MZ_OK;
 }

@@ -1,0 +1,305 @@
+// conv3x3 (C -> C, stride 1, pad 1) as an implicit GEMM on the 5th-generation tensor cores.
+//
+// Used for the residual towers of board-sized states (H <= 6, W <= 7, C = 64: Connect4,
+// models.py:213-229 inside representation / dynamics / prediction).  Per CTA:
+//
+//   weights  [tap 9][C/4][cout C][4] tf32, BN folded      resident in shared memory (bulk copy)
+//   A tile   two boards = 128 rows of the "P64C4" layout   2-stage ring, cp.async.bulk (TMA unit)
+//   D        128 x 64 fp32 accumulator                     TMEM, double buffered
+//
+// P64C4 activation layout (HBM and shared): a board is 64 positions p = (y+1)*8 + x (row 0, rows
+// H+1.. and columns W..7 are zero padding) and channels are grouped by four:
+// act[board][c/4][p][c%4].  With the UMMA K-major SWIZZLE_NONE canonical layout and SBO = 128 B a
+// channel-group plane is a dense array of 16-byte rows, so the operand of filter tap (dy,dx) is the
+// SAME shared-memory tile with its start address moved by (dy*8+dx) rows: the implicit GEMM needs
+// no im2col copy, one bulk load per (board, channel group) and 72 tcgen05.mma (M128 N64 K8, tf32)
+// per tile.  Epilogue warps read the accumulator with tcgen05.ld, add the folded-BN bias, the
+// optional residual and the optional action-plane term (models.py:557-572 folded into a
+// per-position table), apply ReLU, zero the padding positions and store P64C4 again.
+//
+// Warp roles (256 threads): 0 = bulk-copy producer, 1 = MMA issuer, 2 = TMEM allocator,
+// 4..7 = epilogue (TMEM lane quarter = warp % 4).
+#include "pipeline.h"
+#include "conv_tc.h"
+
+namespace mz {
+
+namespace {
+
+constexpr int kC = 64;                 // channels in = out
+constexpr int kPos = 64;               // positions per board (8 x 8 padded grid)
+constexpr int kBoards = 2;             // boards per tile -> M = 128
+constexpr int kHalo = 10;              // zero rows above / below the tile (|shift| <= 9)
+constexpr int kRows = kBoards * kPos + 2 * kHalo;      // 148 rows per plane
+constexpr int kPlaneBytes = kRows * 16;                // LBO of A
+constexpr int kPlanes = kC / 4;                        // 16 channel groups
+constexpr int kStageBytes = kPlanes * kPlaneBytes;     // 37888
+constexpr int kStages = 2;
+constexpr int kWBytes = 9 * kPlanes * kC * 16;         // 147456
+constexpr int kTapBytes = kPlanes * kC * 16;           // 16384
+constexpr int kAccCols = 64;
+constexpr int kThreads = 256;
+
+struct Smem {
+    // offsets
+    static constexpr int w = 0;
+    static constexpr int a = kWBytes;
+    static constexpr int bias = a + kStages * kStageBytes;                 // 64 floats
+    static constexpr int bars = bias + kC * 4;                             // 8-byte aligned
+    static constexpr int tmem_ptr = bars + 16 * 8;
+    static constexpr int total = tmem_ptr + 16;
+};
+static_assert(Smem::total <= 232448, "shared memory budget");
+
+MZ_DEVINL uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+MZ_DEVINL void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+MZ_DEVINL void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+MZ_DEVINL void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+MZ_DEVINL void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t"
+            "}" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    } while (!done);
+}
+MZ_DEVINL void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+MZ_DEVINL void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+MZ_DEVINL void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// K-major, SWIZZLE_NONE shared-memory descriptor (cute::UMMA::SmemDescriptor, version 1)
+MZ_DEVINL uint64_t umma_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((addr >> 4) & 0x3FFF);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;
+    return d;
+}
+
+// kind::tf32, fp32 accumulate, A and B K-major, M = 128, N = 64 (cute::UMMA::InstrDescriptor)
+constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kAccCols >> 3) << 17) | ((128u >> 4) << 24);
+
+MZ_DEVINL void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(kIdesc), "r"(accumulate) : "memory");
+}
+MZ_DEVINL void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+MZ_DEVINL float round_tf32(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return __uint_as_float(r);
+}
+
+}  // namespace
+
+__global__ void __launch_bounds__(kThreads, 1) conv3x3_tc_kernel(const __grid_constant__ ConvTcArgs a) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t s_base = smem_u32(smem);
+    const uint32_t s_w = s_base + Smem::w, s_a = s_base + Smem::a;
+    float* s_bias = reinterpret_cast<float*>(smem + Smem::bias);
+    const uint32_t bars = s_base + Smem::bars;
+    // barrier ids
+    const uint32_t bar_w = bars;                                          // weights landed
+    auto bar_a_full = [&](int s) { return bars + 8u * (1 + s); };
+    auto bar_a_empty = [&](int s) { return bars + 8u * (3 + s); };
+    auto bar_acc_full = [&](int s) { return bars + 8u * (5 + s); };
+    auto bar_acc_empty = [&](int s) { return bars + 8u * (7 + s); };
+    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + Smem::tmem_ptr);
+
+    const int n_tiles = (a.n + kBoards - 1) / kBoards;
+
+    // ---- one-time setup
+    for (int i = threadIdx.x; i < kStages * kStageBytes / 16; i += kThreads)      // zero A (halo rows stay zero)
+        reinterpret_cast<uint4*>(smem + Smem::a)[i] = make_uint4(0, 0, 0, 0);
+    if (threadIdx.x < kC) s_bias[threadIdx.x] = a.bias ? a.bias[threadIdx.x] : 0.0f;
+    if (threadIdx.x == 0) {
+        mbar_init(bar_w, 1);
+        for (int s = 0; s < kStages; ++s) {
+            mbar_init(bar_a_full(s), 1);
+            mbar_init(bar_a_empty(s), 1);
+            mbar_init(bar_acc_full(s), 1);
+            mbar_init(bar_acc_empty(s), 4);           // one arrival per epilogue warp
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic zero-fill -> async proxy readers
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                     ::"r"(s_base + Smem::tmem_ptr), "r"(2 * kAccCols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ================= producer =================
+        if (lane == 0) {
+            mbar_expect_tx(bar_w, kWBytes);
+            for (int t = 0; t < 9; ++t)
+                bulk_g2s(s_w + t * kTapBytes, reinterpret_cast<const unsigned char*>(a.w) + (size_t)t * kTapBytes, kTapBytes, bar_w);
+        }
+        int it = 0;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+            const int s = it % kStages;
+            const uint32_t ph = (it / kStages) & 1;
+            if (lane == 0) mbar_wait(bar_a_empty(s), ph ^ 1);
+            __syncwarp();
+            const int nb = min(kBoards, a.n - tile * kBoards);
+            if (lane == 0) mbar_expect_tx(bar_a_full(s), (uint32_t)nb * kPlanes * kPos * 16);
+            __syncwarp();
+            // 32 lanes: (board, plane) pairs
+            for (int i = lane; i < nb * kPlanes; i += 32) {
+                const int b = i / kPlanes, j = i % kPlanes;
+                const int g = tile * kBoards + b;
+                const float* src = a.gather_parent
+                    ? a.in + ((size_t)g * a.pool_stride + a.gather_parent[g]) * (size_t)(kC * kPos)
+                    : a.in + (size_t)g * (kC * kPos);
+                bulk_g2s(s_a + s * kStageBytes + j * kPlaneBytes + (kHalo + b * kPos) * 16,
+                         src + (size_t)j * kPos * 4, kPos * 16, bar_a_full(s));
+            }
+        }
+    } else if (warp == 1) {
+        // ================= MMA issuer =================
+        mbar_wait(bar_w, 0);
+        int it = 0;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+            const int s = it % kStages;
+            const uint32_t ph = (it / kStages) & 1;
+            mbar_wait(bar_acc_empty(s), ph ^ 1);
+            mbar_wait(bar_a_full(s), ph);
+            tc_fence_after();
+            if (lane == 0) {
+                const uint32_t d = tmem_base + (uint32_t)(s * kAccCols);
+                uint32_t acc = 0;
+#pragma unroll 1
+                for (int tap = 0; tap < 9; ++tap) {
+                    const int shift = (tap / 3 - 1) * 8 + (tap % 3 - 1);
+                    const uint32_t a0 = s_a + s * kStageBytes + (kHalo + shift) * 16;
+                    const uint32_t b0 = s_w + tap * kTapBytes;
+#pragma unroll
+                    for (int ks = 0; ks < kC / 8; ++ks) {
+                        const uint64_t ad = umma_desc(a0 + 2 * ks * kPlaneBytes, kPlaneBytes, 128);
+                        const uint64_t bd = umma_desc(b0 + 2 * ks * (kC * 16), kC * 16, 128);
+                        umma_tf32(d, ad, bd, acc);
+                        acc = 1;
+                    }
+                }
+                umma_commit(bar_a_empty(s));          // smem stage reusable once the MMAs have read it
+                umma_commit(bar_acc_full(s));         // accumulator complete
+            }
+            __syncwarp();
+        }
+    } else if (warp >= 4) {
+        // ================= epilogue =================
+        const int q = warp & 3;                       // TMEM lane quarter
+        const int row = q * 32 + lane;                // tile row = TMEM lane
+        const int b = row / kPos, p = row % kPos;
+        const int y = p / 8 - 1, x = p % 8;
+        const bool inside = (y >= 0 && y < a.H && x < a.W);
+        int it = 0;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+            const int s = it % kStages;
+            const uint32_t ph = (it / kStages) & 1;
+            mbar_wait(bar_acc_full(s), ph);
+            tc_fence_after();
+            uint32_t v[64];
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(s * kAccCols);
+            asm volatile(
+                "tcgen05.ld.sync.aligned.32x32b.x64.b32 "
+                "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, "
+                "%32, %33, %34, %35, %36, %37, %38, %39, %40, %41, %42, %43, %44, %45, %46, %47, "
+                "%48, %49, %50, %51, %52, %53, %54, %55, %56, %57, %58, %59, %60, %61, %62, %63}, [%64];"
+                : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                  "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+                  "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+                  "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31]),
+                  "=r"(v[32]), "=r"(v[33]), "=r"(v[34]), "=r"(v[35]), "=r"(v[36]), "=r"(v[37]), "=r"(v[38]), "=r"(v[39]),
+                  "=r"(v[40]), "=r"(v[41]), "=r"(v[42]), "=r"(v[43]), "=r"(v[44]), "=r"(v[45]), "=r"(v[46]), "=r"(v[47]),
+                  "=r"(v[48]), "=r"(v[49]), "=r"(v[50]), "=r"(v[51]), "=r"(v[52]), "=r"(v[53]), "=r"(v[54]), "=r"(v[55]),
+                  "=r"(v[56]), "=r"(v[57]), "=r"(v[58]), "=r"(v[59]), "=r"(v[60]), "=r"(v[61]), "=r"(v[62]), "=r"(v[63])
+                : "r"(taddr));
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_acc_empty(s));        // accumulator may be overwritten
+            const int g = tile * kBoards + b;
+            if (g < a.n) {
+                float* dst = a.out + (size_t)g * (kC * kPos) + (size_t)p * 4;
+                const float* res = a.residual ? a.residual + (size_t)g * (kC * kPos) + (size_t)p * 4 : nullptr;
+                const float act_scale = a.action ? __fdiv_rn((float)a.action[g], (float)a.A) : 0.0f;
+                const float* atab = a.action ? a.action_table + (size_t)p * kC : nullptr;
+#pragma unroll
+                for (int j = 0; j < kPlanes; ++j) {
+                    float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (inside) {
+                        float r[4];
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) r[c] = __uint_as_float(v[4 * j + c]) + s_bias[4 * j + c];
+                        if (atab) {
+                            const float4 t4 = *reinterpret_cast<const float4*>(atab + 4 * j);
+                            r[0] = fmaf(act_scale, t4.x, r[0]); r[1] = fmaf(act_scale, t4.y, r[1]);
+                            r[2] = fmaf(act_scale, t4.z, r[2]); r[3] = fmaf(act_scale, t4.w, r[3]);
+                        }
+                        if (res) {
+                            const float4 r4 = *reinterpret_cast<const float4*>(res + (size_t)j * kPos * 4);
+                            r[0] += r4.x; r[1] += r4.y; r[2] += r4.z; r[3] += r4.w;
+                        }
+                        if (a.relu) {
+#pragma unroll
+                            for (int c = 0; c < 4; ++c) r[c] = fmaxf(r[c], 0.0f);
+                        }
+                        o = make_float4(round_tf32(r[0]), round_tf32(r[1]), round_tf32(r[2]), round_tf32(r[3]));
+                    }
+                    *reinterpret_cast<float4*>(dst + (size_t)j * kPos * 4) = o;
+                }
+            }
+        }
+    }
+    // ---- teardown
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2 * kAccCols) : "memory");
+}
+
+cudaError_t launch_conv3x3_tc(const ConvTcArgs& a, int sm_count, cudaStream_t stream) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(conv3x3_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem::total);
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    const int n_tiles = (a.n + kBoards - 1) / kBoards;
+    const int grid = n_tiles < sm_count ? n_tiles : sm_count;
+    conv3x3_tc_kernel<<<grid, kThreads, Smem::total, stream>>>(a);
+    return cudaGetLastError();
+}
+
+bool conv_tc_supported(int C, int H, int W) { return C == kC && H >= 1 && H <= 6 && W >= 1 && W <= 7; }
+int conv_tc_board_elems() { return kC * kPos; }
+
+}  // namespace mz

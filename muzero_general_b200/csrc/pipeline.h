@@ -76,6 +76,10 @@ ResNetDevice* resnet_create(const MzNetDesc& net, int max_batch, int sm_count, s
 void resnet_destroy(ResNetDevice* r);
 int resnet_load_weights(ResNetDevice* r, const MzTensor* tensors, int n, std::string* err);
 int resnet_inference(ResNetDevice* r, const InferCall& c, cudaStream_t stream, int64_t* launches, std::string* err);
+int resnet_debug_conv(int n, int C, int H, int W, const float* x, const float* w_oihw, const float* bias,
+                      const float* residual, int relu, int use_tc, float* out, int sm_count, std::string* err);
+int resnet_state_elems(const ResNetDevice* r);        // floats per stored hidden state in the pool
+int resnet_states_to_nchw(ResNetDevice* r, const float* states, int count, float* out, cudaStream_t stream);
 
 cudaError_t launch_fc_inference_pool(const FcNet& net, const float* blob, const InferCall& c, int group, int sm_count, cudaStream_t stream);
 

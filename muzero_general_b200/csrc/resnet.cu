@@ -14,12 +14,15 @@
 // This is the exact-fp32 path ("strict" numerics, also the validation reference for the
 // tensor-core path).
 #include <math.h>
+#include <stdlib.h>
+#include <string.h>
 
 #include <map>
 #include <string>
 #include <vector>
 
 #include "common.cuh"
+#include "conv_tc.h"
 #include "pipeline.h"
 
 namespace mz {
@@ -38,6 +41,7 @@ struct ConvArgs {
     int pool_stride;
     int n, Cin, Cout, Hin, Win, Ho, Wo, stride, relu, A;
     int boards_per_cta, cin_chunk;
+    int out_p64c4;            // write act[g][co/4][(y+1)*8+x][co%4] (tensor-core path layout) instead of NCHW
 };
 
 template <int P, int STRIDE, int MAX_ITEMS>
@@ -145,7 +149,10 @@ __global__ void __launch_bounds__(256) conv3x3_kernel(const __grid_constant__ Co
                 float r = acc[it][c][p] + bias;
                 if (a.residual) r += a.residual[o + p];
                 if (a.relu) r = fmaxf(r, 0.0f);
-                a.out[o + p] = r;
+                if (a.out_p64c4)
+                    a.out[(((size_t)g * (a.Cout / 4) + co / 4) * 64 + (y + 1) * 8 + seg * P + p) * 4 + (co & 3)] = r;
+                else
+                    a.out[o + p] = r;
             }
         }
     }
@@ -193,7 +200,14 @@ struct HeadsArgs {
     float* pool_hidden;        // pool mode target
     int pool_stride, out_slot;
     int smem_floats;
+    int p64c4, W;              // input (and pool target) use the tensor-core board layout
+    float* state_p64c4;        // [n, 4096] rescaled state in P64C4 (input of the prediction tower), or nullptr
 };
+
+// offset of (channel c, dense position p) inside one P64C4 state
+__device__ __forceinline__ int p64c4_index(int c, int p, int W) {
+    return ((c >> 2) * 64 + (p / W + 1) * 8 + (p % W)) * 4 + (c & 3);
+}
 
 __global__ void __launch_bounds__(128) heads_kernel(const __grid_constant__ HeadsArgs a) {
     extern __shared__ __align__(16) float sm[];
@@ -202,11 +216,16 @@ __global__ void __launch_bounds__(128) heads_kernel(const __grid_constant__ Head
     float* s_x = sm;                              // [C*HW]
     float* s_a = s_x + C * HW;                    // activations ping
     float* s_b = s_a + a.smem_floats;             // activations pong
-    const float* x = a.x + (size_t)g * C * HW;
-    for (int i = threadIdx.x; i < C * HW; i += blockDim.x) s_x[i] = x[i];
+    if (a.p64c4) {
+        const float* x = a.x + (size_t)g * 4096;
+        for (int i = threadIdx.x; i < C * HW; i += blockDim.x) s_x[i] = x[p64c4_index(i / HW, i % HW, a.W)];
+    } else {
+        const float* x = a.x + (size_t)g * C * HW;
+        for (int i = threadIdx.x; i < C * HW; i += blockDim.x) s_x[i] = x[i];
+    }
     __syncthreads();
 
-    if (a.rescaled || a.pool_hidden) {
+    if (a.rescaled || a.pool_hidden || a.state_p64c4) {
         // one warp per channel: min / max over HW, then (x - min) / scale
         const int warp = threadIdx.x / 32, lane = threadIdx.x % 32, nw = blockDim.x / 32;
         for (int c = warp; c < C; c += nw) {
@@ -219,7 +238,17 @@ __global__ void __launch_bounds__(128) heads_kernel(const __grid_constant__ Head
             for (int i = lane; i < HW; i += 32) {
                 const float v = __fdiv_rn(__fsub_rn(s_x[c * HW + i], lo), sc);
                 if (a.rescaled) a.rescaled[(size_t)g * C * HW + c * HW + i] = v;
-                if (a.pool_hidden) a.pool_hidden[((size_t)g * a.pool_stride + a.out_slot) * C * HW + c * HW + i] = v;
+                if (a.p64c4) {
+                    // operands of the tf32 tensor-core convs: round to nearest once, here
+                    uint32_t rb;
+                    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(rb) : "f"(v));
+                    const float vt = __uint_as_float(rb);
+                    const int off = p64c4_index(c, i, a.W);
+                    if (a.pool_hidden) a.pool_hidden[((size_t)g * a.pool_stride + a.out_slot) * 4096 + off] = vt;
+                    if (a.state_p64c4) a.state_p64c4[(size_t)g * 4096 + off] = vt;
+                } else if (a.pool_hidden) {
+                    a.pool_hidden[((size_t)g * a.pool_stride + a.out_slot) * C * HW + c * HW + i] = v;
+                }
             }
         }
     }
@@ -275,6 +304,24 @@ __global__ void copy_from_pool_kernel(const float* pool, float* out, int n, int 
     out[i] = pool[(g * pool_stride + slot) * elems + e];
 }
 
+// dense NCHW [count][C][H*W]  <->  P64C4 [count][C/4][64][4]
+__global__ void nchw_to_p64c4_kernel(const float* in, float* out, int count, int C, int H, int W) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int HW = H * W;
+    if (i >= (size_t)count * C * HW) return;
+    const size_t g = i / ((size_t)C * HW);
+    const int c = (i / HW) % C, p = i % HW;
+    out[g * 4096 + p64c4_index(c, p, W)] = in[i];
+}
+__global__ void p64c4_to_nchw_kernel(const float* in, float* out, int count, int C, int H, int W) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int HW = H * W;
+    if (i >= (size_t)count * C * HW) return;
+    const size_t g = i / ((size_t)C * HW);
+    const int c = (i / HW) % C, p = i % HW;
+    out[i] = in[g * 4096 + p64c4_index(c, p, W)];
+}
+
 // ------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------
@@ -282,6 +329,8 @@ struct ConvLayer {
     int cin, cout, stride;
     size_t w_off;             // into the conv blob: [cin][9][cout]
     long b_off;               // folded BN bias [cout], -1 = none
+    long tc_off;              // tensor-core image [9][C/4][C][4] (tf32), -1 = none
+    long tc_table_off;        // dynamics first conv: action-plane table [64][C], -1 = none
 };
 
 struct ResNetDevice {
@@ -298,8 +347,11 @@ struct ResNetDevice {
     float* d_head = nullptr;           // head blob
     float* ws[3] = {nullptr, nullptr, nullptr};
     size_t ws_elems = 0;
-    float* scratch_hidden = nullptr;   // [B, C*hh*hw] rescaled state when no pool is given
+    float* scratch_hidden = nullptr;   // [B, C*hh*hw] rescaled state when no pool is given (dense NCHW)
+    float* scratch_state = nullptr;    // [B, 4096] same state in P64C4 (tensor-core path)
     bool loaded = false;
+    bool use_tc = false;               // residual towers on tcgen05 (conv_tc.cu)
+    int state_elems = 0;               // floats per stored hidden state (dense C*H*W, or 4096 for P64C4)
 };
 
 static int conv_out(int h, int stride) { return (h - 1) / stride + 1; }
@@ -331,12 +383,20 @@ ResNetDevice* resnet_create(const MzNetDesc& net, int max_batch, int sm_count, s
         max_elems = std::max(max_elems, (size_t)net.channels * H * W);
     }
     max_elems = std::max(max_elems, (size_t)(net.channels + 1) * r->hh * r->hw);
+    const char* no_tc = getenv("MZ_NO_TC");
+    r->use_tc = !net.downsample && conv_tc_supported(net.channels, r->hh, r->hw) && !(no_tc && no_tc[0] == '1');
+    r->state_elems = r->use_tc ? conv_tc_board_elems() : r->C * r->hh * r->hw;
+    if (r->use_tc) max_elems = std::max(max_elems, (size_t)conv_tc_board_elems());
     r->ws_elems = max_elems * (size_t)max_batch;
-    for (int i = 0; i < 3; ++i)
+    for (int i = 0; i < 3; ++i) {
         if (cudaMalloc(&r->ws[i], r->ws_elems * 4 + 64) != cudaSuccess) { *err = "workspace allocation failed"; resnet_destroy(r); return nullptr; }
-    if (cudaMalloc(&r->scratch_hidden, (size_t)max_batch * r->C * r->hh * r->hw * 4 + 64) != cudaSuccess) {
+        cudaMemset(r->ws[i], 0, r->ws_elems * 4 + 64);      // P64C4 padding positions must read as zero
+    }
+    if (cudaMalloc(&r->scratch_hidden, (size_t)max_batch * r->C * r->hh * r->hw * 4 + 64) != cudaSuccess ||
+        cudaMalloc(&r->scratch_state, (size_t)max_batch * r->state_elems * 4 + 64) != cudaSuccess) {
         *err = "workspace allocation failed"; resnet_destroy(r); return nullptr;
     }
+    cudaMemset(r->scratch_state, 0, (size_t)max_batch * r->state_elems * 4 + 64);
     return r;
 }
 
@@ -344,6 +404,7 @@ void resnet_destroy(ResNetDevice* r) {
     if (!r) return;
     for (int i = 0; i < 3; ++i) if (r->ws[i]) cudaFree(r->ws[i]);
     if (r->scratch_hidden) cudaFree(r->scratch_hidden);
+    if (r->scratch_state) cudaFree(r->scratch_state);
     if (r->d_conv) cudaFree(r->d_conv);
     if (r->d_head) cudaFree(r->d_head);
     delete r;
@@ -364,8 +425,16 @@ struct Loader {
 };
 
 // conv3x3 [cout][cin][3][3] (+ optional BN prefix) -> [cin][9][cout] with the BN scale folded in
+float to_tf32(float x) {            // round to nearest, ties away (cvt.rna.tf32.f32)
+    uint32_t u;
+    memcpy(&u, &x, 4);
+    u = (u + 0x1000u) & 0xFFFFE000u;
+    memcpy(&x, &u, 4);
+    return x;
+}
+
 bool pack_conv(Loader& L, const std::string& conv, const std::string& bn, int cin, int cout, int stride,
-               std::vector<float>& blob, std::vector<ConvLayer>& layers) {
+               std::vector<float>& blob, std::vector<ConvLayer>& layers, bool tc = false, int H = 0, int W = 0) {
     const MzTensor* w = L.get(conv + ".weight", (int64_t)cout * cin * 9);
     if (!w) return false;
     std::vector<double> scale(cout, 1.0), shift(cout, 0.0);
@@ -396,13 +465,43 @@ bool pack_conv(Loader& L, const std::string& conv, const std::string& bn, int ci
         l.b_off = -1;
     }
     while (blob.size() % 4) blob.push_back(0.0f);           // keep every layer 16-byte aligned
+    l.tc_off = l.tc_table_off = -1;
+    if (tc) {
+        // image [tap][cin/4][cout][4] over the first 64 input channels; an extra (65th) input channel is the
+        // constant action plane and becomes a per-position table (sum of the taps that stay inside the board)
+        const int C = cout;
+        l.tc_off = (long)blob.size();
+        blob.resize(blob.size() + (size_t)9 * C * C);
+        float* img = blob.data() + l.tc_off;
+        for (int tap = 0; tap < 9; ++tap)
+            for (int ci = 0; ci < C; ++ci)
+                for (int co = 0; co < C; ++co)
+                    img[(((size_t)tap * (C / 4) + ci / 4) * C + co) * 4 + (ci % 4)] =
+                        to_tf32((float)((double)w->data[((size_t)co * cin + ci) * 9 + tap] * scale[co]));
+        if (cin == C + 1) {
+            l.tc_table_off = (long)blob.size();
+            blob.resize(blob.size() + (size_t)64 * C, 0.0f);
+            float* tab = blob.data() + l.tc_table_off;
+            for (int y = 0; y < H; ++y)
+                for (int x = 0; x < W; ++x)
+                    for (int co = 0; co < C; ++co) {
+                        double acc = 0.0;
+                        for (int dy = -1; dy <= 1; ++dy)
+                            for (int dx = -1; dx <= 1; ++dx)
+                                if (y + dy >= 0 && y + dy < H && x + dx >= 0 && x + dx < W)
+                                    acc += (double)w->data[((size_t)co * cin + C) * 9 + (dy + 1) * 3 + (dx + 1)] * scale[co];
+                        tab[((y + 1) * 8 + x) * C + co] = (float)acc;
+                    }
+        }
+    }
     layers.push_back(l);
     return true;
 }
 
-bool pack_resblock(Loader& L, const std::string& p, int ch, std::vector<float>& blob, std::vector<ConvLayer>& layers) {
-    return pack_conv(L, p + ".conv1", p + ".bn1", ch, ch, 1, blob, layers) &&
-           pack_conv(L, p + ".conv2", p + ".bn2", ch, ch, 1, blob, layers);
+bool pack_resblock(Loader& L, const std::string& p, int ch, std::vector<float>& blob, std::vector<ConvLayer>& layers,
+                   bool tc = false) {
+    return pack_conv(L, p + ".conv1", p + ".bn1", ch, ch, 1, blob, layers, tc) &&
+           pack_conv(L, p + ".conv2", p + ".bn2", ch, ch, 1, blob, layers, tc);
 }
 
 bool pack_head(Loader& L, const std::string& conv, const std::string& fc, int C, int rc, int HW, const int32_t* hidden,
@@ -454,12 +553,13 @@ int resnet_load_weights(ResNetDevice* r, const MzTensor* tensors, int n, std::st
     } else {
         ok = ok && pack_conv(L, rp + ".conv", rp + ".bn", nd.obs_c, C, 1, conv, r->rep_trunk);
     }
-    for (int i = 0; ok && i < nd.blocks; ++i) ok = pack_resblock(L, rp + ".resblocks." + std::to_string(i), C, conv, r->rep_trunk);
+    const bool tc = r->use_tc;
+    for (int i = 0; ok && i < nd.blocks; ++i) ok = pack_resblock(L, rp + ".resblocks." + std::to_string(i), C, conv, r->rep_trunk, tc);
     const std::string dp = "dynamics_network.module";
-    ok = ok && pack_conv(L, dp + ".conv", dp + ".bn", C + 1, C, 1, conv, r->dyn);
-    for (int i = 0; ok && i < nd.blocks; ++i) ok = pack_resblock(L, dp + ".resblocks." + std::to_string(i), C, conv, r->dyn);
+    ok = ok && pack_conv(L, dp + ".conv", dp + ".bn", C + 1, C, 1, conv, r->dyn, tc, r->hh, r->hw);
+    for (int i = 0; ok && i < nd.blocks; ++i) ok = pack_resblock(L, dp + ".resblocks." + std::to_string(i), C, conv, r->dyn, tc);
     const std::string pp = "prediction_network.module";
-    for (int i = 0; ok && i < nd.blocks; ++i) ok = pack_resblock(L, pp + ".resblocks." + std::to_string(i), C, conv, r->pred);
+    for (int i = 0; ok && i < nd.blocks; ++i) ok = pack_resblock(L, pp + ".resblocks." + std::to_string(i), C, conv, r->pred, tc);
     ok = ok && pack_head(L, dp + ".conv1x1_reward", dp + ".fc", C, nd.reduced_reward, HW, nd.res_fc_reward, nd.n_res_fc_reward, F, head, r->reward_head);
     ok = ok && pack_head(L, pp + ".conv1x1_value", pp + ".fc_value", C, nd.reduced_value, HW, nd.res_fc_value, nd.n_res_fc_value, F, head, r->value_head);
     ok = ok && pack_head(L, pp + ".conv1x1_policy", pp + ".fc_policy", C, nd.reduced_policy, HW, nd.res_fc_policy, nd.n_res_fc_policy, nd.action_space, head, r->policy_head);
@@ -482,9 +582,35 @@ struct Runner {
     bool fail(const char* what, cudaError_t e) { *err = std::string(what) + ": " + cudaGetErrorString(e); return false; }
 
     // conv: in -> out. `in` may be gathered from the pool; action adds the constant plane.
+    bool conv_tc(const ConvLayer& l, const float* in, float* out, const float* residual, bool relu,
+                 const int32_t* gather_parent = nullptr, int pool_stride = 0, const int32_t* action = nullptr) {
+        ConvTcArgs a{};
+        a.in = in; a.out = out; a.residual = residual;
+        a.w = r->d_conv + l.tc_off;
+        a.bias = l.b_off >= 0 ? r->d_conv + l.b_off : nullptr;
+        a.gather_parent = gather_parent; a.pool_stride = pool_stride;
+        a.action = action; a.action_table = l.tc_table_off >= 0 ? r->d_conv + l.tc_table_off : nullptr;
+        a.n = n; a.H = r->hh; a.W = r->hw; a.A = r->net.action_space; a.relu = relu;
+        cudaError_t e = launch_conv3x3_tc(a, r->sm_count, stream);
+        if (e != cudaSuccess) return fail("conv3x3_tc launch", e);
+        *launches += 1;
+        return true;
+    }
+
+    bool blocks_tc(const std::vector<ConvLayer>& layers, size_t first, size_t count, float** cur, float** tmp, float** spare) {
+        for (size_t b = 0; b < count; ++b) {
+            if (!conv_tc(layers[first + 2 * b], *cur, *tmp, nullptr, true)) return false;
+            if (!conv_tc(layers[first + 2 * b + 1], *tmp, *spare, *cur, true)) return false;
+            float* t = *cur; *cur = *spare; *spare = t;
+        }
+        return true;
+    }
+
     bool conv(const ConvLayer& l, const float* in, float* out, const float* residual, bool relu, int Hin, int Win,
-              const int32_t* gather_parent = nullptr, int pool_stride = 0, const int32_t* action = nullptr) {
+              const int32_t* gather_parent = nullptr, int pool_stride = 0, const int32_t* action = nullptr,
+              bool out_p64c4 = false) {
         ConvArgs a{};
+        a.out_p64c4 = out_p64c4 ? 1 : 0;
         a.in = in; a.out = out; a.residual = residual; a.w = r->d_conv + l.w_off;
         a.bias = l.b_off >= 0 ? r->d_conv + l.b_off : nullptr;
         a.gather_parent = gather_parent; a.pool_stride = pool_stride; a.action = action;
@@ -537,8 +663,9 @@ struct Runner {
     }
 
     bool heads(const float* x, int n_heads, const HeadDesc* h0, const HeadDesc* h1, float* l0, float* l1, float* s0, float* s1,
-               float* rescaled, float* pool_hidden, int pool_stride, int out_slot) {
+               float* rescaled, float* pool_hidden, int pool_stride, int out_slot, bool p64c4 = false, float* state_p64c4 = nullptr) {
         HeadsArgs a{};
+        a.p64c4 = p64c4 ? 1 : 0; a.W = r->hw; a.state_p64c4 = state_p64c4;
         a.x = x; a.blob = r->d_head; a.n = n; a.C = r->C; a.HW = r->hh * r->hw; a.S = r->net.support_size;
         a.n_heads = n_heads;
         int maxw = 32;
@@ -563,9 +690,123 @@ struct Runner {
 };
 }  // namespace
 
+// Tensor-core variant: every C->C conv of the three towers runs in conv_tc.cu on the P64C4 layout; the
+// stem conv (obs -> C) and the heads stay on the CUDA-core kernels above, reading / writing that layout.
+static int resnet_inference_tc(ResNetDevice* r, const InferCall& c, cudaStream_t stream, int64_t* launches, std::string* err) {
+    const MzNetDesc& nd = r->net;
+    const int n = c.n, C = r->C, hh = r->hh, hw = r->hw, F = 2 * nd.support_size + 1;
+    Runner R{r, stream, launches, err, n};
+    float *cur = r->ws[0], *tmp = r->ws[1], *spare = r->ws[2];
+    float* state = r->scratch_state;                   // rescaled state, P64C4, input of the prediction tower
+    if (!c.recurrent) {
+        if (!R.conv(r->rep_trunk[0], c.in, cur, nullptr, true, nd.obs_h, nd.obs_w, nullptr, 0, nullptr, true)) return MZ_ECUDA;
+        if (!R.blocks_tc(r->rep_trunk, 1, nd.blocks, &cur, &tmp, &spare)) return MZ_ECUDA;
+        if (!R.heads(cur, 0, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, c.hidden, c.pool_hidden, c.pool_stride, c.out_slot,
+                     true, state))
+            return MZ_ECUDA;
+        if (c.reward_logits) {
+            fill_root_reward_logits_kernel<<<(n * F + 255) / 256, 256, 0, stream>>>(c.reward_logits, n, F, nd.support_size);
+            *launches += 1;
+        }
+        if (c.reward) {
+            fill_root_reward_kernel<<<(n + 255) / 256, 256, 0, stream>>>(c.reward, n);
+            *launches += 1;
+        }
+    } else {
+        const float* in = c.pool_hidden;
+        if (!c.gather_parent) {
+            // plain API call: dense NCHW hidden states -> P64C4
+            const size_t total = (size_t)n * C * hh * hw;
+            nchw_to_p64c4_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(c.in, spare, n, C, hh, hw);
+            *launches += 1;
+            in = spare;
+        }
+        if (!R.conv_tc(r->dyn[0], in, cur, nullptr, true, c.gather_parent, c.pool_stride, c.action)) return MZ_ECUDA;
+        if (!R.blocks_tc(r->dyn, 1, nd.blocks, &cur, &tmp, &spare)) return MZ_ECUDA;
+        if (!R.heads(cur, 1, &r->reward_head, nullptr, c.reward_logits, nullptr, c.reward, nullptr, c.hidden, c.pool_hidden,
+                     c.pool_stride, c.out_slot, true, state))
+            return MZ_ECUDA;
+    }
+    const float* x = state;
+    if (nd.blocks > 0) {
+        if (!R.conv_tc(r->pred[0], state, tmp, nullptr, true)) return MZ_ECUDA;
+        if (!R.conv_tc(r->pred[1], tmp, spare, state, true)) return MZ_ECUDA;
+        { float* t = cur; cur = spare; spare = t; }
+        if (!R.blocks_tc(r->pred, 2, nd.blocks - 1, &cur, &tmp, &spare)) return MZ_ECUDA;
+        x = cur;
+    }
+    if (!R.heads(x, 2, &r->value_head, &r->policy_head, c.value_logits, c.policy_logits, c.value, nullptr, nullptr, nullptr, 0, 0, true))
+        return MZ_ECUDA;
+    return MZ_OK;
+}
+
+int resnet_state_elems(const ResNetDevice* r) { return r->state_elems; }
+
+// Stand-alone conv3x3 (+bias, +residual, +ReLU) on host NCHW data through either implementation.
+// Debug / parity entry point behind mz_debug_conv3x3.
+int resnet_debug_conv(int n, int C, int H, int W, const float* x, const float* w_oihw, const float* bias,
+                      const float* residual, int relu, int use_tc, float* out, int sm_count, std::string* err) {
+    if (use_tc && !conv_tc_supported(C, H, W)) { *err = "shape not supported by the tensor-core conv"; return MZ_EUNSUPPORTED; }
+    if (C % 4) { *err = "C must be a multiple of 4"; return MZ_EINVAL; }
+    MzNetDesc nd{};
+    nd.kind = MZ_NET_RESNET; nd.channels = C; nd.obs_c = C; nd.obs_h = H; nd.obs_w = W; nd.action_space = 1;
+    ResNetDevice r{};
+    r.net = nd; r.max_batch = n; r.sm_count = sm_count; r.C = C; r.hh = H; r.hw = W;
+    // fake a one-tensor state_dict for pack_conv
+    MzTensor t{"conv.weight", w_oihw, (int64_t)C * C * 9};
+    Loader L{&t, 1, err};
+    std::vector<float> blob;
+    std::vector<ConvLayer> layers;
+    if (!pack_conv(L, "conv", "", C, C, 1, blob, layers, use_tc != 0, H, W)) return MZ_EINVAL;
+    long bias_off = -1;
+    if (bias) { bias_off = (long)blob.size(); blob.insert(blob.end(), bias, bias + C); while (blob.size() % 4) blob.push_back(0.f); }
+    layers[0].b_off = bias_off;
+    const size_t dense = (size_t)n * C * H * W, packed = (size_t)n * 4096;
+    float *d_blob = nullptr, *d_x = nullptr, *d_res = nullptr, *d_out = nullptr, *d_px = nullptr, *d_pres = nullptr, *d_pout = nullptr;
+    auto cleanup = [&]() { for (float* p : {d_blob, d_x, d_res, d_out, d_px, d_pres, d_pout}) if (p) cudaFree(p); };
+    bool ok = cudaMalloc(&d_blob, blob.size() * 4) == cudaSuccess && cudaMalloc(&d_x, dense * 4) == cudaSuccess &&
+              cudaMalloc(&d_out, dense * 4) == cudaSuccess && (!residual || cudaMalloc(&d_res, dense * 4) == cudaSuccess);
+    if (ok && use_tc)
+        ok = cudaMalloc(&d_px, packed * 4) == cudaSuccess && cudaMalloc(&d_pout, packed * 4) == cudaSuccess &&
+             (!residual || cudaMalloc(&d_pres, packed * 4) == cudaSuccess);
+    if (!ok) { cleanup(); *err = "allocation failed"; return MZ_ENOMEM; }
+    cudaMemcpy(d_blob, blob.data(), blob.size() * 4, cudaMemcpyHostToDevice);
+    cudaMemcpy(d_x, x, dense * 4, cudaMemcpyHostToDevice);
+    if (residual) cudaMemcpy(d_res, residual, dense * 4, cudaMemcpyHostToDevice);
+    r.d_conv = d_blob;
+    int64_t launches = 0;
+    Runner R{&r, nullptr, &launches, err, n};
+    bool good;
+    if (use_tc) {
+        const unsigned blocks = (unsigned)((dense + 255) / 256);
+        cudaMemset(d_px, 0, packed * 4);
+        nchw_to_p64c4_kernel<<<blocks, 256>>>(d_x, d_px, n, C, H, W);
+        if (residual) { cudaMemset(d_pres, 0, packed * 4); nchw_to_p64c4_kernel<<<blocks, 256>>>(d_res, d_pres, n, C, H, W); }
+        good = R.conv_tc(layers[0], d_px, d_pout, residual ? d_pres : nullptr, relu != 0);
+        if (good) p64c4_to_nchw_kernel<<<blocks, 256>>>(d_pout, d_out, n, C, H, W);
+    } else {
+        good = R.conv(layers[0], d_x, d_out, residual ? d_res : nullptr, relu != 0, H, W);
+    }
+    cudaError_t e = cudaDeviceSynchronize();
+    if (good && e != cudaSuccess) { good = false; *err = std::string("debug conv: ") + cudaGetErrorString(e); }
+    if (good) cudaMemcpy(out, d_out, dense * 4, cudaMemcpyDeviceToHost);
+    r.d_conv = nullptr;
+    cleanup();
+    return good ? MZ_OK : MZ_ECUDA;
+}
+
+// stored hidden states (pool layout) -> dense NCHW, device to device
+int resnet_states_to_nchw(ResNetDevice* r, const float* states, int count, float* out, cudaStream_t stream) {
+    const size_t total = (size_t)count * r->C * r->hh * r->hw;
+    if (r->use_tc) p64c4_to_nchw_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(states, out, count, r->C, r->hh, r->hw);
+    else cudaMemcpyAsync(out, states, total * 4, cudaMemcpyDeviceToDevice, stream);
+    return cudaGetLastError() == cudaSuccess ? MZ_OK : MZ_ECUDA;
+}
+
 int resnet_inference(ResNetDevice* r, const InferCall& c, cudaStream_t stream, int64_t* launches, std::string* err) {
     if (!r->loaded) { *err = "weights not loaded"; return MZ_ESTATE; }
     if (c.n > r->max_batch) { *err = "batch larger than max_games"; return MZ_EINVAL; }
+    if (r->use_tc) return resnet_inference_tc(r, c, stream, launches, err);
     const MzNetDesc& nd = r->net;
     const int n = c.n, C = r->C, hh = r->hh, hw = r->hw, F = 2 * nd.support_size + 1;
     Runner R{r, stream, launches, err, n};

@@ -293,3 +293,19 @@ class SearchEngine:
         out["root_visit"] = int(e.root_visit)
         out["root_value_sum"] = float(e.root_value_sum)
         return out
+
+
+def debug_conv3x3(x, w, bias=None, residual=None, relu=False, tensor_cores=False, device=0):
+    """One conv3x3 (pad 1, stride 1) on the device through mz_debug_conv3x3; numpy NCHW in and out."""
+    lib = _lib.load_library()
+    x = numpy.ascontiguousarray(x, numpy.float32)
+    w = numpy.ascontiguousarray(w, numpy.float32)
+    n, Cc, H, W = x.shape
+    out = numpy.empty_like(x)
+    b = None if bias is None else numpy.ascontiguousarray(bias, numpy.float32)
+    r = None if residual is None else numpy.ascontiguousarray(residual, numpy.float32)
+    rc = lib.mz_debug_conv3x3(device, n, Cc, H, W, x.ctypes.data, w.ctypes.data, None if b is None else b.ctypes.data,
+                              None if r is None else r.ctypes.data, int(relu), int(tensor_cores), out.ctypes.data)
+    if rc != 0:
+        raise _lib.MzError(rc, lib.mz_last_error(None).decode())
+    return out
