@@ -13,7 +13,7 @@ def test_library_exports_every_declared_symbol():
     from muzero_general_b200 import _lib
     lib = _lib.load_library()
     header = open(os.path.join(ROOT, "include", "mzb200.h")).read()
-    declared = set(re.findall(r"^\s*(?:const\s+)?[a-z0-9_]+\s*\*?\s*(mz_[a-z_]+)\s*\(", header, re.M))
+    declared = set(re.findall(r"^\s*(?:const\s+)?[a-z0-9_]+\s*\*?\s*(mz_[a-z0-9_]+)\s*\(", header, re.M))
     assert declared, "no prototypes parsed"
     bound = {name for name, _, _ in _lib.SYMBOLS}
     assert declared == bound, (declared ^ bound)
