@@ -65,8 +65,12 @@ static cudaError_t launch_infer(const FcInferArgs& a, int sm_count, cudaStream_t
     const int groups = kFcThreads / G;
     const size_t smem = (((size_t)a.net.blob_floats + 3) & ~(size_t)3) * 4 + (size_t)groups * (4 * a.net.maxw + 4) * 4;
     auto kern = fc_inference_kernel<G>;
-    cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (err != cudaSuccess) return err;
+    static size_t attr_smem = 0;
+    if (attr_smem < smem) {
+        cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (err != cudaSuccess) return err;
+        attr_smem = smem;
+    }
     int grid = (a.n + groups - 1) / groups;
     if (grid > sm_count * 8) grid = sm_count * 8;
     if (grid < 1) grid = 1;

@@ -639,8 +639,12 @@ struct Runner {
 #define MZ_CONV(PP, SS)                                                                                         \
         if (P == PP && l.stride == SS) {                                                                        \
             auto kern = multi ? conv3x3_kernel<PP, SS, 4> : conv3x3_kernel<PP, SS, 1>;                          \
-            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-            if (e != cudaSuccess) return fail("conv attr", e);                                                  \
+            static size_t attr_smem[2] = {0, 0};                                                                \
+            if (attr_smem[multi] < smem) {                                                                      \
+                cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+                if (e != cudaSuccess) return fail("conv attr", e);                                              \
+                attr_smem[multi] = smem;                                                                        \
+            }                                                                                                   \
             kern<<<grid, threads, smem, stream>>>(a);                                                           \
         }
         MZ_CONV(8, 1) MZ_CONV(7, 1) MZ_CONV(6, 1) MZ_CONV(4, 1) MZ_CONV(3, 1) MZ_CONV(2, 1) MZ_CONV(1, 1)
@@ -679,10 +683,14 @@ struct Runner {
         a.rescaled = rescaled; a.pool_hidden = pool_hidden; a.pool_stride = pool_stride; a.out_slot = out_slot;
         a.smem_floats = (maxw + 3) & ~3;
         const size_t smem = ((size_t)a.C * a.HW + 2 * a.smem_floats) * 4;
-        cudaError_t e = cudaFuncSetAttribute(heads_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return fail("heads attr", e);
+        static size_t attr_smem = 0;
+        if (attr_smem < smem) {
+            cudaError_t e0 = cudaFuncSetAttribute(heads_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e0 != cudaSuccess) return fail("heads attr", e0);
+            attr_smem = smem;
+        }
         heads_kernel<<<n, 128, smem, stream>>>(a);
-        e = cudaGetLastError();
+        cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return fail("heads launch", e);
         *launches += 1;
         return true;

@@ -12,7 +12,16 @@ from muzero_general_b200.netspec import netspec_from_config
 from oracle import mcts as om
 
 pytestmark = pytest.mark.gpu
-TOL = dict(rtol=2e-4, atol=2e-5)
+# "fp32": CUDA-core convs everywhere (MZ_NO_TC=1).  "tf32": the tcgen05 towers where the shape allows
+# (Connect4); operands rounded to tf32 (10-bit mantissa) through 13 stacked convs -> looser bound.
+TOLS = {"fp32": dict(rtol=2e-4, atol=2e-5), "tf32": dict(rtol=2e-2, atol=4e-3)}
+VALUE_TOL = {"fp32": 2e-4, "tf32": 1e-2}
+
+
+@pytest.fixture(params=["fp32", "tf32"])
+def numerics(request, monkeypatch):
+    monkeypatch.setenv("MZ_NO_TC", "1" if request.param == "fp32" else "0")
+    return request.param
 
 
 def _engine(cfg, max_games, N):
@@ -20,8 +29,14 @@ def _engine(cfg, max_games, N):
     return SearchEngine(cfg, max_games=max_games, num_simulations=N)
 
 
+def _report(name, got, want):
+    err = numpy.abs(got - want)
+    print(f"{name}: max abs err {err.max():.3e}, max rel err {(err / (numpy.abs(want) + 1e-3)).max():.3e}")
+
+
 @pytest.mark.parametrize("name", ["tictactoe", "connect4", "breakout"])
-def test_resnet_network_matches_reference(name, game_configs):
+def test_resnet_network_matches_reference(name, numerics, game_configs):
+    TOL = TOLS[numerics]
     cfg = game_configs[name]
     spec = netspec_from_config(cfg)
     g = golden_npz(f"net_{name}.npz")
@@ -29,12 +44,17 @@ def test_resnet_network_matches_reference(name, game_configs):
     eng = _engine(cfg, n, 4)
     eng.load_weights(weights_for(name, spec))
     r0 = eng.initial_inference(g["obs"])
+    _report(f"{name}/{numerics} init hidden", r0["hidden"], g["init_hidden"].reshape(n, -1))
+    _report(f"{name}/{numerics} init value logits", r0["value_logits"], g["init_value"])
     numpy.testing.assert_allclose(r0["hidden"], g["init_hidden"].reshape(n, -1), **TOL)
     numpy.testing.assert_allclose(r0["value_logits"], g["init_value"], **TOL)
     numpy.testing.assert_allclose(r0["policy_logits"], g["init_policy"], **TOL)
     numpy.testing.assert_allclose(r0["value"], g["init_value_scalar"], **TOL)
     assert numpy.isneginf(r0["reward_logits"]).sum() == n * 20 and (r0["reward"] == 0).all()
     r1 = eng.recurrent_inference(g["init_hidden"].reshape(n, -1), g["action"])
+    _report(f"{name}/{numerics} rec hidden", r1["hidden"], g["rec_hidden"].reshape(n, -1))
+    _report(f"{name}/{numerics} rec policy logits", r1["policy_logits"], g["rec_policy"])
+    _report(f"{name}/{numerics} rec value logits", r1["value_logits"], g["rec_value"])
     numpy.testing.assert_allclose(r1["hidden"], g["rec_hidden"].reshape(n, -1), **TOL)
     numpy.testing.assert_allclose(r1["value_logits"], g["rec_value"], **TOL)
     numpy.testing.assert_allclose(r1["reward_logits"], g["rec_reward"], **TOL)
@@ -48,7 +68,7 @@ def test_resnet_network_matches_reference(name, game_configs):
 
 
 @pytest.mark.parametrize("name,N,n", [("tictactoe", 50, 24), ("connect4", 40, 12), ("breakout", 12, 4)])
-def test_resnet_student_forced(name, N, n, game_configs):
+def test_resnet_student_forced(name, N, n, numerics, game_configs):
     """Device search with its own residual networks, replayed through the oracle tree."""
     cfg = game_configs[name]
     spec = netspec_from_config(cfg)
@@ -85,7 +105,10 @@ def test_resnet_student_forced(name, N, n, game_configs):
 
 
 @pytest.mark.parametrize("name", ["tictactoe", "connect4", "breakout"])
-def test_resnet_closed_loop_matches_reference_counts(name, game_configs):
+def test_resnet_closed_loop_matches_reference_counts(name, numerics, game_configs):
+    """Own networks + the reference's noise and first pick.  fp32 path: the reference's visit counts
+    exactly.  tf32 path: counts may move by a visit where two children are nearly tied, so the bound is
+    on the visit distribution (total variation <= 5 %) and on the root value."""
     cfg = game_configs[name]
     spec = netspec_from_config(cfg)
     A = spec.action_space
@@ -97,7 +120,14 @@ def test_resnet_closed_loop_matches_reference_counts(name, game_configs):
         noise = numpy.zeros((1, A)); noise[0, c["legal"]] = c["noise"]
         out = eng.search(obs=obs, legal_mask=legal, to_play=numpy.array([c["to_play"]], numpy.int32),
                          add_exploration_noise=True, noise=noise, first_index=numpy.array([c["first_index"]], numpy.int32))
-        assert [int(out.visit_counts[0, a]) for a in c["root_actions"]] == c["root_visits"]
-        assert abs(out.root_value[0] - c["root_value"]) <= 2e-4 * max(1.0, abs(c["root_value"]))
-        assert abs(out.root_predicted_value[0] - c["root_predicted_value"]) <= 2e-4 * max(1.0, abs(c["root_predicted_value"]))
+        got = [int(out.visit_counts[0, a]) for a in c["root_actions"]]
+        if numerics == "fp32":
+            assert got == c["root_visits"]
+        else:
+            tv = 0.5 * sum(abs(x - y) for x, y in zip(got, c["root_visits"])) / c["num_simulations"]
+            print(f"{name}/tf32 visit counts {got} vs {c['root_visits']} (TV {tv:.3f})")
+            assert tv <= 0.05 and sum(got) == c["num_simulations"]
+        vt = VALUE_TOL[numerics]
+        assert abs(out.root_value[0] - c["root_value"]) <= vt * max(1.0, abs(c["root_value"]))
+        assert abs(out.root_predicted_value[0] - c["root_predicted_value"]) <= vt * max(1.0, abs(c["root_predicted_value"]))
         eng.close()
