@@ -94,6 +94,7 @@ typedef struct MzTrace {
     float* priors;                /* [n, N, A]   fp32 softmax priors of the expanded leaf */
     float* root_priors_raw;       /* [n, A]      root priors before noise (0 for illegal) */
     float* root_reward;           /* [n] */
+    double* noise;                /* [n, A]      Dirichlet noise mixed into the root priors (given or device-drawn) */
 } MzTrace;
 
 /* Teacher forcing: bypass the networks, feed the tree these per-simulation outputs instead. */
@@ -116,7 +117,8 @@ typedef struct MzSearchIO {
     const int32_t* to_play;       /* [n] game.to_play(); NULL = 0 */
     int32_t add_exploration_noise;/* self_play.py:310-314 */
     int32_t flags;                /* MZ_FLAG_* */
-    const double* noise;          /* [n, A] Dirichlet draw by action id (host draws); NULL = device Philox */
+    const double* noise;          /* [n, A] Dirichlet draw by action id (host draws); NULL = drawn on the device
+                                     (Philox + Marsaglia-Tsang gamma, root_dirichlet_alpha) */
     const int32_t* first_index;   /* [n] index into the legal list picked at the first simulation's
                                      all-way tie (self_play.py:371); NULL = device Philox */
     const int64_t* game_id;       /* [n] global game ids keying the Philox stream; NULL = 0..n-1 */

@@ -52,7 +52,7 @@ class MzTensor(C.Structure):
 class MzTrace(C.Structure):
     _fields_ = [("max_depth", C.c_int32), ("reserved", C.c_int32), ("depth", C.c_void_p), ("actions", C.c_void_p),
                 ("value", C.c_void_p), ("reward", C.c_void_p), ("priors", C.c_void_p),
-                ("root_priors_raw", C.c_void_p), ("root_reward", C.c_void_p)]
+                ("root_priors_raw", C.c_void_p), ("root_reward", C.c_void_p), ("noise", C.c_void_p)]
 
 
 class MzTeacher(C.Structure):

@@ -10,7 +10,7 @@ SOURCES = ["abi.cu", "fc_search.cu", "fc_infer.cu", "tree_kernels.cu", "pipeline
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-    "-fmad=false",                      # tree arithmetic must never be contracted; FMAs are explicit fmaf()
+    "-fmad=false", "-diag-suppress", "177",                     # tree arithmetic must never be contracted; FMAs are explicit fmaf()
     "-Xcompiler", "-fPIC", "-Xcompiler", "-O2", "--expt-relaxed-constexpr",
 ]
 

@@ -54,6 +54,11 @@ struct MzHandle {
     unsigned char* h_in = nullptr;
     unsigned char* h_out = nullptr;
     size_t in_cap = 0, out_cap = 0;
+    // CUDA graph of the step-wise pipeline for the last seen argument set (launch-bound inner loop)
+    uint64_t graph_key = 0;
+    int graph_seen = 0;
+    cudaGraphExec_t graph_exec = nullptr;
+    int64_t graph_launches = 0;
     // lazily allocated debug buffers
     std::vector<void*> debug_allocs;
     std::map<std::string, std::pair<void*, size_t>> named;
@@ -237,6 +242,7 @@ extern "C" int mz_destroy(MzHandle* h) {
     for (auto& kv : h->named) cudaFree(kv.second.first);
     if (h->h_in) cudaFreeHost(h->h_in);
     if (h->h_out) cudaFreeHost(h->h_out);
+    if (h->graph_exec) cudaGraphExecDestroy(h->graph_exec);
     if (h->res) resnet_destroy(h->res);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
@@ -330,6 +336,8 @@ extern "C" int mz_load_weights(MzHandle* h, const MzTensor* tensors, int32_t n) 
     if (!h || !tensors || n <= 0) return fail(h, MZ_EINVAL, "mz_load_weights: null argument");
     MZ_CUDA(h, cudaSetDevice(h->device));
     MZ_CUDA(h, cudaStreamSynchronize(h->stream));
+    if (h->graph_exec) { cudaGraphExecDestroy(h->graph_exec); h->graph_exec = nullptr; }   // weight buffers move
+    h->graph_key = 0; h->graph_seen = 0;
     int rc;
     if (h->net.kind == MZ_NET_FC) {
         rc = load_fc_weights(h, tensors, n);
@@ -435,8 +443,6 @@ extern "C" int mz_search(MzHandle* h, const MzSearchIO* io) {
         call.tie_count = io->tie_count; call.root_priors = io->root_priors; call.value_range = io->value_range;
     }
     call.add_noise = io->add_exploration_noise;
-    if (call.add_noise && !call.noise)
-        return fail(h, MZ_EUNSUPPORTED, "mz_search: device-generated Dirichlet noise is not implemented yet; pass `noise`");
     int rc;
     if (teacher) {
         const MzTeacher& t = *io->teacher;
@@ -461,6 +467,7 @@ extern "C" int mz_search(MzHandle* h, const MzSearchIO* io) {
         if ((rc = debug_out(h, "r.priors", t.priors, (size_t)n * N * A, io->mem, &call.trace.priors, dbg_outs))) return rc;
         if ((rc = debug_out(h, "r.root_priors_raw", t.root_priors_raw, (size_t)n * A, io->mem, &call.trace.root_priors_raw, dbg_outs))) return rc;
         if ((rc = debug_out(h, "r.root_reward", t.root_reward, n, io->mem, &call.trace.root_reward, dbg_outs))) return rc;
+        if ((rc = debug_out(h, "r.noise", t.noise, (size_t)n * A, io->mem, &call.trace.noise, dbg_outs))) return rc;
         if (call.trace.depth && (!call.trace.actions || !call.trace.value || !call.trace.reward || !call.trace.priors))
             return fail(h, MZ_EINVAL, "mz_search: trace needs depth, actions, value, reward and priors together");
     }
@@ -471,7 +478,7 @@ extern "C" int mz_search(MzHandle* h, const MzSearchIO* io) {
     if (fused) {
         FcSearchArgs a{};
         a.n_games = n; a.N = N; a.A = A; a.P = h->search.num_players; a.threads = h->fc_threads;
-        a.discount = h->search.discount; a.noise_frac = h->search.root_exploration_fraction; a.seed = h->search.seed;
+        a.discount = h->search.discount; a.noise_frac = h->search.root_exploration_fraction; a.noise_alpha = h->search.root_dirichlet_alpha; a.seed = h->search.seed;
         a.pbc = h->d_pbc; a.sqrtn = h->d_sqrt;
         a.net = h->fc; a.blob = h->d_fc_blob;
         if (teacher) { a.net.E = 1; a.net.maxw = 4; a.net.blob_floats = 0; a.net.A = A; }
@@ -495,9 +502,49 @@ extern "C" int mz_search(MzHandle* h, const MzSearchIO* io) {
             h->launches += 1;
         }
     } else {
-        rc = run_stepwise_search(h->net, h->search, h->pool, h->d_pbc, h->d_sqrt, h->fc, h->d_fc_blob, h->res, call,
-                                 h->fc_group, h->sm_count, h->stream, &h->launches, &h->err);
-        if (rc) return rc;
+        // The step-wise pipeline is 16 small launches per simulation: replay it as a CUDA graph once the
+        // same argument set has been seen twice (first call runs eagerly so lazy attribute setup and
+        // allocations happen outside capture).  Debug modes (teacher / trace) always run eagerly.
+        const bool graphable = !teacher && !io->trace && getenv("MZ_NO_GRAPH") == nullptr;
+        uint64_t key = 1469598103934665603ull;
+        auto mix = [&](uint64_t v) { key = (key ^ v) * 1099511628211ull; };
+        const void* ptrs[] = {call.obs, call.legal_mask, call.to_play, call.noise, call.first_index, call.game_id,
+                              call.move_index, call.visit_counts, call.root_value, call.root_predicted_value,
+                              call.max_tree_depth, call.tie_count, call.root_priors, call.value_range};
+        for (const void* q : ptrs) mix((uint64_t)(uintptr_t)q);
+        mix((uint64_t)n); mix((uint64_t)call.add_noise); mix((uint64_t)call.keep_tree);
+        auto eager = [&]() {
+            return run_stepwise_search(h->net, h->search, h->pool, h->d_pbc, h->d_sqrt, h->fc, h->d_fc_blob, h->res, call,
+                                       h->fc_group, h->sm_count, h->stream, &h->launches, &h->err);
+        };
+        if (graphable && h->graph_exec && h->graph_key == key) {
+            MZ_CUDA(h, cudaGraphLaunch(h->graph_exec, h->stream));
+            h->launches += h->graph_launches;
+        } else if (graphable && h->graph_key == key && h->graph_seen >= 1) {
+            if (h->graph_exec) { cudaGraphExecDestroy(h->graph_exec); h->graph_exec = nullptr; }
+            const int64_t l0 = h->launches;
+            MZ_CUDA(h, cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+            rc = eager();
+            cudaGraph_t graph = nullptr;
+            cudaError_t ce = cudaStreamEndCapture(h->stream, &graph);
+            if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+            if (ce != cudaSuccess) return fail(h, MZ_ECUDA, std::string("graph capture: ") + cudaGetErrorString(ce));
+            ce = cudaGraphInstantiate(&h->graph_exec, graph, 0);
+            cudaGraphDestroy(graph);
+            if (ce != cudaSuccess) { h->graph_exec = nullptr; return fail(h, MZ_ECUDA, std::string("graph instantiate: ") + cudaGetErrorString(ce)); }
+            h->graph_launches = h->launches - l0;
+            MZ_CUDA(h, cudaGraphLaunch(h->graph_exec, h->stream));
+        } else {
+            rc = eager();
+            if (rc) return rc;
+            if (graphable) {
+                if (h->graph_key != key) {
+                    if (h->graph_exec) { cudaGraphExecDestroy(h->graph_exec); h->graph_exec = nullptr; }
+                    h->graph_key = key; h->graph_seen = 0;
+                }
+                h->graph_seen += 1;
+            }
+        }
     }
     MZ_CUDA(h, cudaEventRecord(h->ev1, h->stream));
     if (host && call.out_bytes)

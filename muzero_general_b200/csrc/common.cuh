@@ -102,6 +102,32 @@ MZ_DEVINL int philox_tie_index(uint64_t seed, int64_t game, int move, int sim, i
     return (int)__umulhi(r.x, (uint32_t)n);
 }
 
+// Gamma(alpha, 1) sample for lane-private use (Marsaglia & Tsang 2000, with the alpha < 1 boost
+// gamma(alpha) = gamma(alpha+1) * U^(1/alpha)); uniforms from Philox keyed (game, move, lane, draw).
+// Used to draw the root Dirichlet noise on the device (self_play.py:473) when the host passes none.
+static __device__ __noinline__ double philox_gamma(uint64_t seed, int64_t game, int move, int lane, double alpha) {
+    const double a = alpha < 1.0 ? alpha + 1.0 : alpha;
+    const double d = a - 1.0 / 3.0, c = 1.0 / sqrt(9.0 * d);
+    const double k2 = 1.0 / 4294967296.0;
+    double out = d;
+    for (int it = 0; it < 64; ++it) {
+        const Philox4 r = philox4x32_10((uint32_t)game, (uint32_t)move, (uint32_t)lane, (uint32_t)it,
+                                        (uint32_t)seed, (uint32_t)(seed >> 32) ^ kTagNoise);
+        const double u1 = ((double)r.x + 0.5) * k2, u2 = ((double)r.y + 0.5) * k2, u3 = ((double)r.z + 0.5) * k2;
+        const double x = sqrt(-2.0 * log(u1)) * cospi(2.0 * u2);          // Box-Muller
+        const double t = 1.0 + c * x;
+        if (t <= 0.0) continue;
+        const double v = t * t * t;
+        if (log(u3) < 0.5 * x * x + d - d * v + d * log(v)) { out = d * v; break; }
+    }
+    if (alpha < 1.0) {
+        const Philox4 r = philox4x32_10((uint32_t)game, (uint32_t)move, (uint32_t)lane, 0xFFFFu,
+                                        (uint32_t)seed, (uint32_t)(seed >> 32) ^ kTagNoise);
+        out *= pow(((double)r.x + 0.5) * k2, 1.0 / alpha);
+    }
+    return out;
+}
+
 // ------------------------------------------------------------------------------------------
 // fp32 helpers written with explicit rounding so -fmad cannot change them.
 // ------------------------------------------------------------------------------------------

@@ -59,7 +59,7 @@ __global__ void __launch_bounds__(kFcMaxThreads) fc_search_kernel(const __grid_c
     unsigned char* mine = smem + shared_bytes + (size_t)gi * L.bytes;
 
     TreeConst c;
-    c.A = A; c.N = N; c.P = a.P; c.discount = a.discount; c.noise_frac = a.noise_frac; c.seed = a.seed;
+    c.A = A; c.N = N; c.P = a.P; c.discount = a.discount; c.noise_frac = a.noise_frac; c.noise_alpha = a.noise_alpha; c.seed = a.seed;
     c.pbc = s_pbc; c.sqrtn = s_sqrt;
 
     GameTree t;
@@ -113,7 +113,8 @@ __global__ void __launch_bounds__(kFcMaxThreads) fc_search_kernel(const __grid_c
         if (a.trace.root_priors_raw && lane < A) a.trace.root_priors_raw[(size_t)g * A + lane] = ((legal >> lane) & 1u) ? prior : 0.0f;
         if (a.trace.root_reward && lane == 0) a.trace.root_reward[g] = root_reward;
         tree_init_root<G>(c, t, prior, root_reward,
-                          (a.add_noise && a.noise) ? a.noise + (size_t)g * A : nullptr);
+                          (a.add_noise && a.noise) ? a.noise + (size_t)g * A : nullptr, a.add_noise && !a.noise,
+                          game_id, move, a.trace.noise ? a.trace.noise + (size_t)g * A : nullptr);
 
         // ------------------------------------------------------------------ simulations
         int max_depth = 0;

@@ -10,7 +10,7 @@
 namespace mz {
 
 constexpr int kFcThreads = 128;      // fc_inference_kernel block
-constexpr int kFcMaxThreads = 256;   // upper bound of the fused search kernel's block
+constexpr int kFcMaxThreads = 128;   // upper bound of the fused search kernel's block
 
 // HBM node pool, game-major: game g owns slots [g*(N+1)*A, (g+1)*(N+1)*A).
 struct NodePool {
@@ -45,12 +45,13 @@ struct DevTeacher { const float *root_value, *root_reward, *root_priors, *value,
 struct DevTrace {
     int max_depth;
     int* depth; uint8_t* actions; float *value, *reward, *priors, *root_priors_raw, *root_reward;
+    double* noise;         // [n, A] Dirichlet noise actually mixed in (host-given or device-drawn)
 };
 
 struct FcSearchArgs {
     int n_games, N, A, P;
     int threads;           // block size of the launch (multiple of 32)
-    double discount, noise_frac;
+    double discount, noise_frac, noise_alpha;
     uint64_t seed;
     const double* pbc;
     const double* sqrtn;

@@ -25,7 +25,7 @@ int run_stepwise_search(const MzNetDesc& net, const MzSearchDesc& search, const 
 
     TreeStepArgs a{};
     a.n = n; a.N = N; a.A = A; a.P = search.num_players;
-    a.discount = search.discount; a.noise_frac = search.root_exploration_fraction; a.seed = search.seed;
+    a.discount = search.discount; a.noise_frac = search.root_exploration_fraction; a.noise_alpha = search.root_dirichlet_alpha; a.seed = search.seed;
     a.pbc = d_pbc; a.sqrtn = d_sqrt; a.pool = pool;
     a.legal_mask = call.legal_mask; a.noise = call.noise; a.add_noise = call.add_noise;
     a.first_index = call.first_index; a.game_id = call.game_id; a.move_index = call.move_index;

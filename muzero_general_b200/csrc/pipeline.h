@@ -48,7 +48,7 @@ struct TreeStepArgs {
     int n, N, A, P;
     int sim;                       // simulation selected by this launch (do_select); do_update handles sim-1
     int do_root, do_update, do_select, do_final;
-    double discount, noise_frac;
+    double discount, noise_frac, noise_alpha;
     uint64_t seed;
     const double* pbc;
     const double* sqrtn;

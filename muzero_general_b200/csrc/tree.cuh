@@ -28,6 +28,7 @@ struct TreeConst {
     int P;                 // number of players (1 or 2)
     double discount;
     double noise_frac;     // root_exploration_fraction
+    double noise_alpha;    // root_dirichlet_alpha (device-generated noise only)
     uint64_t seed;
     const double* pbc;     // [N+2]  log((n+base+1)/base)+init
     const double* sqrtn;   // [N+2]  sqrt(n)
@@ -82,14 +83,30 @@ MZ_DEVINL float group_softmax_masked(float logit, bool valid) {
 
 template <int G>
 MZ_DEVINL void tree_init_root(const TreeConst& c, GameTree& t, float prior_f32, float root_reward,
-                              const double* noise /* [A] by action or nullptr */) {
+                              const double* noise /* [A] by action or nullptr */, bool generate_noise = false,
+                              int64_t game_id = 0, int move = 0, double* noise_out = nullptr) {
     const int k = LaneGroup<G>::lane();
+    const bool legal = (k < c.A) && ((t.legal >> k) & 1u);
+    double nz = 0.0;
+    bool have_noise = false;
+    if (noise != nullptr) {
+        nz = legal ? noise[k] : 0.0;
+        have_noise = true;
+    } else if (generate_noise) {
+        // Dirichlet(alpha) over the legal actions = normalised Gamma(alpha) draws (numpy.random.dirichlet)
+        const double gm = legal ? philox_gamma(c.seed, game_id, move, k, c.noise_alpha) : 0.0;
+        double sum = gm;
+        const unsigned m = LaneGroup<G>::mask();
+        for (int off = G >> 1; off > 0; off >>= 1) sum += shfl_xor_f64(m, sum, off, G);
+        nz = gm / sum;
+        have_noise = true;
+    }
+    if (noise_out && k < c.A) noise_out[k] = nz;
     if (k < c.A) {
-        const bool legal = (t.legal >> k) & 1u;
         double p = (double)prior_f32;
-        if (legal && noise != nullptr) {
+        if (legal && have_noise) {
             // prior * (1 - frac) + n * frac       (self_play.py:476)
-            p = __dadd_rn(__dmul_rn(p, __dsub_rn(1.0, c.noise_frac)), __dmul_rn(noise[k], c.noise_frac));
+            p = __dadd_rn(__dmul_rn(p, __dsub_rn(1.0, c.noise_frac)), __dmul_rn(nz, c.noise_frac));
         }
         t.root_prior[k] = legal ? p : 0.0;
         t.visit[k] = 0;

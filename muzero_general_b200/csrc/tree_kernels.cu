@@ -23,7 +23,7 @@ __global__ void __launch_bounds__(128) tree_step_kernel(const __grid_constant__ 
     const NodePool& p = a.pool;
 
     TreeConst c;
-    c.A = A; c.N = N; c.P = a.P; c.discount = a.discount; c.noise_frac = a.noise_frac; c.seed = a.seed;
+    c.A = A; c.N = N; c.P = a.P; c.discount = a.discount; c.noise_frac = a.noise_frac; c.noise_alpha = a.noise_alpha; c.seed = a.seed;
     c.pbc = a.pbc; c.sqrtn = a.sqrtn;
 
     GameTree t;
@@ -48,7 +48,9 @@ __global__ void __launch_bounds__(128) tree_step_kernel(const __grid_constant__ 
         const float root_reward = a.net_reward ? a.net_reward[(size_t)g * a.value_stride] : inverse_value_transform(0.0f);
         if (a.trace.root_priors_raw && lane < A) a.trace.root_priors_raw[(size_t)g * A + lane] = ok ? prior : 0.0f;
         if (a.trace.root_reward && lane == 0) a.trace.root_reward[g] = root_reward;
-        tree_init_root<G>(c, t, prior, root_reward, (a.add_noise && a.noise) ? a.noise + (size_t)g * A : nullptr);
+        tree_init_root<G>(c, t, prior, root_reward, (a.add_noise && a.noise) ? a.noise + (size_t)g * A : nullptr,
+                          a.add_noise && !a.noise, a.game_id ? a.game_id[g] : (int64_t)g, a.move_index ? a.move_index[g] : 0,
+                          a.trace.noise ? a.trace.noise + (size_t)g * A : nullptr);
         if (lane == 0 && a.root_predicted_value) a.root_predicted_value[g] = a.net_value[(size_t)g * a.value_stride];
     } else {
         t.legal = p.legal[g];

@@ -238,7 +238,7 @@ class SearchEngine:
             tr = dict(depth=numpy.zeros((n, N), numpy.int32), actions=numpy.zeros((n, N, D), numpy.uint8),
                       value=numpy.zeros((n, N), numpy.float32), reward=numpy.zeros((n, N), numpy.float32),
                       priors=numpy.zeros((n, N, A), numpy.float32), root_priors_raw=numpy.zeros((n, A), numpy.float32),
-                      root_reward=numpy.zeros(n, numpy.float32))
+                      root_reward=numpy.zeros(n, numpy.float32), noise=numpy.zeros((n, A), numpy.float64))
             t = _lib.MzTrace()
             t.max_depth = D
             for k, v in tr.items():

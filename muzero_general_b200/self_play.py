@@ -268,8 +268,9 @@ def register_as_reference_module():
 class SelfPlay:
     """Plays games and saves them to the replay buffer (self_play.py:11-245)."""
 
-    def __init__(self, initial_checkpoint, Game, config, seed, device=0):
+    def __init__(self, initial_checkpoint, Game, config, seed, device=0, first_game_id=0):
         self.config = config
+        self.first_game_id = int(first_game_id)      # rank * num_parallel_games in a multi-GPU job
         self.Game = Game
         self.seed = seed
         self.num_parallel_games = int(getattr(config, "num_parallel_games", 1) or 1)
@@ -428,7 +429,7 @@ class SelfPlay:
 
     def self_play_stream(self, temperature, temperature_threshold=None):
         """Generator over finished ``GameHistory`` objects; B games advance one move per iteration."""
-        return BatchedSelfPlay(self, temperature, temperature_threshold).run()
+        return BatchedSelfPlay(self, temperature, temperature_threshold, self.first_game_id).run()
 
 
 def _sample_action(actions, visit_counts, temperature, rng):
@@ -485,8 +486,9 @@ class BatchedSelfPlay:
     Per move the host only (1) gathers observations / legal masks from the environments,
     (2) draws the root noise, (3) samples actions from the returned visit counts and
     (4) appends one struct-of-arrays record; ``GameHistory`` objects are materialised only when
-    a game ends.  Game slot g keeps the global id ``seed*0 + g`` for its RNG streams so results do
-    not depend on how many games share the batch (world-size invariance).
+    a game ends.  Game slot g has the global id ``first_game_id + g`` and draws from
+    ``RandomState(seed + global id)``, so a game's history does not depend on how many games share the
+    batch or on how many ranks the batch is split over (world-size invariance).
     """
 
     def __init__(self, worker: SelfPlay, temperature, temperature_threshold, first_game_id=0):

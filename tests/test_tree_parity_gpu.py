@@ -239,3 +239,40 @@ def test_teacher_forced_full_size_vs_c_oracle(game, n, N, stepwise, game_configs
     mask = numpy.arange(D)[None, None, :] < ref["depth"][:, :, None]
     assert (numpy.where(mask, out.trace["actions"], 0) == numpy.where(mask, ref["actions"], 0)).all()
     eng.close()
+
+
+def test_device_drawn_dirichlet_noise(game_configs):
+    """noise=NULL: the root noise is drawn on the device (Philox + Marsaglia-Tsang gamma).  It is a
+    Dirichlet(alpha) sample over the legal actions, keyed by (seed, game id, move), and replaying the
+    search through the oracle with the exported noise reproduces the tree exactly."""
+    cfg = game_configs["connect4"]
+    A, P, N, n = 7, 2, 30, 2048
+    rs = numpy.random.RandomState(21)
+    legal = (rs.uniform(size=(n, A)) < 0.8).astype(numpy.uint8)
+    legal[numpy.arange(n), rs.randint(0, A, n)] = 1
+    t = random_teacher(rs, n, N, A, reward_scale=0.0, legal=legal)
+    to_play = rs.randint(0, P, n).astype(numpy.int32)
+    gid = numpy.arange(n).astype(numpy.int64) + 10_000
+    eng = _engine(cfg, n, N)
+    a = eng.search(legal_mask=legal, to_play=to_play, add_exploration_noise=True, game_id=gid, teacher=t, trace=True, n_games=n)
+    b = eng.search(legal_mask=legal, to_play=to_play, add_exploration_noise=True, game_id=gid, teacher=t, trace=True,
+                   stepwise=True, n_games=n)
+    nz = a.trace["noise"]
+    assert (nz == b.trace["noise"]).all() and (a.visit_counts == b.visit_counts).all()     # deterministic, both paths
+    assert ((nz > 0) == (legal > 0)).all()
+    numpy.testing.assert_allclose(nz.sum(1), 1.0, rtol=1e-12)
+    full = legal.sum(1) == A
+    # Dirichlet(alpha=0.3) over 7 actions: mean 1/7, var = (1/7)(6/7)/(7*0.3+1)
+    numpy.testing.assert_allclose(nz[full].mean(0), 1 / 7, atol=0.02)
+    numpy.testing.assert_allclose(nz[full].var(0), (1 / 7) * (6 / 7) / (A * cfg.root_dirichlet_alpha + 1), rtol=0.15)
+    c = eng.search(legal_mask=legal, to_play=to_play, add_exploration_noise=True, game_id=gid + 1, teacher=t, trace=True, n_games=n)
+    assert (c.trace["noise"] != nz).any()
+    params = om.SearchParams.from_config(cfg, N)
+    for i in range(0, n, 64):
+        acts = [k for k in range(A) if legal[i, k]]
+        res, _ = oracle_replay(params, acts, int(to_play[i]),
+                               (t["root_value"][i], t["root_reward"][i], [t["root_priors"][i, k] for k in acts]),
+                               [(t["value"][i, s], t["reward"][i, s], t["priors"][i, s]) for s in range(N)],
+                               [nz[i, k] for k in acts], None, seed=cfg.seed, game=int(gid[i]))
+        assert [int(a.visit_counts[i, k]) for k in acts] == res.root_visits and a.root_value[i] == res.root_value
+    eng.close()
