@@ -14,6 +14,7 @@
 // This is the exact-fp32 path ("strict" numerics, also the validation reference for the
 // tensor-core path).
 #include <math.h>
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -202,6 +203,8 @@ struct HeadsArgs {
     int smem_floats;
     int p64c4, W;              // input (and pool target) use the tensor-core board layout
     float* state_p64c4;        // [n, 4096] rescaled state in P64C4 (input of the prediction tower), or nullptr
+    int w_lo, w_floats;        // slice of the head blob this launch needs (staged in shared memory)
+    int warp_floats;           // per-warp scratch: x tile + two activation vectors
 };
 
 // offset of (channel c, dense position p) inside one P64C4 state
@@ -209,83 +212,101 @@ __device__ __forceinline__ int p64c4_index(int c, int p, int W) {
     return ((c >> 2) * 64 + (p / W + 1) * 8 + (p % W)) * 4 + (c & 3);
 }
 
-__global__ void __launch_bounds__(128) heads_kernel(const __grid_constant__ HeadsArgs a) {
+// Persistent CTAs (one per SM): the head weights of this launch are staged in shared memory once per
+// CTA, then every WARP takes one sample at a time: x is read as 16-byte chunks into a padded
+// [position][channel] tile (conflict-free for both the per-channel rescale and the per-position
+// conv1x1), lanes own positions in the conv1x1 and output units in the MLP layers.
+__global__ void __launch_bounds__(256) heads_kernel(const __grid_constant__ HeadsArgs a) {
     extern __shared__ __align__(16) float sm[];
-    const int g = blockIdx.x;
-    const int C = a.C, HW = a.HW;
-    float* s_x = sm;                              // [C*HW]
-    float* s_a = s_x + C * HW;                    // activations ping
-    float* s_b = s_a + a.smem_floats;             // activations pong
-    if (a.p64c4) {
-        const float* x = a.x + (size_t)g * 4096;
-        for (int i = threadIdx.x; i < C * HW; i += blockDim.x) s_x[i] = x[p64c4_index(i / HW, i % HW, a.W)];
-    } else {
-        const float* x = a.x + (size_t)g * C * HW;
-        for (int i = threadIdx.x; i < C * HW; i += blockDim.x) s_x[i] = x[i];
-    }
+    const int C = a.C, HW = a.HW, CP = C + 1;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    float* s_w = sm;                                            // head blob slice [w_lo, w_hi)
+    float* s_x = s_w + a.w_floats + (size_t)warp * a.warp_floats;   // [HW][C+1]
+    float* s_a = s_x + HW * CP;                                 // activations ping
+    float* s_b = s_a + a.smem_floats;                           // activations pong
+    for (int i = threadIdx.x; i < a.w_floats; i += blockDim.x) s_w[i] = a.blob[a.w_lo + i];
     __syncthreads();
+    const float* blob = s_w - a.w_lo;                           // so that blob[off] addresses the staged copy
 
-    if (a.rescaled || a.pool_hidden || a.state_p64c4) {
-        // one warp per channel: min / max over HW, then (x - min) / scale
-        const int warp = threadIdx.x / 32, lane = threadIdx.x % 32, nw = blockDim.x / 32;
-        for (int c = warp; c < C; c += nw) {
-            float lo = INFINITY, hi = -INFINITY;
-            for (int i = lane; i < HW; i += 32) { lo = fminf(lo, s_x[c * HW + i]); hi = fmaxf(hi, s_x[c * HW + i]); }
-            lo = -group_max_f32<32>(-lo);
-            hi = group_max_f32<32>(hi);
-            float sc = __fsub_rn(hi, lo);
-            if (sc < 1e-5f) sc = __fadd_rn(sc, 1e-5f);
-            for (int i = lane; i < HW; i += 32) {
-                const float v = __fdiv_rn(__fsub_rn(s_x[c * HW + i], lo), sc);
-                if (a.rescaled) a.rescaled[(size_t)g * C * HW + c * HW + i] = v;
-                if (a.p64c4) {
-                    // operands of the tf32 tensor-core convs: round to nearest once, here
-                    uint32_t rb;
-                    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(rb) : "f"(v));
-                    const float vt = __uint_as_float(rb);
-                    const int off = p64c4_index(c, i, a.W);
-                    if (a.pool_hidden) a.pool_hidden[((size_t)g * a.pool_stride + a.out_slot) * 4096 + off] = vt;
-                    if (a.state_p64c4) a.state_p64c4[(size_t)g * 4096 + off] = vt;
-                } else if (a.pool_hidden) {
-                    a.pool_hidden[((size_t)g * a.pool_stride + a.out_slot) * C * HW + c * HW + i] = v;
+    for (int g = blockIdx.x * nwarps + warp; g < a.n; g += gridDim.x * nwarps) {
+        // ---- stage x[p][c]
+        if (a.p64c4) {
+            const float4* x4 = reinterpret_cast<const float4*>(a.x + (size_t)g * 4096);
+            for (int i = lane; i < (C / 4) * HW; i += 32) {
+                const int j = i / HW, p = i % HW;
+                const float4 v = x4[j * 64 + (p / a.W + 1) * 8 + (p % a.W)];
+                float* d = s_x + p * CP + 4 * j;
+                d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+            }
+        } else {
+            const float* x = a.x + (size_t)g * C * HW;
+            for (int i = lane; i < C * HW; i += 32) s_x[(i % HW) * CP + i / HW] = x[i];
+        }
+        __syncwarp();
+
+        if (a.rescaled || a.pool_hidden || a.state_p64c4) {
+            // lanes own channels: min / max over the positions, then (x - min) / scale   (models.py:530-553)
+            for (int c = lane; c < C; c += 32) {
+                float lo = INFINITY, hi = -INFINITY;
+                for (int p = 0; p < HW; ++p) { const float v = s_x[p * CP + c]; lo = fminf(lo, v); hi = fmaxf(hi, v); }
+                float sc = __fsub_rn(hi, lo);
+                if (sc < 1e-5f) sc = __fadd_rn(sc, 1e-5f);
+                for (int p = 0; p < HW; ++p) {
+                    const float v = __fdiv_rn(__fsub_rn(s_x[p * CP + c], lo), sc);
+                    if (a.rescaled) a.rescaled[(size_t)g * C * HW + c * HW + p] = v;
+                    if (a.p64c4) {
+                        uint32_t rb;                      // operands of the tf32 convs: round to nearest once, here
+                        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(rb) : "f"(v));
+                        const float vt = __uint_as_float(rb);
+                        const int off = p64c4_index(c, p, a.W);
+                        if (a.pool_hidden) a.pool_hidden[((size_t)g * a.pool_stride + a.out_slot) * 4096 + off] = vt;
+                        if (a.state_p64c4) a.state_p64c4[(size_t)g * 4096 + off] = vt;
+                    } else if (a.pool_hidden) {
+                        a.pool_hidden[((size_t)g * a.pool_stride + a.out_slot) * C * HW + c * HW + p] = v;
+                    }
                 }
             }
         }
-    }
 
-    for (int h = 0; h < a.n_heads; ++h) {
-        const HeadDesc& d = a.head[h];
-        __syncthreads();
-        // conv1x1: r[c][p] = b[c] + sum_k W[c][k] x[k][p]
-        for (int i = threadIdx.x; i < d.rc * HW; i += blockDim.x) {
-            const int c = i / HW, p = i % HW;
-            float acc = a.blob[d.b1_off + c];
-            const float* w = a.blob + d.w1_off + c * C;
-            for (int k = 0; k < C; ++k) acc = fmaf(w[k], s_x[k * HW + p], acc);
-            s_a[i] = acc;                         // flatten order (c, h, w) = NCHW view(-1, ...)
-        }
-        __syncthreads();
-        float* cur = s_a;
-        float* nxt = s_b;
-        for (int l = 0; l < d.mlp.n; ++l) {
-            const int in = d.mlp.in[l], out = d.mlp.out[l];
-            const float* W = a.blob + d.mlp.w_off[l];
-            const float* b = a.blob + d.mlp.b_off[l];
-            const bool last = l == d.mlp.n - 1;
-            for (int o = threadIdx.x; o < out; o += blockDim.x) {
-                float acc = b[o];
-                for (int i = 0; i < in; ++i) acc = fmaf(cur[i], W[(size_t)i * out + o], acc);
-                nxt[o] = last ? acc : elu1(acc);
+        for (int h = 0; h < a.n_heads; ++h) {
+            const HeadDesc& d = a.head[h];
+            __syncwarp();
+            // conv1x1: r[c][p] = b[c] + sum_k W[c][k] x[p][k]; lanes own positions
+            for (int p = lane; p < HW; p += 32) {
+                const float* xr = s_x + p * CP;
+                for (int c = 0; c < d.rc; ++c) {
+                    float acc = blob[d.b1_off + c];
+                    const float* w = blob + d.w1_off + c * C;
+#pragma unroll 8
+                    for (int k = 0; k < C; ++k) acc = fmaf(w[k], xr[k], acc);
+                    s_a[c * HW + p] = acc;                // flatten order (c, h, w) = NCHW view(-1, ...)
+                }
             }
-            __syncthreads();
-            float* t = cur; cur = nxt; nxt = t;
+            __syncwarp();
+            float* cur = s_a;
+            float* nxt = s_b;
+            for (int l = 0; l < d.mlp.n; ++l) {
+                const int in = d.mlp.in[l], out = d.mlp.out[l];
+                const float* W = blob + d.mlp.w_off[l];
+                const float* b = blob + d.mlp.b_off[l];
+                const bool last = l == d.mlp.n - 1;
+                for (int o = lane; o < out; o += 32) {
+                    float acc = b[o];
+#pragma unroll 8
+                    for (int i = 0; i < in; ++i) acc = fmaf(cur[i], W[(size_t)i * out + o], acc);
+                    nxt[o] = last ? acc : elu1(acc);
+                }
+                __syncwarp();
+                float* t = cur; cur = nxt; nxt = t;
+            }
+            if (a.logits[h])
+                for (int o = lane; o < d.n_out; o += 32) a.logits[h][(size_t)g * d.n_out + o] = cur[o];
+            if (a.scalar[h]) {
+                const float v = support_to_scalar_group<32>(cur, a.S);
+                if (lane == 0) a.scalar[h][g] = v;
+            }
         }
-        if (a.logits[h])
-            for (int o = threadIdx.x; o < d.n_out; o += blockDim.x) a.logits[h][(size_t)g * d.n_out + o] = cur[o];
-        if (a.scalar[h] && threadIdx.x < 32) {
-            const float v = support_to_scalar_group<32>(cur, a.S);
-            if (threadIdx.x == 0) a.scalar[h][g] = v;
-        }
+        __syncwarp();
     }
 }
 
@@ -682,14 +703,29 @@ struct Runner {
         a.logits[0] = l0; a.logits[1] = l1; a.scalar[0] = s0; a.scalar[1] = s1;
         a.rescaled = rescaled; a.pool_hidden = pool_hidden; a.pool_stride = pool_stride; a.out_slot = out_slot;
         a.smem_floats = (maxw + 3) & ~3;
-        const size_t smem = ((size_t)a.C * a.HW + 2 * a.smem_floats) * 4;
+        // blob slice covering the heads of this launch
+        int lo = 1 << 30, hi = 0;
+        for (int i = 0; i < n_heads; ++i) {
+            const HeadDesc& d = *hs[i];
+            lo = std::min(lo, d.w1_off);
+            const int last = d.mlp.n - 1;
+            hi = std::max(hi, d.mlp.b_off[last] + d.mlp.out[last]);
+        }
+        if (n_heads == 0) { lo = 0; hi = 0; }
+        a.w_lo = lo; a.w_floats = ((hi - lo) + 3) & ~3;
+        a.warp_floats = (a.HW * (a.C + 1) + 2 * a.smem_floats + 3) & ~3;
+        const int threads = 256;
+        const size_t smem = ((size_t)a.w_floats + (size_t)(threads / 32) * a.warp_floats) * 4;
+        if (smem > 227 * 1024) { *err = "heads: weights + tiles exceed shared memory"; return false; }
         static size_t attr_smem = 0;
         if (attr_smem < smem) {
             cudaError_t e0 = cudaFuncSetAttribute(heads_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e0 != cudaSuccess) return fail("heads attr", e0);
             attr_smem = smem;
         }
-        heads_kernel<<<n, 128, smem, stream>>>(a);
+        int grid = (n + threads / 32 - 1) / (threads / 32);
+        if (grid > r->sm_count) grid = r->sm_count;
+        heads_kernel<<<grid, threads, smem, stream>>>(a);
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return fail("heads launch", e);
         *launches += 1;
@@ -797,6 +833,26 @@ int resnet_debug_conv(int n, int C, int H, int W, const float* x, const float* w
     }
     cudaError_t e = cudaDeviceSynchronize();
     if (good && e != cudaSuccess) { good = false; *err = std::string("debug conv: ") + cudaGetErrorString(e); }
+    // optional warm-L2 timing of the bare kernel: MZ_DEBUG_CONV_REPS=k prints the mean of k back-to-back launches
+    const char* reps_env = getenv("MZ_DEBUG_CONV_REPS");
+    if (good && reps_env && atoi(reps_env) > 0) {
+        const int reps = atoi(reps_env);
+        cudaEvent_t e0, e1;
+        cudaEventCreate(&e0); cudaEventCreate(&e1);
+        cudaEventRecord(e0);
+        for (int i = 0; i < reps; ++i) {
+            if (use_tc) R.conv_tc(layers[0], d_px, d_pout, residual ? d_pres : nullptr, relu != 0);
+            else R.conv(layers[0], d_x, d_out, residual ? d_res : nullptr, relu != 0, H, W);
+        }
+        cudaEventRecord(e1);
+        cudaEventSynchronize(e1);
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        const double flops = 2.0 * n * H * W * (double)C * C * 9;
+        fprintf(stderr, "[mz_debug_conv3x3] %s n=%d C=%d %dx%d residual=%d: %.2f us per launch, %.1f TFLOP/s useful\n",
+                use_tc ? "tcgen05" : "cuda-core", n, C, H, W, residual ? 1 : 0, 1000.0 * ms / reps, flops / (ms / reps * 1e-3) / 1e12);
+        cudaEventDestroy(e0); cudaEventDestroy(e1);
+    }
     if (good) cudaMemcpy(out, d_out, dense * 4, cudaMemcpyDeviceToHost);
     r.d_conv = nullptr;
     cleanup();
