@@ -17,8 +17,9 @@
 // optional residual and the optional action-plane term (models.py:557-572 folded into a
 // per-position table), apply ReLU, zero the padding positions and store P64C4 again.
 //
-// Warp roles (256 threads): 0 = bulk-copy producer, 1 = MMA issuer, 2 = TMEM allocator,
-// 4..7 = epilogue (TMEM lane quarter = warp % 4).
+// Warp roles (384 threads): 0 = bulk-copy producer, 1 = MMA issuer, 2 = TMEM allocator,
+// 4..11 = epilogue (TMEM lane quarter = warp % 4, accumulator column half = (warp - 4) / 4); the
+// epilogue prefetches its residual / action terms before it waits for the accumulator.
 #include "pipeline.h"
 #include "conv_tc.h"
 
@@ -38,7 +39,8 @@ constexpr int kStages = 2;
 constexpr int kWBytes = 9 * kPlanes * kC * 16;         // 147456
 constexpr int kTapBytes = kPlanes * kC * 16;           // 16384
 constexpr int kAccCols = 64;
-constexpr int kThreads = 256;
+constexpr int kThreads = 384;             // 4 control warps + 8 epilogue warps
+constexpr int kEpiWarps = 8;
 
 struct Smem {
     // offsets
@@ -46,7 +48,7 @@ struct Smem {
     static constexpr int a = kWBytes;
     static constexpr int bias = a + kStages * kStageBytes;                 // 64 floats
     static constexpr int bars = bias + kC * 4;                             // 8-byte aligned
-    static constexpr int tmem_ptr = bars + 16 * 8;
+    static constexpr int tmem_ptr = bars + 32 * 8;
     static constexpr int total = tmem_ptr + 16;
 };
 static_assert(Smem::total <= 232448, "shared memory budget");
@@ -120,26 +122,30 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_tc_kernel(const __grid_co
     float* s_bias = reinterpret_cast<float*>(smem + Smem::bias);
     const uint32_t bars = s_base + Smem::bars;
     // barrier ids
-    const uint32_t bar_w = bars;                                          // weights landed
-    auto bar_a_full = [&](int s) { return bars + 8u * (1 + s); };
-    auto bar_a_empty = [&](int s) { return bars + 8u * (3 + s); };
-    auto bar_acc_full = [&](int s) { return bars + 8u * (5 + s); };
-    auto bar_acc_empty = [&](int s) { return bars + 8u * (7 + s); };
+    auto bar_w = [&](int tap) { return bars + 8u * tap; };                // weights of one filter tap landed
+    auto bar_a_full = [&](int s) { return bars + 8u * (9 + s); };
+    auto bar_a_empty = [&](int s) { return bars + 8u * (11 + s); };
+    auto bar_acc_full = [&](int s) { return bars + 8u * (13 + s); };
+    auto bar_acc_empty = [&](int s) { return bars + 8u * (15 + s); };
     volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + Smem::tmem_ptr);
 
     const int n_tiles = (a.n + kBoards - 1) / kBoards;
 
     // ---- one-time setup
-    for (int i = threadIdx.x; i < kStages * kStageBytes / 16; i += kThreads)      // zero A (halo rows stay zero)
-        reinterpret_cast<uint4*>(smem + Smem::a)[i] = make_uint4(0, 0, 0, 0);
+    // zero the halo rows of every plane (the board rows are always overwritten by the bulk copies)
+    for (int i = threadIdx.x; i < kStages * kPlanes * 2 * kHalo; i += kThreads) {
+        const int r = i % (2 * kHalo), pl = i / (2 * kHalo);
+        const int row = r < kHalo ? r : kRows - 2 * kHalo + r;
+        reinterpret_cast<uint4*>(smem + Smem::a + pl * kPlaneBytes)[row] = make_uint4(0, 0, 0, 0);
+    }
     if (threadIdx.x < kC) s_bias[threadIdx.x] = a.bias ? a.bias[threadIdx.x] : 0.0f;
     if (threadIdx.x == 0) {
-        mbar_init(bar_w, 1);
+        for (int t = 0; t < 9; ++t) mbar_init(bar_w(t), 1);
         for (int s = 0; s < kStages; ++s) {
             mbar_init(bar_a_full(s), 1);
             mbar_init(bar_a_empty(s), 1);
             mbar_init(bar_acc_full(s), 1);
-            mbar_init(bar_acc_empty(s), 4);           // one arrival per epilogue warp
+            mbar_init(bar_acc_empty(s), kEpiWarps);   // one arrival per epilogue warp
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -156,10 +162,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_tc_kernel(const __grid_co
 
     if (warp == 0) {
         // ================= producer =================
-        if (lane == 0) {
-            mbar_expect_tx(bar_w, kWBytes);
-            for (int t = 0; t < 9; ++t)
-                bulk_g2s(s_w + t * kTapBytes, reinterpret_cast<const unsigned char*>(a.w) + (size_t)t * kTapBytes, kTapBytes, bar_w);
+        if (lane < 9) {                                // one barrier per tap: the MMAs of tap t start as soon as it landed
+            mbar_expect_tx(bar_w(lane), kTapBytes);
+            bulk_g2s(s_w + lane * kTapBytes, reinterpret_cast<const unsigned char*>(a.w) + (size_t)lane * kTapBytes, kTapBytes, bar_w(lane));
         }
         int it = 0;
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
@@ -183,7 +188,6 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_tc_kernel(const __grid_co
         }
     } else if (warp == 1) {
         // ================= MMA issuer =================
-        mbar_wait(bar_w, 0);
         int it = 0;
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
             const int s = it % kStages;
@@ -196,6 +200,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_tc_kernel(const __grid_co
                 uint32_t acc = 0;
 #pragma unroll 1
                 for (int tap = 0; tap < 9; ++tap) {
+                    if (it == 0) { mbar_wait(bar_w(tap), 0); tc_fence_after(); }
                     const int shift = (tap / 3 - 1) * 8 + (tap % 3 - 1);
                     const uint32_t a0 = s_a + s * kStageBytes + (kHalo + shift) * 16;
                     const uint32_t b0 = s_w + tap * kTapBytes;
@@ -215,64 +220,69 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_tc_kernel(const __grid_co
     } else if (warp >= 4) {
         // ================= epilogue =================
         const int q = warp & 3;                       // TMEM lane quarter
+        const int half = (warp - 4) >> 2;             // accumulator columns [32*half, 32*half+32)
         const int row = q * 32 + lane;                // tile row = TMEM lane
         const int b = row / kPos, p = row % kPos;
         const int y = p / 8 - 1, x = p % 8;
         const bool inside = (y >= 0 && y < a.H && x < a.W);
+        constexpr int kJ = kPlanes / 2;               // channel groups handled by this warp
         int it = 0;
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
             const int s = it % kStages;
             const uint32_t ph = (it / kStages) & 1;
+            const int g = tile * kBoards + b;
+            const bool live = inside && g < a.n;
+            // ---- prefetch everything that does not depend on the accumulator
+            float4 add[kJ];
+#pragma unroll
+            for (int j = 0; j < kJ; ++j) add[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (live) {
+                if (a.residual) {
+                    const float* res = a.residual + (size_t)g * (kC * kPos) + (size_t)p * 4 + (size_t)(half * kJ) * kPos * 4;
+#pragma unroll
+                    for (int j = 0; j < kJ; ++j) add[j] = *reinterpret_cast<const float4*>(res + (size_t)j * kPos * 4);
+                }
+                if (a.action) {
+                    const float sc = __fdiv_rn((float)a.action[g], (float)a.A);
+                    const float* atab = a.action_table + (size_t)p * kC + half * 32;
+#pragma unroll
+                    for (int j = 0; j < kJ; ++j) {
+                        const float4 t4 = *reinterpret_cast<const float4*>(atab + 4 * j);
+                        add[j].x = fmaf(sc, t4.x, add[j].x); add[j].y = fmaf(sc, t4.y, add[j].y);
+                        add[j].z = fmaf(sc, t4.z, add[j].z); add[j].w = fmaf(sc, t4.w, add[j].w);
+                    }
+                }
+            }
             mbar_wait(bar_acc_full(s), ph);
             tc_fence_after();
-            uint32_t v[64];
-            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(s * kAccCols);
+            uint32_t v[32];
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(s * kAccCols + half * 32);
             asm volatile(
-                "tcgen05.ld.sync.aligned.32x32b.x64.b32 "
+                "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
                 "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-                "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, "
-                "%32, %33, %34, %35, %36, %37, %38, %39, %40, %41, %42, %43, %44, %45, %46, %47, "
-                "%48, %49, %50, %51, %52, %53, %54, %55, %56, %57, %58, %59, %60, %61, %62, %63}, [%64];"
+                "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
                   "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
                   "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
-                  "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31]),
-                  "=r"(v[32]), "=r"(v[33]), "=r"(v[34]), "=r"(v[35]), "=r"(v[36]), "=r"(v[37]), "=r"(v[38]), "=r"(v[39]),
-                  "=r"(v[40]), "=r"(v[41]), "=r"(v[42]), "=r"(v[43]), "=r"(v[44]), "=r"(v[45]), "=r"(v[46]), "=r"(v[47]),
-                  "=r"(v[48]), "=r"(v[49]), "=r"(v[50]), "=r"(v[51]), "=r"(v[52]), "=r"(v[53]), "=r"(v[54]), "=r"(v[55]),
-                  "=r"(v[56]), "=r"(v[57]), "=r"(v[58]), "=r"(v[59]), "=r"(v[60]), "=r"(v[61]), "=r"(v[62]), "=r"(v[63])
+                  "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
                 : "r"(taddr));
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(bar_acc_empty(s));        // accumulator may be overwritten
-            const int g = tile * kBoards + b;
+            if (lane == 0) mbar_arrive(bar_acc_empty(s));        // accumulator half read: may be overwritten
             if (g < a.n) {
-                float* dst = a.out + (size_t)g * (kC * kPos) + (size_t)p * 4;
-                const float* res = a.residual ? a.residual + (size_t)g * (kC * kPos) + (size_t)p * 4 : nullptr;
-                const float act_scale = a.action ? __fdiv_rn((float)a.action[g], (float)a.A) : 0.0f;
-                const float* atab = a.action ? a.action_table + (size_t)p * kC : nullptr;
+                float* dst = a.out + (size_t)g * (kC * kPos) + (size_t)p * 4 + (size_t)(half * kJ) * kPos * 4;
 #pragma unroll
-                for (int j = 0; j < kPlanes; ++j) {
+                for (int j = 0; j < kJ; ++j) {
                     float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
                     if (inside) {
-                        float r[4];
-#pragma unroll
-                        for (int c = 0; c < 4; ++c) r[c] = __uint_as_float(v[4 * j + c]) + s_bias[4 * j + c];
-                        if (atab) {
-                            const float4 t4 = *reinterpret_cast<const float4*>(atab + 4 * j);
-                            r[0] = fmaf(act_scale, t4.x, r[0]); r[1] = fmaf(act_scale, t4.y, r[1]);
-                            r[2] = fmaf(act_scale, t4.z, r[2]); r[3] = fmaf(act_scale, t4.w, r[3]);
-                        }
-                        if (res) {
-                            const float4 r4 = *reinterpret_cast<const float4*>(res + (size_t)j * kPos * 4);
-                            r[0] += r4.x; r[1] += r4.y; r[2] += r4.z; r[3] += r4.w;
-                        }
-                        if (a.relu) {
-#pragma unroll
-                            for (int c = 0; c < 4; ++c) r[c] = fmaxf(r[c], 0.0f);
-                        }
-                        o = make_float4(round_tf32(r[0]), round_tf32(r[1]), round_tf32(r[2]), round_tf32(r[3]));
+                        const int c0 = half * 32 + 4 * j;
+                        float r0 = __uint_as_float(v[4 * j + 0]) + s_bias[c0 + 0] + add[j].x;
+                        float r1 = __uint_as_float(v[4 * j + 1]) + s_bias[c0 + 1] + add[j].y;
+                        float r2 = __uint_as_float(v[4 * j + 2]) + s_bias[c0 + 2] + add[j].z;
+                        float r3 = __uint_as_float(v[4 * j + 3]) + s_bias[c0 + 3] + add[j].w;
+                        if (a.relu) { r0 = fmaxf(r0, 0.f); r1 = fmaxf(r1, 0.f); r2 = fmaxf(r2, 0.f); r3 = fmaxf(r3, 0.f); }
+                        o = make_float4(round_tf32(r0), round_tf32(r1), round_tf32(r2), round_tf32(r3));
                     }
                     *reinterpret_cast<float4*>(dst + (size_t)j * kPos * 4) = o;
                 }

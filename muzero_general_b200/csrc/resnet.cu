@@ -212,27 +212,38 @@ __device__ __forceinline__ int p64c4_index(int c, int p, int W) {
     return ((c >> 2) * 64 + (p / W + 1) * 8 + (p % W)) * 4 + (c & 3);
 }
 
-// Persistent CTAs (one per SM): the head weights of this launch are staged in shared memory once per
-// CTA, then every WARP takes one sample at a time: x is read as 16-byte chunks into a padded
-// [position][channel] tile (conflict-free for both the per-channel rescale and the per-position
-// conv1x1), lanes own positions in the conv1x1 and output units in the MLP layers.
-__global__ void __launch_bounds__(256) heads_kernel(const __grid_constant__ HeadsArgs a) {
+// Persistent CTAs (one per SM), 512 threads = 4 groups of 128: the head weights of this launch are staged
+// in shared memory once per CTA, then every GROUP takes one sample at a time (named barriers, groups never
+// wait for each other).  x is read as 16-byte chunks into a padded [position][channel] tile
+// (conflict-free for the per-channel rescale and the per-position conv1x1); the two heads of a launch
+// (value + policy) run side by side on the two halves of the group.
+constexpr int kHeadGroup = 128;
+constexpr int kHeadThreads = 512;
+
+__device__ __forceinline__ void group_bar(int group) {
+    asm volatile("bar.sync %0, %1;" ::"r"(group + 1), "r"(kHeadGroup) : "memory");
+}
+
+__global__ void __launch_bounds__(kHeadThreads) heads_kernel(const __grid_constant__ HeadsArgs a) {
     extern __shared__ __align__(16) float sm[];
     const int C = a.C, HW = a.HW, CP = C + 1;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
-    float* s_w = sm;                                            // head blob slice [w_lo, w_hi)
-    float* s_x = s_w + a.w_floats + (size_t)warp * a.warp_floats;   // [HW][C+1]
-    float* s_a = s_x + HW * CP;                                 // activations ping
-    float* s_b = s_a + a.smem_floats;                           // activations pong
-    for (int i = threadIdx.x; i < a.w_floats; i += blockDim.x) s_w[i] = a.blob[a.w_lo + i];
+    const int group = threadIdx.x / kHeadGroup, t = threadIdx.x % kHeadGroup, ngroups = blockDim.x / kHeadGroup;
+    float* s_w = sm;                                                 // head blob slice [w_lo, w_lo + w_floats)
+    float* s_x = s_w + a.w_floats + (size_t)group * a.warp_floats;   // [HW][C+1]
+    float* s_act = s_x + HW * CP;                                    // per head: ping | pong
+    {
+        const float4* src = reinterpret_cast<const float4*>(a.blob + a.w_lo);
+        float4* dst = reinterpret_cast<float4*>(s_w);
+        for (int i = threadIdx.x; i < a.w_floats / 4; i += blockDim.x) dst[i] = src[i];
+    }
     __syncthreads();
-    const float* blob = s_w - a.w_lo;                           // so that blob[off] addresses the staged copy
+    const float* blob = s_w - a.w_lo;                                // blob[off] addresses the staged copy
 
-    for (int g = blockIdx.x * nwarps + warp; g < a.n; g += gridDim.x * nwarps) {
+    for (int g = blockIdx.x * ngroups + group; g < a.n; g += gridDim.x * ngroups) {
         // ---- stage x[p][c]
         if (a.p64c4) {
             const float4* x4 = reinterpret_cast<const float4*>(a.x + (size_t)g * 4096);
-            for (int i = lane; i < (C / 4) * HW; i += 32) {
+            for (int i = t; i < (C / 4) * HW; i += kHeadGroup) {
                 const int j = i / HW, p = i % HW;
                 const float4 v = x4[j * 64 + (p / a.W + 1) * 8 + (p % a.W)];
                 float* d = s_x + p * CP + 4 * j;
@@ -240,13 +251,13 @@ __global__ void __launch_bounds__(256) heads_kernel(const __grid_constant__ Head
             }
         } else {
             const float* x = a.x + (size_t)g * C * HW;
-            for (int i = lane; i < C * HW; i += 32) s_x[(i % HW) * CP + i / HW] = x[i];
+            for (int i = t; i < C * HW; i += kHeadGroup) s_x[(i % HW) * CP + i / HW] = x[i];
         }
-        __syncwarp();
+        group_bar(group);
 
         if (a.rescaled || a.pool_hidden || a.state_p64c4) {
-            // lanes own channels: min / max over the positions, then (x - min) / scale   (models.py:530-553)
-            for (int c = lane; c < C; c += 32) {
+            // threads own channels: min / max over the positions, then (x - min) / scale   (models.py:530-553)
+            for (int c = t; c < C; c += kHeadGroup) {
                 float lo = INFINITY, hi = -INFINITY;
                 for (int p = 0; p < HW; ++p) { const float v = s_x[p * CP + c]; lo = fminf(lo, v); hi = fmaxf(hi, v); }
                 float sc = __fsub_rn(hi, lo);
@@ -268,45 +279,49 @@ __global__ void __launch_bounds__(256) heads_kernel(const __grid_constant__ Head
             }
         }
 
-        for (int h = 0; h < a.n_heads; ++h) {
+        if (a.n_heads > 0) {
+            // the heads of this launch side by side: head h owns threads [h*span, (h+1)*span)
+            const int span = kHeadGroup / a.n_heads;
+            const int h = t / span, u = t % span;
             const HeadDesc& d = a.head[h];
-            __syncwarp();
-            // conv1x1: r[c][p] = b[c] + sum_k W[c][k] x[p][k]; lanes own positions
-            for (int p = lane; p < HW; p += 32) {
+            float* cur = s_act + (size_t)h * 2 * a.smem_floats;
+            float* nxt = cur + a.smem_floats;
+            // conv1x1: r[c][p] = b[c] + sum_k W[c][k] x[p][k]
+            for (int i = u; i < d.rc * HW; i += span) {
+                const int c = i / HW, p = i % HW;
                 const float* xr = s_x + p * CP;
-                for (int c = 0; c < d.rc; ++c) {
-                    float acc = blob[d.b1_off + c];
-                    const float* w = blob + d.w1_off + c * C;
+                const float* w = blob + d.w1_off + c * C;
+                float acc = blob[d.b1_off + c];
 #pragma unroll 8
-                    for (int k = 0; k < C; ++k) acc = fmaf(w[k], xr[k], acc);
-                    s_a[c * HW + p] = acc;                // flatten order (c, h, w) = NCHW view(-1, ...)
-                }
+                for (int k = 0; k < C; ++k) acc = fmaf(w[k], xr[k], acc);
+                cur[i] = acc;                             // flatten order (c, h, w) = NCHW view(-1, ...)
             }
-            __syncwarp();
-            float* cur = s_a;
-            float* nxt = s_b;
-            for (int l = 0; l < d.mlp.n; ++l) {
-                const int in = d.mlp.in[l], out = d.mlp.out[l];
-                const float* W = blob + d.mlp.w_off[l];
-                const float* b = blob + d.mlp.b_off[l];
-                const bool last = l == d.mlp.n - 1;
-                for (int o = lane; o < out; o += 32) {
-                    float acc = b[o];
+            group_bar(group);
+            const int max_layers = max(a.head[0].mlp.n, a.head[a.n_heads - 1].mlp.n);
+            for (int l = 0; l < max_layers; ++l) {
+                if (l < d.mlp.n) {
+                    const int in = d.mlp.in[l], out = d.mlp.out[l];
+                    const float* W = blob + d.mlp.w_off[l];
+                    const float* b = blob + d.mlp.b_off[l];
+                    const bool last = l == d.mlp.n - 1;
+                    for (int o = u; o < out; o += span) {
+                        float acc = b[o];
 #pragma unroll 8
-                    for (int i = 0; i < in; ++i) acc = fmaf(cur[i], W[(size_t)i * out + o], acc);
-                    nxt[o] = last ? acc : elu1(acc);
+                        for (int i = 0; i < in; ++i) acc = fmaf(cur[i], W[(size_t)i * out + o], acc);
+                        nxt[o] = last ? acc : elu1(acc);
+                    }
+                    float* tmp = cur; cur = nxt; nxt = tmp;
                 }
-                __syncwarp();
-                float* t = cur; cur = nxt; nxt = t;
+                group_bar(group);
             }
             if (a.logits[h])
-                for (int o = lane; o < d.n_out; o += 32) a.logits[h][(size_t)g * d.n_out + o] = cur[o];
-            if (a.scalar[h]) {
+                for (int o = u; o < d.n_out; o += span) a.logits[h][(size_t)g * d.n_out + o] = cur[o];
+            if (a.scalar[h] && u < 32) {                   // span is a multiple of 32: one full warp per head
                 const float v = support_to_scalar_group<32>(cur, a.S);
-                if (lane == 0) a.scalar[h][g] = v;
+                if (u == 0) a.scalar[h][g] = v;
             }
         }
-        __syncwarp();
+        group_bar(group);
     }
 }
 
@@ -531,6 +546,7 @@ bool pack_head(Loader& L, const std::string& conv, const std::string& fc, int C,
     const MzTensor* b = L.get(conv + ".bias", rc);
     if (!w || !b) return false;
     d.rc = rc; d.n_out = n_out;
+    while (blob.size() % 4) blob.push_back(0.0f);          // every head starts 16-byte aligned (float4 staging)
     d.w1_off = (int)blob.size(); blob.insert(blob.end(), w->data, w->data + (size_t)rc * C);
     d.b1_off = (int)blob.size(); blob.insert(blob.end(), b->data, b->data + rc);
     std::vector<int> sz;
@@ -713,9 +729,9 @@ struct Runner {
         }
         if (n_heads == 0) { lo = 0; hi = 0; }
         a.w_lo = lo; a.w_floats = ((hi - lo) + 3) & ~3;
-        a.warp_floats = (a.HW * (a.C + 1) + 2 * a.smem_floats + 3) & ~3;
-        const int threads = 256;
-        const size_t smem = ((size_t)a.w_floats + (size_t)(threads / 32) * a.warp_floats) * 4;
+        a.warp_floats = (a.HW * (a.C + 1) + 4 * a.smem_floats + 3) & ~3;       // x tile + (ping, pong) per head
+        const int threads = kHeadThreads;
+        const size_t smem = ((size_t)a.w_floats + (size_t)(threads / kHeadGroup) * a.warp_floats) * 4;
         if (smem > 227 * 1024) { *err = "heads: weights + tiles exceed shared memory"; return false; }
         static size_t attr_smem = 0;
         if (attr_smem < smem) {
@@ -723,7 +739,7 @@ struct Runner {
             if (e0 != cudaSuccess) return fail("heads attr", e0);
             attr_smem = smem;
         }
-        int grid = (n + threads / 32 - 1) / (threads / 32);
+        int grid = (n + threads / kHeadGroup - 1) / (threads / kHeadGroup);
         if (grid > r->sm_count) grid = r->sm_count;
         heads_kernel<<<grid, threads, smem, stream>>>(a);
         cudaError_t e = cudaGetLastError();
