@@ -42,11 +42,17 @@ DEFAULT_WORKLOAD = "cartpole_b4096_n50"
 
 
 def load_peaks():
+    """(HBM GB/s, dense bf16 TFLOP/s, which) from the driver-written MEASURED_PEAKS.json, else the fallback."""
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
         d = json.load(open(p))
-        return float(d["hbm_gbs"]), "measured"
-    return 6650.0, "fallback"
+        return float(d["hbm_gbs"]), float(d.get("bf16_tflops_sustained", d["bf16_tflops"])), "measured"
+    return 6650.0, 1400.0, "fallback"
+
+
+# algorithmic FLOPs of initial_inference / recurrent_inference per sample (SURVEY.md section 8 table)
+NET_FLOPS = {"cartpole": (1312.0, 2752.0), "tictactoe": (1.880e5, 2.315e5), "connect4": (3.737e7, 4.040e7),
+             "breakout": (3.419e7, 1.532e6)}
 
 
 # ----------------------------------------------------------------------------- clocks
@@ -287,11 +293,29 @@ def main():
 
     if rank == 0:
         value = total_steps / wall
-        hbm_peak, peak_kind = load_peaks()
-        # dominant kernel: the fused search kernel, one launch per step
-        alg_bytes = B * (N * bytes_per_sim + eng.obs_elems * 4 + A * 8 + A * 4 + 8)
+        hbm_peak, bf16_peak, peak_kind = load_peaks()
         kern_s = kern_ms / 1000.0 / args.steps
-        achieved = alg_bytes / kern_s / 1e9
+        if game == "cartpole":
+            # dominant kernel: the fused search kernel, one launch per step (HBM roofline)
+            alg_bytes = B * (N * bytes_per_sim + eng.obs_elems * 4 + A * 8 + A * 4 + 8)
+            achieved = alg_bytes / kern_s / 1e9
+            roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+                        "frac": achieved / hbm_peak, "traffic": 242944, "peak_kind": peak_kind,
+                        "kernel": "fc_search_kernel", "algorithmic_bytes_per_launch": alg_bytes,
+                        "note": "tree + hidden states live in shared memory for FC nets: measured DRAM traffic "
+                                "(profiles/r01_fc_search_ncu.md) is 0.24 MB per launch, the kernel is issue/latency-"
+                                "bound (47.6 % of peak issue rate), not HBM-bound"}
+        else:
+            # residual nets: tensor roofline; FLOPs of one step over the device time of the whole
+            # step-wise pipeline (conv kernels dominate; see profiles/ for the per-kernel split).  tf32 peak is
+            # taken as half the measured dense bf16 figure.
+            f0, f1 = NET_FLOPS[game]
+            flops = B * (f0 + N * f1)
+            achieved = flops / kern_s / 1e12
+            peak = bf16_peak / 2.0
+            roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                        "frac": achieved / peak, "traffic": None, "peak_kind": peak_kind + " bf16 / 2 (tf32)",
+                        "kernel": "whole step (conv3x3 kernels dominant)", "algorithmic_flops_per_step": flops}
         out = {
             "metric": "self-play env-steps/sec", "value": value, "unit": "env-steps/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * wall / args.steps,
@@ -304,11 +328,7 @@ def main():
                     "d2h_bytes_per_step": int(B * (A * 4 + 8 + 4 + 4 + 4 + A * 8 + 16))},
             "gpu_launches": int(launches),
             "clocks": clk,
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                         "frac": achieved / hbm_peak, "traffic": None, "peak_kind": peak_kind,
-                         "kernel": "fc_search_kernel", "algorithmic_bytes_per_launch": alg_bytes,
-                         "note": "tree + hidden states live in shared memory for FC nets; the kernel is "
-                                 "latency/issue-bound, HBM traffic is far below the algorithmic bytes"},
+            "roofline": roofline,
         }
         if world == 1 and not args.no_cpu_baseline:
             cores = host_cores()

@@ -173,6 +173,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_tc_kernel(const __grid_co
             if (lane == 0) mbar_wait(bar_a_empty(s), ph ^ 1);
             __syncwarp();
             const int nb = min(kBoards, a.n - tile * kBoards);
+            if (a.debug_skip & 2) { if (lane == 0) mbar_arrive(bar_a_full(s)); __syncwarp(); continue; }
             if (lane == 0) mbar_expect_tx(bar_a_full(s), (uint32_t)nb * kPlanes * kPos * 16);
             __syncwarp();
             // 32 lanes: (board, plane) pairs
@@ -199,7 +200,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_tc_kernel(const __grid_co
                 const uint32_t d = tmem_base + (uint32_t)(s * kAccCols);
                 uint32_t acc = 0;
 #pragma unroll 1
-                for (int tap = 0; tap < 9; ++tap) {
+                for (int tap = 0; tap < ((a.debug_skip & 1) ? 0 : 9); ++tap) {
                     if (it == 0) { mbar_wait(bar_w(tap), 0); tc_fence_after(); }
                     const int shift = (tap / 3 - 1) * 8 + (tap % 3 - 1);
                     const uint32_t a0 = s_a + s * kStageBytes + (kHalo + shift) * 16;
@@ -237,7 +238,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_tc_kernel(const __grid_co
 #pragma unroll
             for (int j = 0; j < kJ; ++j) add[j] = make_float4(0.f, 0.f, 0.f, 0.f);
             if (live) {
-                if (a.residual) {
+                if (a.residual && !(a.debug_skip & 8)) {
                     const float* res = a.residual + (size_t)g * (kC * kPos) + (size_t)p * 4 + (size_t)(half * kJ) * kPos * 4;
 #pragma unroll
                     for (int j = 0; j < kJ; ++j) add[j] = *reinterpret_cast<const float4*>(res + (size_t)j * kPos * 4);
@@ -270,7 +271,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_tc_kernel(const __grid_co
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_acc_empty(s));        // accumulator half read: may be overwritten
-            if (g < a.n) {
+            if (g < a.n && !(a.debug_skip & 4)) {
                 float* dst = a.out + (size_t)g * (kC * kPos) + (size_t)p * 4 + (size_t)(half * kJ) * kPos * 4;
 #pragma unroll
                 for (int j = 0; j < kJ; ++j) {

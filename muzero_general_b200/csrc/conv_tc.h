@@ -16,6 +16,7 @@ struct ConvTcArgs {
     const float* action_table;    // [64][64]
     int pool_stride;
     int n, H, W, A, relu;
+    int debug_skip;               // profiling only: 1 = no MMA, 2 = no A-tile loads, 4 = no global stores, 8 = no residual loads
 };
 
 cudaError_t launch_conv3x3_tc(const ConvTcArgs& a, int sm_count, cudaStream_t stream);

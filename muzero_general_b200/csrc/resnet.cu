@@ -628,6 +628,8 @@ struct Runner {
         a.gather_parent = gather_parent; a.pool_stride = pool_stride;
         a.action = action; a.action_table = l.tc_table_off >= 0 ? r->d_conv + l.tc_table_off : nullptr;
         a.n = n; a.H = r->hh; a.W = r->hw; a.A = r->net.action_space; a.relu = relu;
+        static const int dbg = getenv("MZ_TC_DEBUG_SKIP") ? atoi(getenv("MZ_TC_DEBUG_SKIP")) : 0;
+        a.debug_skip = dbg;
         cudaError_t e = launch_conv3x3_tc(a, r->sm_count, stream);
         if (e != cudaSuccess) return fail("conv3x3_tc launch", e);
         *launches += 1;
