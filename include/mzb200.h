@@ -74,6 +74,10 @@ typedef struct MzSearchDesc {
      * (self_play.py:385-390) exactly.  NULL: the library computes them with C log()/sqrt(). */
     const double* pb_c_table;
     const double* sqrt_table;
+    /* optional [(N+2) x (N+2)]: ucb_table[n_p*(N+2) + n_c] = pb_c_table[n_p] * (sqrt_table[n_p] / (n_c + 1)), i.e. the
+     * exploration factor of self_play.py:384-390 with its two roundings, evaluated by the caller; saves two fp64
+     * operations (one division) per child per tree level on the device.  NULL: computed on the device. */
+    const double* ucb_table;
 } MzSearchDesc;
 
 /* One named tensor of the reference state_dict (models.py:69-73), fp32 host memory. */

@@ -42,6 +42,7 @@ class MzSearchDesc(C.Structure):
         ("discount", C.c_double), ("pb_c_base", C.c_double), ("pb_c_init", C.c_double),
         ("root_dirichlet_alpha", C.c_double), ("root_exploration_fraction", C.c_double),
         ("seed", C.c_uint64), ("pb_c_table", C.POINTER(C.c_double)), ("sqrt_table", C.POINTER(C.c_double)),
+        ("ucb_table", C.POINTER(C.c_double)),
     ]
 
 

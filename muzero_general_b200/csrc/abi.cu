@@ -36,6 +36,7 @@ struct MzHandle {
     // tables
     double* d_pbc = nullptr;
     double* d_sqrt = nullptr;
+    double* d_ucb = nullptr;           // optional host-evaluated exploration-factor table
     // fully-connected weights
     FcNet fc{};
     float* d_fc_blob = nullptr;
@@ -125,6 +126,7 @@ extern "C" int mz_create(const MzNetDesc* net, const MzSearchDesc* search, int d
     h->search = *search;
     h->search.pb_c_table = nullptr;
     h->search.sqrt_table = nullptr;
+    h->search.ucb_table = nullptr;
     h->device = device;
 #define MZ_CREATE_CUDA(expr)                                                                      \
     do {                                                                                          \
@@ -156,6 +158,11 @@ extern "C" int mz_create(const MzNetDesc* net, const MzSearchDesc* search, int d
     MZ_CREATE_CUDA(dev_alloc(&h->d_sqrt, N + 2));
     MZ_CREATE_CUDA(cudaMemcpy(h->d_pbc, pbc.data(), (N + 2) * 8, cudaMemcpyHostToDevice));
     MZ_CREATE_CUDA(cudaMemcpy(h->d_sqrt, sq.data(), (N + 2) * 8, cudaMemcpyHostToDevice));
+    if (search->ucb_table) {
+        const size_t cells = (size_t)(N + 2) * (N + 2);
+        MZ_CREATE_CUDA(dev_alloc(&h->d_ucb, cells));
+        MZ_CREATE_CUDA(cudaMemcpy(h->d_ucb, search->ucb_table, cells * 8, cudaMemcpyHostToDevice));
+    }
 
     // ---- sizes
     h->obs_elems = (int64_t)net->obs_c * net->obs_h * net->obs_w;
@@ -193,6 +200,7 @@ extern "C" int mz_create(const MzNetDesc* net, const MzSearchDesc* search, int d
     MZ_CREATE_CUDA(dev_alloc(&p.max_depth, B));
     MZ_CREATE_CUDA(dev_alloc(&p.legal, B));
     MZ_CREATE_CUDA(dev_alloc(&p.path, (size_t)B * (N + 2)));
+    MZ_CREATE_CUDA(dev_alloc(&p.path_reward, (size_t)B * (N + 2)));
     MZ_CREATE_CUDA(dev_alloc(&p.leaf_depth, B));
     MZ_CREATE_CUDA(dev_alloc(&p.leaf_parent, B));
     MZ_CREATE_CUDA(dev_alloc(&p.leaf_action, B));
@@ -236,8 +244,8 @@ extern "C" int mz_destroy(MzHandle* h) {
     if (h->stream) cudaStreamSynchronize(h->stream);
     NodePool& p = h->pool;
     void* ptrs[] = {p.visit, p.vsum, p.reward, p.prior, p.expansion, p.root_prior, p.hidden, p.root_visit, p.root_vsum,
-                    p.root_reward, p.range, p.n_expanded, p.ties, p.max_depth, p.legal, p.path, p.leaf_depth,
-                    p.leaf_parent, p.leaf_action, p.leaf_slot, p.net_value, p.net_reward, p.net_policy, h->d_pbc, h->d_sqrt, h->d_fc_blob, h->d_in, h->d_out};
+                    p.root_reward, p.range, p.n_expanded, p.ties, p.max_depth, p.legal, p.path, p.path_reward, p.leaf_depth,
+                    p.leaf_parent, p.leaf_action, p.leaf_slot, p.net_value, p.net_reward, p.net_policy, h->d_ucb, h->d_pbc, h->d_sqrt, h->d_fc_blob, h->d_in, h->d_out};
     for (void* q : ptrs) if (q) cudaFree(q);
     for (auto& kv : h->named) cudaFree(kv.second.first);
     if (h->h_in) cudaFreeHost(h->h_in);
@@ -479,7 +487,7 @@ extern "C" int mz_search(MzHandle* h, const MzSearchIO* io) {
         FcSearchArgs a{};
         a.n_games = n; a.N = N; a.A = A; a.P = h->search.num_players; a.threads = h->fc_threads;
         a.discount = h->search.discount; a.noise_frac = h->search.root_exploration_fraction; a.noise_alpha = h->search.root_dirichlet_alpha; a.seed = h->search.seed;
-        a.pbc = h->d_pbc; a.sqrtn = h->d_sqrt;
+        a.pbc = h->d_pbc; a.sqrtn = h->d_sqrt; a.ucb = h->d_ucb;
         a.net = h->fc; a.blob = h->d_fc_blob;
         if (teacher) { a.net.E = 1; a.net.maxw = 4; a.net.blob_floats = 0; a.net.A = A; }
         a.obs = call.obs; a.legal_mask = call.legal_mask; a.to_play = call.to_play; a.add_noise = call.add_noise;
@@ -493,7 +501,7 @@ extern "C" int mz_search(MzHandle* h, const MzSearchIO* io) {
         if (e == cudaErrorInvalidConfiguration) {
             // the tree does not fit in shared memory next to the weights: use the HBM node pool
             (void)cudaGetLastError();
-            rc = run_stepwise_search(h->net, h->search, h->pool, h->d_pbc, h->d_sqrt, h->fc, h->d_fc_blob, h->res, call,
+            rc = run_stepwise_search(h->net, h->search, h->pool, h->d_pbc, h->d_sqrt, h->d_ucb, h->fc, h->d_fc_blob, h->res, call,
                                      h->fc_group, h->sm_count, h->stream, &h->launches, &h->err);
             if (rc) return rc;
         } else if (e != cudaSuccess) {
@@ -514,7 +522,7 @@ extern "C" int mz_search(MzHandle* h, const MzSearchIO* io) {
         for (const void* q : ptrs) mix((uint64_t)(uintptr_t)q);
         mix((uint64_t)n); mix((uint64_t)call.add_noise); mix((uint64_t)call.keep_tree);
         auto eager = [&]() {
-            return run_stepwise_search(h->net, h->search, h->pool, h->d_pbc, h->d_sqrt, h->fc, h->d_fc_blob, h->res, call,
+            return run_stepwise_search(h->net, h->search, h->pool, h->d_pbc, h->d_sqrt, h->d_ucb, h->fc, h->d_fc_blob, h->res, call,
                                        h->fc_group, h->sm_count, h->stream, &h->launches, &h->err);
         };
         if (graphable && h->graph_exec && h->graph_key == key) {

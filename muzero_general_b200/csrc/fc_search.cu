@@ -15,7 +15,7 @@ namespace mz {
 
 struct GameSmem {
     // byte offsets inside one game's region
-    int vsum, root_prior, visit, expansion, reward, prior, path, hidden, act, bytes;
+    int vsum, root_prior, visit, expansion, reward, prior, path, path_reward, hidden, act, bytes;
 };
 
 __host__ __device__ inline GameSmem game_smem_layout(int N, int A, int E, int maxw, bool keep_hidden) {
@@ -31,6 +31,7 @@ __host__ __device__ inline GameSmem game_smem_layout(int N, int A, int E, int ma
     L.reward = take(S * 4);
     L.prior = take(S * 4);
     L.path = take((N + 2) * 4);
+    L.path_reward = take((N + 2) * 4);
     L.hidden = take((keep_hidden ? (N + 1) * Epad : 0) * 4);
     L.act = take(3 * maxw * 4);
     off += 16;          // odd multiple of 16 B between games: spreads games over banks
@@ -60,7 +61,7 @@ __global__ void __launch_bounds__(kFcMaxThreads) fc_search_kernel(const __grid_c
 
     TreeConst c;
     c.A = A; c.N = N; c.P = a.P; c.discount = a.discount; c.noise_frac = a.noise_frac; c.noise_alpha = a.noise_alpha; c.seed = a.seed;
-    c.pbc = s_pbc; c.sqrtn = s_sqrt;
+    c.pbc = s_pbc; c.sqrtn = s_sqrt; c.ucb = a.ucb;
 
     GameTree t;
     t.vsum = reinterpret_cast<double*>(mine + L.vsum);
@@ -70,6 +71,7 @@ __global__ void __launch_bounds__(kFcMaxThreads) fc_search_kernel(const __grid_c
     t.reward = reinterpret_cast<float*>(mine + L.reward);
     t.prior = reinterpret_cast<float*>(mine + L.prior);
     t.path = reinterpret_cast<int*>(mine + L.path);
+    t.path_reward = reinterpret_cast<float*>(mine + L.path_reward);
     float* s_hidden = reinterpret_cast<float*>(mine + L.hidden);
     float* s_act = reinterpret_cast<float*>(mine + L.act);
     const int E = a.net.E, F = a.net.F, S = a.net.S, maxw = a.net.maxw;

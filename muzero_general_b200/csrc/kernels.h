@@ -30,6 +30,7 @@ struct NodePool {
     int* max_depth;        // [B]
     unsigned* legal;       // [B]
     int* path;             // [B, N+2]
+    float* path_reward;    // [B, N+2]
     // leaf of the simulation in flight
     int* leaf_depth;       // [B]
     int* leaf_parent;      // [B]
@@ -55,6 +56,7 @@ struct FcSearchArgs {
     uint64_t seed;
     const double* pbc;
     const double* sqrtn;
+    const double* ucb;
     FcNet net;
     const float* blob;
     // inputs (device)

@@ -5,7 +5,7 @@
 namespace mz {
 
 int run_stepwise_search(const MzNetDesc& net, const MzSearchDesc& search, const NodePool& pool, const double* d_pbc,
-                        const double* d_sqrt, const FcNet& fc, const float* d_fc_blob, ResNetDevice* res,
+                        const double* d_sqrt, const double* d_ucb, const FcNet& fc, const float* d_fc_blob, ResNetDevice* res,
                         const SearchCall& call, int fc_group, int sm_count, cudaStream_t stream, int64_t* launches, std::string* err) {
     const int n = call.n, N = search.num_simulations, A = net.action_space;
     const bool teacher = call.teacher.root_value != nullptr;
@@ -26,7 +26,7 @@ int run_stepwise_search(const MzNetDesc& net, const MzSearchDesc& search, const 
     TreeStepArgs a{};
     a.n = n; a.N = N; a.A = A; a.P = search.num_players;
     a.discount = search.discount; a.noise_frac = search.root_exploration_fraction; a.noise_alpha = search.root_dirichlet_alpha; a.seed = search.seed;
-    a.pbc = d_pbc; a.sqrtn = d_sqrt; a.pool = pool;
+    a.pbc = d_pbc; a.sqrtn = d_sqrt; a.ucb = d_ucb; a.pool = pool;
     a.legal_mask = call.legal_mask; a.noise = call.noise; a.add_noise = call.add_noise;
     a.first_index = call.first_index; a.game_id = call.game_id; a.move_index = call.move_index;
     a.visit_counts = call.visit_counts; a.root_value = call.root_value; a.root_predicted_value = call.root_predicted_value;

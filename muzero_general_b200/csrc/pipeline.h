@@ -52,6 +52,7 @@ struct TreeStepArgs {
     uint64_t seed;
     const double* pbc;
     const double* sqrtn;
+    const double* ucb;
     NodePool pool;
     const uint8_t* legal_mask;
     const double* noise;
@@ -84,7 +85,7 @@ int resnet_states_to_nchw(ResNetDevice* r, const float* states, int count, float
 cudaError_t launch_fc_inference_pool(const FcNet& net, const float* blob, const InferCall& c, int group, int sm_count, cudaStream_t stream);
 
 int run_stepwise_search(const MzNetDesc& net, const MzSearchDesc& search, const NodePool& pool, const double* d_pbc,
-                        const double* d_sqrt, const FcNet& fc, const float* d_fc_blob, ResNetDevice* res,
+                        const double* d_sqrt, const double* d_ucb, const FcNet& fc, const float* d_fc_blob, ResNetDevice* res,
                         const SearchCall& call, int fc_group, int sm_count, cudaStream_t stream, int64_t* launches, std::string* err);
 
 }  // namespace mz

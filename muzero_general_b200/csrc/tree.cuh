@@ -32,6 +32,7 @@ struct TreeConst {
     uint64_t seed;
     const double* pbc;     // [N+2]  log((n+base+1)/base)+init
     const double* sqrtn;   // [N+2]  sqrt(n)
+    const double* ucb;     // [(N+2)^2] pbc[n_p] * (sqrtn[n_p] / (n_c + 1)) precomputed by the host, or nullptr
 };
 
 // Pointers to ONE game's tree (shared or global memory).
@@ -43,6 +44,7 @@ struct GameTree {
     int* expansion;        // [(N+1)*A]
     double* root_prior;    // [A]
     int* path;             // [N+2] slots of the current simulation, path[0] = -1 (root)
+    float* path_reward;    // [N+2] reward of every node on that path (the leaf's entry is filled at expansion)
     // scalars of the game
     int root_visit;
     double root_vsum;
@@ -138,22 +140,32 @@ MZ_DEVINL Leaf tree_select(const TreeConst& c, GameTree& t, int sim, int64_t gam
     int n_parent = t.root_visit;
     int depth = 0;
     Leaf leaf;
-    if (k == 0) t.path[0] = -1;
+    if (k == 0) { t.path[0] = -1; t.path_reward[0] = t.root_reward; }
     while (true) {
         const int base = e * c.A;
         const bool valid = (k < c.A) && (e != 0 || ((t.legal >> k) & 1u));
         double score = -INFINITY;
+        int nc = 0, child_exp_k = -1;
+        float reward_k = 0.0f;
         if (valid) {
-            const int nc = t.visit[base + k];
+            // one round of independent loads per level: everything this lane's child may need
+            nc = t.visit[base + k];
+            child_exp_k = t.expansion[base + k];
             const double pr = (e == 0) ? t.root_prior[k] : (double)t.prior[base + k];
             // pb_c = (log(...) + init) * (sqrt(n_p) / (n_c + 1))     self_play.py:384-390
-            const double q = __ddiv_rn(c.sqrtn[n_parent], (double)(nc + 1));
-            const double pbc = __dmul_rn(c.pbc[n_parent], q);
+            double pbc;
+            if (c.ucb) {
+                pbc = __ldg(c.ucb + n_parent * (c.N + 2) + nc);
+            } else {
+                const double q = __ddiv_rn(c.sqrtn[n_parent], (double)(nc + 1));
+                pbc = __dmul_rn(c.pbc[n_parent], q);
+            }
             score = __dmul_rn(pbc, pr);
             if (nc > 0) {
+                reward_k = t.reward[base + k];
                 const double mean = __ddiv_rn(t.vsum[base + k], (double)nc);
                 const double signed_mean = (c.P == 1) ? mean : -mean;
-                double v = __dadd_rn((double)t.reward[base + k], __dmul_rn(c.discount, signed_mean));
+                double v = __dadd_rn((double)reward_k, __dmul_rn(c.discount, signed_mean));
                 v = value_range_normalize(v, t.lo, t.hi);
                 score = __dadd_rn(score, v);
             } else {
@@ -178,8 +190,10 @@ MZ_DEVINL Leaf tree_select(const TreeConst& c, GameTree& t, int sim, int64_t gam
         }
         const int slot = base + pick;
         depth += 1;
-        if (k == 0) t.path[depth] = slot;
-        const int child_exp = t.expansion[slot];
+        // the picked child's fields come from the lane that scored it (no second round of loads)
+        const int child_exp = LaneGroup<G>::bcast(child_exp_k, pick);
+        const int child_visits = LaneGroup<G>::bcast(nc, pick);
+        if (k == pick) { t.path[depth] = slot; t.path_reward[depth] = reward_k; }
         if (child_exp < 0) {
             leaf.depth = depth;
             leaf.parent_exp = e;
@@ -187,7 +201,7 @@ MZ_DEVINL Leaf tree_select(const TreeConst& c, GameTree& t, int sim, int64_t gam
             leaf.slot = slot;
             break;
         }
-        n_parent = t.visit[slot];
+        n_parent = child_visits;
         e = child_exp;
     }
     LaneGroup<G>::sync();
@@ -205,6 +219,7 @@ MZ_DEVINL int tree_expand(const TreeConst& c, GameTree& t, const Leaf& leaf, flo
     if (k == 0) {
         t.expansion[leaf.slot] = e;
         t.reward[leaf.slot] = reward;
+        t.path_reward[leaf.depth] = reward;
     }
     if (k < c.A) {
         const int s = e * c.A + k;
@@ -231,9 +246,23 @@ MZ_DEVINL void tree_backup(const TreeConst& c, GameTree& t, const Leaf& leaf, fl
     double lo = INFINITY, hi = -INFINITY;
     double v = (double)leaf_value;                    // value seen by node j, starting at j = L
     double root_vsum = t.root_vsum;
+    // lane j holds (slot, reward) of path node j when the path fits in the group: the serial recurrence
+    // then runs on shuffles instead of a dependent chain of loads
+    const bool packed = (L < G);
+    int my_slot = -1;
+    float my_reward = 0.0f;
+    if (packed && k <= L) { my_slot = t.path[k]; my_reward = t.path_reward[k]; }
     for (int j = L; j >= 0; --j) {
-        const int slot = t.path[j];                   // -1 = root (shared-memory broadcast read)
-        const double r = (j == 0) ? (double)t.root_reward : (double)t.reward[slot];
+        int slot;
+        float rf;
+        if (packed) {
+            slot = LaneGroup<G>::bcast(my_slot, j);
+            rf = LaneGroup<G>::bcast(my_reward, j);
+        } else {
+            slot = t.path[j];
+            rf = t.path_reward[j];
+        }
+        const double r = (double)rf;
         // node.to_play == to_play  <=>  (L - j) even (players alternate every level)
         const bool same = (c.P == 1) || (((L - j) & 1) == 0);
         if ((j % G) == k) {
@@ -258,7 +287,6 @@ MZ_DEVINL void tree_backup(const TreeConst& c, GameTree& t, const Leaf& leaf, fl
         const double rr = (c.P == 1) ? r : (same ? -r : r);
         v = __dadd_rn(rr, __dmul_rn(c.discount, v));
     }
-    // lane 0 always owns j = 0 (the root)
     // only lanes 0..L hold candidates: reduce over the smallest power of two covering them,
     // then broadcast lane 0's result (lanes beyond the reduced width hold partial values)
     const int width = (L + 1 >= G) ? G : pow2_ceil(L + 1);

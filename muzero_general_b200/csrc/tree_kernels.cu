@@ -24,7 +24,7 @@ __global__ void __launch_bounds__(128) tree_step_kernel(const __grid_constant__ 
 
     TreeConst c;
     c.A = A; c.N = N; c.P = a.P; c.discount = a.discount; c.noise_frac = a.noise_frac; c.noise_alpha = a.noise_alpha; c.seed = a.seed;
-    c.pbc = a.pbc; c.sqrtn = a.sqrtn;
+    c.pbc = a.pbc; c.sqrtn = a.sqrtn; c.ucb = a.ucb;
 
     GameTree t;
     t.visit = p.visit + g * slots;
@@ -34,6 +34,7 @@ __global__ void __launch_bounds__(128) tree_step_kernel(const __grid_constant__ 
     t.expansion = p.expansion + g * slots;
     t.root_prior = p.root_prior + (size_t)g * A;
     t.path = p.path + (size_t)g * (N + 2);
+    t.path_reward = p.path_reward + (size_t)g * (N + 2);
     int max_depth = 0;
 
     if (a.do_root) {

@@ -102,6 +102,9 @@ class SearchEngine:
         self._sqrt = (C.c_double * n)(*[math.sqrt(i) for i in range(n)])
         s.pb_c_table = C.cast(self._pbc, C.POINTER(C.c_double))
         s.sqrt_table = C.cast(self._sqrt, C.POINTER(C.c_double))
+        # the whole exploration factor pb_c(n_p) * (sqrt(n_p) / (n_c + 1)) with Python's own roundings
+        self._ucb = (C.c_double * (n * n))(*[self._pbc[p] * (self._sqrt[p] / (c + 1)) for p in range(n) for c in range(n)])
+        s.ucb_table = C.cast(self._ucb, C.POINTER(C.c_double))
         self._net_desc = net_desc(self.spec)
         handle = C.c_void_p()
         rc = self.lib.mz_create(C.byref(self._net_desc), C.byref(s), self.device, C.byref(handle))

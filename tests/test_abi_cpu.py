@@ -26,7 +26,7 @@ def test_struct_sizes_match_header_layout():
     from muzero_general_b200 import _lib
     # MzNetDesc: 7 + 5*(1+8) + 5 + 3*(1+8) + 1 int32
     assert ctypes.sizeof(_lib.MzNetDesc) == 4 * (7 + 5 * 9 + 5 + 3 * 9 + 1)
-    assert ctypes.sizeof(_lib.MzSearchDesc) == 16 + 5 * 8 + 8 + 16
+    assert ctypes.sizeof(_lib.MzSearchDesc) == 16 + 5 * 8 + 8 + 24
     assert ctypes.sizeof(_lib.MzSearchIO) == 8 + 3 * 8 + 8 + 4 * 8 + 7 * 8 + 2 * 8
 
 
