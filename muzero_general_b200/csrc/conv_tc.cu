@@ -46,9 +46,9 @@ struct Smem {
     // offsets
     static constexpr int w = 0;
     static constexpr int a = kWBytes;
-    static constexpr int bias = a + kStages * kStageBytes;                 // 64 floats
-    static constexpr int bars = bias + kC * 4;                             // 8-byte aligned
-    static constexpr int tmem_ptr = bars + 32 * 8;
+    static constexpr int bias = a + kStages * kStageBytes;                 // [kTowerMaxLayers][64] floats
+    static constexpr int bars = bias + kTowerMaxLayers * kC * 4;           // 8-byte aligned
+    static constexpr int tmem_ptr = bars + 48 * 8;
     static constexpr int total = tmem_ptr + 16;
 };
 static_assert(Smem::total <= 232448, "shared memory budget");
@@ -114,22 +114,31 @@ MZ_DEVINL float round_tf32(float x) {
 
 }  // namespace
 
-__global__ void __launch_bounds__(kThreads, 1) conv3x3_tc_kernel(const __grid_constant__ ConvTcArgs a) {
+MZ_DEVINL const float* tower_board(const TowerArgs& a, int buf, int g) {
+    if (buf == 0 && a.gather_parent)
+        return a.buf[0] + ((size_t)g * a.pool_stride + a.gather_parent[g]) * (size_t)(kC * kPos);
+    return a.buf[buf] + (size_t)g * (kC * kPos);
+}
+
+__global__ void __launch_bounds__(kThreads, 1) conv_tower_tc_kernel(const __grid_constant__ TowerArgs a) {
     extern __shared__ __align__(1024) unsigned char smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t s_base = smem_u32(smem);
     const uint32_t s_w = s_base + Smem::w, s_a = s_base + Smem::a;
     float* s_bias = reinterpret_cast<float*>(smem + Smem::bias);
     const uint32_t bars = s_base + Smem::bars;
-    // barrier ids
-    auto bar_w = [&](int tap) { return bars + 8u * tap; };                // weights of one filter tap landed
-    auto bar_a_full = [&](int s) { return bars + 8u * (9 + s); };
-    auto bar_a_empty = [&](int s) { return bars + 8u * (11 + s); };
-    auto bar_acc_full = [&](int s) { return bars + 8u * (13 + s); };
-    auto bar_acc_empty = [&](int s) { return bars + 8u * (15 + s); };
+    auto bar_w_full = [&](int tap) { return bars + 8u * tap; };            // weights of (layer, tap) landed
+    auto bar_w_empty = [&](int tap) { return bars + 8u * (9 + tap); };     // last MMA of the layer on this tap done
+    auto bar_a_full = [&](int s) { return bars + 8u * (18 + s); };
+    auto bar_a_empty = [&](int s) { return bars + 8u * (20 + s); };
+    auto bar_acc_full = [&](int s) { return bars + 8u * (22 + s); };
+    auto bar_acc_empty = [&](int s) { return bars + 8u * (24 + s); };
+    auto bar_tile_done = [&](int k) { return bars + 8u * (26 + k); };      // layer output of my k-th tile stored
     volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + Smem::tmem_ptr);
 
     const int n_tiles = (a.n + kBoards - 1) / kBoards;
+    const int my_tiles = ((int)blockIdx.x < n_tiles) ? (n_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+    const int L = a.n_layers;
 
     // ---- one-time setup
     // zero the halo rows of every plane (the board rows are always overwritten by the bulk copies)
@@ -138,15 +147,19 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_tc_kernel(const __grid_co
         const int row = r < kHalo ? r : kRows - 2 * kHalo + r;
         reinterpret_cast<uint4*>(smem + Smem::a + pl * kPlaneBytes)[row] = make_uint4(0, 0, 0, 0);
     }
-    if (threadIdx.x < kC) s_bias[threadIdx.x] = a.bias ? a.bias[threadIdx.x] : 0.0f;
+    for (int i = threadIdx.x; i < L * kC; i += kThreads) {
+        const float* b = a.layer[i / kC].bias;
+        s_bias[i] = b ? b[i % kC] : 0.0f;
+    }
     if (threadIdx.x == 0) {
-        for (int t = 0; t < 9; ++t) mbar_init(bar_w(t), 1);
+        for (int t = 0; t < 9; ++t) { mbar_init(bar_w_full(t), 1); mbar_init(bar_w_empty(t), 1); }
         for (int s = 0; s < kStages; ++s) {
             mbar_init(bar_a_full(s), 1);
             mbar_init(bar_a_empty(s), 1);
             mbar_init(bar_acc_full(s), 1);
             mbar_init(bar_acc_empty(s), kEpiWarps);   // one arrival per epilogue warp
         }
+        for (int k = 0; k < kTowerMaxTiles; ++k) mbar_init(bar_tile_done(k), kEpiWarps);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic zero-fill -> async proxy readers
@@ -162,61 +175,76 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_tc_kernel(const __grid_co
 
     if (warp == 0) {
         // ================= producer =================
-        if (lane < 9) {                                // one barrier per tap: the MMAs of tap t start as soon as it landed
-            mbar_expect_tx(bar_w(lane), kTapBytes);
-            bulk_g2s(s_w + lane * kTapBytes, reinterpret_cast<const unsigned char*>(a.w) + (size_t)lane * kTapBytes, kTapBytes, bar_w(lane));
-        }
         int it = 0;
-        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
-            const int s = it % kStages;
-            const uint32_t ph = (it / kStages) & 1;
-            if (lane == 0) mbar_wait(bar_a_empty(s), ph ^ 1);
+        for (int l = 0; l < L; ++l) {
+            if (my_tiles > 0 && lane < 9) {
+                // slot `lane` is free once the previous layer's last tile has multiplied with it
+                if (l > 0) mbar_wait(bar_w_empty(lane), (uint32_t)((l - 1) & 1));
+                mbar_expect_tx(bar_w_full(lane), kTapBytes);
+                bulk_g2s(s_w + lane * kTapBytes, reinterpret_cast<const unsigned char*>(a.layer[l].w) + (size_t)lane * kTapBytes,
+                         kTapBytes, bar_w_full(lane));
+            }
             __syncwarp();
-            const int nb = min(kBoards, a.n - tile * kBoards);
-            if (a.debug_skip & 2) { if (lane == 0) mbar_arrive(bar_a_full(s)); __syncwarp(); continue; }
-            if (lane == 0) mbar_expect_tx(bar_a_full(s), (uint32_t)nb * kPlanes * kPos * 16);
-            __syncwarp();
-            // 32 lanes: (board, plane) pairs
-            for (int i = lane; i < nb * kPlanes; i += 32) {
-                const int b = i / kPlanes, j = i % kPlanes;
-                const int g = tile * kBoards + b;
-                const float* src = a.gather_parent
-                    ? a.in + ((size_t)g * a.pool_stride + a.gather_parent[g]) * (size_t)(kC * kPos)
-                    : a.in + (size_t)g * (kC * kPos);
-                bulk_g2s(s_a + s * kStageBytes + j * kPlaneBytes + (kHalo + b * kPos) * 16,
-                         src + (size_t)j * kPos * 4, kPos * 16, bar_a_full(s));
+            const int in_buf = a.layer[l].in_buf;
+            for (int k = 0; k < my_tiles; ++k, ++it) {
+                const int tile = blockIdx.x + k * gridDim.x;
+                const int s = it % kStages;
+                const uint32_t ph = (it / kStages) & 1;
+                if (lane == 0) {
+                    mbar_wait(bar_a_empty(s), ph ^ 1);
+                    if (l > 0) {
+                        // this tile's input was written by this CTA's epilogue in the previous layer
+                        mbar_wait(bar_tile_done(k), (uint32_t)((l - 1) & 1));
+                        asm volatile("fence.proxy.async;" ::: "memory");
+                    }
+                }
+                __syncwarp();
+                const int nb = min(kBoards, a.n - tile * kBoards);
+                if (a.debug_skip & 2) { if (lane == 0) mbar_arrive(bar_a_full(s)); __syncwarp(); continue; }
+                if (lane == 0) mbar_expect_tx(bar_a_full(s), (uint32_t)nb * kPlanes * kPos * 16);
+                __syncwarp();
+                for (int i = lane; i < nb * kPlanes; i += 32) {          // (board, channel group) pairs
+                    const int b = i / kPlanes, j = i % kPlanes;
+                    const float* src = tower_board(a, in_buf, tile * kBoards + b);
+                    bulk_g2s(s_a + s * kStageBytes + j * kPlaneBytes + (kHalo + b * kPos) * 16,
+                             src + (size_t)j * kPos * 4, kPos * 16, bar_a_full(s));
+                }
             }
         }
     } else if (warp == 1) {
         // ================= MMA issuer =================
         int it = 0;
-        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
-            const int s = it % kStages;
-            const uint32_t ph = (it / kStages) & 1;
-            mbar_wait(bar_acc_empty(s), ph ^ 1);
-            mbar_wait(bar_a_full(s), ph);
-            tc_fence_after();
-            if (lane == 0) {
-                const uint32_t d = tmem_base + (uint32_t)(s * kAccCols);
-                uint32_t acc = 0;
+        for (int l = 0; l < L; ++l) {
+            for (int k = 0; k < my_tiles; ++k, ++it) {
+                const int s = it % kStages;
+                const uint32_t ph = (it / kStages) & 1;
+                mbar_wait(bar_acc_empty(s), ph ^ 1);
+                mbar_wait(bar_a_full(s), ph);
+                tc_fence_after();
+                if (lane == 0) {
+                    const uint32_t d = tmem_base + (uint32_t)(s * kAccCols);
+                    uint32_t acc = 0;
 #pragma unroll 1
-                for (int tap = 0; tap < ((a.debug_skip & 1) ? 0 : 9); ++tap) {
-                    if (it == 0) { mbar_wait(bar_w(tap), 0); tc_fence_after(); }
-                    const int shift = (tap / 3 - 1) * 8 + (tap % 3 - 1);
-                    const uint32_t a0 = s_a + s * kStageBytes + (kHalo + shift) * 16;
-                    const uint32_t b0 = s_w + tap * kTapBytes;
+                    for (int tap = 0; tap < ((a.debug_skip & 1) ? 0 : 9); ++tap) {
+                        if (k == 0) { mbar_wait(bar_w_full(tap), (uint32_t)(l & 1)); tc_fence_after(); }
+                        const int shift = (tap / 3 - 1) * 8 + (tap % 3 - 1);
+                        const uint32_t a0 = s_a + s * kStageBytes + (kHalo + shift) * 16;
+                        const uint32_t b0 = s_w + tap * kTapBytes;
 #pragma unroll
-                    for (int ks = 0; ks < kC / 8; ++ks) {
-                        const uint64_t ad = umma_desc(a0 + 2 * ks * kPlaneBytes, kPlaneBytes, 128);
-                        const uint64_t bd = umma_desc(b0 + 2 * ks * (kC * 16), kC * 16, 128);
-                        umma_tf32(d, ad, bd, acc);
-                        acc = 1;
+                        for (int ks = 0; ks < kC / 8; ++ks) {
+                            const uint64_t ad = umma_desc(a0 + 2 * ks * kPlaneBytes, kPlaneBytes, 128);
+                            const uint64_t bd = umma_desc(b0 + 2 * ks * (kC * 16), kC * 16, 128);
+                            umma_tf32(d, ad, bd, acc);
+                            acc = 1;
+                        }
+                        if (k == my_tiles - 1) umma_commit(bar_w_empty(tap));   // slot reusable by the next layer
                     }
+                    if (a.debug_skip & 1) { if (k == my_tiles - 1) for (int tap = 0; tap < 9; ++tap) umma_commit(bar_w_empty(tap)); }
+                    umma_commit(bar_a_empty(s));          // smem stage reusable once the MMAs have read it
+                    umma_commit(bar_acc_full(s));         // accumulator complete
                 }
-                umma_commit(bar_a_empty(s));          // smem stage reusable once the MMAs have read it
-                umma_commit(bar_acc_full(s));         // accumulator complete
+                __syncwarp();
             }
-            __syncwarp();
         }
     } else if (warp >= 4) {
         // ================= epilogue =================
@@ -227,65 +255,76 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_tc_kernel(const __grid_co
         const int y = p / 8 - 1, x = p % 8;
         const bool inside = (y >= 0 && y < a.H && x < a.W);
         constexpr int kJ = kPlanes / 2;               // channel groups handled by this warp
+        const size_t my_off = (size_t)p * 4 + (size_t)(half * kJ) * kPos * 4;
         int it = 0;
-        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
-            const int s = it % kStages;
-            const uint32_t ph = (it / kStages) & 1;
-            const int g = tile * kBoards + b;
-            const bool live = inside && g < a.n;
-            // ---- prefetch everything that does not depend on the accumulator
-            float4 add[kJ];
+        for (int l = 0; l < L; ++l) {
+            const TowerLayer& ly = a.layer[l];
+            const float* bias = s_bias + l * kC + half * 32;
+            for (int k = 0; k < my_tiles; ++k, ++it) {
+                const int tile = blockIdx.x + k * gridDim.x;
+                const int s = it % kStages;
+                const uint32_t ph = (it / kStages) & 1;
+                const int g = tile * kBoards + b;
+                const bool live = inside && g < a.n;
+                // ---- prefetch everything that does not depend on the accumulator
+                float4 add[kJ];
 #pragma unroll
-            for (int j = 0; j < kJ; ++j) add[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (live) {
-                if (a.residual && !(a.debug_skip & 8)) {
-                    const float* res = a.residual + (size_t)g * (kC * kPos) + (size_t)p * 4 + (size_t)(half * kJ) * kPos * 4;
+                for (int j = 0; j < kJ; ++j) add[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (live) {
+                    if (ly.res_buf >= 0 && !(a.debug_skip & 8)) {
+                        const float* res = tower_board(a, ly.res_buf, g) + my_off;
 #pragma unroll
-                    for (int j = 0; j < kJ; ++j) add[j] = *reinterpret_cast<const float4*>(res + (size_t)j * kPos * 4);
+                        for (int j = 0; j < kJ; ++j) add[j] = *reinterpret_cast<const float4*>(res + (size_t)j * kPos * 4);
+                    }
+                    if (ly.action_table) {
+                        const float sc = __fdiv_rn((float)a.action[g], (float)a.A);
+                        const float* atab = ly.action_table + (size_t)p * kC + half * 32;
+#pragma unroll
+                        for (int j = 0; j < kJ; ++j) {
+                            const float4 t4 = *reinterpret_cast<const float4*>(atab + 4 * j);
+                            add[j].x = fmaf(sc, t4.x, add[j].x); add[j].y = fmaf(sc, t4.y, add[j].y);
+                            add[j].z = fmaf(sc, t4.z, add[j].z); add[j].w = fmaf(sc, t4.w, add[j].w);
+                        }
+                    }
                 }
-                if (a.action) {
-                    const float sc = __fdiv_rn((float)a.action[g], (float)a.A);
-                    const float* atab = a.action_table + (size_t)p * kC + half * 32;
+                mbar_wait(bar_acc_full(s), ph);
+                tc_fence_after();
+                uint32_t v[32];
+                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(s * kAccCols + half * 32);
+                asm volatile(
+                    "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                    "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                    "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                    : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                      "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+                      "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+                      "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                    : "r"(taddr));
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_acc_empty(s));        // accumulator half read: may be overwritten
+                if (g < a.n && !(a.debug_skip & 4)) {
+                    float* dst = a.buf[ly.out_buf] + (size_t)g * (kC * kPos) + my_off;
 #pragma unroll
                     for (int j = 0; j < kJ; ++j) {
-                        const float4 t4 = *reinterpret_cast<const float4*>(atab + 4 * j);
-                        add[j].x = fmaf(sc, t4.x, add[j].x); add[j].y = fmaf(sc, t4.y, add[j].y);
-                        add[j].z = fmaf(sc, t4.z, add[j].z); add[j].w = fmaf(sc, t4.w, add[j].w);
+                        float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (inside) {
+                            float r0 = __uint_as_float(v[4 * j + 0]) + bias[4 * j + 0] + add[j].x;
+                            float r1 = __uint_as_float(v[4 * j + 1]) + bias[4 * j + 1] + add[j].y;
+                            float r2 = __uint_as_float(v[4 * j + 2]) + bias[4 * j + 2] + add[j].z;
+                            float r3 = __uint_as_float(v[4 * j + 3]) + bias[4 * j + 3] + add[j].w;
+                            if (ly.relu) { r0 = fmaxf(r0, 0.f); r1 = fmaxf(r1, 0.f); r2 = fmaxf(r2, 0.f); r3 = fmaxf(r3, 0.f); }
+                            o = make_float4(round_tf32(r0), round_tf32(r1), round_tf32(r2), round_tf32(r3));
+                        }
+                        *reinterpret_cast<float4*>(dst + (size_t)j * kPos * 4) = o;
                     }
                 }
-            }
-            mbar_wait(bar_acc_full(s), ph);
-            tc_fence_after();
-            uint32_t v[32];
-            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(s * kAccCols + half * 32);
-            asm volatile(
-                "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-                "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-                "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-                : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-                  "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
-                  "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
-                  "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-                : "r"(taddr));
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(bar_acc_empty(s));        // accumulator half read: may be overwritten
-            if (g < a.n && !(a.debug_skip & 4)) {
-                float* dst = a.out + (size_t)g * (kC * kPos) + (size_t)p * 4 + (size_t)(half * kJ) * kPos * 4;
-#pragma unroll
-                for (int j = 0; j < kJ; ++j) {
-                    float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (inside) {
-                        const int c0 = half * 32 + 4 * j;
-                        float r0 = __uint_as_float(v[4 * j + 0]) + s_bias[c0 + 0] + add[j].x;
-                        float r1 = __uint_as_float(v[4 * j + 1]) + s_bias[c0 + 1] + add[j].y;
-                        float r2 = __uint_as_float(v[4 * j + 2]) + s_bias[c0 + 2] + add[j].z;
-                        float r3 = __uint_as_float(v[4 * j + 3]) + s_bias[c0 + 3] + add[j].w;
-                        if (a.relu) { r0 = fmaxf(r0, 0.f); r1 = fmaxf(r1, 0.f); r2 = fmaxf(r2, 0.f); r3 = fmaxf(r3, 0.f); }
-                        o = make_float4(round_tf32(r0), round_tf32(r1), round_tf32(r2), round_tf32(r3));
-                    }
-                    *reinterpret_cast<float4*>(dst + (size_t)j * kPos * 4) = o;
+                if (l + 1 < L) {
+                    // the next layer's bulk copy (async proxy) of this tile must see these stores
+                    __threadfence();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(bar_tile_done(k));
                 }
             }
         }
@@ -297,18 +336,22 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_tc_kernel(const __grid_co
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2 * kAccCols) : "memory");
 }
 
-cudaError_t launch_conv3x3_tc(const ConvTcArgs& a, int sm_count, cudaStream_t stream) {
+cudaError_t launch_conv_tower_tc(const TowerArgs& a, int sm_count, cudaStream_t stream) {
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(conv3x3_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem::total);
+        cudaError_t e = cudaFuncSetAttribute(conv_tower_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem::total);
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
+    if (a.n_layers < 1 || a.n_layers > kTowerMaxLayers) return cudaErrorInvalidValue;
     const int n_tiles = (a.n + kBoards - 1) / kBoards;
     const int grid = n_tiles < sm_count ? n_tiles : sm_count;
-    conv3x3_tc_kernel<<<grid, kThreads, Smem::total, stream>>>(a);
+    if (a.n_layers > 1 && (n_tiles + grid - 1) / grid > kTowerMaxTiles) return cudaErrorInvalidConfiguration;
+    conv_tower_tc_kernel<<<grid, kThreads, Smem::total, stream>>>(a);
     return cudaGetLastError();
 }
+
+int conv_tc_max_boards_fused(int sm_count) { return sm_count * kTowerMaxTiles * kBoards; }
 
 bool conv_tc_supported(int C, int H, int W) { return C == kC && H >= 1 && H <= 6 && W >= 1 && W <= 7; }
 int conv_tc_board_elems() { return kC * kPos; }

@@ -5,22 +5,37 @@
 
 namespace mz {
 
-struct ConvTcArgs {
-    const float* in;              // [n][16][64][4]  (or gathered from the hidden pool, same per-state layout)
-    float* out;                   // [n][16][64][4]
-    const float* residual;        // like out, or nullptr
+constexpr int kTowerMaxLayers = 8;
+constexpr int kTowerMaxTiles = 8;          // tiles (pairs of boards) one CTA may own in the fused-tower mode
+constexpr int kTowerBuffers = 5;
+
+// One conv3x3 (+bias, +residual, +action term, +ReLU) of a tower; buffers are indices into TowerArgs::buf.
+struct TowerLayer {
     const float* w;               // [9][16][64][4] tf32-rounded, BN scale folded
     const float* bias;            // [64] folded BN shift, or nullptr
-    const int32_t* gather_parent; // pool mode: state of game g = in + (g*pool_stride + gather_parent[g]) * 4096
-    const int32_t* action;        // dynamics: add (action/A) * action_table[p][cout]
-    const float* action_table;    // [64][64]
+    const float* action_table;    // dynamics stem: add (action/A) * table[p][cout]; nullptr otherwise
+    int in_buf, out_buf, res_buf; // res_buf = -1: no residual
+    int relu;
+};
+
+// A whole residual tower executed by ONE persistent launch: every CTA keeps its own tiles through all the
+// layers (a conv only needs the board itself: padding is zero), the 9 weight-tap slots in shared memory are
+// refilled for layer l+1 while the last tile of layer l is still multiplying, and activations round-trip
+// through L2 between layers.  n_layers = 1 is the plain single convolution.
+struct TowerArgs {
+    int n_layers;
+    TowerLayer layer[kTowerMaxLayers];
+    float* buf[kTowerBuffers];    // activation buffers [n][16][64][4]; buf[0] may be a gathered pool
+    const int32_t* gather_parent; // buf[0] of game g = buf[0] + (g*pool_stride + gather_parent[g]) * 4096
     int pool_stride;
-    int n, H, W, A, relu;
+    const int32_t* action;        // [n] for layers with an action_table
+    int n, H, W, A;
     int debug_skip;               // profiling only: 1 = no MMA, 2 = no A-tile loads, 4 = no global stores, 8 = no residual loads
 };
 
-cudaError_t launch_conv3x3_tc(const ConvTcArgs& a, int sm_count, cudaStream_t stream);
+cudaError_t launch_conv_tower_tc(const TowerArgs& a, int sm_count, cudaStream_t stream);
 bool conv_tc_supported(int C, int H, int W);
 int conv_tc_board_elems();
+int conv_tc_max_boards_fused(int sm_count);   // largest batch the fused-tower mode handles in one launch
 
 }  // namespace mz

@@ -619,21 +619,35 @@ struct Runner {
     bool fail(const char* what, cudaError_t e) { *err = std::string(what) + ": " + cudaGetErrorString(e); return false; }
 
     // conv: in -> out. `in` may be gathered from the pool; action adds the constant plane.
-    bool conv_tc(const ConvLayer& l, const float* in, float* out, const float* residual, bool relu,
-                 const int32_t* gather_parent = nullptr, int pool_stride = 0, const int32_t* action = nullptr) {
-        ConvTcArgs a{};
-        a.in = in; a.out = out; a.residual = residual;
-        a.w = r->d_conv + l.tc_off;
-        a.bias = l.b_off >= 0 ? r->d_conv + l.b_off : nullptr;
-        a.gather_parent = gather_parent; a.pool_stride = pool_stride;
-        a.action = action; a.action_table = l.tc_table_off >= 0 ? r->d_conv + l.tc_table_off : nullptr;
-        a.n = n; a.H = r->hh; a.W = r->hw; a.A = r->net.action_space; a.relu = relu;
+    TowerLayer tower_layer(const ConvLayer& l, int in_buf, int out_buf, int res_buf, bool relu) {
+        TowerLayer t{};
+        t.w = r->d_conv + l.tc_off;
+        t.bias = l.b_off >= 0 ? r->d_conv + l.b_off : nullptr;
+        t.action_table = l.tc_table_off >= 0 ? r->d_conv + l.tc_table_off : nullptr;
+        t.in_buf = in_buf; t.out_buf = out_buf; t.res_buf = res_buf; t.relu = relu ? 1 : 0;
+        return t;
+    }
+
+    bool launch_tower(TowerArgs& a) {
+        a.n = n; a.H = r->hh; a.W = r->hw; a.A = r->net.action_space;
         static const int dbg = getenv("MZ_TC_DEBUG_SKIP") ? atoi(getenv("MZ_TC_DEBUG_SKIP")) : 0;
         a.debug_skip = dbg;
-        cudaError_t e = launch_conv3x3_tc(a, r->sm_count, stream);
-        if (e != cudaSuccess) return fail("conv3x3_tc launch", e);
+        cudaError_t e = launch_conv_tower_tc(a, r->sm_count, stream);
+        if (e != cudaSuccess) return fail("conv_tower_tc launch", e);
         *launches += 1;
         return true;
+    }
+
+    // one tensor-core conv (a tower of one layer)
+    bool conv_tc(const ConvLayer& l, const float* in, float* out, const float* residual, bool relu,
+                 const int32_t* gather_parent = nullptr, int pool_stride = 0, const int32_t* action = nullptr) {
+        TowerArgs a{};
+        a.n_layers = 1;
+        a.buf[0] = const_cast<float*>(in); a.buf[1] = out; a.buf[2] = const_cast<float*>(residual);
+        a.layer[0] = tower_layer(l, 0, 1, residual ? 2 : -1, relu);
+        if (!action) a.layer[0].action_table = nullptr;
+        a.gather_parent = gather_parent; a.pool_stride = pool_stride; a.action = action;
+        return launch_tower(a);
     }
 
     bool blocks_tc(const std::vector<ConvLayer>& layers, size_t first, size_t count, float** cur, float** tmp, float** spare) {
@@ -643,6 +657,74 @@ struct Runner {
             float* t = *cur; *cur = *spare; *spare = t;
         }
         return true;
+    }
+
+    // [optional stem conv] + `count` residual blocks in as few persistent launches as possible.
+    // ext = tower input (read only, optionally gathered from the hidden pool); ws = three workspaces.
+    // Returns the buffer holding the result (one of ws, or ext if there was nothing to do) or nullptr on error.
+    // `first` = index of the first layer to run; `ext_reusable`: ext is scratch that may be overwritten once read.
+    const float* tower_tc(const std::vector<ConvLayer>& layers, size_t first_layer, bool stem, size_t count, const float* ext,
+                          bool ext_reusable, float* const ws[3], const int32_t* gather_parent, int pool_stride,
+                          const int32_t* action) {
+        if (n > conv_tc_max_boards_fused(r->sm_count)) {
+            // too many tiles per CTA for the fused mode: one launch per conv
+            float* free_ws[3]; int nf = 0;
+            for (int i = 0; i < 3; ++i) if (ws[i] != ext) free_ws[nf++] = ws[i];
+            if (nf < 3) free_ws[nf++] = const_cast<float*>(ext);      // ext is itself a workspace: reusable as the third
+            float *cur = free_ws[0], *tmp = free_ws[1], *spare = free_ws[2];
+            size_t first = first_layer;
+            const float* x = ext;
+            if (stem) { if (!conv_tc(layers[first], ext, cur, nullptr, true, gather_parent, pool_stride, action)) return nullptr; first += 1; x = cur; }
+            if (count > 0 && !stem) {
+                if (!conv_tc(layers[first], ext, tmp, nullptr, true, gather_parent, pool_stride)) return nullptr;
+                if (!conv_tc(layers[first + 1], tmp, spare, ext, true)) return nullptr;      // residual = ext (plain addressing only)
+                { float* t = cur; cur = spare; spare = t; }
+                first += 2; count -= 1; x = cur;
+            }
+            if (!blocks_tc(layers, first, count, &cur, &tmp, &spare)) return nullptr;
+            return x == ext ? x : cur;
+        }
+        size_t li = first_layer, blocks_left = count;
+        bool stem_left = stem;
+        const float* ext_now = ext;                 // buf[0] of the next launch
+        const int32_t* gather_now = gather_parent;
+        const float* result = ext;
+        while (stem_left || blocks_left > 0) {
+            TowerArgs a{};
+            a.buf[0] = const_cast<float*>(ext_now);
+            // the three workspaces, skipping the one that currently holds the input
+            int nb = 1;
+            for (int i = 0; i < 3; ++i) if (ws[i] != ext_now) a.buf[nb++] = ws[i];
+            if (nb < 4) a.buf[nb++] = nullptr;      // (only two spare workspaces when the input is one of ws)
+            a.gather_parent = gather_now; a.pool_stride = pool_stride; a.action = action;
+            int cur = 0, nl = 0;
+            const bool reuse0 = ext_reusable && !gather_now;       // the input buffer is dead after its last reader
+            auto pick = [&](int avoid1, int avoid2) {
+                for (int i = 1; i < 4; ++i) if (i != avoid1 && i != avoid2 && a.buf[i]) return i;
+                if (reuse0 && avoid1 != 0 && avoid2 != 0) return 0;
+                return -1;
+            };
+            if (stem_left) {
+                const int o = pick(cur, -1);
+                a.layer[nl++] = tower_layer(layers[li++], cur, o, -1, true);
+                cur = o; stem_left = false;
+            }
+            while (blocks_left > 0 && nl + 2 <= kTowerMaxLayers) {
+                const int t1 = pick(cur, -1);
+                const int t2 = pick(cur, t1);
+                if (t1 < 0 || t2 < 0) break;
+                a.layer[nl++] = tower_layer(layers[li++], cur, t1, -1, true);
+                a.layer[nl++] = tower_layer(layers[li++], t1, t2, cur, true);
+                cur = t2; --blocks_left;
+            }
+            if (nl == 0) { *err = "tower_tc: no workspace left"; return nullptr; }
+            for (int i = 0; i < nl; ++i) if (!action) a.layer[i].action_table = nullptr;
+            a.n_layers = nl;
+            if (!launch_tower(a)) return nullptr;
+            result = a.buf[cur];
+            ext_now = result; gather_now = nullptr;
+        }
+        return result;
     }
 
     bool conv(const ConvLayer& l, const float* in, float* out, const float* residual, bool relu, int Hin, int Win,
@@ -762,8 +844,10 @@ static int resnet_inference_tc(ResNetDevice* r, const InferCall& c, cudaStream_t
     float* state = r->scratch_state;                   // rescaled state, P64C4, input of the prediction tower
     if (!c.recurrent) {
         if (!R.conv(r->rep_trunk[0], c.in, cur, nullptr, true, nd.obs_h, nd.obs_w, nullptr, 0, nullptr, true)) return MZ_ECUDA;
-        if (!R.blocks_tc(r->rep_trunk, 1, nd.blocks, &cur, &tmp, &spare)) return MZ_ECUDA;
-        if (!R.heads(cur, 0, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, c.hidden, c.pool_hidden, c.pool_stride, c.out_slot,
+        const float* x = R.tower_tc(r->rep_trunk, 1, false, nd.blocks, cur, true, r->ws, nullptr, 0, nullptr);
+        if (!x) return MZ_ECUDA;
+        // note: layers index from 1 in rep_trunk (0 is the stem, run above on the CUDA cores)
+        if (!R.heads(x, 0, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, c.hidden, c.pool_hidden, c.pool_stride, c.out_slot,
                      true, state))
             return MZ_ECUDA;
         if (c.reward_logits) {
@@ -783,22 +867,17 @@ static int resnet_inference_tc(ResNetDevice* r, const InferCall& c, cudaStream_t
             *launches += 1;
             in = spare;
         }
-        if (!R.conv_tc(r->dyn[0], in, cur, nullptr, true, c.gather_parent, c.pool_stride, c.action)) return MZ_ECUDA;
-        if (!R.blocks_tc(r->dyn, 1, nd.blocks, &cur, &tmp, &spare)) return MZ_ECUDA;
-        if (!R.heads(cur, 1, &r->reward_head, nullptr, c.reward_logits, nullptr, c.reward, nullptr, c.hidden, c.pool_hidden,
+        const float* x = R.tower_tc(r->dyn, 0, true, nd.blocks, in, in == spare, r->ws, c.gather_parent, c.pool_stride, c.action);
+        if (!x) return MZ_ECUDA;
+        if (!R.heads(x, 1, &r->reward_head, nullptr, c.reward_logits, nullptr, c.reward, nullptr, c.hidden, c.pool_hidden,
                      c.pool_stride, c.out_slot, true, state))
             return MZ_ECUDA;
     }
-    const float* x = state;
-    if (nd.blocks > 0) {
-        if (!R.conv_tc(r->pred[0], state, tmp, nullptr, true)) return MZ_ECUDA;
-        if (!R.conv_tc(r->pred[1], tmp, spare, state, true)) return MZ_ECUDA;
-        { float* t = cur; cur = spare; spare = t; }
-        if (!R.blocks_tc(r->pred, 2, nd.blocks - 1, &cur, &tmp, &spare)) return MZ_ECUDA;
-        x = cur;
-    }
+    const float* x = R.tower_tc(r->pred, 0, false, nd.blocks, state, true, r->ws, nullptr, 0, nullptr);
+    if (!x) return MZ_ECUDA;
     if (!R.heads(x, 2, &r->value_head, &r->policy_head, c.value_logits, c.policy_logits, c.value, nullptr, nullptr, nullptr, 0, 0, true))
         return MZ_ECUDA;
+    (void)tmp;
     return MZ_OK;
 }
 
