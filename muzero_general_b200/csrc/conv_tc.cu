@@ -39,8 +39,6 @@ constexpr int kStages = 2;
 constexpr int kWBytes = 9 * kPlanes * kC * 16;         // 147456
 constexpr int kTapBytes = kPlanes * kC * 16;           // 16384
 constexpr int kAccCols = 64;
-constexpr int kChains = 2;              // independent accumulator chains per tile (interleaved MMAs), summed in the epilogue
-constexpr int kStageCols = kAccCols * kChains;
 constexpr int kThreads = 384;             // 4 control warps + 8 epilogue warps
 constexpr int kEpiWarps = 8;
 
@@ -167,7 +165,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tower_tc_kernel(const __grid
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic zero-fill -> async proxy readers
     if (warp == 2) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
-                     ::"r"(s_base + Smem::tmem_ptr), "r"(kStages * kStageCols) : "memory");
+                     ::"r"(s_base + Smem::tmem_ptr), "r"(2 * kAccCols) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     tc_fence_before();
@@ -224,8 +222,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tower_tc_kernel(const __grid
                 mbar_wait(bar_a_full(s), ph);
                 tc_fence_after();
                 if (lane == 0) {
-                    const uint32_t d = tmem_base + (uint32_t)(s * kStageCols);
-                    uint32_t acc[kChains] = {0, 0};
+                    const uint32_t d = tmem_base + (uint32_t)(s * kAccCols);
+                    uint32_t acc = 0;
 #pragma unroll 1
                     for (int tap = 0; tap < ((a.debug_skip & 1) ? 0 : 9); ++tap) {
                         if (k == 0) { mbar_wait(bar_w_full(tap), (uint32_t)(l & 1)); tc_fence_after(); }
@@ -236,9 +234,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tower_tc_kernel(const __grid
                         for (int ks = 0; ks < kC / 8; ++ks) {
                             const uint64_t ad = umma_desc(a0 + 2 * ks * kPlaneBytes, kPlaneBytes, 128);
                             const uint64_t bd = umma_desc(b0 + 2 * ks * (kC * 16), kC * 16, 128);
-                            // consecutive MMAs alternate between two accumulators: no back-to-back dependency
-                            umma_tf32(d + (uint32_t)((ks & 1) * kAccCols), ad, bd, acc[ks & 1]);
-                            acc[ks & 1] = 1;
+                            umma_tf32(d, ad, bd, acc);
+                            acc = 1;
                         }
                         if (k == my_tiles - 1) umma_commit(bar_w_empty(tap));   // slot reusable by the next layer
                     }
@@ -292,8 +289,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tower_tc_kernel(const __grid
                 }
                 mbar_wait(bar_acc_full(s), ph);
                 tc_fence_after();
-                uint32_t v[32], v2[32];
-                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(s * kStageCols + half * 32);
+                uint32_t v[32];
+                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(s * kAccCols + half * 32);
                 asm volatile(
                     "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
                     "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
@@ -303,15 +300,6 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tower_tc_kernel(const __grid
                       "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
                       "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
                     : "r"(taddr));
-                asm volatile(
-                    "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-                    "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-                    "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-                    : "=r"(v2[0]), "=r"(v2[1]), "=r"(v2[2]), "=r"(v2[3]), "=r"(v2[4]), "=r"(v2[5]), "=r"(v2[6]), "=r"(v2[7]),
-                      "=r"(v2[8]), "=r"(v2[9]), "=r"(v2[10]), "=r"(v2[11]), "=r"(v2[12]), "=r"(v2[13]), "=r"(v2[14]), "=r"(v2[15]),
-                      "=r"(v2[16]), "=r"(v2[17]), "=r"(v2[18]), "=r"(v2[19]), "=r"(v2[20]), "=r"(v2[21]), "=r"(v2[22]), "=r"(v2[23]),
-                      "=r"(v2[24]), "=r"(v2[25]), "=r"(v2[26]), "=r"(v2[27]), "=r"(v2[28]), "=r"(v2[29]), "=r"(v2[30]), "=r"(v2[31])
-                    : "r"(taddr + (uint32_t)kAccCols));
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
                 tc_fence_before();
                 __syncwarp();
@@ -322,10 +310,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tower_tc_kernel(const __grid
                     for (int j = 0; j < kJ; ++j) {
                         float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
                         if (inside) {
-                            float r0 = (__uint_as_float(v[4 * j + 0]) + __uint_as_float(v2[4 * j + 0])) + bias[4 * j + 0] + add[j].x;
-                            float r1 = (__uint_as_float(v[4 * j + 1]) + __uint_as_float(v2[4 * j + 1])) + bias[4 * j + 1] + add[j].y;
-                            float r2 = (__uint_as_float(v[4 * j + 2]) + __uint_as_float(v2[4 * j + 2])) + bias[4 * j + 2] + add[j].z;
-                            float r3 = (__uint_as_float(v[4 * j + 3]) + __uint_as_float(v2[4 * j + 3])) + bias[4 * j + 3] + add[j].w;
+                            float r0 = __uint_as_float(v[4 * j + 0]) + bias[4 * j + 0] + add[j].x;
+                            float r1 = __uint_as_float(v[4 * j + 1]) + bias[4 * j + 1] + add[j].y;
+                            float r2 = __uint_as_float(v[4 * j + 2]) + bias[4 * j + 2] + add[j].z;
+                            float r3 = __uint_as_float(v[4 * j + 3]) + bias[4 * j + 3] + add[j].w;
                             if (ly.relu) { r0 = fmaxf(r0, 0.f); r1 = fmaxf(r1, 0.f); r2 = fmaxf(r2, 0.f); r3 = fmaxf(r3, 0.f); }
                             o = make_float4(round_tf32(r0), round_tf32(r1), round_tf32(r2), round_tf32(r3));
                         }
@@ -345,7 +333,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tower_tc_kernel(const __grid
     tc_fence_before();
     __syncthreads();
     if (warp == 2)
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kStages * kStageCols) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2 * kAccCols) : "memory");
 }
 
 cudaError_t launch_conv_tower_tc(const TowerArgs& a, int sm_count, cudaStream_t stream) {
