@@ -155,6 +155,29 @@ def host_cores():
         return os.cpu_count() or 1
 
 
+def selfplay_loop(game, B, N, device, moves):
+    """env-steps/s of the full loop: BatchedSelfPlay over B games for ~`moves` lockstep moves."""
+    from muzero_general_b200 import self_play as sp
+    from muzero_general_b200.games import load_game_module
+    from muzero_general_b200.netspec import netspec_from_config, synthetic_weights
+    mod = load_game_module(game)
+    cfg = mod.MuZeroConfig()
+    cfg.num_parallel_games, cfg.rng_mode, cfg.num_simulations = B, "philox", N
+    spec = netspec_from_config(cfg)
+    worker = sp.SelfPlay({"weights": synthetic_weights(spec, 0)}, mod.Game, cfg, seed=0, device=device)
+    worker.play_games(1, 1.0, max_total_moves=2 * B)                  # warm-up (two moves)
+    start_steps, start_games = worker.played_steps, worker.played_games
+    t0 = time.perf_counter()
+    worker.play_games(10 ** 9, 1.0, max_total_moves=start_steps + moves * B)
+    dt = time.perf_counter() - t0
+    steps = worker.played_steps - start_steps
+    res = {"value": steps / dt, "unit": "env-steps/s", "env_steps": int(steps), "seconds": dt,
+           "games_finished": int(worker.played_games - start_games),
+           "includes": "mz_search + numpy vector env step + Dirichlet draw + action sampling + GameHistory assembly"}
+    worker.model.engine.close()
+    return res
+
+
 # ----------------------------------------------------------------------------- main
 def main():
     ap = argparse.ArgumentParser()
@@ -330,6 +353,13 @@ def main():
             "clocks": clk,
             "roofline": roofline,
         }
+        if world == 1 and game in ("cartpole", "tictactoe", "connect4"):
+            # the whole self-play loop through the reference-shaped API (SelfPlay.play_games): search + host
+            # environment stepping (vectorised numpy envs) + action sampling + GameHistory assembly
+            try:
+                out["selfplay_loop"] = selfplay_loop(game, B, N, local_rank, moves=12 if game == "cartpole" else 6)
+            except Exception as e:                       # never lose the headline line over the extra
+                out["selfplay_loop"] = {"error": repr(e)}
         if world == 1 and not args.no_cpu_baseline:
             cores = host_cores()
             v, searches, w = cpu_baseline(game, N, args.cpu_seconds, cores)

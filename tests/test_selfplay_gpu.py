@@ -1,0 +1,105 @@
+"""The reference-shaped SelfPlay / MCTS surface on the real device engine (C ABI underneath)."""
+import numpy
+import pytest
+
+from conftest import golden_json, golden_npz, weights_for
+from muzero_general_b200.games import load_game_module
+from muzero_general_b200.netspec import netspec_from_config
+
+pytestmark = pytest.mark.gpu
+
+
+def _worker(name, seed, **over):
+    from muzero_general_b200 import self_play as sp
+    mod = load_game_module(name)
+    cfg = mod.MuZeroConfig()
+    for k, v in over.items():
+        setattr(cfg, k, v)
+    spec = netspec_from_config(cfg)
+    return sp.SelfPlay({"weights": weights_for(name, spec)}, mod.Game, cfg, seed), cfg, sp
+
+
+@pytest.mark.parametrize("name", ["tictactoe", "connect4"])
+def test_play_game_reproduces_reference_games_on_device(name, monkeypatch):
+    """Whole games through SelfPlay.play_game on the GPU: the reference's action sequences and visit
+    distributions (fp32 CUDA-core networks so the comparison is tight), root values to 1e-4."""
+    monkeypatch.setenv("MZ_NO_TC", "1")
+    for ref in golden_json("play.json")[name]:
+        worker, cfg, sp = _worker(name, ref["seed"], num_simulations=ref["num_simulations"])
+        gh = worker.play_game(ref["temperature"], cfg.temperature_threshold, False, "self", 0)
+        assert [int(a) for a in gh.action_history] == ref["action_history"]
+        assert [[float(x) for x in c] for c in gh.child_visits] == ref["child_visits"]
+        assert [float(r) for r in gh.reward_history] == ref["reward_history"]
+        assert [int(t) for t in gh.to_play_history] == ref["to_play_history"]
+        numpy.testing.assert_allclose(gh.root_values, ref["root_values"], rtol=1e-4, atol=1e-5)
+        worker.model.engine.close()
+
+
+@pytest.mark.parametrize("name,tc", [("tictactoe", "0"), ("connect4", "0"), ("connect4", "1")])
+def test_mcts_run_node_graph_on_device(name, tc, monkeypatch):
+    """MCTS(config).run returns a Node graph with the reference's shape; hidden states come back in NCHW
+    order whatever the internal layout (P64C4 on the tensor-core path)."""
+    monkeypatch.setenv("MZ_NO_TC", "0" if tc == "1" else "1")
+    worker, cfg, sp = _worker(name, 0)
+    c = golden_json(f"mcts_{name}.json")[0]
+    cfg.num_simulations = c["num_simulations"]
+    worker, cfg, sp = _worker(name, 0, num_simulations=c["num_simulations"])
+    numpy.random.seed(c["seed"])
+    obs = numpy.array(c["obs"]).reshape(c["obs_shape"])
+    root, info = sp.MCTS(cfg).run(worker.model, obs, c["legal"], c["to_play"], True)
+    assert list(root.children.keys()) == c["root_actions"]
+    assert [root.children[a].visit_count for a in c["root_actions"]] == c["root_visits"]
+    assert root.visit_count == c["num_simulations"]
+    tol = 1e-4 if tc == "0" else 1e-2
+    assert abs(root.value() - c["root_value"]) <= tol * max(1.0, abs(c["root_value"]))
+    assert info["max_tree_depth"] == c["max_tree_depth"]
+    # root hidden state = the reference network's representation of the observation
+    spec = netspec_from_config(cfg)
+    from oracle.net import OracleNet
+    h = OracleNet(spec, weights_for(name, spec)).initial_inference(obs[None].astype(numpy.float32))[3].numpy().ravel()
+    numpy.testing.assert_allclose(root.hidden_state, h, rtol=2e-2 if tc == "1" else 2e-4, atol=2e-2 if tc == "1" else 2e-5)
+    node = root
+    for a in c["sims"][-1]["actions"][:-1]:
+        node = node.children[a]
+        assert node.expanded() and node.hidden_state is not None and node.hidden_state.shape == (spec.hidden_elems,)
+    worker.model.engine.close()
+
+
+def test_batched_self_play_on_device():
+    """Lockstep batch on the device: every finished GameHistory is well formed; slot 0 equals the
+    single-game run with the same seed (numpy draw order)."""
+    w8, cfg, sp = _worker("tictactoe", 3, num_parallel_games=8, num_simulations=16)
+    games = w8.play_games(8, 1.0)
+    for g in games:
+        T = len(g.action_history) - 1
+        assert 5 <= T <= 9 and len(g.child_visits) == T == len(g.root_values)
+        assert all(abs(sum(c) - 1) < 1e-12 for c in g.child_visits)
+        assert g.observation_history[0].shape == (3, 3, 3)
+    w1, _, _ = _worker("tictactoe", 3, num_parallel_games=1, num_simulations=16)
+    solo = w1.play_games(1, 1.0)[0]
+    same = [g for g in games if [int(a) for a in g.action_history] == [int(a) for a in solo.action_history]]
+    assert same and same[0].child_visits == solo.child_visits
+    w8.model.engine.close(); w1.model.engine.close()
+
+
+def test_error_paths_on_device(game_configs):
+    from muzero_general_b200 import _lib
+    from muzero_general_b200.engine import SearchEngine
+    cfg = game_configs["cartpole"]
+    eng = SearchEngine(cfg, max_games=4, num_simulations=5)
+    obs = numpy.zeros((4, 4), numpy.float32)
+    with pytest.raises(_lib.MzError, match="weights not loaded"):
+        eng.search(obs=obs)
+    spec = netspec_from_config(cfg)
+    w = dict(weights_for("cartpole", spec))
+    bad = dict(w); bad.pop("prediction_value_network.module.2.bias")
+    with pytest.raises(KeyError):
+        eng.load_weights(bad)
+    eng.load_weights(w)
+    with pytest.raises(_lib.MzError, match="out of range"):
+        eng.search(obs=numpy.zeros((5, 4), numpy.float32))
+    with pytest.raises(ValueError):
+        eng.search(obs=numpy.zeros((4, 5), numpy.float32))
+    out = eng.search(obs=obs[:2])                      # fewer games than the capacity
+    assert out.visit_counts.shape == (2, 2) and (out.visit_counts.sum(1) == 5).all()
+    eng.close()
