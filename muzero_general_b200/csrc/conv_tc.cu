@@ -3,23 +3,30 @@
 // Used for the residual towers of board-sized states (H <= 6, W <= 7, C = 64: Connect4,
 // models.py:213-229 inside representation / dynamics / prediction).  Per CTA:
 //
-//   weights  [tap 9][C/4][cout C][4] tf32, BN folded      resident in shared memory (bulk copy)
-//   A tile   two boards = 128 rows of the "P64C4" layout   2-stage ring, cp.async.bulk (TMA unit)
+//   weights  [tap 9][C/8][cout C][8] fp16, BN folded       resident in shared memory (bulk copy)
+//   A tile   two boards = 128 rows of the "P64C8" layout   2-stage ring, cp.async.bulk (TMA unit)
 //   D        128 x 64 fp32 accumulator                     TMEM, double buffered
 //
-// P64C4 activation layout (HBM and shared): a board is 64 positions p = (y+1)*8 + x (row 0, rows
-// H+1.. and columns W..7 are zero padding) and channels are grouped by four:
-// act[board][c/4][p][c%4].  With the UMMA K-major SWIZZLE_NONE canonical layout and SBO = 128 B a
+// Operands are fp16 (10-bit mantissa - the same as tf32 - with fp32 accumulation): one tcgen05.mma
+// consumes K = 16 channels per 32-byte operand row, so a tile needs 36 MMAs instead of the 72 a tf32
+// formulation needs, and every activation / weight byte moved through L2 and shared memory is halved.
+// Measured motivation: profiles/r01_conv_tc_bottleneck.md (the M128 x N64 MMA is operand-fetch bound).
+//
+// P64C8 activation layout (HBM and shared): a board is 64 positions p = (y+1)*8 + x (row 0, rows
+// H+1.. and columns W..7 are zero padding) and channels are grouped by eight:
+// act[board][c/8][p][c%8] (fp16).  With the UMMA K-major SWIZZLE_NONE canonical layout and SBO = 128 B a
 // channel-group plane is a dense array of 16-byte rows, so the operand of filter tap (dy,dx) is the
 // SAME shared-memory tile with its start address moved by (dy*8+dx) rows: the implicit GEMM needs
-// no im2col copy, one bulk load per (board, channel group) and 72 tcgen05.mma (M128 N64 K8, tf32)
-// per tile.  Epilogue warps read the accumulator with tcgen05.ld, add the folded-BN bias, the
-// optional residual and the optional action-plane term (models.py:557-572 folded into a
-// per-position table), apply ReLU, zero the padding positions and store P64C4 again.
+// no im2col copy and one bulk load per (board, channel group).  Epilogue warps read the accumulator with
+// tcgen05.ld, add the folded-BN bias, the optional residual and the optional action-plane term
+// (models.py:557-572 folded into a per-position table), apply ReLU, zero the padding positions,
+// convert to fp16 (round to nearest, saturating) and store P64C8 again.
 //
 // Warp roles (384 threads): 0 = bulk-copy producer, 1 = MMA issuer, 2 = TMEM allocator,
 // 4..11 = epilogue (TMEM lane quarter = warp % 4, accumulator column half = (warp - 4) / 4); the
 // epilogue prefetches its residual / action terms before it waits for the accumulator.
+#include <cuda_fp16.h>
+
 #include "pipeline.h"
 #include "conv_tc.h"
 
@@ -33,11 +40,12 @@ constexpr int kBoards = 2;             // boards per tile -> M = 128
 constexpr int kHalo = 10;              // zero rows above / below the tile (|shift| <= 9)
 constexpr int kRows = kBoards * kPos + 2 * kHalo;      // 148 rows per plane
 constexpr int kPlaneBytes = kRows * 16;                // LBO of A
-constexpr int kPlanes = kC / 4;                        // 16 channel groups
-constexpr int kStageBytes = kPlanes * kPlaneBytes;     // 37888
+constexpr int kPlanes = kC / 8;                        // 8 channel groups of 8 fp16
+constexpr int kStageBytes = kPlanes * kPlaneBytes;     // 18944
 constexpr int kStages = 2;
-constexpr int kWBytes = 9 * kPlanes * kC * 16;         // 147456
-constexpr int kTapBytes = kPlanes * kC * 16;           // 16384
+constexpr int kWBytes = 9 * kPlanes * kC * 16;         // 73728
+constexpr int kTapBytes = kPlanes * kC * 16;           // 8192
+constexpr int kBoardHalves = kC * kPos;                // 4096 fp16 per board
 constexpr int kAccCols = 64;
 constexpr int kThreads = 384;             // 4 control warps + 8 epilogue warps
 constexpr int kEpiWarps = 8;
@@ -92,32 +100,40 @@ MZ_DEVINL uint64_t umma_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_byt
     return d;
 }
 
-// kind::tf32, fp32 accumulate, A and B K-major, M = 128, N = 64 (cute::UMMA::InstrDescriptor)
-constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kAccCols >> 3) << 17) | ((128u >> 4) << 24);
+// kind::f16 with fp16 operands (format 0), fp32 accumulate, A and B K-major, M = 128, N = 64
+// (cute::UMMA::InstrDescriptor)
+constexpr uint32_t kIdesc = (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(kAccCols >> 3) << 17) | ((128u >> 4) << 24);
 
-MZ_DEVINL void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t accumulate) {
+MZ_DEVINL void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t accumulate) {
     asm volatile(
         "{\n\t"
         ".reg .pred p;\n\t"
         "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
         "}" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(kIdesc), "r"(accumulate) : "memory");
 }
 MZ_DEVINL void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
-MZ_DEVINL float round_tf32(float x) {
+// two fp32 -> packed fp16x2, round to nearest even, saturating to the finite range
+MZ_DEVINL uint32_t pack_f16x2(float lo, float hi) {
     uint32_t r;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-    return __uint_as_float(r);
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
+MZ_DEVINL float2 unpack_f16x2(uint32_t v) {
+    __half2 h = *reinterpret_cast<__half2*>(&v);
+    return __half22float2(h);
 }
 
 }  // namespace
 
-MZ_DEVINL const float* tower_board(const TowerArgs& a, int buf, int g) {
+// activation buffers hold fp16 (the host side types them float*: 2048 float slots per board)
+MZ_DEVINL const __half* tower_board(const TowerArgs& a, int buf, int g) {
+    const __half* base = reinterpret_cast<const __half*>(a.buf[buf]);
     if (buf == 0 && a.gather_parent)
-        return a.buf[0] + ((size_t)g * a.pool_stride + a.gather_parent[g]) * (size_t)(kC * kPos);
-    return a.buf[buf] + (size_t)g * (kC * kPos);
+        return base + ((size_t)g * a.pool_stride + a.gather_parent[g]) * (size_t)kBoardHalves;
+    return base + (size_t)g * kBoardHalves;
 }
 
 __global__ void __launch_bounds__(kThreads, 1) conv_tower_tc_kernel(const __grid_constant__ TowerArgs a) {
@@ -205,9 +221,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tower_tc_kernel(const __grid
                 __syncwarp();
                 for (int i = lane; i < nb * kPlanes; i += 32) {          // (board, channel group) pairs
                     const int b = i / kPlanes, j = i % kPlanes;
-                    const float* src = tower_board(a, in_buf, tile * kBoards + b);
+                    const __half* src = tower_board(a, in_buf, tile * kBoards + b);
                     bulk_g2s(s_a + s * kStageBytes + j * kPlaneBytes + (kHalo + b * kPos) * 16,
-                             src + (size_t)j * kPos * 4, kPos * 16, bar_a_full(s));
+                             src + (size_t)j * kPos * 8, kPos * 16, bar_a_full(s));
                 }
             }
         }
@@ -231,10 +247,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tower_tc_kernel(const __grid
                         const uint32_t a0 = s_a + s * kStageBytes + (kHalo + shift) * 16;
                         const uint32_t b0 = s_w + tap * kTapBytes;
 #pragma unroll
-                        for (int ks = 0; ks < kC / 8; ++ks) {
+                        for (int ks = 0; ks < kC / 16; ++ks) {
                             const uint64_t ad = umma_desc(a0 + 2 * ks * kPlaneBytes, kPlaneBytes, 128);
                             const uint64_t bd = umma_desc(b0 + 2 * ks * (kC * 16), kC * 16, 128);
-                            umma_tf32(d, ad, bd, acc);
+                            umma_f16(d, ad, bd, acc);
                             acc = 1;
                         }
                         if (k == my_tiles - 1) umma_commit(bar_w_empty(tap));   // slot reusable by the next layer
@@ -254,8 +270,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tower_tc_kernel(const __grid
         const int b = row / kPos, p = row % kPos;
         const int y = p / 8 - 1, x = p % 8;
         const bool inside = (y >= 0 && y < a.H && x < a.W);
-        constexpr int kJ = kPlanes / 2;               // channel groups handled by this warp
-        const size_t my_off = (size_t)p * 4 + (size_t)(half * kJ) * kPos * 4;
+        constexpr int kJ = kPlanes / 2;               // channel groups (of 8) handled by this warp: 32 channels
+        const size_t my_off = (size_t)p * 8 + (size_t)(half * kJ) * kPos * 8;      // in fp16 elements
         int it = 0;
         for (int l = 0; l < L; ++l) {
             const TowerLayer& ly = a.layer[l];
@@ -267,25 +283,17 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tower_tc_kernel(const __grid
                 const int g = tile * kBoards + b;
                 const bool live = inside && g < a.n;
                 // ---- prefetch everything that does not depend on the accumulator
-                float4 add[kJ];
+                uint4 res[kJ];                          // residual, 8 fp16 per channel group
+                float act_scale = 0.0f;
 #pragma unroll
-                for (int j = 0; j < kJ; ++j) add[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int j = 0; j < kJ; ++j) res[j] = make_uint4(0, 0, 0, 0);
                 if (live) {
                     if (ly.res_buf >= 0 && !(a.debug_skip & 8)) {
-                        const float* res = tower_board(a, ly.res_buf, g) + my_off;
+                        const __half* rp = tower_board(a, ly.res_buf, g) + my_off;
 #pragma unroll
-                        for (int j = 0; j < kJ; ++j) add[j] = *reinterpret_cast<const float4*>(res + (size_t)j * kPos * 4);
+                        for (int j = 0; j < kJ; ++j) res[j] = *reinterpret_cast<const uint4*>(rp + (size_t)j * kPos * 8);
                     }
-                    if (ly.action_table) {
-                        const float sc = __fdiv_rn((float)a.action[g], (float)a.A);
-                        const float* atab = ly.action_table + (size_t)p * kC + half * 32;
-#pragma unroll
-                        for (int j = 0; j < kJ; ++j) {
-                            const float4 t4 = *reinterpret_cast<const float4*>(atab + 4 * j);
-                            add[j].x = fmaf(sc, t4.x, add[j].x); add[j].y = fmaf(sc, t4.y, add[j].y);
-                            add[j].z = fmaf(sc, t4.z, add[j].z); add[j].w = fmaf(sc, t4.w, add[j].w);
-                        }
-                    }
+                    if (ly.action_table) act_scale = __fdiv_rn((float)a.action[g], (float)a.A);
                 }
                 mbar_wait(bar_acc_full(s), ph);
                 tc_fence_after();
@@ -305,19 +313,31 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tower_tc_kernel(const __grid
                 __syncwarp();
                 if (lane == 0) mbar_arrive(bar_acc_empty(s));        // accumulator half read: may be overwritten
                 if (g < a.n && !(a.debug_skip & 4)) {
-                    float* dst = a.buf[ly.out_buf] + (size_t)g * (kC * kPos) + my_off;
+                    __half* dst = reinterpret_cast<__half*>(a.buf[ly.out_buf]) + (size_t)g * kBoardHalves + my_off;
+                    const float* atab = ly.action_table ? ly.action_table + (size_t)p * kC + half * 32 : nullptr;
 #pragma unroll
                     for (int j = 0; j < kJ; ++j) {
-                        float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+                        uint4 o = make_uint4(0, 0, 0, 0);
                         if (inside) {
-                            float r0 = __uint_as_float(v[4 * j + 0]) + bias[4 * j + 0] + add[j].x;
-                            float r1 = __uint_as_float(v[4 * j + 1]) + bias[4 * j + 1] + add[j].y;
-                            float r2 = __uint_as_float(v[4 * j + 2]) + bias[4 * j + 2] + add[j].z;
-                            float r3 = __uint_as_float(v[4 * j + 3]) + bias[4 * j + 3] + add[j].w;
-                            if (ly.relu) { r0 = fmaxf(r0, 0.f); r1 = fmaxf(r1, 0.f); r2 = fmaxf(r2, 0.f); r3 = fmaxf(r3, 0.f); }
-                            o = make_float4(round_tf32(r0), round_tf32(r1), round_tf32(r2), round_tf32(r3));
+                            float r[8];
+                            const uint32_t rw[4] = {res[j].x, res[j].y, res[j].z, res[j].w};
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                const float2 rf = unpack_f16x2(rw[e]);
+                                r[2 * e + 0] = __uint_as_float(v[8 * j + 2 * e + 0]) + bias[8 * j + 2 * e + 0] + rf.x;
+                                r[2 * e + 1] = __uint_as_float(v[8 * j + 2 * e + 1]) + bias[8 * j + 2 * e + 1] + rf.y;
+                            }
+                            if (atab) {
+#pragma unroll
+                                for (int e = 0; e < 8; ++e) r[e] = fmaf(act_scale, atab[8 * j + e], r[e]);
+                            }
+                            if (ly.relu) {
+#pragma unroll
+                                for (int e = 0; e < 8; ++e) r[e] = fmaxf(r[e], 0.0f);
+                            }
+                            o = make_uint4(pack_f16x2(r[0], r[1]), pack_f16x2(r[2], r[3]), pack_f16x2(r[4], r[5]), pack_f16x2(r[6], r[7]));
                         }
-                        *reinterpret_cast<float4*>(dst + (size_t)j * kPos * 4) = o;
+                        *reinterpret_cast<uint4*>(dst + (size_t)j * kPos * 8) = o;
                     }
                 }
                 if (l + 1 < L) {
@@ -354,6 +374,6 @@ cudaError_t launch_conv_tower_tc(const TowerArgs& a, int sm_count, cudaStream_t 
 int conv_tc_max_boards_fused(int sm_count) { return sm_count * kTowerMaxTiles * kBoards; }
 
 bool conv_tc_supported(int C, int H, int W) { return C == kC && H >= 1 && H <= 6 && W >= 1 && W <= 7; }
-int conv_tc_board_elems() { return kC * kPos; }
+int conv_tc_board_elems() { return kBoardHalves / 2; }      // float slots per board (the buffers hold fp16)
 
 }  // namespace mz

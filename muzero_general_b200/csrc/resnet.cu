@@ -22,6 +22,8 @@
 #include <string>
 #include <vector>
 
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 #include "conv_tc.h"
 #include "pipeline.h"
@@ -42,7 +44,7 @@ struct ConvArgs {
     int pool_stride;
     int n, Cin, Cout, Hin, Win, Ho, Wo, stride, relu, A;
     int boards_per_cta, cin_chunk;
-    int out_p64c4;            // write act[g][co/4][(y+1)*8+x][co%4] (tensor-core path layout) instead of NCHW
+    int out_p64c4;            // write fp16 act[g][co/8][(y+1)*8+x][co%8] (tensor-core path layout P64C8) instead of NCHW
 };
 
 template <int P, int STRIDE, int MAX_ITEMS>
@@ -151,7 +153,8 @@ __global__ void __launch_bounds__(256) conv3x3_kernel(const __grid_constant__ Co
                 if (a.residual) r += a.residual[o + p];
                 if (a.relu) r = fmaxf(r, 0.0f);
                 if (a.out_p64c4)
-                    a.out[(((size_t)g * (a.Cout / 4) + co / 4) * 64 + (y + 1) * 8 + seg * P + p) * 4 + (co & 3)] = r;
+                    reinterpret_cast<__half*>(a.out)[(((size_t)g * (a.Cout / 8) + co / 8) * 64 + (y + 1) * 8 + seg * P + p) * 8 + (co & 7)] =
+                        __float2half_rn(r);
                 else
                     a.out[o + p] = r;
             }
@@ -202,14 +205,14 @@ struct HeadsArgs {
     int pool_stride, out_slot;
     int smem_floats;
     int p64c4, W;              // input (and pool target) use the tensor-core board layout
-    float* state_p64c4;        // [n, 4096] rescaled state in P64C4 (input of the prediction tower), or nullptr
+    float* state_p64c4;        // [n, 4096 fp16] rescaled state in P64C8 (input of the prediction tower), or nullptr
     int w_lo, w_floats;        // slice of the head blob this launch needs (staged in shared memory)
     int warp_floats;           // per-warp scratch: x tile + two activation vectors
 };
 
-// offset of (channel c, dense position p) inside one P64C4 state
+// offset (in fp16 elements) of (channel c, dense position p) inside one P64C8 state of 4096 halves
 __device__ __forceinline__ int p64c4_index(int c, int p, int W) {
-    return ((c >> 2) * 64 + (p / W + 1) * 8 + (p % W)) * 4 + (c & 3);
+    return ((c >> 3) * 64 + (p / W + 1) * 8 + (p % W)) * 8 + (c & 7);
 }
 
 // Persistent CTAs (one per SM), 512 threads = 4 groups of 128: the head weights of this launch are staged
@@ -242,12 +245,14 @@ __global__ void __launch_bounds__(kHeadThreads) heads_kernel(const __grid_consta
     for (int g = blockIdx.x * ngroups + group; g < a.n; g += gridDim.x * ngroups) {
         // ---- stage x[p][c]
         if (a.p64c4) {
-            const float4* x4 = reinterpret_cast<const float4*>(a.x + (size_t)g * 4096);
-            for (int i = t; i < (C / 4) * HW; i += kHeadGroup) {
+            const uint4* x8 = reinterpret_cast<const uint4*>(reinterpret_cast<const __half*>(a.x) + (size_t)g * 4096);
+            for (int i = t; i < (C / 8) * HW; i += kHeadGroup) {
                 const int j = i / HW, p = i % HW;
-                const float4 v = x4[j * 64 + (p / a.W + 1) * 8 + (p % a.W)];
-                float* d = s_x + p * CP + 4 * j;
-                d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+                const uint4 v = x8[j * 64 + (p / a.W + 1) * 8 + (p % a.W)];
+                const __half2* h2 = reinterpret_cast<const __half2*>(&v);
+                float* d = s_x + p * CP + 8 * j;
+#pragma unroll
+                for (int e = 0; e < 4; ++e) { const float2 f = __half22float2(h2[e]); d[2 * e] = f.x; d[2 * e + 1] = f.y; }
             }
         } else {
             const float* x = a.x + (size_t)g * C * HW;
@@ -266,12 +271,11 @@ __global__ void __launch_bounds__(kHeadThreads) heads_kernel(const __grid_consta
                     const float v = __fdiv_rn(__fsub_rn(s_x[p * CP + c], lo), sc);
                     if (a.rescaled) a.rescaled[(size_t)g * C * HW + c * HW + p] = v;
                     if (a.p64c4) {
-                        uint32_t rb;                      // operands of the tf32 convs: round to nearest once, here
-                        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(rb) : "f"(v));
-                        const float vt = __uint_as_float(rb);
+                        const __half vt = __float2half_rn(v);      // fp16 operand of the tensor-core convs
                         const int off = p64c4_index(c, p, a.W);
-                        if (a.pool_hidden) a.pool_hidden[((size_t)g * a.pool_stride + a.out_slot) * 4096 + off] = vt;
-                        if (a.state_p64c4) a.state_p64c4[(size_t)g * 4096 + off] = vt;
+                        if (a.pool_hidden)
+                            reinterpret_cast<__half*>(a.pool_hidden)[((size_t)g * a.pool_stride + a.out_slot) * 4096 + off] = vt;
+                        if (a.state_p64c4) reinterpret_cast<__half*>(a.state_p64c4)[(size_t)g * 4096 + off] = vt;
                     } else if (a.pool_hidden) {
                         a.pool_hidden[((size_t)g * a.pool_stride + a.out_slot) * C * HW + c * HW + p] = v;
                     }
@@ -340,14 +344,14 @@ __global__ void copy_from_pool_kernel(const float* pool, float* out, int n, int 
     out[i] = pool[(g * pool_stride + slot) * elems + e];
 }
 
-// dense NCHW [count][C][H*W]  <->  P64C4 [count][C/4][64][4]
+// dense fp32 NCHW [count][C][H*W]  <->  fp16 P64C8 [count][C/8][64][8]
 __global__ void nchw_to_p64c4_kernel(const float* in, float* out, int count, int C, int H, int W) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int HW = H * W;
     if (i >= (size_t)count * C * HW) return;
     const size_t g = i / ((size_t)C * HW);
     const int c = (i / HW) % C, p = i % HW;
-    out[g * 4096 + p64c4_index(c, p, W)] = in[i];
+    reinterpret_cast<__half*>(out)[g * 4096 + p64c4_index(c, p, W)] = __float2half_rn(in[i]);
 }
 __global__ void p64c4_to_nchw_kernel(const float* in, float* out, int count, int C, int H, int W) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -355,7 +359,7 @@ __global__ void p64c4_to_nchw_kernel(const float* in, float* out, int count, int
     if (i >= (size_t)count * C * HW) return;
     const size_t g = i / ((size_t)C * HW);
     const int c = (i / HW) % C, p = i % HW;
-    out[i] = in[g * 4096 + p64c4_index(c, p, W)];
+    out[i] = __half2float(reinterpret_cast<const __half*>(in)[g * 4096 + p64c4_index(c, p, W)]);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -384,10 +388,10 @@ struct ResNetDevice {
     float* ws[3] = {nullptr, nullptr, nullptr};
     size_t ws_elems = 0;
     float* scratch_hidden = nullptr;   // [B, C*hh*hw] rescaled state when no pool is given (dense NCHW)
-    float* scratch_state = nullptr;    // [B, 4096] same state in P64C4 (tensor-core path)
+    float* scratch_state = nullptr;    // [B, 4096 fp16] same state in P64C8 (tensor-core path)
     bool loaded = false;
     bool use_tc = false;               // residual towers on tcgen05 (conv_tc.cu)
-    int state_elems = 0;               // floats per stored hidden state (dense C*H*W, or 4096 for P64C4)
+    int state_elems = 0;               // float slots per stored hidden state (dense C*H*W, or 2048 = 4096 fp16 for P64C8)
 };
 
 static int conv_out(int h, int stride) { return (h - 1) / stride + 1; }
@@ -461,12 +465,27 @@ struct Loader {
 };
 
 // conv3x3 [cout][cin][3][3] (+ optional BN prefix) -> [cin][9][cout] with the BN scale folded in
-float to_tf32(float x) {            // round to nearest, ties away (cvt.rna.tf32.f32)
+uint16_t to_f16(float x) {          // IEEE fp32 -> fp16, round to nearest even, saturating to +-65504
     uint32_t u;
     memcpy(&u, &x, 4);
-    u = (u + 0x1000u) & 0xFFFFE000u;
-    memcpy(&x, &u, 4);
-    return x;
+    const uint32_t sign = (u >> 16) & 0x8000u;
+    u &= 0x7FFFFFFFu;
+    if (u >= 0x477FF000u) return (uint16_t)(sign | 0x7BFFu);               // >= 65520 (or inf/nan): clamp
+    if (u < 0x38800000u) {                                                 // subnormal half or zero
+        if (u < 0x33000000u) return (uint16_t)sign;
+        const int shift = 126 - (int)(u >> 23);                            // 14..24
+        uint32_t mant = (u & 0x7FFFFFu) | 0x800000u;
+        const uint32_t lsb = 1u << shift, half = lsb >> 1;
+        uint32_t q = mant >> shift;
+        const uint32_t rem = mant & (lsb - 1);
+        if (rem > half || (rem == half && (q & 1))) ++q;
+        return (uint16_t)(sign | q);
+    }
+    uint32_t e = ((u >> 23) - 112) << 10, m = (u >> 13) & 0x3FFu;
+    uint32_t h = e | m;
+    const uint32_t rem = u & 0x1FFFu;
+    if (rem > 0x1000u || (rem == 0x1000u && (h & 1))) ++h;                 // may carry into the exponent: still correct
+    return (uint16_t)(sign | h);
 }
 
 bool pack_conv(Loader& L, const std::string& conv, const std::string& bn, int cin, int cout, int stride,
@@ -503,17 +522,18 @@ bool pack_conv(Loader& L, const std::string& conv, const std::string& bn, int ci
     while (blob.size() % 4) blob.push_back(0.0f);           // keep every layer 16-byte aligned
     l.tc_off = l.tc_table_off = -1;
     if (tc) {
-        // image [tap][cin/4][cout][4] over the first 64 input channels; an extra (65th) input channel is the
-        // constant action plane and becomes a per-position table (sum of the taps that stay inside the board)
+        // fp16 image [tap][cin/8][cout][8] over the first 64 input channels (two halves per float slot of the
+        // blob); an extra (65th) input channel is the constant action plane and becomes a per-position fp32
+        // table (sum of the taps that stay inside the board)
         const int C = cout;
         l.tc_off = (long)blob.size();
-        blob.resize(blob.size() + (size_t)9 * C * C);
-        float* img = blob.data() + l.tc_off;
+        blob.resize(blob.size() + (size_t)9 * C * C / 2);
+        uint16_t* img = reinterpret_cast<uint16_t*>(blob.data() + l.tc_off);
         for (int tap = 0; tap < 9; ++tap)
             for (int ci = 0; ci < C; ++ci)
                 for (int co = 0; co < C; ++co)
-                    img[(((size_t)tap * (C / 4) + ci / 4) * C + co) * 4 + (ci % 4)] =
-                        to_tf32((float)((double)w->data[((size_t)co * cin + ci) * 9 + tap] * scale[co]));
+                    img[(((size_t)tap * (C / 8) + ci / 8) * C + co) * 8 + (ci % 8)] =
+                        to_f16((float)((double)w->data[((size_t)co * cin + ci) * 9 + tap] * scale[co]));
         if (cin == C + 1) {
             l.tc_table_off = (long)blob.size();
             blob.resize(blob.size() + (size_t)64 * C, 0.0f);
@@ -902,7 +922,7 @@ int resnet_debug_conv(int n, int C, int H, int W, const float* x, const float* w
     long bias_off = -1;
     if (bias) { bias_off = (long)blob.size(); blob.insert(blob.end(), bias, bias + C); while (blob.size() % 4) blob.push_back(0.f); }
     layers[0].b_off = bias_off;
-    const size_t dense = (size_t)n * C * H * W, packed = (size_t)n * 4096;
+    const size_t dense = (size_t)n * C * H * W, packed = (size_t)n * conv_tc_board_elems();
     float *d_blob = nullptr, *d_x = nullptr, *d_res = nullptr, *d_out = nullptr, *d_px = nullptr, *d_pres = nullptr, *d_pout = nullptr;
     auto cleanup = [&]() { for (float* p : {d_blob, d_x, d_res, d_out, d_px, d_pres, d_pout}) if (p) cudaFree(p); };
     bool ok = cudaMalloc(&d_blob, blob.size() * 4) == cudaSuccess && cudaMalloc(&d_x, dense * 4) == cudaSuccess &&

@@ -1,7 +1,8 @@
 """conv3x3 kernels against torch's fp32 conv2d (a floating-point kernel: torch fp32 is the reference).
 
 Tolerances stated here: the CUDA-core path accumulates in fp32 (rtol 1e-4); the tcgen05 path multiplies
-tf32-rounded operands (10-bit mantissa) with fp32 accumulation: |err| <= 2e-3 * (|w| . |x|) per output."""
+fp16 operands (10-bit mantissa, like tf32) with fp32 accumulation and stores fp16:
+|err| <= 2e-3 * (|w| . |x|) + 1e-3 * |out| per output."""
 import numpy
 import pytest
 import torch
@@ -42,7 +43,7 @@ def test_tensor_core_conv_matches_torch(n, H, W):
         x, w, b, r = _case(n, C, H, W, 2 + n, with_res)
         got = debug_conv3x3(x, w, b, r, relu, tensor_cores=True)
         ref = _ref(x, w, b, r, relu)
-        # error budget: tf32 operand rounding (2^-11 each) on sum |w||x|
+        # error budget: fp16 operand rounding (2^-11 each) on sum |w||x|, fp16 rounding of the stored result
         bound = torch.nn.functional.conv2d(torch.from_numpy(numpy.abs(x)), torch.from_numpy(numpy.abs(w)), None, 1, 1).numpy()
         err = numpy.abs(got - ref)
         assert (err <= 2e-3 * bound + 1e-3 * numpy.abs(ref) + 1e-5).all(), float((err / (bound + 1e-6)).max())
@@ -50,14 +51,14 @@ def test_tensor_core_conv_matches_torch(n, H, W):
         assert numpy.abs(got - ref).mean() < 5e-3
 
 
-def test_tensor_core_conv_exact_on_tf32_representable_inputs():
-    """With operands that are exactly representable in tf32 and small integer values the tensor-core
-    result equals the fp32 reference exactly: proves tiling, tap shifts and padding are right."""
+def test_tensor_core_conv_exact_on_fp16_representable_inputs():
+    """With small integer operands (exact in fp16, results below 2048 so the fp16 store is exact too) the
+    tensor-core result equals the fp32 reference exactly: proves tiling, tap shifts and padding are right."""
     from muzero_general_b200.engine import debug_conv3x3
     rs = numpy.random.RandomState(0)
     n, C, H, W = 11, 64, 6, 7
-    x = rs.randint(-4, 5, size=(n, C, H, W)).astype(numpy.float32)
-    w = rs.randint(-2, 3, size=(C, C, 3, 3)).astype(numpy.float32)
+    x = rs.randint(-2, 3, size=(n, C, H, W)).astype(numpy.float32)
+    w = rs.randint(-1, 2, size=(C, C, 3, 3)).astype(numpy.float32)
     b = rs.randint(-3, 4, size=C).astype(numpy.float32)
     r = rs.randint(-5, 6, size=(n, C, H, W)).astype(numpy.float32)
     got = debug_conv3x3(x, w, b, r, True, tensor_cores=True)

@@ -143,3 +143,58 @@ def test_reference_replay_buffer_and_trainer_consume_our_histories(fake_engine):
     tr = ref_trainer.Trainer(copy.deepcopy(ck), ref_cfg)
     priorities, total_loss, value_loss, reward_loss, policy_loss = tr.update_weights(batch)
     assert numpy.isfinite(total_loss)
+
+
+class _Storage:
+    """Plain-object stand-in for shared_storage.SharedStorage (get_info / set_info, shared_storage.py:23-40)."""
+
+    def __init__(self, weights, training_steps_per_poll=1):
+        self.d = dict(weights=weights, training_step=0, terminate=False, num_played_steps=0, num_played_games=0)
+        self.polls = 0
+        self.rate = training_steps_per_poll
+
+    def get_info(self, keys):
+        if keys == "training_step":          # pretend a trainer is making progress while we play
+            self.polls += 1
+            self.d["training_step"] += self.rate
+        return self.d[keys] if isinstance(keys, str) else {k: self.d[k] for k in keys}
+
+    def set_info(self, keys, values=None):
+        if isinstance(keys, dict):
+            self.d.update(keys)
+        else:
+            self.d[keys] = values
+
+
+class _Buffer:
+    def __init__(self):
+        self.games = []
+
+    def save_game(self, game_history, shared_storage=None):
+        self.games.append(game_history)
+        if shared_storage is not None:
+            shared_storage.set_info("num_played_games", len(self.games))
+            shared_storage.set_info("num_played_steps", sum(len(g.root_values) for g in self.games))
+
+
+@pytest.mark.parametrize("parallel", [1, 3])
+def test_continuous_self_play_loop(parallel, fake_engine):
+    """The actor loop of self_play.py:31-108 with plain objects in place of the Ray handles: refreshes the
+    weights, plays until training_steps is reached, pushes every finished game to the buffer."""
+    worker, cfg = _worker("tictactoe", 0, num_parallel_games=parallel, num_simulations=5, training_steps=12, ratio=None)
+    storage = _Storage(weights_for("tictactoe", netspec_from_config(cfg)), training_steps_per_poll=2)
+    buf = _Buffer()
+    worker.continuous_self_play(storage, buf)
+    assert buf.games and all(len(g.child_visits) == len(g.action_history) - 1 for g in buf.games)
+    assert storage.d["num_played_games"] == len(buf.games)
+    assert storage.d["training_step"] >= cfg.training_steps
+
+
+def test_continuous_self_play_test_mode_reports_metrics(fake_engine):
+    """test_mode: greedy play, metrics written to the shared storage (self_play.py:54-90)."""
+    worker, cfg = _worker("tictactoe", 0, num_simulations=5, training_steps=6, opponent="random", muzero_player=0)
+    storage = _Storage(weights_for("tictactoe", netspec_from_config(cfg)), training_steps_per_poll=3)
+    worker.continuous_self_play(storage, _Buffer(), test_mode=True)
+    for key in ("episode_length", "total_reward", "mean_value", "muzero_reward", "opponent_reward"):
+        assert key in storage.d
+    assert 5 <= storage.d["episode_length"] <= 9
