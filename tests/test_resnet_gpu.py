@@ -16,7 +16,7 @@ pytestmark = pytest.mark.gpu
 # mantissa, fp32 accumulation): the tcgen05 towers where the shape allows (Connect4); activations are
 # rounded to 11 significant bits after each of the 13 stacked convs -> looser bound.
 TOLS = {"fp32": dict(rtol=2e-4, atol=2e-5), "tf32": dict(rtol=2e-2, atol=2e-2)}
-VALUE_TOL = {"fp32": 2e-4, "tf32": 1e-2}
+VALUE_TOL = {"fp32": 2e-4, "tf32": 3e-2}
 
 
 @pytest.fixture(params=["fp32", "tf32"])
