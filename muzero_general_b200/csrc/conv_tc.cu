@@ -26,6 +26,8 @@
 // 4..11 = epilogue (TMEM lane quarter = warp % 4, accumulator column half = (warp - 4) / 4); the
 // epilogue prefetches its residual / action terms before it waits for the accumulator.
 #include <cuda_fp16.h>
+#include <stdio.h>
+#include <stdlib.h>
 
 #include "pipeline.h"
 #include "conv_tc.h"
@@ -356,22 +358,40 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tower_tc_kernel(const __grid
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2 * kAccCols) : "memory");
 }
 
+static int tower_ctas_per_sm() {
+    static int per_sm = 0;
+    if (per_sm == 0) {
+        int occ = 1;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, conv_tower_tc_kernel, kThreads, Smem::total) != cudaSuccess || occ < 1) occ = 1;
+        if (getenv("MZ_TC_VERBOSE")) fprintf(stderr, "[conv_tower_tc] occupancy %d CTAs/SM, %d B shared per CTA\n", occ, Smem::total);
+        const char* e = getenv("MZ_TC_CTAS");           // A/B switch: force one CTA per SM
+        if (e && atoi(e) >= 1 && atoi(e) < occ) occ = atoi(e);
+        per_sm = occ > 2 ? 2 : occ;
+    }
+    return per_sm;
+}
+
 cudaError_t launch_conv_tower_tc(const TowerArgs& a, int sm_count, cudaStream_t stream) {
     static bool attr_set = false;
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(conv_tower_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem::total);
         if (e != cudaSuccess) return e;
+        // all of the SM's unified L1/shared array as shared memory, so two CTAs fit side by side
+        e = cudaFuncSetAttribute(conv_tower_tc_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        if (e != cudaSuccess) return e;
         attr_set = true;
     }
     if (a.n_layers < 1 || a.n_layers > kTowerMaxLayers) return cudaErrorInvalidValue;
     const int n_tiles = (a.n + kBoards - 1) / kBoards;
-    const int grid = n_tiles < sm_count ? n_tiles : sm_count;
+    // two co-resident CTAs per SM (fp16 operands leave room): their MMA streams interleave on the tensor core
+    const int slots = sm_count * tower_ctas_per_sm();
+    const int grid = n_tiles < slots ? n_tiles : slots;
     if (a.n_layers > 1 && (n_tiles + grid - 1) / grid > kTowerMaxTiles) return cudaErrorInvalidConfiguration;
     conv_tower_tc_kernel<<<grid, kThreads, Smem::total, stream>>>(a);
     return cudaGetLastError();
 }
 
-int conv_tc_max_boards_fused(int sm_count) { return sm_count * kTowerMaxTiles * kBoards; }
+int conv_tc_max_boards_fused(int sm_count) { return sm_count * kTowerMaxTiles * kBoards; }   // conservative: one CTA per SM
 
 bool conv_tc_supported(int C, int H, int W) { return C == kC && H >= 1 && H <= 6 && W >= 1 && W <= 7; }
 int conv_tc_board_elems() { return kBoardHalves / 2; }      // float slots per board (the buffers hold fp16)

@@ -261,13 +261,28 @@ __global__ void __launch_bounds__(kHeadThreads) heads_kernel(const __grid_consta
         group_bar(group);
 
         if (a.rescaled || a.pool_hidden || a.state_p64c4) {
-            // threads own channels: min / max over the positions, then (x - min) / scale   (models.py:530-553)
-            for (int c = t; c < C; c += kHeadGroup) {
+            // (x - min) / scale per channel over the positions (models.py:530-553).  Two threads per channel when
+            // the group is wide enough: each scans half of the positions, partial extrema meet in shared memory.
+            const int parts = (2 * C <= kHeadGroup) ? 2 : 1;
+            for (int cb = 0; cb < C; cb += kHeadGroup) {               // one pass unless C > 128
+                const int c = (parts == 2) ? t % C : cb + t;
+                const int part = (parts == 2) ? t / C : 0;
+                const bool active = (parts == 2) ? (t < 2 * C) : (c < C);
+                const int p0 = active ? (part * HW) / parts : 0, p1 = active ? ((part + 1) * HW) / parts : 0;
                 float lo = INFINITY, hi = -INFINITY;
-                for (int p = 0; p < HW; ++p) { const float v = s_x[p * CP + c]; lo = fminf(lo, v); hi = fmaxf(hi, v); }
+                for (int p = p0; p < p1; ++p) { const float v = s_x[p * CP + c]; lo = fminf(lo, v); hi = fmaxf(hi, v); }
+                if (parts == 2) {
+                    if (active) { s_act[2 * t] = lo; s_act[2 * t + 1] = hi; }
+                    group_bar(group);
+                    if (active) {
+                        const int other = (part ? t - C : t + C);
+                        lo = fminf(lo, s_act[2 * other]); hi = fmaxf(hi, s_act[2 * other + 1]);
+                    }
+                    group_bar(group);                     // s_act is reused by the heads below
+                }
                 float sc = __fsub_rn(hi, lo);
                 if (sc < 1e-5f) sc = __fadd_rn(sc, 1e-5f);
-                for (int p = 0; p < HW; ++p) {
+                for (int p = p0; p < p1; ++p) {
                     const float v = __fdiv_rn(__fsub_rn(s_x[p * CP + c], lo), sc);
                     if (a.rescaled) a.rescaled[(size_t)g * C * HW + c * HW + p] = v;
                     if (a.p64c4) {
@@ -822,6 +837,7 @@ struct Runner {
         }
         a.logits[0] = l0; a.logits[1] = l1; a.scalar[0] = s0; a.scalar[1] = s1;
         a.rescaled = rescaled; a.pool_hidden = pool_hidden; a.pool_stride = pool_stride; a.out_slot = out_slot;
+        if (a.C <= kHeadGroup / 2) maxw = std::max(maxw, a.C);      // room for the rescale's partial extrema
         a.smem_floats = (maxw + 3) & ~3;
         // blob slice covering the heads of this launch
         int lo = 1 << 30, hi = 0;
