@@ -87,6 +87,67 @@ MZ_DEVINL float* mlp_forward(const MlpDesc& d, const float* blob, const float* x
     return const_cast<float*>(cur);
 }
 
+// K independent MLPs of equal depth evaluated side by side: one instruction stream with K accumulators per
+// lane, so the three heads of a recurrent inference (reward on the raw state, policy and value on the rescaled
+// state; models.py:157-159,128-131) overlap their shared-memory latencies instead of running back to back.
+// Every accumulator sees exactly the operations of linear_layer, in the same order: results are bit-identical.
+// bufs: K x 2 ping-pong vectors.  out[k] receives the pointer holding MLP k's output.
+template <int G, int K>
+MZ_DEVINL void mlp_forward_multi(const MlpDesc* const (&d)[K], const float* blob, const float* const (&x)[K],
+                                 float* const (&bufs)[K][2], float* (&out)[K]) {
+    const int lane = LaneGroup<G>::lane();
+    const float* cur[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) cur[k] = x[k];
+    const int n_layers = d[0]->n;
+    for (int l = 0; l < n_layers; ++l) {
+        const bool last = (l == n_layers - 1);
+        int in4[K], outk[K], out4[K], max_in4 = 0, max_out4 = 0;
+        const float4* W4[K];
+        const float* bias[K];
+        float* y[K];
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            in4[k] = (d[k]->in_dense[l] + 3) >> 2;
+            outk[k] = d[k]->out[l];
+            out4[k] = (outk[k] + 3) & ~3;
+            W4[k] = reinterpret_cast<const float4*>(blob + d[k]->w_off[l]);
+            bias[k] = blob + d[k]->b_off[l];
+            y[k] = (l & 1) ? bufs[k][1] : bufs[k][0];
+            max_in4 = max(max_in4, in4[k]);
+            max_out4 = max(max_out4, out4[k]);
+        }
+        for (int o = lane; o < max_out4; o += G) {
+            float acc[K];
+            bool on[K];
+#pragma unroll
+            for (int k = 0; k < K; ++k) { on[k] = o < outk[k]; acc[k] = on[k] ? bias[k][o] : 0.0f; }
+#pragma unroll 2
+            for (int i = 0; i < max_in4; ++i) {
+#pragma unroll
+                for (int k = 0; k < K; ++k) {
+                    if (on[k] && i < in4[k]) {
+                        const float4 xv = reinterpret_cast<const float4*>(cur[k])[i];
+                        const float4 wv = W4[k][i * outk[k] + o];
+                        acc[k] = fmaf(xv.x, wv.x, acc[k]);
+                        acc[k] = fmaf(xv.y, wv.y, acc[k]);
+                        acc[k] = fmaf(xv.z, wv.z, acc[k]);
+                        acc[k] = fmaf(xv.w, wv.w, acc[k]);
+                    }
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < K; ++k)
+                if (o < out4[k]) y[k][o] = on[k] ? (last ? acc[k] : elu1(acc[k])) : 0.0f;
+        }
+        LaneGroup<G>::sync();
+#pragma unroll
+        for (int k = 0; k < K; ++k) cur[k] = y[k];
+    }
+#pragma unroll
+    for (int k = 0; k < K; ++k) out[k] = const_cast<float*>(cur[k]);
+}
+
 // copies n floats from global memory into a zero-padded shared vector
 template <int G>
 MZ_DEVINL void load_vector(const float* __restrict__ src, float* dst, int n) {
@@ -129,6 +190,34 @@ MZ_DEVINL float support_to_scalar_group(const float* logits, int S) {
     den = group_sum_f32<G>(den);
     num = group_sum_f32<G>(num);
     return inverse_value_transform(__fdiv_rn(num, den));
+}
+
+// two support_to_scalar evaluations with interleaved reductions (value and reward heads)
+template <int G>
+MZ_DEVINL void support_to_scalar_group2(const float* la, const float* lb, int S, float& ra, float& rb) {
+    const int lane = LaneGroup<G>::lane();
+    const int F = 2 * S + 1;
+    const unsigned m = LaneGroup<G>::mask();
+    float ma = -INFINITY, mb = -INFINITY;
+    for (int i = lane; i < F; i += G) { ma = fmaxf(ma, la[i]); mb = fmaxf(mb, lb[i]); }
+#pragma unroll
+    for (int off = G >> 1; off > 0; off >>= 1) {
+        ma = fmaxf(ma, __shfl_xor_sync(m, ma, off, G));
+        mb = fmaxf(mb, __shfl_xor_sync(m, mb, off, G));
+    }
+    float da = 0.0f, na = 0.0f, db = 0.0f, nb = 0.0f;
+    for (int i = lane; i < F; i += G) {
+        const float ea = expf(la[i] - ma), eb = expf(lb[i] - mb);
+        da += ea; na = fmaf((float)(i - S), ea, na);
+        db += eb; nb = fmaf((float)(i - S), eb, nb);
+    }
+#pragma unroll
+    for (int off = G >> 1; off > 0; off >>= 1) {
+        da += __shfl_xor_sync(m, da, off, G); db += __shfl_xor_sync(m, db, off, G);
+        na += __shfl_xor_sync(m, na, off, G); nb += __shfl_xor_sync(m, nb, off, G);
+    }
+    ra = inverse_value_transform(__fdiv_rn(na, da));
+    rb = inverse_value_transform(__fdiv_rn(nb, db));
 }
 
 }  // namespace mz

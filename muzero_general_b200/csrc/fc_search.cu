@@ -33,7 +33,7 @@ __host__ __device__ inline GameSmem game_smem_layout(int N, int A, int E, int ma
     L.path = take((N + 2) * 4);
     L.path_reward = take((N + 2) * 4);
     L.hidden = take((keep_hidden ? (N + 1) * Epad : 0) * 4);
-    L.act = take(3 * maxw * 4);
+    L.act = take(9 * maxw * 4);        // s0 s1 s2 + three heads x (ping, pong)
     off += 16;          // odd multiple of 16 B between games: spreads games over banks
     L.bytes = off;
     return L;
@@ -79,6 +79,9 @@ __global__ void __launch_bounds__(kFcMaxThreads) fc_search_kernel(const __grid_c
     float* s0 = s_act;
     float* s1 = s_act + maxw;
     float* s2 = s_act + 2 * maxw;
+    float* const hb[3][2] = {{s_act + 3 * maxw, s_act + 4 * maxw}, {s_act + 5 * maxw, s_act + 6 * maxw},
+                             {s_act + 7 * maxw, s_act + 8 * maxw}};
+    const bool fused_heads = (a.net.rew.n == a.net.pol.n) && (a.net.pol.n == a.net.val.n);
 
     for (int g = blockIdx.x * groups_per_cta + gi; g < a.n_games; g += gridDim.x * groups_per_cta) {
         const int64_t game_id = a.game_id ? a.game_id[g] : (int64_t)g;
@@ -131,18 +134,30 @@ __global__ void __launch_bounds__(kFcMaxThreads) fc_search_kernel(const __grid_c
                 // dynamics (models.py:147-170)
                 const float* h = s_hidden + (size_t)leaf.parent_exp * Epad;
                 float* raw = mlp_forward<G>(a.net.dyn, s_blob, h, s0, s1, s2, leaf.action);
-                // reward head reads the un-normalised next state
-                float* rl = mlp_forward<G>(a.net.rew, s_blob, raw, s0, s1, nullptr);
-                reward = support_to_scalar_group<G>(rl, S);
-                LaneGroup<G>::sync();
                 float* hn = s_hidden + (size_t)t.n_expanded * Epad;
-                rescale_unit_range<G>(raw, hn, E);
-                float* pol = mlp_forward<G>(a.net.pol, s_blob, hn, s0, s1, s2);
-                logit = (lane < A) ? pol[lane] : 0.0f;
-                LaneGroup<G>::sync();
-                float* vl = mlp_forward<G>(a.net.val, s_blob, hn, s0, s1, s2);
-                value = support_to_scalar_group<G>(vl, S);
-                LaneGroup<G>::sync();
+                if (fused_heads) {
+                    // rescale first, then reward (raw state), policy and value (rescaled state) side by side
+                    rescale_unit_range<G>(raw, hn, E);
+                    const MlpDesc* const ds[3] = {&a.net.rew, &a.net.pol, &a.net.val};
+                    const float* const xs[3] = {raw, hn, hn};
+                    float* outs[3];
+                    mlp_forward_multi<G, 3>(ds, s_blob, xs, hb, outs);
+                    logit = (lane < A) ? outs[1][lane] : 0.0f;
+                    support_to_scalar_group2<G>(outs[2], outs[0], S, value, reward);
+                    LaneGroup<G>::sync();
+                } else {
+                    // reward head reads the un-normalised next state
+                    float* rl = mlp_forward<G>(a.net.rew, s_blob, raw, s0, s1, nullptr);
+                    reward = support_to_scalar_group<G>(rl, S);
+                    LaneGroup<G>::sync();
+                    rescale_unit_range<G>(raw, hn, E);
+                    float* pol = mlp_forward<G>(a.net.pol, s_blob, hn, s0, s1, s2);
+                    logit = (lane < A) ? pol[lane] : 0.0f;
+                    LaneGroup<G>::sync();
+                    float* vl = mlp_forward<G>(a.net.val, s_blob, hn, s0, s1, s2);
+                    value = support_to_scalar_group<G>(vl, S);
+                    LaneGroup<G>::sync();
+                }
                 prior = group_softmax_masked<G>(logit, lane < A);
             }
             if (a.trace.depth) {
