@@ -342,7 +342,9 @@ def main():
         out = {
             "metric": "self-play env-steps/sec", "value": value, "unit": "env-steps/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * wall / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 nets + f64 tree statistics",
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": ("f32 nets + f64 tree statistics" if game != "connect4" or os.environ.get("MZ_NO_TC") == "1" else
+                      "fp16 operands / f32 accumulate (tensor-core towers), f32 heads, f64 tree statistics"),
             "data": "synthetic", "config": config,
             "sims_per_sec": value * N,
             "kernel_ms_per_step": kern_ms / args.steps,

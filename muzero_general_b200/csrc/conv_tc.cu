@@ -3,8 +3,8 @@
 // Used for the residual towers of board-sized states (H <= 6, W <= 7, C = 64: Connect4,
 // models.py:213-229 inside representation / dynamics / prediction).  Per CTA:
 //
-//   weights  [tap 9][C/8][cout C][8] fp16, BN folded       resident in shared memory (bulk copy)
-//   A tile   two boards = 128 rows of the "P64C8" layout   2-stage ring, cp.async.bulk (TMA unit)
+//   weights  [tap 9][cout C][cin C] fp16, BN folded, 128B-swizzled   resident in shared memory (bulk copy)
+//   A tile   two boards = 128 rows of the "P64S" layout    2-stage ring, one 8 KB cp.async.bulk per board
 //   D        128 x 64 fp32 accumulator                     TMEM, double buffered
 //
 // Operands are fp16 (10-bit mantissa - the same as tf32 - with fp32 accumulation): one tcgen05.mma
@@ -12,15 +12,14 @@
 // formulation needs, and every activation / weight byte moved through L2 and shared memory is halved.
 // Measured motivation: profiles/r01_conv_tc_bottleneck.md (the M128 x N64 MMA is operand-fetch bound).
 //
-// P64C8 activation layout (HBM and shared): a board is 64 positions p = (y+1)*8 + x (row 0, rows
-// H+1.. and columns W..7 are zero padding) and channels are grouped by eight:
-// act[board][c/8][p][c%8] (fp16).  With the UMMA K-major SWIZZLE_NONE canonical layout and SBO = 128 B a
-// channel-group plane is a dense array of 16-byte rows, so the operand of filter tap (dy,dx) is the
-// SAME shared-memory tile with its start address moved by (dy*8+dx) rows: the implicit GEMM needs
-// no im2col copy and one bulk load per (board, channel group).  Epilogue warps read the accumulator with
-// tcgen05.ld, add the folded-BN bias, the optional residual and the optional action-plane term
-// (models.py:557-572 folded into a per-position table), apply ReLU, zero the padding positions,
-// convert to fp16 (round to nearest, saturating) and store P64C8 again.
+// P64S activation layout (HBM and shared): a board is 64 positions p = (y+1)*8 + x (row 0, rows H+1.. and columns
+// W..7 are zero padding), every position one 128-byte row of 64 fp16 channels whose eight 16-byte chunks are stored
+// XOR-ed with p % 8 - i.e. the boards sit in HBM already in the UMMA K-major SWIZZLE_128B shared-memory image, so a
+// plain 1-D bulk copy lands them ready for the tensor core.  Filter tap (dy,dx) is the SAME shared-memory tile with
+// its start address moved by (dy*8+dx) rows (descriptor base_offset = row phase): the implicit GEMM needs no im2col
+// copy.  Epilogue warps read the accumulator with tcgen05.ld, add the folded-BN bias, the optional residual and the
+// optional action-plane term (models.py:557-572 folded into a per-position table), apply ReLU, zero the padding
+// positions, convert to fp16 (round to nearest, saturating) and store P64S again.
 //
 // Warp roles (384 threads): 0 = bulk-copy producer, 1 = MMA issuer, 2 = TMEM allocator,
 // 4..11 = epilogue (TMEM lane quarter = warp % 4, accumulator column half = (warp - 4) / 4); the
@@ -39,14 +38,14 @@ namespace {
 constexpr int kC = 64;                 // channels in = out
 constexpr int kPos = 64;               // positions per board (8 x 8 padded grid)
 constexpr int kBoards = 2;             // boards per tile -> M = 128
-constexpr int kHalo = 10;              // zero rows above / below the tile (|shift| <= 9)
-constexpr int kRows = kBoards * kPos + 2 * kHalo;      // 148 rows per plane
-constexpr int kPlaneBytes = kRows * 16;                // LBO of A
-constexpr int kPlanes = kC / 8;                        // 8 channel groups of 8 fp16
-constexpr int kStageBytes = kPlanes * kPlaneBytes;     // 18944
+constexpr int kHalo = 16;              // zero rows above / below the tile (|shift| <= 9; multiple of 8 keeps the swizzle phase)
+constexpr int kRows = kBoards * kPos + 2 * kHalo;      // 160 rows
+constexpr int kRowBytes = kC * 2;                      // 128 B: one position, 64 fp16 channels = one 128B-swizzle row
+constexpr int kPlanes = kC / 8;                        // 8 sixteen-byte chunks per row
+constexpr int kStageBytes = kRows * kRowBytes;         // 20480
 constexpr int kStages = 2;
-constexpr int kWBytes = 9 * kPlanes * kC * 16;         // 73728
-constexpr int kTapBytes = kPlanes * kC * 16;           // 8192
+constexpr int kTapBytes = kC * kRowBytes;               // 8192: [cout 64][128 B]
+constexpr int kWBytes = 9 * kTapBytes;                 // 73728
 constexpr int kBoardHalves = kC * kPos;                // 4096 fp16 per board
 constexpr int kAccCols = 64;
 constexpr int kThreads = 384;             // 4 control warps + 8 epilogue warps
@@ -89,18 +88,20 @@ MZ_DEVINL void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t 
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
+// exactly one lane of a converged warp (ptxas then knows the tcgen05 operands come from a single thread and
+// moves them to uniform registers without a broadcast loop)
+MZ_DEVINL bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P;\n\t"
+        "elect.sync _|P, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, P;\n\t"
+        "}" : "=r"(pred));
+    return pred != 0;
+}
 MZ_DEVINL void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 MZ_DEVINL void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-// K-major, SWIZZLE_NONE shared-memory descriptor (cute::UMMA::SmemDescriptor, version 1)
-MZ_DEVINL uint64_t umma_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-    uint64_t d = 0;
-    d |= (uint64_t)((addr >> 4) & 0x3FFF);
-    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
-    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
-    d |= (uint64_t)1 << 46;
-    return d;
-}
 
 // kind::f16 with fp16 operands (format 0), fp32 accumulate, A and B K-major, M = 128, N = 64
 // (cute::UMMA::InstrDescriptor)
@@ -113,6 +114,23 @@ MZ_DEVINL void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint3
         "setp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
         "}" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(kIdesc), "r"(accumulate) : "memory");
+}
+// descriptor words shared by every A / B descriptor of this kernel (K-major SWIZZLE_128B, SBO = 1024 B, version 1);
+// the hardware applies the 128B swizzle on absolute shared-memory address bits, so row-shifted tap windows need
+// no base_offset (checked: tests/test_conv_gpu.py is exact with base_offset = 0 and wrong with the row phase)
+constexpr uint32_t kDescLoFlags = 1u << 16;                                           // LBO field = 1 (unused)
+constexpr uint32_t kDescHi = ((1024u >> 4) & 0x3FFFu) | (1u << 14) | (2u << 29);      // SBO | version | SWIZZLE_128B
+
+MZ_DEVINL void umma_f16_words(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        ".reg .b64 da, db;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "mov.b64 da, {%1, %5};\n\t"
+        "mov.b64 db, {%2, %5};\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n\t"
+        "}" ::"r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(kIdesc), "r"(accumulate), "r"(kDescHi) : "memory");
 }
 MZ_DEVINL void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
@@ -159,11 +177,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tower_tc_kernel(const __grid
     const int L = a.n_layers;
 
     // ---- one-time setup
-    // zero the halo rows of every plane (the board rows are always overwritten by the bulk copies)
-    for (int i = threadIdx.x; i < kStages * kPlanes * 2 * kHalo; i += kThreads) {
-        const int r = i % (2 * kHalo), pl = i / (2 * kHalo);
+    // zero the halo rows (the board rows are always overwritten by the bulk copies)
+    for (int i = threadIdx.x; i < kStages * 2 * kHalo * (kRowBytes / 16); i += kThreads) {
+        const int chunk = i % (kRowBytes / 16), r = (i / (kRowBytes / 16)) % (2 * kHalo), st = i / ((kRowBytes / 16) * 2 * kHalo);
         const int row = r < kHalo ? r : kRows - 2 * kHalo + r;
-        reinterpret_cast<uint4*>(smem + Smem::a + pl * kPlaneBytes)[row] = make_uint4(0, 0, 0, 0);
+        reinterpret_cast<uint4*>(smem + Smem::a + st * kStageBytes + row * kRowBytes)[chunk] = make_uint4(0, 0, 0, 0);
     }
     for (int i = threadIdx.x; i < L * kC; i += kThreads) {
         const float* b = a.layer[i / kC].bias;
@@ -219,13 +237,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tower_tc_kernel(const __grid
                 __syncwarp();
                 const int nb = min(kBoards, a.n - tile * kBoards);
                 if (a.debug_skip & 2) { if (lane == 0) mbar_arrive(bar_a_full(s)); __syncwarp(); continue; }
-                if (lane == 0) mbar_expect_tx(bar_a_full(s), (uint32_t)nb * kPlanes * kPos * 16);
+                if (lane == 0) mbar_expect_tx(bar_a_full(s), (uint32_t)nb * kPos * kRowBytes);
                 __syncwarp();
-                for (int i = lane; i < nb * kPlanes; i += 32) {          // (board, channel group) pairs
-                    const int b = i / kPlanes, j = i % kPlanes;
-                    const __half* src = tower_board(a, in_buf, tile * kBoards + b);
-                    bulk_g2s(s_a + s * kStageBytes + j * kPlaneBytes + (kHalo + b * kPos) * 16,
-                             src + (size_t)j * kPos * 8, kPos * 16, bar_a_full(s));
+                if (lane < nb) {                                           // one 8 KB bulk copy per board
+                    const __half* src = tower_board(a, in_buf, tile * kBoards + lane);
+                    bulk_g2s(s_a + s * kStageBytes + (kHalo + lane * kPos) * kRowBytes, src, kPos * kRowBytes, bar_a_full(s));
                 }
             }
         }
@@ -239,20 +255,25 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tower_tc_kernel(const __grid
                 mbar_wait(bar_acc_empty(s), ph ^ 1);
                 mbar_wait(bar_a_full(s), ph);
                 tc_fence_after();
-                if (lane == 0) {
+                if (elect_one()) {
                     const uint32_t d = tmem_base + (uint32_t)(s * kAccCols);
+                    // Descriptors differ only in the 14-bit start-address field: build the constant words once and
+                    // derive every MMA's descriptor with one add (the single issuing thread is latency-bound, so the
+                    // instruction count per MMA is what sets the tensor-pipe duty cycle).
+                    const uint32_t a16 = (s_a + s * kStageBytes + kHalo * kRowBytes) >> 4;     // tile row 0, in 16-byte units
+                    const uint32_t w16 = s_w >> 4;
                     uint32_t acc = 0;
-#pragma unroll 1
-                    for (int tap = 0; tap < ((a.debug_skip & 1) ? 0 : 9); ++tap) {
-                        if (k == 0) { mbar_wait(bar_w_full(tap), (uint32_t)(l & 1)); tc_fence_after(); }
-                        const int shift = (tap / 3 - 1) * 8 + (tap % 3 - 1);
-                        const uint32_t a0 = s_a + s * kStageBytes + (kHalo + shift) * 16;
-                        const uint32_t b0 = s_w + tap * kTapBytes;
 #pragma unroll
-                        for (int ks = 0; ks < kC / 16; ++ks) {
-                            const uint64_t ad = umma_desc(a0 + 2 * ks * kPlaneBytes, kPlaneBytes, 128);
-                            const uint64_t bd = umma_desc(b0 + 2 * ks * (kC * 16), kC * 16, 128);
-                            umma_f16(d, ad, bd, acc);
+                    for (int tap = 0; tap < 9; ++tap) {
+                        if (a.debug_skip & 1) break;
+                        if (k == 0) { mbar_wait(bar_w_full(tap), (uint32_t)(l & 1)); tc_fence_after(); }
+                        constexpr int kRow16 = kRowBytes / 16;                       // 8 sixteen-byte units per row
+                        const int shift = (tap / 3 - 1) * 8 + (tap % 3 - 1);         // compile-time after unrolling
+#pragma unroll
+                        for (int ks = 0; ks < kC / 16; ++ks) {                       // K = 16 channels = 32 bytes of the row
+                            const uint32_t alo = ((a16 + (uint32_t)(shift * kRow16 + ks * 2)) & 0x3FFFu) | kDescLoFlags;
+                            const uint32_t blo = ((w16 + (uint32_t)(tap * (kTapBytes / 16) + ks * 2)) & 0x3FFFu) | kDescLoFlags;
+                            umma_f16_words(d, alo, blo, acc);
                             acc = 1;
                         }
                         if (k == my_tiles - 1) umma_commit(bar_w_empty(tap));   // slot reusable by the next layer
@@ -272,8 +293,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tower_tc_kernel(const __grid
         const int b = row / kPos, p = row % kPos;
         const int y = p / 8 - 1, x = p % 8;
         const bool inside = (y >= 0 && y < a.H && x < a.W);
-        constexpr int kJ = kPlanes / 2;               // channel groups (of 8) handled by this warp: 32 channels
-        const size_t my_off = (size_t)p * 8 + (size_t)(half * kJ) * kPos * 8;      // in fp16 elements
+        constexpr int kJ = kPlanes / 2;               // 16-byte chunks (8 channels) handled by this warp: 32 channels
+        const size_t row_off = (size_t)p * kC;        // this position's 128-byte row, in fp16 elements
+        const int sw = p & 7;                         // chunk c of the row is stored at chunk c ^ sw
         int it = 0;
         for (int l = 0; l < L; ++l) {
             const TowerLayer& ly = a.layer[l];
@@ -291,9 +313,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tower_tc_kernel(const __grid
                 for (int j = 0; j < kJ; ++j) res[j] = make_uint4(0, 0, 0, 0);
                 if (live) {
                     if (ly.res_buf >= 0 && !(a.debug_skip & 8)) {
-                        const __half* rp = tower_board(a, ly.res_buf, g) + my_off;
+                        const __half* rp = tower_board(a, ly.res_buf, g) + row_off;
 #pragma unroll
-                        for (int j = 0; j < kJ; ++j) res[j] = *reinterpret_cast<const uint4*>(rp + (size_t)j * kPos * 8);
+                        for (int j = 0; j < kJ; ++j) res[j] = *reinterpret_cast<const uint4*>(rp + (((half * kJ + j) ^ sw) << 3));
                     }
                     if (ly.action_table) act_scale = __fdiv_rn((float)a.action[g], (float)a.A);
                 }
@@ -315,7 +337,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tower_tc_kernel(const __grid
                 __syncwarp();
                 if (lane == 0) mbar_arrive(bar_acc_empty(s));        // accumulator half read: may be overwritten
                 if (g < a.n && !(a.debug_skip & 4)) {
-                    __half* dst = reinterpret_cast<__half*>(a.buf[ly.out_buf]) + (size_t)g * kBoardHalves + my_off;
+                    __half* dst = reinterpret_cast<__half*>(a.buf[ly.out_buf]) + (size_t)g * kBoardHalves + row_off;
                     const float* atab = ly.action_table ? ly.action_table + (size_t)p * kC + half * 32 : nullptr;
 #pragma unroll
                     for (int j = 0; j < kJ; ++j) {
@@ -339,7 +361,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tower_tc_kernel(const __grid
                             }
                             o = make_uint4(pack_f16x2(r[0], r[1]), pack_f16x2(r[2], r[3]), pack_f16x2(r[4], r[5]), pack_f16x2(r[6], r[7]));
                         }
-                        *reinterpret_cast<uint4*>(dst + (size_t)j * kPos * 8) = o;
+                        *reinterpret_cast<uint4*>(dst + (((half * kJ + j) ^ sw) << 3)) = o;
                     }
                 }
                 if (l + 1 < L) {

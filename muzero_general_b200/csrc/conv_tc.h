@@ -11,7 +11,7 @@ constexpr int kTowerBuffers = 5;
 
 // One conv3x3 (+bias, +residual, +action term, +ReLU) of a tower; buffers are indices into TowerArgs::buf.
 struct TowerLayer {
-    const float* w;               // fp16 image [9][8][64][8] (typed float*: 2 halves per slot), BN scale folded
+    const float* w;               // fp16 image [9][cout 64][cin 64], 128B-swizzled (typed float*), BN scale folded
     const float* bias;            // [64] folded BN shift, or nullptr
     const float* action_table;    // dynamics stem: add (action/A) * table[p][cout]; nullptr otherwise
     int in_buf, out_buf, res_buf; // res_buf = -1: no residual
@@ -25,7 +25,7 @@ struct TowerLayer {
 struct TowerArgs {
     int n_layers;
     TowerLayer layer[kTowerMaxLayers];
-    float* buf[kTowerBuffers];    // activation buffers, fp16 [n][8][64][8] (typed float*); buf[0] may be a gathered pool
+    float* buf[kTowerBuffers];    // activation buffers, fp16 P64S [n][64 pos][64 ch swizzled] (typed float*); buf[0] may be a gathered pool
     const int32_t* gather_parent; // buf[0] of game g = buf[0] + (g*pool_stride + gather_parent[g]) boards
     int pool_stride;
     const int32_t* action;        // [n] for layers with an action_table

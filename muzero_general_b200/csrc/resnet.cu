@@ -44,7 +44,7 @@ struct ConvArgs {
     int pool_stride;
     int n, Cin, Cout, Hin, Win, Ho, Wo, stride, relu, A;
     int boards_per_cta, cin_chunk;
-    int out_p64c4;            // write fp16 act[g][co/8][(y+1)*8+x][co%8] (tensor-core path layout P64C8) instead of NCHW
+    int out_p64c4;            // write the fp16 tensor-core board layout (P64S, conv_tc.cu) instead of NCHW
 };
 
 template <int P, int STRIDE, int MAX_ITEMS>
@@ -152,9 +152,11 @@ __global__ void __launch_bounds__(256) conv3x3_kernel(const __grid_constant__ Co
                 float r = acc[it][c][p] + bias;
                 if (a.residual) r += a.residual[o + p];
                 if (a.relu) r = fmaxf(r, 0.0f);
-                if (a.out_p64c4)
-                    reinterpret_cast<__half*>(a.out)[(((size_t)g * (a.Cout / 8) + co / 8) * 64 + (y + 1) * 8 + seg * P + p) * 8 + (co & 7)] =
+                if (a.out_p64c4) {
+                    const int pos = (y + 1) * 8 + seg * P + p;
+                    reinterpret_cast<__half*>(a.out)[(size_t)g * 4096 + pos * 64 + (((co >> 3) ^ (pos & 7)) << 3) + (co & 7)] =
                         __float2half_rn(r);
+                }
                 else
                     a.out[o + p] = r;
             }
@@ -210,9 +212,11 @@ struct HeadsArgs {
     int warp_floats;           // per-warp scratch: x tile + two activation vectors
 };
 
-// offset (in fp16 elements) of (channel c, dense position p) inside one P64C8 state of 4096 halves
+// offset (in fp16 elements) of (channel c, dense position p) inside one P64S state of 4096 halves: position-major
+// rows of 64 channels, the 8-channel chunks of a row XOR-ed with (padded position % 8) (conv_tc.cu)
 __device__ __forceinline__ int p64c4_index(int c, int p, int W) {
-    return ((c >> 3) * 64 + (p / W + 1) * 8 + (p % W)) * 8 + (c & 7);
+    const int pos = (p / W + 1) * 8 + (p % W);
+    return pos * 64 + ((((c >> 3) ^ (pos & 7))) << 3) + (c & 7);
 }
 
 // Persistent CTAs (one per SM), 512 threads = 4 groups of 128: the head weights of this launch are staged
@@ -248,7 +252,8 @@ __global__ void __launch_bounds__(kHeadThreads) heads_kernel(const __grid_consta
             const uint4* x8 = reinterpret_cast<const uint4*>(reinterpret_cast<const __half*>(a.x) + (size_t)g * 4096);
             for (int i = t; i < (C / 8) * HW; i += kHeadGroup) {
                 const int j = i / HW, p = i % HW;
-                const uint4 v = x8[j * 64 + (p / a.W + 1) * 8 + (p % a.W)];
+                const int pos = (p / a.W + 1) * 8 + (p % a.W);
+                const uint4 v = x8[pos * 8 + (j ^ (pos & 7))];
                 const __half2* h2 = reinterpret_cast<const __half2*>(&v);
                 float* d = s_x + p * CP + 8 * j;
 #pragma unroll
@@ -537,9 +542,9 @@ bool pack_conv(Loader& L, const std::string& conv, const std::string& bn, int ci
     while (blob.size() % 4) blob.push_back(0.0f);           // keep every layer 16-byte aligned
     l.tc_off = l.tc_table_off = -1;
     if (tc) {
-        // fp16 image [tap][cin/8][cout][8] over the first 64 input channels (two halves per float slot of the
-        // blob); an extra (65th) input channel is the constant action plane and becomes a per-position fp32
-        // table (sum of the taps that stay inside the board)
+        // fp16 image [tap][cout][cin] over the first 64 input channels, the 16-byte chunks of a cout row XOR-ed with
+        // cout % 8 (UMMA K-major SWIZZLE_128B; two halves per float slot of the blob); an extra (65th) input channel
+        // is the constant action plane and becomes a per-position fp32 table (sum of the taps that stay inside the board)
         const int C = cout;
         l.tc_off = (long)blob.size();
         blob.resize(blob.size() + (size_t)9 * C * C / 2);
@@ -547,7 +552,7 @@ bool pack_conv(Loader& L, const std::string& conv, const std::string& bn, int ci
         for (int tap = 0; tap < 9; ++tap)
             for (int ci = 0; ci < C; ++ci)
                 for (int co = 0; co < C; ++co)
-                    img[(((size_t)tap * (C / 8) + ci / 8) * C + co) * 8 + (ci % 8)] =
+                    img[((size_t)tap * C + co) * C + ((((ci >> 3) ^ (co & 7))) << 3) + (ci & 7)] =
                         to_f16((float)((double)w->data[((size_t)co * cin + ci) * 9 + tap] * scale[co]));
         if (cin == C + 1) {
             l.tc_table_off = (long)blob.size();
