@@ -196,6 +196,14 @@ int64_t mz_launch_count(const MzHandle* h);
 /* device time of the search kernels of the last mz_search call, ms (CUDA events on the library stream) */
 double mz_last_search_ms(const MzHandle* h);
 
+/* Per-kernel-class device timing for the roofline line of bench.py.  While enabled (process-wide), the step-wise
+ * pipeline runs launch by launch with a CUDA event pair around every kernel instead of replaying its CUDA graph.
+ * mz_kernel_times synchronises and returns the accumulated milliseconds / launch counts since the last call:
+ * [0] tree_step_kernel, [1] conv_tower_tc_kernel, [2] heads_kernel, [3] conv3x3_kernel (CUDA cores), [4] other. */
+#define MZ_KERNEL_CLASSES 5
+int mz_kernel_timing(MzHandle* h, int32_t enable);
+int mz_kernel_times(MzHandle* h, double* ms, int64_t* count);
+
 /* Debug / parity: one conv3x3 (C -> C, stride 1, pad 1; models.py:206-209) with optional bias, residual and
  * ReLU on host NCHW fp32 data, through the CUDA-core kernel (use_tensor_cores = 0) or the tcgen05 implicit
  * GEMM (1; C = 64, H <= 6, W <= 7).  w is [C][C][3][3] as in the reference state_dict. */

@@ -17,6 +17,7 @@
 
 #include "kernels.h"
 #include "pipeline.h"
+#include "ktimer.h"
 
 using namespace mz;
 
@@ -513,7 +514,7 @@ extern "C" int mz_search(MzHandle* h, const MzSearchIO* io) {
         // The step-wise pipeline is 16 small launches per simulation: replay it as a CUDA graph once the
         // same argument set has been seen twice (first call runs eagerly so lazy attribute setup and
         // allocations happen outside capture).  Debug modes (teacher / trace) always run eagerly.
-        const bool graphable = !teacher && !io->trace && getenv("MZ_NO_GRAPH") == nullptr;
+        const bool graphable = !teacher && !io->trace && !kt_enabled() && getenv("MZ_NO_GRAPH") == nullptr;
         uint64_t key = 1469598103934665603ull;
         auto mix = [&](uint64_t v) { key = (key ^ v) * 1099511628211ull; };
         const void* ptrs[] = {call.obs, call.legal_mask, call.to_play, call.noise, call.first_index, call.game_id,
@@ -662,6 +663,23 @@ extern "C" int mz_export_tree(MzHandle* h, int32_t game, MzTreeExport* out) {
 }
 
 // ------------------------------------------------------------------------------------------
+// per-kernel-class device times for bench.py's roofline line (ktimer.h)
+extern "C" int mz_kernel_timing(MzHandle* h, int32_t enable) {
+    if (!h) return fail(nullptr, MZ_EINVAL, "mz_kernel_timing: null handle");
+    kt_enable(enable != 0);
+    return MZ_OK;
+}
+
+extern "C" int mz_kernel_times(MzHandle* h, double* ms, int64_t* count) {
+    if (!h || !ms || !count) return fail(h, MZ_EINVAL, "mz_kernel_times: bad argument");
+    cudaSetDevice(h->device);
+    MZ_CUDA(h, cudaStreamSynchronize(h->stream));
+    for (int i = 0; i < MZ_KERNEL_CLASSES; ++i) { ms[i] = 0.0; count[i] = 0; }
+    cudaError_t e = kt_collect(ms, count);
+    if (e != cudaSuccess) return fail(h, MZ_ECUDA, std::string("mz_kernel_times: ") + cudaGetErrorString(e));
+    return MZ_OK;
+}
+
 // debug: one conv3x3 through either implementation (host NCHW in / out)
 // ------------------------------------------------------------------------------------------
 extern "C" int mz_debug_conv3x3(int device, int32_t n, int32_t C, int32_t H, int32_t W, const float* x, const float* w,

@@ -1,6 +1,7 @@
 // Orchestration of the step-wise search: N+1 tree launches with the batched network call
 // in between (MCTS.run, self_play.py:260-361, for a whole batch of games in lockstep).
 #include "pipeline.h"
+#include "ktimer.h"
 
 namespace mz {
 
@@ -15,7 +16,9 @@ int run_stepwise_search(const MzNetDesc& net, const MzSearchDesc& search, const 
     };
     auto infer = [&](const InferCall& c) -> int {
         if (net.kind == MZ_NET_FC) {
+            kt_begin(KT_OTHER, stream);
             cudaError_t e = launch_fc_inference_pool(fc, d_fc_blob, c, fc_group, sm_count, stream);
+            kt_end(stream);
             if (e != cudaSuccess) return cuda_fail("fc_inference", e);
             *launches += 1;
             return MZ_OK;
@@ -48,7 +51,9 @@ int run_stepwise_search(const MzNetDesc& net, const MzSearchDesc& search, const 
         a.value_stride = 1; a.policy_stride = A; a.policy_is_prior = 0;
     }
     a.sim = 0; a.do_root = 1; a.do_update = 0; a.do_select = N > 0; a.do_final = N == 0;
+    kt_begin(KT_TREE, stream);
     cudaError_t e = launch_tree_step(a, stream);
+    kt_end(stream);
     if (e != cudaSuccess) return cuda_fail("tree_step(root)", e);
     *launches += 1;
 
@@ -69,7 +74,9 @@ int run_stepwise_search(const MzNetDesc& net, const MzSearchDesc& search, const 
             a.value_stride = 1; a.policy_stride = A; a.policy_is_prior = 0;
         }
         a.sim = sim + 1; a.do_root = 0; a.do_update = 1; a.do_select = (sim + 1 < N); a.do_final = (sim + 1 == N);
+        kt_begin(KT_TREE, stream);
         e = launch_tree_step(a, stream);
+        kt_end(stream);
         if (e != cudaSuccess) return cuda_fail("tree_step", e);
         *launches += 1;
     }

@@ -25,6 +25,7 @@
 #include <cuda_fp16.h>
 
 #include "common.cuh"
+#include "ktimer.h"
 #include "conv_tc.h"
 #include "pipeline.h"
 
@@ -219,13 +220,13 @@ __device__ __forceinline__ int p64c4_index(int c, int p, int W) {
     return pos * 64 + ((((c >> 3) ^ (pos & 7))) << 3) + (c & 7);
 }
 
-// Persistent CTAs (one per SM), 512 threads = 4 groups of 128: the head weights of this launch are staged
+// Persistent CTAs (one per SM), 1024 threads = 8 groups of 128: the head weights of this launch are staged
 // in shared memory once per CTA, then every GROUP takes one sample at a time (named barriers, groups never
 // wait for each other).  x is read as 16-byte chunks into a padded [position][channel] tile
 // (conflict-free for the per-channel rescale and the per-position conv1x1); the two heads of a launch
 // (value + policy) run side by side on the two halves of the group.
 constexpr int kHeadGroup = 128;
-constexpr int kHeadThreads = 512;
+constexpr int kHeadThreads = 1024;
 
 __device__ __forceinline__ void group_bar(int group) {
     asm volatile("bar.sync %0, %1;" ::"r"(group + 1), "r"(kHeadGroup) : "memory");
@@ -672,7 +673,9 @@ struct Runner {
         a.n = n; a.H = r->hh; a.W = r->hw; a.A = r->net.action_space;
         static const int dbg = getenv("MZ_TC_DEBUG_SKIP") ? atoi(getenv("MZ_TC_DEBUG_SKIP")) : 0;
         a.debug_skip = dbg;
+        kt_begin(KT_TOWER, stream);
         cudaError_t e = launch_conv_tower_tc(a, r->sm_count, stream);
+        kt_end(stream);
         if (e != cudaSuccess) return fail("conv_tower_tc launch", e);
         *launches += 1;
         return true;
@@ -806,7 +809,9 @@ struct Runner {
                 if (e != cudaSuccess) return fail("conv attr", e);                                              \
                 attr_smem[multi] = smem;                                                                        \
             }                                                                                                   \
+            kt_begin(KT_CONV, stream);                                                                          \
             kern<<<grid, threads, smem, stream>>>(a);                                                           \
+            kt_end(stream);                                                                                     \
         }
         MZ_CONV(8, 1) MZ_CONV(7, 1) MZ_CONV(6, 1) MZ_CONV(4, 1) MZ_CONV(3, 1) MZ_CONV(2, 1) MZ_CONV(1, 1)
         MZ_CONV(8, 2) MZ_CONV(6, 2) MZ_CONV(4, 2) MZ_CONV(3, 2) MZ_CONV(2, 2) MZ_CONV(1, 2) MZ_CONV(7, 2)
@@ -866,7 +871,9 @@ struct Runner {
         }
         int grid = (n + threads / kHeadGroup - 1) / (threads / kHeadGroup);
         if (grid > r->sm_count) grid = r->sm_count;
+        kt_begin(KT_HEADS, stream);
         heads_kernel<<<grid, threads, smem, stream>>>(a);
+        kt_end(stream);
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return fail("heads launch", e);
         *launches += 1;

@@ -141,6 +141,20 @@ class SearchEngine:
     def last_search_ms(self):
         return float(self.lib.mz_last_search_ms(self._h))
 
+    KERNEL_CLASSES = ("tree_step_kernel", "conv_tower_tc_kernel", "heads_kernel", "conv3x3_kernel", "other")
+
+    def kernel_timing(self, enable):
+        """Bracket every kernel of the step-wise pipeline with CUDA events (no graph replay while enabled)."""
+        self._check(self.lib.mz_kernel_timing(self._h, 1 if enable else 0))
+
+    def kernel_times(self):
+        """{kernel class: (total ms, launches)} since the last call (mz_kernel_times)."""
+        import ctypes as C
+        ms = (C.c_double * len(self.KERNEL_CLASSES))()
+        cnt = (C.c_int64 * len(self.KERNEL_CLASSES))()
+        self._check(self.lib.mz_kernel_times(self._h, ms, cnt))
+        return {k: (float(ms[i]), int(cnt[i])) for i, k in enumerate(self.KERNEL_CLASSES)}
+
     @staticmethod
     def _ptr(x, dtype, keep):
         """Pointer of a numpy array (made contiguous, right dtype) or of a CUDA torch tensor."""
