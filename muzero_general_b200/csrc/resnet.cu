@@ -26,6 +26,7 @@
 
 #include "common.cuh"
 #include "ktimer.h"
+#include "small_tower.h"
 #include "conv_tc.h"
 #include "pipeline.h"
 
@@ -412,6 +413,7 @@ struct ResNetDevice {
     float* scratch_state = nullptr;    // [B, 4096 fp16] same state in P64C8 (tensor-core path)
     bool loaded = false;
     bool use_tc = false;               // residual towers on tcgen05 (conv_tc.cu)
+    bool fuse_small = true;            // CUDA-core towers as one fused launch where they fit (small_tower.cu); MZ_NO_FUSE=1: per layer
     int state_elems = 0;               // float slots per stored hidden state (dense C*H*W, or 2048 = 4096 fp16 for P64C8)
 };
 
@@ -446,6 +448,8 @@ ResNetDevice* resnet_create(const MzNetDesc& net, int max_batch, int sm_count, s
     max_elems = std::max(max_elems, (size_t)(net.channels + 1) * r->hh * r->hw);
     const char* no_tc = getenv("MZ_NO_TC");
     r->use_tc = !net.downsample && conv_tc_supported(net.channels, r->hh, r->hw) && !(no_tc && no_tc[0] == '1');
+    const char* no_fuse = getenv("MZ_NO_FUSE");
+    r->fuse_small = !(no_fuse && no_fuse[0] == '1');
     r->state_elems = r->use_tc ? conv_tc_board_elems() : r->C * r->hh * r->hw;
     if (r->use_tc) max_elems = std::max(max_elems, (size_t)conv_tc_board_elems());
     r->ws_elems = max_elems * (size_t)max_batch;
@@ -822,6 +826,33 @@ struct Runner {
         return true;
     }
 
+    // [optional stem conv] + `count` residual blocks as ONE fused CUDA-core launch (small_tower.cu).
+    // Returns 1 = launched, 0 = shape not supported (caller falls back to one launch per conv), -1 = error.
+    int small_tower(const std::vector<ConvLayer>& layers, size_t first, bool stem, size_t count, const float* in, float* out,
+                    int in_channels, int H, int W, const int32_t* gather_parent = nullptr, int pool_stride = 0,
+                    const int32_t* action = nullptr) {
+        const bool off = !r->fuse_small;
+        const size_t nl = (stem ? 1 : 0) + 2 * count;
+        if (off || nl == 0 || nl > (size_t)kSmallTowerMaxLayers) return 0;
+        SmallTowerArgs a{};
+        a.in = in; a.out = out; a.blob = r->d_conv; a.gather_parent = gather_parent; a.action = action; a.pool_stride = pool_stride;
+        a.n = n; a.C = r->C; a.H = H; a.W = W; a.A = r->net.action_space; a.in_channels = in_channels; a.n_layers = (int)nl;
+        for (size_t i = 0; i < nl; ++i) {
+            const ConvLayer& l = layers[first + i];
+            if (l.stride != 1 || l.cout != r->C) return 0;
+            SmallTowerLayer& t = a.layer[i];
+            t.w_off = (int)l.w_off; t.b_off = (int)l.b_off; t.cin = l.cin; t.relu = 1;
+            t.residual = (i >= (stem ? 1u : 0u) && ((i - (stem ? 1 : 0)) & 1)) ? 1 : 0;     // second conv of a block
+        }
+        if (!small_tower_supported(a)) return 0;
+        kt_begin(KT_CONV, stream);
+        cudaError_t e = launch_small_tower(a, r->sm_count, stream);
+        kt_end(stream);
+        if (e != cudaSuccess) { fail("small_tower launch", e); return -1; }
+        *launches += 1;
+        return 1;
+    }
+
     // residual tower: layers[2k], layers[2k+1] are one block; x ends up in `*cur`
     bool blocks(const std::vector<ConvLayer>& layers, size_t first, size_t count, float** cur, float** tmp, float** spare, int H, int W) {
         for (size_t b = 0; b < count; ++b) {
@@ -1042,10 +1073,17 @@ int resnet_inference(ResNetDevice* r, const InferCall& c, cudaStream_t stream, i
                 H = Ho; W = Wo;
                 if (pool == 0 && !R.blocks(d, 12, 3, &cur, &tmp, &spare, H, W)) return MZ_ECUDA;
             }
-            if (!R.blocks(r->rep_trunk, 0, nd.blocks, &cur, &tmp, &spare, H, W)) return MZ_ECUDA;
+            const int fused = R.small_tower(r->rep_trunk, 0, false, nd.blocks, cur, tmp, C, H, W);
+            if (fused < 0) return MZ_ECUDA;
+            if (fused) { float* t = cur; cur = tmp; tmp = t; }
+            else if (!R.blocks(r->rep_trunk, 0, nd.blocks, &cur, &tmp, &spare, H, W)) return MZ_ECUDA;
         } else {
-            if (!R.conv(r->rep_trunk[0], c.in, cur, nullptr, true, H, W)) return MZ_ECUDA;
-            if (!R.blocks(r->rep_trunk, 1, nd.blocks, &cur, &tmp, &spare, H, W)) return MZ_ECUDA;
+            const int fused = R.small_tower(r->rep_trunk, 0, true, nd.blocks, c.in, cur, nd.obs_c, H, W);
+            if (fused < 0) return MZ_ECUDA;
+            if (!fused) {
+                if (!R.conv(r->rep_trunk[0], c.in, cur, nullptr, true, H, W)) return MZ_ECUDA;
+                if (!R.blocks(r->rep_trunk, 1, nd.blocks, &cur, &tmp, &spare, H, W)) return MZ_ECUDA;
+            }
         }
         // rescale -> hidden (no heads on the raw state at the root)
         if (!R.heads(cur, 0, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, hidden_out, c.pool_hidden, c.pool_stride, c.out_slot))
@@ -1060,8 +1098,12 @@ int resnet_inference(ResNetDevice* r, const InferCall& c, cudaStream_t stream, i
         }
     } else {
         const float* in = c.gather_parent ? c.pool_hidden : c.in;
-        if (!R.conv(r->dyn[0], in, cur, nullptr, true, hh, hw, c.gather_parent, c.pool_stride, c.action)) return MZ_ECUDA;
-        if (!R.blocks(r->dyn, 1, nd.blocks, &cur, &tmp, &spare, hh, hw)) return MZ_ECUDA;
+        const int fused = R.small_tower(r->dyn, 0, true, nd.blocks, in, cur, C, hh, hw, c.gather_parent, c.pool_stride, c.action);
+        if (fused < 0) return MZ_ECUDA;
+        if (!fused) {
+            if (!R.conv(r->dyn[0], in, cur, nullptr, true, hh, hw, c.gather_parent, c.pool_stride, c.action)) return MZ_ECUDA;
+            if (!R.blocks(r->dyn, 1, nd.blocks, &cur, &tmp, &spare, hh, hw)) return MZ_ECUDA;
+        }
         // reward head on the raw state + rescale -> hidden
         if (!R.heads(cur, 1, &r->reward_head, nullptr, c.reward_logits, nullptr, c.reward, nullptr, hidden_out, c.pool_hidden,
                      c.pool_stride, c.out_slot))
@@ -1072,7 +1114,11 @@ int resnet_inference(ResNetDevice* r, const InferCall& c, cudaStream_t stream, i
         float* x = hidden_out;
         // the tower must not overwrite the hidden state: first conv reads it, writes workspace
         float *pc = cur, *pt = tmp, *ps = spare;
-        if (nd.blocks > 0) {
+        const int fused = nd.blocks > 0 ? R.small_tower(r->pred, 0, false, nd.blocks, x, pt, C, hh, hw) : 0;
+        if (fused < 0) return MZ_ECUDA;
+        if (fused) {
+            x = pt;
+        } else if (nd.blocks > 0) {
             if (!R.conv(r->pred[0], x, pt, nullptr, true, hh, hw)) return MZ_ECUDA;
             if (!R.conv(r->pred[1], pt, ps, x, true, hh, hw)) return MZ_ECUDA;
             { float* t = pc; pc = ps; ps = t; }

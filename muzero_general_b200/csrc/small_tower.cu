@@ -1,0 +1,205 @@
+// Fused CUDA-core residual tower (small_tower.h).
+//
+// The per-layer conv3x3_kernel (resnet.cu) is latency-bound on small boards: a TicTacToe / Breakout-hidden conv is
+// 20-340 MFLOP per launch, far too little to amortise a launch, the weight staging and the input staging, and a
+// simulation needs 5-9 of them.  Here ONE persistent launch runs the whole tower: every CTA stages the weights of all
+// layers once, then takes tiles of `boards_per_cta` boards through all layers with the activations ping-ponging
+// between two zero-padded shared-memory buffers; only the tower input is read from and the tower output written to
+// global memory.  A residual block (models.py:213-231) is conv1: X -> T, conv2: T -> X with the residual X added in
+// place by the thread that owns the output.  The arithmetic (fp32 FMA chain over cin, dy, dx; + bias, + residual,
+// ReLU) is in exactly the order of conv3x3_kernel, so both paths give bit-identical results.
+//
+// Thread mapping: one item = (board, row y, group of CO output channels) computes the P = W pixels of that row
+// for CO channels (P x CO accumulators); CO = 4 when the batch is large enough to fill the GPU that way (float4
+// weight loads, 4.5+ FMAs per shared-memory load), CO = 1 for small batches (4x the threads, lower latency).
+#include "small_tower.h"
+
+#include <algorithm>
+
+namespace mz {
+
+namespace {
+constexpr int kMaxThreads = 256;
+
+template <int P, int CO>
+__global__ void __launch_bounds__(kMaxThreads) small_tower_kernel(const __grid_constant__ SmallTowerArgs a) {
+    extern __shared__ __align__(16) float smem[];
+    const int H = a.H, C = a.C;
+    constexpr int Wp = P + 2;
+    const int plane = (H + 2) * Wp;
+    const int nb = a.boards_per_cta, cap = a.cap_channels;
+    const int bufsz = nb * cap * plane;
+    float* s_w = smem;
+    float* s_act = smem + a.w_floats;
+
+    // ---- once per CTA: weights + biases of every layer, zeroed activation buffers (padding stays zero)
+    for (int l = 0; l < a.n_layers; ++l) {
+        const int count = a.layer[l].cin * 9 * C;
+        const float4* src = reinterpret_cast<const float4*>(a.blob + a.layer[l].w_off);
+        float4* dst = reinterpret_cast<float4*>(s_w + a.w_smem_off[l]);
+        for (int i = threadIdx.x; i < count / 4; i += blockDim.x) dst[i] = src[i];
+        for (int i = threadIdx.x; i < C; i += blockDim.x)
+            s_w[a.b_smem_off[l] + i] = a.layer[l].b_off >= 0 ? a.blob[a.layer[l].b_off + i] : 0.0f;
+    }
+    for (int i = threadIdx.x; i < 2 * bufsz; i += blockDim.x) s_act[i] = 0.0f;
+
+    const int cgs = C / CO;
+    const int items_per_board = cgs * H;
+    const int item = threadIdx.x;
+    const int cgi = item % cgs;
+    const int y = (item / cgs) % H;
+    const int b = item / items_per_board;
+    const int HW = H * P;
+    const int cin0 = a.layer[0].cin;
+    const size_t sample_elems = (size_t)a.in_channels * HW;
+
+    for (int tile = blockIdx.x; tile * nb < a.n; tile += gridDim.x) {
+        const int b0 = tile * nb;
+        const int nbt = min(nb, a.n - b0);
+        __syncthreads();                                   // previous tile fully consumed / initial fill visible
+        // ---- stage the tower input (interior only) into buffer 0
+        for (int i = threadIdx.x; i < nbt * cin0 * HW; i += blockDim.x) {
+            const int x = i % P, yy = (i / P) % H, ci = (i / HW) % cin0, bb = i / (HW * cin0);
+            const int g = b0 + bb;
+            float v;
+            if (ci < a.in_channels) {
+                const float* src = a.gather_parent ? a.in + ((size_t)g * a.pool_stride + a.gather_parent[g]) * sample_elems
+                                                   : a.in + (size_t)g * sample_elems;
+                v = src[ci * HW + yy * P + x];
+            } else {
+                v = __fdiv_rn((float)a.action[g], (float)a.A);        // action / |A| plane (models.py:586-600)
+            }
+            s_act[(bb * cap + ci) * plane + (yy + 1) * Wp + x + 1] = v;
+        }
+        __syncthreads();
+
+        const bool active = b < nbt;
+        int cur = 0;
+        for (int l = 0; l < a.n_layers; ++l) {
+            const float* sin = s_act + cur * bufsz;
+            float* sout = s_act + (cur ^ 1) * bufsz;
+            if (active) {
+                float acc[CO][P];
+#pragma unroll
+                for (int c = 0; c < CO; ++c)
+#pragma unroll
+                    for (int p = 0; p < P; ++p) acc[c][p] = 0.0f;
+                const float* ib = sin + b * cap * plane + y * Wp;
+                const float* wb = s_w + a.w_smem_off[l] + cgi * CO;
+                const int cin = a.layer[l].cin;
+                for (int ci = 0; ci < cin; ++ci) {
+#pragma unroll
+                    for (int dy = 0; dy < 3; ++dy) {
+                        float v[P + 2];
+#pragma unroll
+                        for (int j = 0; j < P + 2; ++j) v[j] = ib[ci * plane + dy * Wp + j];
+#pragma unroll
+                        for (int dx = 0; dx < 3; ++dx) {
+                            float w[CO];
+                            if constexpr (CO == 4) {
+                                const float4 w4 = *reinterpret_cast<const float4*>(wb + (ci * 9 + dy * 3 + dx) * C);
+                                w[0] = w4.x; w[1] = w4.y; w[2] = w4.z; w[3] = w4.w;
+                            } else {
+#pragma unroll
+                                for (int c = 0; c < CO; ++c) w[c] = wb[(ci * 9 + dy * 3 + dx) * C + c];
+                            }
+#pragma unroll
+                            for (int p = 0; p < P; ++p)
+#pragma unroll
+                                for (int c = 0; c < CO; ++c) acc[c][p] = fmaf(v[p + dx], w[c], acc[c][p]);
+                        }
+                    }
+                }
+                const bool last = l == a.n_layers - 1;
+                const int g = b0 + b;
+#pragma unroll
+                for (int c = 0; c < CO; ++c) {
+                    const int co = cgi * CO + c;
+                    const float bias = s_w[a.b_smem_off[l] + co];
+                    float* so = sout + (b * cap + co) * plane + (y + 1) * Wp + 1;
+#pragma unroll
+                    for (int p = 0; p < P; ++p) {
+                        float r = acc[c][p] + bias;
+                        if (a.layer[l].residual) r += so[p];
+                        if (a.layer[l].relu) r = fmaxf(r, 0.0f);
+                        if (last) a.out[(((size_t)g * C + co) * H + y) * P + p] = r;
+                        else so[p] = r;
+                    }
+                }
+            }
+            __syncthreads();
+            cur ^= 1;
+        }
+    }
+}
+
+struct Plan { int P, CO, nb, threads, grid; size_t smem; bool ok; };
+
+Plan make_plan(SmallTowerArgs& a, int sm_count) {
+    Plan pl{};
+    pl.ok = false;
+    if (a.n < 1 || a.n_layers < 1 || a.n_layers > kSmallTowerMaxLayers) return pl;
+    if (a.W < 2 || a.W > 8 || a.H < 1 || a.H > 16 || a.C % 4 != 0 || a.C < 4) return pl;
+    int cap = a.C, w_floats = 0;
+    for (int l = 0; l < a.n_layers; ++l) {
+        cap = std::max(cap, a.layer[l].cin);
+        a.w_smem_off[l] = w_floats; w_floats += a.layer[l].cin * 9 * a.C;
+        a.b_smem_off[l] = w_floats; w_floats += a.C;
+    }
+    if (a.layer[0].cin != a.in_channels + (a.action ? 1 : 0)) return pl;
+    const int plane = (a.H + 2) * (a.W + 2);
+    // CO = 4 only when that still gives every SM a few hundred threads
+    int CO = ((long)a.n * (a.C / 4) * a.H >= (long)sm_count * 384) ? 4 : 1;
+    if ((a.C / CO) * a.H > kMaxThreads) CO = 4;
+    const int items = (a.C / CO) * a.H;
+    if (items > kMaxThreads) return pl;
+    int nb = std::min(kMaxThreads / items, a.n);
+    const size_t budget = 200 * 1024;
+    auto bytes = [&](int boards) { return ((size_t)w_floats + 2ull * boards * cap * plane) * 4; };
+    while (nb > 1 && bytes(nb) > 100 * 1024) --nb;          // prefer two or more CTAs per SM
+    if (bytes(nb) > budget) return pl;
+    // persistent grid; spread the boards evenly over the resident CTAs
+    auto resident = [&](int boards) {
+        const int threads = ((boards * items + 31) / 32) * 32;
+        int per_sm = (int)std::min<size_t>((227 * 1024) / (bytes(boards) + 1024), (size_t)(2048 / threads));
+        return sm_count * std::max(1, std::min(per_sm, 8));
+    };
+    int grid = resident(nb);
+    const int rounds = (a.n + grid * nb - 1) / (grid * nb);
+    nb = std::min(nb, (a.n + grid * rounds - 1) / (grid * rounds));
+    grid = std::min((a.n + nb - 1) / nb, resident(nb));
+    a.boards_per_cta = nb; a.cap_channels = cap; a.w_floats = w_floats;
+    pl.P = a.W; pl.CO = CO; pl.nb = nb; pl.threads = ((nb * items + 31) / 32) * 32; pl.grid = grid; pl.smem = bytes(nb);
+    pl.ok = true;
+    return pl;
+}
+
+template <int P, int CO>
+cudaError_t launch(const SmallTowerArgs& a, const Plan& pl, cudaStream_t stream) {
+    static size_t attr = 0;
+    if (attr < pl.smem) {
+        cudaError_t e = cudaFuncSetAttribute(small_tower_kernel<P, CO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem);
+        if (e != cudaSuccess) return e;
+        attr = pl.smem;
+    }
+    small_tower_kernel<P, CO><<<pl.grid, pl.threads, pl.smem, stream>>>(a);
+    return cudaGetLastError();
+}
+}  // namespace
+
+bool small_tower_supported(const SmallTowerArgs& a) {
+    SmallTowerArgs copy = a;
+    return make_plan(copy, 148).ok;
+}
+
+cudaError_t launch_small_tower(SmallTowerArgs a, int sm_count, cudaStream_t stream) {
+    const Plan pl = make_plan(a, sm_count);
+    if (!pl.ok) return cudaErrorInvalidValue;
+#define MZ_ST(PP)                                                                             \
+    if (pl.P == PP) return pl.CO == 4 ? launch<PP, 4>(a, pl, stream) : launch<PP, 1>(a, pl, stream);
+    MZ_ST(2) MZ_ST(3) MZ_ST(4) MZ_ST(5) MZ_ST(6) MZ_ST(7) MZ_ST(8)
+#undef MZ_ST
+    return cudaErrorInvalidValue;
+}
+
+}  // namespace mz

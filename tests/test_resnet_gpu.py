@@ -132,3 +132,36 @@ def test_resnet_closed_loop_matches_reference_counts(name, numerics, game_config
         assert abs(out.root_value[0] - c["root_value"]) <= vt * max(1.0, abs(c["root_value"]))
         assert abs(out.root_predicted_value[0] - c["root_predicted_value"]) <= vt * max(1.0, abs(c["root_predicted_value"]))
         eng.close()
+
+
+@pytest.mark.parametrize("name,n", [("tictactoe", 700), ("breakout", 37), ("breakout", 200)])
+def test_fused_cuda_core_tower_is_bit_identical_to_per_layer_launches(name, n, game_configs, monkeypatch):
+    """small_tower.cu keeps conv3x3_kernel's accumulation order: one fused launch == one launch per conv, bit for bit
+    (multi-tile grids, ragged last tile, gathered pool input with the action plane are all exercised by the search)."""
+    cfg = game_configs[name]
+    spec = netspec_from_config(cfg)
+    rs = numpy.random.RandomState(5)
+    obs = rs.random_sample((n, spec.obs_elems)).astype(numpy.float32)
+    actions = rs.randint(0, spec.action_space, size=n)
+    outs = []
+    for no_fuse in ("1", "0"):
+        monkeypatch.setenv("MZ_NO_TC", "1")
+        monkeypatch.setenv("MZ_NO_FUSE", no_fuse)
+        eng = _engine(cfg, n, 6)
+        eng.load_weights(weights_for(name, spec))
+        l0 = eng.launch_count
+        r0 = eng.initial_inference(obs)
+        l1 = eng.launch_count
+        r1 = eng.recurrent_inference(r0["hidden"], actions)
+        l2 = eng.launch_count
+        res = eng.search(obs=obs, add_exploration_noise=False)
+        outs.append((r0, r1, res, l1 - l0, l2 - l1))
+        eng.close()
+    (a0, a1, sa, la0, la1), (b0, b1, sb, lb0, lb1) = outs
+    for k in ("hidden", "value_logits", "policy_logits", "value"):
+        assert numpy.array_equal(a0[k], b0[k]), k
+    for k in ("hidden", "value_logits", "policy_logits", "reward_logits", "value", "reward"):
+        assert numpy.array_equal(a1[k], b1[k]), k
+    assert numpy.array_equal(sa.visit_counts, sb.visit_counts)
+    assert numpy.array_equal(sa.root_value, sb.root_value)
+    assert lb1 < la1 and lb0 < la0, "fused path must need fewer launches"
