@@ -44,6 +44,9 @@ MZ_DEVINL double shfl_f64(unsigned mask, double v, int src, int width) {
 }
 
 // smallest power of two >= n (n >= 1)
+// hint: bring the line holding *p into L1 (no register, no dependency)
+MZ_DEVINL void prefetch_l1(const void* p) { asm volatile("prefetch.L1 [%0];" ::"l"(p)); }
+
 MZ_DEVINL int pow2_ceil(int n) { return n <= 1 ? 1 : 1 << (32 - __clz(n - 1)); }
 
 // Exact max / min (no rounding involved), NaN-free inputs assumed.

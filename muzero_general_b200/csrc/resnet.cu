@@ -223,9 +223,13 @@ __device__ __forceinline__ int p64c4_index(int c, int p, int W) {
 
 // Persistent CTAs (one per SM), 1024 threads = 8 groups of 128: the head weights of this launch are staged
 // in shared memory once per CTA, then every GROUP takes one sample at a time (named barriers, groups never
-// wait for each other).  x is read as 16-byte chunks into a padded [position][channel] tile
-// (conflict-free for the per-channel rescale and the per-position conv1x1); the two heads of a launch
-// (value + policy) run side by side on the two halves of the group.
+// wait for each other).  x is staged as a [position][channel] tile with 16-byte aligned rows (row stride C+4:
+// conflict-free for 128-bit row reads and for per-channel column scans).  Everything that touches global
+// memory or the weights moves 16 bytes per instruction: the P64S state is read and written as whole 8-channel
+// chunks, conv1x1 reads x rows and weight rows as float4, the FC layers read packed [in/4][out][4] weights and
+// float4 activations; index arithmetic with runtime divisors happens once per chunk, not per element.
+// The accumulation order of every dot product is ascending input index (as torch's reference loops are
+// compared with a tolerance anyway, this only keeps results independent of the vector width).
 constexpr int kHeadGroup = 128;
 constexpr int kHeadThreads = 1024;
 
@@ -235,11 +239,14 @@ __device__ __forceinline__ void group_bar(int group) {
 
 __global__ void __launch_bounds__(kHeadThreads) heads_kernel(const __grid_constant__ HeadsArgs a) {
     extern __shared__ __align__(16) float sm[];
-    const int C = a.C, HW = a.HW, CP = C + 1;
+    const int C = a.C, HW = a.HW, CP = C + 4;
     const int group = threadIdx.x / kHeadGroup, t = threadIdx.x % kHeadGroup, ngroups = blockDim.x / kHeadGroup;
     float* s_w = sm;                                                 // head blob slice [w_lo, w_lo + w_floats)
-    float* s_x = s_w + a.w_floats + (size_t)group * a.warp_floats;   // [HW][C+1]
-    float* s_act = s_x + HW * CP;                                    // per head: ping | pong
+    float* s_x = s_w + a.w_floats + (size_t)group * a.warp_floats;   // [HW][C+4]
+    float* s_lo = s_x + HW * CP;                                     // [C] channel minimum
+    float* s_sc = s_lo + C;                                          // [C] channel scale
+    float* s_part = s_sc + C;                                        // [2][2][C] partial extrema
+    float* s_act = s_part + 4 * C;                                   // per head: ping | pong
     {
         const float4* src = reinterpret_cast<const float4*>(a.blob + a.w_lo);
         float4* dst = reinterpret_cast<float4*>(s_w);
@@ -247,19 +254,22 @@ __global__ void __launch_bounds__(kHeadThreads) heads_kernel(const __grid_consta
     }
     __syncthreads();
     const float* blob = s_w - a.w_lo;                                // blob[off] addresses the staged copy
+    const int cj = C >> 3;                                           // 8-channel chunks per position (P64S path)
 
     for (int g = blockIdx.x * ngroups + group; g < a.n; g += gridDim.x * ngroups) {
         // ---- stage x[p][c]
         if (a.p64c4) {
             const uint4* x8 = reinterpret_cast<const uint4*>(reinterpret_cast<const __half*>(a.x) + (size_t)g * 4096);
-            for (int i = t; i < (C / 8) * HW; i += kHeadGroup) {
-                const int j = i / HW, p = i % HW;
+            for (int i = t; i < cj * HW; i += kHeadGroup) {
+                const int j = i % cj, p = i / cj;
                 const int pos = (p / a.W + 1) * 8 + (p % a.W);
                 const uint4 v = x8[pos * 8 + (j ^ (pos & 7))];
                 const __half2* h2 = reinterpret_cast<const __half2*>(&v);
-                float* d = s_x + p * CP + 8 * j;
-#pragma unroll
-                for (int e = 0; e < 4; ++e) { const float2 f = __half22float2(h2[e]); d[2 * e] = f.x; d[2 * e + 1] = f.y; }
+                const float2 f0 = __half22float2(h2[0]), f1 = __half22float2(h2[1]);
+                const float2 f2 = __half22float2(h2[2]), f3 = __half22float2(h2[3]);
+                float4* d = reinterpret_cast<float4*>(s_x + p * CP + 8 * j);
+                d[0] = make_float4(f0.x, f0.y, f1.x, f1.y);
+                d[1] = make_float4(f2.x, f2.y, f3.x, f3.y);
             }
         } else {
             const float* x = a.x + (size_t)g * C * HW;
@@ -268,39 +278,62 @@ __global__ void __launch_bounds__(kHeadThreads) heads_kernel(const __grid_consta
         group_bar(group);
 
         if (a.rescaled || a.pool_hidden || a.state_p64c4) {
-            // (x - min) / scale per channel over the positions (models.py:530-553).  Two threads per channel when
-            // the group is wide enough: each scans half of the positions, partial extrema meet in shared memory.
+            // (x - min) / scale per channel over the positions (models.py:530-553).
+            // Phase A: channel extrema (two threads per channel when the group is wide enough).
             const int parts = (2 * C <= kHeadGroup) ? 2 : 1;
-            for (int cb = 0; cb < C; cb += kHeadGroup) {               // one pass unless C > 128
-                const int c = (parts == 2) ? t % C : cb + t;
-                const int part = (parts == 2) ? t / C : 0;
-                const bool active = (parts == 2) ? (t < 2 * C) : (c < C);
-                const int p0 = active ? (part * HW) / parts : 0, p1 = active ? ((part + 1) * HW) / parts : 0;
+            for (int i = t; i < parts * C; i += kHeadGroup) {
+                const int c = i % C, part = i / C;
+                const int p0 = (part * HW) / parts, p1 = ((part + 1) * HW) / parts;
                 float lo = INFINITY, hi = -INFINITY;
                 for (int p = p0; p < p1; ++p) { const float v = s_x[p * CP + c]; lo = fminf(lo, v); hi = fmaxf(hi, v); }
-                if (parts == 2) {
-                    if (active) { s_act[2 * t] = lo; s_act[2 * t + 1] = hi; }
-                    group_bar(group);
-                    if (active) {
-                        const int other = (part ? t - C : t + C);
-                        lo = fminf(lo, s_act[2 * other]); hi = fmaxf(hi, s_act[2 * other + 1]);
-                    }
-                    group_bar(group);                     // s_act is reused by the heads below
-                }
+                s_part[(part * 2) * C + c] = lo;
+                s_part[(part * 2 + 1) * C + c] = hi;
+            }
+            group_bar(group);
+            for (int c = t; c < C; c += kHeadGroup) {
+                float lo = s_part[c], hi = s_part[C + c];
+                if (parts == 2) { lo = fminf(lo, s_part[2 * C + c]); hi = fmaxf(hi, s_part[3 * C + c]); }
                 float sc = __fsub_rn(hi, lo);
                 if (sc < 1e-5f) sc = __fadd_rn(sc, 1e-5f);
-                for (int p = p0; p < p1; ++p) {
-                    const float v = __fdiv_rn(__fsub_rn(s_x[p * CP + c], lo), sc);
-                    if (a.rescaled) a.rescaled[(size_t)g * C * HW + c * HW + p] = v;
-                    if (a.p64c4) {
-                        const __half vt = __float2half_rn(v);      // fp16 operand of the tensor-core convs
-                        const int off = p64c4_index(c, p, a.W);
-                        if (a.pool_hidden)
-                            reinterpret_cast<__half*>(a.pool_hidden)[((size_t)g * a.pool_stride + a.out_slot) * 4096 + off] = vt;
-                        if (a.state_p64c4) reinterpret_cast<__half*>(a.state_p64c4)[(size_t)g * 4096 + off] = vt;
-                    } else if (a.pool_hidden) {
-                        a.pool_hidden[((size_t)g * a.pool_stride + a.out_slot) * C * HW + c * HW + p] = v;
+                s_lo[c] = lo; s_sc[c] = sc;
+            }
+            group_bar(group);
+            // Phase B: normalise and store
+            if (a.p64c4) {
+                for (int i = t; i < cj * HW; i += kHeadGroup) {
+                    const int j = i % cj, p = i / cj;
+                    const int pos = (p / a.W + 1) * 8 + (p % a.W);
+                    const float4* xr = reinterpret_cast<const float4*>(s_x + p * CP + 8 * j);
+                    const float4* lr = reinterpret_cast<const float4*>(s_lo + 8 * j);
+                    const float4* sr = reinterpret_cast<const float4*>(s_sc + 8 * j);
+                    float v[8];
+#pragma unroll
+                    for (int q = 0; q < 2; ++q) {
+                        const float4 x4 = xr[q], l4 = lr[q], c4 = sr[q];
+                        v[4 * q + 0] = __fdiv_rn(__fsub_rn(x4.x, l4.x), c4.x);
+                        v[4 * q + 1] = __fdiv_rn(__fsub_rn(x4.y, l4.y), c4.y);
+                        v[4 * q + 2] = __fdiv_rn(__fsub_rn(x4.z, l4.z), c4.z);
+                        v[4 * q + 3] = __fdiv_rn(__fsub_rn(x4.w, l4.w), c4.w);
                     }
+                    if (a.rescaled) {
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) a.rescaled[(size_t)g * C * HW + (8 * j + e) * HW + p] = v[e];
+                    }
+                    uint4 packed;                                   // fp16 operand of the tensor-core convs
+                    __half2* h2 = reinterpret_cast<__half2*>(&packed);
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) h2[e] = __floats2half2_rn(v[2 * e], v[2 * e + 1]);
+                    const int off8 = pos * 8 + (j ^ (pos & 7));     // in 16-byte units inside the 8 KB state
+                    if (a.pool_hidden)
+                        reinterpret_cast<uint4*>(a.pool_hidden)[((size_t)g * a.pool_stride + a.out_slot) * 512 + off8] = packed;
+                    if (a.state_p64c4) reinterpret_cast<uint4*>(a.state_p64c4)[(size_t)g * 512 + off8] = packed;
+                }
+            } else {
+                for (int i = t; i < C * HW; i += kHeadGroup) {
+                    const int c = i / HW, p = i % HW;
+                    const float v = __fdiv_rn(__fsub_rn(s_x[p * CP + c], s_lo[c]), s_sc[c]);
+                    if (a.rescaled) a.rescaled[(size_t)g * C * HW + i] = v;
+                    if (a.pool_hidden) a.pool_hidden[((size_t)g * a.pool_stride + a.out_slot) * C * HW + i] = v;
                 }
             }
         }
@@ -312,29 +345,58 @@ __global__ void __launch_bounds__(kHeadThreads) heads_kernel(const __grid_consta
             const HeadDesc& d = a.head[h];
             float* cur = s_act + (size_t)h * 2 * a.smem_floats;
             float* nxt = cur + a.smem_floats;
-            // conv1x1: r[c][p] = b[c] + sum_k W[c][k] x[p][k]
-            for (int i = u; i < d.rc * HW; i += span) {
-                const int c = i / HW, p = i % HW;
-                const float* xr = s_x + p * CP;
-                const float* w = blob + d.w1_off + c * C;
-                float acc = blob[d.b1_off + c];
-#pragma unroll 8
-                for (int k = 0; k < C; ++k) acc = fmaf(w[k], xr[k], acc);
-                cur[i] = acc;                             // flatten order (c, h, w) = NCHW view(-1, ...)
+            // conv1x1: r[c][p] = b[c] + sum_k W[c][k] x[p][k]; one thread per position, 4 channels at a time
+            for (int p = u; p < HW; p += span) {
+                const float4* xr = reinterpret_cast<const float4*>(s_x + p * CP);
+                for (int c0 = 0; c0 < d.rc; c0 += 4) {
+                    const int nc = min(4, d.rc - c0);
+                    float acc[4];
+#pragma unroll
+                    for (int cc = 0; cc < 4; ++cc) acc[cc] = cc < nc ? blob[d.b1_off + c0 + cc] : 0.0f;
+                    const float4* w0 = reinterpret_cast<const float4*>(blob + d.w1_off + (size_t)c0 * C);
+                    for (int k4 = 0; k4 < C / 4; ++k4) {
+                        const float4 x4 = xr[k4];
+#pragma unroll
+                        for (int cc = 0; cc < 4; ++cc) {
+                            if (cc < nc) {
+                                const float4 w4 = w0[cc * (C / 4) + k4];
+                                acc[cc] = fmaf(w4.x, x4.x, acc[cc]);
+                                acc[cc] = fmaf(w4.y, x4.y, acc[cc]);
+                                acc[cc] = fmaf(w4.z, x4.z, acc[cc]);
+                                acc[cc] = fmaf(w4.w, x4.w, acc[cc]);
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int cc = 0; cc < 4; ++cc)
+                        if (cc < nc) cur[(c0 + cc) * HW + p] = acc[cc];      // flatten order (c, h, w) = NCHW view(-1, ...)
+                }
             }
+            if (u < 4) { const int i = d.rc * HW + u; if (i < ((d.rc * HW + 3) & ~3)) cur[i] = 0.0f; }   // zero the padding
             group_bar(group);
             const int max_layers = max(a.head[0].mlp.n, a.head[a.n_heads - 1].mlp.n);
             for (int l = 0; l < max_layers; ++l) {
                 if (l < d.mlp.n) {
-                    const int in = d.mlp.in[l], out = d.mlp.out[l];
-                    const float* W = blob + d.mlp.w_off[l];
+                    const int in4 = (d.mlp.in[l] + 3) >> 2, out = d.mlp.out[l];
+                    const float4* W4 = reinterpret_cast<const float4*>(blob + d.mlp.w_off[l]);      // [in/4][out][4]
+                    const float4* a4 = reinterpret_cast<const float4*>(cur);
                     const float* b = blob + d.mlp.b_off[l];
                     const bool last = l == d.mlp.n - 1;
-                    for (int o = u; o < out; o += span) {
-                        float acc = b[o];
-#pragma unroll 8
-                        for (int i = 0; i < in; ++i) acc = fmaf(cur[i], W[(size_t)i * out + o], acc);
-                        nxt[o] = last ? acc : elu1(acc);
+                    for (int o = u; o < ((out + 3) & ~3); o += span) {
+                        if (o < out) {
+                            float acc = b[o];
+#pragma unroll 4
+                            for (int i = 0; i < in4; ++i) {
+                                const float4 x4 = a4[i], w4 = W4[(size_t)i * out + o];
+                                acc = fmaf(x4.x, w4.x, acc);
+                                acc = fmaf(x4.y, w4.y, acc);
+                                acc = fmaf(x4.z, w4.z, acc);
+                                acc = fmaf(x4.w, w4.w, acc);
+                            }
+                            nxt[o] = last ? acc : elu1(acc);
+                        } else {
+                            nxt[o] = 0.0f;                          // padding read by the next layer's float4 loads
+                        }
                     }
                     float* tmp = cur; cur = nxt; nxt = tmp;
                 }
@@ -605,14 +667,17 @@ bool pack_head(Loader& L, const std::string& conv, const std::string& fc, int C,
         const MzTensor* lb = L.get(fc + "." + std::to_string(2 * l) + ".bias", out);
         if (!lw || !lb) return false;
         d.mlp.in[l] = in; d.mlp.out[l] = out;
+        while (blob.size() % 4) blob.push_back(0.0f);
         d.mlp.w_off[l] = (int)blob.size();
-        blob.resize(blob.size() + (size_t)in * out);
+        const int in4 = (in + 3) / 4;
+        blob.resize(blob.size() + (size_t)in4 * out * 4, 0.0f);        // packed [in/4][out][4], zero rows pad `in`
         float* dst = blob.data() + d.mlp.w_off[l];
         for (int o = 0; o < out; ++o)
-            for (int i = 0; i < in; ++i) dst[(size_t)i * out + o] = lw->data[(size_t)o * in + i];
+            for (int i = 0; i < in; ++i) dst[((size_t)(i / 4) * out + o) * 4 + (i % 4)] = lw->data[(size_t)o * in + i];
         d.mlp.b_off[l] = (int)blob.size();
         blob.insert(blob.end(), lb->data, lb->data + out);
     }
+    while (blob.size() % 4) blob.push_back(0.0f);
     return true;
 }
 }  // namespace
@@ -873,12 +938,11 @@ struct Runner {
         const HeadDesc* hs[2] = {h0, h1};
         for (int i = 0; i < n_heads; ++i) {
             a.head[i] = *hs[i];
-            maxw = std::max(maxw, hs[i]->rc * a.HW);
-            for (int l = 0; l < hs[i]->mlp.n; ++l) maxw = std::max(maxw, hs[i]->mlp.out[l]);
+            maxw = std::max(maxw, hs[i]->rc * a.HW + 4);
+            for (int l = 0; l < hs[i]->mlp.n; ++l) maxw = std::max(maxw, hs[i]->mlp.out[l] + 4);
         }
         a.logits[0] = l0; a.logits[1] = l1; a.scalar[0] = s0; a.scalar[1] = s1;
         a.rescaled = rescaled; a.pool_hidden = pool_hidden; a.pool_stride = pool_stride; a.out_slot = out_slot;
-        if (a.C <= kHeadGroup / 2) maxw = std::max(maxw, a.C);      // room for the rescale's partial extrema
         a.smem_floats = (maxw + 3) & ~3;
         // blob slice covering the heads of this launch
         int lo = 1 << 30, hi = 0;
@@ -890,7 +954,7 @@ struct Runner {
         }
         if (n_heads == 0) { lo = 0; hi = 0; }
         a.w_lo = lo; a.w_floats = ((hi - lo) + 3) & ~3;
-        a.warp_floats = (a.HW * (a.C + 1) + 4 * a.smem_floats + 3) & ~3;       // x tile + (ping, pong) per head
+        a.warp_floats = (a.HW * (a.C + 4) + 6 * a.C + 4 * a.smem_floats + 3) & ~3;   // x tile + channel stats + (ping, pong) per head
         const int threads = kHeadThreads;
         const size_t smem = ((size_t)a.w_floats + (size_t)(threads / kHeadGroup) * a.warp_floats) * 4;
         if (smem > 227 * 1024) { *err = "heads: weights + tiles exceed shared memory"; return false; }

@@ -132,7 +132,11 @@ MZ_DEVINL void tree_init_root(const TreeConst& c, GameTree& t, float prior_f32, 
 // first_index >= 0: host-supplied pick (index into the tied list) for the all-way tie of the
 // first simulation (self_play.py:371-377 with sqrt(0) = 0).
 // ------------------------------------------------------------------------------------------
-template <int G>
+// kPool: the tree lives in the HBM node pool (step-wise pipeline).  Every level is then exactly ONE round trip to
+// L2: all fields of this lane's child (and the two table entries of the parent) are requested together, nothing
+// is loaded conditionally on a value that has just arrived, and as soon as the child's expansion id is known the
+// lines holding ITS children are prefetched into L1, overlapping the score arithmetic of the current level.
+template <int G, bool kPool = false>
 MZ_DEVINL Leaf tree_select(const TreeConst& c, GameTree& t, int sim, int64_t game_id, int move, int first_index) {
     const int k = LaneGroup<G>::lane();
     const int width = pow2_ceil(c.A);
@@ -152,9 +156,24 @@ MZ_DEVINL Leaf tree_select(const TreeConst& c, GameTree& t, int sim, int64_t gam
             nc = t.visit[base + k];
             child_exp_k = t.expansion[base + k];
             const double pr = (e == 0) ? t.root_prior[k] : (double)t.prior[base + k];
+            double vs = 0.0, tab_pbc = 0.0, tab_sqrt = 0.0;
+            if (kPool) {
+                reward_k = t.reward[base + k];
+                vs = t.vsum[base + k];
+                tab_pbc = __ldg(c.pbc + n_parent);
+                tab_sqrt = __ldg(c.sqrtn + n_parent);
+                if (child_exp_k >= 0) {
+                    const int nb = child_exp_k * c.A;
+                    prefetch_l1(t.visit + nb); prefetch_l1(t.expansion + nb); prefetch_l1(t.prior + nb);
+                    prefetch_l1(t.reward + nb); prefetch_l1(t.vsum + nb);
+                    prefetch_l1(t.vsum + nb + c.A - 1);             // A doubles may straddle a line
+                }
+            }
             // pb_c = (log(...) + init) * (sqrt(n_p) / (n_c + 1))     self_play.py:384-390
             double pbc;
-            if (c.ucb) {
+            if (kPool) {
+                pbc = __dmul_rn(tab_pbc, __ddiv_rn(tab_sqrt, (double)(nc + 1)));
+            } else if (c.ucb) {
                 pbc = __ldg(c.ucb + n_parent * (c.N + 2) + nc);
             } else {
                 const double q = __ddiv_rn(c.sqrtn[n_parent], (double)(nc + 1));
@@ -162,13 +181,14 @@ MZ_DEVINL Leaf tree_select(const TreeConst& c, GameTree& t, int sim, int64_t gam
             }
             score = __dmul_rn(pbc, pr);
             if (nc > 0) {
-                reward_k = t.reward[base + k];
-                const double mean = __ddiv_rn(t.vsum[base + k], (double)nc);
+                if (!kPool) { reward_k = t.reward[base + k]; vs = t.vsum[base + k]; }
+                const double mean = __ddiv_rn(vs, (double)nc);
                 const double signed_mean = (c.P == 1) ? mean : -mean;
                 double v = __dadd_rn((double)reward_k, __dmul_rn(c.discount, signed_mean));
                 v = value_range_normalize(v, t.lo, t.hi);
                 score = __dadd_rn(score, v);
             } else {
+                reward_k = 0.0f;                   // (an unvisited child's stored reward is 0 anyway)
                 score = __dadd_rn(score, 0.0);     // prior_score + 0
             }
         }

@@ -13,7 +13,9 @@
 
 namespace mz {
 
-template <int G>
+// kLatency: few games in flight (the launch is bound by the chain of dependent round trips to L2, not by
+// throughput): selection uses the single-round-trip + L1-prefetch variant of tree_select (tree.cuh).
+template <int G, bool kLatency>
 __global__ void __launch_bounds__(128) tree_step_kernel(const __grid_constant__ TreeStepArgs a) {
     const int g = (blockIdx.x * blockDim.x + threadIdx.x) / G;
     if (g >= a.n) return;
@@ -93,7 +95,7 @@ __global__ void __launch_bounds__(128) tree_step_kernel(const __grid_constant__ 
         const int64_t game_id = a.game_id ? a.game_id[g] : (int64_t)g;
         const int move = a.move_index ? a.move_index[g] : 0;
         const int first_index = a.first_index ? a.first_index[g] : -1;
-        const Leaf leaf = tree_select<G>(c, t, a.sim, game_id, move, first_index);
+        const Leaf leaf = tree_select<G, kLatency>(c, t, a.sim, game_id, move, first_index);
         if (lane == 0) {
             p.leaf_depth[g] = leaf.depth;
             p.leaf_parent[g] = leaf.parent_exp;
@@ -135,13 +137,18 @@ cudaError_t launch_tree_step(const TreeStepArgs& a, cudaStream_t stream) {
     const int threads = 128;
     const int games_per_cta = threads / G;
     const int grid = (a.n + games_per_cta - 1) / games_per_cta;
+    // below ~4 resident warps per scheduler the kernel is latency-bound
+    const bool latency = (long)a.n * G <= 148L * 512;
+#define MZ_TREE(GG)                                                                                 \
+    case GG:                                                                                        \
+        if (latency) tree_step_kernel<GG, true><<<grid, threads, 0, stream>>>(a);                   \
+        else tree_step_kernel<GG, false><<<grid, threads, 0, stream>>>(a);                          \
+        break;
     switch (G) {
-        case 4: tree_step_kernel<4><<<grid, threads, 0, stream>>>(a); break;
-        case 8: tree_step_kernel<8><<<grid, threads, 0, stream>>>(a); break;
-        case 16: tree_step_kernel<16><<<grid, threads, 0, stream>>>(a); break;
-        case 32: tree_step_kernel<32><<<grid, threads, 0, stream>>>(a); break;
+        MZ_TREE(4) MZ_TREE(8) MZ_TREE(16) MZ_TREE(32)
         default: return cudaErrorInvalidValue;
     }
+#undef MZ_TREE
     return cudaGetLastError();
 }
 
