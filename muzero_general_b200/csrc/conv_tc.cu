@@ -46,6 +46,7 @@ constexpr int kStageBytes = kRows * kRowBytes;         // 20480
 constexpr int kStages = 2;
 constexpr int kTapBytes = kC * kRowBytes;               // 8192: [cout 64][128 B]
 constexpr int kWBytes = 9 * kTapBytes;                 // 73728
+constexpr int kOutBytes = kBoards * kPos * kRowBytes;  // 16384: one output tile in the global board layout
 constexpr int kBoardHalves = kC * kPos;                // 4096 fp16 per board
 constexpr int kAccCols = 64;
 constexpr int kThreads = 384;             // 4 control warps + 8 epilogue warps
@@ -54,10 +55,11 @@ constexpr int kEpiWarps = 8;
 struct Smem {
     // offsets
     static constexpr int w = 0;
-    static constexpr int a = kWBytes;
-    static constexpr int bias = a + kStages * kStageBytes;                 // [kTowerMaxLayers][64] floats
+    static constexpr int a = 2 * kWBytes;                                  // two weight sets: layer l+1 is prefetched while layer l multiplies
+    static constexpr int out = a + kStages * kStageBytes;                  // 2 output tiles (2 boards x 8 KB) staged for the bulk store
+    static constexpr int bias = out + 2 * kOutBytes;                       // [kTowerMaxLayers][64] floats
     static constexpr int bars = bias + kTowerMaxLayers * kC * 4;           // 8-byte aligned
-    static constexpr int tmem_ptr = bars + 48 * 8;
+    static constexpr int tmem_ptr = bars + 64 * 8;
     static constexpr int total = tmem_ptr + 16;
 };
 static_assert(Smem::total <= 232448, "shared memory budget");
@@ -132,6 +134,10 @@ MZ_DEVINL void umma_f16_words(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uin
         "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n\t"
         "}" ::"r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(kIdesc), "r"(accumulate), "r"(kDescHi) : "memory");
 }
+// shared -> global bulk copy (TMA unit), tracked by the thread's bulk async-group
+MZ_DEVINL void bulk_s2g(void* gdst, uint32_t ssrc, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(ssrc), "r"(bytes) : "memory");
+}
 MZ_DEVINL void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -163,13 +169,16 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tower_tc_kernel(const __grid
     const uint32_t s_w = s_base + Smem::w, s_a = s_base + Smem::a;
     float* s_bias = reinterpret_cast<float*>(smem + Smem::bias);
     const uint32_t bars = s_base + Smem::bars;
-    auto bar_w_full = [&](int tap) { return bars + 8u * tap; };            // weights of (layer, tap) landed
-    auto bar_w_empty = [&](int tap) { return bars + 8u * (9 + tap); };     // last MMA of the layer on this tap done
-    auto bar_a_full = [&](int s) { return bars + 8u * (18 + s); };
-    auto bar_a_empty = [&](int s) { return bars + 8u * (20 + s); };
-    auto bar_acc_full = [&](int s) { return bars + 8u * (22 + s); };
-    auto bar_acc_empty = [&](int s) { return bars + 8u * (24 + s); };
-    auto bar_tile_done = [&](int k) { return bars + 8u * (26 + k); };      // layer output of my k-th tile stored
+    // weight set = layer & 1
+    auto bar_w_full = [&](int set, int tap) { return bars + 8u * (set * 9 + tap); };          // weights of (layer, tap) landed
+    auto bar_w_empty = [&](int set, int tap) { return bars + 8u * (18 + set * 9 + tap); };    // last MMA of the layer on this tap done
+    auto bar_a_full = [&](int s) { return bars + 8u * (36 + s); };
+    auto bar_a_empty = [&](int s) { return bars + 8u * (38 + s); };
+    auto bar_acc_full = [&](int s) { return bars + 8u * (40 + s); };
+    auto bar_acc_empty = [&](int s) { return bars + 8u * (42 + s); };
+    auto bar_tile_done = [&](int k) { return bars + 8u * (44 + k); };      // layer output of my k-th tile stored
+    auto bar_out_full = [&](int st) { return bars + 8u * (52 + st); };     // output tile staged in shared memory
+    auto bar_out_empty = [&](int st) { return bars + 8u * (54 + st); };    // ... and drained by the bulk store
     volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + Smem::tmem_ptr);
 
     const int n_tiles = (a.n + kBoards - 1) / kBoards;
@@ -188,14 +197,15 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tower_tc_kernel(const __grid
         s_bias[i] = b ? b[i % kC] : 0.0f;
     }
     if (threadIdx.x == 0) {
-        for (int t = 0; t < 9; ++t) { mbar_init(bar_w_full(t), 1); mbar_init(bar_w_empty(t), 1); }
+        for (int t = 0; t < 18; ++t) { mbar_init(bar_w_full(t / 9, t % 9), 1); mbar_init(bar_w_empty(t / 9, t % 9), 1); }
         for (int s = 0; s < kStages; ++s) {
             mbar_init(bar_a_full(s), 1);
             mbar_init(bar_a_empty(s), 1);
             mbar_init(bar_acc_full(s), 1);
             mbar_init(bar_acc_empty(s), kEpiWarps);   // one arrival per epilogue warp
         }
-        for (int k = 0; k < kTowerMaxTiles; ++k) mbar_init(bar_tile_done(k), kEpiWarps);
+        for (int k = 0; k < kTowerMaxTiles; ++k) mbar_init(bar_tile_done(k), 1);
+        for (int st = 0; st < 2; ++st) { mbar_init(bar_out_full(st), kEpiWarps); mbar_init(bar_out_empty(st), 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic zero-fill -> async proxy readers
@@ -212,14 +222,18 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tower_tc_kernel(const __grid
     if (warp == 0) {
         // ================= producer =================
         int it = 0;
+        // weights: two sets of nine tap slots; layer l uses set l & 1 and is loaded one layer ahead, as soon as the
+        // last tile of layer l-2 has multiplied with the slot (so a layer never starts by waiting for its weights)
+        auto load_weights = [&](int l) {
+            const int set = l & 1, use = l >> 1;
+            if (use > 0) mbar_wait(bar_w_empty(set, lane), (uint32_t)((use - 1) & 1));
+            mbar_expect_tx(bar_w_full(set, lane), kTapBytes);
+            bulk_g2s(s_w + set * kWBytes + lane * kTapBytes,
+                     reinterpret_cast<const unsigned char*>(a.layer[l].w) + (size_t)lane * kTapBytes, kTapBytes, bar_w_full(set, lane));
+        };
+        if (my_tiles > 0 && lane < 9) { load_weights(0); if (L > 1) load_weights(1); }
         for (int l = 0; l < L; ++l) {
-            if (my_tiles > 0 && lane < 9) {
-                // slot `lane` is free once the previous layer's last tile has multiplied with it
-                if (l > 0) mbar_wait(bar_w_empty(lane), (uint32_t)((l - 1) & 1));
-                mbar_expect_tx(bar_w_full(lane), kTapBytes);
-                bulk_g2s(s_w + lane * kTapBytes, reinterpret_cast<const unsigned char*>(a.layer[l].w) + (size_t)lane * kTapBytes,
-                         kTapBytes, bar_w_full(lane));
-            }
+            if (l >= 1 && l + 1 < L && my_tiles > 0 && lane < 9) load_weights(l + 1);
             __syncwarp();
             const int in_buf = a.layer[l].in_buf;
             for (int k = 0; k < my_tiles; ++k, ++it) {
@@ -261,12 +275,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tower_tc_kernel(const __grid
                     // derive every MMA's descriptor with one add (the single issuing thread is latency-bound, so the
                     // instruction count per MMA is what sets the tensor-pipe duty cycle).
                     const uint32_t a16 = (s_a + s * kStageBytes + kHalo * kRowBytes) >> 4;     // tile row 0, in 16-byte units
-                    const uint32_t w16 = s_w >> 4;
+                    const uint32_t w16 = (s_w + (uint32_t)((l & 1) * kWBytes)) >> 4;
                     uint32_t acc = 0;
 #pragma unroll
                     for (int tap = 0; tap < 9; ++tap) {
                         if (a.debug_skip & 1) break;
-                        if (k == 0) { mbar_wait(bar_w_full(tap), (uint32_t)(l & 1)); tc_fence_after(); }
+                        if (k == 0) { mbar_wait(bar_w_full(l & 1, tap), (uint32_t)((l >> 1) & 1)); tc_fence_after(); }
                         constexpr int kRow16 = kRowBytes / 16;                       // 8 sixteen-byte units per row
                         const int shift = (tap / 3 - 1) * 8 + (tap % 3 - 1);         // compile-time after unrolling
 #pragma unroll
@@ -276,9 +290,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tower_tc_kernel(const __grid
                             umma_f16_words(d, alo, blo, acc);
                             acc = 1;
                         }
-                        if (k == my_tiles - 1) umma_commit(bar_w_empty(tap));   // slot reusable by the next layer
+                        if (k == my_tiles - 1) umma_commit(bar_w_empty(l & 1, tap));   // slot reusable by layer l + 2
                     }
-                    if (a.debug_skip & 1) { if (k == my_tiles - 1) for (int tap = 0; tap < 9; ++tap) umma_commit(bar_w_empty(tap)); }
+                    if (a.debug_skip & 1) { if (k == my_tiles - 1) for (int tap = 0; tap < 9; ++tap) umma_commit(bar_w_empty(l & 1, tap)); }
                     umma_commit(bar_a_empty(s));          // smem stage reusable once the MMAs have read it
                     umma_commit(bar_acc_full(s));         // accumulator complete
                 }
@@ -315,7 +329,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tower_tc_kernel(const __grid
                     if (ly.res_buf >= 0 && !(a.debug_skip & 8)) {
                         const __half* rp = tower_board(a, ly.res_buf, g) + row_off;
 #pragma unroll
-                        for (int j = 0; j < kJ; ++j) res[j] = *reinterpret_cast<const uint4*>(rp + (((half * kJ + j) ^ sw) << 3));
+                        for (int j = 0; j < kJ; ++j) res[j] = __ldcg(reinterpret_cast<const uint4*>(rp + (((half * kJ + j) ^ sw) << 3)));   // written by bulk stores: not through L1
                     }
                     if (ly.action_table) act_scale = __fdiv_rn((float)a.action[g], (float)a.A);
                 }
@@ -336,8 +350,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tower_tc_kernel(const __grid
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(bar_acc_empty(s));        // accumulator half read: may be overwritten
-                if (g < a.n && !(a.debug_skip & 4)) {
-                    __half* dst = reinterpret_cast<__half*>(a.buf[ly.out_buf]) + (size_t)g * kBoardHalves + row_off;
+                // the output tile is staged in shared memory in the global board layout and leaves with one bulk store
+                // per board (warp 3): the epilogue never waits for global memory
+                const int st = it & 1;
+                mbar_wait(bar_out_empty(st), ((uint32_t)(it >> 1) & 1u) ^ 1u);
+                if (g < a.n) {
+                    unsigned char* dst = smem + Smem::out + st * kOutBytes + (b * kPos + p) * kRowBytes;
                     const float* atab = ly.action_table ? ly.action_table + (size_t)p * kC + half * 32 : nullptr;
 #pragma unroll
                     for (int j = 0; j < kJ; ++j) {
@@ -361,14 +379,35 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tower_tc_kernel(const __grid
                             }
                             o = make_uint4(pack_f16x2(r[0], r[1]), pack_f16x2(r[2], r[3]), pack_f16x2(r[4], r[5]), pack_f16x2(r[6], r[7]));
                         }
-                        *reinterpret_cast<uint4*>(dst + (((half * kJ + j) ^ sw) << 3)) = o;
+                        *reinterpret_cast<uint4*>(dst + (((half * kJ + j) ^ sw) << 4)) = o;
                     }
                 }
-                if (l + 1 < L) {
-                    // the next layer's bulk copy (async proxy) of this tile must see these stores
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic smem writes -> bulk-copy reader
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_out_full(st));
+            }
+        }
+    } else if (warp == 3) {
+        // ================= output store =================
+        if (lane == 0) {
+            int it = 0;
+            for (int l = 0; l < L; ++l) {
+                __half* out = reinterpret_cast<__half*>(a.buf[a.layer[l].out_buf]);
+                for (int k = 0; k < my_tiles; ++k, ++it) {
+                    const int st = it & 1;
+                    const int tile = blockIdx.x + k * gridDim.x;
+                    const int nb = min(kBoards, a.n - tile * kBoards);
+                    mbar_wait(bar_out_full(st), (uint32_t)(it >> 1) & 1u);
+                    if (!(a.debug_skip & 4)) {
+                        for (int b = 0; b < nb; ++b)
+                            bulk_s2g(out + (size_t)(tile * kBoards + b) * kBoardHalves,
+                                     s_base + Smem::out + st * kOutBytes + b * (kPos * kRowBytes), kPos * kRowBytes);
+                    }
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");      // written (not only read): the next layer loads it
                     __threadfence();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(bar_tile_done(k));
+                    mbar_arrive(bar_out_empty(st));
+                    if (l + 1 < L) mbar_arrive(bar_tile_done(k));
                 }
             }
         }
