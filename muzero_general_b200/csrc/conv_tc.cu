@@ -404,10 +404,19 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tower_tc_kernel(const __grid
                                      s_base + Smem::out + st * kOutBytes + b * (kPos * kRowBytes), kPos * kRowBytes);
                     }
                     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-                    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");      // written (not only read): the next layer loads it
-                    __threadfence();
+                    // the staging buffer is free as soon as the copy engine has READ it; the tile counts as stored
+                    // (next layer may load it) only when the writes are complete - tracked one store behind, so two
+                    // stores are in flight inside a layer, and drained at the end of every layer
+                    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
                     mbar_arrive(bar_out_empty(st));
-                    if (l + 1 < L) mbar_arrive(bar_tile_done(k));
+                    if (k > 0) {
+                        asm volatile("cp.async.bulk.wait_group 1;" ::: "memory");
+                        if (l + 1 < L) { __threadfence(); mbar_arrive(bar_tile_done(k - 1)); }
+                    }
+                    if (k == my_tiles - 1) {
+                        asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+                        if (l + 1 < L) { __threadfence(); mbar_arrive(bar_tile_done(k)); }
+                    }
                 }
             }
         }
@@ -417,6 +426,259 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tower_tc_kernel(const __grid
     __syncthreads();
     if (warp == 2)
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2 * kAccCols) : "memory");
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Resident tower: the same convolutions, but the activations of a CTA's tiles never leave shared memory between the
+// layers.  Two activation buffers B0 / B1 hold the CTA's (up to kResTiles) tiles back to back in the board layout
+// (consecutive boards are separated by their own zero padding rows, so a tap window that leaves a board only reads
+// zeros); layer l reads B[l & 1] and writes B[(l & 1) ^ 1]; the second conv of a block adds the residual IN PLACE (the
+// block input is what the output buffer still holds, and a row is read and overwritten by the same thread).  Global
+// memory is touched three times per tower: bulk loads of the input boards, the weight taps (one slot set, refilled
+// for layer l+1 while the last tile of layer l multiplies), bulk stores of the last layer's tiles.  There is no
+// activation ring, no per-tile store fence and no "tile stored" handshake: MMA(l+1, k) only waits for the epilogue
+// of (l, k); write-after-read hazards are excluded by the in-order completion of the MMAs (the epilogue of layer
+// l+2 starts after a tcgen05.commit that follows every MMA of layer l+1).
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int kResTiles = 4;
+constexpr int kResRows = kResTiles * kBoards * kPos + 2 * kHalo;      // 544
+constexpr int kResBufBytes = kResRows * kRowBytes;                    // 69632 (multiple of 1024: swizzle phase kept)
+
+struct SmemR {
+    static constexpr int w = 0;
+    static constexpr int act = kWBytes;                                    // B0 | B1
+    static constexpr int bias = act + 2 * kResBufBytes;
+    static constexpr int bars = bias + kTowerMaxLayers * kC * 4;
+    static constexpr int tmem_ptr = bars + 48 * 8;
+    static constexpr int total = tmem_ptr + 16;
+};
+static_assert(SmemR::total <= 232448, "shared memory budget");
+static_assert(SmemR::act % 1024 == 0 && kResBufBytes % 1024 == 0, "activation buffers must keep the 1024-byte swizzle phase");
+
+__global__ void __launch_bounds__(kThreads, 1) conv_tower_resident_kernel(const __grid_constant__ TowerArgs a) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t s_base = smem_u32(smem);
+    const uint32_t s_w = s_base + SmemR::w, s_act = s_base + SmemR::act;
+    float* s_bias = reinterpret_cast<float*>(smem + SmemR::bias);
+    const uint32_t bars = s_base + SmemR::bars;
+    auto bar_w_full = [&](int tap) { return bars + 8u * tap; };
+    auto bar_w_empty = [&](int tap) { return bars + 8u * (9 + tap); };
+    auto bar_in_full = [&](int k) { return bars + 8u * (18 + k); };         // input boards of my k-th tile landed
+    auto bar_tile_ready = [&](int k) { return bars + 8u * (22 + k); };      // epilogue of (layer, k) wrote its rows (one phase per layer)
+    auto bar_out_ready = [&](int k) { return bars + 8u * (26 + k); };       // last layer's rows of tile k written
+    auto bar_acc_full = [&](int s) { return bars + 8u * (30 + s); };
+    auto bar_acc_empty = [&](int s) { return bars + 8u * (32 + s); };
+    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + SmemR::tmem_ptr);
+
+    const int n_tiles = (a.n + kBoards - 1) / kBoards;
+    const int my_tiles = ((int)blockIdx.x < n_tiles) ? (n_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+    const int L = a.n_layers;
+
+    // ---- one-time setup: zero halos of both buffers, biases, barriers, TMEM
+    for (int i = threadIdx.x; i < 2 * 2 * kHalo * (kRowBytes / 16); i += kThreads) {
+        const int chunk = i % (kRowBytes / 16), r = (i / (kRowBytes / 16)) % (2 * kHalo), bf = i / ((kRowBytes / 16) * 2 * kHalo);
+        const int row = r < kHalo ? r : kResRows - 2 * kHalo + r;
+        reinterpret_cast<uint4*>(smem + SmemR::act + bf * kResBufBytes + row * kRowBytes)[chunk] = make_uint4(0, 0, 0, 0);
+    }
+    for (int i = threadIdx.x; i < L * kC; i += kThreads) {
+        const float* b = a.layer[i / kC].bias;
+        s_bias[i] = b ? b[i % kC] : 0.0f;
+    }
+    if (threadIdx.x == 0) {
+        for (int t = 0; t < 9; ++t) { mbar_init(bar_w_full(t), 1); mbar_init(bar_w_empty(t), 1); }
+        for (int k = 0; k < kResTiles; ++k) {
+            mbar_init(bar_in_full(k), 1);
+            mbar_init(bar_tile_ready(k), kEpiWarps);
+            mbar_init(bar_out_ready(k), kEpiWarps);
+        }
+        for (int s = 0; s < 2; ++s) { mbar_init(bar_acc_full(s), 1); mbar_init(bar_acc_empty(s), kEpiWarps); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                     ::"r"(s_base + SmemR::tmem_ptr), "r"(2 * kAccCols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ================= producer: weights of every layer, input boards once =================
+        if (my_tiles > 0 && lane < 9) {
+            mbar_expect_tx(bar_w_full(lane), kTapBytes);
+            bulk_g2s(s_w + lane * kTapBytes, reinterpret_cast<const unsigned char*>(a.layer[0].w) + (size_t)lane * kTapBytes, kTapBytes,
+                     bar_w_full(lane));
+        }
+        __syncwarp();
+        const int in_buf = a.layer[0].in_buf;
+        for (int k = 0; k < my_tiles; ++k) {
+            const int tile = blockIdx.x + k * gridDim.x;
+            const int nb = min(kBoards, a.n - tile * kBoards);
+            if (lane == 0) mbar_expect_tx(bar_in_full(k), (uint32_t)nb * kPos * kRowBytes);
+            __syncwarp();
+            if (lane < nb)
+                bulk_g2s(s_act + (kHalo + (k * kBoards + lane) * kPos) * kRowBytes, tower_board(a, in_buf, tile * kBoards + lane),
+                         kPos * kRowBytes, bar_in_full(k));
+        }
+        for (int l = 1; l < L; ++l) {
+            if (my_tiles > 0 && lane < 9) {
+                mbar_wait(bar_w_empty(lane), (uint32_t)((l - 1) & 1));        // last tile of layer l-1 is done with this tap
+                mbar_expect_tx(bar_w_full(lane), kTapBytes);
+                bulk_g2s(s_w + lane * kTapBytes, reinterpret_cast<const unsigned char*>(a.layer[l].w) + (size_t)lane * kTapBytes,
+                         kTapBytes, bar_w_full(lane));
+            }
+            __syncwarp();
+        }
+    } else if (warp == 1) {
+        // ================= MMA issuer =================
+        int it = 0;
+        for (int l = 0; l < L; ++l) {
+            for (int k = 0; k < my_tiles; ++k, ++it) {
+                const int s = it & 1;
+                const uint32_t ph = (uint32_t)(it >> 1) & 1u;
+                if (l == 0) mbar_wait(bar_in_full(k), 0);
+                else mbar_wait(bar_tile_ready(k), (uint32_t)((l - 1) & 1));
+                mbar_wait(bar_acc_empty(s), ph ^ 1);
+                tc_fence_after();
+                if (elect_one()) {
+                    const uint32_t d = tmem_base + (uint32_t)(s * kAccCols);
+                    const uint32_t a16 = (s_act + (uint32_t)((l & 1) * kResBufBytes + (kHalo + k * kBoards * kPos) * kRowBytes)) >> 4;
+                    const uint32_t w16 = s_w >> 4;
+                    uint32_t acc = 0;
+#pragma unroll
+                    for (int tap = 0; tap < 9; ++tap) {
+                        if (a.debug_skip & 1) break;
+                        if (k == 0) { mbar_wait(bar_w_full(tap), (uint32_t)(l & 1)); tc_fence_after(); }
+                        constexpr int kRow16 = kRowBytes / 16;
+                        const int shift = (tap / 3 - 1) * 8 + (tap % 3 - 1);
+#pragma unroll
+                        for (int ks = 0; ks < kC / 16; ++ks) {
+                            const uint32_t alo = ((a16 + (uint32_t)(shift * kRow16 + ks * 2)) & 0x3FFFu) | kDescLoFlags;
+                            const uint32_t blo = ((w16 + (uint32_t)(tap * (kTapBytes / 16) + ks * 2)) & 0x3FFFu) | kDescLoFlags;
+                            umma_f16_words(d, alo, blo, acc);
+                            acc = 1;
+                        }
+                        if (k == my_tiles - 1) umma_commit(bar_w_empty(tap));
+                    }
+                    if (a.debug_skip & 1) { if (k == my_tiles - 1) for (int tap = 0; tap < 9; ++tap) umma_commit(bar_w_empty(tap)); }
+                    umma_commit(bar_acc_full(s));
+                }
+                __syncwarp();
+            }
+        }
+    } else if (warp == 3) {
+        // ================= output store: the last layer's tiles leave as bulk copies =================
+        if (lane == 0) {
+            __half* out = reinterpret_cast<__half*>(a.buf[a.layer[L - 1].out_buf]);
+            const uint32_t src = s_act + (uint32_t)((((L - 1) & 1) ^ 1) * kResBufBytes + kHalo * kRowBytes);
+            for (int k = 0; k < my_tiles; ++k) {
+                const int tile = blockIdx.x + k * gridDim.x;
+                const int nb = min(kBoards, a.n - tile * kBoards);
+                mbar_wait(bar_out_ready(k), 0);
+                if (!(a.debug_skip & 4))
+                    for (int b = 0; b < nb; ++b)
+                        bulk_s2g(out + (size_t)(tile * kBoards + b) * kBoardHalves, src + (uint32_t)((k * kBoards + b) * kPos * kRowBytes),
+                                 kPos * kRowBytes);
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
+            asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+        }
+    } else if (warp >= 4) {
+        // ================= epilogue =================
+        const int q = warp & 3;                       // TMEM lane quarter
+        const int half = (warp - 4) >> 2;             // accumulator columns [32*half, 32*half+32)
+        const int row = q * 32 + lane;                // tile row = TMEM lane
+        const int b = row / kPos, p = row % kPos;
+        const int y = p / 8 - 1, x = p % 8;
+        const bool inside = (y >= 0 && y < a.H && x < a.W);
+        constexpr int kJ = kPlanes / 2;               // 16-byte chunks (8 channels) handled by this warp: 32 channels
+        const int sw = p & 7;                         // chunk c of the row is stored at chunk c ^ sw
+        int it = 0;
+        for (int l = 0; l < L; ++l) {
+            const TowerLayer& ly = a.layer[l];
+            const float* bias = s_bias + l * kC + half * 32;
+            const bool last = l == L - 1;
+            for (int k = 0; k < my_tiles; ++k, ++it) {
+                const int tile = blockIdx.x + k * gridDim.x;
+                const int s = it & 1;
+                const uint32_t ph = (uint32_t)(it >> 1) & 1u;
+                const int g = tile * kBoards + b;
+                const bool live = inside && g < a.n;
+                // this thread's row in the output buffer (residual source and destination)
+                unsigned char* orow = smem + SmemR::act + ((l & 1) ^ 1) * kResBufBytes + (kHalo + k * kBoards * kPos + row) * kRowBytes;
+                float act_scale = 0.0f;
+                if (live && ly.action_table) act_scale = __fdiv_rn((float)a.action[g], (float)a.A);
+                mbar_wait(bar_acc_full(s), ph);
+                tc_fence_after();
+                uint32_t v[32];
+                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(s * kAccCols + half * 32);
+                asm volatile(
+                    "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                    "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                    "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                    : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                      "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+                      "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+                      "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                    : "r"(taddr));
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_acc_empty(s));        // accumulator half read: may be overwritten
+                const float* atab = ly.action_table ? ly.action_table + (size_t)p * kC + half * 32 : nullptr;
+#pragma unroll
+                for (int j = 0; j < kJ; ++j) {
+                    uint4* slot = reinterpret_cast<uint4*>(orow + (((half * kJ + j) ^ sw) << 4));
+                    uint4 o = make_uint4(0, 0, 0, 0);
+                    if (live) {
+                        uint4 res = make_uint4(0, 0, 0, 0);
+                        if (ly.res_buf >= 0) res = *slot;               // block input, added in place
+                        float r[8];
+                        const uint32_t rw[4] = {res.x, res.y, res.z, res.w};
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const float2 rf = unpack_f16x2(rw[e]);
+                            r[2 * e + 0] = __uint_as_float(v[8 * j + 2 * e + 0]) + bias[8 * j + 2 * e + 0] + rf.x;
+                            r[2 * e + 1] = __uint_as_float(v[8 * j + 2 * e + 1]) + bias[8 * j + 2 * e + 1] + rf.y;
+                        }
+                        if (atab) {
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) r[e] = fmaf(act_scale, atab[8 * j + e], r[e]);
+                        }
+                        if (ly.relu) {
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) r[e] = fmaxf(r[e], 0.0f);
+                        }
+                        o = make_uint4(pack_f16x2(r[0], r[1]), pack_f16x2(r[2], r[3]), pack_f16x2(r[4], r[5]), pack_f16x2(r[6], r[7]));
+                    }
+                    *slot = o;                                         // zeros on padding rows and missing boards
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic smem writes -> tcgen05 / bulk-copy readers
+                __syncwarp();
+                if (lane == 0) mbar_arrive(last ? bar_out_ready(k) : bar_tile_ready(k));
+            }
+        }
+    }
+    // ---- teardown
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2 * kAccCols) : "memory");
+}
+
+// the resident kernel needs the block structure: every residual is the input of the layer before, buffers alternate
+static bool tower_is_resident_shape(const TowerArgs& a, int tiles_per_cta) {
+    if (a.n_layers < 2 || tiles_per_cta > kResTiles) return false;
+    for (int l = 0; l < a.n_layers; ++l) {
+        const TowerLayer& t = a.layer[l];
+        if (l > 0 && t.in_buf != a.layer[l - 1].out_buf) return false;
+        if (t.res_buf >= 0 && (l == 0 || t.res_buf != a.layer[l - 1].in_buf)) return false;
+    }
+    return true;
 }
 
 static int tower_ctas_per_sm() {
@@ -448,6 +710,19 @@ cudaError_t launch_conv_tower_tc(const TowerArgs& a, int sm_count, cudaStream_t 
     const int slots = sm_count * tower_ctas_per_sm();
     const int grid = n_tiles < slots ? n_tiles : slots;
     if (a.n_layers > 1 && (n_tiles + grid - 1) / grid > kTowerMaxTiles) return cudaErrorInvalidConfiguration;
+    const char* nr = getenv("MZ_TC_NO_RESIDENT");            // A/B switch (tests compare both kernels)
+    const bool no_resident = nr && nr[0] == '1';
+    if (!no_resident && tower_is_resident_shape(a, (n_tiles + sm_count - 1) / sm_count)) {
+        static bool attr_r = false;
+        if (!attr_r) {
+            cudaError_t e = cudaFuncSetAttribute(conv_tower_resident_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SmemR::total);
+            if (e != cudaSuccess) return e;
+            attr_r = true;
+        }
+        const int grid_r = n_tiles < sm_count ? n_tiles : sm_count;
+        conv_tower_resident_kernel<<<grid_r, kThreads, SmemR::total, stream>>>(a);
+        return cudaGetLastError();
+    }
     conv_tower_tc_kernel<<<grid, kThreads, Smem::total, stream>>>(a);
     return cudaGetLastError();
 }

@@ -165,3 +165,31 @@ def test_fused_cuda_core_tower_is_bit_identical_to_per_layer_launches(name, n, g
     assert numpy.array_equal(sa.visit_counts, sb.visit_counts)
     assert numpy.array_equal(sa.root_value, sb.root_value)
     assert lb1 < la1 and lb0 < la0, "fused path must need fewer launches"
+
+
+@pytest.mark.parametrize("n", [5, 300, 1024])
+def test_resident_tower_is_bit_identical_to_streaming_tower(n, game_configs, monkeypatch):
+    """conv_tower_resident_kernel (activations stay in shared memory between layers) and conv_tower_tc_kernel
+    (activations round-trip through L2) perform the same fp16 x fp16 -> fp32 MMAs and the same epilogue arithmetic."""
+    cfg = game_configs["connect4"]
+    spec = netspec_from_config(cfg)
+    rs = numpy.random.RandomState(11)
+    obs = rs.random_sample((n, spec.obs_elems)).astype(numpy.float32)
+    actions = rs.randint(0, spec.action_space, size=n)
+    outs = []
+    for flag in ("1", "0"):
+        monkeypatch.setenv("MZ_NO_TC", "0")
+        monkeypatch.setenv("MZ_TC_NO_RESIDENT", flag)
+        eng = _engine(cfg, n, 6)
+        eng.load_weights(weights_for("connect4", spec))
+        r0 = eng.initial_inference(obs)
+        r1 = eng.recurrent_inference(r0["hidden"], actions)
+        res = eng.search(obs=obs, add_exploration_noise=False)
+        outs.append((r0, r1, res))
+        eng.close()
+    (a0, a1, sa), (b0, b1, sb) = outs
+    for k in ("hidden", "value_logits", "policy_logits", "value"):
+        assert numpy.array_equal(a0[k], b0[k]), k
+    for k in ("hidden", "value_logits", "policy_logits", "reward_logits", "value", "reward"):
+        assert numpy.array_equal(a1[k], b1[k]), k
+    assert numpy.array_equal(sa.visit_counts, sb.visit_counts)
