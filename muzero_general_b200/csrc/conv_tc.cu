@@ -30,6 +30,7 @@
 
 #include "pipeline.h"
 #include "conv_tc.h"
+#include "launch.h"
 
 namespace mz {
 
@@ -218,6 +219,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tower_tc_kernel(const __grid
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_launch_dependents();
+    pdl_wait();
 
     if (warp == 0) {
         // ================= producer =================
@@ -489,10 +492,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tower_resident_kernel(const 
         for (int t = 0; t < 9; ++t) { mbar_init(bar_w_full(t), 1); mbar_init(bar_w_empty(t), 1); }
         for (int k = 0; k < kResTiles; ++k) {
             mbar_init(bar_in_full(k), 1);
-            mbar_init(bar_tile_ready(k), kEpiWarps);
-            mbar_init(bar_out_ready(k), kEpiWarps);
+            mbar_init(bar_tile_ready(k), kEpiWarps / 2);
+            mbar_init(bar_out_ready(k), kEpiWarps / 2);
         }
-        for (int s = 0; s < 2; ++s) { mbar_init(bar_acc_full(s), 1); mbar_init(bar_acc_empty(s), kEpiWarps); }
+        for (int s = 0; s < 2; ++s) { mbar_init(bar_acc_full(s), 1); mbar_init(bar_acc_empty(s), kEpiWarps / 2); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -508,11 +511,13 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tower_resident_kernel(const 
 
     if (warp == 0) {
         // ================= producer: weights of every layer, input boards once =================
+        pdl_launch_dependents();
         if (my_tiles > 0 && lane < 9) {
             mbar_expect_tx(bar_w_full(lane), kTapBytes);
             bulk_g2s(s_w + lane * kTapBytes, reinterpret_cast<const unsigned char*>(a.layer[0].w) + (size_t)lane * kTapBytes, kTapBytes,
                      bar_w_full(lane));
         }
+        pdl_wait();                                    // weights are constants; the boards come from the previous kernel
         __syncwarp();
         const int in_buf = a.layer[0].in_buf;
         for (int k = 0; k < my_tiles; ++k) {
@@ -588,23 +593,26 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tower_resident_kernel(const 
             asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
         }
     } else if (warp >= 4) {
-        // ================= epilogue =================
+        // ================= epilogue: two groups of four warps, group s owns accumulator stage s =================
+        pdl_wait();                                    // reads a.action (written by the tree kernel)
+        // (consecutive tiles are drained by different groups, so the wait -> tcgen05.ld -> store -> fence -> arrive
+        // chain of one tile overlaps the next tile's)
         const int q = warp & 3;                       // TMEM lane quarter
-        const int half = (warp - 4) >> 2;             // accumulator columns [32*half, 32*half+32)
+        const int grp = (warp - 4) >> 2;              // tiles with (it & 1) == grp
         const int row = q * 32 + lane;                // tile row = TMEM lane
         const int b = row / kPos, p = row % kPos;
         const int y = p / 8 - 1, x = p % 8;
         const bool inside = (y >= 0 && y < a.H && x < a.W);
-        constexpr int kJ = kPlanes / 2;               // 16-byte chunks (8 channels) handled by this warp: 32 channels
         const int sw = p & 7;                         // chunk c of the row is stored at chunk c ^ sw
         int it = 0;
         for (int l = 0; l < L; ++l) {
             const TowerLayer& ly = a.layer[l];
-            const float* bias = s_bias + l * kC + half * 32;
+            const float* bias = s_bias + l * kC;
             const bool last = l == L - 1;
             for (int k = 0; k < my_tiles; ++k, ++it) {
+                if ((it & 1) != grp) continue;
                 const int tile = blockIdx.x + k * gridDim.x;
-                const int s = it & 1;
+                const int s = grp;
                 const uint32_t ph = (uint32_t)(it >> 1) & 1u;
                 const int g = tile * kBoards + b;
                 const bool live = inside && g < a.n;
@@ -614,25 +622,29 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tower_resident_kernel(const 
                 if (live && ly.action_table) act_scale = __fdiv_rn((float)a.action[g], (float)a.A);
                 mbar_wait(bar_acc_full(s), ph);
                 tc_fence_after();
-                uint32_t v[32];
-                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(s * kAccCols + half * 32);
-                asm volatile(
-                    "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-                    "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-                    "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-                    : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-                      "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
-                      "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
-                      "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-                    : "r"(taddr));
+                uint32_t v[64];
+                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(s * kAccCols);
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    uint32_t* w = v + 32 * h;
+                    asm volatile(
+                        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                        : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7]),
+                          "=r"(w[8]), "=r"(w[9]), "=r"(w[10]), "=r"(w[11]), "=r"(w[12]), "=r"(w[13]), "=r"(w[14]), "=r"(w[15]),
+                          "=r"(w[16]), "=r"(w[17]), "=r"(w[18]), "=r"(w[19]), "=r"(w[20]), "=r"(w[21]), "=r"(w[22]), "=r"(w[23]),
+                          "=r"(w[24]), "=r"(w[25]), "=r"(w[26]), "=r"(w[27]), "=r"(w[28]), "=r"(w[29]), "=r"(w[30]), "=r"(w[31])
+                        : "r"(taddr + (uint32_t)(32 * h)));
+                }
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(bar_acc_empty(s));        // accumulator half read: may be overwritten
-                const float* atab = ly.action_table ? ly.action_table + (size_t)p * kC + half * 32 : nullptr;
+                if (lane == 0) mbar_arrive(bar_acc_empty(s));        // accumulator rows read: may be overwritten
+                const float* atab = ly.action_table ? ly.action_table + (size_t)p * kC : nullptr;
 #pragma unroll
-                for (int j = 0; j < kJ; ++j) {
-                    uint4* slot = reinterpret_cast<uint4*>(orow + (((half * kJ + j) ^ sw) << 4));
+                for (int j = 0; j < kPlanes; ++j) {
+                    uint4* slot = reinterpret_cast<uint4*>(orow + ((j ^ sw) << 4));
                     uint4 o = make_uint4(0, 0, 0, 0);
                     if (live) {
                         uint4 res = make_uint4(0, 0, 0, 0);
@@ -720,11 +732,11 @@ cudaError_t launch_conv_tower_tc(const TowerArgs& a, int sm_count, cudaStream_t 
             attr_r = true;
         }
         const int grid_r = n_tiles < sm_count ? n_tiles : sm_count;
-        conv_tower_resident_kernel<<<grid_r, kThreads, SmemR::total, stream>>>(a);
-        return cudaGetLastError();
+        cudaError_t e = launch_chained(conv_tower_resident_kernel, dim3(grid_r), dim3(kThreads), SmemR::total, stream, a);
+        return e != cudaSuccess ? e : cudaGetLastError();
     }
-    conv_tower_tc_kernel<<<grid, kThreads, Smem::total, stream>>>(a);
-    return cudaGetLastError();
+    cudaError_t e = launch_chained(conv_tower_tc_kernel, dim3(grid), dim3(kThreads), Smem::total, stream, a);
+    return e != cudaSuccess ? e : cudaGetLastError();
 }
 
 int conv_tc_max_boards_fused(int sm_count) { return sm_count * kTowerMaxTiles * kBoards; }   // conservative: one CTA per SM

@@ -27,6 +27,7 @@
 #include "common.cuh"
 #include "ktimer.h"
 #include "small_tower.h"
+#include "launch.h"
 #include "conv_tc.h"
 #include "pipeline.h"
 
@@ -247,12 +248,14 @@ __global__ void __launch_bounds__(kHeadThreads) heads_kernel(const __grid_consta
     float* s_sc = s_lo + C;                                          // [C] channel scale
     float* s_part = s_sc + C;                                        // [2][2][C] partial extrema
     float* s_act = s_part + 4 * C;                                   // per head: ping | pong
+    pdl_launch_dependents();
     {
         const float4* src = reinterpret_cast<const float4*>(a.blob + a.w_lo);
         float4* dst = reinterpret_cast<float4*>(s_w);
         for (int i = threadIdx.x; i < a.w_floats / 4; i += blockDim.x) dst[i] = src[i];
     }
     __syncthreads();
+    pdl_wait();                                                      // the weights are constants; x comes from the previous kernel
     const float* blob = s_w - a.w_lo;                                // blob[off] addresses the staged copy
     const int cj = C >> 3;                                           // 8-channel chunks per position (P64S path)
 
@@ -967,9 +970,9 @@ struct Runner {
         int grid = (n + threads / kHeadGroup - 1) / (threads / kHeadGroup);
         if (grid > r->sm_count) grid = r->sm_count;
         kt_begin(KT_HEADS, stream);
-        heads_kernel<<<grid, threads, smem, stream>>>(a);
+        cudaError_t e = launch_chained(heads_kernel, dim3(grid), dim3(threads), smem, stream, a);
         kt_end(stream);
-        cudaError_t e = cudaGetLastError();
+        if (e == cudaSuccess) e = cudaGetLastError();
         if (e != cudaSuccess) return fail("heads launch", e);
         *launches += 1;
         return true;

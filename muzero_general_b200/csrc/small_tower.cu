@@ -13,6 +13,7 @@
 // for CO channels (P x CO accumulators); CO = 4 when the batch is large enough to fill the GPU that way (float4
 // weight loads, 4.5+ FMAs per shared-memory load), CO = 1 for small batches (4x the threads, lower latency).
 #include "small_tower.h"
+#include "launch.h"
 
 #include <algorithm>
 
@@ -33,6 +34,7 @@ __global__ void __launch_bounds__(kMaxThreads) small_tower_kernel(const __grid_c
     float* s_act = smem + a.w_floats;
 
     // ---- once per CTA: weights + biases of every layer, zeroed activation buffers (padding stays zero)
+    pdl_launch_dependents();
     for (int l = 0; l < a.n_layers; ++l) {
         const int count = a.layer[l].cin * 9 * C;
         const float4* src = reinterpret_cast<const float4*>(a.blob + a.layer[l].w_off);
@@ -42,6 +44,7 @@ __global__ void __launch_bounds__(kMaxThreads) small_tower_kernel(const __grid_c
             s_w[a.b_smem_off[l] + i] = a.layer[l].b_off >= 0 ? a.blob[a.layer[l].b_off + i] : 0.0f;
     }
     for (int i = threadIdx.x; i < 2 * bufsz; i += blockDim.x) s_act[i] = 0.0f;
+    pdl_wait();                                            // weights are constants; the input comes from the previous kernel
 
     const int cgs = C / CO;
     const int items_per_board = cgs * H;
@@ -182,8 +185,8 @@ cudaError_t launch(const SmallTowerArgs& a, const Plan& pl, cudaStream_t stream)
         if (e != cudaSuccess) return e;
         attr = pl.smem;
     }
-    small_tower_kernel<P, CO><<<pl.grid, pl.threads, pl.smem, stream>>>(a);
-    return cudaGetLastError();
+    cudaError_t e = launch_chained(small_tower_kernel<P, CO>, dim3(pl.grid), dim3(pl.threads), pl.smem, stream, a);
+    return e != cudaSuccess ? e : cudaGetLastError();
 }
 }  // namespace
 

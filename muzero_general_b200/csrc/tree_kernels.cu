@@ -10,6 +10,7 @@
 #include "kernels.h"
 #include "pipeline.h"
 #include "tree.cuh"
+#include "launch.h"
 
 namespace mz {
 
@@ -17,6 +18,8 @@ namespace mz {
 // throughput): selection uses the single-round-trip + L1-prefetch variant of tree_select (tree.cuh).
 template <int G, bool kLatency>
 __global__ void __launch_bounds__(128) tree_step_kernel(const __grid_constant__ TreeStepArgs a) {
+    pdl_launch_dependents();
+    pdl_wait();                                   // everything below reads what the network kernels just wrote
     const int g = (blockIdx.x * blockDim.x + threadIdx.x) / G;
     if (g >= a.n) return;
     const int lane = LaneGroup<G>::lane();
@@ -139,17 +142,18 @@ cudaError_t launch_tree_step(const TreeStepArgs& a, cudaStream_t stream) {
     const int grid = (a.n + games_per_cta - 1) / games_per_cta;
     // below ~4 resident warps per scheduler the kernel is latency-bound
     const bool latency = (long)a.n * G <= 148L * 512;
+    cudaError_t e = cudaSuccess;
 #define MZ_TREE(GG)                                                                                 \
     case GG:                                                                                        \
-        if (latency) tree_step_kernel<GG, true><<<grid, threads, 0, stream>>>(a);                   \
-        else tree_step_kernel<GG, false><<<grid, threads, 0, stream>>>(a);                          \
+        e = latency ? launch_chained(tree_step_kernel<GG, true>, dim3(grid), dim3(threads), 0, stream, a)      \
+                    : launch_chained(tree_step_kernel<GG, false>, dim3(grid), dim3(threads), 0, stream, a);    \
         break;
     switch (G) {
         MZ_TREE(4) MZ_TREE(8) MZ_TREE(16) MZ_TREE(32)
         default: return cudaErrorInvalidValue;
     }
 #undef MZ_TREE
-    return cudaGetLastError();
+    return e != cudaSuccess ? e : cudaGetLastError();
 }
 
 }  // namespace mz

@@ -193,3 +193,29 @@ def test_resident_tower_is_bit_identical_to_streaming_tower(n, game_configs, mon
     for k in ("hidden", "value_logits", "policy_logits", "reward_logits", "value", "reward"):
         assert numpy.array_equal(a1[k], b1[k]), k
     assert numpy.array_equal(sa.visit_counts, sb.visit_counts)
+
+
+@pytest.mark.parametrize("name,n,N", [("connect4", 64, 30), ("tictactoe", 200, 25)])
+def test_graph_replay_and_dependent_launch_do_not_change_results(name, n, N, game_configs, monkeypatch):
+    """CUDA-graph replay and programmatic dependent launch only change WHEN kernels start: a search repeated three
+    times (eager, capture, replay) with and without them gives identical visit counts and root values."""
+    cfg = game_configs[name]
+    spec = netspec_from_config(cfg)
+    rs = numpy.random.RandomState(3)
+    obs = rs.random_sample((n, spec.obs_elems)).astype(numpy.float32)
+    results = []
+    for no_graph, no_pdl in (("1", "1"), ("0", "1"), ("0", "0")):
+        monkeypatch.setenv("MZ_NO_TC", "0")
+        monkeypatch.setenv("MZ_NO_GRAPH", no_graph)
+        monkeypatch.setenv("MZ_NO_PDL", no_pdl)
+        eng = _engine(cfg, n, N)
+        eng.load_weights(weights_for(name, spec))
+        runs = [eng.search(obs=obs, add_exploration_noise=False) for _ in range(3)]
+        for r in runs[1:]:
+            assert numpy.array_equal(r.visit_counts, runs[0].visit_counts)
+            assert numpy.array_equal(r.root_value, runs[0].root_value)
+        results.append(runs[0])
+        eng.close()
+    for r in results[1:]:
+        assert numpy.array_equal(r.visit_counts, results[0].visit_counts)
+        assert numpy.array_equal(r.root_value, results[0].root_value)
