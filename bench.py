@@ -56,7 +56,7 @@ NET_FLOPS = {"cartpole": (1312.0, 2752.0), "tictactoe": (1.880e5, 2.315e5), "con
 
 
 # measured DRAM bytes per launch of the dominant kernel (ncu --set full, profiles/): fc_search / conv tower
-TRAFFIC = {"connect4": 8962560 + 127232}
+TRAFFIC = {"connect4": None}
 
 
 def conv3x3_flops(spec, N):
@@ -386,8 +386,9 @@ def main():
                         "kernel_split": split,
                         "step_level": {"algorithmic_flops_per_step": flops, "achieved": flops / kern_s / 1e12,
                                        "frac": flops / kern_s / 1e12 / bf16_peak},
-                        "note": ("fp16 operands, fp32 accumulate on tcgen05; 84 of 128 rows of every MMA are real board "
-                                 "positions" if dominant == "conv_tower_tc_kernel" else
+                        "note": ("tcgen05 towers: conv_tower_resident_kernel up to 1184 boards per launch (activations stay in "
+                                 "shared memory), conv_tower_tc_kernel above; fp16 operands, fp32 accumulate; 84 of 128 rows "
+                                 "of every MMA are real board positions" if dominant == "conv_tower_tc_kernel" else
                                  "fp32 CUDA-core direct convolution (strict numerics): the tensor peak is not reachable by design")}
         out = {
             "metric": "self-play env-steps/sec", "value": value, "unit": "env-steps/s", "n_gpus": world,

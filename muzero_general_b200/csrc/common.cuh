@@ -44,6 +44,14 @@ MZ_DEVINL double shfl_f64(unsigned mask, double v, int src, int width) {
 }
 
 // smallest power of two >= n (n >= 1)
+// d / sc (IEEE round-to-nearest) for sc > 0.  A zero numerator - every channel minimum, every ReLU zero - sends
+// div.rn.f32 down its out-of-line slow path (FCHK rejects zero / denormal operands) and the whole warp waits for it;
+// 0 / sc is +0 anyway, so divide a harmless 1.0 instead and select.
+MZ_DEVINL float div_pos_or_zero(float d, float sc) {
+    const float q = __fdiv_rn(d == 0.0f ? 1.0f : d, sc);
+    return d == 0.0f ? 0.0f : q;
+}
+
 // hint: bring the line holding *p into L1 (no register, no dependency)
 MZ_DEVINL void prefetch_l1(const void* p) { asm volatile("prefetch.L1 [%0];" ::"l"(p)); }
 

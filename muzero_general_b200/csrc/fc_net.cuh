@@ -169,7 +169,7 @@ MZ_DEVINL void rescale_unit_range(const float* x, float* out, int n) {
     float sc = __fsub_rn(hi, lo);
     if (sc < 1e-5f) sc = __fadd_rn(sc, 1e-5f);
     const int n4 = (n + 3) & ~3;
-    for (int i = lane; i < n4; i += G) out[i] = (i < n) ? __fdiv_rn(__fsub_rn(x[i], lo), sc) : 0.0f;
+    for (int i = lane; i < n4; i += G) out[i] = (i < n) ? div_pos_or_zero(__fsub_rn(x[i], lo), sc) : 0.0f;
     LaneGroup<G>::sync();
 }
 

@@ -313,10 +313,10 @@ __global__ void __launch_bounds__(kHeadThreads) heads_kernel(const __grid_consta
 #pragma unroll
                     for (int q = 0; q < 2; ++q) {
                         const float4 x4 = xr[q], l4 = lr[q], c4 = sr[q];
-                        v[4 * q + 0] = __fdiv_rn(__fsub_rn(x4.x, l4.x), c4.x);
-                        v[4 * q + 1] = __fdiv_rn(__fsub_rn(x4.y, l4.y), c4.y);
-                        v[4 * q + 2] = __fdiv_rn(__fsub_rn(x4.z, l4.z), c4.z);
-                        v[4 * q + 3] = __fdiv_rn(__fsub_rn(x4.w, l4.w), c4.w);
+                        v[4 * q + 0] = div_pos_or_zero(__fsub_rn(x4.x, l4.x), c4.x);
+                        v[4 * q + 1] = div_pos_or_zero(__fsub_rn(x4.y, l4.y), c4.y);
+                        v[4 * q + 2] = div_pos_or_zero(__fsub_rn(x4.z, l4.z), c4.z);
+                        v[4 * q + 3] = div_pos_or_zero(__fsub_rn(x4.w, l4.w), c4.w);
                     }
                     if (a.rescaled) {
 #pragma unroll
@@ -334,7 +334,7 @@ __global__ void __launch_bounds__(kHeadThreads) heads_kernel(const __grid_consta
             } else {
                 for (int i = t; i < C * HW; i += kHeadGroup) {
                     const int c = i / HW, p = i % HW;
-                    const float v = __fdiv_rn(__fsub_rn(s_x[p * CP + c], s_lo[c]), s_sc[c]);
+                    const float v = div_pos_or_zero(__fsub_rn(s_x[p * CP + c], s_lo[c]), s_sc[c]);
                     if (a.rescaled) a.rescaled[(size_t)g * C * HW + i] = v;
                     if (a.pool_hidden) a.pool_hidden[((size_t)g * a.pool_stride + a.out_slot) * C * HW + i] = v;
                 }

@@ -64,7 +64,13 @@ struct Leaf {
 
 MZ_DEVINL double value_range_normalize(double v, double lo, double hi) {
     // MinMaxStats.normalize, self_play.py:566-570
-    if (hi > lo) return __ddiv_rn(__dsub_rn(v, lo), __dsub_rn(hi, lo));
+    if (hi > lo) {
+        // the node that set the lower bound has v == lo: a zero numerator would send the division down its out-of-line
+        // slow path (and the whole warp with it); 0 / (hi - lo) is +0, so divide a harmless 1.0 and select
+        const double d = __dsub_rn(v, lo);
+        const double q = __ddiv_rn(d == 0.0 ? 1.0 : d, __dsub_rn(hi, lo));
+        return d == 0.0 ? 0.0 : q;
+    }
     return v;
 }
 
@@ -80,7 +86,7 @@ MZ_DEVINL float group_softmax_masked(float logit, bool valid) {
     const float m = group_max_f32<G>(valid ? logit : -INFINITY);
     const float e = valid ? expf(logit - m) : 0.0f;
     const float s = group_sum_f32<G>(e);
-    return __fdiv_rn(e, s);
+    return div_pos_or_zero(e, s);          // masked lanes (e = 0) must not drag the warp through the division slow path
 }
 
 template <int G>
