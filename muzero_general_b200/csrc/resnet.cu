@@ -231,14 +231,20 @@ __device__ __forceinline__ int p64c4_index(int c, int p, int W) {
 // float4 activations; index arithmetic with runtime divisors happens once per chunk, not per element.
 // The accumulation order of every dot product is ascending input index (as torch's reference loops are
 // compared with a tolerance anyway, this only keeps results independent of the vector width).
-constexpr int kHeadGroup = 128;
+// GROUP = 128 threads per sample for wide states (Connect4: 64 x 42), GROUP = 32 (one warp per sample, __syncwarp
+// instead of named barriers, 4x the samples in flight) when a sample is only a few hundred values (TicTacToe 16 x 9,
+// Breakout's 16 x 36 hidden board).
 constexpr int kHeadThreads = 1024;
 
+template <int GROUP>
 __device__ __forceinline__ void group_bar(int group) {
-    asm volatile("bar.sync %0, %1;" ::"r"(group + 1), "r"(kHeadGroup) : "memory");
+    if constexpr (GROUP == 32) __syncwarp();
+    else asm volatile("bar.sync %0, %1;" ::"r"(group + 1), "r"(GROUP) : "memory");
 }
 
+template <int GROUP>
 __global__ void __launch_bounds__(kHeadThreads) heads_kernel(const __grid_constant__ HeadsArgs a) {
+    constexpr int kHeadGroup = GROUP;
     extern __shared__ __align__(16) float sm[];
     const int C = a.C, HW = a.HW, CP = C + 4;
     const int group = threadIdx.x / kHeadGroup, t = threadIdx.x % kHeadGroup, ngroups = blockDim.x / kHeadGroup;
@@ -278,7 +284,7 @@ __global__ void __launch_bounds__(kHeadThreads) heads_kernel(const __grid_consta
             const float* x = a.x + (size_t)g * C * HW;
             for (int i = t; i < C * HW; i += kHeadGroup) s_x[(i % HW) * CP + i / HW] = x[i];
         }
-        group_bar(group);
+        group_bar<GROUP>(group);
 
         if (a.rescaled || a.pool_hidden || a.state_p64c4) {
             // (x - min) / scale per channel over the positions (models.py:530-553).
@@ -292,7 +298,7 @@ __global__ void __launch_bounds__(kHeadThreads) heads_kernel(const __grid_consta
                 s_part[(part * 2) * C + c] = lo;
                 s_part[(part * 2 + 1) * C + c] = hi;
             }
-            group_bar(group);
+            group_bar<GROUP>(group);
             for (int c = t; c < C; c += kHeadGroup) {
                 float lo = s_part[c], hi = s_part[C + c];
                 if (parts == 2) { lo = fminf(lo, s_part[2 * C + c]); hi = fmaxf(hi, s_part[3 * C + c]); }
@@ -300,7 +306,7 @@ __global__ void __launch_bounds__(kHeadThreads) heads_kernel(const __grid_consta
                 if (sc < 1e-5f) sc = __fadd_rn(sc, 1e-5f);
                 s_lo[c] = lo; s_sc[c] = sc;
             }
-            group_bar(group);
+            group_bar<GROUP>(group);
             // Phase B: normalise and store
             if (a.p64c4) {
                 for (int i = t; i < cj * HW; i += kHeadGroup) {
@@ -376,7 +382,7 @@ __global__ void __launch_bounds__(kHeadThreads) heads_kernel(const __grid_consta
                 }
             }
             if (u < 4) { const int i = d.rc * HW + u; if (i < ((d.rc * HW + 3) & ~3)) cur[i] = 0.0f; }   // zero the padding
-            group_bar(group);
+            group_bar<GROUP>(group);
             const int max_layers = max(a.head[0].mlp.n, a.head[a.n_heads - 1].mlp.n);
             for (int l = 0; l < max_layers; ++l) {
                 if (l < d.mlp.n) {
@@ -403,16 +409,23 @@ __global__ void __launch_bounds__(kHeadThreads) heads_kernel(const __grid_consta
                     }
                     float* tmp = cur; cur = nxt; nxt = tmp;
                 }
-                group_bar(group);
+                group_bar<GROUP>(group);
             }
             if (a.logits[h])
                 for (int o = u; o < d.n_out; o += span) a.logits[h][(size_t)g * d.n_out + o] = cur[o];
-            if (a.scalar[h] && u < 32) {                   // span is a multiple of 32: one full warp per head
-                const float v = support_to_scalar_group<32>(cur, a.S);
-                if (u == 0) a.scalar[h][g] = v;
+            if (a.scalar[h]) {
+                if (span >= 32) {                          // span is a multiple of 32: the head's first warp
+                    if (u < 32) {
+                        const float v = support_to_scalar_group<32>(cur, a.S);
+                        if (u == 0) a.scalar[h][g] = v;
+                    }
+                } else {                                   // two heads share a warp: 16 lanes each
+                    const float v = support_to_scalar_group<16>(cur, a.S);
+                    if (u == 0) a.scalar[h][g] = v;
+                }
             }
         }
-        group_bar(group);
+        group_bar<GROUP>(group);
     }
 }
 
@@ -958,19 +971,28 @@ struct Runner {
         if (n_heads == 0) { lo = 0; hi = 0; }
         a.w_lo = lo; a.w_floats = ((hi - lo) + 3) & ~3;
         a.warp_floats = (a.HW * (a.C + 4) + 6 * a.C + 4 * a.smem_floats + 3) & ~3;   // x tile + channel stats + (ping, pong) per head
-        const int threads = kHeadThreads;
-        const size_t smem = ((size_t)a.w_floats + (size_t)(threads / kHeadGroup) * a.warp_floats) * 4;
+        // one warp per sample when a sample is small (and, for small batches, only as many groups per CTA as it takes
+        // to give every SM work); 128 threads per sample otherwise
+        const bool narrow = a.C * a.HW <= 1024 && n_heads <= 2;
+        const int group = narrow ? 32 : 128;
+        int groups = kHeadThreads / group;
+        if (narrow) groups = std::max(1, std::min(groups, (n + r->sm_count - 1) / r->sm_count));
+        size_t smem = ((size_t)a.w_floats + (size_t)groups * a.warp_floats) * 4;
+        while (groups > 1 && smem > 227 * 1024) { --groups; smem = ((size_t)a.w_floats + (size_t)groups * a.warp_floats) * 4; }
         if (smem > 227 * 1024) { *err = "heads: weights + tiles exceed shared memory"; return false; }
-        static size_t attr_smem = 0;
-        if (attr_smem < smem) {
-            cudaError_t e0 = cudaFuncSetAttribute(heads_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        const int threads = groups * group;
+        static size_t attr_smem[2] = {0, 0};
+        if (attr_smem[narrow] < smem) {
+            cudaError_t e0 = narrow ? cudaFuncSetAttribute(heads_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                                    : cudaFuncSetAttribute(heads_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e0 != cudaSuccess) return fail("heads attr", e0);
-            attr_smem = smem;
+            attr_smem[narrow] = smem;
         }
-        int grid = (n + threads / kHeadGroup - 1) / (threads / kHeadGroup);
+        int grid = (n + groups - 1) / groups;
         if (grid > r->sm_count) grid = r->sm_count;
         kt_begin(KT_HEADS, stream);
-        cudaError_t e = launch_chained(heads_kernel, dim3(grid), dim3(threads), smem, stream, a);
+        cudaError_t e = narrow ? launch_chained(heads_kernel<32>, dim3(grid), dim3(threads), smem, stream, a)
+                               : launch_chained(heads_kernel<128>, dim3(grid), dim3(threads), smem, stream, a);
         kt_end(stream);
         if (e == cudaSuccess) e = cudaGetLastError();
         if (e != cudaSuccess) return fail("heads launch", e);
