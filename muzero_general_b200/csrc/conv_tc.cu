@@ -277,8 +277,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tower_tc_kernel(const __grid
                     // Descriptors differ only in the 14-bit start-address field: build the constant words once and
                     // derive every MMA's descriptor with one add (the single issuing thread is latency-bound, so the
                     // instruction count per MMA is what sets the tensor-pipe duty cycle).
-                    const uint32_t a16 = (s_a + s * kStageBytes + kHalo * kRowBytes) >> 4;     // tile row 0, in 16-byte units
-                    const uint32_t w16 = (s_w + (uint32_t)((l & 1) * kWBytes)) >> 4;
+                    const uint32_t a16 = ((s_a + s * kStageBytes + kHalo * kRowBytes) >> 4) | kDescLoFlags;     // tile row 0, in 16-byte units
+                    const uint32_t w16 = ((s_w + (uint32_t)((l & 1) * kWBytes)) >> 4) | kDescLoFlags;
                     uint32_t acc = 0;
 #pragma unroll
                     for (int tap = 0; tap < 9; ++tap) {
@@ -288,8 +288,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tower_tc_kernel(const __grid
                         const int shift = (tap / 3 - 1) * 8 + (tap % 3 - 1);         // compile-time after unrolling
 #pragma unroll
                         for (int ks = 0; ks < kC / 16; ++ks) {                       // K = 16 channels = 32 bytes of the row
-                            const uint32_t alo = ((a16 + (uint32_t)(shift * kRow16 + ks * 2)) & 0x3FFFu) | kDescLoFlags;
-                            const uint32_t blo = ((w16 + (uint32_t)(tap * (kTapBytes / 16) + ks * 2)) & 0x3FFFu) | kDescLoFlags;
+                            const uint32_t alo = a16 + (uint32_t)(shift * kRow16 + ks * 2);      // < 2^14: never carries into the flag bits
+                            const uint32_t blo = w16 + (uint32_t)(tap * (kTapBytes / 16) + ks * 2);
                             umma_f16_words(d, alo, blo, acc);
                             acc = 1;
                         }
@@ -551,8 +551,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tower_resident_kernel(const 
                 tc_fence_after();
                 if (elect_one()) {
                     const uint32_t d = tmem_base + (uint32_t)(s * kAccCols);
-                    const uint32_t a16 = (s_act + (uint32_t)((l & 1) * kResBufBytes + (kHalo + k * kBoards * kPos) * kRowBytes)) >> 4;
-                    const uint32_t w16 = s_w >> 4;
+                    const uint32_t a16 = ((s_act + (uint32_t)((l & 1) * kResBufBytes + (kHalo + k * kBoards * kPos) * kRowBytes)) >> 4) | kDescLoFlags;
+                    const uint32_t w16 = (s_w >> 4) | kDescLoFlags;
                     uint32_t acc = 0;
 #pragma unroll
                     for (int tap = 0; tap < 9; ++tap) {
@@ -562,8 +562,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tower_resident_kernel(const 
                         const int shift = (tap / 3 - 1) * 8 + (tap % 3 - 1);
 #pragma unroll
                         for (int ks = 0; ks < kC / 16; ++ks) {
-                            const uint32_t alo = ((a16 + (uint32_t)(shift * kRow16 + ks * 2)) & 0x3FFFu) | kDescLoFlags;
-                            const uint32_t blo = ((w16 + (uint32_t)(tap * (kTapBytes / 16) + ks * 2)) & 0x3FFFu) | kDescLoFlags;
+                            const uint32_t alo = a16 + (uint32_t)(shift * kRow16 + ks * 2);      // < 2^14: never carries into the flag bits
+                            const uint32_t blo = w16 + (uint32_t)(tap * (kTapBytes / 16) + ks * 2);
                             umma_f16_words(d, alo, blo, acc);
                             acc = 1;
                         }

@@ -219,3 +219,27 @@ def test_graph_replay_and_dependent_launch_do_not_change_results(name, n, N, gam
     for r in results[1:]:
         assert numpy.array_equal(r.visit_counts, results[0].visit_counts)
         assert numpy.array_equal(r.root_value, results[0].root_value)
+
+
+def test_tower_modes_agree_across_batch_sizes(game_configs, monkeypatch):
+    """The tensor-core towers pick their kernel by batch size (resident <= 1184 boards, streaming <= 2368 boards, one
+    launch per conv above).  A batch of 2500 boards evaluated at once must equal the same boards evaluated in chunks."""
+    cfg = game_configs["connect4"]
+    spec = netspec_from_config(cfg)
+    monkeypatch.setenv("MZ_NO_TC", "0")
+    n = 2500
+    rs = numpy.random.RandomState(21)
+    obs = rs.random_sample((n, spec.obs_elems)).astype(numpy.float32)
+    actions = rs.randint(0, spec.action_space, size=n)
+    eng = _engine(cfg, n, 2)
+    eng.load_weights(weights_for("connect4", spec))
+    whole0 = eng.initial_inference(obs)
+    whole1 = eng.recurrent_inference(whole0["hidden"], actions)
+    for lo, hi in ((0, 1000), (1000, 2400), (2400, 2500)):
+        part0 = eng.initial_inference(obs[lo:hi])
+        part1 = eng.recurrent_inference(part0["hidden"], actions[lo:hi])
+        for k in ("hidden", "value_logits", "policy_logits", "value"):
+            assert numpy.array_equal(part0[k], whole0[k][lo:hi]), (k, lo)
+        for k in ("hidden", "value_logits", "policy_logits", "reward_logits", "value", "reward"):
+            assert numpy.array_equal(part1[k], whole1[k][lo:hi]), (k, lo)
+    eng.close()
