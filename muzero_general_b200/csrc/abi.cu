@@ -186,6 +186,7 @@ extern "C" int mz_create(const MzNetDesc* net, const MzSearchDesc* search, int d
     NodePool& p = h->pool;
     MZ_CREATE_CUDA(dev_alloc(&p.visit, slots));
     MZ_CREATE_CUDA(dev_alloc(&p.vsum, slots));
+    MZ_CREATE_CUDA(dev_alloc(&p.mval, slots));
     MZ_CREATE_CUDA(dev_alloc(&p.reward, slots));
     MZ_CREATE_CUDA(dev_alloc(&p.prior, slots));
     MZ_CREATE_CUDA(dev_alloc(&p.expansion, slots));
@@ -244,7 +245,7 @@ extern "C" int mz_destroy(MzHandle* h) {
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
     NodePool& p = h->pool;
-    void* ptrs[] = {p.visit, p.vsum, p.reward, p.prior, p.expansion, p.root_prior, p.hidden, p.root_visit, p.root_vsum,
+    void* ptrs[] = {p.visit, p.vsum, p.mval, p.reward, p.prior, p.expansion, p.root_prior, p.hidden, p.root_visit, p.root_vsum,
                     p.root_reward, p.range, p.n_expanded, p.ties, p.max_depth, p.legal, p.path, p.path_reward, p.leaf_depth,
                     p.leaf_parent, p.leaf_action, p.leaf_slot, p.net_value, p.net_reward, p.net_policy, h->d_ucb, h->d_pbc, h->d_sqrt, h->d_fc_blob, h->d_in, h->d_out};
     for (void* q : ptrs) if (q) cudaFree(q);

@@ -15,7 +15,7 @@ namespace mz {
 
 struct GameSmem {
     // byte offsets inside one game's region
-    int vsum, root_prior, visit, expansion, reward, prior, path, path_reward, hidden, act, bytes;
+    int vsum, mval, root_prior, visit, expansion, reward, prior, path, path_reward, hidden, act, bytes;
 };
 
 __host__ __device__ inline GameSmem game_smem_layout(int N, int A, int E, int maxw, bool keep_hidden) {
@@ -25,6 +25,7 @@ __host__ __device__ inline GameSmem game_smem_layout(int N, int A, int E, int ma
     int off = 0;
     auto take = [&](int bytes) { int o = off; off = (off + bytes + 15) & ~15; return o; };
     L.vsum = take(S * 8);
+    L.mval = take(S * 8);
     L.root_prior = take(A * 8);
     L.visit = take(S * 4);
     L.expansion = take(S * 4);
@@ -65,6 +66,7 @@ __global__ void __launch_bounds__(kFcMaxThreads) fc_search_kernel(const __grid_c
 
     GameTree t;
     t.vsum = reinterpret_cast<double*>(mine + L.vsum);
+    t.mval = reinterpret_cast<double*>(mine + L.mval);
     t.root_prior = reinterpret_cast<double*>(mine + L.root_prior);
     t.visit = reinterpret_cast<int*>(mine + L.visit);
     t.expansion = reinterpret_cast<int*>(mine + L.expansion);

@@ -16,6 +16,7 @@ constexpr int kFcMaxThreads = 128;   // upper bound of the fused search kernel's
 struct NodePool {
     int* visit;            // [B, (N+1)*A]
     double* vsum;          // [B, (N+1)*A]
+    double* mval;          // [B, (N+1)*A] cached reward + discount * (+/-)mean of every visited child (tree.cuh)
     float* reward;         // [B, (N+1)*A]
     float* prior;          // [B, (N+1)*A]
     int* expansion;        // [B, (N+1)*A]

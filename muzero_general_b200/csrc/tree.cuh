@@ -39,6 +39,7 @@ struct TreeConst {
 struct GameTree {
     int* visit;            // [(N+1)*A]
     double* vsum;          // [(N+1)*A]
+    double* mval;          // [(N+1)*A] reward + discount * (+/-)(value_sum / visits), refreshed by every backup (see tree_backup)
     float* reward;         // [(N+1)*A]
     float* prior;          // [(N+1)*A]
     int* expansion;        // [(N+1)*A]
@@ -162,17 +163,17 @@ MZ_DEVINL Leaf tree_select(const TreeConst& c, GameTree& t, int sim, int64_t gam
             nc = t.visit[base + k];
             child_exp_k = t.expansion[base + k];
             const double pr = (e == 0) ? t.root_prior[k] : (double)t.prior[base + k];
-            double vs = 0.0, tab_pbc = 0.0, tab_sqrt = 0.0;
+            double mv = 0.0, tab_pbc = 0.0, tab_sqrt = 0.0;
             if (kPool) {
                 reward_k = t.reward[base + k];
-                vs = t.vsum[base + k];
+                mv = t.mval[base + k];
                 tab_pbc = __ldg(c.pbc + n_parent);
                 tab_sqrt = __ldg(c.sqrtn + n_parent);
                 if (child_exp_k >= 0) {
                     const int nb = child_exp_k * c.A;
                     prefetch_l1(t.visit + nb); prefetch_l1(t.expansion + nb); prefetch_l1(t.prior + nb);
-                    prefetch_l1(t.reward + nb); prefetch_l1(t.vsum + nb);
-                    prefetch_l1(t.vsum + nb + c.A - 1);             // A doubles may straddle a line
+                    prefetch_l1(t.reward + nb); prefetch_l1(t.mval + nb);
+                    prefetch_l1(t.mval + nb + c.A - 1);             // A doubles may straddle a line
                 }
             }
             // pb_c = (log(...) + init) * (sqrt(n_p) / (n_c + 1))     self_play.py:384-390
@@ -187,11 +188,12 @@ MZ_DEVINL Leaf tree_select(const TreeConst& c, GameTree& t, int sim, int64_t gam
             }
             score = __dmul_rn(pbc, pr);
             if (nc > 0) {
-                if (!kPool) { reward_k = t.reward[base + k]; vs = t.vsum[base + k]; }
-                const double mean = __ddiv_rn(vs, (double)nc);
-                const double signed_mean = (c.P == 1) ? mean : -mean;
-                double v = __dadd_rn((double)reward_k, __dmul_rn(c.discount, signed_mean));
-                v = value_range_normalize(v, t.lo, t.hi);
+                // value_score = normalize(reward + discount * (+/-)mean)  (self_play.py:392-402).  The argument only changes
+                // when a backup passes through the child, and the backup evaluates exactly this expression for the
+                // min-max statistics: it is stored there (mval) and read back here, which takes an fp64 division and a
+                // multiply-add off the per-level critical path without changing a bit.
+                if (!kPool) reward_k = t.reward[base + k];
+                const double v = value_range_normalize(kPool ? mv : t.mval[base + k], t.lo, t.hi);
                 score = __dadd_rn(score, v);
             } else {
                 reward_k = 0.0f;                   // (an unvisited child's stored reward is 0 anyway)
@@ -305,6 +307,7 @@ MZ_DEVINL void tree_backup(const TreeConst& c, GameTree& t, const Leaf& leaf, fl
                 q = __ddiv_rn(s, (double)n);
             }
             const double m = __dadd_rn(r, __dmul_rn(c.discount, (c.P == 1) ? q : -q));
+            if (j > 0) t.mval[slot] = m;           // what the next selection will normalise for this child
             lo = fmin(lo, m);
             hi = fmax(hi, m);
         }

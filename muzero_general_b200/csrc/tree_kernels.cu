@@ -34,6 +34,7 @@ __global__ void __launch_bounds__(128) tree_step_kernel(const __grid_constant__ 
     GameTree t;
     t.visit = p.visit + g * slots;
     t.vsum = p.vsum + g * slots;
+    t.mval = p.mval + g * slots;
     t.reward = p.reward + g * slots;
     t.prior = p.prior + g * slots;
     t.expansion = p.expansion + g * slots;
