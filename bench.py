@@ -56,7 +56,7 @@ NET_FLOPS = {"cartpole": (1312.0, 2752.0), "tictactoe": (1.880e5, 2.315e5), "con
 
 
 # measured DRAM bytes per launch of the dominant kernel (ncu --set full, profiles/): fc_search / conv tower
-TRAFFIC = {"connect4": None}
+TRAFFIC = {"connect4": 8919424}      # conv_tower_resident_kernel: (8966144 + 8872704) / 2 bytes read, 0 written back within the capture
 
 
 def conv3x3_flops(spec, N):
