@@ -489,7 +489,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tower_resident_kernel(const 
         s_bias[i] = b ? b[i % kC] : 0.0f;
     }
     if (threadIdx.x == 0) {
-        for (int t = 0; t < 9; ++t) { mbar_init(bar_w_full(t), 1); mbar_init(bar_w_empty(t), 2); }   // both MMA issuers release a tap
+        for (int t = 0; t < 9; ++t) { mbar_init(bar_w_full(t), 1); mbar_init(bar_w_empty(t), 1); }
         for (int k = 0; k < kResTiles; ++k) {
             mbar_init(bar_in_full(k), 1);
             mbar_init(bar_tile_ready(k), kEpiWarps / 2);
@@ -538,26 +538,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tower_resident_kernel(const 
             }
             __syncwarp();
         }
-    } else if (warp == 1 || warp == 2) {
-        // ================= two MMA issuers: issuer j owns accumulator stage j = the tiles with (it & 1) == j =================
-        // One thread needs ~75 cycles per tcgen05.mma while the tensor pipe is busy for ~39 of them; two issuing threads
-        // working on different tiles (different TMEM accumulators) interleave their MMAs in the pipe.
-        const int issuer = warp - 1;
+    } else if (warp == 1) {
+        // ================= MMA issuer =================
         int it = 0;
         for (int l = 0; l < L; ++l) {
-            // my first / last tile of this layer (the parity of `it` at k = 0 alternates with odd my_tiles)
-            const int k_first = ((l * my_tiles) & 1) == issuer ? 0 : 1;
-            const int k_last = k_first + ((my_tiles - 1 - k_first) & ~1);        // < k_first when I have no tile in this layer
-            if (k_first >= my_tiles) {
-                // nothing to multiply in this layer (my_tiles == 1): still release the weight slots for the producer - with
-                // a commit, so that the arrival stays ordered behind this thread's MMAs of the previous layer
-                if (my_tiles > 0 && elect_one())
-                    for (int tap = 0; tap < 9; ++tap) umma_commit(bar_w_empty(tap));
-                __syncwarp();
-            }
             for (int k = 0; k < my_tiles; ++k, ++it) {
-                if ((it & 1) != issuer) continue;
-                const int s = issuer;
+                const int s = it & 1;
                 const uint32_t ph = (uint32_t)(it >> 1) & 1u;
                 if (l == 0) mbar_wait(bar_in_full(k), 0);
                 else mbar_wait(bar_tile_ready(k), (uint32_t)((l - 1) & 1));
@@ -571,7 +557,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tower_resident_kernel(const 
 #pragma unroll
                     for (int tap = 0; tap < 9; ++tap) {
                         if (a.debug_skip & 1) break;
-                        if (k == k_first) { mbar_wait(bar_w_full(tap), (uint32_t)(l & 1)); tc_fence_after(); }
+                        if (k == 0) { mbar_wait(bar_w_full(tap), (uint32_t)(l & 1)); tc_fence_after(); }
                         constexpr int kRow16 = kRowBytes / 16;
                         const int shift = (tap / 3 - 1) * 8 + (tap % 3 - 1);
 #pragma unroll
@@ -581,9 +567,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tower_resident_kernel(const 
                             umma_f16_words(d, alo, blo, acc);
                             acc = 1;
                         }
-                        if (k == k_last) umma_commit(bar_w_empty(tap));
+                        if (k == my_tiles - 1) umma_commit(bar_w_empty(tap));
                     }
-                    if (a.debug_skip & 1) { if (k == k_last) for (int tap = 0; tap < 9; ++tap) umma_commit(bar_w_empty(tap)); }
+                    if (a.debug_skip & 1) { if (k == my_tiles - 1) for (int tap = 0; tap < 9; ++tap) umma_commit(bar_w_empty(tap)); }
                     umma_commit(bar_acc_full(s));
                 }
                 __syncwarp();
