@@ -12,7 +12,7 @@ FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-fmad=false", "-diag-suppress", "177",                     # tree arithmetic must never be contracted; FMAs are explicit fmaf()
     "-Xcompiler", "-fPIC", "-Xcompiler", "-O2", "--expt-relaxed-constexpr",
-]
+] + os.environ.get("MZ_NVCC_EXTRA", "").split()        # e.g. -DMZ_DUAL_ISSUER for the experiment in conv_tc.cu
 
 
 def needs_build():
