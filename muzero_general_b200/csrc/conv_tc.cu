@@ -1,11 +1,16 @@
 // conv3x3 (C -> C, stride 1, pad 1) as an implicit GEMM on the 5th-generation tensor cores.
 //
 // Used for the residual towers of board-sized states (H <= 6, W <= 7, C = 64: Connect4,
-// models.py:213-229 inside representation / dynamics / prediction).  Per CTA:
+// models.py:213-229 inside representation / dynamics / prediction).  Two kernels share the MMA loop:
 //
-//   weights  [tap 9][cout C][cin C] fp16, BN folded, 128B-swizzled   resident in shared memory (bulk copy)
-//   A tile   two boards = 128 rows of the "P64S" layout    2-stage ring, one 8 KB cp.async.bulk per board
-//   D        128 x 64 fp32 accumulator                     TMEM, double buffered
+//   conv_tower_resident_kernel   up to 4 tiles per CTA (1184 boards on 148 SMs): the activations of a CTA's tiles stay
+//                                in shared memory through all layers of a tower (see the comment above the kernel)
+//   conv_tower_tc_kernel         larger batches / single convs: activations stream through L2, per CTA
+//
+//     weights  [tap 9][cout C][cin C] fp16, BN folded, 128B-swizzled   shared memory (bulk copy), two slot sets
+//     A tile   two boards = 128 rows of the "P64S" layout    2-stage ring, one 8 KB cp.async.bulk per board
+//     D        128 x 64 fp32 accumulator                     TMEM, double buffered
+//     out      two output tiles staged in shared memory      one 8 KB bulk store per board (dedicated warp)
 //
 // Operands are fp16 (10-bit mantissa - the same as tf32 - with fp32 accumulation): one tcgen05.mma
 // consumes K = 16 channels per 32-byte operand row, so a tile needs 36 MMAs instead of the 72 a tf32
@@ -16,14 +21,14 @@
 // W..7 are zero padding), every position one 128-byte row of 64 fp16 channels whose eight 16-byte chunks are stored
 // XOR-ed with p % 8 - i.e. the boards sit in HBM already in the UMMA K-major SWIZZLE_128B shared-memory image, so a
 // plain 1-D bulk copy lands them ready for the tensor core.  Filter tap (dy,dx) is the SAME shared-memory tile with
-// its start address moved by (dy*8+dx) rows (descriptor base_offset = row phase): the implicit GEMM needs no im2col
-// copy.  Epilogue warps read the accumulator with tcgen05.ld, add the folded-BN bias, the optional residual and the
-// optional action-plane term (models.py:557-572 folded into a per-position table), apply ReLU, zero the padding
-// positions, convert to fp16 (round to nearest, saturating) and store P64S again.
+// its start address moved by (dy*8+dx) rows (the hardware swizzles on absolute address bits, so base_offset stays 0):
+// the implicit GEMM needs no im2col copy.  Epilogue warps read the accumulator with tcgen05.ld, add the folded-BN
+// bias, the optional residual and the optional action-plane term (models.py:557-572 folded into a per-position
+// table), apply ReLU, zero the padding positions, convert to fp16 (round to nearest, saturating) and store P64S again.
 //
-// Warp roles (384 threads): 0 = bulk-copy producer, 1 = MMA issuer, 2 = TMEM allocator,
-// 4..11 = epilogue (TMEM lane quarter = warp % 4, accumulator column half = (warp - 4) / 4); the
-// epilogue prefetches its residual / action terms before it waits for the accumulator.
+// Warp roles (384 threads): 0 = bulk-copy producer, 1 = MMA issuer (one elected thread issues every tcgen05.mma of
+// the CTA), 2 = TMEM allocator, 3 = output store (bulk copies shared -> global), 4..11 = epilogue (TMEM lane quarter
+// = warp % 4; streaming kernel: accumulator column half = (warp - 4) / 4, resident kernel: tile parity = (warp - 4) / 4).
 #include <cuda_fp16.h>
 #include <stdio.h>
 #include <stdlib.h>
