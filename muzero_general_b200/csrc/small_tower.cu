@@ -9,8 +9,8 @@
 // place by the thread that owns the output.  The arithmetic (fp32 FMA chain over cin, dy, dx; + bias, + residual,
 // ReLU) is in exactly the order of conv3x3_kernel, so both paths give bit-identical results.
 //
-// Thread mapping: one item = (board, row y, group of CO output channels) computes the P = W pixels of that row
-// for CO channels (P x CO accumulators); CO = 4 when the batch is large enough to fill the GPU that way (float4
+// Thread mapping: one item = (board, row y, row segment, group of CO output channels) computes P consecutive pixels of
+// that row for CO channels (P x CO accumulators; P = W, or W/2 for small latency-bound batches); CO = 4 when the batch is large enough to fill the GPU that way (float4
 // weight loads, 4.5+ FMAs per shared-memory load), CO = 1 for small batches (4x the threads, lower latency).
 #include "small_tower.h"
 #include "launch.h"
@@ -25,9 +25,10 @@ constexpr int kMaxThreads = 256;
 template <int P, int CO>
 __global__ void __launch_bounds__(kMaxThreads) small_tower_kernel(const __grid_constant__ SmallTowerArgs a) {
     extern __shared__ __align__(16) float smem[];
-    const int H = a.H, C = a.C;
-    constexpr int Wp = P + 2;
+    const int H = a.H, W = a.W, C = a.C;
+    const int Wp = W + 2;
     const int plane = (H + 2) * Wp;
+    const int segs = W / P;                                 // row segments: a thread owns P consecutive pixels of a row
     const int nb = a.boards_per_cta, cap = a.cap_channels;
     const int bufsz = nb * cap * plane;
     float* s_w = smem;
@@ -47,12 +48,13 @@ __global__ void __launch_bounds__(kMaxThreads) small_tower_kernel(const __grid_c
     pdl_wait();                                            // weights are constants; the input comes from the previous kernel
 
     const int cgs = C / CO;
-    const int items_per_board = cgs * H;
+    const int items_per_board = cgs * H * segs;
     const int item = threadIdx.x;
     const int cgi = item % cgs;
-    const int y = (item / cgs) % H;
+    const int seg = (item / cgs) % segs;
+    const int y = (item / (cgs * segs)) % H;
     const int b = item / items_per_board;
-    const int HW = H * P;
+    const int HW = H * W;
     const int cin0 = a.layer[0].cin;
     const size_t sample_elems = (size_t)a.in_channels * HW;
 
@@ -62,13 +64,13 @@ __global__ void __launch_bounds__(kMaxThreads) small_tower_kernel(const __grid_c
         __syncthreads();                                   // previous tile fully consumed / initial fill visible
         // ---- stage the tower input (interior only) into buffer 0
         for (int i = threadIdx.x; i < nbt * cin0 * HW; i += blockDim.x) {
-            const int x = i % P, yy = (i / P) % H, ci = (i / HW) % cin0, bb = i / (HW * cin0);
+            const int x = i % W, yy = (i / W) % H, ci = (i / HW) % cin0, bb = i / (HW * cin0);
             const int g = b0 + bb;
             float v;
             if (ci < a.in_channels) {
                 const float* src = a.gather_parent ? a.in + ((size_t)g * a.pool_stride + a.gather_parent[g]) * sample_elems
                                                    : a.in + (size_t)g * sample_elems;
-                v = src[ci * HW + yy * P + x];
+                v = src[ci * HW + yy * W + x];
             } else {
                 v = __fdiv_rn((float)a.action[g], (float)a.A);        // action / |A| plane (models.py:586-600)
             }
@@ -87,7 +89,7 @@ __global__ void __launch_bounds__(kMaxThreads) small_tower_kernel(const __grid_c
                 for (int c = 0; c < CO; ++c)
 #pragma unroll
                     for (int p = 0; p < P; ++p) acc[c][p] = 0.0f;
-                const float* ib = sin + b * cap * plane + y * Wp;
+                const float* ib = sin + b * cap * plane + y * Wp + seg * P;
                 const float* wb = s_w + a.w_smem_off[l] + cgi * CO;
                 const int cin = a.layer[l].cin;
                 for (int ci = 0; ci < cin; ++ci) {
@@ -119,13 +121,13 @@ __global__ void __launch_bounds__(kMaxThreads) small_tower_kernel(const __grid_c
                 for (int c = 0; c < CO; ++c) {
                     const int co = cgi * CO + c;
                     const float bias = s_w[a.b_smem_off[l] + co];
-                    float* so = sout + (b * cap + co) * plane + (y + 1) * Wp + 1;
+                    float* so = sout + (b * cap + co) * plane + (y + 1) * Wp + 1 + seg * P;
 #pragma unroll
                     for (int p = 0; p < P; ++p) {
                         float r = acc[c][p] + bias;
                         if (a.layer[l].residual) r += so[p];
                         if (a.layer[l].relu) r = fmaxf(r, 0.0f);
-                        if (last) a.out[(((size_t)g * C + co) * H + y) * P + p] = r;
+                        if (last) a.out[(((size_t)g * C + co) * H + y) * W + seg * P + p] = r;
                         else so[p] = r;
                     }
                 }
@@ -154,7 +156,10 @@ Plan make_plan(SmallTowerArgs& a, int sm_count) {
     // CO = 4 only when that still gives every SM a few hundred threads
     int CO = ((long)a.n * (a.C / 4) * a.H >= (long)sm_count * 384) ? 4 : 1;
     if ((a.C / CO) * a.H > kMaxThreads) CO = 4;
-    const int items = (a.C / CO) * a.H;
+    // small batches (CO = 1) are latency-bound: split the rows in two segments so twice as many threads share a board
+    int P = a.W;
+    if (CO == 1 && a.W >= 4 && a.W % 2 == 0 && (a.C / CO) * a.H * 2 <= kMaxThreads) P = a.W / 2;
+    const int items = (a.C / CO) * a.H * (a.W / P);
     if (items > kMaxThreads) return pl;
     int nb = std::min(kMaxThreads / items, a.n);
     const size_t budget = 200 * 1024;
@@ -172,7 +177,7 @@ Plan make_plan(SmallTowerArgs& a, int sm_count) {
     nb = std::min(nb, (a.n + grid * rounds - 1) / (grid * rounds));
     grid = std::min((a.n + nb - 1) / nb, resident(nb));
     a.boards_per_cta = nb; a.cap_channels = cap; a.w_floats = w_floats;
-    pl.P = a.W; pl.CO = CO; pl.nb = nb; pl.threads = ((nb * items + 31) / 32) * 32; pl.grid = grid; pl.smem = bytes(nb);
+    pl.P = P; pl.CO = CO; pl.nb = nb; pl.threads = ((nb * items + 31) / 32) * 32; pl.grid = grid; pl.smem = bytes(nb);
     pl.ok = true;
     return pl;
 }

@@ -50,3 +50,21 @@ def test_more_than_two_players_rejected(game_configs):
     from muzero_general_b200.engine import SearchEngine
     with pytest.raises(NotImplementedError):
         SearchEngine(cfg, max_games=1)
+
+
+def test_bench_conv_flops_agree_with_survey_table():
+    """bench.py derives the tensor roofline's algorithmic FLOPs from the network shape; the 3x3 convolutions must account
+    for (almost) all of the per-inference FLOPs quoted in SURVEY.md section 8 (the rest are the 1x1 convs and FC heads)."""
+    import importlib.util
+    import os
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(os.path.dirname(os.path.dirname(__file__)), "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    from muzero_general_b200.games import load_game_module
+    from muzero_general_b200.netspec import netspec_from_config
+    for game, N in (("tictactoe", 50), ("connect4", 200), ("breakout", 50)):
+        ns = netspec_from_config(load_game_module(game).MuZeroConfig())
+        f0, f1 = bench.NET_FLOPS[game]
+        conv = bench.conv3x3_flops(ns, N)
+        total = f0 + N * f1
+        assert 0.85 * total < conv <= total, (game, conv, total)
