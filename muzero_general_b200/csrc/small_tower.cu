@@ -20,7 +20,7 @@
 namespace mz {
 
 namespace {
-constexpr int kMaxThreads = 256;
+constexpr int kMaxThreads = 704;      // 22 warps: one CTA can hold a whole SM's share of a large batch (weights staged once per SM)
 
 template <int P, int CO>
 __global__ void __launch_bounds__(kMaxThreads) small_tower_kernel(const __grid_constant__ SmallTowerArgs a) {
@@ -161,21 +161,26 @@ Plan make_plan(SmallTowerArgs& a, int sm_count) {
     if (CO == 1 && a.W >= 4 && a.W % 2 == 0 && (a.C / CO) * a.H * 2 <= kMaxThreads) P = a.W / 2;
     const int items = (a.C / CO) * a.H * (a.W / P);
     if (items > kMaxThreads) return pl;
-    int nb = std::min(kMaxThreads / items, a.n);
-    const size_t budget = 200 * 1024;
     auto bytes = [&](int boards) { return ((size_t)w_floats + 2ull * boards * cap * plane) * 4; };
-    while (nb > 1 && bytes(nb) > 100 * 1024) --nb;          // prefer two or more CTAs per SM
-    if (bytes(nb) > budget) return pl;
+    // c CTAs per SM, each with as many boards as its threads and its share of shared memory allow: take the split that
+    // keeps most of an SM's share of the batch in flight at once (ties: fewer CTAs, the weights are staged per CTA)
+    const size_t smem_cap = 226 * 1024;
+    const int want = (a.n + sm_count - 1) / sm_count;
+    int best_c = 0, best_nb = 0, best_cover = -1;
+    for (int c = 1; c <= 4; ++c) {
+        int nb_c = std::min(std::min(kMaxThreads / items, a.n), 2048 / c / items);
+        while (nb_c >= 1 && (bytes(nb_c) + 1024) * c > smem_cap) --nb_c;
+        if (nb_c < 1) break;
+        const int cover = std::min(c * nb_c, want);
+        if (cover > best_cover) { best_cover = cover; best_c = c; best_nb = nb_c; }
+    }
+    if (best_c == 0) return pl;
     // persistent grid; spread the boards evenly over the resident CTAs
-    auto resident = [&](int boards) {
-        const int threads = ((boards * items + 31) / 32) * 32;
-        int per_sm = (int)std::min<size_t>((227 * 1024) / (bytes(boards) + 1024), (size_t)(2048 / threads));
-        return sm_count * std::max(1, std::min(per_sm, 8));
-    };
-    int grid = resident(nb);
+    int nb = best_nb;
+    int grid = sm_count * best_c;
     const int rounds = (a.n + grid * nb - 1) / (grid * nb);
     nb = std::min(nb, (a.n + grid * rounds - 1) / (grid * rounds));
-    grid = std::min((a.n + nb - 1) / nb, resident(nb));
+    grid = std::min((a.n + nb - 1) / nb, grid);
     a.boards_per_cta = nb; a.cap_channels = cap; a.w_floats = w_floats;
     pl.P = P; pl.CO = CO; pl.nb = nb; pl.threads = ((nb * items + 31) / 32) * 32; pl.grid = grid; pl.smem = bytes(nb);
     pl.ok = true;
