@@ -1,24 +1,28 @@
 #!/usr/bin/env python
-"""bench.py - self-play search throughput (BASELINE.json metric) on N B200s.
-
-A "step" is one pass of the hot path over one batch: a batched MCTS.run (root inference +
-num_simulations x {select, recurrent inference, expand, backup}) for every game of the batch,
-i.e. one env-step's worth of search per game.
+"""bench.py - self-play throughput (BASELINE.json metric: env-steps/s and MCTS simulations/s) on N B200s.
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--workload NAME] [--impl ours|reference]
+                  [--extras a,b,c | --no-extras] [--no-cpu-baseline] [--no-loop]
 
-N=1 workload: BASELINE.json configs[1] - CartPole, fully-connected net, num_simulations=50,
-4096 parallel games per GPU (weak scaling: every rank owns its own 4096 games; no data-path
-collective - only one NCCL all-gather of per-rank counters per reporting step).
+What is timed
+-------------
+One SEARCH = the hot path over one batch: a batched MCTS.run (root inference + num_simulations x {select, recurrent
+inference, expand, backup}) for every game of the batch = one env-step's worth of search per game.  One STEP =
+`searches_per_step` searches over different synthetic batches, chosen so that K steps last >= 1 s (a 0.6 ms CartPole
+search would otherwise give a 12 ms sample); the L2 is flushed (256 MiB write, untimed) before every search.
+`value` = env-steps/s of search with the inputs resident in HBM (search only - the environment step is NOT in it);
+`e2e`   = the same through the C ABI with pinned HOST buffers, H2D + D2H inside the timed region;
+`loop`  = env-steps/s of the WHOLE self-play loop through the public `SelfPlay` API (SURVEY.md 8d's full definition:
+          search + environment step + action sampling + GameHistory hand-over), timed >= 1 s;
+`workloads` = the same sub-lines for the other BASELINE configs at this --gpus N.
 
-Prints ONE JSON line (see the keys at the bottom).  `value` = env-steps/s with the inputs
-resident in HBM; `e2e` = the same through the C ABI with pinned HOST buffers (H2D + D2H inside
-the timed region); `roofline` = algorithmic tree+hidden bytes of the dominant kernel over its
-CUDA-event duration against the measured HBM peak; `cpu_baseline` = the oracle port of the
-reference's batch-1 Python/torch search timed on this box's host cores.
+N=1 headline workload: BASELINE.json configs[1] - CartPole, fully-connected net, num_simulations=50, 4096 parallel
+games per GPU (weak scaling: every rank owns its own games; no data-path collective - one all-gather of per-rank
+counters per reporting step, `muzero_general_b200.parallel.gather_counters`).
 """
 import argparse
 import json
+import math
 import os
 import subprocess
 import sys
@@ -39,6 +43,12 @@ WORKLOADS = {
     "breakout_b128_n50": ("breakout", 128, 50, 5100.0),
 }
 DEFAULT_WORKLOAD = "cartpole_b4096_n50"
+DEFAULT_EXTRAS = ["connect4_b1024_n200", "connect4_b1024_n200@fp16", "tictactoe_b8192_n50", "breakout_b128_n50"]
+MIN_TIMED_SECONDS = 1.0
+
+# algorithmic FLOPs of initial_inference / recurrent_inference per sample (SURVEY.md section 8 table)
+NET_FLOPS = {"cartpole": (1312.0, 2752.0), "tictactoe": (1.880e5, 2.315e5), "connect4": (3.737e7, 4.040e7),
+             "breakout": (3.419e7, 1.532e6)}
 
 
 def load_peaks():
@@ -50,13 +60,13 @@ def load_peaks():
     return 6650.0, 1400.0, "fallback"
 
 
-# algorithmic FLOPs of initial_inference / recurrent_inference per sample (SURVEY.md section 8 table)
-NET_FLOPS = {"cartpole": (1312.0, 2752.0), "tictactoe": (1.880e5, 2.315e5), "connect4": (3.737e7, 4.040e7),
-             "breakout": (3.419e7, 1.532e6)}
-
-
-# measured DRAM bytes per launch of the dominant kernel (ncu --set full, profiles/): fc_search / conv tower
-TRAFFIC = {"connect4": 8919424}      # conv_tower_resident_kernel: (8966144 + 8872704) / 2 bytes read, 0 written back within the capture
+def load_traffic():
+    """Measured DRAM bytes per launch of the dominant kernels, from the committed ncu captures (profiles/traffic.json)."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        return json.load(open(p))
+    except (OSError, ValueError):
+        return {}
 
 
 def conv3x3_flops(spec, N):
@@ -128,10 +138,38 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------- CPU arm (oracle port)
-def _cpu_worker(args):
-    game, n_sim, seconds, seed = args
+def physical_cores():
+    """One logical CPU per physical core inside this process's affinity set (SMT siblings dropped)."""
+    try:
+        allowed = sorted(os.sched_getaffinity(0))
+    except AttributeError:
+        return list(range(os.cpu_count() or 1))
+    seen, out = set(), []
+    for c in allowed:
+        try:
+            sib = open(f"/sys/devices/system/cpu/cpu{c}/topology/thread_siblings_list").read().strip()
+        except OSError:
+            sib = str(c)
+        if sib not in seen:
+            seen.add(sib)
+            out.append(c)
+    return out or allowed
+
+
+_CPU = {}
+
+
+def _cpu_init(game, n_sim, cpus, counter):
+    """Pool initializer: pin this worker to its own physical core, build the oracle network once."""
     import torch
     torch.set_num_threads(1)
+    with counter.get_lock():
+        idx = counter.value
+        counter.value += 1
+    try:
+        os.sched_setaffinity(0, {cpus[idx % len(cpus)]})
+    except (AttributeError, OSError):
+        pass
     from muzero_general_b200.games import load_game_module
     from muzero_general_b200.netspec import netspec_from_config, synthetic_weights
     from oracle import mcts as om
@@ -139,140 +177,105 @@ def _cpu_worker(args):
     cfg = load_game_module(game).MuZeroConfig()
     spec = netspec_from_config(cfg)
     net = OracleNet(spec, synthetic_weights(spec, 0))
-    params = om.SearchParams.from_config(cfg, n_sim)
-    rs = numpy.random.RandomState(seed)
-    draws = om.LegacyNumpyDraws(rs)
-    search = om.TreeSearch(params)
-    ev = om.ModelEvaluator(net, spec.support_size)
-    shape = (spec.in_channels,) + tuple(spec.obs_shape[1:])
-    legal = list(range(spec.action_space))
+    rs = numpy.random.RandomState(1000 + idx)
+    _CPU.update(game=game, spec=spec, rs=rs, draws=om.LegacyNumpyDraws(rs),
+                search=om.TreeSearch(om.SearchParams.from_config(cfg, n_sim)),
+                ev=om.ModelEvaluator(net, spec.support_size),
+                shape=(spec.in_channels,) + tuple(spec.obs_shape[1:]), legal=list(range(spec.action_space)))
+    _cpu_one()                 # warm-up
 
-    def one():
-        if game == "cartpole":
-            obs = rs.uniform(-0.05, 0.05, size=shape).astype(numpy.float32)
-        else:
-            obs = rs.random_sample(shape).astype(numpy.float32)
-        search.run(ev, obs, legal, 0, True, draws)
 
-    one()                      # warm-up
+def _cpu_one():
+    c = _CPU
+    if c["game"] == "cartpole":
+        obs = c["rs"].uniform(-0.05, 0.05, size=c["shape"]).astype(numpy.float32)
+    else:
+        obs = c["rs"].random_sample(c["shape"]).astype(numpy.float32)
+    c["search"].run(c["ev"], obs, c["legal"], 0, True, c["draws"])
+
+
+def _cpu_run(seconds):
     t0 = time.perf_counter()
     done = 0
     while time.perf_counter() - t0 < seconds:
-        one()
+        _cpu_one()
         done += 1
     return done, time.perf_counter() - t0
 
 
-def cpu_baseline(game, n_sim, seconds, cores):
-    """env-steps/s of the oracle port (batch-1 Python/torch MCTS.run) on `cores` host processes."""
-    import multiprocessing as mp
-    ctx = mp.get_context("spawn")
-    with ctx.Pool(cores) as pool:
-        res = pool.map(_cpu_worker, [(game, n_sim, seconds, 1000 + i) for i in range(cores)])
-    searches = sum(r[0] for r in res)
-    wall = max(r[1] for r in res)
-    return searches / wall, searches, wall
+class CpuArm:
+    """The oracle port of the reference's batch-1 Python/torch MCTS.run, one pinned process per physical core.
+    The pool is created once (importing torch in 64+ fresh processes costs more than the measurement)."""
+
+    def __init__(self, game, n_sim):
+        import multiprocessing as mp
+        self.cpus = physical_cores()
+        ctx = mp.get_context("spawn")
+        self.pool = ctx.Pool(len(self.cpus), initializer=_cpu_init, initargs=(game, n_sim, self.cpus, ctx.Value("i", 0)))
+
+    @property
+    def cores(self):
+        return len(self.cpus)
+
+    def run(self, seconds):
+        res = self.pool.map(_cpu_run, [seconds] * len(self.cpus), chunksize=1)
+        searches = sum(r[0] for r in res)
+        wall = max(r[1] for r in res)
+        return searches / wall, searches, wall
+
+    def close(self):
+        self.pool.close()
+        self.pool.join()
 
 
-def host_cores():
-    try:
-        return max(1, len(os.sched_getaffinity(0)))
-    except AttributeError:
-        return os.cpu_count() or 1
+# ----------------------------------------------------------------------------- distributed helpers
+class Dist:
+    def __init__(self, dist, dev):
+        self.dist, self.dev = dist, dev
+
+    def barrier(self):
+        import torch
+        if self.dist is not None:
+            self.dist.barrier()
+        torch.cuda.synchronize()
+
+    def max(self, values):
+        import torch
+        t = torch.tensor(list(values), dtype=torch.float64, device=self.dev)
+        if self.dist is not None:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return [float(x) for x in t.tolist()]
 
 
-def selfplay_loop(game, B, N, device, moves):
-    """env-steps/s of the full loop: BatchedSelfPlay over B games for ~`moves` lockstep moves."""
-    from muzero_general_b200 import self_play as sp
-    from muzero_general_b200.games import load_game_module
-    from muzero_general_b200.netspec import netspec_from_config, synthetic_weights
-    mod = load_game_module(game)
-    cfg = mod.MuZeroConfig()
-    cfg.num_parallel_games, cfg.rng_mode, cfg.num_simulations = B, "philox", N
-    spec = netspec_from_config(cfg)
-    worker = sp.SelfPlay({"weights": synthetic_weights(spec, 0)}, mod.Game, cfg, seed=0, device=device)
-    worker.play_games(1, 1.0, max_total_moves=2 * B)                  # warm-up (two moves)
-    start_steps, start_games = worker.played_steps, worker.played_games
-    t0 = time.perf_counter()
-    worker.play_games(10 ** 9, 1.0, max_total_moves=start_steps + moves * B)
-    dt = time.perf_counter() - t0
-    steps = worker.played_steps - start_steps
-    res = {"value": steps / dt, "unit": "env-steps/s", "env_steps": int(steps), "seconds": dt,
-           "games_finished": int(worker.played_games - start_games),
-           "includes": "mz_search + numpy vector env step + Dirichlet draw + action sampling + GameHistory assembly"}
-    worker.model.engine.close()
-    return res
+def percentiles(ms):
+    a = numpy.asarray(ms, dtype=numpy.float64)
+    return {"median": float(numpy.median(a)), "p10": float(numpy.percentile(a, 10)), "p90": float(numpy.percentile(a, 90)),
+            "min": float(a.min()), "max": float(a.max()), "count": int(a.size)}
 
 
-# ----------------------------------------------------------------------------- main
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--cpu-seconds", type=float, default=12.0)
-    ap.add_argument("--no-cpu-baseline", action="store_true")
-    args = ap.parse_args()
-    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
-
-    game, B, N, bytes_per_sim = WORKLOADS[args.workload]
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    config = {"workload": args.workload, "game": game, "games_per_gpu": B, "num_simulations": N,
-              "net": "fullyconnected" if game == "cartpole" else "resnet", "weights": "synthetic seed 0",
-              "l2": "256 MiB buffer written between timed steps", "parallelism": f"games sharded x{world}"}
-
-    # ------------------------------------------------------------------ reference arm (CPU)
-    if args.impl == "reference":
-        if rank != 0:
-            return 0
-        cores = host_cores()
-        steps, total, wall = max(1, args.steps), 0, 0.0
-        per_step = max(2.0, min(20.0, 120.0 / (steps + args.warmup)))
-        for _ in range(args.warmup):
-            cpu_baseline(game, N, 1.0, cores)
-        for _ in range(steps):
-            _, s, w = cpu_baseline(game, N, per_step, cores)
-            total += s; wall += w
-        v = total / wall
-        sample = f"{steps} steps x {per_step:.1f}s of batch-1 MCTS.run (N={N}) on {cores} processes"
-        print(json.dumps({
-            "impl": "reference", "metric": "self-play env-steps/sec", "value": v, "unit": "env-steps/s",
-            "n_gpus": args.gpus, "steps": steps, "warmup": args.warmup, "ms_per_step": 1000.0 * wall / steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32+f64",
-            "data": "synthetic", "config": config, "sims_per_sec": v * N,
-            "cpu_baseline": {"value": v, "unit": "env-steps/s", "cores": cores, "kind": "port", "sample": sample},
-            "e2e": {"value": v, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        }))
-        return 0
-
-    # ------------------------------------------------------------------ our arm (GPU)
+# ----------------------------------------------------------------------------- one workload on this rank
+def run_workload(name, args, D, rank, local_rank, world, with_loop, headline):
+    """Times one workload on this rank (collectively with the other ranks); returns the sub-line on every rank."""
     import torch
     from muzero_general_b200.engine import SearchEngine
     from muzero_general_b200.games import load_game_module
     from muzero_general_b200.netspec import netspec_from_config, synthetic_weights
+    from muzero_general_b200 import parallel
 
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
-    dist = None
-    if world > 1:
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"          # keep stdout to the single JSON line
-        import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    torch.cuda.set_device(local_rank)
+    base, _, mode = name.partition("@")
+    game, B, N, bytes_per_sim = WORKLOADS[base]
+    prev_mode = os.environ.get("MZ_TC_MODE")
+    if mode:
+        os.environ["MZ_TC_MODE"] = mode
     dev = torch.device("cuda", local_rank)
-
     cfg = load_game_module(game).MuZeroConfig()
     spec = netspec_from_config(cfg)
     A = spec.action_space
     eng = SearchEngine(cfg, max_games=B, device=local_rank, num_simulations=N, seed=cfg.seed + rank)
     eng.load_weights(synthetic_weights(spec, 0))
+    numerics = eng.numerics if hasattr(eng, "numerics") else "f32"
 
-    # synthetic inputs, a different batch every step (global game ids keep streams rank-independent)
+    # synthetic inputs, a different batch every search (global game ids keep streams rank-independent)
     n_batches = 4
     rs = numpy.random.RandomState(100 + rank)
     shape = (B, eng.obs_elems)
@@ -290,136 +293,287 @@ def main():
     dev_gid = torch.from_numpy(game_id).to(dev)
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
 
-    def barrier():
-        if dist is not None:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def step_device(i):
+    def search_device(i):
         return eng.search(obs=dev_obs[i % n_batches], add_exploration_noise=True, noise=dev_noise[i % n_batches],
                           game_id=dev_gid)
 
-    def step_host(i):
+    def search_host(i):
         return eng.search(obs=pinned_obs[i % n_batches].numpy(), add_exploration_noise=True,
                           noise=pinned_noise[i % n_batches].numpy(), game_id=game_id)
 
-    def timed(fn, steps, warmup):
-        for i in range(warmup):
-            fn(i)
-        barrier()
-        wall, kern, visits = 0.0, 0.0, None
-        for i in range(steps):
-            flush.fill_(i & 0xFF)                      # evict L2 between timed iterations (untimed)
-            torch.cuda.synchronize()
-            t0 = time.perf_counter()
-            out = fn(i)                                # mz_search synchronises its stream before returning
-            torch.cuda.synchronize()
-            wall += time.perf_counter() - t0
-            kern += out.device_ms
-            visits = out.visit_counts
-        return wall, kern, visits
+    def one(fn, i):
+        flush.fill_(i & 0xFF)                      # evict L2 before every timed search (untimed)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        out = fn(i)                                # mz_search synchronises its stream before returning
+        torch.cuda.synchronize()
+        return time.perf_counter() - t0, out
 
-    clocks = ClockSampler(local_rank)
-    clocks.start()
+    def timed(fn, steps, warmup):
+        est = 0.0
+        for i in range(warmup):
+            est, _ = one(fn, i)
+        # every rank times the same number of searches: K steps x `inner` searches, >= MIN_TIMED_SECONDS in total
+        est = D.max([est])[0]
+        inner = max(1, int(math.ceil(MIN_TIMED_SECONDS / max(est * steps, 1e-9))))
+        D.barrier()
+        per_search, per_step, kern, visits = [], [], 0.0, None
+        i = 0
+        for _ in range(steps):
+            acc = 0.0
+            for _ in range(inner):
+                dt, out = one(fn, i)
+                i += 1
+                acc += dt
+                per_search.append(1000.0 * dt)
+                kern += out.device_ms
+                visits = out.visit_counts
+            per_step.append(1000.0 * acc)
+        D.barrier()
+        return dict(wall=sum(per_step) / 1000.0, kern_ms=kern, searches=steps * inner, inner=inner,
+                    per_search=per_search, per_step=per_step, visits=visits)
+
+    clocks = ClockSampler(local_rank) if headline else None
+    if clocks:
+        clocks.start()
     launches0 = eng.launch_count
-    wall, kern_ms, visits = timed(step_device, args.steps, args.warmup)
+    dv = timed(search_device, args.steps, args.warmup)
     launches = eng.launch_count - launches0
-    clk = clocks.stop()
-    wall_e2e, _, visits_h = timed(step_host, args.steps, args.warmup)
-    assert int(numpy.asarray(visits_h).sum()) == B * N
+    clk = clocks.stop() if clocks else None
+    hv = timed(search_host, args.steps, args.warmup)
+    assert int(numpy.asarray(hv["visits"]).sum()) == B * N
     kernel_split = {}
-    if game != "cartpole" and rank == 0:
+    if game != "cartpole":
         eng.kernel_timing(True)
         eng.kernel_times()
         flush.fill_(7)
         torch.cuda.synchronize()
-        step_device(0)
+        search_device(0)
         kernel_split = eng.kernel_times()
         eng.kernel_timing(False)
 
-    # max over ranks + the single counter all-gather of the reporting step
-    t = torch.tensor([wall, wall_e2e, kern_ms], dtype=torch.float64, device=dev)
-    counts = torch.tensor([B * args.steps, B * args.steps * N], dtype=torch.int64, device=dev)
-    if dist is not None:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        gathered = [torch.zeros_like(counts) for _ in range(world)]
-        dist.all_gather(gathered, counts)
-        total_steps = int(sum(int(g[0]) for g in gathered))
+    # slowest rank's time; ONE all-gather of the per-rank counters of this reporting step
+    wall, wall_e2e, kern_ms = D.max([dv["wall"], hv["wall"], dv["kern_ms"]])
+    table, totals = parallel.gather_counters(D.dist, 0, B * dv["searches"], B * dv["searches"] * N, device=dev)
+    total_steps = totals[1]
+    hbm_peak, bf16_peak, peak_kind = load_peaks()
+    traffic = load_traffic()
+    value = total_steps / wall
+    kern_s = kern_ms / 1000.0 / dv["searches"]
+    if game == "cartpole":
+        # dominant kernel: the fused search kernel, one launch per search (HBM roofline)
+        alg_bytes = B * (N * bytes_per_sim + eng.obs_elems * 4 + A * 8 + A * 4 + 8)
+        achieved = alg_bytes / kern_s / 1e9
+        tr = traffic.get("fc_search_kernel", {})
+        roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+                    "frac": achieved / hbm_peak, "traffic": tr.get("dram_bytes_per_launch"), "traffic_source": tr.get("source"),
+                    "peak_kind": peak_kind, "kernel": "fc_search_kernel", "algorithmic_bytes_per_launch": alg_bytes,
+                    "avg_launch_us": 1e6 * kern_s,
+                    "note": "tree + hidden states live in shared memory for FC nets: measured DRAM traffic is a fraction "
+                            "of the algorithmic bytes, the kernel is issue/latency-bound, not HBM-bound"}
     else:
-        total_steps = int(counts[0])
-    wall, wall_e2e, kern_ms = (float(x) for x in t.tolist())
+        # residual nets: tensor roofline for the dominant kernel, timed live with CUDA event pairs around every
+        # launch of one extra (untimed) search (mz_kernel_timing); algorithmic FLOPs = the 3x3 convolutions that kernel class
+        # executes in one search (2*H*W*Cin*Cout*9 each).  Tensor peak = the measured dense bf16 figure whatever the operand
+        # split (the x3 mode issues 3 MMAs per algorithmic MMA: its useful-FLOP fraction is reported, not its issue rate).
+        f0, f1 = NET_FLOPS[game]
+        flops = B * (f0 + N * f1)
+        conv_flops = B * conv3x3_flops(spec, N)
+        split = {k: {"ms": v[0], "launches": v[1]} for k, v in kernel_split.items() if v[1]}
+        total_ms = sum(v["ms"] for v in split.values()) or 1.0
+        for v in split.values():
+            v["share"] = v["ms"] / total_ms
+        conv_classes = [k for k in ("conv_tower_tc_kernel", "small_tower_kernel", "conv3x3_kernel") if k in split]
+        dominant = max(conv_classes, key=lambda k: split[k]["ms"]) if conv_classes else "other"
+        conv_ms = sum(split[k]["ms"] for k in conv_classes) or total_ms
+        dom = split.get(dominant, {"ms": total_ms, "launches": 1})
+        # the dominant class's share of the conv FLOPs ~ its share of the conv time is NOT assumed: classes other than the
+        # dominant one only run the stem / DownSample convs, a few % of the FLOPs; achieved uses ALL conv FLOPs over ALL conv time
+        achieved = conv_flops / (conv_ms / 1000.0) / 1e12
+        tr = traffic.get(dominant + ":" + game, traffic.get(dominant, {}))
+        roofline = {"bound": "tensor", "achieved": achieved, "peak": bf16_peak, "unit": "TFLOP/s",
+                    "frac": achieved / bf16_peak, "traffic": tr.get("dram_bytes_per_launch"), "traffic_source": tr.get("source"),
+                    "peak_kind": peak_kind + " dense bf16 (sustained)",
+                    "kernel": dominant, "launches_per_search": dom["launches"],
+                    "avg_launch_us": 1000.0 * dom["ms"] / max(dom["launches"], 1),
+                    "algorithmic_flops_per_launch": conv_flops / max(dom["launches"], 1),
+                    "kernel_split": split,
+                    "step_level": {"algorithmic_flops_per_search": flops, "achieved": flops / kern_s / 1e12,
+                                   "frac": flops / kern_s / 1e12 / bf16_peak}}
+    sub = {
+        "workload": name, "value": value, "unit": "env-steps/s", "sims_per_sec": value * N,
+        "value_is": "search only (no environment step); see loop",
+        "dtype": numerics, "games_per_gpu": B, "num_simulations": N,
+        "steps": args.steps, "searches_per_step": dv["inner"], "ms_per_step": 1000.0 * wall / args.steps,
+        "ms_per_search": percentiles(dv["per_search"]), "timed_seconds": wall,
+        "kernel_ms_per_search": kern_ms / dv["searches"],
+        "e2e": {"value": B * world * hv["searches"] / wall_e2e, "unit": "env-steps/s",
+                "h2d_bytes_per_step": int(hv["inner"] * B * (eng.obs_elems * 4 + A * 8 + 8)),
+                "d2h_bytes_per_step": int(hv["inner"] * B * (A * 4 + 8 + 4 + 4 + 4 + A * 8 + 16)),
+                "ms_per_search": percentiles(hv["per_search"]), "searches_per_step": hv["inner"]},
+        "gpu_launches": int(launches), "roofline": roofline, "per_rank_counters": table,
+    }
+    if clk:
+        sub["clocks"] = clk
+    eng.close()
+    del flush, dev_obs, dev_noise
+    torch.cuda.empty_cache()
+    if with_loop:
+        try:
+            sub["loop"] = selfplay_loop(game, B, N, local_rank, rank, world, D)
+        except Exception as e:                           # never lose the line over the loop measurement
+            sub["loop"] = {"error": repr(e)}
+    if mode:
+        if prev_mode is None:
+            os.environ.pop("MZ_TC_MODE", None)
+        else:
+            os.environ["MZ_TC_MODE"] = prev_mode
+    return sub
+
+
+def selfplay_loop(game, B, N, device, rank, world, D):
+    """env-steps/s of the full loop through the public API: `SelfPlay.play_moves` over B games per rank for >= 1 s."""
+    from muzero_general_b200 import parallel
+    from muzero_general_b200 import self_play as sp
+    from muzero_general_b200.games import load_game_module
+    from muzero_general_b200.netspec import netspec_from_config, synthetic_weights
+    mod = load_game_module(game)
+    cfg = mod.MuZeroConfig()
+    cfg.num_parallel_games, cfg.rng_mode, cfg.num_simulations = B, "philox", N
+    spec = netspec_from_config(cfg)
+    worker = sp.SelfPlay({"weights": synthetic_weights(spec, 0)}, mod.Game, cfg, seed=0, device=device,
+                         first_game_id=rank * B)
+    worker.play_moves(3, 1.0)                                          # warm-up
+    t0 = time.perf_counter()
+    worker.play_moves(2, 1.0)
+    est = D.max([(time.perf_counter() - t0) / 2])[0]
+    moves = max(4, int(math.ceil(MIN_TIMED_SECONDS / max(est, 1e-9))))
+    D.barrier()
+    steps0, games0 = worker.env_steps, worker.played_games
+    t0 = time.perf_counter()
+    finished = worker.play_moves(moves, 1.0)
+    import torch
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    lengths = [len(g.root_values) for g in finished[:64]]              # touch a few histories: they must be real
+    dt_max = D.max([dt])[0]
+    table, totals = parallel.gather_counters(D.dist, worker.played_games - games0, worker.env_steps - steps0,
+                                             (worker.env_steps - steps0) * N, device=torch.device("cuda", device))
+    res = {"value": totals[1] / dt_max, "unit": "env-steps/s", "env_steps": int(totals[1]), "seconds": dt_max,
+           "moves": moves, "games_finished": int(totals[0]), "mean_finished_length": float(numpy.mean(lengths)) if lengths else None,
+           "path": worker.loop_path,
+           "includes": "search + environment step + root noise + action sampling + GameHistory hand-over, per move"}
+    worker.close()
+    return res
+
+
+# ----------------------------------------------------------------------------- main
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--workload", default=DEFAULT_WORKLOAD)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--extras", default=None, help="comma-separated extra workloads (name or name@tc-mode)")
+    ap.add_argument("--no-extras", action="store_true")
+    ap.add_argument("--no-loop", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "ours":
+        args.warmup = max(args.warmup, 3)
+    base = args.workload.partition("@")[0]
+    if base not in WORKLOADS:
+        raise SystemExit(f"unknown workload {args.workload}; known: {sorted(WORKLOADS)}")
+
+    game, B, N, _ = WORKLOADS[base]
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    config = {"workload": args.workload, "game": game, "games_per_gpu": B, "num_simulations": N,
+              "net": "fullyconnected" if game == "cartpole" else "resnet", "weights": "synthetic seed 0",
+              "l2": "256 MiB buffer written before every timed search",
+              "step": f"searches_per_step searches so that steps x step >= {MIN_TIMED_SECONDS} s",
+              "value_is": "search only; loop = the whole self-play loop", "parallelism": f"games sharded x{world}"}
+
+    # ------------------------------------------------------------------ reference arm (CPU)
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        steps = max(1, args.steps)
+        per_step = max(2.0, min(20.0, 120.0 / (steps + args.warmup)))
+        arm = CpuArm(game, N)
+        for _ in range(args.warmup):
+            arm.run(1.0)
+        total, wall = 0, 0.0
+        for _ in range(steps):
+            _, s, w = arm.run(per_step)
+            total += s; wall += w
+        arm.close()
+        v = total / wall
+        sample = (f"{steps} steps x {per_step:.1f}s of batch-1 MCTS.run (N={N}) on {arm.cores} processes, "
+                  "one pinned per physical core")
+        print(json.dumps({
+            "impl": "reference", "metric": "self-play env-steps/sec", "value": v, "unit": "env-steps/s",
+            "n_gpus": args.gpus, "steps": steps, "warmup": args.warmup, "ms_per_step": 1000.0 * wall / steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32+f64",
+            "data": "synthetic", "config": config, "sims_per_sec": v * N,
+            "cpu_baseline": {"value": v, "unit": "env-steps/s", "cores": arm.cores, "kind": "port", "sample": sample},
+            "e2e": {"value": v, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        }))
+        return 0
+
+    # ------------------------------------------------------------------ our arm (GPU)
+    import torch
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    dist = None
+    if world > 1:
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"          # keep stdout to the single JSON line
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    torch.cuda.set_device(local_rank)
+    D = Dist(dist, torch.device("cuda", local_rank))
+
+    head = run_workload(args.workload, args, D, rank, local_rank, world, with_loop=not args.no_loop, headline=True)
+    extras = {}
+    names = [] if args.no_extras else (args.extras.split(",") if args.extras else DEFAULT_EXTRAS)
+    for nme in names:
+        if not nme or nme == args.workload:
+            continue
+        try:
+            extras[nme] = run_workload(nme, args, D, rank, local_rank, world,
+                                       with_loop=(not args.no_loop and "@" not in nme), headline=False)
+        except Exception as e:
+            if world > 1:
+                raise                                   # a rank that skips its collectives would hang the others
+            extras[nme] = {"error": repr(e)}
 
     if rank == 0:
-        value = total_steps / wall
-        hbm_peak, bf16_peak, peak_kind = load_peaks()
-        kern_s = kern_ms / 1000.0 / args.steps
-        if game == "cartpole":
-            # dominant kernel: the fused search kernel, one launch per step (HBM roofline)
-            alg_bytes = B * (N * bytes_per_sim + eng.obs_elems * 4 + A * 8 + A * 4 + 8)
-            achieved = alg_bytes / kern_s / 1e9
-            roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                        "frac": achieved / hbm_peak, "traffic": 242944, "peak_kind": peak_kind,
-                        "kernel": "fc_search_kernel", "algorithmic_bytes_per_launch": alg_bytes,
-                        "note": "tree + hidden states live in shared memory for FC nets: measured DRAM traffic "
-                                "(profiles/r01_fc_search_ncu.md) is 0.24 MB per launch, the kernel is issue/latency-"
-                                "bound (47.6 % of peak issue rate), not HBM-bound"}
-        else:
-            # residual nets: tensor roofline for the dominant kernel, timed live with CUDA event pairs
-            # around every launch of one extra (untimed) step (mz_kernel_timing); algorithmic FLOPs = the 3x3
-            # convolutions that kernel class executes in one step (2*H*W*Cin*Cout*9 each).  fp16 tensor-core rate
-            # = the measured dense bf16 figure.  The whole-step figure (all kernels) is kept as `step_level`.
-            f0, f1 = NET_FLOPS[game]
-            flops = B * (f0 + N * f1)
-            conv_flops = B * conv3x3_flops(spec, N)
-            split = {k: {"ms": v[0], "launches": v[1]} for k, v in kernel_split.items() if v[1]}
-            total_ms = sum(v["ms"] for v in split.values()) or 1.0
-            for v in split.values():
-                v["share"] = v["ms"] / total_ms
-            dominant = max(("conv_tower_tc_kernel", "conv3x3_kernel"), key=lambda k: split.get(k, {"ms": 0.0})["ms"])
-            dom = split.get(dominant, {"ms": total_ms, "launches": 1})
-            achieved = conv_flops / (dom["ms"] / 1000.0) / 1e12
-            roofline = {"bound": "tensor", "achieved": achieved, "peak": bf16_peak, "unit": "TFLOP/s",
-                        "frac": achieved / bf16_peak, "traffic": TRAFFIC.get(game), "peak_kind": peak_kind + " dense bf16 (sustained)",
-                        "kernel": dominant, "launches_per_step": dom["launches"],
-                        "avg_launch_us": 1000.0 * dom["ms"] / max(dom["launches"], 1),
-                        "algorithmic_flops_per_launch": conv_flops / max(dom["launches"], 1),
-                        "kernel_split": split,
-                        "step_level": {"algorithmic_flops_per_step": flops, "achieved": flops / kern_s / 1e12,
-                                       "frac": flops / kern_s / 1e12 / bf16_peak},
-                        "note": ("tcgen05 towers: conv_tower_resident_kernel up to 1184 boards per launch (activations stay in "
-                                 "shared memory), conv_tower_tc_kernel above; fp16 operands, fp32 accumulate; 84 of 128 rows "
-                                 "of every MMA are real board positions" if dominant == "conv_tower_tc_kernel" else
-                                 "fp32 CUDA-core direct convolution (strict numerics): the tensor peak is not reachable by design")}
         out = {
-            "metric": "self-play env-steps/sec", "value": value, "unit": "env-steps/s", "n_gpus": world,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * wall / args.steps,
+            "metric": "self-play env-steps/sec", "value": head["value"], "unit": "env-steps/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": head["ms_per_step"],
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": ("f32 nets + f64 tree statistics" if game != "connect4" or os.environ.get("MZ_NO_TC") == "1" else
-                      "fp16 operands / f32 accumulate (tensor-core towers), f32 heads, f64 tree statistics"),
-            "data": "synthetic", "config": config,
-            "sims_per_sec": value * N,
-            "kernel_ms_per_step": kern_ms / args.steps,
-            "e2e": {"value": total_steps / wall_e2e, "unit": "env-steps/s",
-                    "h2d_bytes_per_step": int(B * (eng.obs_elems * 4 + A * 8 + 8)),
-                    "d2h_bytes_per_step": int(B * (A * 4 + 8 + 4 + 4 + 4 + A * 8 + 16))},
-            "gpu_launches": int(launches),
-            "clocks": clk,
-            "roofline": roofline,
+            "dtype": head["dtype"], "data": "synthetic", "config": dict(config, searches_per_step=head["searches_per_step"]),
+            "sims_per_sec": head["sims_per_sec"], "ms_per_search": head["ms_per_search"],
+            "kernel_ms_per_search": head["kernel_ms_per_search"], "timed_seconds": head["timed_seconds"],
+            "e2e": head["e2e"], "gpu_launches": head["gpu_launches"], "clocks": head.get("clocks"),
+            "roofline": head["roofline"],
         }
-        if world == 1 and game in ("cartpole", "tictactoe", "connect4"):
-            # the whole self-play loop through the reference-shaped API (SelfPlay.play_games): search + host
-            # environment stepping (vectorised numpy envs) + action sampling + GameHistory assembly
-            try:
-                out["selfplay_loop"] = selfplay_loop(game, B, N, local_rank, moves=12 if game == "cartpole" else 6)
-            except Exception as e:                       # never lose the headline line over the extra
-                out["selfplay_loop"] = {"error": repr(e)}
+        if "loop" in head:
+            out["loop"] = head["loop"]
+        if extras:
+            out["workloads"] = extras
         if world == 1 and not args.no_cpu_baseline:
-            cores = host_cores()
-            v, searches, w = cpu_baseline(game, N, args.cpu_seconds, cores)
-            out["cpu_baseline"] = {"value": v, "unit": "env-steps/s", "cores": cores, "kind": "port",
-                                   "sample": f"{searches} batch-1 MCTS.run calls (N={N}) in {w:.1f}s on {cores} processes"}
+            arm = CpuArm(game, N)
+            v, searches, w = arm.run(args.cpu_seconds)
+            arm.close()
+            out["cpu_baseline"] = {"value": v, "unit": "env-steps/s", "cores": arm.cores, "kind": "port",
+                                   "sample": f"{searches} batch-1 MCTS.run calls (N={N}) in {w:.1f}s on {arm.cores} processes, "
+                                             "one pinned per physical core"}
         print(json.dumps(out))
-    eng.close()
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()

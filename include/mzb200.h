@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define MZ_ABI_VERSION 1
+#define MZ_ABI_VERSION 2
 #define MZ_MAX_LAYERS 8          /* hidden layers per MLP head */
 #define MZ_MAX_ACTIONS 32        /* |action_space| supported by the tree kernels */
 
@@ -199,8 +199,9 @@ double mz_last_search_ms(const MzHandle* h);
 /* Per-kernel-class device timing for the roofline line of bench.py.  While enabled (process-wide), the step-wise
  * pipeline runs launch by launch with a CUDA event pair around every kernel instead of replaying its CUDA graph.
  * mz_kernel_times synchronises and returns the accumulated milliseconds / launch counts since the last call:
- * [0] tree_step_kernel, [1] conv_tower_tc_kernel, [2] heads_kernel, [3] conv3x3_kernel (CUDA cores), [4] other. */
-#define MZ_KERNEL_CLASSES 5
+ * [0] tree_step_kernel, [1] conv_tower_tc_kernel (tcgen05 towers, resident or streaming), [2] heads_kernel,
+ * [3] conv3x3_kernel (CUDA cores, one conv per launch), [4] other, [5] small_tower_kernel (fused CUDA-core towers). */
+#define MZ_KERNEL_CLASSES 6
 int mz_kernel_timing(MzHandle* h, int32_t enable);
 int mz_kernel_times(MzHandle* h, double* ms, int64_t* count);
 
@@ -209,6 +210,73 @@ int mz_kernel_times(MzHandle* h, double* ms, int64_t* count);
  * GEMM (1; C = 64, H <= 6, W <= 7).  w is [C][C][3][3] as in the reference state_dict. */
 int mz_debug_conv3x3(int device, int32_t n, int32_t C, int32_t H, int32_t W, const float* x, const float* w,
                      const float* bias, const float* residual, int32_t relu, int32_t use_tensor_cores, float* out);
+
+/* Arithmetic the handle's search path computes in, e.g. "f32 nets + f64 tree statistics" (bench.py's dtype). */
+const char* mz_numerics(const MzHandle* h);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Device-resident self-play: the per-move loop of SelfPlay.play_game (self_play.py:110-183) for
+ * max_games environments whose state lives on the GPU.  One move = [batched MCTS.run on the device-side observations]
+ * -> [visit-count sampling, self_play.py:222-245] -> [environment step] -> [one struct-of-arrays record per game].
+ * A finished game (done, or max_moves reached, self_play.py:129-131) is packed into a pinned host staging area by the
+ * kernel that detects it and its slot starts a new game with a fresh global id (old id + max_games); the host reads
+ * finished games only.  Root noise, the first simulation's tie and the action sample come from Philox4x32-10 streams
+ * keyed (seed, game id, move), so a game's history does not depend on the batch or on the number of ranks.
+ * Requires config.stacked_observations == 0 (the observation is the environment's own). */
+enum { MZ_ENV_CARTPOLE = 0, MZ_ENV_TICTACTOE = 1, MZ_ENV_CONNECT4 = 2 };
+
+typedef struct MzSelfPlayDesc {
+    int32_t env;                  /* MZ_ENV_*: games/cartpole.py:131-174 (restated cart-pole physics),
+                                     games/tictactoe.py:243-306, games/connect4.py:220-305 */
+    int32_t max_moves;            /* config.max_moves */
+    int32_t temperature_threshold;/* config.temperature_threshold, 0 = None (self_play.py:153-156) */
+    int32_t reward_scale;         /* board games: reward of the winning move (tictactoe.py:144: 20, connect4.py:144: 10) */
+    int64_t first_game_id;        /* slot g plays the global games first_game_id + g + k * max_games, k = 0, 1, ... */
+    uint64_t staging_bytes;       /* capacity of the finished-game staging area, 0 = library default */
+} MzSelfPlayDesc;
+
+/* Optional per-move overrides (HOST pointers, n = max_games; only with n_moves == 1).  Parity tests drive the
+ * environments with recorded actions and replay the host loop's draws through them. */
+typedef struct MzSelfPlayInject {
+    const int32_t* forced_action; /* [n] play this action instead of sampling (entries < 0: sample) */
+    const double* uniform;        /* [n] the uniform of the action sample instead of the Philox draw */
+    const double* noise;          /* [n, A] root Dirichlet noise by action id instead of the device draw */
+    const int32_t* first_index;   /* [n] first-simulation pick instead of the device draw */
+} MzSelfPlayInject;
+
+typedef struct MzSelfPlayStats {
+    int64_t env_steps;            /* moves played since mz_selfplay_begin (all slots) */
+    int64_t games_finished;       /* games packed into the staging area since mz_selfplay_begin */
+    int64_t staged_bytes;         /* bytes waiting in the staging area */
+    int32_t staged_games;         /* games waiting in the staging area */
+    int32_t parked_slots;         /* finished games that did not fit into the staging area and wait for a drain */
+    double device_ms;             /* device time of the last mz_selfplay_moves call */
+} MzSelfPlayStats;
+
+/* Current device-side view of the environments (HOST output pointers, any may be NULL). */
+typedef struct MzSelfPlayPeek {
+    float* obs;                   /* [n, obs_elems] observation the next search will see */
+    uint8_t* legal_mask;          /* [n, A] */
+    int32_t* to_play;             /* [n] */
+    int64_t* game_id;             /* [n] */
+    int32_t* move_index;          /* [n] moves played in the slot's current game */
+    int32_t* last_action;         /* [n] action played by the last move (-1 before the first) */
+} MzSelfPlayPeek;
+
+/* Staged games are self-describing blocks laid out back to back (all little endian, 8-byte aligned):
+ *   int64 game_id; int32 slot; int32 length T; int32 first_to_play; int32 obs_elems O; int32 actions A; int32 bytes;
+ *   double root_value[T]; int32 visit_counts[T][A]; int32 action[T]; float reward[T]; int32 to_play[T] (after the move);
+ *   float observation[T+1][O] (index 0 = reset observation); padding to 8 bytes.
+ * = the fields of GameHistory (self_play.py:479-511) minus the dummy first entries. */
+#define MZ_STAGED_HEADER_BYTES 32
+
+/* replaces the per-move body of SelfPlay.play_game / continuous_self_play for a whole batch (self_play.py:31-183) */
+int mz_selfplay_begin(MzHandle* h, const MzSelfPlayDesc* desc);
+int mz_selfplay_moves(MzHandle* h, int32_t n_moves, double temperature, const MzSelfPlayInject* inject, MzSelfPlayStats* stats);
+/* pointer to the staged games (pinned host memory owned by the library), valid until the next mz_selfplay_moves;
+ * marks the area as consumed */
+int mz_selfplay_drain(MzHandle* h, const void** data, uint64_t* bytes, int32_t* n_games);
+int mz_selfplay_peek(MzHandle* h, const MzSelfPlayPeek* out);
 
 #ifdef __cplusplus
 }

@@ -85,6 +85,28 @@ class MzInferenceOut(C.Structure):
                 ("hidden", C.c_void_p), ("value", C.c_void_p), ("reward", C.c_void_p)]
 
 
+class MzSelfPlayDesc(C.Structure):
+    _fields_ = [("env", C.c_int32), ("max_moves", C.c_int32), ("temperature_threshold", C.c_int32),
+                ("reward_scale", C.c_int32), ("first_game_id", C.c_int64), ("staging_bytes", C.c_uint64)]
+
+
+class MzSelfPlayInject(C.Structure):
+    _fields_ = [("forced_action", C.c_void_p), ("uniform", C.c_void_p), ("noise", C.c_void_p), ("first_index", C.c_void_p)]
+
+
+class MzSelfPlayStats(C.Structure):
+    _fields_ = [("env_steps", C.c_int64), ("games_finished", C.c_int64), ("staged_bytes", C.c_int64),
+                ("staged_games", C.c_int32), ("parked_slots", C.c_int32), ("device_ms", C.c_double)]
+
+
+class MzSelfPlayPeek(C.Structure):
+    _fields_ = [("obs", C.c_void_p), ("legal_mask", C.c_void_p), ("to_play", C.c_void_p), ("game_id", C.c_void_p),
+                ("move_index", C.c_void_p), ("last_action", C.c_void_p)]
+
+
+MZ_ENV_CARTPOLE, MZ_ENV_TICTACTOE, MZ_ENV_CONNECT4 = 0, 1, 2
+MZ_STAGED_HEADER_BYTES = 32
+
 # every symbol include/mzb200.h declares: (name, restype, argtypes)
 SYMBOLS = [
     ("mz_create", C.c_int, [C.POINTER(MzNetDesc), C.POINTER(MzSearchDesc), C.c_int, C.POINTER(C.c_void_p)]),
@@ -102,6 +124,11 @@ SYMBOLS = [
     ("mz_last_search_ms", C.c_double, [C.c_void_p]),
     ("mz_kernel_timing", C.c_int, [C.c_void_p, C.c_int32]),
     ("mz_kernel_times", C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
+    ("mz_numerics", C.c_char_p, [C.c_void_p]),
+    ("mz_selfplay_begin", C.c_int, [C.c_void_p, C.POINTER(MzSelfPlayDesc)]),
+    ("mz_selfplay_moves", C.c_int, [C.c_void_p, C.c_int32, C.c_double, C.POINTER(MzSelfPlayInject), C.POINTER(MzSelfPlayStats)]),
+    ("mz_selfplay_drain", C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64), C.POINTER(C.c_int32)]),
+    ("mz_selfplay_peek", C.c_int, [C.c_void_p, C.POINTER(MzSelfPlayPeek)]),
     ("mz_debug_conv3x3", C.c_int, [C.c_int, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
                                    C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
 ]

@@ -15,68 +15,16 @@
 #include <string>
 #include <vector>
 
-#include "kernels.h"
-#include "pipeline.h"
-#include "ktimer.h"
+#include "handle.h"
 
 using namespace mz;
 
 static thread_local std::string g_create_error;
 
-struct MzHandle {
-    MzNetDesc net;
-    MzSearchDesc search;
-    int device = 0;
-    int sm_count = 0;
-    size_t smem_cap = 0;
-    cudaStream_t stream = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    std::string err;
-    int64_t launches = 0;
-    double last_ms = 0.0;
-    // tables
-    double* d_pbc = nullptr;
-    double* d_sqrt = nullptr;
-    double* d_ucb = nullptr;           // optional host-evaluated exploration-factor table
-    // fully-connected weights
-    FcNet fc{};
-    float* d_fc_blob = nullptr;
-    bool weights_loaded = false;
-    int fc_group = 16;
-    int fc_threads = 64;
-    // residual weights + workspace
-    ResNetDevice* res = nullptr;
-    // pool
-    NodePool pool{};
-    int64_t hidden_elems = 0, obs_elems = 0;
-    int64_t pool_state_elems = 0;      // floats per hidden state as stored in the pool (layout dependent)
-    // IO arenas
-    unsigned char* d_in = nullptr;
-    unsigned char* d_out = nullptr;
-    unsigned char* h_in = nullptr;
-    unsigned char* h_out = nullptr;
-    size_t in_cap = 0, out_cap = 0;
-    // CUDA graph of the step-wise pipeline for the last seen argument set (launch-bound inner loop)
-    uint64_t graph_key = 0;
-    int graph_seen = 0;
-    cudaGraphExec_t graph_exec = nullptr;
-    int64_t graph_launches = 0;
-    // lazily allocated debug buffers
-    std::vector<void*> debug_allocs;
-    std::map<std::string, std::pair<void*, size_t>> named;
-};
-
-static int fail(MzHandle* h, int code, const std::string& msg) {
+int mz_fail(MzHandle* h, int code, const std::string& msg) {
     if (h) h->err = msg; else g_create_error = msg;
     return code;
 }
-
-#define MZ_CUDA(h, expr)                                                                          \
-    do {                                                                                          \
-        cudaError_t _e = (expr);                                                                  \
-        if (_e != cudaSuccess)                                                                    \
-            return fail(h, MZ_ECUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));          \
-    } while (0)
 
 template <typename T>
 static cudaError_t dev_alloc(T** p, size_t count) { return cudaMalloc(reinterpret_cast<void**>(p), count * sizeof(T) + 16); }
@@ -244,6 +192,7 @@ extern "C" int mz_destroy(MzHandle* h) {
     if (!h) return MZ_OK;
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
+    mz_selfplay_destroy(h);
     NodePool& p = h->pool;
     void* ptrs[] = {p.visit, p.vsum, p.mval, p.reward, p.prior, p.expansion, p.root_prior, p.hidden, p.root_visit, p.root_vsum,
                     p.root_reward, p.range, p.n_expanded, p.ties, p.max_depth, p.legal, p.path, p.path_reward, p.leaf_depth,
@@ -261,6 +210,11 @@ extern "C" int mz_destroy(MzHandle* h) {
     return MZ_OK;
 }
 
+extern "C" const char* mz_numerics(const MzHandle* h) {
+    if (!h) return "";
+    if (h->net.kind == MZ_NET_FC) return "f32 nets + f64 tree statistics";
+    return resnet_numerics(h->res);
+}
 extern "C" int64_t mz_hidden_elems(const MzHandle* h) { return h ? h->hidden_elems : 0; }
 extern "C" int64_t mz_obs_elems(const MzHandle* h) { return h ? h->obs_elems : 0; }
 extern "C" int64_t mz_launch_count(const MzHandle* h) { return h ? h->launches : 0; }
@@ -410,6 +364,87 @@ static int debug_out(MzHandle* h, const char* name, T* user, size_t count, int m
     return MZ_OK;
 }
 
+// ------------------------------------------------------------------------------------------
+// One batched search on device buffers (no synchronisation): fused FC kernel or step-wise pipeline.
+// ------------------------------------------------------------------------------------------
+int mz_dispatch_search(MzHandle* h, const SearchCall& call, bool teacher, bool trace, int flags) {
+    const int n = call.n, N = h->search.num_simulations, A = h->net.action_space;
+    int rc;
+    const bool fused = (h->net.kind == MZ_NET_FC || teacher) && !(flags & MZ_FLAG_STEPWISE);
+    if (fused) {
+        FcSearchArgs a{};
+        a.n_games = n; a.N = N; a.A = A; a.P = h->search.num_players; a.threads = h->fc_threads;
+        a.discount = h->search.discount; a.noise_frac = h->search.root_exploration_fraction; a.noise_alpha = h->search.root_dirichlet_alpha; a.seed = h->search.seed;
+        a.pbc = h->d_pbc; a.sqrtn = h->d_sqrt; a.ucb = h->d_ucb;
+        a.net = h->fc; a.blob = h->d_fc_blob;
+        if (teacher) { a.net.E = 1; a.net.maxw = 4; a.net.blob_floats = 0; a.net.A = A; }
+        a.obs = call.obs; a.legal_mask = call.legal_mask; a.to_play = call.to_play; a.add_noise = call.add_noise;
+        a.noise = call.noise; a.first_index = call.first_index; a.game_id = call.game_id; a.move_index = call.move_index;
+        a.visit_counts = call.visit_counts; a.root_value = call.root_value; a.root_predicted_value = call.root_predicted_value;
+        a.max_tree_depth = call.max_tree_depth; a.tie_count = call.tie_count; a.root_priors = call.root_priors;
+        a.value_range = call.value_range; a.teacher = call.teacher; a.trace = call.trace;
+        if (call.keep_tree) a.pool = h->pool;
+        FcLaunchInfo info{};
+        cudaError_t e = launch_fc_search(a, h->fc_group, teacher, h->sm_count, h->smem_cap, h->stream, &info);
+        if (e == cudaErrorInvalidConfiguration) {
+            // the tree does not fit in shared memory next to the weights: use the HBM node pool
+            (void)cudaGetLastError();
+            rc = run_stepwise_search(h->net, h->search, h->pool, h->d_pbc, h->d_sqrt, h->d_ucb, h->fc, h->d_fc_blob, h->res, call,
+                                     h->fc_group, h->sm_count, h->stream, &h->launches, &h->err);
+            if (rc) return rc;
+        } else if (e != cudaSuccess) {
+            return fail(h, MZ_ECUDA, std::string("fc_search launch: ") + cudaGetErrorString(e));
+        } else {
+            h->launches += 1;
+        }
+    } else {
+        // The step-wise pipeline is 16 small launches per simulation: replay it as a CUDA graph once the
+        // same argument set has been seen twice (first call runs eagerly so lazy attribute setup and
+        // allocations happen outside capture).  Debug modes (teacher / trace) always run eagerly.
+        const bool graphable = !teacher && !trace && !kt_enabled() && getenv("MZ_NO_GRAPH") == nullptr;
+        uint64_t key = 1469598103934665603ull;
+        auto mix = [&](uint64_t v) { key = (key ^ v) * 1099511628211ull; };
+        const void* ptrs[] = {call.obs, call.legal_mask, call.to_play, call.noise, call.first_index, call.game_id,
+                              call.move_index, call.visit_counts, call.root_value, call.root_predicted_value,
+                              call.max_tree_depth, call.tie_count, call.root_priors, call.value_range};
+        for (const void* q : ptrs) mix((uint64_t)(uintptr_t)q);
+        mix((uint64_t)n); mix((uint64_t)call.add_noise); mix((uint64_t)call.keep_tree);
+        auto eager = [&]() {
+            return run_stepwise_search(h->net, h->search, h->pool, h->d_pbc, h->d_sqrt, h->d_ucb, h->fc, h->d_fc_blob, h->res, call,
+                                       h->fc_group, h->sm_count, h->stream, &h->launches, &h->err);
+        };
+        if (graphable && h->graph_exec && h->graph_key == key) {
+            MZ_CUDA(h, cudaGraphLaunch(h->graph_exec, h->stream));
+            h->launches += h->graph_launches;
+        } else if (graphable && h->graph_key == key && h->graph_seen >= 1) {
+            if (h->graph_exec) { cudaGraphExecDestroy(h->graph_exec); h->graph_exec = nullptr; }
+            const int64_t l0 = h->launches;
+            MZ_CUDA(h, cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+            rc = eager();
+            cudaGraph_t graph = nullptr;
+            cudaError_t ce = cudaStreamEndCapture(h->stream, &graph);
+            if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+            if (ce != cudaSuccess) return fail(h, MZ_ECUDA, std::string("graph capture: ") + cudaGetErrorString(ce));
+            ce = cudaGraphInstantiate(&h->graph_exec, graph, 0);
+            cudaGraphDestroy(graph);
+            if (ce != cudaSuccess) { h->graph_exec = nullptr; return fail(h, MZ_ECUDA, std::string("graph instantiate: ") + cudaGetErrorString(ce)); }
+            h->graph_launches = h->launches - l0;
+            MZ_CUDA(h, cudaGraphLaunch(h->graph_exec, h->stream));
+        } else {
+            rc = eager();
+            if (rc) return rc;
+            if (graphable) {
+                if (h->graph_key != key) {
+                    if (h->graph_exec) { cudaGraphExecDestroy(h->graph_exec); h->graph_exec = nullptr; }
+                    h->graph_key = key; h->graph_seen = 0;
+                }
+                h->graph_seen += 1;
+            }
+        }
+    }
+    return MZ_OK;
+}
+
 extern "C" int mz_search(MzHandle* h, const MzSearchIO* io) {
     if (!h || !io) return fail(h, MZ_EINVAL, "mz_search: null argument");
     const int n = io->n_games, N = h->search.num_simulations, A = h->net.action_space;
@@ -484,78 +519,7 @@ extern "C" int mz_search(MzHandle* h, const MzSearchIO* io) {
     call.keep_tree = (io->flags & MZ_FLAG_KEEP_TREE) != 0;
 
     MZ_CUDA(h, cudaEventRecord(h->ev0, h->stream));
-    const bool fused = (h->net.kind == MZ_NET_FC || teacher) && !(io->flags & MZ_FLAG_STEPWISE);
-    if (fused) {
-        FcSearchArgs a{};
-        a.n_games = n; a.N = N; a.A = A; a.P = h->search.num_players; a.threads = h->fc_threads;
-        a.discount = h->search.discount; a.noise_frac = h->search.root_exploration_fraction; a.noise_alpha = h->search.root_dirichlet_alpha; a.seed = h->search.seed;
-        a.pbc = h->d_pbc; a.sqrtn = h->d_sqrt; a.ucb = h->d_ucb;
-        a.net = h->fc; a.blob = h->d_fc_blob;
-        if (teacher) { a.net.E = 1; a.net.maxw = 4; a.net.blob_floats = 0; a.net.A = A; }
-        a.obs = call.obs; a.legal_mask = call.legal_mask; a.to_play = call.to_play; a.add_noise = call.add_noise;
-        a.noise = call.noise; a.first_index = call.first_index; a.game_id = call.game_id; a.move_index = call.move_index;
-        a.visit_counts = call.visit_counts; a.root_value = call.root_value; a.root_predicted_value = call.root_predicted_value;
-        a.max_tree_depth = call.max_tree_depth; a.tie_count = call.tie_count; a.root_priors = call.root_priors;
-        a.value_range = call.value_range; a.teacher = call.teacher; a.trace = call.trace;
-        if (call.keep_tree) a.pool = h->pool;
-        FcLaunchInfo info{};
-        cudaError_t e = launch_fc_search(a, h->fc_group, teacher, h->sm_count, h->smem_cap, h->stream, &info);
-        if (e == cudaErrorInvalidConfiguration) {
-            // the tree does not fit in shared memory next to the weights: use the HBM node pool
-            (void)cudaGetLastError();
-            rc = run_stepwise_search(h->net, h->search, h->pool, h->d_pbc, h->d_sqrt, h->d_ucb, h->fc, h->d_fc_blob, h->res, call,
-                                     h->fc_group, h->sm_count, h->stream, &h->launches, &h->err);
-            if (rc) return rc;
-        } else if (e != cudaSuccess) {
-            return fail(h, MZ_ECUDA, std::string("fc_search launch: ") + cudaGetErrorString(e));
-        } else {
-            h->launches += 1;
-        }
-    } else {
-        // The step-wise pipeline is 16 small launches per simulation: replay it as a CUDA graph once the
-        // same argument set has been seen twice (first call runs eagerly so lazy attribute setup and
-        // allocations happen outside capture).  Debug modes (teacher / trace) always run eagerly.
-        const bool graphable = !teacher && !io->trace && !kt_enabled() && getenv("MZ_NO_GRAPH") == nullptr;
-        uint64_t key = 1469598103934665603ull;
-        auto mix = [&](uint64_t v) { key = (key ^ v) * 1099511628211ull; };
-        const void* ptrs[] = {call.obs, call.legal_mask, call.to_play, call.noise, call.first_index, call.game_id,
-                              call.move_index, call.visit_counts, call.root_value, call.root_predicted_value,
-                              call.max_tree_depth, call.tie_count, call.root_priors, call.value_range};
-        for (const void* q : ptrs) mix((uint64_t)(uintptr_t)q);
-        mix((uint64_t)n); mix((uint64_t)call.add_noise); mix((uint64_t)call.keep_tree);
-        auto eager = [&]() {
-            return run_stepwise_search(h->net, h->search, h->pool, h->d_pbc, h->d_sqrt, h->d_ucb, h->fc, h->d_fc_blob, h->res, call,
-                                       h->fc_group, h->sm_count, h->stream, &h->launches, &h->err);
-        };
-        if (graphable && h->graph_exec && h->graph_key == key) {
-            MZ_CUDA(h, cudaGraphLaunch(h->graph_exec, h->stream));
-            h->launches += h->graph_launches;
-        } else if (graphable && h->graph_key == key && h->graph_seen >= 1) {
-            if (h->graph_exec) { cudaGraphExecDestroy(h->graph_exec); h->graph_exec = nullptr; }
-            const int64_t l0 = h->launches;
-            MZ_CUDA(h, cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
-            rc = eager();
-            cudaGraph_t graph = nullptr;
-            cudaError_t ce = cudaStreamEndCapture(h->stream, &graph);
-            if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
-            if (ce != cudaSuccess) return fail(h, MZ_ECUDA, std::string("graph capture: ") + cudaGetErrorString(ce));
-            ce = cudaGraphInstantiate(&h->graph_exec, graph, 0);
-            cudaGraphDestroy(graph);
-            if (ce != cudaSuccess) { h->graph_exec = nullptr; return fail(h, MZ_ECUDA, std::string("graph instantiate: ") + cudaGetErrorString(ce)); }
-            h->graph_launches = h->launches - l0;
-            MZ_CUDA(h, cudaGraphLaunch(h->graph_exec, h->stream));
-        } else {
-            rc = eager();
-            if (rc) return rc;
-            if (graphable) {
-                if (h->graph_key != key) {
-                    if (h->graph_exec) { cudaGraphExecDestroy(h->graph_exec); h->graph_exec = nullptr; }
-                    h->graph_key = key; h->graph_seen = 0;
-                }
-                h->graph_seen += 1;
-            }
-        }
-    }
+    if ((rc = mz_dispatch_search(h, call, teacher, io->trace != nullptr, io->flags))) return rc;
     MZ_CUDA(h, cudaEventRecord(h->ev1, h->stream));
     if (host && call.out_bytes)
         MZ_CUDA(h, cudaMemcpyAsync(h->h_out, h->d_out, call.out_bytes, cudaMemcpyDeviceToHost, h->stream));

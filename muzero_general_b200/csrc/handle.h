@@ -1,0 +1,72 @@
+// The library handle and the helpers shared by the entry-point files (abi.cu, selfplay.cu).
+#pragma once
+#include <map>
+#include <string>
+#include <vector>
+
+#include "kernels.h"
+#include "pipeline.h"
+#include "ktimer.h"
+
+struct MzSelfPlay;                     // device-resident self-play state (selfplay.cu)
+using namespace mz;
+
+struct MzHandle {
+    MzNetDesc net;
+    MzSearchDesc search;
+    int device = 0;
+    int sm_count = 0;
+    size_t smem_cap = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    std::string err;
+    int64_t launches = 0;
+    double last_ms = 0.0;
+    // tables
+    double* d_pbc = nullptr;
+    double* d_sqrt = nullptr;
+    double* d_ucb = nullptr;           // optional host-evaluated exploration-factor table
+    // fully-connected weights
+    FcNet fc{};
+    float* d_fc_blob = nullptr;
+    bool weights_loaded = false;
+    int fc_group = 16;
+    int fc_threads = 64;
+    // residual weights + workspace
+    ResNetDevice* res = nullptr;
+    // pool
+    NodePool pool{};
+    int64_t hidden_elems = 0, obs_elems = 0;
+    int64_t pool_state_elems = 0;      // floats per hidden state as stored in the pool (layout dependent)
+    // IO arenas
+    unsigned char* d_in = nullptr;
+    unsigned char* d_out = nullptr;
+    unsigned char* h_in = nullptr;
+    unsigned char* h_out = nullptr;
+    size_t in_cap = 0, out_cap = 0;
+    // CUDA graph of the step-wise pipeline for the last seen argument set (launch-bound inner loop)
+    uint64_t graph_key = 0;
+    int graph_seen = 0;
+    cudaGraphExec_t graph_exec = nullptr;
+    int64_t graph_launches = 0;
+    // lazily allocated debug buffers
+    std::vector<void*> debug_allocs;
+    std::map<std::string, std::pair<void*, size_t>> named;
+    MzSelfPlay* sp = nullptr;          // mz_selfplay_begin
+};
+
+int mz_fail(MzHandle* h, int code, const std::string& msg);
+static inline int fail(MzHandle* h, int code, const std::string& msg) { return mz_fail(h, code, msg); }
+
+#define MZ_CUDA(h, expr)                                                                          \
+    do {                                                                                          \
+        cudaError_t _e = (expr);                                                                  \
+        if (_e != cudaSuccess)                                                                    \
+            return fail(h, MZ_ECUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));          \
+    } while (0)
+
+
+// One batched search on device buffers, enqueued on h->stream without synchronising: the fused FC kernel or the
+// step-wise pipeline (eager for the first two calls with a given argument set, then a CUDA-graph replay).
+int mz_dispatch_search(MzHandle* h, const mz::SearchCall& call, bool teacher, bool trace, int flags);
+void mz_selfplay_destroy(MzHandle* h);

@@ -524,8 +524,12 @@ ResNetDevice* resnet_create(const MzNetDesc& net, int max_batch, int sm_count, s
         max_elems = std::max(max_elems, (size_t)net.channels * H * W);
     }
     max_elems = std::max(max_elems, (size_t)(net.channels + 1) * r->hh * r->hw);
+    // MZ_TC_MODE = "off": fp32 CUDA-core towers everywhere; anything else: tcgen05 towers where the shape allows
+    // (conv_tc.cu).  MZ_NO_TC=1 is the older spelling of "off".
     const char* no_tc = getenv("MZ_NO_TC");
-    r->use_tc = !net.downsample && conv_tc_supported(net.channels, r->hh, r->hw) && !(no_tc && no_tc[0] == '1');
+    const char* tc_mode = getenv("MZ_TC_MODE");
+    const bool tc_off = (no_tc && no_tc[0] == '1') || (tc_mode && strcmp(tc_mode, "off") == 0);
+    r->use_tc = !net.downsample && conv_tc_supported(net.channels, r->hh, r->hw) && !tc_off;
     const char* no_fuse = getenv("MZ_NO_FUSE");
     r->fuse_small = !(no_fuse && no_fuse[0] == '1');
     r->state_elems = r->use_tc ? conv_tc_board_elems() : r->C * r->hh * r->hw;
@@ -926,7 +930,7 @@ struct Runner {
             t.residual = (i >= (stem ? 1u : 0u) && ((i - (stem ? 1 : 0)) & 1)) ? 1 : 0;     // second conv of a block
         }
         if (!small_tower_supported(a)) return 0;
-        kt_begin(KT_CONV, stream);
+        kt_begin(KT_SMALL, stream);
         cudaError_t e = launch_small_tower(a, r->sm_count, stream);
         kt_end(stream);
         if (e != cudaSuccess) { fail("small_tower launch", e); return -1; }
@@ -1050,6 +1054,10 @@ static int resnet_inference_tc(ResNetDevice* r, const InferCall& c, cudaStream_t
 }
 
 int resnet_state_elems(const ResNetDevice* r) { return r->state_elems; }
+const char* resnet_numerics(const ResNetDevice* r) {
+    return r->use_tc ? "fp16 operands / f32 accumulate (tensor-core towers), f32 heads, f64 tree statistics"
+                     : "f32 nets + f64 tree statistics";
+}
 
 // Stand-alone conv3x3 (+bias, +residual, +ReLU) on host NCHW data through either implementation.
 // Debug / parity entry point behind mz_debug_conv3x3.

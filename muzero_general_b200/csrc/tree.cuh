@@ -204,8 +204,9 @@ MZ_DEVINL Leaf tree_select(const TreeConst& c, GameTree& t, int sim, int64_t gam
         const unsigned tied = LaneGroup<G>::ballot(valid && score == best);
         const int n_tied = __popc(tied);
         int pick;
-        if (n_tied == 1) {
-            pick = __ffs(tied) - 1;
+        if (n_tied <= 1) {
+            pick = max(__ffs(tied) - 1, 0);        // n_tied == 0 only for a root without legal actions (rejected by the
+                                                   // host; the clamp keeps the slot inside the game's pool regardless)
         } else {
             int idx;
             if (sim == 0 && depth == 0 && first_index >= 0) {

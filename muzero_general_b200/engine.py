@@ -141,7 +141,12 @@ class SearchEngine:
     def last_search_ms(self):
         return float(self.lib.mz_last_search_ms(self._h))
 
-    KERNEL_CLASSES = ("tree_step_kernel", "conv_tower_tc_kernel", "heads_kernel", "conv3x3_kernel", "other")
+    @property
+    def numerics(self):
+        """Arithmetic of the search path (bench.py's dtype)."""
+        return self.lib.mz_numerics(self._h).decode()
+
+    KERNEL_CLASSES = ("tree_step_kernel", "conv_tower_tc_kernel", "heads_kernel", "conv3x3_kernel", "other", "small_tower_kernel")
 
     def kernel_timing(self, enable):
         """Bracket every kernel of the step-wise pipeline with CUDA events (no graph replay while enabled)."""
@@ -216,6 +221,11 @@ class SearchEngine:
                 if obs.shape[1] != self.obs_elems:
                     raise ValueError(f"observation has {obs.shape[1]} elements, expected {self.obs_elems}")
             io.obs = self._ptr(obs, numpy.float32, keep)
+        if legal_mask is not None and not _is_torch(legal_mask):
+            # the reference asserts this per game (self_play.py:296); a row without a legal action would also
+            # index the node pool out of bounds on the device
+            assert numpy.asarray(legal_mask).reshape(n, -1).any(axis=1).all(), \
+                "Legal actions should not be an empty array."
         io.legal_mask = self._ptr(legal_mask, numpy.uint8, keep)
         io.to_play = self._ptr(to_play, numpy.int32, keep)
         io.add_exploration_noise = int(bool(add_exploration_noise))
@@ -310,6 +320,84 @@ class SearchEngine:
         out["root_visit"] = int(e.root_visit)
         out["root_value_sum"] = float(e.root_value_sum)
         return out
+
+
+class DeviceSelfPlayLoop:
+    """Python face of mz_selfplay_*: ``max_games`` environments stepped on the GPU, one batched search per move,
+    finished games handed back as packed struct-of-arrays blocks (include/mzb200.h)."""
+
+    ENVS = {"cartpole": _lib.MZ_ENV_CARTPOLE, "tictactoe": _lib.MZ_ENV_TICTACTOE, "connect4": _lib.MZ_ENV_CONNECT4}
+
+    def __init__(self, engine: SearchEngine, env: str, max_moves: int, temperature_threshold=None, reward_scale: int = 1,
+                 first_game_id: int = 0, staging_bytes: int = 0):
+        if env not in self.ENVS:
+            raise NotImplementedError(f"no device-resident environment for {env!r}")
+        self.engine = engine
+        d = _lib.MzSelfPlayDesc()
+        d.env = self.ENVS[env]
+        d.max_moves = int(max_moves)
+        d.temperature_threshold = int(temperature_threshold or 0)
+        d.reward_scale = int(reward_scale)
+        d.first_game_id = int(first_game_id)
+        d.staging_bytes = int(staging_bytes)
+        engine._check(engine.lib.mz_selfplay_begin(engine._h, C.byref(d)))
+        self.stats = _lib.MzSelfPlayStats()
+
+    def moves(self, n_moves: int, temperature: float, forced_action=None, uniform=None, noise=None, first_index=None):
+        """Play ``n_moves`` lockstep moves; returns the stats struct (env_steps, games_finished, staged_*, device_ms)."""
+        eng = self.engine
+        inj, keep = None, []
+        if forced_action is not None or uniform is not None or noise is not None or first_index is not None:
+            inj = _lib.MzSelfPlayInject()
+            inj.forced_action = eng._ptr(forced_action, numpy.int32, keep)
+            inj.uniform = eng._ptr(uniform, numpy.float64, keep)
+            inj.noise = eng._ptr(noise, numpy.float64, keep)
+            inj.first_index = eng._ptr(first_index, numpy.int32, keep)
+        eng._check(eng.lib.mz_selfplay_moves(eng._h, int(n_moves), float(temperature),
+                                            C.byref(inj) if inj is not None else None, C.byref(self.stats)))
+        return self.stats
+
+    def drain(self):
+        """(bytes, n_games): the staged finished games (a copy: the staging area is reused by the next call)."""
+        eng = self.engine
+        ptr, nbytes, ngames = C.c_void_p(), C.c_uint64(), C.c_int32()
+        eng._check(eng.lib.mz_selfplay_drain(eng._h, C.byref(ptr), C.byref(nbytes), C.byref(ngames)))
+        if nbytes.value == 0:
+            return b"", 0
+        return C.string_at(ptr.value, nbytes.value), int(ngames.value)
+
+    def peek(self):
+        eng = self.engine
+        B, A = eng.max_games, eng.A
+        out = dict(obs=numpy.empty((B, eng.obs_elems), numpy.float32), legal_mask=numpy.empty((B, A), numpy.uint8),
+                   to_play=numpy.empty(B, numpy.int32), game_id=numpy.empty(B, numpy.int64),
+                   move_index=numpy.empty(B, numpy.int32), last_action=numpy.empty(B, numpy.int32))
+        pk = _lib.MzSelfPlayPeek()
+        for k, v in out.items():
+            setattr(pk, k, v.ctypes.data)
+        eng._check(eng.lib.mz_selfplay_peek(eng._h, C.byref(pk)))
+        return out
+
+
+def parse_staged_games(buf: bytes, n_games: int):
+    """Split the packed blocks of ``mz_selfplay_drain`` into per-game dicts of numpy views (no copies)."""
+    games, off = [], 0
+    H = _lib.MZ_STAGED_HEADER_BYTES
+    for _ in range(n_games):
+        gid = int(numpy.frombuffer(buf, numpy.int64, 1, off)[0])
+        slot, T, first_to_play, O, A, nbytes = (int(x) for x in numpy.frombuffer(buf, numpy.int32, 6, off + 8))
+        p = off + H
+        root = numpy.frombuffer(buf, numpy.float64, T, p); p += 8 * T
+        visits = numpy.frombuffer(buf, numpy.int32, T * A, p).reshape(T, A); p += 4 * T * A
+        action = numpy.frombuffer(buf, numpy.int32, T, p); p += 4 * T
+        reward = numpy.frombuffer(buf, numpy.float32, T, p); p += 4 * T
+        to_play = numpy.frombuffer(buf, numpy.int32, T, p); p += 4 * T
+        obs = numpy.frombuffer(buf, numpy.float32, (T + 1) * O, p).reshape(T + 1, O)
+        games.append(dict(game_id=gid, slot=slot, length=T, first_to_play=first_to_play, root_value=root, visits=visits,
+                          action=action, reward=reward, to_play=to_play, obs=obs))
+        off += nbytes
+    assert off == len(buf), "staged blocks do not add up"
+    return games
 
 
 def debug_conv3x3(x, w, bias=None, residual=None, relu=False, tensor_cores=False, device=0):

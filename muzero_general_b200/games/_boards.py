@@ -82,6 +82,30 @@ class BoardVector(VectorGame):
         return self.observations(), reward, won | full
 
 
+def _threat_scan(board, player, windows, default):
+    """Shared core of the reference's hard-coded opponents (``games/tictactoe.py:310-349``,
+    ``games/connect4.py:307-348``): walk ``windows`` - tuples ``(cells, need, playable)`` - in the reference's
+    scan order; a window whose stones sum to +-``need`` has exactly one empty cell: that cell's action becomes the
+    candidate if ``playable(cell)`` holds, and is returned at once when the window belongs to the side to move (a win);
+    otherwise (a block) the scan continues and a later window may overwrite the candidate."""
+    action = default
+    for cells, need, playable, fixed_action in windows:
+        vals = [int(board[y][x]) for y, x in cells]
+        total = sum(vals)
+        if abs(total) != need:
+            continue
+        if fixed_action is not None:                  # Connect4's vertical check names the column without looking for the gap
+            action = fixed_action
+        else:
+            y, x = cells[vals.index(0)]
+            if not playable(y, x):
+                continue
+            action = playable.action(y, x)
+        if player * total > 0:
+            return action
+    return action
+
+
 class BoardGame:
     """Single-game facade over a one-game ``BoardVector`` with reference return types."""
     VECTOR = BoardVector
@@ -111,3 +135,17 @@ class BoardGame:
 
     def close(self):
         pass
+
+    def expert_agent(self):
+        """Hard-coded opponent of the evaluation worker (``self_play.py:211-212``).  Like the reference it first
+        draws a uniformly random legal action from the global ``numpy.random`` stream (consumed even when a threat is
+        found), then scans for a winning move / a move that blocks the opponent."""
+        env = self.env
+        H, W = env.H, env.W
+        board = env.board[0].reshape(H, W)
+        player = int(env.player[0])
+        default = numpy.random.choice(self.legal_actions())
+        return _threat_scan(board, player, self._expert_windows(board), default)
+
+    def _expert_windows(self, board):
+        raise NotImplementedError

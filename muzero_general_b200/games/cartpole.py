@@ -67,6 +67,7 @@ class CartPoleVector(VectorGame):
 
 class Game(AbstractGame):
     """Single-game facade with the reference's return shapes (obs (1,1,4), reward 1.0)."""
+    DEVICE_ENV = "cartpole"        # the same dynamics exist as a device-resident environment (csrc/selfplay.cu)
 
     def __init__(self, seed=None):
         self.env = CartPoleVector(1, seed)

@@ -30,7 +30,35 @@ class TicTacToeVector(BoardVector):
 
 
 class Game(BoardGame, AbstractGame):
+    DEVICE_ENV = "tictactoe"        # csrc/selfplay.cu restates these rules on the device
     VECTOR = TicTacToeVector
 
     def action_to_string(self, action_number):
         return f"Play row {action_number // 3 + 1}, column {action_number % 3 + 1}"
+
+    def _expert_windows(self, board):
+        """Scan order of games/tictactoe.py:313-347: row i then column i for i = 0..2, diagonal, anti-diagonal."""
+        class Any:
+            def __call__(self, y, x): return True
+            @staticmethod
+            def action(y, x): return y * 3 + x
+        ok = Any()
+        out = []
+        for i in range(3):
+            out.append(([(i, 0), (i, 1), (i, 2)], 2, ok, None))
+            out.append(([(0, i), (1, i), (2, i)], 2, ok, None))
+        out.append(([(0, 0), (1, 1), (2, 2)], 2, ok, None))
+        out.append(([(0, 2), (1, 1), (2, 0)], 2, ok, None))      # numpy.fliplr(board).diagonal(): index j <-> (j, 2 - j)
+        return out
+
+    def human_to_action(self):
+        while True:
+            try:
+                row = int(input(f"Enter the row (1, 2 or 3) to play for the player {self.to_play()}: "))
+                col = int(input(f"Enter the column (1, 2 or 3) to play for the player {self.to_play()}: "))
+                choice = (row - 1) * 3 + (col - 1)
+                if choice in self.legal_actions() and 1 <= row <= 3 and 1 <= col <= 3:
+                    return choice
+            except ValueError:
+                pass
+            print("Wrong input, try again")

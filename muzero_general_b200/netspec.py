@@ -229,3 +229,37 @@ def synthetic_weights(spec: NetSpec, seed: int = 0):
             fan_in = int(numpy.prod(shape[1:]))
             out[key] = (rs.standard_normal(size=shape) / math.sqrt(fan_in)).astype(numpy.float32)
     return out
+
+
+def stress_weights(spec: NetSpec, seed: int = 0, mode: str = "large"):
+    """``synthetic_weights`` with the BatchNorm affine terms of the residual towers rescaled so that the tower
+    activations leave the comfortable O(1) range (the range guard of the tensor-core towers is tested with these):
+
+    * ``"large"``     every tower BN gamma x4: activations grow ~16x per block, up to ~1e3..1e4 (inside fp16 range)
+    * ``"overflow"``  every tower BN gamma x12: activations exceed 65504, the largest finite fp16
+    * ``"tiny"``      first BN of every block x1e-5 (gamma and beta), second BN gamma x1e5, mean x1e-5: the intermediate
+                      activation of a block is ~1e-5 (below the smallest normal fp16) while the block output stays O(1)
+    """
+    import numpy
+
+    w = synthetic_weights(spec, seed)
+    if spec.kind != RESNET:
+        raise ValueError("stress_weights is for residual networks")
+    for key in list(w):
+        parts = key.split(".")
+        leaf, bn = parts[-1], parts[-2]
+        if not bn.startswith("bn") or "downsample_net" in key:
+            continue
+        if mode in ("large", "overflow"):
+            if leaf == "weight":
+                w[key] = (w[key] * (4.0 if mode == "large" else 12.0)).astype(numpy.float32)
+        elif mode == "tiny":
+            if bn == "bn1" and leaf in ("weight", "bias"):
+                w[key] = (w[key] * 1e-5).astype(numpy.float32)
+            elif bn == "bn2" and leaf == "weight":
+                w[key] = (w[key] * 1e5).astype(numpy.float32)
+            elif bn == "bn2" and leaf == "running_mean":
+                w[key] = (w[key] * 1e-5).astype(numpy.float32)
+        else:
+            raise ValueError(f"unknown stress mode {mode!r}")
+    return w

@@ -26,7 +26,7 @@ from collections import deque
 
 import numpy
 
-from .engine import SearchEngine
+from .engine import DeviceSelfPlayLoop, SearchEngine, parse_staged_games
 
 
 # ----------------------------------------------------------------------------------------
@@ -248,6 +248,53 @@ class MinMaxStats:
         return value
 
 
+class PackedGameHistory(GameHistory):
+    """A finished game as it left the device (one packed struct-of-arrays block, ``mz_selfplay_drain``), presented
+    as a ``GameHistory``.  The reference's list attributes (self_play.py:485-494) are built on first access - a
+    consumer that only counts games or forwards them pays nothing per position - and the object pickles as a plain
+    ``GameHistory``, so the reference's ReplayBuffer / Trainer / replay_buffer.pkl see the usual type."""
+
+    _LISTS = ("observation_history", "action_history", "reward_history", "to_play_history", "child_visits", "root_values")
+
+    def __init__(self, packed, obs_shape, obs_dtype, reward_type):
+        # deliberately NOT calling GameHistory.__init__: the six lists stay absent until asked for
+        self.__dict__["_packed"] = (packed, tuple(obs_shape), obs_dtype, reward_type)
+        self.reanalysed_predicted_root_values = None
+        self.priorities = None
+        self.game_priority = None
+
+    def __len__(self):
+        return int(self._packed[0]["length"])
+
+    @property
+    def game_id(self):
+        return int(self._packed[0]["game_id"])
+
+    def __getattr__(self, name):
+        if name in PackedGameHistory._LISTS and "_packed" in self.__dict__:
+            self._materialise()
+            return self.__dict__[name]
+        raise AttributeError(name)
+
+    def _materialise(self):
+        g, shape, dtype, reward_type = self._packed
+        T = int(g["length"])
+        obs = g["obs"].reshape((T + 1,) + shape).astype(dtype)
+        d = self.__dict__
+        d["observation_history"] = list(obs)
+        d["action_history"] = [0] + list(g["action"].astype(numpy.int64))
+        d["reward_history"] = [0] + [reward_type(r) for r in g["reward"].tolist()]
+        d["to_play_history"] = [int(g["first_to_play"])] + g["to_play"].tolist()
+        visits = g["visits"]
+        d["child_visits"] = (visits / visits.sum(1, keepdims=True)).tolist()
+        d["root_values"] = g["root_value"].tolist()
+
+    def __reduce__(self):
+        self._materialise()
+        state = {k: v for k, v in self.__dict__.items() if k != "_packed"}
+        return (object.__new__, (GameHistory,), state)      # unpickles as a plain GameHistory, no helper of ours needed
+
+
 def register_as_reference_module():
     """Make pickles of ``GameHistory`` interchangeable with the reference's replay_buffer.pkl
     (muzero.py:338-346,444-446): the class is published under the module name ``self_play``."""
@@ -282,7 +329,9 @@ class SelfPlay:
 
         self.model = DeviceModel(config, max_games=self.num_parallel_games, device=device, seed=seed)
         self.model.set_weights(initial_checkpoint["weights"])
-        self._stream = None
+        self._device_loop = None      # device-resident variant of the same (play_moves)
+        self._batched = None          # persistent lockstep batch: environments, RNG streams and game ids carry
+        self._stream = None           # across play_games calls (its generator)
         self.played_games = 0
         self.played_steps = 0
 
@@ -296,9 +345,13 @@ class SelfPlay:
                 temperature = cfg.visit_softmax_temperature_fn(
                     trained_steps=_call(shared_storage, "get_info", "training_step"))
                 if self.num_parallel_games > 1:
-                    # one lockstep batch per weight refresh; every finished game goes to the buffer
-                    for game_history in self.play_games(self.num_parallel_games, temperature,
-                                                        cfg.temperature_threshold):
+                    # the lockstep batch advances between two weight refreshes; every finished game goes to the buffer
+                    if self.loop_path == "device":
+                        games = self.play_moves(int(getattr(cfg, "moves_per_weight_refresh", 8)), temperature,
+                                                cfg.temperature_threshold)
+                    else:
+                        games = self.play_games(self.num_parallel_games, temperature, cfg.temperature_threshold)
+                    for game_history in games:
                         _fire(replay_buffer, "save_game", game_history, shared_storage)
                 else:
                     game_history = self.play_game(temperature, cfg.temperature_threshold, False, "self", 0)
@@ -416,20 +469,81 @@ class SelfPlay:
 
     # ------------------------------------------------------------------ batched play
     def play_games(self, num_games, temperature, temperature_threshold=None, max_total_moves=None):
-        """Play ``num_games`` games, ``num_parallel_games`` at a time in lockstep; returns the histories."""
+        """The next ``num_games`` finished games of the worker's lockstep batch (``num_parallel_games`` games in flight).
+
+        The batch is PERSISTENT: games still in flight when the quota is reached keep their state and finish in a
+        later call (long episodes are not dropped), every game gets a fresh global id / RNG stream, and a weight
+        refresh between calls (``continuous_self_play``) simply applies to the remaining moves - like a reference
+        actor that reloads weights between games.  ``max_total_moves`` bounds the env-steps of THIS call."""
+        stream = self.self_play_stream(temperature, temperature_threshold)
+        start = self._batched.env_steps
         out = []
-        for gh in self.self_play_stream(temperature, temperature_threshold):
-            out.append(gh)
-            if len(out) >= num_games:
+        while len(out) < num_games:
+            out.append(next(stream))
+            if max_total_moves is not None and self._batched.env_steps - start >= max_total_moves:
                 break
-            if max_total_moves is not None and self.played_steps >= max_total_moves:
-                break
-        self._stream = None
         return out
 
     def self_play_stream(self, temperature, temperature_threshold=None):
         """Generator over finished ``GameHistory`` objects; B games advance one move per iteration."""
-        return BatchedSelfPlay(self, temperature, temperature_threshold, self.first_game_id).run()
+        if self._batched is None:
+            self._batched = BatchedSelfPlay(self, temperature, temperature_threshold, self.first_game_id)
+            self._stream = self._batched.run()
+        else:
+            self._batched.temperature = temperature
+            self._batched.temperature_threshold = temperature_threshold
+        return self._stream
+
+    def reset_stream(self):
+        """Drop the games in flight (e.g. after changing ``config`` fields the batch was built from)."""
+        self._batched = None
+        self._stream = None
+        self._device_loop = None
+
+    # ------------------------------------------------------------------ whole-batch moves
+    def _device_env_name(self):
+        """Name of the device-resident environment for this worker, or None (host environments)."""
+        cfg = self.config
+        name = getattr(self.Game, "DEVICE_ENV", None)
+        if (name is None or self.rng_mode != "philox" or cfg.stacked_observations
+                or not getattr(cfg, "device_envs", True)):
+            return None
+        return name
+
+    @property
+    def loop_path(self):
+        """"device": environments, sampling and records on the GPU (mz_selfplay_*); "host": numpy environments."""
+        return "device" if self._device_env_name() else "host"
+
+    @property
+    def env_steps(self):
+        """Moves played by the lockstep batch so far (finished games or not)."""
+        if getattr(self, "_device_loop", None) is not None:
+            return int(self._device_loop.loop.stats.env_steps)
+        return self._batched.env_steps if self._batched is not None else 0
+
+    def play_moves(self, n_moves, temperature, temperature_threshold=None):
+        """Advance every game of the lockstep batch by ``n_moves`` moves; returns the games that finished.
+
+        With ``rng_mode="philox"`` and a game that has a device-resident environment (CartPole, TicTacToe, Connect4)
+        the whole loop - observation, search, visit-count sampling, environment step, history records - runs on the
+        GPU (``mz_selfplay_moves``) and only finished games cross to the host, as ``PackedGameHistory`` objects.
+        Otherwise the host loop (``BatchedSelfPlay.move``) is used."""
+        if self._device_env_name():
+            if getattr(self, "_device_loop", None) is None:
+                self._device_loop = DeviceBatchedSelfPlay(self, temperature_threshold)
+            games = self._device_loop.moves(n_moves, temperature)
+            self.played_games += len(games)
+            self.played_steps += sum(len(g) for g in games)
+            return games
+        self.self_play_stream(temperature, temperature_threshold)
+        out = []
+        for _ in range(n_moves):
+            out.extend(self._batched.move())
+        return out
+
+    def close(self):
+        self.model.engine.close()
 
 
 def _sample_action(actions, visit_counts, temperature, rng):
@@ -480,6 +594,32 @@ class _ObjectVector:
         return numpy.array([game.to_play() for game in self.games], dtype=numpy.int32)
 
 
+class DeviceBatchedSelfPlay:
+    """Lockstep self-play with the environments on the GPU: per call ONE ``mz_selfplay_moves`` for
+    ``n_moves`` moves of the whole batch, then one read of the packed finished games.  Slot g plays the global games
+    ``first_game_id + g + k*B``; every random draw is a Philox stream keyed by (seed, global game id, move), so a
+    game's history is independent of the batch size and of the number of ranks."""
+
+    def __init__(self, worker, temperature_threshold=None):
+        cfg = worker.config
+        Game = worker.Game
+        vec = getattr(Game, "VECTOR", None)
+        self.obs_shape = tuple(cfg.observation_shape)
+        self.obs_dtype = getattr(vec, "OBS_DTYPE", numpy.float32)
+        self.reward_type = int if vec is not None else float
+        self.loop = DeviceSelfPlayLoop(worker.model.engine, Game.DEVICE_ENV, cfg.max_moves,
+                                       temperature_threshold=temperature_threshold,
+                                       reward_scale=getattr(vec, "REWARD_SCALE", 1),
+                                       first_game_id=worker.first_game_id,
+                                       staging_bytes=int(getattr(cfg, "selfplay_staging_bytes", 0) or 0))
+
+    def moves(self, n_moves, temperature, **inject):
+        self.loop.moves(n_moves, temperature, **inject)
+        buf, n = self.loop.drain()
+        return [PackedGameHistory(g, self.obs_shape, self.obs_dtype, self.reward_type)
+                for g in parse_staged_games(buf, n)]
+
+
 class BatchedSelfPlay:
     """Lockstep self-play of B games: one ``mz_search`` call per move for the whole batch.
 
@@ -504,6 +644,7 @@ class BatchedSelfPlay:
             self.env = Game.vector(self.B, worker.seed)
         else:
             self.env = _ObjectVector(Game, self.B, worker.seed, self.A)
+        self.env_steps = 0                         # moves stepped by the batch so far (finished or not)
         self.numpy_mode = worker.rng_mode == "numpy"
         if self.numpy_mode:
             self.streams = [numpy.random.RandomState(worker.seed + first_game_id + g) for g in range(self.B)]
@@ -541,67 +682,86 @@ class BatchedSelfPlay:
         greedy = t == 0
         with numpy.errstate(divide="ignore"):
             p = visit_counts.astype(numpy.float64) ** (1.0 / numpy.where(greedy, 1.0, t))[:, None]
+        p = numpy.where(legal > 0, p, 0.0)           # 0 ** 0 = 1 at T = inf must not give illegal actions any mass
         cdf = numpy.cumsum(p / p.sum(1, keepdims=True), axis=1)
         u = self.fast.random_sample(B)
-        sampled = (u[:, None] >= cdf).sum(1).clip(0, self.A - 1)
-        return numpy.where(greedy, visit_counts.argmax(1), sampled).astype(numpy.int64)
+        last_legal = self.A - 1 - numpy.argmax(legal[:, ::-1] > 0, axis=1)
+        sampled = numpy.minimum((u[:, None] >= cdf).sum(1), last_legal)    # cdf rounding can leave u >= cdf[-1]
+        return numpy.where(greedy, numpy.where(legal > 0, visit_counts, -1).argmax(1), sampled).astype(numpy.int64)
+
+    def _begin(self):
+        B = self.B
+        env = self.env
+        self.obs = env.reset()
+        # per-slot bookkeeping
+        self.start = numpy.zeros(B, numpy.int64)        # index into `records` of the slot's first move
+        self.moves = numpy.zeros(B, numpy.int64)        # moves played in the current game
+        self.first_obs = [numpy.asarray(self.obs[g]).copy() for g in range(B)]
+        self.first_to_play = numpy.asarray(env.to_play()).copy()
+        self.game_ids = (self.first_game_id + numpy.arange(B)).astype(numpy.int64)
+        self.records = deque()                          # one dict of [B,...] arrays per move
+        self.base = 0                                   # absolute index of records[0]
+        self.t_abs = 0
+        self._begun = True
+
+    def move(self):
+        """One lockstep move of the whole batch; returns the GameHistory objects of the games it finished."""
+        if not getattr(self, "_begun", False):
+            self._begin()
+        cfg, B, A, w = self.cfg, self.B, self.A, self.w
+        env, records, start, moves, first_obs = self.env, self.records, self.start, self.moves, self.first_obs
+        engine = w.model.engine
+        obs = self.obs
+        legal = numpy.asarray(env.legal_mask(), dtype=numpy.uint8)
+        to_play = numpy.asarray(env.to_play(), dtype=numpy.int32)
+        if cfg.stacked_observations:
+            batch = numpy.stack([self._stacked(g, obs, records, self.base, start, first_obs) for g in range(B)])
+        else:
+            batch = numpy.stack([numpy.asarray(o, dtype=numpy.float32) for o in obs]) \
+                if not isinstance(obs, numpy.ndarray) else obs
+        noise, first = self._noise_and_first(legal)
+        out = engine.search(obs=numpy.asarray(batch, dtype=numpy.float32).reshape(B, -1), legal_mask=legal,
+                            to_play=to_play, add_exploration_noise=True, noise=noise, first_index=first,
+                            game_id=self.game_ids, move_index=moves.astype(numpy.int32))
+        actions = self._actions(out.visit_counts, legal, moves)
+        obs, reward, done = env.step(actions)
+        records.append(dict(visits=out.visit_counts, legal=legal, root_value=out.root_value, action=actions,
+                            obs=[numpy.asarray(o).copy() for o in obs] if not isinstance(obs, numpy.ndarray) else obs.copy(),
+                            reward=numpy.asarray(reward).copy() if isinstance(reward, numpy.ndarray) else list(reward),
+                            to_play=numpy.asarray(env.to_play()).copy()))
+        self.t_abs += 1
+        moves += 1
+        self.env_steps += B
+        out_games = []
+        finished = numpy.asarray(done, dtype=bool) | (moves >= cfg.max_moves)
+        if finished.any():
+            for g in numpy.nonzero(finished)[0]:
+                gh = self._materialise(g, records, self.base, int(start[g]), self.t_abs, first_obs[g], self.first_to_play[g])
+                w.played_games += 1                  # counted when the game is handed over, like self_play.py:52
+                w.played_steps += len(gh.action_history) - 1
+                out_games.append(gh)
+            obs = env.reset(finished)
+            tp = numpy.asarray(env.to_play())
+            for g in numpy.nonzero(finished)[0]:
+                first_obs[g] = numpy.asarray(obs[g]).copy()
+                self.first_to_play[g] = tp[g]
+                start[g] = self.t_abs
+                moves[g] = 0
+                self.game_ids[g] += B           # a fresh global game id for the slot's next game
+                if self.numpy_mode:
+                    self.streams[g] = numpy.random.RandomState(self.w.seed + int(self.game_ids[g]))
+        self.obs = obs
+        drop = int(start.min()) - self.base
+        for _ in range(drop):
+            records.popleft()
+        self.base += drop
+        return out_games
 
     def run(self):
-        cfg, B, A, w = self.cfg, self.B, self.A, self.w
-        env = self.env
-        engine = w.model.engine
-        obs = env.reset()
-        # per-slot bookkeeping
-        start = numpy.zeros(B, numpy.int64)        # index into `records` of the slot's first move
-        moves = numpy.zeros(B, numpy.int64)        # moves played in the current game
-        first_obs = [numpy.asarray(obs[g]).copy() for g in range(B)]
-        first_to_play = numpy.asarray(env.to_play()).copy()
-        game_ids = (self.first_game_id + numpy.arange(B)).astype(numpy.int64)
-        records = deque()                          # one dict of [B,...] arrays per move
-        base = 0                                   # absolute index of records[0]
-        stacked = cfg.stacked_observations
-        partial = [None] * B                       # GameHistory under construction (only if stacking)
-        t_abs = 0
+        """Generator over finished games, one lockstep move at a time."""
         while True:
-            legal = numpy.asarray(env.legal_mask(), dtype=numpy.uint8)
-            to_play = numpy.asarray(env.to_play(), dtype=numpy.int32)
-            if stacked:
-                batch = numpy.stack([self._stacked(g, obs, records, base, start, first_obs) for g in range(B)])
-            else:
-                batch = numpy.stack([numpy.asarray(o, dtype=numpy.float32) for o in obs]) \
-                    if not isinstance(obs, numpy.ndarray) else obs
-            noise, first = self._noise_and_first(legal)
-            out = engine.search(obs=numpy.asarray(batch, dtype=numpy.float32).reshape(B, -1), legal_mask=legal,
-                                to_play=to_play, add_exploration_noise=True, noise=noise, first_index=first,
-                                game_id=game_ids, move_index=moves.astype(numpy.int32))
-            actions = self._actions(out.visit_counts, legal, moves)
-            obs, reward, done = env.step(actions)
-            records.append(dict(visits=out.visit_counts, legal=legal, root_value=out.root_value, action=actions,
-                                obs=[numpy.asarray(o).copy() for o in obs] if not isinstance(obs, numpy.ndarray) else obs.copy(),
-                                reward=numpy.asarray(reward).copy() if isinstance(reward, numpy.ndarray) else list(reward),
-                                to_play=numpy.asarray(env.to_play()).copy()))
-            t_abs += 1
-            moves += 1
-            w.played_steps += B
-            finished = numpy.asarray(done, dtype=bool) | (moves >= cfg.max_moves)
-            if finished.any():
-                for g in numpy.nonzero(finished)[0]:
-                    yield self._materialise(g, records, base, int(start[g]), t_abs, first_obs[g], first_to_play[g])
-                    w.played_games += 1
-                obs = env.reset(finished)
-                tp = numpy.asarray(env.to_play())
-                for g in numpy.nonzero(finished)[0]:
-                    first_obs[g] = numpy.asarray(obs[g]).copy()
-                    first_to_play[g] = tp[g]
-                    start[g] = t_abs
-                    moves[g] = 0
-                    game_ids[g] += B           # a fresh global game id for the slot's next game
-                    if self.numpy_mode:
-                        self.streams[g] = numpy.random.RandomState(self.w.seed + int(game_ids[g]))
-            drop = int(start.min()) - base
-            for _ in range(drop):
-                records.popleft()
-            base += drop
+            for gh in self.move():
+                yield gh
 
     def _stacked(self, g, obs, records, base, start, first_obs):
         gh = GameHistory()

@@ -397,8 +397,123 @@ def main():
     cfg.num_simulations = 200
     json.dump(plays, open(os.path.join(OUT, "play.json"), "w"))
     json.dump(manifest, open(os.path.join(OUT, "MANIFEST.json"), "w"), indent=1)
+    main_round2()
     print("done ->", OUT)
 
 
+def layer_extrema(models, net, obs, act):
+    """Largest |activation| after every conv/BN/ReLU stage of the three towers (forward hooks on the reference)."""
+    peaks = {}
+
+    def hook(name):
+        def fn(mod, inp, out):
+            peaks[name] = max(peaks.get(name, 0.0), float(out.detach().abs().max()))
+        return fn
+
+    handles = [m.register_forward_hook(hook(n)) for n, m in net.named_modules()
+               if isinstance(m, (torch.nn.BatchNorm2d, models.ResidualBlock))]
+    with torch.no_grad():
+        _, _, _, h = net.initial_inference(torch.from_numpy(obs))
+        net.recurrent_inference(h, torch.from_numpy(act))
+    for hd in handles:
+        hd.remove()
+    return peaks
+
+
+def main_round2():
+    """Round-2 fixtures: the BASELINE closed-loop configs (Connect4 N=200, Breakout N=50), a batch-64 Connect4
+    network fixture, and network fixtures on STRESS weights (activations up to ~1e4, beyond the fp16 range, and
+    down to ~1e-5) for the tensor-core towers' range guard.  Existing fixtures are untouched."""
+    from muzero_general_b200.netspec import stress_weights
+    sp, models, replay_buffer, trainer = load_reference()
+    specs, ref_cfgs, ref_games = {}, {}, {}
+    for name in ("connect4", "breakout"):
+        ref_games[name] = load_reference_game(name)
+        ref_cfgs[name] = ref_games[name].MuZeroConfig()
+        specs[name] = netspec_from_config(ref_cfgs[name])
+
+    def ref_net(name, weights):
+        net = models.MuZeroNetwork(ref_cfgs[name])
+        net.set_weights(to_torch_sd(weights))
+        net.eval()
+        return net
+
+    # ---- closed loop at the BASELINE simulation counts
+    cfg = ref_cfgs["connect4"]
+    net = ref_net("connect4", synthetic_weights(specs["connect4"], 0))
+    runs = []
+    for moves, seed in (((), 0), ((3, 3, 2, 4, 3, 3, 3, 3), 1), ((0, 6, 1, 5, 2), 2)):
+        cfg.num_simulations = 200
+        o, legal, tp = board_obs(ref_games["connect4"], moves)
+        runs.append(run_traced_search(sp, cfg, net, o, legal, tp, True, seed))
+    json.dump(runs, open(os.path.join(OUT, "mcts_connect4_n200.json"), "w"))
+    cfg = ref_cfgs["breakout"]
+    net = ref_net("breakout", synthetic_weights(specs["breakout"], 0))
+    cfg.num_simulations = 50
+    runs = []
+    for obs_seed, seed in ((19, 5),):
+        o = numpy.random.RandomState(obs_seed).random_sample((3, 96, 96)).astype(numpy.float32)
+        runs.append(run_traced_search(sp, cfg, net, o, [0, 1, 2, 3], 0, True, seed))
+    cfg.num_simulations = 30
+    json.dump(runs, open(os.path.join(OUT, "mcts_breakout_n50.json"), "w"))
+    print("BASELINE-size closed-loop fixtures written")
+
+    # ---- hard-coded opponents (expert_agent): reference choice at every position of random playouts
+    experts = {}
+    for gname in ("tictactoe", "connect4"):
+        gm = load_reference_game(gname)
+        rs = numpy.random.RandomState(23)
+        cases = []
+        for g in range(40):
+            ref = gm.Game(g)
+            ref.reset()
+            moves, done = [], False
+            while not done:
+                seed = len(cases)
+                numpy.random.seed(seed)
+                cases.append(dict(moves=list(moves), seed=seed, action=int(ref.expert_agent())))
+                legal = ref.legal_actions()
+                # mostly random moves, sometimes the expert's own, so that threats of both colours show up
+                a = cases[-1]["action"] if rs.uniform() < 0.3 else int(legal[rs.randint(len(legal))])
+                _, _, done = ref.step(a)
+                moves.append(a)
+        experts[gname] = cases
+    json.dump(experts, open(os.path.join(OUT, "expert.json"), "w"))
+    print("expert fixtures:", {k: len(v) for k, v in experts.items()})
+
+    # ---- FC network on the shipped CartPole checkpoint (the round-1 fixture only covered synthetic weights)
+    cart_mod = load_reference_game("cartpole")
+    cart_cfg = cart_mod.MuZeroConfig()
+    cart_spec = netspec_from_config(cart_cfg)
+    pre = dict(numpy.load(os.path.join(OUT, "weights_cartpole_pretrained.npz")))
+    os.rename(os.path.join(OUT, "net_cartpole.npz"), os.path.join(OUT, "net_cartpole.keep"))
+    gen_net(models, "cartpole", cart_cfg, cart_spec, pre, 16, seed=29)
+    os.rename(os.path.join(OUT, "net_cartpole.npz"), os.path.join(OUT, "net_cartpole_pretrained.npz"))
+    os.rename(os.path.join(OUT, "net_cartpole.keep"), os.path.join(OUT, "net_cartpole.npz"))
+
+    # ---- larger network batches
+    name = "connect4"
+    w = synthetic_weights(specs[name], seed=0)
+    os.rename(os.path.join(OUT, f"net_{name}.npz"), os.path.join(OUT, f"net_{name}.keep"))
+    gen_net(models, name, ref_cfgs[name], specs[name], w, 64, seed=13)
+    os.rename(os.path.join(OUT, f"net_{name}.npz"), os.path.join(OUT, f"net_{name}_b64.npz"))
+    # ---- stress weights
+    info = {}
+    for mode in ("large", "overflow", "tiny"):
+        w = stress_weights(specs[name], 0, mode)
+        net = gen_net(models, name, ref_cfgs[name], specs[name], w, 8, seed=17)
+        os.rename(os.path.join(OUT, f"net_{name}.npz"), os.path.join(OUT, f"net_{name}_stress_{mode}.npz"))
+        g = dict(numpy.load(os.path.join(OUT, f"net_{name}_stress_{mode}.npz")))
+        peaks = layer_extrema(models, net, g["obs"], g["action"])
+        info[mode] = dict(max_activation=max(peaks.values()), min_layer_peak=min(peaks.values()))
+        print("stress", mode, info[mode])
+    os.rename(os.path.join(OUT, f"net_{name}.keep"), os.path.join(OUT, f"net_{name}.npz"))
+    json.dump(info, open(os.path.join(OUT, "net_connect4_stress_info.json"), "w"), indent=1)
+    print("network fixtures (batch 64, stress weights) written")
+
+
 if __name__ == "__main__":
-    main()
+    if "--round2" in sys.argv:
+        main_round2()
+    else:
+        main()

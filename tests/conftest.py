@@ -32,7 +32,9 @@ def game_configs():
 
 def weights_for(name, spec):
     """Weights matching the golden fixtures: synthetic seed 0, or the shipped CartPole checkpoint."""
-    from muzero_general_b200.netspec import synthetic_weights
+    from muzero_general_b200.netspec import stress_weights, synthetic_weights
     if name == "cartpole_pretrained":
         return golden_npz("weights_cartpole_pretrained.npz")
+    if "_stress_" in name:                      # e.g. connect4_stress_large (oracle/gen_golden.py::main_round2)
+        return stress_weights(spec, 0, name.rsplit("_", 1)[1])
     return synthetic_weights(spec, 0)

@@ -19,15 +19,78 @@ def test_library_exports_every_declared_symbol():
     assert declared == bound, (declared ^ bound)
     for name in declared:
         assert hasattr(lib, name)
-    assert lib.mz_abi_version() == 1
+    assert lib.mz_abi_version() == 2
 
 
-def test_struct_sizes_match_header_layout():
+_PRIM = {"int32_t": 4, "uint32_t": 4, "int64_t": 8, "uint64_t": 8, "double": 8, "float": 4, "uint8_t": 1, "int8_t": 1, "int": 4}
+
+
+def _header_structs():
+    """Parse every `typedef struct X { ... } X;` of include/mzb200.h into [(field, offset, size)] + total size,
+    with natural alignment (what gcc / nvcc do for these plain structs)."""
+    header = open(os.path.join(ROOT, "include", "mzb200.h")).read()
+    consts = {k: int(v) for k, v in re.findall(r"#define\s+(MZ_[A-Z_]+)\s+(\d+)", header)}
+    text = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    out = {}
+    for name, body in re.findall(r"typedef struct (\w+) \{(.*?)\} \1;", text, flags=re.S):
+        off, align_max, fields = 0, 1, []
+        for decl in body.split(";"):
+            decl = " ".join(decl.split())
+            if not decl:
+                continue
+            m = re.match(r"(?:const )?(?:struct )?(\w+)(\s*\*)?\s*(.*)", decl)
+            base, star, rest = m.group(1), m.group(2), m.group(3)
+            for item in rest.split(","):
+                item = item.strip()
+                ptr = bool(star) or item.startswith("*")
+                item = item.lstrip("* ")
+                am = re.match(r"(\w+)\[(\w+)\]", item)
+                count = 1
+                if am:
+                    item, count = am.group(1), consts.get(am.group(2)) or int(am.group(2))
+                size = 8 if ptr else _PRIM[base]
+                off = (off + size - 1) // size * size
+                fields.append((item, off, size * count))
+                off += size * count
+                align_max = max(align_max, size)
+        out[name] = (fields, (off + align_max - 1) // align_max * align_max)
+    return out
+
+
+def test_ctypes_structs_match_the_header_field_by_field():
     from muzero_general_b200 import _lib
-    # MzNetDesc: 7 + 5*(1+8) + 5 + 3*(1+8) + 1 int32
-    assert ctypes.sizeof(_lib.MzNetDesc) == 4 * (7 + 5 * 9 + 5 + 3 * 9 + 1)
-    assert ctypes.sizeof(_lib.MzSearchDesc) == 16 + 5 * 8 + 8 + 24
-    assert ctypes.sizeof(_lib.MzSearchIO) == 8 + 3 * 8 + 8 + 4 * 8 + 7 * 8 + 2 * 8
+    structs = _header_structs()
+    assert {"MzNetDesc", "MzSearchDesc", "MzSearchIO", "MzSelfPlayDesc", "MzSelfPlayStats"} <= set(structs)
+    for name, (fields, size) in structs.items():
+        cls = getattr(_lib, name)
+        assert ctypes.sizeof(cls) == size, (name, ctypes.sizeof(cls), size)
+        assert [f[0] for f in cls._fields_] == [f[0] for f in fields], name
+        for fname, off, fsize in fields:
+            d = getattr(cls, fname)
+            assert (d.offset, d.size) == (off, fsize), (name, fname)
+
+
+def test_integration_doc_stub_matches_the_library():
+    """INTEGRATION.md shows the ctypes stub a maintainer would paste: every fenced python block that defines
+    Structures is executed and its classes must have the layout of the real binding."""
+    from muzero_general_b200 import _lib
+    doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    blocks = [b for b in re.findall(r"```python\n(.*?)```", doc, flags=re.S) if "C.Structure" in b]
+    assert blocks, "no ctypes stub found in INTEGRATION.md"
+    checked = 0
+    for block in blocks:
+        # keep the declarations, drop the usage lines that need a GPU / real buffers
+        decl = block.split("# ---- usage")[0]
+        ns = {}
+        exec(decl, ns)
+        for name, obj in ns.items():
+            if isinstance(obj, type) and issubclass(obj, ctypes.Structure) and obj is not ctypes.Structure:
+                real = getattr(_lib, name)
+                assert ctypes.sizeof(obj) == ctypes.sizeof(real), name
+                assert [(f[0], getattr(obj, f[0]).offset) for f in obj._fields_] == \
+                       [(f[0], getattr(real, f[0]).offset) for f in real._fields_], name
+                checked += 1
+    assert checked >= 3
 
 
 def test_no_cpu_fallback(game_configs):

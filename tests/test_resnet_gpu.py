@@ -35,10 +35,10 @@ def _report(name, got, want):
     print(f"{name}: max abs err {err.max():.3e}, max rel err {(err / (numpy.abs(want) + 1e-3)).max():.3e}")
 
 
-@pytest.mark.parametrize("name", ["tictactoe", "connect4", "breakout"])
+@pytest.mark.parametrize("name", ["tictactoe", "connect4", "breakout", "connect4_b64"])
 def test_resnet_network_matches_reference(name, numerics, game_configs):
     TOL = TOLS[numerics]
-    cfg = game_configs[name]
+    cfg = game_configs[name.split("_")[0]]
     spec = netspec_from_config(cfg)
     g = golden_npz(f"net_{name}.npz")
     n = len(g["obs"])
@@ -105,12 +105,12 @@ def test_resnet_student_forced(name, N, n, numerics, game_configs):
     eng.close()
 
 
-@pytest.mark.parametrize("name", ["tictactoe", "connect4", "breakout"])
+@pytest.mark.parametrize("name", ["tictactoe", "connect4", "breakout", "connect4_n200", "breakout_n50"])
 def test_resnet_closed_loop_matches_reference_counts(name, numerics, game_configs):
     """Own networks + the reference's noise and first pick.  fp32 path: the reference's visit counts
     exactly.  tf32 path: counts may move by a visit where two children are nearly tied, so the bound is
     on the visit distribution (total variation <= 5 %) and on the root value."""
-    cfg = game_configs[name]
+    cfg = game_configs[name.split("_")[0]]
     spec = netspec_from_config(cfg)
     A = spec.action_space
     for c in golden_json(f"mcts_{name}.json"):

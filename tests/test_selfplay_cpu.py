@@ -198,3 +198,72 @@ def test_continuous_self_play_test_mode_reports_metrics(fake_engine):
     for key in ("episode_length", "total_reward", "mean_value", "muzero_reward", "opponent_reward"):
         assert key in storage.d
     assert 5 <= storage.d["episode_length"] <= 9
+
+
+@pytest.mark.parametrize("name", ["tictactoe", "connect4"])
+def test_expert_agent_matches_reference(name):
+    """The hard-coded evaluation opponent (games/*.py expert_action) picks the reference's move at every position
+    of the recorded playouts, consuming the global numpy stream the same way."""
+    mod = load_game_module(name)
+    cases = golden_json("expert.json")[name]
+    assert len(cases) > 100
+    for c in cases:
+        g = mod.Game(0)
+        g.reset()
+        for a in c["moves"]:
+            g.step(a)
+        numpy.random.seed(c["seed"])
+        assert int(g.expert_agent()) == c["action"], c
+
+
+def test_test_mode_with_the_shipped_default_opponent(fake_engine):
+    """The shipped board-game configs keep opponent="expert" (games/tictactoe.py, games/connect4.py): the evaluation
+    worker must run with them as they are."""
+    for name in ("tictactoe", "connect4"):
+        worker, cfg = _worker(name, 0, num_simulations=4, training_steps=6)
+        assert cfg.opponent == "expert"
+        storage = _Storage(weights_for(name, netspec_from_config(cfg)), training_steps_per_poll=3)
+        worker.continuous_self_play(storage, _Buffer(), test_mode=True)
+        assert storage.d["episode_length"] >= 5 and "opponent_reward" in storage.d
+
+
+@pytest.mark.parametrize("name,mode", [("tictactoe", "numpy"), ("cartpole", "numpy"), ("cartpole", "philox")])
+def test_consecutive_batches_are_new_games(name, mode, fake_engine):
+    """play_games keeps ONE lockstep batch alive across calls: new start states / RNG streams / game ids every game,
+    games in flight at the end of a call are finished by the next one, counters count handed-over games."""
+    worker, cfg = _worker(name, 0, num_parallel_games=3, num_simulations=4, rng_mode=mode, max_moves=12)
+    first = worker.play_games(3, 1.0)
+    ids_after_first = worker._batched.game_ids.copy()
+    steps_first = worker._batched.env_steps
+    second = worker.play_games(3, 1.0)
+    assert len(first) == 3 and len(second) == 3
+    key = lambda g: ([int(a) for a in g.action_history], [numpy.asarray(o).tobytes() for o in g.observation_history],
+                     g.child_visits)
+    assert all(key(a) != key(b) for a in first for b in second)
+    assert len({tuple(key(g)[0]) + (key(g)[1][0],) for g in first + second}) >= 4
+    assert (worker._batched.game_ids >= ids_after_first).all() and worker._batched.game_ids.max() >= 3
+    assert worker._batched.env_steps > steps_first
+    assert worker.played_games == 6
+    assert worker.played_steps == sum(len(g.action_history) - 1 for g in first + second)
+    # a different temperature applies from the next move on, without restarting the batch
+    batch = worker._batched
+    worker.play_games(1, 0.0)
+    assert worker._batched is batch and batch.temperature == 0.0
+
+
+def test_long_games_survive_the_quota(fake_engine):
+    """Short games recycle their slots while a long game is in flight; the long one is still delivered later."""
+    worker, cfg = _worker("cartpole", 0, num_parallel_games=4, num_simulations=3, rng_mode="philox", max_moves=40)
+    lengths = []
+    for _ in range(6):
+        lengths += [len(g.action_history) - 1 for g in worker.play_games(2, 1.0)]
+    assert worker.played_games == 12 and len(lengths) == 12
+    assert sum(lengths) == worker.played_steps <= worker._batched.env_steps
+
+
+def test_search_rejects_a_row_without_legal_actions():
+    from muzero_general_b200.engine import SearchEngine
+    eng = SearchEngine.__new__(SearchEngine)          # marshalling only: no library / GPU needed for the check
+    eng.A, eng.N, eng.obs_elems = 3, 2, 4
+    with pytest.raises(AssertionError, match="Legal actions should not be an empty array"):
+        eng.search(obs=numpy.zeros((2, 4), numpy.float32), legal_mask=numpy.array([[1, 0, 0], [0, 0, 0]], numpy.uint8))

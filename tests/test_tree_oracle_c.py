@@ -8,7 +8,8 @@ from oracle import build_c
 from oracle import mcts as om
 
 
-@pytest.mark.parametrize("name", ["cartpole_synth", "cartpole_pretrained", "tictactoe", "connect4", "breakout"])
+@pytest.mark.parametrize("name", ["cartpole_synth", "cartpole_pretrained", "tictactoe", "connect4", "breakout",
+                                  "connect4_n200", "breakout_n50"])
 def test_c_oracle_reproduces_reference_traces(name, game_configs):
     cfg = game_configs[name.split("_")[0]]
     A = len(cfg.action_space)

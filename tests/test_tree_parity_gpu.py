@@ -14,7 +14,7 @@ from oracle import mcts as om
 
 pytestmark = pytest.mark.gpu
 
-SEARCH_FILES = ["cartpole_synth", "cartpole_pretrained", "tictactoe", "connect4", "breakout"]
+SEARCH_FILES = ["cartpole_synth", "cartpole_pretrained", "tictactoe", "connect4", "breakout", "connect4_n200", "breakout_n50"]
 
 
 def _engine(cfg, max_games, N):
@@ -93,9 +93,9 @@ def test_teacher_forced_synthetic_vs_oracle(game, N, n, stepwise, game_configs):
 def test_fc_network_matches_reference(name, game_configs):
     cfg = game_configs["cartpole"]
     spec = netspec_from_config(cfg)
-    g = golden_npz("net_cartpole.npz")
-    eng = _engine(cfg, 8, 5)
-    eng.load_weights(weights_for("cartpole", spec))
+    g = golden_npz(f"net_{name}.npz")
+    eng = _engine(cfg, len(g["obs"]), 5)
+    eng.load_weights(weights_for(name, spec))
     r0 = eng.initial_inference(g["obs"])
     tol = dict(rtol=2e-5, atol=2e-6)
     numpy.testing.assert_allclose(r0["value_logits"], g["init_value"], **tol)
