@@ -455,7 +455,7 @@ def selfplay_loop(game, B, N, device, rank, world, D):
     import torch
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
-    lengths = [len(g.root_values) for g in finished[:64]]              # touch a few histories: they must be real
+    lengths = [len(g.root_values) for g in finished[:64]]              # materialise a few histories: they must be real
     dt_max = D.max([dt])[0]
     table, totals = parallel.gather_counters(D.dist, worker.played_games - games0, worker.env_steps - steps0,
                                              (worker.env_steps - steps0) * N, device=torch.device("cuda", device))

@@ -274,8 +274,9 @@ typedef struct MzSelfPlayPeek {
 int mz_selfplay_begin(MzHandle* h, const MzSelfPlayDesc* desc);
 int mz_selfplay_moves(MzHandle* h, int32_t n_moves, double temperature, const MzSelfPlayInject* inject, MzSelfPlayStats* stats);
 /* pointer to the staged games (pinned host memory owned by the library), valid until the next mz_selfplay_moves;
- * marks the area as consumed */
-int mz_selfplay_drain(MzHandle* h, const void** data, uint64_t* bytes, int32_t* n_games);
+ * marks the area as consumed.  `index` (may be NULL) receives a table of n_games pairs of uint64:
+ * {byte offset of the game's block, (slot << 32) | length}, so a consumer can address any game without walking. */
+int mz_selfplay_drain(MzHandle* h, const void** data, uint64_t* bytes, int32_t* n_games, const uint64_t** index);
 int mz_selfplay_peek(MzHandle* h, const MzSelfPlayPeek* out);
 
 #ifdef __cplusplus

@@ -58,6 +58,7 @@ struct SpDev {
     unsigned long long* counters;
     unsigned char* staging;    // mapped pinned host memory
     unsigned long long staging_cap;
+    unsigned long long* index; // mapped pinned host memory: per staged game {byte offset, (slot << 32) | length}
     // per-move overrides (device copies) or nullptr
     const int32_t* forced_action;
     const double* uniform;
@@ -313,8 +314,14 @@ __global__ void selfplay_pack_kernel(const SpDev s) {
             if (prev == old) { ok = 1; off = old; break; }
             old = prev;
         }
-        if (ok) { atomicAdd(&s.counters[1], 1ull); atomicAdd(&s.counters[3], 1ull); }
-        else atomicAdd(&s.counters[4], 1ull);
+        if (ok) {
+            atomicAdd(&s.counters[1], 1ull);
+            const unsigned long long i = atomicAdd(&s.counters[3], 1ull);
+            s.index[2 * i] = off;
+            s.index[2 * i + 1] = ((unsigned long long)(unsigned)g << 32) | (unsigned)T;
+        } else {
+            atomicAdd(&s.counters[4], 1ull);
+        }
     }
     ok = __shfl_sync(0xffffffffu, ok, 0);
     if (!ok) return;                                 // parked: packed by a later move, after the host has drained
@@ -362,6 +369,7 @@ struct MzSelfPlay {
     SpDev dev{};
     std::vector<void*> allocs;
     unsigned char* staging = nullptr;          // pinned + mapped
+    unsigned long long* index = nullptr;       // pinned + mapped
     unsigned long long* h_counters = nullptr;  // pinned copy of the counters
     int32_t* d_forced = nullptr;
     double* d_uniform = nullptr;
@@ -376,6 +384,7 @@ void mz_selfplay_destroy(MzHandle* h) {
     MzSelfPlay* sp = h->sp;
     for (void* p : sp->allocs) cudaFree(p);
     if (sp->staging) cudaFreeHost(sp->staging);
+    if (sp->index) cudaFreeHost(sp->index);
     if (sp->h_counters) cudaFreeHost(sp->h_counters);
     if (sp->e0) cudaEventDestroy(sp->e0);
     if (sp->e1) cudaEventDestroy(sp->e1);
@@ -430,7 +439,9 @@ extern "C" int mz_selfplay_begin(MzHandle* h, const MzSelfPlayDesc* d) {
     const unsigned long long worst = staged_block_bytes(d->max_moves, A, O) * (unsigned long long)B;
     if (cap == 0) cap = worst < (256ull << 20) ? worst : (256ull << 20);
     if (cap < staged_block_bytes(d->max_moves, A, O)) { mz_selfplay_destroy(h); return fail(h, MZ_EINVAL, "mz_selfplay_begin: staging_bytes smaller than one game"); }
+    const unsigned long long index_entries = cap / staged_block_bytes(1, A, O) + 1;
     if (cudaHostAlloc(reinterpret_cast<void**>(&sp->staging), cap, cudaHostAllocMapped) != cudaSuccess ||
+        cudaHostAlloc(reinterpret_cast<void**>(&sp->index), index_entries * 16, cudaHostAllocMapped) != cudaSuccess ||
         cudaHostAlloc(reinterpret_cast<void**>(&sp->h_counters), 64, cudaHostAllocDefault) != cudaSuccess) {
         (void)cudaGetLastError();
         mz_selfplay_destroy(h);
@@ -440,6 +451,8 @@ extern "C" int mz_selfplay_begin(MzHandle* h, const MzSelfPlayDesc* d) {
     if (cudaHostGetDevicePointer(&dptr, sp->staging, 0) != cudaSuccess) { mz_selfplay_destroy(h); return fail(h, MZ_ECUDA, "mz_selfplay_begin: staging is not device-mappable"); }
     s.staging = reinterpret_cast<unsigned char*>(dptr);
     s.staging_cap = cap;
+    if (cudaHostGetDevicePointer(&dptr, sp->index, 0) != cudaSuccess) { mz_selfplay_destroy(h); return fail(h, MZ_ECUDA, "mz_selfplay_begin: index is not device-mappable"); }
+    s.index = reinterpret_cast<unsigned long long*>(dptr);
     cudaEventCreate(&sp->e0); cudaEventCreate(&sp->e1);
     selfplay_reset_kernel<<<(B + 127) / 128, 128, 0, h->stream>>>(s, d->first_game_id);
     h->launches += 1;
@@ -518,13 +531,14 @@ extern "C" int mz_selfplay_moves(MzHandle* h, int32_t n_moves, double temperatur
     return MZ_OK;
 }
 
-extern "C" int mz_selfplay_drain(MzHandle* h, const void** data, uint64_t* bytes, int32_t* n_games) {
+extern "C" int mz_selfplay_drain(MzHandle* h, const void** data, uint64_t* bytes, int32_t* n_games, const uint64_t** index) {
     if (!h || !h->sp || !data || !bytes || !n_games) return fail(h, MZ_EINVAL, "mz_selfplay_drain: bad argument");
     MzSelfPlay* sp = h->sp;
     MZ_CUDA(h, cudaSetDevice(h->device));
     int rc = sp_read_counters(h, nullptr, 0.0f);
     if (rc) return rc;
     *data = sp->staging;
+    if (index) *index = reinterpret_cast<const uint64_t*>(sp->index);
     *bytes = sp->h_counters[2];
     *n_games = (int32_t)sp->h_counters[3];
     sp->drained_bytes = sp->h_counters[2] ? sp->h_counters[2] : 0;

@@ -358,13 +358,16 @@ class DeviceSelfPlayLoop:
         return self.stats
 
     def drain(self):
-        """(bytes, n_games): the staged finished games (a copy: the staging area is reused by the next call)."""
+        """(bytes, index) of the staged finished games - copies, the staging area is reused by the next call.
+        ``index`` is an ``[n, 2]`` uint64 array: byte offset of each game's block, ``(slot << 32) | length``."""
         eng = self.engine
-        ptr, nbytes, ngames = C.c_void_p(), C.c_uint64(), C.c_int32()
-        eng._check(eng.lib.mz_selfplay_drain(eng._h, C.byref(ptr), C.byref(nbytes), C.byref(ngames)))
-        if nbytes.value == 0:
-            return b"", 0
-        return C.string_at(ptr.value, nbytes.value), int(ngames.value)
+        ptr, nbytes, ngames, iptr = C.c_void_p(), C.c_uint64(), C.c_int32(), C.c_void_p()
+        eng._check(eng.lib.mz_selfplay_drain(eng._h, C.byref(ptr), C.byref(nbytes), C.byref(ngames), C.byref(iptr)))
+        n = int(ngames.value)
+        if n == 0:
+            return b"", numpy.zeros((0, 2), numpy.uint64)
+        index = numpy.frombuffer(C.string_at(iptr.value, 16 * n), numpy.uint64).reshape(n, 2)
+        return C.string_at(ptr.value, nbytes.value), index
 
     def peek(self):
         eng = self.engine
@@ -379,24 +382,28 @@ class DeviceSelfPlayLoop:
         return out
 
 
-def parse_staged_games(buf: bytes, n_games: int):
-    """Split the packed blocks of ``mz_selfplay_drain`` into per-game dicts of numpy views (no copies)."""
-    games, off = [], 0
+def parse_staged_game(buf: bytes, off: int):
+    """One packed block of ``mz_selfplay_drain`` -> dict of numpy views into ``buf`` (no copies)."""
     H = _lib.MZ_STAGED_HEADER_BYTES
-    for _ in range(n_games):
-        gid = int(numpy.frombuffer(buf, numpy.int64, 1, off)[0])
-        slot, T, first_to_play, O, A, nbytes = (int(x) for x in numpy.frombuffer(buf, numpy.int32, 6, off + 8))
-        p = off + H
-        root = numpy.frombuffer(buf, numpy.float64, T, p); p += 8 * T
-        visits = numpy.frombuffer(buf, numpy.int32, T * A, p).reshape(T, A); p += 4 * T * A
-        action = numpy.frombuffer(buf, numpy.int32, T, p); p += 4 * T
-        reward = numpy.frombuffer(buf, numpy.float32, T, p); p += 4 * T
-        to_play = numpy.frombuffer(buf, numpy.int32, T, p); p += 4 * T
-        obs = numpy.frombuffer(buf, numpy.float32, (T + 1) * O, p).reshape(T + 1, O)
-        games.append(dict(game_id=gid, slot=slot, length=T, first_to_play=first_to_play, root_value=root, visits=visits,
-                          action=action, reward=reward, to_play=to_play, obs=obs))
-        off += nbytes
-    assert off == len(buf), "staged blocks do not add up"
+    gid = int(numpy.frombuffer(buf, numpy.int64, 1, off)[0])
+    slot, T, first_to_play, O, A, nbytes = (int(x) for x in numpy.frombuffer(buf, numpy.int32, 6, off + 8))
+    p = off + H
+    root = numpy.frombuffer(buf, numpy.float64, T, p); p += 8 * T
+    visits = numpy.frombuffer(buf, numpy.int32, T * A, p).reshape(T, A); p += 4 * T * A
+    action = numpy.frombuffer(buf, numpy.int32, T, p); p += 4 * T
+    reward = numpy.frombuffer(buf, numpy.float32, T, p); p += 4 * T
+    to_play = numpy.frombuffer(buf, numpy.int32, T, p); p += 4 * T
+    obs = numpy.frombuffer(buf, numpy.float32, (T + 1) * O, p).reshape(T + 1, O)
+    return dict(game_id=gid, slot=slot, length=T, first_to_play=first_to_play, root_value=root, visits=visits,
+                action=action, reward=reward, to_play=to_play, obs=obs, bytes=nbytes)
+
+
+def parse_staged_games(buf: bytes, index):
+    """All staged games of one drain, in staging order."""
+    games = [parse_staged_game(buf, int(off)) for off in index[:, 0]]
+    assert sum(g["bytes"] for g in games) == len(buf), "staged blocks do not add up"
+    for g, meta in zip(games, index[:, 1]):
+        assert (int(meta) >> 32, int(meta) & 0xFFFFFFFF) == (g["slot"], g["length"])
     return games
 
 

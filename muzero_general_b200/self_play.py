@@ -26,7 +26,7 @@ from collections import deque
 
 import numpy
 
-from .engine import DeviceSelfPlayLoop, SearchEngine, parse_staged_games
+from .engine import DeviceSelfPlayLoop, SearchEngine, parse_staged_game
 
 
 # ----------------------------------------------------------------------------------------
@@ -534,7 +534,7 @@ class SelfPlay:
                 self._device_loop = DeviceBatchedSelfPlay(self, temperature_threshold)
             games = self._device_loop.moves(n_moves, temperature)
             self.played_games += len(games)
-            self.played_steps += sum(len(g) for g in games)
+            self.played_steps += games.total_moves
             return games
         self.self_play_stream(temperature, temperature_threshold)
         out = []
@@ -612,12 +612,70 @@ class DeviceBatchedSelfPlay:
                                        reward_scale=getattr(vec, "REWARD_SCALE", 1),
                                        first_game_id=worker.first_game_id,
                                        staging_bytes=int(getattr(cfg, "selfplay_staging_bytes", 0) or 0))
+        self.moves_per_call = int(getattr(cfg, "selfplay_moves_per_call", 16) or 16)
 
     def moves(self, n_moves, temperature, **inject):
-        self.loop.moves(n_moves, temperature, **inject)
-        buf, n = self.loop.drain()
-        return [PackedGameHistory(g, self.obs_shape, self.obs_dtype, self.reward_type)
-                for g in parse_staged_games(buf, n)]
+        """``n_moves`` lockstep moves -> ``PackedGames`` (a lazy sequence of the games that finished).  The moves run
+        in chunks of ``moves_per_call`` per ``mz_selfplay_moves`` (one host synchronisation and one drain per chunk);
+        if a chunk ever produces more finished games than the staging area holds, the surplus waits on the device
+        (parked slots) and arrives with the next drain - nothing is lost."""
+        out = PackedGames(self.obs_shape, self.obs_dtype, self.reward_type)
+        left = int(n_moves)
+        while left > 0:
+            k = 1 if inject else min(left, self.moves_per_call)
+            self.loop.moves(k, temperature, **inject)
+            out.add(*self.loop.drain())
+            left -= k
+        return out
+
+
+class PackedGames:
+    """Finished games of one or more drains, still in their packed device format.  ``len``, iteration and indexing
+    work like a list of ``GameHistory``; a ``PackedGameHistory`` is only created when an element is asked for, so
+    handing thousands of games per second to a consumer costs nothing per game until the consumer looks at them
+    (bulk ingest with lazily materialised histories)."""
+
+    def __init__(self, obs_shape, obs_dtype, reward_type):
+        self._args = (obs_shape, obs_dtype, reward_type)
+        self._chunks = []            # (bytes, index[n, 2])
+        self._n = 0
+        self.total_moves = 0
+
+    def add(self, buf, index):
+        if len(index):
+            self._chunks.append((buf, index))
+            self._n += len(index)
+            self.total_moves += int((index[:, 1] & numpy.uint64(0xFFFFFFFF)).sum())
+
+    def __len__(self):
+        return self._n
+
+    def __bool__(self):
+        return self._n > 0
+
+    def lengths(self):
+        """Moves per game, without touching the blocks."""
+        return numpy.concatenate([(ix[:, 1] & numpy.uint64(0xFFFFFFFF)).astype(numpy.int64) for _, ix in self._chunks]) \
+            if self._chunks else numpy.zeros(0, numpy.int64)
+
+    def _make(self, buf, off):
+        return PackedGameHistory(parse_staged_game(buf, int(off)), *self._args)
+
+    def __iter__(self):
+        for buf, index in self._chunks:
+            for off in index[:, 0]:
+                yield self._make(buf, off)
+
+    def __getitem__(self, i):
+        if isinstance(i, slice):
+            return [self[j] for j in range(*i.indices(self._n))]
+        if i < 0:
+            i += self._n
+        for buf, index in self._chunks:
+            if i < len(index):
+                return self._make(buf, index[i, 0])
+            i -= len(index)
+        raise IndexError("game index out of range")
 
 
 class BatchedSelfPlay:

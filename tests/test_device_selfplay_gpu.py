@@ -30,8 +30,7 @@ def _loop(name, B, N, seed=0, first_game_id=0, staging_bytes=0, **over):
 
 def _drain(loop):
     from muzero_general_b200.engine import parse_staged_games
-    buf, n = loop.drain()
-    return parse_staged_games(buf, n)
+    return parse_staged_games(*loop.drain())
 
 
 @pytest.mark.parametrize("name", ["tictactoe", "connect4"])
@@ -109,7 +108,6 @@ def test_cartpole_physics_one_step_at_a_time():
             obs, _, done = env.step(numpy.array([rec["action"][t]]))
             numpy.testing.assert_allclose(obs.ravel(), rec["obs"][t + 1], rtol=2e-6, atol=2e-7)
             checked += 1
-        x, th = rec["obs"][T]
         x, th = float(rec["obs"][T][0]), float(rec["obs"][T][2])
         ended = abs(x) > 2.4 or abs(th) > cp._THETA_LIMIT
         assert ended or T == 60
@@ -193,9 +191,9 @@ def test_backpressure_parks_finished_games_until_the_host_drains():
     for _ in range(80):
         st = loop.moves(1, 1.0)
         parked_max = max(parked_max, st.parked_slots)
-        buf, n = loop.drain()
+        buf, index = loop.drain()
         assert len(buf) <= 3 * 2048
-        for rec in parse_staged_games(buf, n):
+        for rec in parse_staged_games(buf, index):
             assert rec["game_id"] not in seen
             seen[rec["game_id"]] = rec["length"]
     assert parked_max > 0
@@ -224,7 +222,9 @@ def test_selfplay_api_on_the_device_loop(name, monkeypatch):
     assert worker.loop_path == "device"
     games = []
     for _ in range(12):
-        games += worker.play_moves(3, 1.0)
+        batch = worker.play_moves(3, 1.0)
+        assert len(batch.lengths()) == len(batch) and batch.total_moves == int(batch.lengths().sum())
+        games += list(batch)
     assert games and worker.env_steps == 24 * 36 and worker.played_games == len(games)
     assert worker.played_steps == sum(len(g.root_values) for g in games)
     for gh in games[:10]:
