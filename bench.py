@@ -43,7 +43,7 @@ WORKLOADS = {
     "breakout_b128_n50": ("breakout", 128, 50, 5100.0),
 }
 DEFAULT_WORKLOAD = "cartpole_b4096_n50"
-DEFAULT_EXTRAS = ["connect4_b1024_n200", "connect4_b1024_n200@fp16", "tictactoe_b8192_n50", "breakout_b128_n50"]
+DEFAULT_EXTRAS = ["connect4_b1024_n200", "connect4_b1024_n200@fp16", "connect4_b1024_n200@off", "tictactoe_b8192_n50", "breakout_b128_n50"]
 MIN_TIMED_SECONDS = 1.0
 
 # algorithmic FLOPs of initial_inference / recurrent_inference per sample

@@ -207,7 +207,8 @@ int mz_kernel_times(MzHandle* h, double* ms, int64_t* count);
 
 /* Debug / parity: one conv3x3 (C -> C, stride 1, pad 1; models.py:206-209) with optional bias, residual and
  * ReLU on host NCHW fp32 data, through the CUDA-core kernel (use_tensor_cores = 0) or the tcgen05 implicit
- * GEMM (1; C = 64, H <= 6, W <= 7).  w is [C][C][3][3] as in the reference state_dict. */
+ * GEMM (C = 64, H <= 6, W <= 7): 1 = fp16 operands, 2 = split fp16+bf16 operands with three partial products
+ * (fp32-grade, the default of the search path).  w is [C][C][3][3] as in the reference state_dict. */
 int mz_debug_conv3x3(int device, int32_t n, int32_t C, int32_t H, int32_t W, const float* x, const float* w,
                      const float* bias, const float* residual, int32_t relu, int32_t use_tensor_cores, float* out);
 

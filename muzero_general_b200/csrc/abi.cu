@@ -364,6 +364,17 @@ static int debug_out(MzHandle* h, const char* name, T* user, size_t count, int m
     return MZ_OK;
 }
 
+// The x3 towers' range guard fired: fp32 CUDA-core towers from now on (the hidden-state pool is large enough for the
+// dense layout; a captured graph refers to the old kernels and is dropped).
+void mz_switch_to_strict(MzHandle* h) {
+    if (!h->res) return;
+    resnet_use_strict(h->res);
+    h->pool_state_elems = resnet_state_elems(h->res);
+    if (h->graph_exec) { cudaGraphExecDestroy(h->graph_exec); h->graph_exec = nullptr; }
+    h->graph_key = 0; h->graph_seen = 0;
+    h->range_fallbacks += 1;
+}
+
 // ------------------------------------------------------------------------------------------
 // One batched search on device buffers (no synchronisation): fused FC kernel or step-wise pipeline.
 // ------------------------------------------------------------------------------------------
@@ -526,6 +537,19 @@ extern "C" int mz_search(MzHandle* h, const MzSearchIO* io) {
     for (const DebugOut& d : dbg_outs)
         MZ_CUDA(h, cudaMemcpyAsync(d.user, d.dev, d.bytes, cudaMemcpyDeviceToHost, h->stream));
     MZ_CUDA(h, cudaStreamSynchronize(h->stream));
+    if (h->res && !teacher && resnet_take_saturations(h->res, h->stream) > 0) {
+        // an activation left the fp16 range inside the tensor-core towers: the results above are outside the accuracy
+        // contract.  Switch this handle to the fp32 CUDA-core towers for good and redo the search.
+        mz_switch_to_strict(h);
+        MZ_CUDA(h, cudaEventRecord(h->ev0, h->stream));
+        if ((rc = mz_dispatch_search(h, call, teacher, io->trace != nullptr, io->flags))) return rc;
+        MZ_CUDA(h, cudaEventRecord(h->ev1, h->stream));
+        if (host && call.out_bytes)
+            MZ_CUDA(h, cudaMemcpyAsync(h->h_out, h->d_out, call.out_bytes, cudaMemcpyDeviceToHost, h->stream));
+        for (const DebugOut& d : dbg_outs)
+            MZ_CUDA(h, cudaMemcpyAsync(d.user, d.dev, d.bytes, cudaMemcpyDeviceToHost, h->stream));
+        MZ_CUDA(h, cudaStreamSynchronize(h->stream));
+    }
     for (const OutSlot& s : outs) memcpy(s.user, h->h_out + s.off, s.bytes);
     float ms = 0.f;
     if (cudaEventElapsedTime(&ms, h->ev0, h->ev1) == cudaSuccess) h->last_ms = ms;
@@ -565,6 +589,12 @@ static int run_inference(MzHandle* h, int n, int mem, const float* in, const int
         if (e != cudaSuccess) return fail(h, MZ_ECUDA, std::string("fc_inference launch: ") + cudaGetErrorString(e));
         h->launches += 1;
     } else {
+        std::string e;
+        rc = resnet_inference(h->res, c, h->stream, &h->launches, &e);
+        if (rc) return fail(h, rc, "resnet_inference: " + e);
+    }
+    if (h->res && resnet_take_saturations(h->res, h->stream) > 0) {
+        mz_switch_to_strict(h);
         std::string e;
         rc = resnet_inference(h->res, c, h->stream, &h->launches, &e);
         if (rc) return fail(h, rc, "resnet_inference: " + e);

@@ -36,10 +36,13 @@
 #include "pipeline.h"
 #include "conv_tc.h"
 #include "launch.h"
+#include "tc_common.cuh"
 
 namespace mz {
 
 namespace {
+
+using namespace tc;
 
 constexpr int kC = 64;                 // channels in = out
 constexpr int kPos = 64;               // positions per board (8 x 8 padded grid)
@@ -70,47 +73,6 @@ struct Smem {
 };
 static_assert(Smem::total <= 232448, "shared memory budget");
 
-MZ_DEVINL uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-MZ_DEVINL void mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-MZ_DEVINL void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-MZ_DEVINL void mbar_arrive(uint32_t bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-MZ_DEVINL void mbar_wait(uint32_t bar, uint32_t parity) {
-    uint32_t done;
-    do {
-        asm volatile(
-            "{\n\t"
-            ".reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t"
-            "}" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
-    } while (!done);
-}
-MZ_DEVINL void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
-}
-// exactly one lane of a converged warp (ptxas then knows the tcgen05 operands come from a single thread and
-// moves them to uniform registers without a broadcast loop)
-MZ_DEVINL bool elect_one() {
-    uint32_t pred;
-    asm volatile(
-        "{\n\t"
-        ".reg .pred P;\n\t"
-        "elect.sync _|P, 0xffffffff;\n\t"
-        "selp.u32 %0, 1, 0, P;\n\t"
-        "}" : "=r"(pred));
-    return pred != 0;
-}
-MZ_DEVINL void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-MZ_DEVINL void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
 // kind::f16 with fp16 operands (format 0), fp32 accumulate, A and B K-major, M = 128, N = 64
 // (cute::UMMA::InstrDescriptor)
 constexpr uint32_t kIdesc = (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(kAccCols >> 3) << 17) | ((128u >> 4) << 24);
@@ -123,12 +85,6 @@ MZ_DEVINL void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint3
         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
         "}" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(kIdesc), "r"(accumulate) : "memory");
 }
-// descriptor words shared by every A / B descriptor of this kernel (K-major SWIZZLE_128B, SBO = 1024 B, version 1);
-// the hardware applies the 128B swizzle on absolute shared-memory address bits, so row-shifted tap windows need
-// no base_offset (checked: tests/test_conv_gpu.py is exact with base_offset = 0 and wrong with the row phase)
-constexpr uint32_t kDescLoFlags = 1u << 16;                                           // LBO field = 1 (unused)
-constexpr uint32_t kDescHi = ((1024u >> 4) & 0x3FFFu) | (1u << 14) | (2u << 29);      // SBO | version | SWIZZLE_128B
-
 MZ_DEVINL void umma_f16_words(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t accumulate) {
     asm volatile(
         "{\n\t"
@@ -140,24 +96,6 @@ MZ_DEVINL void umma_f16_words(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uin
         "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n\t"
         "}" ::"r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(kIdesc), "r"(accumulate), "r"(kDescHi) : "memory");
 }
-// shared -> global bulk copy (TMA unit), tracked by the thread's bulk async-group
-MZ_DEVINL void bulk_s2g(void* gdst, uint32_t ssrc, uint32_t bytes) {
-    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(ssrc), "r"(bytes) : "memory");
-}
-MZ_DEVINL void umma_commit(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-// two fp32 -> packed fp16x2, round to nearest even, saturating to the finite range
-MZ_DEVINL uint32_t pack_f16x2(float lo, float hi) {
-    uint32_t r;
-    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
-    return r;
-}
-MZ_DEVINL float2 unpack_f16x2(uint32_t v) {
-    __half2 h = *reinterpret_cast<__half2*>(&v);
-    return __half22float2(h);
-}
-
 }  // namespace
 
 // activation buffers hold fp16 (the host side types them float*: 2048 float slots per board)
@@ -747,6 +685,6 @@ cudaError_t launch_conv_tower_tc(const TowerArgs& a, int sm_count, cudaStream_t 
 int conv_tc_max_boards_fused(int sm_count) { return sm_count * kTowerMaxTiles * kBoards; }   // conservative: one CTA per SM
 
 bool conv_tc_supported(int C, int H, int W) { return C == kC && H >= 1 && H <= 6 && W >= 1 && W <= 7; }
-int conv_tc_board_elems() { return kBoardHalves / 2; }      // float slots per board (the buffers hold fp16)
+int conv_tc_board_elems(bool split) { return split ? kBoardHalves : kBoardHalves / 2; }      // float slots per board (fp16 plane, or x_h | x_l planes)
 
 }  // namespace mz

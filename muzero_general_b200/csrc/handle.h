@@ -53,6 +53,7 @@ struct MzHandle {
     std::vector<void*> debug_allocs;
     std::map<std::string, std::pair<void*, size_t>> named;
     MzSelfPlay* sp = nullptr;          // mz_selfplay_begin
+    int range_fallbacks = 0;           // times the x3 range guard switched this handle to the fp32 towers (0 or 1)
 };
 
 int mz_fail(MzHandle* h, int code, const std::string& msg);
@@ -70,3 +71,4 @@ static inline int fail(MzHandle* h, int code, const std::string& msg) { return m
 // step-wise pipeline (eager for the first two calls with a given argument set, then a CUDA-graph replay).
 int mz_dispatch_search(MzHandle* h, const mz::SearchCall& call, bool teacher, bool trace, int flags);
 void mz_selfplay_destroy(MzHandle* h);
+void mz_switch_to_strict(MzHandle* h);

@@ -79,7 +79,9 @@ int resnet_load_weights(ResNetDevice* r, const MzTensor* tensors, int n, std::st
 int resnet_inference(ResNetDevice* r, const InferCall& c, cudaStream_t stream, int64_t* launches, std::string* err);
 int resnet_debug_conv(int n, int C, int H, int W, const float* x, const float* w_oihw, const float* bias,
                       const float* residual, int relu, int use_tc, float* out, int sm_count, std::string* err);
-const char* resnet_numerics(const ResNetDevice* r);   // arithmetic of the residual towers (bench.py dtype)
+const char* resnet_numerics(const ResNetDevice* r);
+int resnet_take_saturations(ResNetDevice* r, cudaStream_t stream);   // x3 range guard (synchronises)
+void resnet_use_strict(ResNetDevice* r);                             // fp32 CUDA-core towers from now on   // arithmetic of the residual towers (bench.py dtype)
 int resnet_state_elems(const ResNetDevice* r);        // floats per stored hidden state in the pool
 int resnet_states_to_nchw(ResNetDevice* r, const float* states, int count, float* out, cudaStream_t stream);
 

@@ -22,6 +22,7 @@
 #include <string>
 #include <vector>
 
+#include <cuda_bf16.h>
 #include <cuda_fp16.h>
 
 #include "common.cuh"
@@ -32,6 +33,16 @@
 #include "pipeline.h"
 
 namespace mz {
+
+// Board layouts of the tensor-core towers (conv_tc.cu / conv_x3.cu): kLayoutF16 = one fp16 plane of 4096 halves,
+// kLayoutSplit = two planes, x_h fp16 then x_l bf16 with x ~ x_h + x_l (8192 halves = 4096 float slots per board).
+enum { kLayoutDense = 0, kLayoutF16 = 1, kLayoutSplit = 2 };
+
+__device__ __forceinline__ void split_f32(float v, __half* hi, __nv_bfloat16* lo) {
+    const __half h = __float2half_rn(fminf(fmaxf(v, -65504.0f), 65504.0f));     // saturate: x_l carries what is left
+    *hi = h;
+    *lo = __float2bfloat16_rn(v - __half2float(h));
+}
 
 // ------------------------------------------------------------------------------------------
 // conv3x3 (+folded BN bias, +residual, +ReLU), stride 1 or 2, pad 1
@@ -47,7 +58,7 @@ struct ConvArgs {
     int pool_stride;
     int n, Cin, Cout, Hin, Win, Ho, Wo, stride, relu, A;
     int boards_per_cta, cin_chunk;
-    int out_p64c4;            // write the fp16 tensor-core board layout (P64S, conv_tc.cu) instead of NCHW
+    int out_p64c4;            // kLayoutF16 / kLayoutSplit: write the tensor-core board layout (P64S) instead of NCHW
 };
 
 template <int P, int STRIDE, int MAX_ITEMS>
@@ -157,8 +168,13 @@ __global__ void __launch_bounds__(256) conv3x3_kernel(const __grid_constant__ Co
                 if (a.relu) r = fmaxf(r, 0.0f);
                 if (a.out_p64c4) {
                     const int pos = (y + 1) * 8 + seg * P + p;
-                    reinterpret_cast<__half*>(a.out)[(size_t)g * 4096 + pos * 64 + (((co >> 3) ^ (pos & 7)) << 3) + (co & 7)] =
-                        __float2half_rn(r);
+                    const int e = pos * 64 + (((co >> 3) ^ (pos & 7)) << 3) + (co & 7);
+                    if (a.out_p64c4 == kLayoutSplit) {
+                        __half* base = reinterpret_cast<__half*>(a.out) + (size_t)g * 8192;
+                        split_f32(r, base + e, reinterpret_cast<__nv_bfloat16*>(base + 4096) + e);
+                    } else {
+                        reinterpret_cast<__half*>(a.out)[(size_t)g * 4096 + e] = __float2half_rn(r);
+                    }
                 }
                 else
                     a.out[o + p] = r;
@@ -209,7 +225,7 @@ struct HeadsArgs {
     float* pool_hidden;        // pool mode target
     int pool_stride, out_slot;
     int smem_floats;
-    int p64c4, W;              // input (and pool target) use the tensor-core board layout
+    int p64c4, W;              // kLayoutF16 / kLayoutSplit: input (and pool target) use the tensor-core board layout
     float* state_p64c4;        // [n, 4096 fp16] rescaled state in P64C8 (input of the prediction tower), or nullptr
     int w_lo, w_floats;        // slice of the head blob this launch needs (staged in shared memory)
     int warp_floats;           // per-warp scratch: x tile + two activation vectors
@@ -268,14 +284,23 @@ __global__ void __launch_bounds__(kHeadThreads) heads_kernel(const __grid_consta
     for (int g = blockIdx.x * ngroups + group; g < a.n; g += gridDim.x * ngroups) {
         // ---- stage x[p][c]
         if (a.p64c4) {
-            const uint4* x8 = reinterpret_cast<const uint4*>(reinterpret_cast<const __half*>(a.x) + (size_t)g * 4096);
+            const bool split = a.p64c4 == kLayoutSplit;
+            const uint4* x8 = reinterpret_cast<const uint4*>(reinterpret_cast<const __half*>(a.x) + (size_t)g * (split ? 8192 : 4096));
             for (int i = t; i < cj * HW; i += kHeadGroup) {
                 const int j = i % cj, p = i / cj;
                 const int pos = (p / a.W + 1) * 8 + (p % a.W);
                 const uint4 v = x8[pos * 8 + (j ^ (pos & 7))];
                 const __half2* h2 = reinterpret_cast<const __half2*>(&v);
-                const float2 f0 = __half22float2(h2[0]), f1 = __half22float2(h2[1]);
-                const float2 f2 = __half22float2(h2[2]), f3 = __half22float2(h2[3]);
+                float2 f0 = __half22float2(h2[0]), f1 = __half22float2(h2[1]);
+                float2 f2 = __half22float2(h2[2]), f3 = __half22float2(h2[3]);
+                if (split) {                                   // x = x_h + x_l (second plane, bf16)
+                    const uint4 w = x8[512 + pos * 8 + (j ^ (pos & 7))];
+                    const __nv_bfloat162* b2 = reinterpret_cast<const __nv_bfloat162*>(&w);
+                    const float2 g0 = __bfloat1622float2(b2[0]), g1 = __bfloat1622float2(b2[1]);
+                    const float2 g2 = __bfloat1622float2(b2[2]), g3 = __bfloat1622float2(b2[3]);
+                    f0.x += g0.x; f0.y += g0.y; f1.x += g1.x; f1.y += g1.y;
+                    f2.x += g2.x; f2.y += g2.y; f3.x += g3.x; f3.y += g3.y;
+                }
                 float4* d = reinterpret_cast<float4*>(s_x + p * CP + 8 * j);
                 d[0] = make_float4(f0.x, f0.y, f1.x, f1.y);
                 d[1] = make_float4(f2.x, f2.y, f3.x, f3.y);
@@ -328,14 +353,28 @@ __global__ void __launch_bounds__(kHeadThreads) heads_kernel(const __grid_consta
 #pragma unroll
                         for (int e = 0; e < 8; ++e) a.rescaled[(size_t)g * C * HW + (8 * j + e) * HW + p] = v[e];
                     }
-                    uint4 packed;                                   // fp16 operand of the tensor-core convs
+                    uint4 packed, packed_lo;                        // 16-bit operands of the tensor-core convs
                     __half2* h2 = reinterpret_cast<__half2*>(&packed);
+                    __nv_bfloat162* b2 = reinterpret_cast<__nv_bfloat162*>(&packed_lo);
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) h2[e] = __floats2half2_rn(v[2 * e], v[2 * e + 1]);
-                    const int off8 = pos * 8 + (j ^ (pos & 7));     // in 16-byte units inside the 8 KB state
-                    if (a.pool_hidden)
-                        reinterpret_cast<uint4*>(a.pool_hidden)[((size_t)g * a.pool_stride + a.out_slot) * 512 + off8] = packed;
-                    if (a.state_p64c4) reinterpret_cast<uint4*>(a.state_p64c4)[(size_t)g * 512 + off8] = packed;
+                    for (int e = 0; e < 4; ++e) {
+                        h2[e] = __floats2half2_rn(v[2 * e], v[2 * e + 1]);
+                        const float2 back = __half22float2(h2[e]);
+                        b2[e] = __floats2bfloat162_rn(v[2 * e] - back.x, v[2 * e + 1] - back.y);
+                    }
+                    const bool split = a.p64c4 == kLayoutSplit;
+                    const int off8 = pos * 8 + (j ^ (pos & 7));     // in 16-byte units inside the state's first plane
+                    const size_t board16 = split ? 1024 : 512;      // 16-byte units per stored state
+                    if (a.pool_hidden) {
+                        uint4* dst = reinterpret_cast<uint4*>(a.pool_hidden) + ((size_t)g * a.pool_stride + a.out_slot) * board16;
+                        dst[off8] = packed;
+                        if (split) dst[512 + off8] = packed_lo;
+                    }
+                    if (a.state_p64c4) {
+                        uint4* dst = reinterpret_cast<uint4*>(a.state_p64c4) + (size_t)g * board16;
+                        dst[off8] = packed;
+                        if (split) dst[512 + off8] = packed_lo;
+                    }
                 }
             } else {
                 for (int i = t; i < C * HW; i += kHeadGroup) {
@@ -445,21 +484,33 @@ __global__ void copy_from_pool_kernel(const float* pool, float* out, int n, int 
 }
 
 // dense fp32 NCHW [count][C][H*W]  <->  fp16 P64C8 [count][C/8][64][8]
-__global__ void nchw_to_p64c4_kernel(const float* in, float* out, int count, int C, int H, int W) {
+__global__ void nchw_to_p64c4_kernel(const float* in, float* out, int count, int C, int H, int W, int split) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int HW = H * W;
     if (i >= (size_t)count * C * HW) return;
     const size_t g = i / ((size_t)C * HW);
     const int c = (i / HW) % C, p = i % HW;
-    reinterpret_cast<__half*>(out)[g * 4096 + p64c4_index(c, p, W)] = __float2half_rn(in[i]);
+    const int e = p64c4_index(c, p, W);
+    if (split) {
+        __half* base = reinterpret_cast<__half*>(out) + g * 8192;
+        split_f32(in[i], base + e, reinterpret_cast<__nv_bfloat16*>(base + 4096) + e);
+    } else {
+        reinterpret_cast<__half*>(out)[g * 4096 + e] = __float2half_rn(in[i]);
+    }
 }
-__global__ void p64c4_to_nchw_kernel(const float* in, float* out, int count, int C, int H, int W) {
+__global__ void p64c4_to_nchw_kernel(const float* in, float* out, int count, int C, int H, int W, int split) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int HW = H * W;
     if (i >= (size_t)count * C * HW) return;
     const size_t g = i / ((size_t)C * HW);
     const int c = (i / HW) % C, p = i % HW;
-    out[i] = __half2float(reinterpret_cast<const __half*>(in)[g * 4096 + p64c4_index(c, p, W)]);
+    const int e = p64c4_index(c, p, W);
+    if (split) {
+        const __half* base = reinterpret_cast<const __half*>(in) + g * 8192;
+        out[i] = __half2float(base[e]) + __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(base + 4096)[e]);
+    } else {
+        out[i] = __half2float(reinterpret_cast<const __half*>(in)[g * 4096 + e]);
+    }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -471,6 +522,7 @@ struct ConvLayer {
     long b_off;               // folded BN bias [cout], -1 = none
     long tc_off;              // tensor-core image [9][C/4][C][4] (tf32), -1 = none
     long tc_table_off;        // dynamics first conv: action-plane table [64][C], -1 = none
+    long tc_scale_off;        // x3 mode: [C] per-output-channel power of two undoing the weight prescale, -1 = none
 };
 
 struct ResNetDevice {
@@ -490,7 +542,11 @@ struct ResNetDevice {
     float* scratch_hidden = nullptr;   // [B, C*hh*hw] rescaled state when no pool is given (dense NCHW)
     float* scratch_state = nullptr;    // [B, 4096 fp16] same state in P64C8 (tensor-core path)
     bool loaded = false;
-    bool use_tc = false;               // residual towers on tcgen05 (conv_tc.cu)
+    bool use_tc = false;               // residual towers on tcgen05 (conv_tc.cu / conv_x3.cu)
+    bool split = false;                // x3 mode: split operands, fp32-grade accuracy (conv_x3.cu); false = plain fp16 operands
+    bool tc_capable = false;           // the shape allows the tensor-core towers at all
+    int* d_sat = nullptr;              // x3 mode: number of epilogue threads that stored an activation beyond the fp16 range
+    int fell_back = 0;                 // set when the range guard switched this net to the fp32 CUDA-core towers
     bool fuse_small = true;            // CUDA-core towers as one fused launch where they fit (small_tower.cu); MZ_NO_FUSE=1: per layer
     int state_elems = 0;               // float slots per stored hidden state (dense C*H*W, or 2048 = 4096 fp16 for P64C8)
 };
@@ -529,11 +585,15 @@ ResNetDevice* resnet_create(const MzNetDesc& net, int max_batch, int sm_count, s
     const char* no_tc = getenv("MZ_NO_TC");
     const char* tc_mode = getenv("MZ_TC_MODE");
     const bool tc_off = (no_tc && no_tc[0] == '1') || (tc_mode && strcmp(tc_mode, "off") == 0);
-    r->use_tc = !net.downsample && conv_tc_supported(net.channels, r->hh, r->hw) && !tc_off;
+    r->tc_capable = !net.downsample && conv_tc_supported(net.channels, r->hh, r->hw);
+    r->use_tc = r->tc_capable && !tc_off;
+    // default "x3": split 16-bit operands, three partial products, fp32-grade accuracy; "fp16": plain fp16 operands
+    // (3x fewer MMAs, ~1e-2 hidden-state error: opt-in)
+    r->split = r->use_tc && !(tc_mode && strcmp(tc_mode, "fp16") == 0);
     const char* no_fuse = getenv("MZ_NO_FUSE");
     r->fuse_small = !(no_fuse && no_fuse[0] == '1');
-    r->state_elems = r->use_tc ? conv_tc_board_elems() : r->C * r->hh * r->hw;
-    if (r->use_tc) max_elems = std::max(max_elems, (size_t)conv_tc_board_elems());
+    r->state_elems = r->use_tc ? conv_tc_board_elems(r->split) : r->C * r->hh * r->hw;
+    if (r->use_tc) max_elems = std::max(max_elems, (size_t)conv_tc_board_elems(r->split));
     r->ws_elems = max_elems * (size_t)max_batch;
     for (int i = 0; i < 3; ++i) {
         if (cudaMalloc(&r->ws[i], r->ws_elems * 4 + 64) != cudaSuccess) { *err = "workspace allocation failed"; resnet_destroy(r); return nullptr; }
@@ -544,6 +604,8 @@ ResNetDevice* resnet_create(const MzNetDesc& net, int max_batch, int sm_count, s
         *err = "workspace allocation failed"; resnet_destroy(r); return nullptr;
     }
     cudaMemset(r->scratch_state, 0, (size_t)max_batch * r->state_elems * 4 + 64);
+    if (cudaMalloc(&r->d_sat, 64) != cudaSuccess) { *err = "workspace allocation failed"; resnet_destroy(r); return nullptr; }
+    cudaMemset(r->d_sat, 0, 64);
     return r;
 }
 
@@ -552,6 +614,7 @@ void resnet_destroy(ResNetDevice* r) {
     for (int i = 0; i < 3; ++i) if (r->ws[i]) cudaFree(r->ws[i]);
     if (r->scratch_hidden) cudaFree(r->scratch_hidden);
     if (r->scratch_state) cudaFree(r->scratch_state);
+    if (r->d_sat) cudaFree(r->d_sat);
     if (r->d_conv) cudaFree(r->d_conv);
     if (r->d_head) cudaFree(r->d_head);
     delete r;
@@ -595,8 +658,21 @@ uint16_t to_f16(float x) {          // IEEE fp32 -> fp16, round to nearest even,
     return (uint16_t)(sign | h);
 }
 
+float f16_to_float(uint16_t h) {
+    const uint32_t sign = (uint32_t)(h & 0x8000u) << 16;
+    uint32_t e = (h >> 10) & 0x1Fu, m = h & 0x3FFu, u;
+    if (e == 0) {
+        if (m == 0) u = sign;
+        else { int sh = 0; while (!(m & 0x400u)) { m <<= 1; ++sh; } m &= 0x3FFu; u = sign | ((uint32_t)(113 - sh) << 23) | (m << 13); }
+    } else if (e == 31) u = sign | 0x7F800000u | (m << 13);
+    else u = sign | ((e + 112) << 23) | (m << 13);
+    float f;
+    memcpy(&f, &u, 4);
+    return f;
+}
+
 bool pack_conv(Loader& L, const std::string& conv, const std::string& bn, int cin, int cout, int stride,
-               std::vector<float>& blob, std::vector<ConvLayer>& layers, bool tc = false, int H = 0, int W = 0) {
+               std::vector<float>& blob, std::vector<ConvLayer>& layers, int tc = 0, int H = 0, int W = 0) {
     const MzTensor* w = L.get(conv + ".weight", (int64_t)cout * cin * 9);
     if (!w) return false;
     std::vector<double> scale(cout, 1.0), shift(cout, 0.0);
@@ -627,8 +703,56 @@ bool pack_conv(Loader& L, const std::string& conv, const std::string& bn, int ci
         l.b_off = -1;
     }
     while (blob.size() % 4) blob.push_back(0.0f);           // keep every layer 16-byte aligned
-    l.tc_off = l.tc_table_off = -1;
-    if (tc) {
+    l.tc_off = l.tc_table_off = l.tc_scale_off = -1;
+    if (tc == kLayoutSplit) {
+        // x3 image [tap][128 rows][cin 64]: rows 0..63 = w_h of cout 0..63, rows 64..127 = w_l; w' = w * 2^k with k per
+        // output channel such that the row's largest |w'| lies in [1, 2); w_h = fp16(w'), w_l = fp16(w' - w_h).
+        // The 16-byte chunks of a row are XOR-ed with row % 8 (UMMA K-major SWIZZLE_128B).
+        const int C = cout;
+        l.tc_off = (long)blob.size();
+        blob.resize(blob.size() + (size_t)9 * 128 * C / 2);
+        l.tc_scale_off = (long)blob.size();
+        blob.resize(blob.size() + (size_t)C, 1.0f);
+        uint16_t* img = reinterpret_cast<uint16_t*>(blob.data() + l.tc_off);
+        float* undo = blob.data() + l.tc_scale_off;
+        for (int co = 0; co < C; ++co) {
+            float mx = 0.0f;
+            for (int ci = 0; ci < C; ++ci)
+                for (int tap = 0; tap < 9; ++tap)
+                    mx = std::max(mx, fabsf((float)((double)w->data[((size_t)co * cin + ci) * 9 + tap] * scale[co])));
+            int k = 0;
+            if (mx > 0.0f && std::isfinite(mx)) { int e; frexpf(mx, &e); k = 1 - e; }      // mx * 2^k in [1, 2)
+            if (k > 100) k = 100;
+            if (k < -100) k = -100;
+            undo[co] = ldexpf(1.0f, -k);
+            for (int tap = 0; tap < 9; ++tap)
+                for (int ci = 0; ci < C; ++ci) {
+                    const float wf = (float)((double)w->data[((size_t)co * cin + ci) * 9 + tap] * scale[co]);   // the fp32 path's weight
+                    const float ws = ldexpf(wf, k);
+                    const uint16_t hb = to_f16(ws);
+                    const float back = f16_to_float(hb);
+                    const uint16_t lb = to_f16(ws - back);
+                    const size_t col = (size_t)((((ci >> 3) ^ (co & 7))) << 3) + (ci & 7);
+                    img[((size_t)tap * 128 + co) * C + col] = hb;
+                    img[((size_t)tap * 128 + 64 + co) * C + col] = lb;
+                }
+        }
+        if (cin == C + 1) {
+            l.tc_table_off = (long)blob.size();
+            blob.resize(blob.size() + (size_t)64 * C, 0.0f);
+            float* tab = blob.data() + l.tc_table_off;
+            for (int y = 0; y < H; ++y)
+                for (int x = 0; x < W; ++x)
+                    for (int co = 0; co < C; ++co) {
+                        double acc = 0.0;
+                        for (int dy = -1; dy <= 1; ++dy)
+                            for (int dx = -1; dx <= 1; ++dx)
+                                if (y + dy >= 0 && y + dy < H && x + dx >= 0 && x + dx < W)
+                                    acc += (double)w->data[((size_t)co * cin + C) * 9 + (dy + 1) * 3 + (dx + 1)] * scale[co];
+                        tab[((y + 1) * 8 + x) * C + co] = (float)acc;
+                    }
+        }
+    } else if (tc) {
         // fp16 image [tap][cout][cin] over the first 64 input channels, the 16-byte chunks of a cout row XOR-ed with
         // cout % 8 (UMMA K-major SWIZZLE_128B; two halves per float slot of the blob); an extra (65th) input channel
         // is the constant action plane and becomes a per-position fp32 table (sum of the taps that stay inside the board)
@@ -662,7 +786,7 @@ bool pack_conv(Loader& L, const std::string& conv, const std::string& bn, int ci
 }
 
 bool pack_resblock(Loader& L, const std::string& p, int ch, std::vector<float>& blob, std::vector<ConvLayer>& layers,
-                   bool tc = false) {
+                   int tc = 0) {
     return pack_conv(L, p + ".conv1", p + ".bn1", ch, ch, 1, blob, layers, tc) &&
            pack_conv(L, p + ".conv2", p + ".bn2", ch, ch, 1, blob, layers, tc);
 }
@@ -720,7 +844,9 @@ int resnet_load_weights(ResNetDevice* r, const MzTensor* tensors, int n, std::st
     } else {
         ok = ok && pack_conv(L, rp + ".conv", rp + ".bn", nd.obs_c, C, 1, conv, r->rep_trunk);
     }
-    const bool tc = r->use_tc;
+    // the tensor-core images are packed whenever the shape allows them (both the fp16 and the x3 image are cheap), so the
+    // range guard can switch paths without reloading; which one is used is decided per launch
+    const int tc = !r->tc_capable ? 0 : (r->split ? kLayoutSplit : kLayoutF16);
     for (int i = 0; ok && i < nd.blocks; ++i) ok = pack_resblock(L, rp + ".resblocks." + std::to_string(i), C, conv, r->rep_trunk, tc);
     const std::string dp = "dynamics_network.module";
     ok = ok && pack_conv(L, dp + ".conv", dp + ".bn", C + 1, C, 1, conv, r->dyn, tc, r->hh, r->hw);
@@ -754,6 +880,7 @@ struct Runner {
         t.w = r->d_conv + l.tc_off;
         t.bias = l.b_off >= 0 ? r->d_conv + l.b_off : nullptr;
         t.action_table = l.tc_table_off >= 0 ? r->d_conv + l.tc_table_off : nullptr;
+        t.scale = l.tc_scale_off >= 0 ? r->d_conv + l.tc_scale_off : nullptr;
         t.in_buf = in_buf; t.out_buf = out_buf; t.res_buf = res_buf; t.relu = relu ? 1 : 0;
         return t;
     }
@@ -762,11 +889,12 @@ struct Runner {
         a.n = n; a.H = r->hh; a.W = r->hw; a.A = r->net.action_space;
         static const int dbg = getenv("MZ_TC_DEBUG_SKIP") ? atoi(getenv("MZ_TC_DEBUG_SKIP")) : 0;
         a.debug_skip = dbg;
+        a.g0 = 0; a.sat_count = r->d_sat;
         kt_begin(KT_TOWER, stream);
-        cudaError_t e = launch_conv_tower_tc(a, r->sm_count, stream);
+        cudaError_t e = r->split ? launch_conv_tower_x3(a, r->sm_count, stream) : launch_conv_tower_tc(a, r->sm_count, stream);
         kt_end(stream);
         if (e != cudaSuccess) return fail("conv_tower_tc launch", e);
-        *launches += 1;
+        *launches += r->split ? conv_x3_launches(n, r->sm_count) : 1;
         return true;
     }
 
@@ -798,7 +926,7 @@ struct Runner {
     const float* tower_tc(const std::vector<ConvLayer>& layers, size_t first_layer, bool stem, size_t count, const float* ext,
                           bool ext_reusable, float* const ws[3], const int32_t* gather_parent, int pool_stride,
                           const int32_t* action) {
-        if (n > conv_tc_max_boards_fused(r->sm_count)) {
+        if (!r->split && n > conv_tc_max_boards_fused(r->sm_count)) {
             // too many tiles per CTA for the fused mode: one launch per conv
             float* free_ws[3]; int nf = 0;
             for (int i = 0; i < 3; ++i) if (ws[i] != ext) free_ws[nf++] = ws[i];
@@ -863,7 +991,7 @@ struct Runner {
               const int32_t* gather_parent = nullptr, int pool_stride = 0, const int32_t* action = nullptr,
               bool out_p64c4 = false) {
         ConvArgs a{};
-        a.out_p64c4 = out_p64c4 ? 1 : 0;
+        a.out_p64c4 = out_p64c4 ? (r->split ? kLayoutSplit : kLayoutF16) : 0;
         a.in = in; a.out = out; a.residual = residual; a.w = r->d_conv + l.w_off;
         a.bias = l.b_off >= 0 ? r->d_conv + l.b_off : nullptr;
         a.gather_parent = gather_parent; a.pool_stride = pool_stride; a.action = action;
@@ -951,7 +1079,7 @@ struct Runner {
     bool heads(const float* x, int n_heads, const HeadDesc* h0, const HeadDesc* h1, float* l0, float* l1, float* s0, float* s1,
                float* rescaled, float* pool_hidden, int pool_stride, int out_slot, bool p64c4 = false, float* state_p64c4 = nullptr) {
         HeadsArgs a{};
-        a.p64c4 = p64c4 ? 1 : 0; a.W = r->hw; a.state_p64c4 = state_p64c4;
+        a.p64c4 = p64c4 ? (r->split ? kLayoutSplit : kLayoutF16) : 0; a.W = r->hw; a.state_p64c4 = state_p64c4;
         a.x = x; a.blob = r->d_head; a.n = n; a.C = r->C; a.HW = r->hh * r->hw; a.S = r->net.support_size;
         a.n_heads = n_heads;
         int maxw = 32;
@@ -1035,7 +1163,7 @@ static int resnet_inference_tc(ResNetDevice* r, const InferCall& c, cudaStream_t
         if (!c.gather_parent) {
             // plain API call: dense NCHW hidden states -> P64C4
             const size_t total = (size_t)n * C * hh * hw;
-            nchw_to_p64c4_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(c.in, spare, n, C, hh, hw);
+            nchw_to_p64c4_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(c.in, spare, n, C, hh, hw, r->split ? 1 : 0);
             *launches += 1;
             in = spare;
         }
@@ -1055,8 +1183,25 @@ static int resnet_inference_tc(ResNetDevice* r, const InferCall& c, cudaStream_t
 
 int resnet_state_elems(const ResNetDevice* r) { return r->state_elems; }
 const char* resnet_numerics(const ResNetDevice* r) {
-    return r->use_tc ? "fp16 operands / f32 accumulate (tensor-core towers), f32 heads, f64 tree statistics"
-                     : "f32 nets + f64 tree statistics";
+    if (!r->use_tc) return r->fell_back ? "f32 nets + f64 tree statistics (tensor-core towers left after an activation exceeded the fp16 range)"
+                                        : "f32 nets + f64 tree statistics";
+    return r->split ? "f32-grade nets (tensor-core towers on split fp16+bf16 operands, 3 partial products, f32 accumulate; f32 heads) + f64 tree statistics"
+                    : "fp16 operands / f32 accumulate (tensor-core towers), f32 heads, f64 tree statistics";
+}
+
+// Range guard of the x3 towers: number of epilogue threads that stored an activation beyond the fp16 range since the
+// last call (synchronises the stream).  resnet_use_strict switches the handle to the fp32 CUDA-core towers for good.
+int resnet_take_saturations(ResNetDevice* r, cudaStream_t stream) {
+    if (!r->use_tc || !r->split || !r->d_sat) return 0;
+    int count = 0;
+    if (cudaMemcpyAsync(&count, r->d_sat, 4, cudaMemcpyDeviceToHost, stream) != cudaSuccess) return 0;
+    if (cudaStreamSynchronize(stream) != cudaSuccess) return 0;
+    if (count) cudaMemsetAsync(r->d_sat, 0, 4, stream);
+    return count;
+}
+void resnet_use_strict(ResNetDevice* r) {
+    r->use_tc = false; r->split = false; r->fell_back = 1;
+    r->state_elems = r->C * r->hh * r->hw;           // dense NCHW states: smaller than the board layout, the pool fits
 }
 
 // Stand-alone conv3x3 (+bias, +residual, +ReLU) on host NCHW data through either implementation.
@@ -1074,11 +1219,13 @@ int resnet_debug_conv(int n, int C, int H, int W, const float* x, const float* w
     Loader L{&t, 1, err};
     std::vector<float> blob;
     std::vector<ConvLayer> layers;
-    if (!pack_conv(L, "conv", "", C, C, 1, blob, layers, use_tc != 0, H, W)) return MZ_EINVAL;
+    r.use_tc = use_tc != 0; r.split = use_tc == 2; r.tc_capable = true;
+    if (!pack_conv(L, "conv", "", C, C, 1, blob, layers, use_tc == 2 ? kLayoutSplit : (use_tc ? kLayoutF16 : 0), H, W)) return MZ_EINVAL;
     long bias_off = -1;
     if (bias) { bias_off = (long)blob.size(); blob.insert(blob.end(), bias, bias + C); while (blob.size() % 4) blob.push_back(0.f); }
     layers[0].b_off = bias_off;
-    const size_t dense = (size_t)n * C * H * W, packed = (size_t)n * conv_tc_board_elems();
+    const bool split = use_tc == 2;
+    const size_t dense = (size_t)n * C * H * W, packed = (size_t)n * conv_tc_board_elems(split);
     float *d_blob = nullptr, *d_x = nullptr, *d_res = nullptr, *d_out = nullptr, *d_px = nullptr, *d_pres = nullptr, *d_pout = nullptr;
     auto cleanup = [&]() { for (float* p : {d_blob, d_x, d_res, d_out, d_px, d_pres, d_pout}) if (p) cudaFree(p); };
     bool ok = cudaMalloc(&d_blob, blob.size() * 4) == cudaSuccess && cudaMalloc(&d_x, dense * 4) == cudaSuccess &&
@@ -1097,10 +1244,10 @@ int resnet_debug_conv(int n, int C, int H, int W, const float* x, const float* w
     if (use_tc) {
         const unsigned blocks = (unsigned)((dense + 255) / 256);
         cudaMemset(d_px, 0, packed * 4);
-        nchw_to_p64c4_kernel<<<blocks, 256>>>(d_x, d_px, n, C, H, W);
-        if (residual) { cudaMemset(d_pres, 0, packed * 4); nchw_to_p64c4_kernel<<<blocks, 256>>>(d_res, d_pres, n, C, H, W); }
+        nchw_to_p64c4_kernel<<<blocks, 256>>>(d_x, d_px, n, C, H, W, split ? 1 : 0);
+        if (residual) { cudaMemset(d_pres, 0, packed * 4); nchw_to_p64c4_kernel<<<blocks, 256>>>(d_res, d_pres, n, C, H, W, split ? 1 : 0); }
         good = R.conv_tc(layers[0], d_px, d_pout, residual ? d_pres : nullptr, relu != 0);
-        if (good) p64c4_to_nchw_kernel<<<blocks, 256>>>(d_pout, d_out, n, C, H, W);
+        if (good) p64c4_to_nchw_kernel<<<blocks, 256>>>(d_pout, d_out, n, C, H, W, split ? 1 : 0);
     } else {
         good = R.conv(layers[0], d_x, d_out, residual ? d_res : nullptr, relu != 0, H, W);
     }
@@ -1135,7 +1282,7 @@ int resnet_debug_conv(int n, int C, int H, int W, const float* x, const float* w
 // stored hidden states (pool layout) -> dense NCHW, device to device
 int resnet_states_to_nchw(ResNetDevice* r, const float* states, int count, float* out, cudaStream_t stream) {
     const size_t total = (size_t)count * r->C * r->hh * r->hw;
-    if (r->use_tc) p64c4_to_nchw_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(states, out, count, r->C, r->hh, r->hw);
+    if (r->use_tc) p64c4_to_nchw_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(states, out, count, r->C, r->hh, r->hw, r->split ? 1 : 0);
     else cudaMemcpyAsync(out, states, total * 4, cudaMemcpyDeviceToDevice, stream);
     return cudaGetLastError() == cudaSuccess ? MZ_OK : MZ_ECUDA;
 }

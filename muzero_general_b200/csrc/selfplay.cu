@@ -526,6 +526,11 @@ extern "C" int mz_selfplay_moves(MzHandle* h, int32_t n_moves, double temperatur
     MZ_CUDA(h, cudaEventRecord(sp->e1, h->stream));
     int rc = sp_read_counters(h, stats, 0.0f);
     if (rc) return rc;
+    if (h->res && resnet_take_saturations(h->res, h->stream) > 0) {
+        // the moves above searched with towers outside their accuracy contract (activations beyond the fp16 range are
+        // carried at bf16 precision, not clipped); later calls use the fp32 towers
+        mz_switch_to_strict(h);
+    }
     float ms = 0.0f;
     if (cudaEventElapsedTime(&ms, sp->e0, sp->e1) == cudaSuccess && stats) stats->device_ms = ms;
     return MZ_OK;

@@ -408,7 +408,8 @@ def parse_staged_games(buf: bytes, index):
 
 
 def debug_conv3x3(x, w, bias=None, residual=None, relu=False, tensor_cores=False, device=0):
-    """One conv3x3 (pad 1, stride 1) on the device through mz_debug_conv3x3; numpy NCHW in and out."""
+    """One conv3x3 (pad 1, stride 1) on the device through mz_debug_conv3x3; numpy NCHW in and out.
+    ``tensor_cores``: False / "off" = CUDA cores, "fp16" = tcgen05 with fp16 operands, True / "x3" = tcgen05 split operands."""
     lib = _lib.load_library()
     x = numpy.ascontiguousarray(x, numpy.float32)
     w = numpy.ascontiguousarray(w, numpy.float32)
@@ -416,8 +417,9 @@ def debug_conv3x3(x, w, bias=None, residual=None, relu=False, tensor_cores=False
     out = numpy.empty_like(x)
     b = None if bias is None else numpy.ascontiguousarray(bias, numpy.float32)
     r = None if residual is None else numpy.ascontiguousarray(residual, numpy.float32)
+    mode = {False: 0, True: 2, "off": 0, "fp16": 1, "x3": 2}[tensor_cores]
     rc = lib.mz_debug_conv3x3(device, n, Cc, H, W, x.ctypes.data, w.ctypes.data, None if b is None else b.ctypes.data,
-                              None if r is None else r.ctypes.data, int(relu), int(tensor_cores), out.ctypes.data)
+                              None if r is None else r.ctypes.data, int(relu), mode, out.ctypes.data)
     if rc != 0:
         raise _lib.MzError(rc, lib.mz_last_error(None).decode())
     return out

@@ -118,7 +118,7 @@ def test_cartpole_physics_one_step_at_a_time():
     eng.close()
 
 
-@pytest.mark.parametrize("name,B,N,moves", [("cartpole", 48, 20, 14), ("tictactoe", 40, 16, 12), ("connect4", 24, 12, 10)])
+@pytest.mark.parametrize("name,B,N,moves", [("cartpole", 48, 20, 14), ("tictactoe", 40, 16, 12), ("connect4", 24, 12, 30)])
 def test_device_loop_equals_host_composition_with_injected_draws(name, B, N, moves, monkeypatch):
     """One move at a time with the host's draws injected (root noise, action uniforms): the action the device plays and
     the record it keeps equal [mz_search on the peeked observation] + [the host's visit-count sampling rule]."""

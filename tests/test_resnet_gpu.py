@@ -1,8 +1,15 @@
-"""GPU parity of the residual-network kernels (fp32 CUDA-core path) and the step-wise search.
+"""GPU parity of the residual-network kernels and the step-wise search, in the three tower modes (MZ_TC_MODE):
 
-Tolerances: the CUDA-core conv path accumulates in fp32 with FMAs and folds BatchNorm into the
-weights, the reference uses oneDNN/ATen on the CPU: logits / hidden states agree to
-rtol 2e-4, atol 2e-5 (stated here, checked below)."""
+  "off"   fp32 CUDA-core convs everywhere (reference arithmetic, different summation order)
+  "x3"    DEFAULT for 64-channel board nets: tcgen05 towers on split fp16+bf16 operands, three partial products, fp32
+          accumulation (csrc/conv_x3.cu) - fp32-grade, held to the SAME tolerance as "off"
+  "fp16"  opt-in fast mode: plain fp16 operands (csrc/conv_tc.cu), 3x fewer MMAs; per-quantity bounds below
+
+Tolerances (stated here, checked below): logits and hidden states of "off" / "x3" agree with the reference (oneDNN/ATen
+on the CPU) to rtol 2e-4, atol 2e-5; scalarised values / rewards to 5e-4 absolute (support_to_scalar sums 21 softmax
+terms weighted by up to 10: fp32 logit noise of ~2e-6 is amplified ~100x).  "fp16": logits within 5e-3 absolute,
+hidden states (after the per-channel min-max rescale, which divides by ranges as small as 1e-2) within 1.5e-2 for
+99.9 % of the elements and 1e-1 for all, scalars within 3e-2."""
 import numpy
 import pytest
 
@@ -12,17 +19,43 @@ from muzero_general_b200.netspec import netspec_from_config
 from oracle import mcts as om
 
 pytestmark = pytest.mark.gpu
-# "fp32": CUDA-core convs everywhere (MZ_NO_TC=1).  "tf32" (name kept; now fp16 operands, the same 10-bit
-# mantissa, fp32 accumulation): the tcgen05 towers where the shape allows (Connect4); activations are
-# rounded to 11 significant bits after each of the 13 stacked convs -> looser bound.
-TOLS = {"fp32": dict(rtol=2e-4, atol=2e-5), "tf32": dict(rtol=2e-2, atol=2e-2)}
-VALUE_TOL = {"fp32": 2e-4, "tf32": 3e-2}
+TOL = dict(rtol=2e-4, atol=2e-5)
+SCALAR_ATOL = 5e-4
+VALUE_TOL = {"off": 2e-4, "x3": 2e-4, "fp16": 3e-2}
 
 
-@pytest.fixture(params=["fp32", "tf32"])
+def _uses_tensor_cores(name):
+    return name.startswith("connect4")
+
+
+@pytest.fixture(params=["off", "x3", "fp16"])
 def numerics(request, monkeypatch):
-    monkeypatch.setenv("MZ_NO_TC", "1" if request.param == "fp32" else "0")
+    monkeypatch.delenv("MZ_NO_TC", raising=False)
+    monkeypatch.setenv("MZ_TC_MODE", request.param)
     return request.param
+
+
+def _skip_redundant(name, numerics):
+    if numerics != "off" and not _uses_tensor_cores(name):
+        pytest.skip("no tensor-core towers for this net: identical to mode off")
+
+
+def _close(name, got, want, numerics, kind):
+    """kind: 'logits' | 'hidden' | 'scalar'."""
+    got, want = numpy.asarray(got), numpy.asarray(want)
+    err = numpy.abs(got - want)
+    print(f"{name} [{numerics}] {kind}: max abs err {err.max():.3e}, max rel err {(err / (numpy.abs(want) + 1e-3)).max():.3e}")
+    if numerics == "fp16":
+        if kind == "logits":
+            assert err.max() <= 5e-3, name
+        elif kind == "hidden":
+            assert err.max() <= 1e-1 and numpy.quantile(err, 0.999) <= 1.5e-2, name
+        else:
+            assert err.max() <= 3e-2, name
+    elif kind == "scalar":
+        numpy.testing.assert_allclose(got, want, rtol=2e-4, atol=SCALAR_ATOL, err_msg=name)
+    else:
+        numpy.testing.assert_allclose(got, want, err_msg=name, **TOL)
 
 
 def _engine(cfg, max_games, N):
@@ -37,40 +70,82 @@ def _report(name, got, want):
 
 @pytest.mark.parametrize("name", ["tictactoe", "connect4", "breakout", "connect4_b64"])
 def test_resnet_network_matches_reference(name, numerics, game_configs):
-    TOL = TOLS[numerics]
+    _skip_redundant(name, numerics)
     cfg = game_configs[name.split("_")[0]]
     spec = netspec_from_config(cfg)
     g = golden_npz(f"net_{name}.npz")
     n = len(g["obs"])
     eng = _engine(cfg, n, 4)
     eng.load_weights(weights_for(name, spec))
+    if _uses_tensor_cores(name):
+        assert {"off": "f32 nets", "x3": "f32-grade nets", "fp16": "fp16 operands"}[numerics] in eng.numerics
+    tag = f"{name}"
     r0 = eng.initial_inference(g["obs"])
-    _report(f"{name}/{numerics} init hidden", r0["hidden"], g["init_hidden"].reshape(n, -1))
-    _report(f"{name}/{numerics} init value logits", r0["value_logits"], g["init_value"])
-    numpy.testing.assert_allclose(r0["hidden"], g["init_hidden"].reshape(n, -1), **TOL)
-    numpy.testing.assert_allclose(r0["value_logits"], g["init_value"], **TOL)
-    numpy.testing.assert_allclose(r0["policy_logits"], g["init_policy"], **TOL)
-    numpy.testing.assert_allclose(r0["value"], g["init_value_scalar"], **TOL)
+    _close(tag + " init hidden", r0["hidden"], g["init_hidden"].reshape(n, -1), numerics, "hidden")
+    _close(tag + " init value logits", r0["value_logits"], g["init_value"], numerics, "logits")
+    _close(tag + " init policy logits", r0["policy_logits"], g["init_policy"], numerics, "logits")
+    _close(tag + " init value", r0["value"], g["init_value_scalar"], numerics, "scalar")
     assert numpy.isneginf(r0["reward_logits"]).sum() == n * 20 and (r0["reward"] == 0).all()
     r1 = eng.recurrent_inference(g["init_hidden"].reshape(n, -1), g["action"])
-    _report(f"{name}/{numerics} rec hidden", r1["hidden"], g["rec_hidden"].reshape(n, -1))
-    _report(f"{name}/{numerics} rec policy logits", r1["policy_logits"], g["rec_policy"])
-    _report(f"{name}/{numerics} rec value logits", r1["value_logits"], g["rec_value"])
-    numpy.testing.assert_allclose(r1["hidden"], g["rec_hidden"].reshape(n, -1), **TOL)
-    numpy.testing.assert_allclose(r1["value_logits"], g["rec_value"], **TOL)
-    numpy.testing.assert_allclose(r1["reward_logits"], g["rec_reward"], **TOL)
-    numpy.testing.assert_allclose(r1["policy_logits"], g["rec_policy"], **TOL)
-    numpy.testing.assert_allclose(r1["value"], g["rec_value_scalar"], **TOL)
-    numpy.testing.assert_allclose(r1["reward"], g["rec_reward_scalar"], **TOL)
+    _close(tag + " rec hidden", r1["hidden"], g["rec_hidden"].reshape(n, -1), numerics, "hidden")
+    _close(tag + " rec value logits", r1["value_logits"], g["rec_value"], numerics, "logits")
+    _close(tag + " rec reward logits", r1["reward_logits"], g["rec_reward"], numerics, "logits")
+    _close(tag + " rec policy logits", r1["policy_logits"], g["rec_policy"], numerics, "logits")
+    _close(tag + " rec value", r1["value"], g["rec_value_scalar"], numerics, "scalar")
+    _close(tag + " rec reward", r1["reward"], g["rec_reward_scalar"], numerics, "scalar")
     r2 = eng.recurrent_inference(g["rec_hidden"].reshape(n, -1), (g["action"] + 1) % spec.action_space)
-    numpy.testing.assert_allclose(r2["hidden"], g["rec2_hidden"].reshape(n, -1), **TOL)
-    numpy.testing.assert_allclose(r2["policy_logits"], g["rec2_policy"], **TOL)
+    _close(tag + " rec2 hidden", r2["hidden"], g["rec2_hidden"].reshape(n, -1), numerics, "hidden")
+    _close(tag + " rec2 policy logits", r2["policy_logits"], g["rec2_policy"], numerics, "logits")
+    eng.close()
+
+
+@pytest.mark.parametrize("mode", ["large", "tiny", "overflow"])
+def test_tower_range_guard_on_stress_weights(mode, game_configs, monkeypatch):
+    """Weights whose tower activations reach ~1e4 ("large"), sit at ~1e-5 inside every block ("tiny") or exceed the fp16
+    range ("overflow", ~2e7): the default x3 towers hold the fp32 tolerance on the first two WITHOUT leaving the tensor
+    cores, and on the third the range guard notices, the handle switches to the fp32 CUDA-core towers and the call is
+    redone - the caller sees reference-accurate numbers either way (fixtures: oracle/gen_golden.py::main_round2)."""
+    monkeypatch.delenv("MZ_NO_TC", raising=False)
+    monkeypatch.setenv("MZ_TC_MODE", "x3")
+    name = f"connect4_stress_{mode}"
+    cfg = game_configs["connect4"]
+    spec = netspec_from_config(cfg)
+    g = golden_npz(f"net_{name}.npz")
+    info = golden_json("net_connect4_stress_info.json")[mode]
+    assert {"large": 1e3 < info["max_activation"] < 65504, "tiny": info["min_layer_peak"] < 6e-5,
+            "overflow": info["max_activation"] > 65504}[mode]
+    n = len(g["obs"])
+    eng = _engine(cfg, n, 4)
+    eng.load_weights(weights_for(name, spec))
+    assert "f32-grade nets" in eng.numerics
+    r0 = eng.initial_inference(g["obs"])
+    r1 = eng.recurrent_inference(g["init_hidden"].reshape(n, -1), g["action"])
+    if mode == "overflow":
+        assert "left after an activation exceeded the fp16 range" in eng.numerics
+    else:
+        assert "f32-grade nets" in eng.numerics               # still on the tensor cores
+    scale = lambda a: max(1.0, float(numpy.abs(a).max()))
+    for got, want, what in ((r0["hidden"], g["init_hidden"].reshape(n, -1), "init hidden"),
+                            (r0["value_logits"], g["init_value"], "init value logits"),
+                            (r0["policy_logits"], g["init_policy"], "init policy logits"),
+                            (r1["hidden"], g["rec_hidden"].reshape(n, -1), "rec hidden"),
+                            (r1["value_logits"], g["rec_value"], "rec value logits"),
+                            (r1["reward_logits"], g["rec_reward"], "rec reward logits"),
+                            (r1["policy_logits"], g["rec_policy"], "rec policy logits")):
+        err = numpy.abs(got - want)
+        print(f"{name} {what}: max abs err {err.max():.3e} (scale {scale(want):.3e})")
+        # rtol on the element, atol relative to the tensor's scale (logits of 1e4..1e7 carry fp32 noise of that scale)
+        numpy.testing.assert_allclose(got, want, rtol=2e-4, atol=2e-5 * scale(want), err_msg=f"{name} {what}")
+    # a whole search still works after the switch / on the stressed towers
+    out = eng.search(obs=g["obs"].reshape(n, -1), add_exploration_noise=False)
+    assert (out.visit_counts.sum(1) == 4).all()
     eng.close()
 
 
 @pytest.mark.parametrize("name,N,n", [("tictactoe", 50, 24), ("connect4", 40, 12), ("breakout", 12, 4)])
 def test_resnet_student_forced(name, N, n, numerics, game_configs):
     """Device search with its own residual networks, replayed through the oracle tree."""
+    _skip_redundant(name, numerics)
     cfg = game_configs[name]
     spec = netspec_from_config(cfg)
     A, P = spec.action_space, len(cfg.players)
@@ -107,9 +182,10 @@ def test_resnet_student_forced(name, N, n, numerics, game_configs):
 
 @pytest.mark.parametrize("name", ["tictactoe", "connect4", "breakout", "connect4_n200", "breakout_n50"])
 def test_resnet_closed_loop_matches_reference_counts(name, numerics, game_configs):
-    """Own networks + the reference's noise and first pick.  fp32 path: the reference's visit counts
-    exactly.  tf32 path: counts may move by a visit where two children are nearly tied, so the bound is
-    on the visit distribution (total variation <= 5 %) and on the root value."""
+    """Own networks + the reference's noise and first pick.  "off" and "x3": the reference's visit counts EXACTLY, at the
+    BASELINE simulation counts too (Connect4 N=200, Breakout N=50).  "fp16": counts may move where two children are
+    nearly tied, so the bound is on the visit distribution (total variation <= 5 %) and on the root value."""
+    _skip_redundant(name, numerics)
     cfg = game_configs[name.split("_")[0]]
     spec = netspec_from_config(cfg)
     A = spec.action_space
@@ -122,11 +198,12 @@ def test_resnet_closed_loop_matches_reference_counts(name, numerics, game_config
         out = eng.search(obs=obs, legal_mask=legal, to_play=numpy.array([c["to_play"]], numpy.int32),
                          add_exploration_noise=True, noise=noise, first_index=numpy.array([c["first_index"]], numpy.int32))
         got = [int(out.visit_counts[0, a]) for a in c["root_actions"]]
-        if numerics == "fp32":
-            assert got == c["root_visits"]
+        if numerics != "fp16":
+            assert got == c["root_visits"], (name, numerics)
+            assert out.max_tree_depth[0] == c["max_tree_depth"]
         else:
             tv = 0.5 * sum(abs(x - y) for x, y in zip(got, c["root_visits"])) / c["num_simulations"]
-            print(f"{name}/tf32 visit counts {got} vs {c['root_visits']} (TV {tv:.3f})")
+            print(f"{name}/fp16 visit counts {got} vs {c['root_visits']} (TV {tv:.3f})")
             assert tv <= 0.05 and sum(got) == c["num_simulations"]
         vt = VALUE_TOL[numerics]
         assert abs(out.root_value[0] - c["root_value"]) <= vt * max(1.0, abs(c["root_value"]))
@@ -145,7 +222,7 @@ def test_fused_cuda_core_tower_is_bit_identical_to_per_layer_launches(name, n, g
     actions = rs.randint(0, spec.action_space, size=n)
     outs = []
     for no_fuse in ("1", "0"):
-        monkeypatch.setenv("MZ_NO_TC", "1")
+        monkeypatch.setenv("MZ_TC_MODE", "off")
         monkeypatch.setenv("MZ_NO_FUSE", no_fuse)
         eng = _engine(cfg, n, 6)
         eng.load_weights(weights_for(name, spec))
@@ -178,7 +255,7 @@ def test_resident_tower_is_bit_identical_to_streaming_tower(n, game_configs, mon
     actions = rs.randint(0, spec.action_space, size=n)
     outs = []
     for flag in ("1", "0"):
-        monkeypatch.setenv("MZ_NO_TC", "0")
+        monkeypatch.setenv("MZ_TC_MODE", "fp16")
         monkeypatch.setenv("MZ_TC_NO_RESIDENT", flag)
         eng = _engine(cfg, n, 6)
         eng.load_weights(weights_for("connect4", spec))
@@ -205,7 +282,7 @@ def test_graph_replay_and_dependent_launch_do_not_change_results(name, n, N, gam
     obs = rs.random_sample((n, spec.obs_elems)).astype(numpy.float32)
     results = []
     for no_graph, no_pdl in (("1", "1"), ("0", "1"), ("0", "0")):
-        monkeypatch.setenv("MZ_NO_TC", "0")
+        monkeypatch.setenv("MZ_TC_MODE", "x3")
         monkeypatch.setenv("MZ_NO_GRAPH", no_graph)
         monkeypatch.setenv("MZ_NO_PDL", no_pdl)
         eng = _engine(cfg, n, N)
@@ -221,12 +298,14 @@ def test_graph_replay_and_dependent_launch_do_not_change_results(name, n, N, gam
         assert numpy.array_equal(r.root_value, results[0].root_value)
 
 
-def test_tower_modes_agree_across_batch_sizes(game_configs, monkeypatch):
-    """The tensor-core towers pick their kernel by batch size (resident <= 1184 boards, streaming <= 2368 boards, one
-    launch per conv above).  A batch of 2500 boards evaluated at once must equal the same boards evaluated in chunks."""
+@pytest.mark.parametrize("mode", ["x3", "fp16"])
+def test_tower_modes_agree_across_batch_sizes(mode, game_configs, monkeypatch):
+    """The tensor-core towers pick their kernel / launch count by batch size (fp16: resident <= 1184 boards, streaming
+    <= 2368 boards, one launch per conv above; x3: launches of <= 592 boards).  A batch of 2500 boards evaluated at once
+    must equal the same boards evaluated in chunks, bit for bit."""
     cfg = game_configs["connect4"]
     spec = netspec_from_config(cfg)
-    monkeypatch.setenv("MZ_NO_TC", "0")
+    monkeypatch.setenv("MZ_TC_MODE", mode)
     n = 2500
     rs = numpy.random.RandomState(21)
     obs = rs.random_sample((n, spec.obs_elems)).astype(numpy.float32)

@@ -19,12 +19,12 @@ def _worker(name, seed, **over):
     return sp.SelfPlay({"weights": weights_for(name, spec)}, mod.Game, cfg, seed), cfg, sp
 
 
-@pytest.mark.parametrize("name", ["tictactoe", "connect4"])
-def test_play_game_reproduces_reference_games_on_device(name, monkeypatch):
+@pytest.mark.parametrize("name,mode", [("tictactoe", "off"), ("connect4", "off"), ("connect4", "x3")])
+def test_play_game_reproduces_reference_games_on_device(name, mode, monkeypatch):
     """Whole games through SelfPlay.play_game on the GPU: the reference's action sequences and visit
-    distributions exactly (fp32 CUDA-core networks); root values within 5e-3 (fp32 network differences of
-    ~1e-6 per logit accumulate through 25-50 backed-up simulations)."""
-    monkeypatch.setenv("MZ_NO_TC", "1")
+    distributions exactly (fp32 CUDA-core networks, and the default fp32-grade tensor-core towers); root values within
+    5e-3 (fp32 network differences of ~1e-6 per logit accumulate through 25-50 backed-up simulations)."""
+    monkeypatch.setenv("MZ_TC_MODE", mode)
     for ref in golden_json("play.json")[name]:
         worker, cfg, sp = _worker(name, ref["seed"], num_simulations=ref["num_simulations"])
         gh = worker.play_game(ref["temperature"], cfg.temperature_threshold, False, "self", 0)
@@ -36,11 +36,11 @@ def test_play_game_reproduces_reference_games_on_device(name, monkeypatch):
         worker.model.engine.close()
 
 
-@pytest.mark.parametrize("name,tc", [("tictactoe", "0"), ("connect4", "0"), ("connect4", "1")])
+@pytest.mark.parametrize("name,tc", [("tictactoe", "off"), ("connect4", "off"), ("connect4", "x3"), ("connect4", "fp16")])
 def test_mcts_run_node_graph_on_device(name, tc, monkeypatch):
     """MCTS(config).run returns a Node graph with the reference's shape; hidden states come back in NCHW
     order whatever the internal layout (P64C4 on the tensor-core path)."""
-    monkeypatch.setenv("MZ_NO_TC", "0" if tc == "1" else "1")
+    monkeypatch.setenv("MZ_TC_MODE", tc)
     worker, cfg, sp = _worker(name, 0)
     c = golden_json(f"mcts_{name}.json")[0]
     cfg.num_simulations = c["num_simulations"]
@@ -50,20 +50,20 @@ def test_mcts_run_node_graph_on_device(name, tc, monkeypatch):
     root, info = sp.MCTS(cfg).run(worker.model, obs, c["legal"], c["to_play"], True)
     assert list(root.children.keys()) == c["root_actions"]
     got = [root.children[a].visit_count for a in c["root_actions"]]
-    if tc == "0":
+    if tc != "fp16":
         assert got == c["root_visits"]
     else:      # fp16 tensor-core towers: a visit may move between two nearly tied children
         assert 0.5 * sum(abs(x - y) for x, y in zip(got, c["root_visits"])) / c["num_simulations"] <= 0.05
     assert root.visit_count == c["num_simulations"] == sum(got)
-    tol = 1e-4 if tc == "0" else 3e-2
+    tol = 1e-4 if tc != "fp16" else 3e-2
     assert abs(root.value() - c["root_value"]) <= tol * max(1.0, abs(c["root_value"]))
-    if tc == "0":
+    if tc != "fp16":
         assert info["max_tree_depth"] == c["max_tree_depth"]
     # root hidden state = the reference network's representation of the observation
     spec = netspec_from_config(cfg)
     from oracle.net import OracleNet
     h = OracleNet(spec, weights_for(name, spec)).initial_inference(obs[None].astype(numpy.float32))[3].numpy().ravel()
-    numpy.testing.assert_allclose(root.hidden_state, h, rtol=2e-2 if tc == "1" else 2e-4, atol=2e-2 if tc == "1" else 2e-5)
+    numpy.testing.assert_allclose(root.hidden_state, h, rtol=2e-2 if tc == "fp16" else 2e-4, atol=2e-2 if tc == "fp16" else 2e-5)
     node = root
     for a in c["sims"][-1]["actions"][:-1]:
         node = node.children[a]
