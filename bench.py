@@ -450,6 +450,8 @@ def selfplay_loop(game, B, N, device, rank, world, D):
     moves = max(4, int(math.ceil(MIN_TIMED_SECONDS / max(est, 1e-9))))
     D.barrier()
     steps0, games0 = worker.env_steps, worker.played_games
+    dl = getattr(worker, "_device_loop", None)
+    dev0, calls0 = (dl.device_ms, dl.calls) if dl is not None else (0.0, 0)
     t0 = time.perf_counter()
     finished = worker.play_moves(moves, 1.0)
     import torch
@@ -462,6 +464,8 @@ def selfplay_loop(game, B, N, device, rank, world, D):
     res = {"value": totals[1] / dt_max, "unit": "env-steps/s", "env_steps": int(totals[1]), "seconds": dt_max,
            "moves": moves, "games_finished": int(totals[0]), "mean_finished_length": float(numpy.mean(lengths)) if lengths else None,
            "path": worker.loop_path,
+           "device_seconds": (dl.device_ms - dev0) / 1000.0 if dl is not None else None,
+           "library_calls": (dl.calls - calls0) if dl is not None else None,
            "includes": "search + environment step + root noise + action sampling + GameHistory hand-over, per move"}
     worker.close()
     return res

@@ -250,7 +250,8 @@ typedef struct MzSelfPlayStats {
     int64_t games_finished;       /* games packed into the staging area since mz_selfplay_begin */
     int64_t staged_bytes;         /* bytes waiting in the staging area */
     int32_t staged_games;         /* games waiting in the staging area */
-    int32_t parked_slots;         /* finished games that did not fit into the staging area and wait for a drain */
+    int32_t parked_slots;         /* times a finished game did not fit into the staging area during the last call
+                                     (it waits in its slot and is staged after the next drain) */
     double device_ms;             /* device time of the last mz_selfplay_moves call */
 } MzSelfPlayStats;
 

@@ -3,31 +3,33 @@
 // The reference evaluates its networks in fp32 (models.py:206-231).  A tcgen05 kind::f16 MMA only takes 16-bit
 // operands, so every fp32 operand is split in two 16-bit terms and three of the four partial products are kept:
 //
-//     x = x_h + x_l        x_h = fp16(x) (11 significant bits),  x_l = bf16(x - x_h) (8 more bits, fp32 exponent range)
+//     x = x_h + x_l/2^11   x_h = fp16(x) (11 significant bits),  x_l = fp16((x - x_h) 2^11) (11 more bits; the scale keeps
+//                          the remainder a NORMAL fp16 number wherever x_h is one, so small activations keep 22 bits too)
 //     w = (w_h + w_l)/s    s = a power of two per output channel that brings the row's largest |w| into [1, 2);
 //                          w_h = fp16(w s), w_l = fp16(w s - w_h): 22 significant bits relative to the row maximum
 //     conv = sum x_h w_h + x_h w_l + x_l w_h                    (the dropped x_l w_l term is 2^-22 of |x||w|)
 //
 // Products of 16-bit operands are exact in fp32 and the accumulation in TMEM is fp32, so the result carries ~2^-20
 // relative error per term: the class of an fp32 FMA loop in a different summation order, and two to three orders of
-// magnitude inside the 2e-4 network tolerance of the test-suite.  Activations beyond the fp16 range (|x| > 65504) do
-// not clip - x_h saturates and x_l = bf16(x - 65504) carries the rest at 8 bits - but they leave the accuracy
-// contract, so the epilogue tracks the largest |x| it stores and bumps a counter the host checks after every search
+// magnitude inside the 2e-4 network tolerance of the test-suite.  (kind::f16 takes fp16 or bf16 operands but not one of
+// each - an x_l in bf16 against an fp16 w_h raises an illegal-instruction fault - hence the scaled fp16 remainder.)
+// Activations beyond the fp16 range (|x| > 65504) saturate x_h (and possibly x_l): they leave the accuracy contract,
+// so the epilogue tracks the largest |x| it stores and bumps a counter the host checks after every search
 // (ResNetDevice falls back to the fp32 CUDA-core towers, resnet.cu).
 //
 // Cost: 2 MMAs per 16-channel K-step instead of 1 - the two products that share x_h are ONE M128 x N128 x K16 MMA
 // against [w_h ; w_l] stacked along N (the A tile is fetched from shared memory once), x_l w_h is an M128 x N64 x K16
-// MMA into the first 64 accumulator columns; the epilogue adds column c and column 64 + c.
+// MMA into a third group of 64 accumulator columns; the epilogue forms col[c] + col[64 + c] + col[128 + c] / 2^11.
 //
 // Kernel structure (one CTA per SM, up to two tiles = four boards per CTA, all layers of a tower in one launch):
 //   weights   [9 taps][128 rows: w_h couts | w_l couts][64 cin fp16], 128B-swizzled, 144 KB, ONE slot set refilled
 //             tap by tap for layer l+1 while the last tile of layer l still multiplies
-//   X         the CTA's boards as two swizzled planes (x_h fp16, x_l bf16), 2 x 36 KB, updated IN PLACE: a layer's
+//   X         the CTA's boards as two swizzled fp16 planes (x_h, x_l), 2 x 36 KB, updated IN PLACE: a layer's
 //             output may overwrite its input because (a) the epilogue of a tile starts after the last MMA that reads
 //             the tile's rows, (b) neighbouring tiles only ever read each other's padding rows, which hold zeros before
 //             and after, and (c) the residual stream lives in the epilogue threads' REGISTERS in fp32 (each thread owns
 //             one board position of one tile through the whole tower), so a block input never has to stay in memory
-//   D         TMEM, 128 columns per tile (tile k uses stage k)
+//   D         TMEM, 192 columns per tile (tile k starts at column 256 k)
 // Warp roles as in conv_tc.cu: 0 = bulk-copy producer, 1 = MMA issuer (one elected thread), 2 = TMEM allocator,
 // 3 = output store, 4..7 = epilogue of tile 0, 8..11 = epilogue of tile 1.
 #include <cuda_bf16.h>
@@ -58,7 +60,8 @@ constexpr int kTapBytes = 128 * kRowBytes;                   // 16384
 constexpr int kWBytes = 9 * kTapBytes;                       // 147456
 constexpr int kBoardPlane = kPos * kRowBytes;                // 8192: one plane of one board
 constexpr int kBoardBytes = 2 * kBoardPlane;                 // 16384: x_h plane | x_l plane
-constexpr int kAccCols = 128;
+constexpr int kAccCols = 256;                                // columns reserved per tile (192 used: x_h w_h | x_h w_l | x_l w_h)
+constexpr float kLoScale = 2048.0f, kLoUnscale = 1.0f / 2048.0f;
 constexpr int kThreads = 384;
 
 struct SmemX {
@@ -78,8 +81,8 @@ static_assert(SmemX::hi % 1024 == 0 && SmemX::lo % 1024 == 0, "activation planes
 constexpr uint32_t idesc(uint32_t a_fmt, uint32_t b_fmt, uint32_t n) {
     return (1u << 4) | (a_fmt << 7) | (b_fmt << 10) | ((n >> 3) << 17) | ((128u >> 4) << 24);
 }
-constexpr uint32_t kIdescMain = idesc(0, 0, 128);      // x_h (fp16) x [w_h ; w_l] (fp16)
-constexpr uint32_t kIdescLo = idesc(1, 0, 64);         // x_l (bf16) x w_h (fp16)
+constexpr uint32_t kIdescMain = idesc(0, 0, 128);      // x_h x [w_h ; w_l]
+constexpr uint32_t kIdescLo = idesc(0, 0, 64);         // x_l x w_h
 
 MZ_DEVINL void umma_words(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t idesc_word, uint32_t accumulate) {
     asm volatile(
@@ -93,12 +96,11 @@ MZ_DEVINL void umma_words(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_
         "}" ::"r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(idesc_word), "r"(accumulate), "r"(kDescHi) : "memory");
 }
 
-MZ_DEVINL uint32_t pack_bf16x2(float lo, float hi) {
-    uint32_t r;
-    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
-    return r;
+// x = x_h + x_l / 2^11 from the two packed planes
+MZ_DEVINL float2 join_split(uint32_t h, uint32_t l) {
+    const float2 hf = unpack_f16x2(h), lf = unpack_f16x2(l);
+    return make_float2(fmaf(lf.x, kLoUnscale, hf.x), fmaf(lf.y, kLoUnscale, hf.y));
 }
-MZ_DEVINL float2 unpack_bf16x2(uint32_t v) { return make_float2(__uint_as_float(v << 16), __uint_as_float(v & 0xFFFF0000u)); }
 
 MZ_DEVINL void tmem_ld16(uint32_t taddr, uint32_t* v) {
     asm volatile(
@@ -172,7 +174,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tower_x3_kernel(const __grid
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     if (warp == 2) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
-                     ::"r"(s_base + SmemX::tmem_ptr), "r"(kTiles * kAccCols) : "memory");
+                     ::"r"(s_base + SmemX::tmem_ptr), "r"(kTiles * kAccCols) : "memory");       // 512 columns: one CTA per SM
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     tc_fence_before();
@@ -234,8 +236,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tower_x3_kernel(const __grid
                         for (int ks = 0; ks < kC / 16; ++ks) {
                             const uint32_t off = (uint32_t)(shift * kRow16 + ks * 2);
                             const uint32_t blo = w16 + (uint32_t)(tap * (kTapBytes / 16) + ks * 2);
-                            umma_words(d, ah16 + off, blo, kIdescMain, acc);        // [x_h w_h | x_h w_l]
-                            umma_words(d, al16 + off, blo, kIdescLo, 1u);           // x_l w_h onto the first 64 columns
+                            umma_words(d, ah16 + off, blo, kIdescMain, acc);        // [x_h w_h | x_h w_l] -> columns 0..127
+                            umma_words(d + 128u, al16 + off, blo, kIdescLo, acc);   // x_l w_h -> columns 128..191
                             acc = 1;
                         }
                         if (k == my_tiles - 1) umma_commit(bar_w_empty(tap));
@@ -282,7 +284,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tower_x3_kernel(const __grid
             float res[kC];                                 // residual stream of this board position, fp32, in registers
 #pragma unroll
             for (int c = 0; c < kC; ++c) res[c] = 0.0f;
-            float peak = 0.0f;                             // largest |activation| this thread stored
+            float peak = 0.0f;                             // largest |activation| this thread read or stored
             const bool res_from_input = L >= 2 && a.layer[1].res_buf >= 0;      // the tower starts with a block
             const bool res_external = a.layer[0].res_buf >= 0;                  // single conv with a residual (debug entry)
             if (res_from_input) {
@@ -294,9 +296,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tower_x3_kernel(const __grid
                     const uint32_t hw[4] = {h.x, h.y, h.z, h.w}, lv[4] = {lw.x, lw.y, lw.z, lw.w};
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
-                        const float2 hf = unpack_f16x2(hw[e]), lf = unpack_bf16x2(lv[e]);
-                        res[8 * j + 2 * e] = hf.x + lf.x;
-                        res[8 * j + 2 * e + 1] = hf.y + lf.y;
+                        const float2 xf = join_split(hw[e], lv[e]);
+                        res[8 * j + 2 * e] = xf.x;
+                        res[8 * j + 2 * e + 1] = xf.y;
+                        peak = fmaxf(peak, fmaxf(fabsf(xf.x), fabsf(xf.y)));
                     }
                 }
             } else if (res_external && live) {
@@ -308,9 +311,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tower_x3_kernel(const __grid
                     const uint32_t hw[4] = {h.x, h.y, h.z, h.w}, lv[4] = {lw.x, lw.y, lw.z, lw.w};
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
-                        const float2 hf = unpack_f16x2(hw[e]), lf = unpack_bf16x2(lv[e]);
-                        res[8 * j + 2 * e] = hf.x + lf.x;
-                        res[8 * j + 2 * e + 1] = hf.y + lf.y;
+                        const float2 xf = join_split(hw[e], lv[e]);
+                        res[8 * j + 2 * e] = xf.x;
+                        res[8 * j + 2 * e + 1] = xf.y;
+                        peak = fmaxf(peak, fmaxf(fabsf(xf.x), fabsf(xf.y)));
                     }
                 }
             }
@@ -329,15 +333,16 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tower_x3_kernel(const __grid
                 const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(k * kAccCols);
 #pragma unroll
                 for (int c4 = 0; c4 < 4; ++c4) {
-                    uint32_t vm[16], vc[16];
+                    uint32_t vm[16], vc[16], vl[16];
                     tmem_ld16(taddr + (uint32_t)(16 * c4), vm);
                     tmem_ld16(taddr + (uint32_t)(64 + 16 * c4), vc);
+                    tmem_ld16(taddr + (uint32_t)(128 + 16 * c4), vl);
                     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
                     float r[16];
 #pragma unroll
                     for (int e = 0; e < 16; ++e) {
                         const int c = 16 * c4 + e;
-                        float v = (__uint_as_float(vm[e]) + __uint_as_float(vc[e])) * scale[c] + bias[c];
+                        float v = fmaf(__uint_as_float(vl[e]), kLoUnscale, __uint_as_float(vm[e]) + __uint_as_float(vc[e])) * scale[c] + bias[c];
                         if (add_res) v += res[c];
                         if (atab) v = fmaf(act_scale, atab[c], v);
                         if (ly.relu) v = fmaxf(v, 0.0f);
@@ -354,7 +359,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tower_x3_kernel(const __grid
                             const float v0 = r[8 * j2 + 2 * e], v1 = r[8 * j2 + 2 * e + 1];
                             hw[e] = pack_f16x2(v0, v1);
                             const float2 hf = unpack_f16x2(hw[e]);
-                            lw[e] = pack_bf16x2(v0 - hf.x, v1 - hf.y);
+                            lw[e] = pack_f16x2((v0 - hf.x) * kLoScale, (v1 - hf.y) * kLoScale);
                         }
                         const int j = 2 * c4 + j2;
                         *reinterpret_cast<uint4*>(hi_row + ((j ^ sw) << 4)) = make_uint4(hw[0], hw[1], hw[2], hw[3]);

@@ -35,13 +35,15 @@
 namespace mz {
 
 // Board layouts of the tensor-core towers (conv_tc.cu / conv_x3.cu): kLayoutF16 = one fp16 plane of 4096 halves,
-// kLayoutSplit = two planes, x_h fp16 then x_l bf16 with x ~ x_h + x_l (8192 halves = 4096 float slots per board).
+// kLayoutSplit = two fp16 planes, x_h then x_l with x ~ x_h + x_l / 2^11 (8192 halves = 4096 float slots per board).
 enum { kLayoutDense = 0, kLayoutF16 = 1, kLayoutSplit = 2 };
+constexpr float kSplitLoScale = 2048.0f, kSplitLoUnscale = 1.0f / 2048.0f;
 
-__device__ __forceinline__ void split_f32(float v, __half* hi, __nv_bfloat16* lo) {
-    const __half h = __float2half_rn(fminf(fmaxf(v, -65504.0f), 65504.0f));     // saturate: x_l carries what is left
+__device__ __forceinline__ float sat_f16_range(float v) { return fminf(fmaxf(v, -65504.0f), 65504.0f); }
+__device__ __forceinline__ void split_f32(float v, __half* hi, __half* lo) {
+    const __half h = __float2half_rn(sat_f16_range(v));
     *hi = h;
-    *lo = __float2bfloat16_rn(v - __half2float(h));
+    *lo = __float2half_rn(sat_f16_range((v - __half2float(h)) * kSplitLoScale));
 }
 
 // ------------------------------------------------------------------------------------------
@@ -171,7 +173,7 @@ __global__ void __launch_bounds__(256) conv3x3_kernel(const __grid_constant__ Co
                     const int e = pos * 64 + (((co >> 3) ^ (pos & 7)) << 3) + (co & 7);
                     if (a.out_p64c4 == kLayoutSplit) {
                         __half* base = reinterpret_cast<__half*>(a.out) + (size_t)g * 8192;
-                        split_f32(r, base + e, reinterpret_cast<__nv_bfloat16*>(base + 4096) + e);
+                        split_f32(r, base + e, base + 4096 + e);
                     } else {
                         reinterpret_cast<__half*>(a.out)[(size_t)g * 4096 + e] = __float2half_rn(r);
                     }
@@ -293,13 +295,15 @@ __global__ void __launch_bounds__(kHeadThreads) heads_kernel(const __grid_consta
                 const __half2* h2 = reinterpret_cast<const __half2*>(&v);
                 float2 f0 = __half22float2(h2[0]), f1 = __half22float2(h2[1]);
                 float2 f2 = __half22float2(h2[2]), f3 = __half22float2(h2[3]);
-                if (split) {                                   // x = x_h + x_l (second plane, bf16)
+                if (split) {                                   // x = x_h + x_l / 2^11 (second plane)
                     const uint4 w = x8[512 + pos * 8 + (j ^ (pos & 7))];
-                    const __nv_bfloat162* b2 = reinterpret_cast<const __nv_bfloat162*>(&w);
-                    const float2 g0 = __bfloat1622float2(b2[0]), g1 = __bfloat1622float2(b2[1]);
-                    const float2 g2 = __bfloat1622float2(b2[2]), g3 = __bfloat1622float2(b2[3]);
-                    f0.x += g0.x; f0.y += g0.y; f1.x += g1.x; f1.y += g1.y;
-                    f2.x += g2.x; f2.y += g2.y; f3.x += g3.x; f3.y += g3.y;
+                    const __half2* l2 = reinterpret_cast<const __half2*>(&w);
+                    const float2 g0 = __half22float2(l2[0]), g1 = __half22float2(l2[1]);
+                    const float2 g2 = __half22float2(l2[2]), g3 = __half22float2(l2[3]);
+                    f0.x = fmaf(g0.x, kSplitLoUnscale, f0.x); f0.y = fmaf(g0.y, kSplitLoUnscale, f0.y);
+                    f1.x = fmaf(g1.x, kSplitLoUnscale, f1.x); f1.y = fmaf(g1.y, kSplitLoUnscale, f1.y);
+                    f2.x = fmaf(g2.x, kSplitLoUnscale, f2.x); f2.y = fmaf(g2.y, kSplitLoUnscale, f2.y);
+                    f3.x = fmaf(g3.x, kSplitLoUnscale, f3.x); f3.y = fmaf(g3.y, kSplitLoUnscale, f3.y);
                 }
                 float4* d = reinterpret_cast<float4*>(s_x + p * CP + 8 * j);
                 d[0] = make_float4(f0.x, f0.y, f1.x, f1.y);
@@ -355,12 +359,12 @@ __global__ void __launch_bounds__(kHeadThreads) heads_kernel(const __grid_consta
                     }
                     uint4 packed, packed_lo;                        // 16-bit operands of the tensor-core convs
                     __half2* h2 = reinterpret_cast<__half2*>(&packed);
-                    __nv_bfloat162* b2 = reinterpret_cast<__nv_bfloat162*>(&packed_lo);
+                    __half2* l2 = reinterpret_cast<__half2*>(&packed_lo);
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) {
+                    for (int e = 0; e < 4; ++e) {                   // values are in [0, 1]: no range concerns
                         h2[e] = __floats2half2_rn(v[2 * e], v[2 * e + 1]);
                         const float2 back = __half22float2(h2[e]);
-                        b2[e] = __floats2bfloat162_rn(v[2 * e] - back.x, v[2 * e + 1] - back.y);
+                        l2[e] = __floats2half2_rn((v[2 * e] - back.x) * kSplitLoScale, (v[2 * e + 1] - back.y) * kSplitLoScale);
                     }
                     const bool split = a.p64c4 == kLayoutSplit;
                     const int off8 = pos * 8 + (j ^ (pos & 7));     // in 16-byte units inside the state's first plane
@@ -493,7 +497,7 @@ __global__ void nchw_to_p64c4_kernel(const float* in, float* out, int count, int
     const int e = p64c4_index(c, p, W);
     if (split) {
         __half* base = reinterpret_cast<__half*>(out) + g * 8192;
-        split_f32(in[i], base + e, reinterpret_cast<__nv_bfloat16*>(base + 4096) + e);
+        split_f32(in[i], base + e, base + 4096 + e);
     } else {
         reinterpret_cast<__half*>(out)[g * 4096 + e] = __float2half_rn(in[i]);
     }
@@ -507,7 +511,7 @@ __global__ void p64c4_to_nchw_kernel(const float* in, float* out, int count, int
     const int e = p64c4_index(c, p, W);
     if (split) {
         const __half* base = reinterpret_cast<const __half*>(in) + g * 8192;
-        out[i] = __half2float(base[e]) + __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(base + 4096)[e]);
+        out[i] = fmaf(__half2float(base[4096 + e]), kSplitLoUnscale, __half2float(base[e]));
     } else {
         out[i] = __half2float(reinterpret_cast<const __half*>(in)[g * 4096 + e]);
     }
@@ -1185,7 +1189,7 @@ int resnet_state_elems(const ResNetDevice* r) { return r->state_elems; }
 const char* resnet_numerics(const ResNetDevice* r) {
     if (!r->use_tc) return r->fell_back ? "f32 nets + f64 tree statistics (tensor-core towers left after an activation exceeded the fp16 range)"
                                         : "f32 nets + f64 tree statistics";
-    return r->split ? "f32-grade nets (tensor-core towers on split fp16+bf16 operands, 3 partial products, f32 accumulate; f32 heads) + f64 tree statistics"
+    return r->split ? "f32-grade nets (tensor-core towers on split fp16 operands x = x_h + x_l/2^11, 3 partial products, f32 accumulate; f32 heads) + f64 tree statistics"
                     : "fp16 operands / f32 accumulate (tensor-core towers), f32 heads, f64 tree statistics";
 }
 

@@ -1,8 +1,8 @@
 // Device-resident self-play: the per-move loop of SelfPlay.play_game (self_play.py:110-183) for a whole batch.
 //
 //   move t:   [batched MCTS.run on the device-side observations]            mz_dispatch_search (fc_search.cu / pipeline.cu)
-//             [select_action (self_play.py:222-245) + Game.step + record]   selfplay_act_kernel, one thread per game
-//             [finished games -> pinned host staging, slot restarts]        selfplay_pack_kernel, one warp per slot
+//             [select_action (self_play.py:222-245) + Game.step + record]   selfplay_step_kernel, lane 0 of the slot's warp
+//             [finished games -> pinned host staging, slot restarts]        the same kernel, the whole warp
 //
 // Environments restated for the device (rules and observation planes of the reference):
 //   CartPole   games/cartpole.py:131-174 wraps gym's CartPole-v1 (not vendored): Euler-integrated cart-pole, 20 ms step,
@@ -246,45 +246,40 @@ MZ_DEVINL int sample_action(const SpDev& s, int g, double temperature, double u)
     return pick > last ? last : pick;                          // rounding can leave u >= cdf[-1]
 }
 
-__global__ void selfplay_act_kernel(const SpDev s) {
-    const int g = blockIdx.x * blockDim.x + threadIdx.x;
-    bool active = g < s.B && s.fin[g] == 0;
-    if (active) {
-        const int t = s.move[g];
-        const int64_t gid = s.game_id[g];
-        int action = s.forced_action ? s.forced_action[g] : -1;
-        if (action < 0) {
-            const double T = (s.threshold == 0 || t + 1 < s.threshold) ? s.temperature : 0.0;
-            const double u = s.uniform ? s.uniform[g] : philox_uniform53(s.seed, gid, t, 0u, kTagAction);
-            action = sample_action(s, g, T, u);
-        }
-        float reward;
-        bool done;
-        if (s.env == MZ_ENV_CARTPOLE) {
-            done = cartpole_step(s, g, action);
-            reward = 1.0f;
-        } else {
-            bool won;
-            board_step(s, g, action, &won, &done);
-            reward = won ? (float)s.reward_scale : 0.0f;
-        }
-        // record of move t (store_search_statistics uses the pre-step root, self_play.py:169-175)
-        const size_t r = (size_t)g * s.max_moves + t;
-        s.rec_root[r] = s.root_value[g];
-        for (int k = 0; k < s.A; ++k) s.rec_visits[r * s.A + k] = s.visits[(size_t)g * s.A + k];
-        s.rec_action[r] = action;
-        s.rec_reward[r] = reward;
-        publish(s, g);
-        s.rec_to_play[r] = s.to_play[g];
-        const float* o = s.obs + (size_t)g * s.O;
-        float* ro = s.rec_obs + ((size_t)g * (s.max_moves + 1) + t + 1) * s.O;
-        for (int i = 0; i < s.O; ++i) ro[i] = o[i];
-        s.move[g] = t + 1;
-        s.last_action[g] = action;
-        if (done || t + 1 >= s.max_moves) s.fin[g] = t + 1;
+// select_action + Game.step + record for slot g (one thread)
+MZ_DEVINL void slot_act(const SpDev& s, int g) {
+    const int t = s.move[g];
+    const int64_t gid = s.game_id[g];
+    int action = s.forced_action ? s.forced_action[g] : -1;
+    if (action < 0) {
+        const double T = (s.threshold == 0 || t + 1 < s.threshold) ? s.temperature : 0.0;
+        const double u = s.uniform ? s.uniform[g] : philox_uniform53(s.seed, gid, t, 0u, kTagAction);
+        action = sample_action(s, g, T, u);
     }
-    const unsigned n = __popc(__ballot_sync(0xffffffffu, active));
-    if ((threadIdx.x & 31) == 0 && n) atomicAdd(&s.counters[0], (unsigned long long)n);
+    float reward;
+    bool done;
+    if (s.env == MZ_ENV_CARTPOLE) {
+        done = cartpole_step(s, g, action);
+        reward = 1.0f;
+    } else {
+        bool won;
+        board_step(s, g, action, &won, &done);
+        reward = won ? (float)s.reward_scale : 0.0f;
+    }
+    // record of move t (store_search_statistics uses the pre-step root, self_play.py:169-175)
+    const size_t r = (size_t)g * s.max_moves + t;
+    s.rec_root[r] = s.root_value[g];
+    for (int k = 0; k < s.A; ++k) s.rec_visits[r * s.A + k] = s.visits[(size_t)g * s.A + k];
+    s.rec_action[r] = action;
+    s.rec_reward[r] = reward;
+    publish(s, g);
+    s.rec_to_play[r] = s.to_play[g];
+    const float* o = s.obs + (size_t)g * s.O;
+    float* ro = s.rec_obs + ((size_t)g * (s.max_moves + 1) + t + 1) * s.O;
+    for (int i = 0; i < s.O; ++i) ro[i] = o[i];
+    s.move[g] = t + 1;
+    s.last_action[g] = action;
+    if (done || t + 1 >= s.max_moves) s.fin[g] = t + 1;
 }
 
 __host__ __device__ inline unsigned long long staged_block_bytes(int T, int A, int O) {
@@ -296,13 +291,25 @@ __host__ __device__ inline unsigned long long staged_block_bytes(int T, int A, i
     return (b + 7) & ~7ull;
 }
 
-// one warp per slot: a finished game is copied into the staging area and the slot starts its next game
-__global__ void selfplay_pack_kernel(const SpDev s) {
+// One warp per slot.  act != 0: lane 0 plays the slot's move (sampling, environment step, record) unless the slot is
+// parked; then, whatever `act`, a finished game is copied into the staging area by the whole warp and the slot starts
+// its next game (act == 0 is the drain-only pass that re-packs games parked by an earlier call).
+__global__ void selfplay_step_kernel(const SpDev s, int act) {
     const int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (g >= s.B) return;
-    const int T = s.fin[g];
+    int T = 0;
+    if (lane == 0) {
+        T = s.fin[g];
+        if (act && T == 0) {
+            slot_act(s, g);
+            atomicAdd(&s.counters[0], 1ull);
+            T = s.fin[g];
+        }
+    }
+    T = __shfl_sync(0xffffffffu, T, 0);
     if (T == 0) return;
+    __syncwarp();
     const unsigned long long bytes = staged_block_bytes(T, s.A, s.O);
     unsigned long long off = 0;
     int ok = 0;
@@ -447,6 +454,7 @@ extern "C" int mz_selfplay_begin(MzHandle* h, const MzSelfPlayDesc* d) {
         mz_selfplay_destroy(h);
         return fail(h, MZ_ENOMEM, "mz_selfplay_begin: pinned staging allocation failed");
     }
+    memset(sp->h_counters, 0, 64);
     void* dptr = nullptr;
     if (cudaHostGetDevicePointer(&dptr, sp->staging, 0) != cudaSuccess) { mz_selfplay_destroy(h); return fail(h, MZ_ECUDA, "mz_selfplay_begin: staging is not device-mappable"); }
     s.staging = reinterpret_cast<unsigned char*>(dptr);
@@ -509,18 +517,16 @@ extern "C" int mz_selfplay_moves(MzHandle* h, int32_t n_moves, double temperatur
     call.game_id = s.game_id; call.move_index = s.move;
     call.visit_counts = s.visits; call.root_value = s.root_value;
     MZ_CUDA(h, cudaEventRecord(sp->e0, h->stream));
+    if (sp->h_counters[4]) {                           // games parked by the previous call first, so their slots play again
+        selfplay_step_kernel<<<(B * 32 + 127) / 128, 128, 0, h->stream>>>(s, 0);
+        h->launches += 1;
+    }
+    MZ_CUDA(h, cudaMemsetAsync(s.counters + 4, 0, 8, h->stream));      // [4] = park events of THIS call
     for (int m = 0; m < n_moves; ++m) {
-        MZ_CUDA(h, cudaMemsetAsync(s.counters + 4, 0, 8, h->stream));
-        if (m == 0) {                                  // parked games first, so their slots play this move
-            selfplay_pack_kernel<<<(B * 32 + 127) / 128, 128, 0, h->stream>>>(s);
-            h->launches += 1;
-            MZ_CUDA(h, cudaMemsetAsync(s.counters + 4, 0, 8, h->stream));
-        }
         int rc = mz_dispatch_search(h, call, false, false, 0);
         if (rc) return rc;
-        selfplay_act_kernel<<<(B + 127) / 128, 128, 0, h->stream>>>(s);
-        selfplay_pack_kernel<<<(B * 32 + 127) / 128, 128, 0, h->stream>>>(s);
-        h->launches += 2;
+        selfplay_step_kernel<<<(B * 32 + 127) / 128, 128, 0, h->stream>>>(s, 1);
+        h->launches += 1;
     }
     MZ_CUDA(h, cudaGetLastError());
     MZ_CUDA(h, cudaEventRecord(sp->e1, h->stream));

@@ -612,7 +612,9 @@ class DeviceBatchedSelfPlay:
                                        reward_scale=getattr(vec, "REWARD_SCALE", 1),
                                        first_game_id=worker.first_game_id,
                                        staging_bytes=int(getattr(cfg, "selfplay_staging_bytes", 0) or 0))
-        self.moves_per_call = int(getattr(cfg, "selfplay_moves_per_call", 16) or 16)
+        self.moves_per_call = int(getattr(cfg, "selfplay_moves_per_call", 32) or 32)
+        self.device_ms = 0.0          # device time of all mz_selfplay_moves calls so far
+        self.calls = 0
 
     def moves(self, n_moves, temperature, **inject):
         """``n_moves`` lockstep moves -> ``PackedGames`` (a lazy sequence of the games that finished).  The moves run
@@ -623,7 +625,9 @@ class DeviceBatchedSelfPlay:
         left = int(n_moves)
         while left > 0:
             k = 1 if inject else min(left, self.moves_per_call)
-            self.loop.moves(k, temperature, **inject)
+            st = self.loop.moves(k, temperature, **inject)
+            self.device_ms += st.device_ms
+            self.calls += 1
             out.add(*self.loop.drain())
             left -= k
         return out

@@ -2,7 +2,7 @@
 
 Tolerances stated here: the CUDA-core path accumulates in fp32 (rtol 1e-4); the tcgen05 "fp16" mode multiplies
 fp16 operands (10-bit mantissa, like tf32) with fp32 accumulation and stores fp16:
-|err| <= 2e-3 * (|w| . |x|) + 1e-3 * |out| per output; the tcgen05 "x3" mode (split fp16+bf16 operands, three partial
+|err| <= 2e-3 * (|w| . |x|) + 1e-3 * |out| per output; the tcgen05 "x3" mode (split fp16 operands (x = x_h + x_l/2^11), three partial
 products, csrc/conv_x3.cu) is fp32-grade: |err| <= 4e-6 * (|w| . |x|) + 2e-6 * |out| + 1e-6 - two orders of magnitude
 inside the CUDA-core path's own tolerance."""
 import numpy
