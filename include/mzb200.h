@@ -220,7 +220,7 @@ const char* mz_numerics(const MzHandle* h);
  * max_games environments whose state lives on the GPU.  One move = [batched MCTS.run on the device-side observations]
  * -> [visit-count sampling, self_play.py:222-245] -> [environment step] -> [one struct-of-arrays record per game].
  * A finished game (done, or max_moves reached, self_play.py:129-131) is packed into a pinned host staging area by the
- * kernel that detects it and its slot starts a new game with a fresh global id (old id + max_games); the host reads
+ * kernel that detects it and its slot starts a new game with a fresh global id (old id + game_id_stride); the host reads
  * finished games only.  Root noise, the first simulation's tie and the action sample come from Philox4x32-10 streams
  * keyed (seed, game id, move), so a game's history does not depend on the batch or on the number of ranks.
  * Requires config.stacked_observations == 0 (the observation is the environment's own). */
@@ -232,7 +232,8 @@ typedef struct MzSelfPlayDesc {
     int32_t max_moves;            /* config.max_moves */
     int32_t temperature_threshold;/* config.temperature_threshold, 0 = None (self_play.py:153-156) */
     int32_t reward_scale;         /* board games: reward of the winning move (tictactoe.py:144: 20, connect4.py:144: 10) */
-    int64_t first_game_id;        /* slot g plays the global games first_game_id + g + k * max_games, k = 0, 1, ... */
+    int64_t first_game_id;        /* slot g plays the global games first_game_id + g + k * game_id_stride, k = 0, 1, ... */
+    int64_t game_id_stride;       /* 0 = max_games; world_size * max_games keeps ids unique across ranks */
     uint64_t staging_bytes;       /* capacity of the finished-game staging area, 0 = library default */
 } MzSelfPlayDesc;
 

@@ -87,7 +87,8 @@ class MzInferenceOut(C.Structure):
 
 class MzSelfPlayDesc(C.Structure):
     _fields_ = [("env", C.c_int32), ("max_moves", C.c_int32), ("temperature_threshold", C.c_int32),
-                ("reward_scale", C.c_int32), ("first_game_id", C.c_int64), ("staging_bytes", C.c_uint64)]
+                ("reward_scale", C.c_int32), ("first_game_id", C.c_int64), ("game_id_stride", C.c_int64),
+                ("staging_bytes", C.c_uint64)]
 
 
 class MzSelfPlayInject(C.Structure):

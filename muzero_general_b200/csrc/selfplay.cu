@@ -31,6 +31,7 @@ constexpr int kMaxCells = 48;              // board cells per slot (Connect4: 42
 struct SpDev {
     int env, B, A, O, H, W, K, max_moves, threshold, reward_scale;
     uint64_t seed;
+    int64_t id_stride;         // a slot's next game id = current + id_stride
     // environment state
     double* cart;              // [B][4]
     int* cart_steps;           // [B]
@@ -364,7 +365,7 @@ __global__ void selfplay_step_kernel(const SpDev s, int act) {
         for (int i = lane; i < (T + 1) * s.O; i += 32) f[i] = src[i];
     }
     __syncwarp();
-    if (lane == 0) start_game(s, g, s.game_id[g] + s.B);
+    if (lane == 0) start_game(s, g, s.game_id[g] + s.id_stride);
 }
 
 }  // namespace mz
@@ -430,6 +431,7 @@ extern "C" int mz_selfplay_begin(MzHandle* h, const MzSelfPlayDesc* d) {
     SpDev& s = sp->dev;
     s.env = d->env; s.B = B; s.A = A; s.O = O; s.H = H; s.W = W; s.K = K; s.max_moves = d->max_moves;
     s.threshold = d->temperature_threshold; s.reward_scale = d->reward_scale; s.seed = h->search.seed;
+    s.id_stride = d->game_id_stride > 0 ? d->game_id_stride : B;
     const size_t T = (size_t)d->max_moves;
     bool ok = sp_alloc(sp, &s.cart, (size_t)B * 4) && sp_alloc(sp, &s.cart_steps, B) && sp_alloc(sp, &s.board, (size_t)B * kMaxCells) &&
               sp_alloc(sp, &s.player, B) && sp_alloc(sp, &s.obs, (size_t)B * O) && sp_alloc(sp, &s.legal, (size_t)B * A) &&

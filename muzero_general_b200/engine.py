@@ -329,7 +329,7 @@ class DeviceSelfPlayLoop:
     ENVS = {"cartpole": _lib.MZ_ENV_CARTPOLE, "tictactoe": _lib.MZ_ENV_TICTACTOE, "connect4": _lib.MZ_ENV_CONNECT4}
 
     def __init__(self, engine: SearchEngine, env: str, max_moves: int, temperature_threshold=None, reward_scale: int = 1,
-                 first_game_id: int = 0, staging_bytes: int = 0):
+                 first_game_id: int = 0, staging_bytes: int = 0, game_id_stride: int = 0):
         if env not in self.ENVS:
             raise NotImplementedError(f"no device-resident environment for {env!r}")
         self.engine = engine
@@ -339,6 +339,7 @@ class DeviceSelfPlayLoop:
         d.temperature_threshold = int(temperature_threshold or 0)
         d.reward_scale = int(reward_scale)
         d.first_game_id = int(first_game_id)
+        d.game_id_stride = int(game_id_stride)
         d.staging_bytes = int(staging_bytes)
         engine._check(engine.lib.mz_selfplay_begin(engine._h, C.byref(d)))
         self.stats = _lib.MzSelfPlayStats()

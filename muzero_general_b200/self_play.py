@@ -315,9 +315,11 @@ def register_as_reference_module():
 class SelfPlay:
     """Plays games and saves them to the replay buffer (self_play.py:11-245)."""
 
-    def __init__(self, initial_checkpoint, Game, config, seed, device=0, first_game_id=0):
+    def __init__(self, initial_checkpoint, Game, config, seed, device=0, first_game_id=0, game_id_stride=None):
         self.config = config
         self.first_game_id = int(first_game_id)      # rank * num_parallel_games in a multi-GPU job
+        # a slot's next game takes (current id + stride): world_size * num_parallel_games keeps ids unique over ranks
+        self.game_id_stride = int(game_id_stride or getattr(config, "num_parallel_games", 1) or 1)
         self.Game = Game
         self.seed = seed
         self.num_parallel_games = int(getattr(config, "num_parallel_games", 1) or 1)
@@ -610,7 +612,7 @@ class DeviceBatchedSelfPlay:
         self.loop = DeviceSelfPlayLoop(worker.model.engine, Game.DEVICE_ENV, cfg.max_moves,
                                        temperature_threshold=temperature_threshold,
                                        reward_scale=getattr(vec, "REWARD_SCALE", 1),
-                                       first_game_id=worker.first_game_id,
+                                       first_game_id=worker.first_game_id, game_id_stride=worker.game_id_stride,
                                        staging_bytes=int(getattr(cfg, "selfplay_staging_bytes", 0) or 0))
         self.moves_per_call = int(getattr(cfg, "selfplay_moves_per_call", 32) or 32)
         self.device_ms = 0.0          # device time of all mz_selfplay_moves calls so far
@@ -809,7 +811,7 @@ class BatchedSelfPlay:
                 self.first_to_play[g] = tp[g]
                 start[g] = self.t_abs
                 moves[g] = 0
-                self.game_ids[g] += B           # a fresh global game id for the slot's next game
+                self.game_ids[g] += w.game_id_stride       # a fresh global game id for the slot's next game
                 if self.numpy_mode:
                     self.streams[g] = numpy.random.RandomState(self.w.seed + int(self.game_ids[g]))
         self.obs = obs

@@ -65,6 +65,15 @@ class FakeSearchEngine:
             self._last.append(res)
         return out
 
+    def initial_inference(self, obs):
+        from oracle.net import support_to_scalar
+        obs = numpy.asarray(obs, dtype=numpy.float32)
+        shape = (obs.shape[0], self.spec.in_channels) + tuple(self.spec.obs_shape[1:])
+        v, r, p, h = self.net.initial_inference(obs.reshape(shape))
+        return dict(value_logits=v.numpy(), reward_logits=r.numpy(), policy_logits=p.numpy(),
+                    hidden=h.numpy().reshape(obs.shape[0], -1), value=support_to_scalar(v, self.spec.support_size).numpy()[:, 0],
+                    reward=support_to_scalar(r, self.spec.support_size).numpy()[:, 0])
+
     def export_tree(self, game, with_hidden=False):
         """Oracle tree -> the SoA layout of mz_export_tree (expansion e owns slots [e*A, e*A+A))."""
         res, A, N = self._last[game], self.A, self.N

@@ -260,3 +260,34 @@ def test_selfplay_api_on_the_device_loop(name, monkeypatch):
     buf = Buffer()
     worker.continuous_self_play(Storage(), buf)
     assert buf.games and all(len(g.child_visits) == len(g.action_history) - 1 for g in buf.games)
+
+
+def test_multi_rank_entry_point_is_world_size_invariant(tmp_path):
+    """python -m muzero_general_b200.parallel: 32 CartPole games on one rank and 2 x 16 games on two ranks (torchrun;
+    the ranks share the GPU and talk over gloo when the box has a single one, NCCL otherwise) finish the SAME games -
+    every global game id both runs completed has the same content hash; counters add up over the ranks."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    common = ["--game", "cartpole", "--games", "32", "--reports", "3", "--moves-per-report", "12", "--simulations", "10"]
+    env = dict(os.environ, PYTHONPATH=root)
+    one = tmp_path / "one"
+    subprocess.run([sys.executable, "-m", "muzero_general_b200.parallel", *common, "--dump-histories", str(one)],
+                   check=True, cwd=root, env=env, timeout=600)
+    two = tmp_path / "two"
+    subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+                    "127.0.0.1", "--master-port", "29731", "-m", "muzero_general_b200.parallel", *common,
+                    "--dump-histories", str(two)], check=True, cwd=root, env=env, timeout=600)
+    a = json.load(open(one / "rank0.json"))
+    b0, b1 = json.load(open(two / "rank0.json")), json.load(open(two / "rank1.json"))
+    assert a["summary"]["num_played_steps"] == 32 * 36 == b0["summary"]["num_played_steps"]
+    assert b0["summary"]["world"] == 2 and len(b0["lines"][0]["per_rank"]) == 2
+    merged = dict(b0["digests"], **b1["digests"])
+    assert not set(b0["digests"]) & set(b1["digests"])
+    # first games of every slot carry the ids 0..31 in both runs
+    first = [str(g) for g in range(32) if str(g) in a["digests"] and str(g) in merged]
+    assert len(first) >= 16
+    for g in first:
+        assert a["digests"][g] == merged[g], g

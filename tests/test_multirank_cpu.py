@@ -80,3 +80,36 @@ def test_two_ranks_shard_games_and_exchange_counters(tmp_path):
     for k in range(world):
         for hist, rv in zip(r[k]["histories"], r[k]["root_values"]):
             assert tuple(hist) in played and played[tuple(hist)] == rv
+
+
+def _bcast_main(rank, world, port, out_dir):
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path[:0] = [root, os.path.join(root, "tests")]
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from muzero_general_b200 import parallel
+    from muzero_general_b200.games import load_game_module
+    from muzero_general_b200.netspec import netspec_from_config, synthetic_weights, weights_spec
+    spec = netspec_from_config(load_game_module("tictactoe").MuZeroConfig())
+    mine = synthetic_weights(spec, 3) if rank == 0 else None          # only the "trainer" rank has the weights
+    got = parallel.broadcast_weights(dist, mine, weights_spec(spec))
+    torch.save({k: torch.from_numpy(numpy.asarray(v)) for k, v in got.items()}, os.path.join(out_dir, f"w{rank}.pt"))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_weight_broadcast_on_refresh(tmp_path):
+    """Rank 0's state_dict reaches every rank bit for bit as one flat blob (the replacement for self_play.py:37)."""
+    world, port = 2, _free_port()
+    mp.spawn(_bcast_main, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    from muzero_general_b200.games import load_game_module
+    from muzero_general_b200.netspec import netspec_from_config, synthetic_weights
+    want = synthetic_weights(netspec_from_config(load_game_module("tictactoe").MuZeroConfig()), 3)
+    for k in range(world):
+        got = torch.load(tmp_path / f"w{k}.pt")
+        assert list(got) == list(want)
+        for key, v in want.items():
+            if not key.endswith("num_batches_tracked"):
+                assert numpy.array_equal(got[key].numpy(), v), key

@@ -5,9 +5,10 @@
           accumulation (csrc/conv_x3.cu) - fp32-grade, held to the SAME tolerance as "off"
   "fp16"  opt-in fast mode: plain fp16 operands (csrc/conv_tc.cu), 3x fewer MMAs; per-quantity bounds below
 
-Tolerances (stated here, checked below): logits and hidden states of "off" / "x3" agree with the reference (oneDNN/ATen
-on the CPU) to rtol 2e-4, atol 2e-5; scalarised values / rewards to 5e-4 absolute (support_to_scalar sums 21 softmax
-terms weighted by up to 10: fp32 logit noise of ~2e-6 is amplified ~100x).  "fp16": logits within 5e-3 absolute,
+Tolerances (stated here, checked below): logits of "off" / "x3" agree with the reference (oneDNN/ATen on the CPU) to
+rtol 2e-4, atol 2e-5; hidden states to rtol 2e-4, atol 5e-5 (the per-channel min-max rescale divides the tower output by
+channel ranges down to ~0.05, amplifying its ~2e-6 fp32 noise); scalarised values / rewards to 5e-4 absolute
+(support_to_scalar sums 21 softmax terms weighted by up to 10: fp32 logit noise of ~2e-6 is amplified ~100x).  "fp16": logits within 5e-3 absolute,
 hidden states (after the per-channel min-max rescale, which divides by ranges as small as 1e-2) within 1.5e-2 for
 99.9 % of the elements and 1e-1 for all, scalars within 3e-2."""
 import numpy
@@ -54,6 +55,8 @@ def _close(name, got, want, numerics, kind):
             assert err.max() <= 3e-2, name
     elif kind == "scalar":
         numpy.testing.assert_allclose(got, want, rtol=2e-4, atol=SCALAR_ATOL, err_msg=name)
+    elif kind == "hidden":
+        numpy.testing.assert_allclose(got, want, rtol=2e-4, atol=5e-5, err_msg=name)
     else:
         numpy.testing.assert_allclose(got, want, err_msg=name, **TOL)
 
