@@ -63,7 +63,9 @@ typedef struct MzSearchDesc {
     int32_t max_games;            /* capacity B: games searched in lockstep by one call */
     int32_t num_simulations;      /* config.num_simulations */
     int32_t num_players;          /* len(config.players); 1 or 2 (self_play.py:411-430) */
-    int32_t reserved;
+    int32_t extra_expansions;     /* node-pool room beyond num_simulations + 1 expansions per game, for searches that
+                                     continue from an imported tree (override_root_with, self_play.py:275-277); the
+                                     three tables below then have num_simulations + extra_expansions + 2 entries (per side) */
     double discount;              /* config.discount */
     double pb_c_base, pb_c_init;  /* self_play.py:384-390 */
     double root_dirichlet_alpha;  /* used only when noise is generated on the device */
@@ -141,6 +143,10 @@ typedef struct MzSearchIO {
 
 #define MZ_FLAG_KEEP_TREE 1       /* leave the full tree in the HBM node pool for mz_export_tree */
 #define MZ_FLAG_STEPWISE  2       /* force the generic select/infer/expand+backup pipeline */
+#define MZ_FLAG_CONTINUE  4       /* MCTS.run(..., override_root_with=node), self_play.py:275-277: no root inference; the
+                                     search runs num_simulations more simulations on the tree mz_import_tree put into the
+                                     pool (n_games must be 1; fresh MinMaxStats; the root noise is mixed into the
+                                     imported root priors).  obs is ignored. */
 
 /* Full tree of one game after a search with MZ_FLAG_KEEP_TREE (host pointers). Slot layout:
  * expansion e (0 = root, e = i+1 for simulation i) owns child slots [e*A, e*A+A). */
@@ -154,6 +160,8 @@ typedef struct MzTreeExport {
     float* hidden;                /* [(N+1), hidden_elems] or NULL */
     int32_t root_visit;           /* out */
     double root_value_sum;        /* out */
+    float root_reward;            /* out: reward of the root node (-0.0 for a fresh root; the child's reward after an import) */
+    int32_t reserved;
 } MzTreeExport;
 
 /* Results of a batched network call, all DEVICE or all HOST per `mem`; any pointer may be NULL. */
@@ -187,6 +195,10 @@ int mz_recurrent_inference(MzHandle* h, int32_t n, int32_t mem, const float* hid
 
 /* Node graph access for callers that walk the tree (self_play.py:229-232,499-509; diagnose_model.py:164,222-255) */
 int mz_export_tree(MzHandle* h, int32_t game, MzTreeExport* out);
+/* The inverse: seed game `game`'s tree in the pool from host arrays in the same layout (n_expansions, root_visit,
+ * root_value_sum, root_reward are inputs; hidden = [n_expansions, hidden_elems] dense states, required unless the
+ * search is teacher-forced).  Used by MCTS.run(override_root_with=...) followed by mz_search(MZ_FLAG_CONTINUE). */
+int mz_import_tree(MzHandle* h, int32_t game, const MzTreeExport* tree);
 
 /* sizes derived from the descriptors */
 int64_t mz_hidden_elems(const MzHandle* h);

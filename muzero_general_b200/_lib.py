@@ -12,7 +12,7 @@ LIB_PATH = os.path.join(_HERE, "libmzb200.so")
 MZ_MAX_LAYERS = 8
 MZ_MAX_ACTIONS = 32
 MZ_MEM_HOST, MZ_MEM_DEVICE = 0, 1
-MZ_FLAG_KEEP_TREE, MZ_FLAG_STEPWISE = 1, 2
+MZ_FLAG_KEEP_TREE, MZ_FLAG_STEPWISE, MZ_FLAG_CONTINUE = 1, 2, 4
 MZ_EUNSUPPORTED = -3
 
 _L = C.c_int32 * MZ_MAX_LAYERS
@@ -38,7 +38,7 @@ class MzNetDesc(C.Structure):
 
 class MzSearchDesc(C.Structure):
     _fields_ = [
-        ("max_games", C.c_int32), ("num_simulations", C.c_int32), ("num_players", C.c_int32), ("reserved", C.c_int32),
+        ("max_games", C.c_int32), ("num_simulations", C.c_int32), ("num_players", C.c_int32), ("extra_expansions", C.c_int32),
         ("discount", C.c_double), ("pb_c_base", C.c_double), ("pb_c_init", C.c_double),
         ("root_dirichlet_alpha", C.c_double), ("root_exploration_fraction", C.c_double),
         ("seed", C.c_uint64), ("pb_c_table", C.POINTER(C.c_double)), ("sqrt_table", C.POINTER(C.c_double)),
@@ -77,7 +77,8 @@ class MzSearchIO(C.Structure):
 class MzTreeExport(C.Structure):
     _fields_ = [("n_expansions", C.c_int32), ("child_visit", C.c_void_p), ("child_value_sum", C.c_void_p),
                 ("child_reward", C.c_void_p), ("child_prior", C.c_void_p), ("child_expansion", C.c_void_p),
-                ("hidden", C.c_void_p), ("root_visit", C.c_int32), ("root_value_sum", C.c_double)]
+                ("hidden", C.c_void_p), ("root_visit", C.c_int32), ("root_value_sum", C.c_double),
+                ("root_reward", C.c_float), ("reserved", C.c_int32)]
 
 
 class MzInferenceOut(C.Structure):
@@ -119,6 +120,7 @@ SYMBOLS = [
     ("mz_initial_inference", C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.POINTER(MzInferenceOut)]),
     ("mz_recurrent_inference", C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.POINTER(MzInferenceOut)]),
     ("mz_export_tree", C.c_int, [C.c_void_p, C.c_int32, C.POINTER(MzTreeExport)]),
+    ("mz_import_tree", C.c_int, [C.c_void_p, C.c_int32, C.POINTER(MzTreeExport)]),
     ("mz_hidden_elems", C.c_int64, [C.c_void_p]),
     ("mz_obs_elems", C.c_int64, [C.c_void_p]),
     ("mz_launch_count", C.c_int64, [C.c_void_p]),

@@ -95,7 +95,10 @@ extern "C" int mz_create(const MzNetDesc* net, const MzSearchDesc* search, int d
     MZ_CREATE_CUDA(cudaEventCreate(&h->ev0));
     MZ_CREATE_CUDA(cudaEventCreate(&h->ev1));
 
-    const int B = search->max_games, N = search->num_simulations, A = net->action_space;
+    if (search->extra_expansions < 0) { fail(nullptr, MZ_EINVAL, "mz_create: extra_expansions < 0"); mz_destroy(h); return MZ_EINVAL; }
+    // N below is the LAYOUT size of the pool and tables (room for num_simulations + 1 + extra_expansions expansions)
+    const int B = search->max_games, N = search->num_simulations + search->extra_expansions, A = net->action_space;
+    h->pool_n = N;
     // ---- UCB tables (self_play.py:385-390)
     std::vector<double> pbc(N + 2), sq(N + 2);
     for (int n = 0; n < N + 2; ++n) {
@@ -381,6 +384,10 @@ void mz_switch_to_strict(MzHandle* h) {
 int mz_dispatch_search(MzHandle* h, const SearchCall& call, bool teacher, bool trace, int flags) {
     const int n = call.n, N = h->search.num_simulations, A = h->net.action_space;
     int rc;
+    if (h->search.extra_expansions > 0) flags |= MZ_FLAG_STEPWISE;     // the fused FC kernel lays its tree out for N + 1 expansions
+    SearchCall cont = call;
+    cont.continue_from = (flags & MZ_FLAG_CONTINUE) ? h->imported_expansions : 0;
+    const SearchCall& call_ = cont;
     const bool fused = (h->net.kind == MZ_NET_FC || teacher) && !(flags & MZ_FLAG_STEPWISE);
     if (fused) {
         FcSearchArgs a{};
@@ -400,7 +407,7 @@ int mz_dispatch_search(MzHandle* h, const SearchCall& call, bool teacher, bool t
         if (e == cudaErrorInvalidConfiguration) {
             // the tree does not fit in shared memory next to the weights: use the HBM node pool
             (void)cudaGetLastError();
-            rc = run_stepwise_search(h->net, h->search, h->pool, h->d_pbc, h->d_sqrt, h->d_ucb, h->fc, h->d_fc_blob, h->res, call,
+            rc = run_stepwise_search(h->net, h->search, h->pool_n, h->pool, h->d_pbc, h->d_sqrt, h->d_ucb, h->fc, h->d_fc_blob, h->res, call_,
                                      h->fc_group, h->sm_count, h->stream, &h->launches, &h->err);
             if (rc) return rc;
         } else if (e != cudaSuccess) {
@@ -419,9 +426,9 @@ int mz_dispatch_search(MzHandle* h, const SearchCall& call, bool teacher, bool t
                               call.move_index, call.visit_counts, call.root_value, call.root_predicted_value,
                               call.max_tree_depth, call.tie_count, call.root_priors, call.value_range};
         for (const void* q : ptrs) mix((uint64_t)(uintptr_t)q);
-        mix((uint64_t)n); mix((uint64_t)call.add_noise); mix((uint64_t)call.keep_tree);
+        mix((uint64_t)n); mix((uint64_t)call.add_noise); mix((uint64_t)call.keep_tree); mix((uint64_t)call_.continue_from);
         auto eager = [&]() {
-            return run_stepwise_search(h->net, h->search, h->pool, h->d_pbc, h->d_sqrt, h->d_ucb, h->fc, h->d_fc_blob, h->res, call,
+            return run_stepwise_search(h->net, h->search, h->pool_n, h->pool, h->d_pbc, h->d_sqrt, h->d_ucb, h->fc, h->d_fc_blob, h->res, call_,
                                        h->fc_group, h->sm_count, h->stream, &h->launches, &h->err);
         };
         if (graphable && h->graph_exec && h->graph_key == key) {
@@ -462,7 +469,14 @@ extern "C" int mz_search(MzHandle* h, const MzSearchIO* io) {
     if (n < 1 || n > h->search.max_games) return fail(h, MZ_EINVAL, "mz_search: n_games out of range");
     const bool teacher = io->teacher != nullptr;
     if (!teacher && !h->weights_loaded) return fail(h, MZ_ESTATE, "mz_search: weights not loaded");
-    if (!teacher && !io->obs) return fail(h, MZ_EINVAL, "mz_search: obs is null");
+    const bool cont = (io->flags & MZ_FLAG_CONTINUE) != 0;
+    if (!teacher && !io->obs && !cont) return fail(h, MZ_EINVAL, "mz_search: obs is null");
+    if (cont) {
+        if (n != 1) return fail(h, MZ_EINVAL, "mz_search: MZ_FLAG_CONTINUE takes one game");
+        if (h->imported_expansions < 1) return fail(h, MZ_ESTATE, "mz_search: MZ_FLAG_CONTINUE without mz_import_tree");
+        if (h->imported_expansions + h->search.num_simulations > h->pool_n + 1)
+            return fail(h, MZ_EINVAL, "mz_search: the imported tree plus num_simulations exceeds the pool (raise extra_expansions)");
+    }
     MZ_CUDA(h, cudaSetDevice(h->device));
 
     SearchCall call{};
@@ -472,7 +486,7 @@ extern "C" int mz_search(MzHandle* h, const MzSearchIO* io) {
     const bool host = io->mem == MZ_MEM_HOST;
     if (host) {
         Arena ai, ao;
-        call.obs = teacher ? nullptr : stage_in(h, ai, io->obs, (size_t)n * h->obs_elems);
+        call.obs = (teacher || cont) ? nullptr : stage_in(h, ai, io->obs, (size_t)n * h->obs_elems);
         call.legal_mask = stage_in(h, ai, io->legal_mask, (size_t)n * A);
         call.to_play = stage_in(h, ai, io->to_play, n);
         call.noise = stage_in(h, ai, io->add_exploration_noise ? io->noise : nullptr, (size_t)n * A);
@@ -622,7 +636,7 @@ extern "C" int mz_export_tree(MzHandle* h, int32_t game, MzTreeExport* out) {
     if (game < 0 || game >= h->search.max_games) return fail(h, MZ_EINVAL, "mz_export_tree: game out of range");
     MZ_CUDA(h, cudaSetDevice(h->device));
     MZ_CUDA(h, cudaStreamSynchronize(h->stream));
-    const int N = h->search.num_simulations, A = h->net.action_space;
+    const int N = h->pool_n, A = h->net.action_space;
     const size_t S = (size_t)(N + 1) * A, base = (size_t)game * S;
     const NodePool& p = h->pool;
     int nexp = 0;
@@ -654,6 +668,68 @@ extern "C" int mz_export_tree(MzHandle* h, int32_t game, MzTreeExport* out) {
     }
     MZ_CUDA(h, cudaMemcpy(&out->root_visit, p.root_visit + game, 4, cudaMemcpyDeviceToHost));
     MZ_CUDA(h, cudaMemcpy(&out->root_value_sum, p.root_vsum + game, 8, cudaMemcpyDeviceToHost));
+    MZ_CUDA(h, cudaMemcpy(&out->root_reward, p.root_reward + game, 4, cudaMemcpyDeviceToHost));
+    return MZ_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// tree import (override_root_with, self_play.py:275-277)
+// ------------------------------------------------------------------------------------------
+extern "C" int mz_import_tree(MzHandle* h, int32_t game, const MzTreeExport* t) {
+    if (!h || !t) return fail(h, MZ_EINVAL, "mz_import_tree: null argument");
+    if (game < 0 || game >= h->search.max_games) return fail(h, MZ_EINVAL, "mz_import_tree: game out of range");
+    const int N = h->pool_n, A = h->net.action_space, K = t->n_expansions;
+    if (K < 1 || K > N + 1) return fail(h, MZ_EINVAL, "mz_import_tree: n_expansions does not fit the pool (raise extra_expansions)");
+    if (!t->child_visit || !t->child_value_sum || !t->child_reward || !t->child_prior || !t->child_expansion)
+        return fail(h, MZ_EINVAL, "mz_import_tree: incomplete tree");
+    MZ_CUDA(h, cudaSetDevice(h->device));
+    MZ_CUDA(h, cudaStreamSynchronize(h->stream));
+    const size_t S = (size_t)(N + 1) * A, base = (size_t)game * S, used = (size_t)K * A;
+    const NodePool& p = h->pool;
+    std::vector<float> prior(used);
+    std::vector<double> mval(used, 0.0), rp(A);
+    const double discount = h->search.discount;
+    const bool two = h->search.num_players == 2;
+    for (size_t i = 0; i < used; ++i) {
+        prior[i] = (float)t->child_prior[i];
+        if (t->child_visit[i] > 0) {
+            // the value term selection reads back: reward + discount * (+/-)(value_sum / visits)   (tree.cuh, tree_backup)
+            const double q = t->child_value_sum[i] / (double)t->child_visit[i];
+            mval[i] = (double)t->child_reward[i] + discount * (two ? -q : q);
+        }
+    }
+    for (int a = 0; a < A; ++a) rp[a] = t->child_prior[a];
+    MZ_CUDA(h, cudaMemcpy(p.visit + base, t->child_visit, used * 4, cudaMemcpyHostToDevice));
+    MZ_CUDA(h, cudaMemcpy(p.vsum + base, t->child_value_sum, used * 8, cudaMemcpyHostToDevice));
+    MZ_CUDA(h, cudaMemcpy(p.mval + base, mval.data(), used * 8, cudaMemcpyHostToDevice));
+    MZ_CUDA(h, cudaMemcpy(p.reward + base, t->child_reward, used * 4, cudaMemcpyHostToDevice));
+    MZ_CUDA(h, cudaMemcpy(p.prior + base, prior.data(), used * 4, cudaMemcpyHostToDevice));
+    MZ_CUDA(h, cudaMemcpy(p.expansion + base, t->child_expansion, used * 4, cudaMemcpyHostToDevice));
+    MZ_CUDA(h, cudaMemcpy(p.root_prior + (size_t)game * A, rp.data(), A * 8, cudaMemcpyHostToDevice));
+    const unsigned legal = A >= 32 ? 0xffffffffu : ((1u << A) - 1u);       // children of a non-root node: the whole action space
+    const double range[2] = {INFINITY, -INFINITY};
+    const int zero = 0;
+    MZ_CUDA(h, cudaMemcpy(p.legal + game, &legal, 4, cudaMemcpyHostToDevice));
+    MZ_CUDA(h, cudaMemcpy(p.root_visit + game, &t->root_visit, 4, cudaMemcpyHostToDevice));
+    MZ_CUDA(h, cudaMemcpy(p.root_vsum + game, &t->root_value_sum, 8, cudaMemcpyHostToDevice));
+    MZ_CUDA(h, cudaMemcpy(p.root_reward + game, &t->root_reward, 4, cudaMemcpyHostToDevice));
+    MZ_CUDA(h, cudaMemcpy(p.range + 2 * (size_t)game, range, 16, cudaMemcpyHostToDevice));
+    MZ_CUDA(h, cudaMemcpy(p.n_expanded + game, &K, 4, cudaMemcpyHostToDevice));
+    MZ_CUDA(h, cudaMemcpy(p.ties + game, &zero, 4, cudaMemcpyHostToDevice));
+    MZ_CUDA(h, cudaMemcpy(p.max_depth + game, &zero, 4, cudaMemcpyHostToDevice));
+    if (t->hidden) {
+        float* dst = p.hidden + (size_t)game * (N + 1) * h->pool_state_elems;
+        if (h->net.kind == MZ_NET_RESNET) {
+            void* tmp = named_buffer(h, "x.import", (size_t)K * h->hidden_elems * 4);
+            if (!tmp) return fail(h, MZ_ENOMEM, "mz_import_tree: out of device memory");
+            MZ_CUDA(h, cudaMemcpy(tmp, t->hidden, (size_t)K * h->hidden_elems * 4, cudaMemcpyHostToDevice));
+            if (resnet_states_from_nchw(h->res, (const float*)tmp, K, dst, h->stream)) return fail(h, MZ_ECUDA, "mz_import_tree: layout conversion failed");
+            MZ_CUDA(h, cudaStreamSynchronize(h->stream));
+        } else {
+            MZ_CUDA(h, cudaMemcpy(dst, t->hidden, (size_t)K * h->hidden_elems * 4, cudaMemcpyHostToDevice));
+        }
+    }
+    h->imported_expansions = K;
     return MZ_OK;
 }
 

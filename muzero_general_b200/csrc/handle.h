@@ -53,6 +53,8 @@ struct MzHandle {
     std::vector<void*> debug_allocs;
     std::map<std::string, std::pair<void*, size_t>> named;
     MzSelfPlay* sp = nullptr;          // mz_selfplay_begin
+    int pool_n = 0;                    // layout "N" of the node pool and tables: num_simulations + extra_expansions
+    int imported_expansions = 0;       // expansions of the tree mz_import_tree seeded last (MZ_FLAG_CONTINUE)
     int range_fallbacks = 0;           // times the x3 range guard switched this handle to the fp32 towers (0 or 1)
 };
 

@@ -5,11 +5,13 @@
 
 namespace mz {
 
-int run_stepwise_search(const MzNetDesc& net, const MzSearchDesc& search, const NodePool& pool, const double* d_pbc,
+int run_stepwise_search(const MzNetDesc& net, const MzSearchDesc& search, int pool_n, const NodePool& pool, const double* d_pbc,
                         const double* d_sqrt, const double* d_ucb, const FcNet& fc, const float* d_fc_blob, ResNetDevice* res,
                         const SearchCall& call, int fc_group, int sm_count, cudaStream_t stream, int64_t* launches, std::string* err) {
-    const int n = call.n, N = search.num_simulations, A = net.action_space;
+    // N = simulations of this call; NP = the layout size of the pool / tables (N + extra_expansions)
+    const int n = call.n, N = search.num_simulations, NP = pool_n, A = net.action_space;
     const bool teacher = call.teacher.root_value != nullptr;
+    const int K0 = call.continue_from;                 // expansions already in the pool (MZ_FLAG_CONTINUE), else 0
     auto cuda_fail = [&](const char* what, cudaError_t e) {
         *err = std::string(what) + ": " + cudaGetErrorString(e);
         return MZ_ECUDA;
@@ -27,7 +29,7 @@ int run_stepwise_search(const MzNetDesc& net, const MzSearchDesc& search, const 
     };
 
     TreeStepArgs a{};
-    a.n = n; a.N = N; a.A = A; a.P = search.num_players;
+    a.n = n; a.N = NP; a.A = A; a.P = search.num_players;
     a.discount = search.discount; a.noise_frac = search.root_exploration_fraction; a.noise_alpha = search.root_dirichlet_alpha; a.seed = search.seed;
     a.pbc = d_pbc; a.sqrtn = d_sqrt; a.ucb = d_ucb; a.pool = pool;
     a.legal_mask = call.legal_mask; a.noise = call.noise; a.add_noise = call.add_noise;
@@ -37,20 +39,23 @@ int run_stepwise_search(const MzNetDesc& net, const MzSearchDesc& search, const 
     a.value_range = call.value_range; a.trace = call.trace;
 
     // ---- root
-    if (teacher) {
+    if (K0 > 0) {
+        a.net_value = pool.net_value; a.net_reward = nullptr; a.net_policy = pool.net_policy;     // unused by do_root == 2
+        a.value_stride = 1; a.policy_stride = A; a.policy_is_prior = 0;
+    } else if (teacher) {
         a.net_value = call.teacher.root_value; a.net_reward = call.teacher.root_reward; a.net_policy = call.teacher.root_priors;
         a.value_stride = 1; a.policy_stride = A; a.policy_is_prior = 1;
     } else {
         InferCall c{};
         c.n = n; c.recurrent = 0; c.in = call.obs;
-        c.pool_hidden = pool.hidden; c.pool_stride = N + 1; c.out_slot = 0;
+        c.pool_hidden = pool.hidden; c.pool_stride = NP + 1; c.out_slot = 0;
         c.value = pool.net_value; c.policy_logits = pool.net_policy;
         int rc = infer(c);
         if (rc) return rc;
         a.net_value = pool.net_value; a.net_reward = nullptr; a.net_policy = pool.net_policy;
         a.value_stride = 1; a.policy_stride = A; a.policy_is_prior = 0;
     }
-    a.sim = 0; a.do_root = 1; a.do_update = 0; a.do_select = N > 0; a.do_final = N == 0;
+    a.sim = 0; a.do_root = K0 > 0 ? 2 : 1; a.do_update = 0; a.do_select = N > 0; a.do_final = N == 0;
     kt_begin(KT_TREE, stream);
     cudaError_t e = launch_tree_step(a, stream);
     kt_end(stream);
@@ -66,7 +71,7 @@ int run_stepwise_search(const MzNetDesc& net, const MzSearchDesc& search, const 
         } else {
             InferCall c{};
             c.n = n; c.recurrent = 1; c.action = pool.leaf_action; c.gather_parent = pool.leaf_parent;
-            c.pool_hidden = pool.hidden; c.pool_stride = N + 1; c.out_slot = sim + 1;
+            c.pool_hidden = pool.hidden; c.pool_stride = NP + 1; c.out_slot = (K0 > 0 ? K0 : 1) + sim;
             c.value = pool.net_value; c.reward = pool.net_reward; c.policy_logits = pool.net_policy;
             int rc = infer(c);
             if (rc) return rc;

@@ -28,6 +28,7 @@ struct SearchCall {
     DevTrace trace;
     bool keep_tree;
     size_t out_bytes;
+    int continue_from;             // > 0: MZ_FLAG_CONTINUE, the pool already holds this many expansions of every game
 };
 
 // One batched network call. Plain mode: sample g reads in[g*in_elems...] and writes hidden[g*H...].
@@ -47,7 +48,7 @@ struct InferCall {
 struct TreeStepArgs {
     int n, N, A, P;
     int sim;                       // simulation selected by this launch (do_select); do_update handles sim-1
-    int do_root, do_update, do_select, do_final;
+    int do_root, do_update, do_select, do_final;      // do_root: 1 = expand a fresh root, 2 = adopt the imported tree
     double discount, noise_frac, noise_alpha;
     uint64_t seed;
     const double* pbc;
@@ -87,7 +88,9 @@ int resnet_states_to_nchw(ResNetDevice* r, const float* states, int count, float
 
 cudaError_t launch_fc_inference_pool(const FcNet& net, const float* blob, const InferCall& c, int group, int sm_count, cudaStream_t stream);
 
-int run_stepwise_search(const MzNetDesc& net, const MzSearchDesc& search, const NodePool& pool, const double* d_pbc,
+int resnet_states_from_nchw(ResNetDevice* r, const float* dense, int count, float* states, cudaStream_t stream);
+
+int run_stepwise_search(const MzNetDesc& net, const MzSearchDesc& search, int pool_n, const NodePool& pool, const double* d_pbc,
                         const double* d_sqrt, const double* d_ucb, const FcNet& fc, const float* d_fc_blob, ResNetDevice* res,
                         const SearchCall& call, int fc_group, int sm_count, cudaStream_t stream, int64_t* launches, std::string* err);
 

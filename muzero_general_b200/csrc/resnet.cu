@@ -1291,6 +1291,18 @@ int resnet_states_to_nchw(ResNetDevice* r, const float* states, int count, float
     return cudaGetLastError() == cudaSuccess ? MZ_OK : MZ_ECUDA;
 }
 
+// dense NCHW states -> the pool layout, device to device (mz_import_tree)
+int resnet_states_from_nchw(ResNetDevice* r, const float* dense, int count, float* states, cudaStream_t stream) {
+    const size_t total = (size_t)count * r->C * r->hh * r->hw;
+    if (r->use_tc) {
+        cudaMemsetAsync(states, 0, (size_t)count * r->state_elems * 4, stream);          // padding positions read as zero
+        nchw_to_p64c4_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(dense, states, count, r->C, r->hh, r->hw, r->split ? 1 : 0);
+    } else {
+        cudaMemcpyAsync(states, dense, total * 4, cudaMemcpyDeviceToDevice, stream);
+    }
+    return cudaGetLastError() == cudaSuccess ? MZ_OK : MZ_ECUDA;
+}
+
 int resnet_inference(ResNetDevice* r, const InferCall& c, cudaStream_t stream, int64_t* launches, std::string* err) {
     if (!r->loaded) { *err = "weights not loaded"; return MZ_ESTATE; }
     if (c.n > r->max_batch) { *err = "batch larger than max_games"; return MZ_EINVAL; }

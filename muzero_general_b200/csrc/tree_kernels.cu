@@ -43,7 +43,7 @@ __global__ void __launch_bounds__(128) tree_step_kernel(const __grid_constant__ 
     t.path_reward = p.path_reward + (size_t)g * (N + 2);
     int max_depth = 0;
 
-    if (a.do_root) {
+    if (a.do_root == 1) {
         unsigned legal = 0;
         for (int k = 0; k < A; ++k)
             legal |= (a.legal_mask == nullptr || a.legal_mask[(size_t)g * A + k]) ? (1u << k) : 0u;
@@ -69,6 +69,27 @@ __global__ void __launch_bounds__(128) tree_step_kernel(const __grid_constant__ 
         t.n_expanded = p.n_expanded[g];
         t.ties = p.ties[g];
         max_depth = p.max_depth[g];
+        if (a.do_root == 2) {
+            // override_root_with (self_play.py:275-277, 310-314): the imported node is the root; fresh MinMaxStats; the
+            // exploration noise is mixed into the priors the root's children already have (self_play.py:467-476)
+            t.lo = INFINITY; t.hi = -INFINITY; t.ties = 0; max_depth = 0;
+            if (a.add_noise && lane < A) {
+                double nz;
+                const int64_t gid = a.game_id ? a.game_id[g] : (int64_t)g;
+                const int mv = a.move_index ? a.move_index[g] : 0;
+                if (a.noise) {
+                    nz = a.noise[(size_t)g * A + lane];
+                } else {
+                    const double gm = philox_gamma(a.seed, gid, mv, lane, a.noise_alpha);
+                    double sum = 0.0;
+                    for (int k = 0; k < A; ++k) sum += LaneGroup<G>::bcast(gm, k);     // A <= G lanes hold a draw each
+                    nz = gm / sum;
+                }
+                if (a.trace.noise) a.trace.noise[(size_t)g * A + lane] = nz;
+                t.root_prior[lane] = __dadd_rn(__dmul_rn(t.root_prior[lane], __dsub_rn(1.0, a.noise_frac)), __dmul_rn(nz, a.noise_frac));
+            }
+            LaneGroup<G>::sync();
+        }
     }
 
     if (a.do_update) {

@@ -73,7 +73,7 @@ class SearchOutput:
 
 class SearchEngine:
     def __init__(self, config, max_games: int = 1, device: int = 0, seed: Optional[int] = None,
-                 num_simulations: Optional[int] = None):
+                 num_simulations: Optional[int] = None, extra_expansions: int = 0):
         self.lib = _lib.load_library()
         self.config = config
         self.spec = netspec_from_config(config)
@@ -85,9 +85,12 @@ class SearchEngine:
         self.N = int(config.num_simulations if num_simulations is None else num_simulations)
         self.max_games = int(max_games)
         self.device = int(device)
+        self.extra_expansions = int(extra_expansions)       # pool room for searches continued from an imported tree
+        self.pool_n = self.N + self.extra_expansions
         s = _lib.MzSearchDesc()
         s.max_games = self.max_games
         s.num_simulations = self.N
+        s.extra_expansions = self.extra_expansions
         s.num_players = len(config.players)
         s.discount = float(config.discount)
         s.pb_c_base = float(config.pb_c_base)
@@ -96,7 +99,7 @@ class SearchEngine:
         s.root_exploration_fraction = float(config.root_exploration_fraction)
         s.seed = int(config.seed if seed is None else seed) & 0xFFFFFFFFFFFFFFFF
         # math.log / math.sqrt exactly as the reference evaluates them (self_play.py:385-390)
-        n = self.N + 2
+        n = self.pool_n + 2
         self._pbc = (C.c_double * n)(*[math.log((i + config.pb_c_base + 1) / config.pb_c_base) + config.pb_c_init
                                        for i in range(n)])
         self._sqrt = (C.c_double * n)(*[math.sqrt(i) for i in range(n)])
@@ -204,12 +207,12 @@ class SearchEngine:
     # ------------------------------------------------------------------ search
     def search(self, obs=None, legal_mask=None, to_play=None, add_exploration_noise=False, noise=None,
                first_index=None, game_id=None, move_index=None, teacher=None, trace=False, trace_depth=None,
-               keep_tree=False, stepwise=False, n_games=None) -> SearchOutput:
+               keep_tree=False, stepwise=False, n_games=None, continue_tree=False) -> SearchOutput:
         A, N = self.A, self.N
         keep = []
         if n_games is None:
             src = obs if obs is not None else (teacher["root_value"] if teacher else legal_mask)
-            n_games = int(src.shape[0])
+            n_games = 1 if (src is None and continue_tree) else int(src.shape[0])
         n = n_games
         device_mem = _is_torch(obs)
         io = _lib.MzSearchIO()
@@ -229,7 +232,8 @@ class SearchEngine:
         io.legal_mask = self._ptr(legal_mask, numpy.uint8, keep)
         io.to_play = self._ptr(to_play, numpy.int32, keep)
         io.add_exploration_noise = int(bool(add_exploration_noise))
-        io.flags = (_lib.MZ_FLAG_KEEP_TREE if keep_tree else 0) | (_lib.MZ_FLAG_STEPWISE if stepwise else 0)
+        io.flags = ((_lib.MZ_FLAG_KEEP_TREE if keep_tree else 0) | (_lib.MZ_FLAG_STEPWISE if stepwise else 0)
+                    | (_lib.MZ_FLAG_CONTINUE if continue_tree else 0))
         io.noise = self._ptr(noise, numpy.float64, keep)
         io.first_index = self._ptr(first_index, numpy.int32, keep)
         io.game_id = self._ptr(game_id, numpy.int64, keep)
@@ -305,7 +309,7 @@ class SearchEngine:
 
     # ------------------------------------------------------------------ tree
     def export_tree(self, game: int, with_hidden: bool = False):
-        S = (self.N + 1) * self.A
+        S = (self.pool_n + 1) * self.A
         out = dict(child_visit=numpy.zeros(S, numpy.int32), child_value_sum=numpy.zeros(S, numpy.float64),
                    child_reward=numpy.zeros(S, numpy.float32), child_prior=numpy.zeros(S, numpy.float64),
                    child_expansion=numpy.full(S, -1, numpy.int32))
@@ -313,13 +317,38 @@ class SearchEngine:
         for k, v in out.items():
             setattr(e, k, v.ctypes.data)
         if with_hidden:
-            out["hidden"] = numpy.zeros((self.N + 1, self.hidden_elems), numpy.float32)
+            out["hidden"] = numpy.zeros((self.pool_n + 1, self.hidden_elems), numpy.float32)
             e.hidden = out["hidden"].ctypes.data
         self._check(self.lib.mz_export_tree(self._h, int(game), C.byref(e)))
         out["n_expansions"] = int(e.n_expansions)
         out["root_visit"] = int(e.root_visit)
         out["root_value_sum"] = float(e.root_value_sum)
+        out["root_reward"] = float(e.root_reward)
         return out
+
+    def import_tree(self, game: int, tree: dict):
+        """Seed game ``game``'s tree in the node pool (the inverse of ``export_tree``; ``mz_import_tree``): arrays
+        ``child_visit / child_value_sum / child_reward / child_prior / child_expansion`` of ``n_expansions * A`` entries,
+        ``hidden [n_expansions, hidden_elems]``, ``root_visit``, ``root_value_sum``, ``root_reward``."""
+        keep = []
+        K = int(tree["n_expansions"])
+        e = _lib.MzTreeExport()
+        e.n_expansions = K
+        for k, dt in (("child_visit", numpy.int32), ("child_value_sum", numpy.float64), ("child_reward", numpy.float32),
+                      ("child_prior", numpy.float64), ("child_expansion", numpy.int32)):
+            a = numpy.ascontiguousarray(tree[k], dtype=dt).reshape(-1)
+            assert a.size >= K * self.A, k
+            keep.append(a)
+            setattr(e, k, a.ctypes.data)
+        if tree.get("hidden") is not None:
+            hdn = numpy.ascontiguousarray(tree["hidden"], dtype=numpy.float32).reshape(-1)
+            assert hdn.size >= K * self.hidden_elems
+            keep.append(hdn)
+            e.hidden = hdn.ctypes.data
+        e.root_visit = int(tree["root_visit"])
+        e.root_value_sum = float(tree["root_value_sum"])
+        e.root_reward = float(tree.get("root_reward", 0.0))
+        self._check(self.lib.mz_import_tree(self._h, int(game), C.byref(e)))
 
 
 class DeviceSelfPlayLoop:

@@ -60,8 +60,11 @@ class DeviceModel:
 
     def __init__(self, config, max_games=1, device=0, seed=None, num_simulations=None):
         self.config = config
+        # a single-game model also serves MCTS.run(override_root_with=...) (diagnose_model.py:61-72): the continued
+        # search adds num_simulations expansions to an imported subtree of up to num_simulations expansions
+        n = int(config.num_simulations if num_simulations is None else num_simulations)
         self.engine = SearchEngine(config, max_games=max_games, device=device, seed=seed,
-                                   num_simulations=num_simulations)
+                                   num_simulations=num_simulations, extra_expansions=n + 1 if max_games == 1 else 0)
         self._weights = None
 
     def set_weights(self, weights):
@@ -117,6 +120,56 @@ class Node:
             return 0
         return self.value_sum / self.visit_count
 
+    def expand(self, actions, to_play, reward, policy_logits, hidden_state):
+        """Fill the node from a network output (self_play.py:451-465) - host side, for callers that build a root by
+        hand before ``MCTS.run(..., override_root_with=root)`` (diagnose_model.py:54-69)."""
+        import torch
+        self.to_play = to_play
+        self.reward = reward
+        self.hidden_state = hidden_state
+        policy_values = torch.softmax(torch.tensor([policy_logits[0][a] for a in actions]), dim=0).tolist()
+        for i, action in enumerate(actions):
+            self.children[action] = Node(policy_values[i])
+
+    def add_exploration_noise(self, dirichlet_alpha, exploration_fraction):
+        """self_play.py:467-476."""
+        actions = list(self.children.keys())
+        noise = numpy.random.dirichlet([dirichlet_alpha] * len(actions))
+        frac = exploration_fraction
+        for a, n in zip(actions, noise):
+            self.children[a].prior = self.children[a].prior * (1 - frac) + n * frac
+
+
+def _flatten_subtree(root, A, hidden_elems):
+    """``Node`` graph -> the struct-of-arrays tree ``mz_import_tree`` takes: expansion 0 = ``root``, expanded
+    children numbered breadth first, child slots ``[e*A, e*A+A)`` by action id."""
+    nodes, order = [root], {id(root): 0}
+    i = 0
+    while i < len(nodes):
+        for a in range(A):
+            ch = nodes[i].children.get(a)
+            if ch is not None and ch.expanded():
+                order[id(ch)] = len(nodes)
+                nodes.append(ch)
+        i += 1
+    K = len(nodes)
+    t = dict(n_expansions=K, child_visit=numpy.zeros(K * A, numpy.int32), child_value_sum=numpy.zeros(K * A),
+             child_reward=numpy.zeros(K * A, numpy.float32), child_prior=numpy.zeros(K * A),
+             child_expansion=numpy.full(K * A, -1, numpy.int32), hidden=numpy.zeros((K, hidden_elems), numpy.float32),
+             root_visit=int(root.visit_count), root_value_sum=float(root.value_sum), root_reward=float(root.reward))
+    for e, node in enumerate(nodes):
+        assert set(node.children) == set(range(A)), "override_root_with: an expanded non-root node has every action as a child"
+        t["hidden"][e] = numpy.asarray(node.hidden_state, dtype=numpy.float32).ravel()
+        for a, ch in node.children.items():
+            s = e * A + a
+            t["child_visit"][s] = ch.visit_count
+            t["child_value_sum"][s] = ch.value_sum
+            t["child_prior"][s] = ch.prior
+            if ch.expanded():
+                t["child_reward"][s] = ch.reward
+                t["child_expansion"][s] = order[id(ch)]
+    return t
+
 
 def _node_graph(tree, legal_actions, to_play, num_players, A):
     """Rebuild the ``Node`` graph of one game from ``SearchEngine.export_tree``."""
@@ -124,7 +177,7 @@ def _node_graph(tree, legal_actions, to_play, num_players, A):
     root.visit_count = tree["root_visit"]
     root.value_sum = tree["root_value_sum"]
     root.to_play = to_play
-    root.reward = -0.0
+    root.reward = tree.get("root_reward", -0.0)
     hidden = tree.get("hidden")
     if hidden is not None:
         root.hidden_state = hidden[0]
@@ -156,9 +209,9 @@ class MCTS:
         self.config = config
 
     def run(self, model, observation, legal_actions, to_play, add_exploration_noise, override_root_with=None):
-        if override_root_with:
-            raise NotImplementedError("override_root_with (diagnose_model.py:70-72) is not supported yet")
         config = self.config
+        if override_root_with:
+            return self._continue(model, legal_actions, to_play, add_exploration_noise, override_root_with)
         assert legal_actions, f"Legal actions should not be an empty array. Got {legal_actions}."
         assert set(legal_actions).issubset(set(config.action_space)), \
             "Legal actions should be a subset of the action space."
@@ -187,6 +240,36 @@ class MCTS:
 # ----------------------------------------------------------------------------------------
 # output format
 # ----------------------------------------------------------------------------------------
+def _mcts_continue(self, model, legal_actions, to_play, add_exploration_noise, node):
+    """``MCTS.run(..., override_root_with=node)`` (self_play.py:275-277; diagnose_model.py:61-72): ``node`` - an expanded
+    node of an earlier search, typically ``root.children[action]`` - becomes the root, ``num_simulations`` more
+    simulations are run on top of what it already holds, with fresh ``MinMaxStats``; ``root_predicted_value`` is None.
+    The subtree is uploaded with ``mz_import_tree`` and searched with ``MZ_FLAG_CONTINUE``; a new ``Node`` graph is
+    returned (the reference mutates ``node`` in place)."""
+    config = self.config
+    engine = model.engine
+    A = engine.A
+    assert node.expanded(), "override_root_with needs an expanded node"
+    assert list(legal_actions) == list(range(A)), "a non-root node has the whole action space as children"
+    tree = _flatten_subtree(node, A, engine.hidden_elems)
+    engine.import_tree(0, tree)
+    noise, first = None, None
+    if add_exploration_noise:
+        noise = numpy.random.dirichlet([config.root_dirichlet_alpha] * A)[None]     # self_play.py:473 on the node's children
+    if node.visit_count == 0:
+        # an unvisited root: every child scores exactly 0 in the first simulation -> uniform pick (self_play.py:371)
+        first = numpy.array([numpy.random.choice(A)], numpy.int32)
+    out = engine.search(legal_mask=numpy.ones((1, A), numpy.uint8), to_play=numpy.array([to_play], numpy.int32),
+                        add_exploration_noise=add_exploration_noise, noise=noise, first_index=first, keep_tree=True,
+                        continue_tree=True, n_games=1)
+    new = engine.export_tree(0, with_hidden=True)
+    root = _node_graph(new, list(range(A)), to_play, len(config.players), A)
+    return root, {"max_tree_depth": int(out.max_tree_depth[0]), "root_predicted_value": None}
+
+
+MCTS._continue = _mcts_continue
+
+
 class GameHistory:
     """Same attributes and helpers as the reference's (self_play.py:479-550)."""
 

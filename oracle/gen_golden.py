@@ -481,6 +481,52 @@ def main_round2():
     json.dump(experts, open(os.path.join(OUT, "expert.json"), "w"))
     print("expert fixtures:", {k: len(v) for k, v in experts.items()})
 
+    # ---- override_root_with (self_play.py:275-277): (a) subtree reuse - the most visited child of a finished search
+    # becomes the root of a second search; (b) diagnose_model.py:54-69 - a hand-expanded, unvisited root
+    over = {}
+    for gname, moves in (("tictactoe", (4, 0)), ("cartpole", None)):
+        gm = load_reference_game(gname)
+        rcfg = gm.MuZeroConfig()
+        rcfg.num_simulations = 25
+        rspec = netspec_from_config(rcfg)
+        wts = synthetic_weights(rspec, 0)
+        rnet = models.MuZeroNetwork(rcfg); rnet.set_weights(to_torch_sd(wts)); rnet.eval()
+        if moves is None:
+            o, legal, tp = numpy.array([[[0.01, -0.02, 0.03, 0.04]]], dtype=numpy.float32), [0, 1], 0
+        else:
+            o, legal, tp = board_obs(gm, moves)
+        first = run_traced_search(sp, rcfg, rnet, o, legal, tp, True, 0)
+        cases = []
+        for kind in ("subtree", "fresh"):
+            numpy.random.seed(0)
+            with torch.no_grad():
+                root, _ = sp.MCTS(rcfg).run(rnet, o, legal, tp, True)
+                action = int(sp.SelfPlay.select_action(root, 0))
+                ntp = rcfg.players[tp + 1] if tp + 1 < len(rcfg.players) else rcfg.players[0]
+                if kind == "subtree":
+                    node = root.children[action]
+                else:
+                    value, reward, policy_logits, hidden_state = rnet.recurrent_inference(root.hidden_state, torch.tensor([[action]]))
+                    reward = models.support_to_scalar(reward, rcfg.support_size).item()
+                    node = sp.Node(0)
+                    node.expand(rcfg.action_space, ntp, reward, policy_logits, hidden_state)
+                pre_visits = int(node.visit_count)
+                with Tracer(sp) as tr:
+                    root2, info2 = sp.MCTS(rcfg).run(rnet, None, rcfg.action_space, ntp, True, node)
+            kids = list(root2.children.keys())
+            cases.append(dict(kind=kind, action=action, to_play=int(ntp), pre_visits=pre_visits,
+                              noise=tr.dirichlet[0], choices=[[n, i] for n, i in tr.choices],
+                              root_actions=[int(a) for a in kids],
+                              root_visits=[int(root2.children[a].visit_count) for a in kids],
+                              root_child_value_sums=[float(root2.children[a].value_sum) for a in kids],
+                              root_priors=[float(root2.children[a].prior) for a in kids],
+                              root_visit_count=int(root2.visit_count), root_value=float(root2.value()),
+                              max_tree_depth=int(info2["max_tree_depth"]),
+                              root_predicted_value=info2["root_predicted_value"]))
+        over[gname] = dict(first=first, cases=cases)
+    json.dump(over, open(os.path.join(OUT, "override_root.json"), "w"))
+    print("override_root_with fixtures:", {k: [c["root_visits"] for c in v["cases"]] for k, v in over.items()})
+
     # ---- FC network on the shipped CartPole checkpoint (the round-1 fixture only covered synthetic weights)
     cart_mod = load_reference_game("cartpole")
     cart_cfg = cart_mod.MuZeroConfig()

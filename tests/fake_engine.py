@@ -13,7 +13,7 @@ from oracle.net import OracleNet
 
 
 class FakeSearchEngine:
-    def __init__(self, config, max_games=1, device=0, seed=None, num_simulations=None):
+    def __init__(self, config, max_games=1, device=0, seed=None, num_simulations=None, extra_expansions=0):
         self.config = config
         self.spec = netspec_from_config(config)
         self.A = self.spec.action_space

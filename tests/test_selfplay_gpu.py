@@ -109,3 +109,39 @@ def test_error_paths_on_device(game_configs):
     out = eng.search(obs=obs[:2])                      # fewer games than the capacity
     assert out.visit_counts.shape == (2, 2) and (out.visit_counts.sum(1) == 5).all()
     eng.close()
+
+
+@pytest.mark.parametrize("name", ["tictactoe", "cartpole"])
+def test_override_root_with_on_device(name, monkeypatch):
+    """MCTS.run(..., override_root_with=node) (self_play.py:275-277): (a) the most visited child of a finished search
+    becomes the root of a second search (subtree reuse); (b) a hand-expanded, unvisited node as diagnose_model.py:54-69
+    builds it.  The device continues the imported tree and reproduces the reference's visit counts exactly."""
+    monkeypatch.setenv("MZ_TC_MODE", "off")
+    fx = golden_json("override_root.json")[name]
+    first = fx["first"]
+    worker, cfg, sp = _worker(name, 0, num_simulations=first["num_simulations"])
+    A = len(cfg.action_space)
+    obs = numpy.array(first["obs"]).reshape(first["obs_shape"])
+    for case in fx["cases"]:
+        numpy.random.seed(0)
+        root, _ = sp.MCTS(cfg).run(worker.model, obs, first["legal"], first["to_play"], True)
+        assert [root.children[a].visit_count for a in first["root_actions"]] == first["root_visits"]
+        action = int(sp.SelfPlay.select_action(root, 0))
+        assert action == case["action"]
+        if case["kind"] == "subtree":
+            node = root.children[action]
+        else:
+            r = worker.model.engine.recurrent_inference(root.hidden_state[None], [action])
+            node = sp.Node(0)
+            node.expand(cfg.action_space, case["to_play"], float(r["reward"][0]), r["policy_logits"], r["hidden"][0])
+        assert node.visit_count == case["pre_visits"]
+        root2, info2 = sp.MCTS(cfg).run(worker.model, None, cfg.action_space, case["to_play"], True, node)
+        assert list(root2.children.keys()) == case["root_actions"]
+        assert [root2.children[a].visit_count for a in case["root_actions"]] == case["root_visits"], case["kind"]
+        assert root2.visit_count == case["root_visit_count"] == case["pre_visits"] + first["num_simulations"]
+        assert info2["root_predicted_value"] is None and info2["max_tree_depth"] == case["max_tree_depth"]
+        assert abs(root2.value() - case["root_value"]) <= 1e-4 * max(1.0, abs(case["root_value"]))
+        numpy.testing.assert_allclose([root2.children[a].prior for a in case["root_actions"]], case["root_priors"], rtol=1e-5, atol=1e-7)
+        numpy.testing.assert_allclose([root2.children[a].value_sum for a in case["root_actions"]], case["root_child_value_sums"],
+                                      rtol=1e-3, atol=1e-3)
+    worker.model.engine.close()
