@@ -390,7 +390,8 @@ def run_workload(name, args, D, rank, local_rank, world, with_loop, headline):
         # the dominant class's share of the conv FLOPs ~ its share of the conv time is NOT assumed: classes other than the
         # dominant one only run the stem / DownSample convs, a few % of the FLOPs; achieved uses ALL conv FLOPs over ALL conv time
         achieved = conv_flops / (conv_ms / 1000.0) / 1e12
-        tr = traffic.get(dominant + ":" + game, traffic.get(dominant, {}))
+        tr = traffic.get(f"{dominant}:{game}@{mode}" if mode else f"{dominant}:{game}") or \
+            traffic.get(f"{dominant}:{game}" if not mode else "", {}) or {}
         roofline = {"bound": "tensor", "achieved": achieved, "peak": bf16_peak, "unit": "TFLOP/s",
                     "frac": achieved / bf16_peak, "traffic": tr.get("dram_bytes_per_launch"), "traffic_source": tr.get("source"),
                     "peak_kind": peak_kind + " dense bf16 (sustained)",
@@ -416,6 +417,8 @@ def run_workload(name, args, D, rank, local_rank, world, with_loop, headline):
     if clk:
         sub["clocks"] = clk
     eng.close()
+    if headline and game == "cartpole" and world == 1 and not args.no_saturation:
+        sub["saturation"] = saturation_curve(cfg, spec, N, local_rank, dev)
     del flush, dev_obs, dev_noise
     torch.cuda.empty_cache()
     if with_loop:
@@ -429,6 +432,27 @@ def run_workload(name, args, D, rank, local_rank, world, with_loop, headline):
         else:
             os.environ["MZ_TC_MODE"] = prev_mode
     return sub
+
+
+def saturation_curve(cfg, spec, N, device, dev):
+    """Search throughput of the fused FC kernel at larger batches than the BASELINE's 4096 games: the headline launch
+    lasts one game's chain of N dependent simulations with 28 games per SM in flight; more games per SM fill the issue
+    slots that chain leaves idle (device time of 5 searches per point, inputs resident, no L2 flush)."""
+    import torch
+    from muzero_general_b200.engine import SearchEngine
+    from muzero_general_b200.netspec import synthetic_weights
+    out = []
+    for B in (4096, 8192, 16384, 32768, 65536):
+        eng = SearchEngine(cfg, max_games=B, device=device, num_simulations=N)
+        eng.load_weights(synthetic_weights(spec, 0))
+        rs = numpy.random.RandomState(B)
+        obs = torch.from_numpy(rs.uniform(-0.05, 0.05, size=(B, eng.obs_elems)).astype(numpy.float32)).to(dev)
+        for _ in range(2):
+            eng.search(obs=obs, add_exploration_noise=True)
+        ms = [eng.search(obs=obs, add_exploration_noise=True).device_ms for _ in range(5)]
+        out.append({"games": B, "kernel_ms": float(numpy.median(ms)), "env_steps_per_s": B / (float(numpy.median(ms)) / 1000.0)})
+        eng.close()
+    return out
 
 
 def selfplay_loop(game, B, N, device, rank, world, D):
@@ -482,6 +506,7 @@ def main():
     ap.add_argument("--extras", default=None, help="comma-separated extra workloads (name or name@tc-mode)")
     ap.add_argument("--no-extras", action="store_true")
     ap.add_argument("--no-loop", action="store_true")
+    ap.add_argument("--no-saturation", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -568,6 +593,8 @@ def main():
         }
         if "loop" in head:
             out["loop"] = head["loop"]
+        if "saturation" in head:
+            out["saturation"] = head["saturation"]
         if extras:
             out["workloads"] = extras
         if world == 1 and not args.no_cpu_baseline:

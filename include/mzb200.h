@@ -246,7 +246,8 @@ typedef struct MzSelfPlayDesc {
     int32_t reward_scale;         /* board games: reward of the winning move (tictactoe.py:144: 20, connect4.py:144: 10) */
     int64_t first_game_id;        /* slot g plays the global games first_game_id + g + k * game_id_stride, k = 0, 1, ... */
     int64_t game_id_stride;       /* 0 = max_games; world_size * max_games keeps ids unique across ranks */
-    uint64_t staging_bytes;       /* capacity of the finished-game staging area, 0 = library default */
+    uint64_t staging_bytes;       /* capacity of the finished-game staging area, 0 = library default (4x the bytes of
+                                     every slot finishing a maximum-length game at once, within [32 MiB, 256 MiB]) */
 } MzSelfPlayDesc;
 
 /* Optional per-move overrides (HOST pointers, n = max_games; only with n_moves == 1).  Parity tests drive the
@@ -266,6 +267,7 @@ typedef struct MzSelfPlayStats {
     int32_t parked_slots;         /* times a finished game did not fit into the staging area during the last call
                                      (it waits in its slot and is staged after the next drain) */
     double device_ms;             /* device time of the last mz_selfplay_moves call */
+    int64_t staging_capacity;     /* bytes the staging area holds (callers size their moves-per-call from it) */
 } MzSelfPlayStats;
 
 /* Current device-side view of the environments (HOST output pointers, any may be NULL). */

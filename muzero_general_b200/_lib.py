@@ -98,7 +98,8 @@ class MzSelfPlayInject(C.Structure):
 
 class MzSelfPlayStats(C.Structure):
     _fields_ = [("env_steps", C.c_int64), ("games_finished", C.c_int64), ("staged_bytes", C.c_int64),
-                ("staged_games", C.c_int32), ("parked_slots", C.c_int32), ("device_ms", C.c_double)]
+                ("staged_games", C.c_int32), ("parked_slots", C.c_int32), ("device_ms", C.c_double),
+                ("staging_capacity", C.c_int64)]
 
 
 class MzSelfPlayPeek(C.Structure):

@@ -443,10 +443,15 @@ extern "C" int mz_selfplay_begin(MzHandle* h, const MzSelfPlayDesc* d) {
               sp_alloc(sp, &sp->d_forced, B) && sp_alloc(sp, &sp->d_uniform, B) && sp_alloc(sp, &sp->d_noise, (size_t)B * A) &&
               sp_alloc(sp, &sp->d_first, B);
     if (!ok) { mz_selfplay_destroy(h); return fail(h, MZ_ENOMEM, "mz_selfplay_begin: out of device memory"); }
-    // staging: room for every slot finishing a maximum-length game at once, capped at 256 MiB unless asked otherwise
+    // staging: by default 4x the room for every slot finishing a maximum-length game at once, within [32, 256] MiB;
+    // whatever the size, games that do not fit wait in their slots (parked) - nothing is dropped
     unsigned long long cap = d->staging_bytes;
     const unsigned long long worst = staged_block_bytes(d->max_moves, A, O) * (unsigned long long)B;
-    if (cap == 0) cap = worst < (256ull << 20) ? worst : (256ull << 20);
+    if (cap == 0) {
+        cap = 4 * worst;
+        if (cap < (32ull << 20)) cap = 32ull << 20;
+        if (cap > (256ull << 20)) cap = 256ull << 20;
+    }
     if (cap < staged_block_bytes(d->max_moves, A, O)) { mz_selfplay_destroy(h); return fail(h, MZ_EINVAL, "mz_selfplay_begin: staging_bytes smaller than one game"); }
     const unsigned long long index_entries = cap / staged_block_bytes(1, A, O) + 1;
     if (cudaHostAlloc(reinterpret_cast<void**>(&sp->staging), cap, cudaHostAllocMapped) != cudaSuccess ||
@@ -482,6 +487,7 @@ static int sp_read_counters(MzHandle* h, MzSelfPlayStats* stats, float ms) {
         stats->staged_games = (int32_t)sp->h_counters[3];
         stats->parked_slots = (int32_t)sp->h_counters[4];
         stats->device_ms = ms;
+        stats->staging_capacity = (int64_t)sp->dev.staging_cap;
     }
     return MZ_OK;
 }

@@ -697,7 +697,8 @@ class DeviceBatchedSelfPlay:
                                        reward_scale=getattr(vec, "REWARD_SCALE", 1),
                                        first_game_id=worker.first_game_id, game_id_stride=worker.game_id_stride,
                                        staging_bytes=int(getattr(cfg, "selfplay_staging_bytes", 0) or 0))
-        self.moves_per_call = int(getattr(cfg, "selfplay_moves_per_call", 32) or 32)
+        self.moves_per_call = int(getattr(cfg, "selfplay_moves_per_call", 64) or 64)   # upper bound of a chunk
+        self.chunk = min(4, self.moves_per_call)                                      # adapted to the staging fill below
         self.device_ms = 0.0          # device time of all mz_selfplay_moves calls so far
         self.calls = 0
 
@@ -709,10 +710,17 @@ class DeviceBatchedSelfPlay:
         out = PackedGames(self.obs_shape, self.obs_dtype, self.reward_type)
         left = int(n_moves)
         while left > 0:
-            k = 1 if inject else min(left, self.moves_per_call)
+            k = 1 if inject else min(left, self.chunk)
             st = self.loop.moves(k, temperature, **inject)
             self.device_ms += st.device_ms
             self.calls += 1
+            # next chunk: as many moves as fill about half of the staging area at the rate just seen
+            if st.parked_slots:
+                self.chunk = max(1, self.chunk // 2)
+            elif st.staged_bytes > 0:
+                self.chunk = max(1, min(self.moves_per_call, int(0.5 * st.staging_capacity * k / st.staged_bytes)))
+            else:
+                self.chunk = min(self.moves_per_call, 2 * self.chunk)
             out.add(*self.loop.drain())
             left -= k
         return out
