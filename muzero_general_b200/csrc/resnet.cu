@@ -60,6 +60,7 @@ struct ConvArgs {
     int pool_stride;
     int n, Cin, Cout, Hin, Win, Ho, Wo, stride, relu, A;
     int boards_per_cta, cin_chunk;
+    int band_rows;            // output rows per CTA (blockIdx.z picks the band); = Ho unless the image is too large for one CTA
     int out_p64c4;            // kLayoutF16 / kLayoutSplit: write the tensor-core board layout (P64S) instead of NCHW
 };
 
@@ -67,13 +68,17 @@ template <int P, int STRIDE, int MAX_ITEMS>
 __global__ void __launch_bounds__(256) conv3x3_kernel(const __grid_constant__ ConvArgs a) {
     extern __shared__ __align__(16) float smem[];
     constexpr int IN_SPAN = (P - 1) * STRIDE + 3;              // input columns feeding P outputs
-    const int Hp = a.Hin + 2, Wp = a.Win + 2;                   // padded plane
+    // this CTA's band of output rows [r0, r0 + nbr) and the input rows it needs: [r0*STRIDE - 1, (r0+nbr-1)*STRIDE + 1]
+    const int r0 = blockIdx.z * a.band_rows;
+    const int nbr = min(a.band_rows, a.Ho - r0);
+    const int y_in0 = r0 * STRIDE - 1;
+    const int Hp = (a.band_rows - 1) * STRIDE + 3, Wp = a.Win + 2;   // staged (padded) plane of the band
     const int plane = Hp * Wp;
     const int ct = a.Cout < 64 ? a.Cout : 64;                   // cout tile of this CTA
     const int cout0 = blockIdx.y * ct;
     const int cgs = ct / 4;
     const int segs = a.Wo / P;
-    const int items_per_board = cgs * a.Ho * segs;
+    const int items_per_board = cgs * nbr * segs;
     const int b0 = blockIdx.x * a.boards_per_cta;
     const int nb = min(a.boards_per_cta, a.n - b0);
     float* s_w = smem;                                          // [cin_chunk][9][ct]
@@ -104,14 +109,15 @@ __global__ void __launch_bounds__(256) conv3x3_kernel(const __grid_constant__ Co
             const int x = i % Wp, y = (i / Wp) % Hp, ci = (i / plane) % cc, b = i / (plane * cc);
             const int g = b0 + b, cg = c0 + ci;
             float v = 0.0f;
-            if (x >= 1 && x <= a.Win && y >= 1 && y <= a.Hin) {
+            const int yi = y_in0 + y;                           // input row of staged row y
+            if (x >= 1 && x <= a.Win && yi >= 0 && yi < a.Hin) {
                 if (a.action && cg == a.Cin - 1) {
                     v = __fdiv_rn((float)a.action[g], (float)a.A);       // action / |A| plane
                 } else {
                     const float* src = a.gather_parent
                         ? a.in + ((size_t)g * a.pool_stride + a.gather_parent[g]) * sample_elems
                         : a.in + (size_t)g * sample_elems;
-                    v = src[((size_t)cg * a.Hin + (y - 1)) * a.Win + (x - 1)];
+                    v = src[((size_t)cg * a.Hin + yi) * a.Win + (x - 1)];
                 }
             }
             s_in[i] = v;
@@ -124,7 +130,7 @@ __global__ void __launch_bounds__(256) conv3x3_kernel(const __grid_constant__ Co
             if (item >= total_items) break;
             const int cgi = item % cgs;
             const int rest = item / cgs;
-            const int seg = rest % segs, y = (rest / segs) % a.Ho, b = rest / (segs * a.Ho);
+            const int seg = rest % segs, y = (rest / segs) % nbr, b = rest / (segs * nbr);
             const float* ib = s_in + (size_t)b * cc * plane + (y * STRIDE) * Wp + seg * P * STRIDE;
             const float* wb = s_w + cgi * 4;
             for (int ci = 0; ci < cc; ++ci) {
@@ -156,7 +162,7 @@ __global__ void __launch_bounds__(256) conv3x3_kernel(const __grid_constant__ Co
         if (item >= total_items) break;
         const int cgi = item % cgs;
         const int rest = item / cgs;
-        const int seg = rest % segs, y = (rest / segs) % a.Ho, b = rest / (segs * a.Ho);
+        const int seg = rest % segs, y = r0 + (rest / segs) % nbr, b = rest / (segs * nbr);
         const int g = b0 + b;
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
@@ -472,6 +478,75 @@ __global__ void __launch_bounds__(kHeadThreads) heads_kernel(const __grid_consta
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// Generic heads for nets whose head weights do not fit in shared memory (games/atari.py: 256 reduced channels x 36
+// positions -> FC 9216 -> 256 -> 256 -> 601, 9.4 MB for the first FC layer alone): the same operations as heads_kernel,
+// one plain kernel per stage, every dot product accumulated in the same ascending order (so the two routes agree bit
+// for bit where both apply).  Throughput is not the point here - availability of the large configuration is.
+// ------------------------------------------------------------------------------------------
+__global__ void big_rescale_kernel(const float* x, int n, int C, int HW, float* rescaled, float* pool_hidden, int pool_stride, int out_slot) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;           // (sample, channel)
+    if (i >= n * C) return;
+    const int g = i / C;
+    const float* src = x + (size_t)i * HW;
+    float lo = INFINITY, hi = -INFINITY;
+    for (int p = 0; p < HW; ++p) { lo = fminf(lo, src[p]); hi = fmaxf(hi, src[p]); }
+    float sc = __fsub_rn(hi, lo);
+    if (sc < 1e-5f) sc = __fadd_rn(sc, 1e-5f);
+    for (int p = 0; p < HW; ++p) {
+        const float v = div_pos_or_zero(__fsub_rn(src[p], lo), sc);
+        if (rescaled) rescaled[(size_t)i * HW + p] = v;
+        if (pool_hidden) pool_hidden[((size_t)g * pool_stride + out_slot) * C * HW + (size_t)(i % C) * HW + p] = v;
+    }
+}
+// r[g][c][p] = b[c] + sum_k W[c][k] x[g][k][p]
+__global__ void big_conv1x1_kernel(const float* x, const float* w, const float* b, int n, int C, int rc, int HW, float* out, int out_stride) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (size_t)n * rc * HW) return;
+    const int p = i % HW, c = (i / HW) % rc;
+    const size_t g = i / ((size_t)HW * rc);
+    const float* xs = x + g * C * HW + p;
+    const float* ws = w + (size_t)c * C;
+    float acc = b[c];
+    for (int k = 0; k < C; ++k) acc = fmaf(ws[k], xs[(size_t)k * HW], acc);
+    out[g * out_stride + (size_t)c * HW + p] = acc;
+}
+// y[g][o] = act(b[o] + sum_i x[g][i] W[i][o]), W packed [in/4][out][4]; x rows are `in_stride` apart and zero padded to 4
+__global__ void big_fc_kernel(const float* x, const float* W, const float* b, int n, int in, int out, int in_stride, int out_stride,
+                              int elu, float* y) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int out4 = (out + 3) & ~3;
+    if (i >= (size_t)n * out4) return;
+    const int o = i % out4;
+    const size_t g = i / out4;
+    float r = 0.0f;
+    if (o < out) {
+        const float4* x4 = reinterpret_cast<const float4*>(x + g * in_stride);
+        const float4* W4 = reinterpret_cast<const float4*>(W);
+        float acc = b[o];
+        const int in4 = (in + 3) >> 2;
+        for (int k = 0; k < in4; ++k) {
+            const float4 xv = x4[k], wv = W4[(size_t)k * out + o];
+            acc = fmaf(xv.x, wv.x, acc);
+            acc = fmaf(xv.y, wv.y, acc);
+            acc = fmaf(xv.z, wv.z, acc);
+            acc = fmaf(xv.w, wv.w, acc);
+        }
+        r = elu ? elu1(acc) : acc;
+    }
+    y[g * out_stride + o] = r;                                     // the padding entries read by the next layer are zero
+}
+__global__ void big_scalar_kernel(const float* logits, int n, int stride, int n_out, int S, float* logits_out, float* scalar) {
+    const int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (g >= n) return;
+    const float* l = logits + (size_t)g * stride;
+    if (logits_out) for (int o = lane; o < n_out; o += 32) logits_out[(size_t)g * n_out + o] = l[o];
+    if (scalar) {
+        const float v = support_to_scalar_group<32>(l, S);
+        if (lane == 0) scalar[g] = v;
+    }
+}
+
 __global__ void fill_root_reward_logits_kernel(float* out, int n, int F, int S) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n * F) out[i] = (i % F == S) ? 0.0f : -INFINITY;
@@ -549,6 +624,8 @@ struct ResNetDevice {
     bool use_tc = false;               // residual towers on tcgen05 (conv_tc.cu / conv_x3.cu)
     bool split = false;                // x3 mode: split operands, fp32-grade accuracy (conv_x3.cu); false = plain fp16 operands
     bool tc_capable = false;           // the shape allows the tensor-core towers at all
+    float* big_scratch = nullptr;      // activations of the generic heads route (heads_big)
+    size_t big_elems = 0;
     int* d_sat = nullptr;              // x3 mode: number of epilogue threads that stored an activation beyond the fp16 range
     int fell_back = 0;                 // set when the range guard switched this net to the fp32 CUDA-core towers
     bool fuse_small = true;            // CUDA-core towers as one fused launch where they fit (small_tower.cu); MZ_NO_FUSE=1: per layer
@@ -619,6 +696,7 @@ void resnet_destroy(ResNetDevice* r) {
     if (r->scratch_hidden) cudaFree(r->scratch_hidden);
     if (r->scratch_state) cudaFree(r->scratch_state);
     if (r->d_sat) cudaFree(r->d_sat);
+    if (r->big_scratch) cudaFree(r->big_scratch);
     if (r->d_conv) cudaFree(r->d_conv);
     if (r->d_head) cudaFree(r->d_head);
     delete r;
@@ -1004,14 +1082,19 @@ struct Runner {
         int P = 1;
         for (int cand : {8, 7, 6, 4, 3, 2}) if (a.Wo % cand == 0) { P = cand; break; }
         const int ct = l.cout < 64 ? l.cout : 64;
-        const int items_per_board = (ct / 4) * a.Ho * (a.Wo / P);
         const int threads = 256;
+        // large images (e.g. 128 output channels at 48 x 48, games/atari.py): split the output rows into bands, one CTA each
+        int bands = 1;
+        while (bands < a.Ho && (ct / 4) * ((a.Ho + bands - 1) / bands) * (a.Wo / P) > threads * 4) ++bands;
+        a.band_rows = (a.Ho + bands - 1) / bands;
+        bands = (a.Ho + a.band_rows - 1) / a.band_rows;
+        const int items_per_board = (ct / 4) * a.band_rows * (a.Wo / P);
         int boards = 1;
         if (items_per_board < threads) boards = threads / items_per_board;
         if (boards > 32) boards = 32;
         if (boards > n) boards = n;
         if (items_per_board * boards > threads * 4) { *err = "conv3x3: image too large for the item budget"; return false; }
-        const size_t plane = (size_t)(Hin + 2) * (Win + 2);
+        const size_t plane = (size_t)((a.band_rows - 1) * l.stride + 3) * (Win + 2);
         // pick the cin chunk so weights + planes fit comfortably
         const size_t budget = 200 * 1024 / 4;
         int chunk = l.cin;
@@ -1019,7 +1102,7 @@ struct Runner {
         if ((size_t)chunk * 9 * ct + (size_t)boards * chunk * plane > budget) { *err = "conv3x3: tile does not fit in shared memory"; return false; }
         a.boards_per_cta = boards; a.cin_chunk = chunk;
         const size_t smem = ((size_t)chunk * 9 * ct + (size_t)boards * chunk * plane) * 4;
-        dim3 grid((n + boards - 1) / boards, l.cout / ct);
+        dim3 grid((n + boards - 1) / boards, l.cout / ct, bands);
         const bool multi = items_per_board * boards > threads;
 #define MZ_CONV(PP, SS)                                                                                         \
         if (P == PP && l.stride == SS) {                                                                        \
@@ -1080,6 +1163,51 @@ struct Runner {
         return true;
     }
 
+    // heads whose weights do not fit in shared memory: one plain kernel per stage (see big_*_kernel above)
+    bool heads_big(const float* x, int n_heads, const HeadDesc* const* hs, float* l0, float* l1, float* s0, float* s1,
+                   float* rescaled, float* pool_hidden, int pool_stride, int out_slot) {
+        const int C = r->C, HW = r->hh * r->hw, S = r->net.support_size;
+        kt_begin(KT_HEADS, stream);
+        if (rescaled || pool_hidden) {
+            big_rescale_kernel<<<(n * C + 127) / 128, 128, 0, stream>>>(x, n, C, HW, rescaled, pool_hidden, pool_stride, out_slot);
+            *launches += 1;
+        }
+        float* logits_out[2] = {l0, l1};
+        float* scalar_out[2] = {s0, s1};
+        for (int hi = 0; hi < n_heads; ++hi) {
+            const HeadDesc& d = *hs[hi];
+            int width = ((d.rc * HW + 3) & ~3);
+            for (int l = 0; l < d.mlp.n; ++l) width = std::max(width, (d.mlp.out[l] + 3) & ~3);
+            const size_t need = (size_t)2 * n * width;
+            if (r->big_elems < need) {
+                if (r->big_scratch) cudaFree(r->big_scratch);
+                r->big_scratch = nullptr; r->big_elems = 0;
+                if (cudaMalloc(&r->big_scratch, need * 4 + 64) != cudaSuccess) { *err = "heads: scratch allocation failed"; kt_end(stream); return false; }
+                r->big_elems = need;
+            }
+            float* cur = r->big_scratch;
+            float* nxt = r->big_scratch + (size_t)n * width;
+            cudaMemsetAsync(cur, 0, (size_t)n * width * 4, stream);           // zero padding behind rc*HW
+            const size_t items = (size_t)n * d.rc * HW;
+            big_conv1x1_kernel<<<(unsigned)((items + 127) / 128), 128, 0, stream>>>(x, r->d_head + d.w1_off, r->d_head + d.b1_off, n, C, d.rc, HW, cur, width);
+            *launches += 1;
+            for (int l = 0; l < d.mlp.n; ++l) {
+                const int out4 = (d.mlp.out[l] + 3) & ~3;
+                big_fc_kernel<<<(unsigned)(((size_t)n * out4 + 127) / 128), 128, 0, stream>>>(
+                    cur, r->d_head + d.mlp.w_off[l], r->d_head + d.mlp.b_off[l], n, d.mlp.in[l], d.mlp.out[l], width, width,
+                    l == d.mlp.n - 1 ? 0 : 1, nxt);
+                *launches += 1;
+                float* t = cur; cur = nxt; nxt = t;
+            }
+            big_scalar_kernel<<<(n * 32 + 127) / 128, 128, 0, stream>>>(cur, n, width, d.n_out, S, logits_out[hi], scalar_out[hi]);
+            *launches += 1;
+        }
+        kt_end(stream);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return fail("heads (generic route)", e);
+        return true;
+    }
+
     bool heads(const float* x, int n_heads, const HeadDesc* h0, const HeadDesc* h1, float* l0, float* l1, float* s0, float* s1,
                float* rescaled, float* pool_hidden, int pool_stride, int out_slot, bool p64c4 = false, float* state_p64c4 = nullptr) {
         HeadsArgs a{};
@@ -1115,7 +1243,10 @@ struct Runner {
         if (narrow) groups = std::max(1, std::min(groups, (n + r->sm_count - 1) / r->sm_count));
         size_t smem = ((size_t)a.w_floats + (size_t)groups * a.warp_floats) * 4;
         while (groups > 1 && smem > 227 * 1024) { --groups; smem = ((size_t)a.w_floats + (size_t)groups * a.warp_floats) * 4; }
-        if (smem > 227 * 1024) { *err = "heads: weights + tiles exceed shared memory"; return false; }
+        if (smem > 227 * 1024) {
+            if (p64c4) { *err = "heads: weights + tiles exceed shared memory"; return false; }
+            return heads_big(x, n_heads, hs, l0, l1, s0, s1, rescaled, pool_hidden, pool_stride, out_slot);
+        }
         const int threads = groups * group;
         static size_t attr_smem[2] = {0, 0};
         if (attr_smem[narrow] < smem) {

@@ -55,7 +55,8 @@ struct SpDev {
     int32_t* first_to_play;    // [B]
     int32_t* fin;              // [B] 0 = playing, T > 0 = finished after T moves, waiting to be packed
     int32_t* last_action;      // [B]
-    // counters: [0] env_steps, [1] games_finished, [2] staged bytes (cursor), [3] staged games, [4] parked slots (this move)
+    // counters: [0] env_steps, [1] games_finished, [2] staging cursor (may run past the capacity), [3] staged games,
+    //           [4] park events of this call, [5] end of the valid staged bytes
     unsigned long long* counters;
     unsigned char* staging;    // mapped pinned host memory
     unsigned long long staging_cap;
@@ -292,80 +293,90 @@ __host__ __device__ inline unsigned long long staged_block_bytes(int T, int A, i
     return (b + 7) & ~7ull;
 }
 
-// One warp per slot.  act != 0: lane 0 plays the slot's move (sampling, environment step, record) unless the slot is
-// parked; then, whatever `act`, a finished game is copied into the staging area by the whole warp and the slot starts
-// its next game (act == 0 is the drain-only pass that re-packs games parked by an earlier call).
-__global__ void selfplay_step_kernel(const SpDev s, int act) {
+// One warp per slot, 32 slots per CTA.  act != 0: lane 0 plays the slot's move (sampling, environment step, record)
+// unless the slot is parked; then, whatever `act`, a finished game is copied into the staging area by the whole warp and
+// the slot starts its next game (act == 0 is the drain-only pass that re-packs games parked by an earlier call).
+// Staging space is reserved with ONE atomicAdd per finished game (a compare-and-swap loop serialises hundreds of
+// finishing warps per move: 89 us per launch at 4096 CartPole games, profiles/r02_selfplay_loop.md): the cursor may run
+// past the capacity, reservations that end beyond it are void (the game stays parked), and since the cursor only grows
+// the valid reservations are a contiguous prefix whose end is tracked in counters[5].
+constexpr int kStepThreads = 1024;
+
+__global__ void __launch_bounds__(kStepThreads) selfplay_step_kernel(const SpDev s, int act) {
+    __shared__ int s_active;
+    if (threadIdx.x == 0) s_active = 0;
+    __syncthreads();
     const int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
-    if (g >= s.B) return;
     int T = 0;
-    if (lane == 0) {
-        T = s.fin[g];
-        if (act && T == 0) {
-            slot_act(s, g);
-            atomicAdd(&s.counters[0], 1ull);
+    if (g < s.B) {
+        if (lane == 0) {
             T = s.fin[g];
+            if (act && T == 0) {
+                slot_act(s, g);
+                atomicAdd(&s_active, 1);
+                T = s.fin[g];
+            }
+        }
+        T = __shfl_sync(0xffffffffu, T, 0);
+        __syncwarp();
+    }
+    if (T != 0) {
+        const unsigned long long bytes = staged_block_bytes(T, s.A, s.O);
+        unsigned long long off = 0;
+        int ok = 0;
+        if (lane == 0) {
+            off = atomicAdd(&s.counters[2], bytes);
+            ok = off + bytes <= s.staging_cap;
+            if (ok) {
+                atomicMax(&s.counters[5], off + bytes);
+                atomicAdd(&s.counters[1], 1ull);
+                const unsigned long long i = atomicAdd(&s.counters[3], 1ull);
+                s.index[2 * i] = off;
+                s.index[2 * i + 1] = ((unsigned long long)(unsigned)g << 32) | (unsigned)T;
+            } else {
+                atomicAdd(&s.counters[4], 1ull);
+            }
+        }
+        ok = __shfl_sync(0xffffffffu, ok, 0);
+        if (ok) {                                     // else parked: packed by a later call, after the host has drained
+            off = ((unsigned long long)__shfl_sync(0xffffffffu, (unsigned)(off >> 32), 0) << 32) | __shfl_sync(0xffffffffu, (unsigned)off, 0);
+            unsigned char* dst = s.staging + off;
+            if (lane == 0) {
+                *reinterpret_cast<int64_t*>(dst) = s.game_id[g];
+                int32_t* hd = reinterpret_cast<int32_t*>(dst + 8);
+                hd[0] = g; hd[1] = T; hd[2] = s.first_to_play[g]; hd[3] = s.O; hd[4] = s.A; hd[5] = (int32_t)bytes;
+            }
+            unsigned char* p = dst + MZ_STAGED_HEADER_BYTES;
+            const size_t r = (size_t)g * s.max_moves;
+            {
+                double* d = reinterpret_cast<double*>(p);
+                for (int i = lane; i < T; i += 32) d[i] = s.rec_root[r + i];
+                p += (size_t)T * 8;
+            }
+            {
+                int32_t* d = reinterpret_cast<int32_t*>(p);
+                for (int i = lane; i < T * s.A; i += 32) d[i] = s.rec_visits[r * s.A + i];
+                p += (size_t)T * s.A * 4;
+                d = reinterpret_cast<int32_t*>(p);
+                for (int i = lane; i < T; i += 32) d[i] = s.rec_action[r + i];
+                p += (size_t)T * 4;
+                float* f = reinterpret_cast<float*>(p);
+                for (int i = lane; i < T; i += 32) f[i] = s.rec_reward[r + i];
+                p += (size_t)T * 4;
+                d = reinterpret_cast<int32_t*>(p);
+                for (int i = lane; i < T; i += 32) d[i] = s.rec_to_play[r + i];
+                p += (size_t)T * 4;
+                f = reinterpret_cast<float*>(p);
+                const float* src = s.rec_obs + (size_t)g * (s.max_moves + 1) * s.O;
+                for (int i = lane; i < (T + 1) * s.O; i += 32) f[i] = src[i];
+            }
+            __syncwarp();
+            if (lane == 0) start_game(s, g, s.game_id[g] + s.id_stride);
         }
     }
-    T = __shfl_sync(0xffffffffu, T, 0);
-    if (T == 0) return;
-    __syncwarp();
-    const unsigned long long bytes = staged_block_bytes(T, s.A, s.O);
-    unsigned long long off = 0;
-    int ok = 0;
-    if (lane == 0) {
-        unsigned long long old = *reinterpret_cast<volatile unsigned long long*>(&s.counters[2]);
-        while (true) {
-            if (old + bytes > s.staging_cap) break;
-            const unsigned long long prev = atomicCAS(&s.counters[2], old, old + bytes);
-            if (prev == old) { ok = 1; off = old; break; }
-            old = prev;
-        }
-        if (ok) {
-            atomicAdd(&s.counters[1], 1ull);
-            const unsigned long long i = atomicAdd(&s.counters[3], 1ull);
-            s.index[2 * i] = off;
-            s.index[2 * i + 1] = ((unsigned long long)(unsigned)g << 32) | (unsigned)T;
-        } else {
-            atomicAdd(&s.counters[4], 1ull);
-        }
-    }
-    ok = __shfl_sync(0xffffffffu, ok, 0);
-    if (!ok) return;                                 // parked: packed by a later move, after the host has drained
-    off = ((unsigned long long)__shfl_sync(0xffffffffu, (unsigned)(off >> 32), 0) << 32) | __shfl_sync(0xffffffffu, (unsigned)off, 0);
-    unsigned char* dst = s.staging + off;
-    if (lane == 0) {
-        *reinterpret_cast<int64_t*>(dst) = s.game_id[g];
-        int32_t* hd = reinterpret_cast<int32_t*>(dst + 8);
-        hd[0] = g; hd[1] = T; hd[2] = s.first_to_play[g]; hd[3] = s.O; hd[4] = s.A; hd[5] = (int32_t)bytes;
-    }
-    unsigned char* p = dst + MZ_STAGED_HEADER_BYTES;
-    const size_t r = (size_t)g * s.max_moves;
-    {
-        double* d = reinterpret_cast<double*>(p);
-        for (int i = lane; i < T; i += 32) d[i] = s.rec_root[r + i];
-        p += (size_t)T * 8;
-    }
-    {
-        int32_t* d = reinterpret_cast<int32_t*>(p);
-        for (int i = lane; i < T * s.A; i += 32) d[i] = s.rec_visits[r * s.A + i];
-        p += (size_t)T * s.A * 4;
-        d = reinterpret_cast<int32_t*>(p);
-        for (int i = lane; i < T; i += 32) d[i] = s.rec_action[r + i];
-        p += (size_t)T * 4;
-        float* f = reinterpret_cast<float*>(p);
-        for (int i = lane; i < T; i += 32) f[i] = s.rec_reward[r + i];
-        p += (size_t)T * 4;
-        d = reinterpret_cast<int32_t*>(p);
-        for (int i = lane; i < T; i += 32) d[i] = s.rec_to_play[r + i];
-        p += (size_t)T * 4;
-        f = reinterpret_cast<float*>(p);
-        const float* src = s.rec_obs + (size_t)g * (s.max_moves + 1) * s.O;
-        for (int i = lane; i < (T + 1) * s.O; i += 32) f[i] = src[i];
-    }
-    __syncwarp();
-    if (lane == 0) start_game(s, g, s.game_id[g] + s.id_stride);
+    __syncthreads();
+    if (threadIdx.x == 0 && s_active) atomicAdd(&s.counters[0], (unsigned long long)s_active);
 }
 
 }  // namespace mz
@@ -478,12 +489,12 @@ extern "C" int mz_selfplay_begin(MzHandle* h, const MzSelfPlayDesc* d) {
 
 static int sp_read_counters(MzHandle* h, MzSelfPlayStats* stats, float ms) {
     MzSelfPlay* sp = h->sp;
-    MZ_CUDA(h, cudaMemcpyAsync(sp->h_counters, sp->dev.counters, 40, cudaMemcpyDeviceToHost, h->stream));
+    MZ_CUDA(h, cudaMemcpyAsync(sp->h_counters, sp->dev.counters, 48, cudaMemcpyDeviceToHost, h->stream));
     MZ_CUDA(h, cudaStreamSynchronize(h->stream));
     if (stats) {
         stats->env_steps = (int64_t)sp->h_counters[0];
         stats->games_finished = (int64_t)sp->h_counters[1];
-        stats->staged_bytes = (int64_t)sp->h_counters[2];
+        stats->staged_bytes = (int64_t)sp->h_counters[5];
         stats->staged_games = (int32_t)sp->h_counters[3];
         stats->parked_slots = (int32_t)sp->h_counters[4];
         stats->device_ms = ms;
@@ -516,6 +527,7 @@ extern "C" int mz_selfplay_moves(MzHandle* h, int32_t n_moves, double temperatur
     if (sp->drained_bytes) {
         // the host has consumed the staged games: rewind the cursor (parked games are packed by the first move below)
         MZ_CUDA(h, cudaMemsetAsync(s.counters + 2, 0, 16, h->stream));
+        MZ_CUDA(h, cudaMemsetAsync(s.counters + 5, 0, 8, h->stream));
         sp->drained_bytes = 0;
     }
     SearchCall call{};
@@ -526,14 +538,14 @@ extern "C" int mz_selfplay_moves(MzHandle* h, int32_t n_moves, double temperatur
     call.visit_counts = s.visits; call.root_value = s.root_value;
     MZ_CUDA(h, cudaEventRecord(sp->e0, h->stream));
     if (sp->h_counters[4]) {                           // games parked by the previous call first, so their slots play again
-        selfplay_step_kernel<<<(B * 32 + 127) / 128, 128, 0, h->stream>>>(s, 0);
+        selfplay_step_kernel<<<(B * 32 + kStepThreads - 1) / kStepThreads, kStepThreads, 0, h->stream>>>(s, 0);
         h->launches += 1;
     }
     MZ_CUDA(h, cudaMemsetAsync(s.counters + 4, 0, 8, h->stream));      // [4] = park events of THIS call
     for (int m = 0; m < n_moves; ++m) {
         int rc = mz_dispatch_search(h, call, false, false, 0);
         if (rc) return rc;
-        selfplay_step_kernel<<<(B * 32 + 127) / 128, 128, 0, h->stream>>>(s, 1);
+        selfplay_step_kernel<<<(B * 32 + kStepThreads - 1) / kStepThreads, kStepThreads, 0, h->stream>>>(s, 1);
         h->launches += 1;
     }
     MZ_CUDA(h, cudaGetLastError());
@@ -558,9 +570,9 @@ extern "C" int mz_selfplay_drain(MzHandle* h, const void** data, uint64_t* bytes
     if (rc) return rc;
     *data = sp->staging;
     if (index) *index = reinterpret_cast<const uint64_t*>(sp->index);
-    *bytes = sp->h_counters[2];
+    *bytes = sp->h_counters[5];
     *n_games = (int32_t)sp->h_counters[3];
-    sp->drained_bytes = sp->h_counters[2] ? sp->h_counters[2] : 0;
+    sp->drained_bytes = sp->h_counters[2];             // the cursor moved (valid or void reservations): rewind it next call
     return MZ_OK;
 }
 

@@ -527,6 +527,27 @@ def main_round2():
     json.dump(over, open(os.path.join(OUT, "override_root.json"), "w"))
     print("override_root_with fixtures:", {k: [c["root_visits"] for c in v["cases"]] for k, v in over.items()})
 
+    # ---- the large configuration (games/atari.py: 131 stacked input planes, 16 blocks x 256 channels, 601-bin heads):
+    # outputs only - the 9.6 MB observation batch is regenerated from its seed by the tests
+    import muzero_general_b200.games as mygames
+    at_ref = load_reference_game("atari").MuZeroConfig()
+    at_spec = check_config_and_spec(models, "atari", at_ref, mygames.load_game_module("atari").MuZeroConfig())
+    at_net = models.MuZeroNetwork(at_ref)
+    at_net.set_weights(to_torch_sd(synthetic_weights(at_spec, 0)))
+    at_net.eval()
+    at_obs = numpy.random.RandomState(41).random_sample((2, at_spec.in_channels, 96, 96)).astype(numpy.float32)
+    at_act = numpy.array([[1], [3]], dtype=numpy.int64)
+    with torch.no_grad():
+        v0, r0, p0, h0 = at_net.initial_inference(torch.from_numpy(at_obs))
+        v1, r1, p1, h1 = at_net.recurrent_inference(h0, torch.from_numpy(at_act))
+        sc = lambda t: models.support_to_scalar(t, at_ref.support_size).numpy()[:, 0]
+        numpy.savez_compressed(os.path.join(OUT, "net_atari.npz"), obs_seed=41, action=at_act,
+                               init_value=v0.numpy(), init_policy=p0.numpy(), init_hidden=h0.numpy(), init_value_scalar=sc(v0),
+                               rec_value=v1.numpy(), rec_reward=r1.numpy(), rec_policy=p1.numpy(), rec_hidden=h1.numpy(),
+                               rec_value_scalar=sc(v1), rec_reward_scalar=sc(r1))
+    del at_net
+    print("large-configuration network fixture written")
+
     # ---- FC network on the shipped CartPole checkpoint (the round-1 fixture only covered synthetic weights)
     cart_mod = load_reference_game("cartpole")
     cart_cfg = cart_mod.MuZeroConfig()

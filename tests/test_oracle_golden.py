@@ -43,6 +43,20 @@ def test_network_matches_reference_outputs(name, game_configs):
     assert (support_to_scalar(r0, S).numpy() == 0).all()
 
 
+def test_large_configuration_network_matches_reference_outputs(game_configs):
+    """games/atari.py: 131 stacked planes of 96x96, DownSample stem, 16 blocks x 256 channels, 601-bin heads."""
+    spec, net = _net("atari", game_configs)
+    g = golden_npz("net_atari.npz")
+    obs = numpy.random.RandomState(int(g["obs_seed"])).random_sample((2, spec.in_channels, 96, 96)).astype(numpy.float32)
+    v0, r0, p0, h0 = net.initial_inference(obs)
+    v1, r1, p1, h1 = net.recurrent_inference(h0, g["action"])
+    tol = dict(rtol=2e-5, atol=2e-6)
+    for got, key in ((v0, "init_value"), (p0, "init_policy"), (h0, "init_hidden"), (v1, "rec_value"), (r1, "rec_reward"),
+                     (p1, "rec_policy"), (h1, "rec_hidden")):
+        numpy.testing.assert_allclose(got.numpy(), g[key], err_msg=key, **tol)
+    numpy.testing.assert_allclose(support_to_scalar(v1, spec.support_size).numpy()[:, 0], g["rec_value_scalar"], rtol=1e-4, atol=1e-4)
+
+
 def test_support_to_scalar_kat():
     k = golden_json("kat.json")["support_to_scalar"]
     out = support_to_scalar(torch.tensor(k["logits"], dtype=torch.float32), 10)[:, 0]

@@ -102,6 +102,46 @@ def test_resnet_network_matches_reference(name, numerics, game_configs):
     eng.close()
 
 
+def test_large_configuration_runs_on_the_device(game_configs):
+    """games/atari.py: 32 stacked observations = 131 input planes of 96x96, DownSample stem with 128/256
+    channels (row-banded CUDA-core convolutions), 16 blocks x 256 channels, heads of 9216 -> 256 -> 256 -> 601 whose
+    weights (9.4 MB per first layer) take the generic heads route.  Network outputs against the reference's, and a
+    short search student-forced through the oracle tree."""
+    cfg = game_configs["atari"]
+    spec = netspec_from_config(cfg)
+    assert spec.in_channels == 131 and spec.full_support == 601
+    g = golden_npz("net_atari.npz")
+    obs = numpy.random.RandomState(int(g["obs_seed"])).random_sample((2, spec.in_channels, 96, 96)).astype(numpy.float32)
+    N = 6
+    eng = _engine(cfg, 2, N)
+    eng.load_weights(weights_for("atari", spec))
+    r0 = eng.initial_inference(obs)
+    _close("atari init hidden", r0["hidden"], g["init_hidden"].reshape(2, -1), "off", "hidden")
+    _close("atari init value logits", r0["value_logits"], g["init_value"], "off", "logits")
+    _close("atari init policy logits", r0["policy_logits"], g["init_policy"], "off", "logits")
+    numpy.testing.assert_allclose(r0["value"], g["init_value_scalar"], rtol=1e-3, atol=5e-3)
+    r1 = eng.recurrent_inference(g["init_hidden"].reshape(2, -1), g["action"])
+    _close("atari rec hidden", r1["hidden"], g["rec_hidden"].reshape(2, -1), "off", "hidden")
+    _close("atari rec value logits", r1["value_logits"], g["rec_value"], "off", "logits")
+    _close("atari rec reward logits", r1["reward_logits"], g["rec_reward"], "off", "logits")
+    _close("atari rec policy logits", r1["policy_logits"], g["rec_policy"], "off", "logits")
+    numpy.testing.assert_allclose(r1["reward"], g["rec_reward_scalar"], rtol=1e-3, atol=5e-3)
+    A = spec.action_space
+    rs = numpy.random.RandomState(3)
+    noise = rs.dirichlet([cfg.root_dirichlet_alpha] * A, size=2)
+    first = rs.randint(0, A, 2).astype(numpy.int32)
+    out = eng.search(obs=obs.reshape(2, -1), add_exploration_noise=True, noise=noise, first_index=first, trace=True)
+    params = om.SearchParams.from_config(cfg, N)
+    for i in range(2):
+        tr = out.trace
+        res, _ = oracle_replay(params, list(range(A)), 0,
+                               (out.root_predicted_value[i], tr["root_reward"][i], list(tr["root_priors_raw"][i])),
+                               [(tr["value"][i, s], tr["reward"][i, s], tr["priors"][i, s]) for s in range(N)],
+                               list(noise[i]), int(first[i]), seed=cfg.seed, game=i)
+        assert [int(v) for v in out.visit_counts[i]] == res.root_visits and out.root_value[i] == res.root_value
+    eng.close()
+
+
 @pytest.mark.parametrize("mode", ["large", "tiny", "overflow"])
 def test_tower_range_guard_on_stress_weights(mode, game_configs, monkeypatch):
     """Weights whose tower activations reach ~1e4 ("large"), sit at ~1e-5 inside every block ("tiny") or exceed the fp16
