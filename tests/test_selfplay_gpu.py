@@ -145,3 +145,61 @@ def test_override_root_with_on_device(name, monkeypatch):
         numpy.testing.assert_allclose([root2.children[a].value_sum for a in case["root_actions"]], case["root_child_value_sums"],
                                       rtol=1e-3, atol=1e-3)
     worker.model.engine.close()
+
+
+def test_batched_reanalyse_on_device(monkeypatch):
+    """Reanalyse (replay_buffer.py:307-373) on the real engine: games played by continuous_self_play on the GPU are
+    re-evaluated in ONE batched mz_initial_inference; the values equal the oracle network's per-game computation, the
+    bulk priorities are attached, and the reference-shaped actor loop updates a buffer."""
+    import torch
+    monkeypatch.setenv("MZ_TC_MODE", "off")
+    from muzero_general_b200 import reanalyse as ra
+    from oracle.net import OracleNet, support_to_scalar
+    worker, cfg, sp = _worker("tictactoe", 2, num_parallel_games=6, num_simulations=8, training_steps=6, ratio=None)
+    spec = netspec_from_config(cfg)
+    w = weights_for("tictactoe", spec)
+
+    class Storage:
+        def __init__(self):
+            self.d = dict(weights=w, training_step=0, terminate=False, num_played_steps=0, num_played_games=0, num_reanalysed_games=0)
+        def get_info(self, k):
+            if k == "training_step":
+                self.d[k] += 2
+            return self.d[k]
+        def set_info(self, k, v=None):
+            self.d.update(k if isinstance(k, dict) else {k: v})
+
+    class Buffer:
+        def __init__(self):
+            self.buffer, self.updated = {}, set()
+        def save_game(self, gh, storage=None):
+            self.buffer[len(self.buffer)] = gh
+            if storage is not None:
+                storage.set_info("num_played_games", len(self.buffer))
+        def sample_game(self, force_uniform=False):
+            i = int(numpy.random.randint(len(self.buffer)))
+            return i, self.buffer[i], None
+        def update_game_history(self, game_id, gh):
+            self.updated.add(game_id); self.buffer[game_id] = gh
+
+    st, buf = Storage(), Buffer()
+    worker.continuous_self_play(st, buf)                       # a17 on the GPU engine (host loop, numpy draws)
+    games = list(buf.buffer.values())
+    assert len(games) >= 6
+    for gh in games:                                            # bulk PER ingest (replay_buffer.py:39-51)
+        gh.priorities, gh.game_priority = ra.initial_priorities(gh, cfg)
+        assert gh.priorities.shape == (len(gh.root_values),) and gh.game_priority == gh.priorities.max()
+    actor = ra.Reanalyse({"weights": w, "num_reanalysed_games": 0}, cfg, max_positions=32)
+    actor.reanalyse_games(games)
+    net = OracleNet(spec, w)
+    for gh in games:
+        T = len(gh.root_values)
+        obs = numpy.array([gh.get_stacked_observations(i, cfg.stacked_observations, 9) for i in range(T)], dtype=numpy.float32)
+        want = torch.squeeze(support_to_scalar(net.initial_inference(obs)[0], cfg.support_size)).numpy()
+        assert gh.reanalysed_predicted_root_values.shape == want.shape
+        numpy.testing.assert_allclose(gh.reanalysed_predicted_root_values, want, rtol=2e-4, atol=5e-4)
+    st.d["training_step"] = 0
+    actor.games_per_call = 4
+    actor.reanalyse(buf, st)
+    assert buf.updated and st.d["num_reanalysed_games"] > len(games)
+    actor.close(); worker.model.engine.close()
