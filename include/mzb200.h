@@ -290,8 +290,12 @@ typedef struct MzSelfPlayPeek {
 /* replaces the per-move body of SelfPlay.play_game / continuous_self_play for a whole batch (self_play.py:31-183) */
 int mz_selfplay_begin(MzHandle* h, const MzSelfPlayDesc* desc);
 int mz_selfplay_moves(MzHandle* h, int32_t n_moves, double temperature, const MzSelfPlayInject* inject, MzSelfPlayStats* stats);
-/* pointer to the staged games (pinned host memory owned by the library), valid until the next mz_selfplay_moves;
- * marks the area as consumed.  `index` (may be NULL) receives a table of n_games pairs of uint64:
+/* the same in two halves, so the host can work while the device plays: enqueue returns at once, wait synchronises */
+int mz_selfplay_enqueue(MzHandle* h, int32_t n_moves, double temperature);
+int mz_selfplay_wait(MzHandle* h, MzSelfPlayStats* stats);
+/* pointer to the staged games (pinned host memory owned by the library) and marks them consumed.  The library keeps
+ * two staging areas and swaps them here: the games returned stay intact during the NEXT mz_selfplay_moves / enqueue and
+ * are overwritten by the one after the next drain.  `index` (may be NULL) receives a table of n_games pairs of uint64:
  * {byte offset of the game's block, (slot << 32) | length}, so a consumer can address any game without walking. */
 int mz_selfplay_drain(MzHandle* h, const void** data, uint64_t* bytes, int32_t* n_games, const uint64_t** index);
 int mz_selfplay_peek(MzHandle* h, const MzSelfPlayPeek* out);

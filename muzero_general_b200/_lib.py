@@ -131,6 +131,8 @@ SYMBOLS = [
     ("mz_numerics", C.c_char_p, [C.c_void_p]),
     ("mz_selfplay_begin", C.c_int, [C.c_void_p, C.POINTER(MzSelfPlayDesc)]),
     ("mz_selfplay_moves", C.c_int, [C.c_void_p, C.c_int32, C.c_double, C.POINTER(MzSelfPlayInject), C.POINTER(MzSelfPlayStats)]),
+    ("mz_selfplay_enqueue", C.c_int, [C.c_void_p, C.c_int32, C.c_double]),
+    ("mz_selfplay_wait", C.c_int, [C.c_void_p, C.POINTER(MzSelfPlayStats)]),
     ("mz_selfplay_drain", C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64), C.POINTER(C.c_int32),
                                     C.POINTER(C.c_void_p)]),
     ("mz_selfplay_peek", C.c_int, [C.c_void_p, C.POINTER(MzSelfPlayPeek)]),

@@ -387,8 +387,14 @@ struct MzSelfPlay {
     MzSelfPlayDesc desc{};
     SpDev dev{};
     std::vector<void*> allocs;
-    unsigned char* staging = nullptr;          // pinned + mapped
-    unsigned long long* index = nullptr;       // pinned + mapped
+    // two staging areas (pinned + mapped) used alternately: while the host reads the games of call i, call i+1 writes the
+    // other one, so the copy on the host overlaps the next moves on the device
+    unsigned char* staging[2] = {nullptr, nullptr};
+    unsigned long long* index[2] = {nullptr, nullptr};
+    unsigned char* d_staging[2] = {nullptr, nullptr};       // device views of the same memory
+    unsigned long long* d_index[2] = {nullptr, nullptr};
+    int cur = 0;                               // area the next mz_selfplay_moves / enqueue writes
+    bool in_flight = false;                    // moves enqueued, not waited for yet
     unsigned long long* h_counters = nullptr;  // pinned copy of the counters
     int32_t* d_forced = nullptr;
     double* d_uniform = nullptr;
@@ -402,8 +408,10 @@ void mz_selfplay_destroy(MzHandle* h) {
     if (!h || !h->sp) return;
     MzSelfPlay* sp = h->sp;
     for (void* p : sp->allocs) cudaFree(p);
-    if (sp->staging) cudaFreeHost(sp->staging);
-    if (sp->index) cudaFreeHost(sp->index);
+    for (int i = 0; i < 2; ++i) {
+        if (sp->staging[i]) cudaFreeHost(sp->staging[i]);
+        if (sp->index[i]) cudaFreeHost(sp->index[i]);
+    }
     if (sp->h_counters) cudaFreeHost(sp->h_counters);
     if (sp->e0) cudaEventDestroy(sp->e0);
     if (sp->e1) cudaEventDestroy(sp->e1);
@@ -465,20 +473,26 @@ extern "C" int mz_selfplay_begin(MzHandle* h, const MzSelfPlayDesc* d) {
     }
     if (cap < staged_block_bytes(d->max_moves, A, O)) { mz_selfplay_destroy(h); return fail(h, MZ_EINVAL, "mz_selfplay_begin: staging_bytes smaller than one game"); }
     const unsigned long long index_entries = cap / staged_block_bytes(1, A, O) + 1;
-    if (cudaHostAlloc(reinterpret_cast<void**>(&sp->staging), cap, cudaHostAllocMapped) != cudaSuccess ||
-        cudaHostAlloc(reinterpret_cast<void**>(&sp->index), index_entries * 16, cudaHostAllocMapped) != cudaSuccess ||
-        cudaHostAlloc(reinterpret_cast<void**>(&sp->h_counters), 64, cudaHostAllocDefault) != cudaSuccess) {
+    bool pinned = cudaHostAlloc(reinterpret_cast<void**>(&sp->h_counters), 64, cudaHostAllocDefault) == cudaSuccess;
+    for (int i = 0; i < 2 && pinned; ++i)
+        pinned = cudaHostAlloc(reinterpret_cast<void**>(&sp->staging[i]), cap, cudaHostAllocMapped) == cudaSuccess &&
+                 cudaHostAlloc(reinterpret_cast<void**>(&sp->index[i]), index_entries * 16, cudaHostAllocMapped) == cudaSuccess;
+    if (!pinned) {
         (void)cudaGetLastError();
         mz_selfplay_destroy(h);
         return fail(h, MZ_ENOMEM, "mz_selfplay_begin: pinned staging allocation failed");
     }
     memset(sp->h_counters, 0, 64);
-    void* dptr = nullptr;
-    if (cudaHostGetDevicePointer(&dptr, sp->staging, 0) != cudaSuccess) { mz_selfplay_destroy(h); return fail(h, MZ_ECUDA, "mz_selfplay_begin: staging is not device-mappable"); }
-    s.staging = reinterpret_cast<unsigned char*>(dptr);
+    for (int i = 0; i < 2; ++i) {
+        void* dptr = nullptr;
+        if (cudaHostGetDevicePointer(&dptr, sp->staging[i], 0) != cudaSuccess) { mz_selfplay_destroy(h); return fail(h, MZ_ECUDA, "mz_selfplay_begin: staging is not device-mappable"); }
+        sp->d_staging[i] = reinterpret_cast<unsigned char*>(dptr);
+        if (cudaHostGetDevicePointer(&dptr, sp->index[i], 0) != cudaSuccess) { mz_selfplay_destroy(h); return fail(h, MZ_ECUDA, "mz_selfplay_begin: index is not device-mappable"); }
+        sp->d_index[i] = reinterpret_cast<unsigned long long*>(dptr);
+    }
+    s.staging = sp->d_staging[0];
+    s.index = sp->d_index[0];
     s.staging_cap = cap;
-    if (cudaHostGetDevicePointer(&dptr, sp->index, 0) != cudaSuccess) { mz_selfplay_destroy(h); return fail(h, MZ_ECUDA, "mz_selfplay_begin: index is not device-mappable"); }
-    s.index = reinterpret_cast<unsigned long long*>(dptr);
     cudaEventCreate(&sp->e0); cudaEventCreate(&sp->e1);
     selfplay_reset_kernel<<<(B + 127) / 128, 128, 0, h->stream>>>(s, d->first_game_id);
     h->launches += 1;
@@ -503,16 +517,19 @@ static int sp_read_counters(MzHandle* h, MzSelfPlayStats* stats, float ms) {
     return MZ_OK;
 }
 
-extern "C" int mz_selfplay_moves(MzHandle* h, int32_t n_moves, double temperature, const MzSelfPlayInject* inj, MzSelfPlayStats* stats) {
-    if (!h || !h->sp) return fail(h, MZ_ESTATE, "mz_selfplay_moves: call mz_selfplay_begin first");
-    if (!h->weights_loaded) return fail(h, MZ_ESTATE, "mz_selfplay_moves: weights not loaded");
-    if (n_moves < 0) return fail(h, MZ_EINVAL, "mz_selfplay_moves: n_moves < 0");
+static int sp_enqueue(MzHandle* h, int32_t n_moves, double temperature, const MzSelfPlayInject* inj, const char* who) {
+    if (!h || !h->sp) return fail(h, MZ_ESTATE, std::string(who) + ": call mz_selfplay_begin first");
+    if (!h->weights_loaded) return fail(h, MZ_ESTATE, std::string(who) + ": weights not loaded");
+    if (n_moves < 0) return fail(h, MZ_EINVAL, std::string(who) + ": n_moves < 0");
     if (inj && n_moves > 1 && (inj->forced_action || inj->uniform || inj->noise || inj->first_index))
-        return fail(h, MZ_EINVAL, "mz_selfplay_moves: per-move overrides need n_moves == 1");
-    if (!(temperature >= 0.0)) return fail(h, MZ_EINVAL, "mz_selfplay_moves: temperature must be >= 0");
-    MZ_CUDA(h, cudaSetDevice(h->device));
+        return fail(h, MZ_EINVAL, std::string(who) + ": per-move overrides need n_moves == 1");
+    if (!(temperature >= 0.0)) return fail(h, MZ_EINVAL, std::string(who) + ": temperature must be >= 0");
     MzSelfPlay* sp = h->sp;
+    if (sp->in_flight) return fail(h, MZ_ESTATE, std::string(who) + ": moves already enqueued, call mz_selfplay_wait first");
+    MZ_CUDA(h, cudaSetDevice(h->device));
     SpDev s = sp->dev;
+    s.staging = sp->d_staging[sp->cur];
+    s.index = sp->d_index[sp->cur];
     const int B = s.B, A = s.A;
     s.temperature = temperature;
     s.forced_action = nullptr; s.uniform = nullptr;
@@ -525,7 +542,8 @@ extern "C" int mz_selfplay_moves(MzHandle* h, int32_t n_moves, double temperatur
         if (inj->first_index) { MZ_CUDA(h, cudaMemcpyAsync(sp->d_first, inj->first_index, (size_t)B * 4, cudaMemcpyHostToDevice, h->stream)); first = sp->d_first; }
     }
     if (sp->drained_bytes) {
-        // the host has consumed the staged games: rewind the cursor (parked games are packed by the first move below)
+        // the host has taken the staged games (and the areas were swapped): rewind the cursor; parked games are packed
+        // by the first pass below
         MZ_CUDA(h, cudaMemsetAsync(s.counters + 2, 0, 16, h->stream));
         MZ_CUDA(h, cudaMemsetAsync(s.counters + 5, 0, 8, h->stream));
         sp->drained_bytes = 0;
@@ -550,11 +568,18 @@ extern "C" int mz_selfplay_moves(MzHandle* h, int32_t n_moves, double temperatur
     }
     MZ_CUDA(h, cudaGetLastError());
     MZ_CUDA(h, cudaEventRecord(sp->e1, h->stream));
+    sp->in_flight = true;
+    return MZ_OK;
+}
+
+static int sp_wait(MzHandle* h, MzSelfPlayStats* stats) {
+    MzSelfPlay* sp = h->sp;
     int rc = sp_read_counters(h, stats, 0.0f);
     if (rc) return rc;
+    sp->in_flight = false;
     if (h->res && resnet_take_saturations(h->res, h->stream) > 0) {
         // the moves above searched with towers outside their accuracy contract (activations beyond the fp16 range are
-        // carried at bf16 precision, not clipped); later calls use the fp32 towers
+        // carried with a saturated high part, not dropped); later calls use the fp32 towers
         mz_switch_to_strict(h);
     }
     float ms = 0.0f;
@@ -562,17 +587,41 @@ extern "C" int mz_selfplay_moves(MzHandle* h, int32_t n_moves, double temperatur
     return MZ_OK;
 }
 
+extern "C" int mz_selfplay_moves(MzHandle* h, int32_t n_moves, double temperature, const MzSelfPlayInject* inj, MzSelfPlayStats* stats) {
+    int rc = sp_enqueue(h, n_moves, temperature, inj, "mz_selfplay_moves");
+    if (rc) return rc;
+    return sp_wait(h, stats);
+}
+
+extern "C" int mz_selfplay_enqueue(MzHandle* h, int32_t n_moves, double temperature) {
+    return sp_enqueue(h, n_moves, temperature, nullptr, "mz_selfplay_enqueue");
+}
+
+extern "C" int mz_selfplay_wait(MzHandle* h, MzSelfPlayStats* stats) {
+    if (!h || !h->sp) return fail(h, MZ_ESTATE, "mz_selfplay_wait: call mz_selfplay_begin first");
+    if (!h->sp->in_flight) return fail(h, MZ_ESTATE, "mz_selfplay_wait: nothing enqueued");
+    MZ_CUDA(h, cudaSetDevice(h->device));
+    return sp_wait(h, stats);
+}
+
 extern "C" int mz_selfplay_drain(MzHandle* h, const void** data, uint64_t* bytes, int32_t* n_games, const uint64_t** index) {
     if (!h || !h->sp || !data || !bytes || !n_games) return fail(h, MZ_EINVAL, "mz_selfplay_drain: bad argument");
     MzSelfPlay* sp = h->sp;
+    if (sp->in_flight) return fail(h, MZ_ESTATE, "mz_selfplay_drain: moves in flight, call mz_selfplay_wait first");
     MZ_CUDA(h, cudaSetDevice(h->device));
     int rc = sp_read_counters(h, nullptr, 0.0f);
     if (rc) return rc;
-    *data = sp->staging;
-    if (index) *index = reinterpret_cast<const uint64_t*>(sp->index);
+    *data = sp->staging[sp->cur];
+    if (index) *index = reinterpret_cast<const uint64_t*>(sp->index[sp->cur]);
     *bytes = sp->h_counters[5];
     *n_games = (int32_t)sp->h_counters[3];
-    sp->drained_bytes = sp->h_counters[2];             // the cursor moved (valid or void reservations): rewind it next call
+    if (sp->h_counters[2]) {
+        // the cursor moved (valid or void reservations): the next call rewinds it and writes the OTHER area, so what is
+        // returned here stays intact while those moves run
+        sp->drained_bytes = sp->h_counters[2];
+        sp->cur ^= 1;
+        sp->h_counters[2] = sp->h_counters[3] = sp->h_counters[5] = 0;     // a second drain before new moves returns nothing
+    }
     return MZ_OK;
 }
 

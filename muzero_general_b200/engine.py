@@ -387,17 +387,37 @@ class DeviceSelfPlayLoop:
                                             C.byref(inj) if inj is not None else None, C.byref(self.stats)))
         return self.stats
 
-    def drain(self):
-        """(bytes, index) of the staged finished games - copies, the staging area is reused by the next call.
-        ``index`` is an ``[n, 2]`` uint64 array: byte offset of each game's block, ``(slot << 32) | length``."""
+    def enqueue(self, n_moves: int, temperature: float):
+        """Start ``n_moves`` moves without waiting (``mz_selfplay_enqueue``); pair with ``wait``."""
+        eng = self.engine
+        eng._check(eng.lib.mz_selfplay_enqueue(eng._h, int(n_moves), float(temperature)))
+
+    def wait(self):
+        eng = self.engine
+        eng._check(eng.lib.mz_selfplay_wait(eng._h, C.byref(self.stats)))
+        return self.stats
+
+    def drain_pointers(self):
+        """(data address, bytes, games, index address) of the staged games, zero-copy.  The library swaps its two staging
+        areas here, so the memory stays intact while the next moves run; copy it before the drain after that."""
         eng = self.engine
         ptr, nbytes, ngames, iptr = C.c_void_p(), C.c_uint64(), C.c_int32(), C.c_void_p()
         eng._check(eng.lib.mz_selfplay_drain(eng._h, C.byref(ptr), C.byref(nbytes), C.byref(ngames), C.byref(iptr)))
-        n = int(ngames.value)
+        return ptr.value, int(nbytes.value), int(ngames.value), iptr.value
+
+    @staticmethod
+    def copy_staged(pointers):
+        """``drain_pointers()`` -> (bytes, index[n, 2] uint64) copies."""
+        ptr, nbytes, n, iptr = pointers
         if n == 0:
             return b"", numpy.zeros((0, 2), numpy.uint64)
-        index = numpy.frombuffer(C.string_at(iptr.value, 16 * n), numpy.uint64).reshape(n, 2)
-        return C.string_at(ptr.value, nbytes.value), index
+        index = numpy.frombuffer(C.string_at(iptr, 16 * n), numpy.uint64).reshape(n, 2)
+        return C.string_at(ptr, nbytes), index
+
+    def drain(self):
+        """(bytes, index) of the staged finished games - copies.
+        ``index`` is an ``[n, 2]`` uint64 array: byte offset of each game's block, ``(slot << 32) | length``."""
+        return self.copy_staged(self.drain_pointers())
 
     def peek(self):
         eng = self.engine

@@ -709,21 +709,42 @@ class DeviceBatchedSelfPlay:
         (parked slots) and arrives with the next drain - nothing is lost."""
         out = PackedGames(self.obs_shape, self.obs_dtype, self.reward_type)
         left = int(n_moves)
-        while left > 0:
-            k = 1 if inject else min(left, self.chunk)
-            st = self.loop.moves(k, temperature, **inject)
-            self.device_ms += st.device_ms
-            self.calls += 1
-            # next chunk: as many moves as fill about half of the staging area at the rate just seen
-            if st.parked_slots:
-                self.chunk = max(1, self.chunk // 2)
-            elif st.staged_bytes > 0:
-                self.chunk = max(1, min(self.moves_per_call, int(0.5 * st.staging_capacity * k / st.staged_bytes)))
+        if inject:                                   # parity / debug: one synchronous move with injected draws
+            while left > 0:
+                st = self.loop.moves(1, temperature, **inject)
+                self._account(st, 1)
+                out.add(*self.loop.drain())
+                left -= 1
+            return out
+        # pipelined: while the host copies the games of chunk i out of one staging area, the device plays chunk i+1
+        # into the other one (mz_selfplay_enqueue / wait; the library swaps the areas at every drain)
+        k = min(left, self.chunk)
+        self.loop.enqueue(k, temperature)
+        left -= k
+        while True:
+            st = self.loop.wait()
+            self._account(st, k)
+            pointers = self.loop.drain_pointers()
+            if left > 0:
+                k = min(left, self.chunk)
+                self.loop.enqueue(k, temperature)
+                left -= k
+                out.add(*self.loop.copy_staged(pointers))
             else:
-                self.chunk = min(self.moves_per_call, 2 * self.chunk)
-            out.add(*self.loop.drain())
-            left -= k
+                out.add(*self.loop.copy_staged(pointers))
+                break
         return out
+
+    def _account(self, st, k):
+        self.device_ms += st.device_ms
+        self.calls += 1
+        # next chunk: as many moves as fill about half of a staging area at the rate just seen
+        if st.parked_slots:
+            self.chunk = max(1, self.chunk // 2)
+        elif st.staged_bytes > 0:
+            self.chunk = max(1, min(self.moves_per_call, int(0.5 * st.staging_capacity * k / st.staged_bytes)))
+        else:
+            self.chunk = min(self.moves_per_call, 2 * self.chunk)
 
 
 class PackedGames:
