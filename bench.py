@@ -566,13 +566,26 @@ def main():
     torch.cuda.set_device(local_rank)
     D = Dist(dist, torch.device("cuda", local_rank))
 
+    import faulthandler
+    # a rank that is still here after 10 minutes writes its Python stack to stderr (and keeps going): a hung collective
+    # then shows where every rank sits instead of an empty log
+    faulthandler.dump_traceback_later(float(os.environ.get("MZ_BENCH_WATCHDOG", "600")), repeat=True, exit=False)
+
+    def note(msg):
+        if rank == 0:
+            sys.stderr.write(f"[bench {time.strftime('%H:%M:%S')}] {msg}\n")
+            sys.stderr.flush()
+
+    note(f"{args.workload} ...")
     head = run_workload(args.workload, args, D, rank, local_rank, world, with_loop=not args.no_loop, headline=True)
+    note(f"{args.workload}: {head['value']:.0f} env-steps/s, loop {(head.get('loop') or {}).get('value')}")
     extras = {}
     names = [] if args.no_extras else (args.extras.split(",") if args.extras else DEFAULT_EXTRAS)
     for nme in names:
         if not nme or nme == args.workload:
             continue
         try:
+            note(f"{nme} ...")
             extras[nme] = run_workload(nme, args, D, rank, local_rank, world,
                                        with_loop=(not args.no_loop and "@" not in nme), headline=False)
         except Exception as e:
@@ -605,6 +618,7 @@ def main():
                                    "sample": f"{searches} batch-1 MCTS.run calls (N={N}) in {w:.1f}s on {arm.cores} processes, "
                                              "one pinned per physical core"}
         print(json.dumps(out))
+    faulthandler.cancel_dump_traceback_later()
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()

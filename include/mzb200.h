@@ -247,7 +247,8 @@ typedef struct MzSelfPlayDesc {
     int64_t first_game_id;        /* slot g plays the global games first_game_id + g + k * game_id_stride, k = 0, 1, ... */
     int64_t game_id_stride;       /* 0 = max_games; world_size * max_games keeps ids unique across ranks */
     uint64_t staging_bytes;       /* capacity of the finished-game staging area, 0 = library default (4x the bytes of
-                                     every slot finishing a maximum-length game at once, within [32 MiB, 256 MiB]) */
+                                     every slot finishing a maximum-length game at once, within [16 MiB, 64 MiB];
+                                     the library keeps two such areas) */
 } MzSelfPlayDesc;
 
 /* Optional per-move overrides (HOST pointers, n = max_games; only with n_moves == 1).  Parity tests drive the

@@ -462,14 +462,16 @@ extern "C" int mz_selfplay_begin(MzHandle* h, const MzSelfPlayDesc* d) {
               sp_alloc(sp, &sp->d_forced, B) && sp_alloc(sp, &sp->d_uniform, B) && sp_alloc(sp, &sp->d_noise, (size_t)B * A) &&
               sp_alloc(sp, &sp->d_first, B);
     if (!ok) { mz_selfplay_destroy(h); return fail(h, MZ_ENOMEM, "mz_selfplay_begin: out of device memory"); }
-    // staging: by default 4x the room for every slot finishing a maximum-length game at once, within [32, 256] MiB;
+    // staging (two areas of this size): by default 4x the room for every slot finishing a maximum-length game at once,
+    // within [16, 64] MiB;
     // whatever the size, games that do not fit wait in their slots (parked) - nothing is dropped
     unsigned long long cap = d->staging_bytes;
     const unsigned long long worst = staged_block_bytes(d->max_moves, A, O) * (unsigned long long)B;
     if (cap == 0) {
         cap = 4 * worst;
-        if (cap < (32ull << 20)) cap = 32ull << 20;
-        if (cap > (256ull << 20)) cap = 256ull << 20;
+        if (cap < (16ull << 20)) cap = 16ull << 20;
+        if (cap > (64ull << 20)) cap = 64ull << 20;
+        if (cap < staged_block_bytes(d->max_moves, A, O)) cap = staged_block_bytes(d->max_moves, A, O);
     }
     if (cap < staged_block_bytes(d->max_moves, A, O)) { mz_selfplay_destroy(h); return fail(h, MZ_EINVAL, "mz_selfplay_begin: staging_bytes smaller than one game"); }
     const unsigned long long index_entries = cap / staged_block_bytes(1, A, O) + 1;
