@@ -246,6 +246,14 @@ typedef struct MzSelfPlayDesc {
     int32_t reward_scale;         /* board games: reward of the winning move (tictactoe.py:144: 20, connect4.py:144: 10) */
     int64_t first_game_id;        /* slot g plays the global games first_game_id + g + k * game_id_stride, k = 0, 1, ... */
     int64_t game_id_stride;       /* 0 = max_games; world_size * max_games keeps ids unique across ranks */
+    /* Initial prioritised-replay priorities |root_value - n-step target| ** PER_alpha of every position of a finished
+     * game (ReplayBuffer.save_game + compute_target_value, replay_buffer.py:33-51,230-262), evaluated by the warp that packs
+     * the game.  td_steps = 0: not computed.  discount_pow[k] = config.discount ** k for k = 0..td_steps, computed by the
+     * caller (Python's own pow, so the products are the reference's); per_alpha must be 0.5 or 1 (an exact sqrt / identity). */
+    int32_t td_steps;
+    int32_t reserved;
+    double per_alpha;
+    const double* discount_pow;
     uint64_t staging_bytes;       /* capacity of the finished-game staging area, 0 = library default (4x the bytes of
                                      every slot finishing a maximum-length game at once, within [16 MiB, 64 MiB];
                                      the library keeps two such areas) */
@@ -284,7 +292,7 @@ typedef struct MzSelfPlayPeek {
 /* Staged games are self-describing blocks laid out back to back (all little endian, 8-byte aligned):
  *   int64 game_id; int32 slot; int32 length T; int32 first_to_play; int32 obs_elems O; int32 actions A; int32 bytes;
  *   double root_value[T]; int32 visit_counts[T][A]; int32 action[T]; float reward[T]; int32 to_play[T] (after the move);
- *   float observation[T+1][O] (index 0 = reset observation); padding to 8 bytes.
+ *   float priority[T] (zeros unless td_steps > 0); float observation[T+1][O] (index 0 = reset observation); padding to 8.
  * = the fields of GameHistory (self_play.py:479-511) minus the dummy first entries. */
 #define MZ_STAGED_HEADER_BYTES 32
 

@@ -32,6 +32,9 @@ struct SpDev {
     int env, B, A, O, H, W, K, max_moves, threshold, reward_scale;
     uint64_t seed;
     int64_t id_stride;         // a slot's next game id = current + id_stride
+    int td_steps;              // > 0: PER priorities are computed while packing (replay_buffer.py:33-51)
+    double per_alpha;
+    const double* discount_pow;   // [td_steps + 1] discount ** k as the caller's language evaluates it
     // environment state
     double* cart;              // [B][4]
     int* cart_steps;           // [B]
@@ -288,9 +291,34 @@ __host__ __device__ inline unsigned long long staged_block_bytes(int T, int A, i
     unsigned long long b = MZ_STAGED_HEADER_BYTES;
     b += (unsigned long long)T * 8;                 // root_value
     b += (unsigned long long)T * A * 4;             // visit counts
-    b += (unsigned long long)T * 4 * 3;             // action, reward, to_play
+    b += (unsigned long long)T * 4 * 4;             // action, reward, to_play, priority
     b += (unsigned long long)(T + 1) * O * 4;       // observations
     return (b + 7) & ~7ull;
+}
+
+// ReplayBuffer.save_game's initial priority of position i of the finished game in slot g (replay_buffer.py:39-51 with
+// compute_target_value, :230-262), in the reference's operation order on fp64:
+//   value = (+/-)root_value[i + td] * discount**td           if i + td < T, else 0
+//   value += (+/-)reward_history[i + 1 + k] * discount**k    for k = 0 .. td - 1 while i + 1 + k <= T
+//   priority = |root_value[i] - value| ** alpha
+// reward_history[j + 1] = the reward of move j; to_play_history[0] = first_to_play, [j + 1] = to_play after move j.
+MZ_DEVINL float initial_priority(const SpDev& s, int g, int T, int i) {
+    const size_t r = (size_t)g * s.max_moves;
+    auto to_play_hist = [&](int j) { return j == 0 ? s.first_to_play[g] : s.rec_to_play[r + j - 1]; };
+    const int td = s.td_steps;
+    const int me = to_play_hist(i);
+    double value = 0.0;
+    if (i + td < T) {
+        const double last = to_play_hist(i + td) == me ? s.rec_root[r + i + td] : -s.rec_root[r + i + td];
+        value = __dmul_rn(last, s.discount_pow[td]);
+    }
+    for (int k = 0; k < td && i + k < T; ++k) {
+        const double rew = (double)s.rec_reward[r + i + k];
+        const double signed_rew = to_play_hist(i + k) == me ? rew : -rew;
+        value = __dadd_rn(value, __dmul_rn(signed_rew, s.discount_pow[k]));
+    }
+    const double d = fabs(__dsub_rn(s.rec_root[r + i], value));
+    return (float)(s.per_alpha == 1.0 ? d : __dsqrt_rn(d));
 }
 
 // One warp per slot, 32 slots per CTA.  act != 0: lane 0 plays the slot's move (sampling, environment step, record)
@@ -366,6 +394,9 @@ __global__ void __launch_bounds__(kStepThreads) selfplay_step_kernel(const SpDev
                 p += (size_t)T * 4;
                 d = reinterpret_cast<int32_t*>(p);
                 for (int i = lane; i < T; i += 32) d[i] = s.rec_to_play[r + i];
+                p += (size_t)T * 4;
+                f = reinterpret_cast<float*>(p);
+                for (int i = lane; i < T; i += 32) f[i] = s.td_steps > 0 ? initial_priority(s, g, T, i) : 0.0f;
                 p += (size_t)T * 4;
                 f = reinterpret_cast<float*>(p);
                 const float* src = s.rec_obs + (size_t)g * (s.max_moves + 1) * s.O;
@@ -451,6 +482,17 @@ extern "C" int mz_selfplay_begin(MzHandle* h, const MzSelfPlayDesc* d) {
     s.env = d->env; s.B = B; s.A = A; s.O = O; s.H = H; s.W = W; s.K = K; s.max_moves = d->max_moves;
     s.threshold = d->temperature_threshold; s.reward_scale = d->reward_scale; s.seed = h->search.seed;
     s.id_stride = d->game_id_stride > 0 ? d->game_id_stride : B;
+    s.td_steps = 0; s.per_alpha = 1.0; s.discount_pow = nullptr;
+    if (d->td_steps > 0) {
+        if (!d->discount_pow || !(d->per_alpha == 0.5 || d->per_alpha == 1.0)) {
+            mz_selfplay_destroy(h);
+            return fail(h, MZ_EUNSUPPORTED, "mz_selfplay_begin: device priorities need discount_pow and per_alpha of 0.5 or 1");
+        }
+        double* dp = nullptr;
+        if (!sp_alloc(sp, &dp, (size_t)d->td_steps + 1)) { mz_selfplay_destroy(h); return fail(h, MZ_ENOMEM, "mz_selfplay_begin: out of device memory"); }
+        MZ_CUDA(h, cudaMemcpy(dp, d->discount_pow, ((size_t)d->td_steps + 1) * 8, cudaMemcpyHostToDevice));
+        s.td_steps = d->td_steps; s.per_alpha = d->per_alpha; s.discount_pow = dp;
+    }
     const size_t T = (size_t)d->max_moves;
     bool ok = sp_alloc(sp, &s.cart, (size_t)B * 4) && sp_alloc(sp, &s.cart_steps, B) && sp_alloc(sp, &s.board, (size_t)B * kMaxCells) &&
               sp_alloc(sp, &s.player, B) && sp_alloc(sp, &s.obs, (size_t)B * O) && sp_alloc(sp, &s.legal, (size_t)B * A) &&

@@ -358,7 +358,8 @@ class DeviceSelfPlayLoop:
     ENVS = {"cartpole": _lib.MZ_ENV_CARTPOLE, "tictactoe": _lib.MZ_ENV_TICTACTOE, "connect4": _lib.MZ_ENV_CONNECT4}
 
     def __init__(self, engine: SearchEngine, env: str, max_moves: int, temperature_threshold=None, reward_scale: int = 1,
-                 first_game_id: int = 0, staging_bytes: int = 0, game_id_stride: int = 0):
+                 first_game_id: int = 0, staging_bytes: int = 0, game_id_stride: int = 0, td_steps: int = 0,
+                 per_alpha: float = 1.0, discount: float = 1.0):
         if env not in self.ENVS:
             raise NotImplementedError(f"no device-resident environment for {env!r}")
         self.engine = engine
@@ -369,6 +370,12 @@ class DeviceSelfPlayLoop:
         d.reward_scale = int(reward_scale)
         d.first_game_id = int(first_game_id)
         d.game_id_stride = int(game_id_stride)
+        if td_steps and per_alpha in (0.5, 1, 1.0):
+            # PER priorities on the device: discount ** k evaluated HERE, with Python's pow, like replay_buffer.py:246,260
+            self._discount_pow = (C.c_double * (int(td_steps) + 1))(*[discount ** k for k in range(int(td_steps) + 1)])
+            d.td_steps, d.per_alpha = int(td_steps), float(per_alpha)
+            d.discount_pow = C.cast(self._discount_pow, C.c_void_p)
+        self.with_priorities = bool(d.td_steps)
         d.staging_bytes = int(staging_bytes)
         engine._check(engine.lib.mz_selfplay_begin(engine._h, C.byref(d)))
         self.stats = _lib.MzSelfPlayStats()
@@ -443,9 +450,10 @@ def parse_staged_game(buf: bytes, off: int):
     action = numpy.frombuffer(buf, numpy.int32, T, p); p += 4 * T
     reward = numpy.frombuffer(buf, numpy.float32, T, p); p += 4 * T
     to_play = numpy.frombuffer(buf, numpy.int32, T, p); p += 4 * T
+    priority = numpy.frombuffer(buf, numpy.float32, T, p); p += 4 * T
     obs = numpy.frombuffer(buf, numpy.float32, (T + 1) * O, p).reshape(T + 1, O)
     return dict(game_id=gid, slot=slot, length=T, first_to_play=first_to_play, root_value=root, visits=visits,
-                action=action, reward=reward, to_play=to_play, obs=obs, bytes=nbytes)
+                action=action, reward=reward, to_play=to_play, priority=priority, obs=obs, bytes=nbytes)
 
 
 def parse_staged_games(buf: bytes, index):

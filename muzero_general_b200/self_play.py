@@ -339,12 +339,16 @@ class PackedGameHistory(GameHistory):
 
     _LISTS = ("observation_history", "action_history", "reward_history", "to_play_history", "child_visits", "root_values")
 
-    def __init__(self, packed, obs_shape, obs_dtype, reward_type):
+    def __init__(self, packed, obs_shape, obs_dtype, reward_type, with_priorities=False):
         # deliberately NOT calling GameHistory.__init__: the six lists stay absent until asked for
         self.__dict__["_packed"] = (packed, tuple(obs_shape), obs_dtype, reward_type)
         self.reanalysed_predicted_root_values = None
         self.priorities = None
         self.game_priority = None
+        if with_priorities:
+            # computed by the packing warp on the device (replay_buffer.py:39-51): save_game keeps them as they are
+            self.priorities = packed["priority"].copy()
+            self.game_priority = numpy.max(self.priorities)
 
     def __len__(self):
         return int(self._packed[0]["length"])
@@ -696,6 +700,8 @@ class DeviceBatchedSelfPlay:
                                        temperature_threshold=temperature_threshold,
                                        reward_scale=getattr(vec, "REWARD_SCALE", 1),
                                        first_game_id=worker.first_game_id, game_id_stride=worker.game_id_stride,
+                                       td_steps=int(cfg.td_steps) if getattr(cfg, "PER", False) and getattr(cfg, "device_priorities", True) else 0,
+                                       per_alpha=cfg.PER_alpha, discount=cfg.discount,
                                        staging_bytes=int(getattr(cfg, "selfplay_staging_bytes", 0) or 0))
         self.moves_per_call = int(getattr(cfg, "selfplay_moves_per_call", 64) or 64)   # upper bound of a chunk
         self.chunk = min(4, self.moves_per_call)                                      # adapted to the staging fill below
@@ -707,7 +713,7 @@ class DeviceBatchedSelfPlay:
         in chunks of ``moves_per_call`` per ``mz_selfplay_moves`` (one host synchronisation and one drain per chunk);
         if a chunk ever produces more finished games than the staging area holds, the surplus waits on the device
         (parked slots) and arrives with the next drain - nothing is lost."""
-        out = PackedGames(self.obs_shape, self.obs_dtype, self.reward_type)
+        out = PackedGames(self.obs_shape, self.obs_dtype, self.reward_type, self.loop.with_priorities)
         left = int(n_moves)
         if inject:                                   # parity / debug: one synchronous move with injected draws
             while left > 0:
@@ -753,8 +759,8 @@ class PackedGames:
     handing thousands of games per second to a consumer costs nothing per game until the consumer looks at them
     (bulk ingest with lazily materialised histories)."""
 
-    def __init__(self, obs_shape, obs_dtype, reward_type):
-        self._args = (obs_shape, obs_dtype, reward_type)
+    def __init__(self, obs_shape, obs_dtype, reward_type, with_priorities=False):
+        self._args = (obs_shape, obs_dtype, reward_type, with_priorities)
         self._chunks = []            # (bytes, index[n, 2])
         self._n = 0
         self.total_moves = 0

@@ -238,6 +238,14 @@ def test_selfplay_api_on_the_device_loop(name, monkeypatch):
         assert gh.get_stacked_observations(-1, 0, len(cfg.action_space)).shape == tuple(cfg.observation_shape)
         plain = pickle.loads(pickle.dumps(gh))
         assert type(plain) is sp.GameHistory and plain.child_visits == gh.child_visits
+        # PER priorities computed by the packing warp == the reference's save_game loop (restated in reanalyse.py and
+        # pinned bit for bit to the unmodified ReplayBuffer in tests/test_reanalyse_cpu.py); alpha = 0.5 is an exact sqrt
+        # on the device and numpy's pow on the host: one float32 ulp of slack
+        from muzero_general_b200 import reanalyse as ra
+        want, top = ra.initial_priorities(gh, cfg)
+        assert gh.priorities.dtype == numpy.float32 and gh.priorities.shape == want.shape
+        numpy.testing.assert_allclose(gh.priorities, want, rtol=2e-7, atol=0)
+        assert gh.game_priority == gh.priorities.max()
         if name == "tictactoe":
             assert gh.observation_history[0].dtype == numpy.int32 and isinstance(gh.reward_history[-1], int)
 
