@@ -490,6 +490,7 @@ def selfplay_loop(game, B, N, device, rank, world, D):
            "path": worker.loop_path,
            "device_seconds": (dl.device_ms - dev0) / 1000.0 if dl is not None else None,
            "library_calls": (dl.calls - calls0) if dl is not None else None,
+           "parked_events": dl.parked_events if dl is not None else None,
            "includes": "search + environment step + root noise + action sampling + GameHistory hand-over, per move"}
     worker.close()
     return res

@@ -707,6 +707,7 @@ class DeviceBatchedSelfPlay:
         self.chunk = min(4, self.moves_per_call)                                      # adapted to the staging fill below
         self.device_ms = 0.0          # device time of all mz_selfplay_moves calls so far
         self.calls = 0
+        self.parked_events = 0        # finished games that had to wait for a drain (staging area full), so far
 
     def moves(self, n_moves, temperature, **inject):
         """``n_moves`` lockstep moves -> ``PackedGames`` (a lazy sequence of the games that finished).  The moves run
@@ -744,13 +745,16 @@ class DeviceBatchedSelfPlay:
     def _account(self, st, k):
         self.device_ms += st.device_ms
         self.calls += 1
-        # next chunk: as many moves as fill about half of a staging area at the rate just seen
+        self.parked_events += int(st.parked_slots)
+        # next chunk: as many moves as fill about half of a staging area at the rate just seen, growing at most 2x per
+        # call (the first finishes of a fresh batch arrive in a burst after a quiet start: one sample says little)
         if st.parked_slots:
             self.chunk = max(1, self.chunk // 2)
-        elif st.staged_bytes > 0:
-            self.chunk = max(1, min(self.moves_per_call, int(0.5 * st.staging_capacity * k / st.staged_bytes)))
         else:
-            self.chunk = min(self.moves_per_call, 2 * self.chunk)
+            grow = min(self.moves_per_call, 2 * max(k, 1))
+            if st.staged_bytes > 0:
+                grow = min(grow, int(0.5 * st.staging_capacity * k / st.staged_bytes))
+            self.chunk = max(1, grow)
 
 
 class PackedGames:

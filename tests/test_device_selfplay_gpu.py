@@ -234,7 +234,7 @@ def test_selfplay_api_on_the_device_loop(name, monkeypatch):
         assert gh.action_history[0] == 0 and gh.reward_history[0] == 0
         assert gh.observation_history[0].shape == tuple(cfg.observation_shape)
         assert all(abs(sum(c) - 1) < 1e-12 for c in gh.child_visits)
-        assert isinstance(gh.root_values[0], float) and gh.priorities is None
+        assert isinstance(gh.root_values[0], float) and gh.priorities is not None
         assert gh.get_stacked_observations(-1, 0, len(cfg.action_space)).shape == tuple(cfg.observation_shape)
         plain = pickle.loads(pickle.dumps(gh))
         assert type(plain) is sp.GameHistory and plain.child_visits == gh.child_visits
