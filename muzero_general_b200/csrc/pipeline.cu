@@ -55,9 +55,11 @@ int run_stepwise_search(const MzNetDesc& net, const MzSearchDesc& search, int po
         a.net_value = pool.net_value; a.net_reward = nullptr; a.net_policy = pool.net_policy;
         a.value_stride = 1; a.policy_stride = A; a.policy_is_prior = 0;
     }
-    a.sim = 0; a.do_root = K0 > 0 ? 2 : 1; a.do_update = 0; a.do_select = N > 0; a.do_final = N == 0;
+    a.sim = 0; a.do_root = K0 > 0 ? 0 : 1; a.do_update = 0; a.do_select = N > 0; a.do_final = N == 0;
     kt_begin(KT_TREE, stream);
-    cudaError_t e = launch_tree_step(a, stream);
+    cudaError_t e = cudaSuccess;
+    if (K0 > 0) { e = launch_tree_adopt_root(a, stream); *launches += 1; }
+    if (e == cudaSuccess) e = launch_tree_step(a, stream);
     kt_end(stream);
     if (e != cudaSuccess) return cuda_fail("tree_step(root)", e);
     *launches += 1;

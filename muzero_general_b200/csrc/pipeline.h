@@ -48,7 +48,7 @@ struct InferCall {
 struct TreeStepArgs {
     int n, N, A, P;
     int sim;                       // simulation selected by this launch (do_select); do_update handles sim-1
-    int do_root, do_update, do_select, do_final;      // do_root: 1 = expand a fresh root, 2 = adopt the imported tree
+    int do_root, do_update, do_select, do_final;
     double discount, noise_frac, noise_alpha;
     uint64_t seed;
     const double* pbc;
@@ -72,6 +72,7 @@ struct TreeStepArgs {
     DevTrace trace;
 };
 cudaError_t launch_tree_step(const TreeStepArgs& a, cudaStream_t stream);
+cudaError_t launch_tree_adopt_root(const TreeStepArgs& a, cudaStream_t stream);     // MZ_FLAG_CONTINUE: adopt the imported tree
 
 struct ResNetDevice;
 ResNetDevice* resnet_create(const MzNetDesc& net, int max_batch, int sm_count, std::string* err);

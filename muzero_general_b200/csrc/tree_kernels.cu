@@ -12,6 +12,8 @@
 #include "tree.cuh"
 #include "launch.h"
 
+#include <stdlib.h>
+
 namespace mz {
 
 // kLatency: few games in flight (the launch is bound by the chain of dependent round trips to L2, not by
@@ -69,27 +71,6 @@ __global__ void __launch_bounds__(128) tree_step_kernel(const __grid_constant__ 
         t.n_expanded = p.n_expanded[g];
         t.ties = p.ties[g];
         max_depth = p.max_depth[g];
-        if (a.do_root == 2) {
-            // override_root_with (self_play.py:275-277, 310-314): the imported node is the root; fresh MinMaxStats; the
-            // exploration noise is mixed into the priors the root's children already have (self_play.py:467-476)
-            t.lo = INFINITY; t.hi = -INFINITY; t.ties = 0; max_depth = 0;
-            if (a.add_noise && lane < A) {
-                double nz;
-                const int64_t gid = a.game_id ? a.game_id[g] : (int64_t)g;
-                const int mv = a.move_index ? a.move_index[g] : 0;
-                if (a.noise) {
-                    nz = a.noise[(size_t)g * A + lane];
-                } else {
-                    const double gm = philox_gamma(a.seed, gid, mv, lane, a.noise_alpha);
-                    double sum = 0.0;
-                    for (int k = 0; k < A; ++k) sum += LaneGroup<G>::bcast(gm, k);     // A <= G lanes hold a draw each
-                    nz = gm / sum;
-                }
-                if (a.trace.noise) a.trace.noise[(size_t)g * A + lane] = nz;
-                t.root_prior[lane] = __dadd_rn(__dmul_rn(t.root_prior[lane], __dsub_rn(1.0, a.noise_frac)), __dmul_rn(nz, a.noise_frac));
-            }
-            LaneGroup<G>::sync();
-        }
     }
 
     if (a.do_update) {
@@ -156,14 +137,67 @@ __global__ void __launch_bounds__(128) tree_step_kernel(const __grid_constant__ 
     }
 }
 
+// override_root_with (self_play.py:275-277, 310-314): the tree mz_import_tree put into the pool becomes the root of a new
+// search - fresh MinMaxStats, tie / depth counters reset, and the exploration noise mixed into the priors the root's
+// children already have (self_play.py:467-476).  Its own kernel (one game per lane group, launched once per continued
+// search) so that the per-simulation kernel keeps its register budget.
+template <int G>
+__global__ void __launch_bounds__(128) tree_adopt_root_kernel(const __grid_constant__ TreeStepArgs a) {
+    const int g = (blockIdx.x * blockDim.x + threadIdx.x) / G;
+    if (g >= a.n) return;
+    const int lane = LaneGroup<G>::lane();
+    const int A = a.A;
+    const NodePool& p = a.pool;
+    if (lane == 0) {
+        p.range[2 * g] = INFINITY;
+        p.range[2 * g + 1] = -INFINITY;
+        p.ties[g] = 0;
+        p.max_depth[g] = 0;
+    }
+    if (a.add_noise) {
+        double nz = 0.0;
+        const int64_t gid = a.game_id ? a.game_id[g] : (int64_t)g;
+        const int mv = a.move_index ? a.move_index[g] : 0;
+        if (a.noise) {
+            if (lane < A) nz = a.noise[(size_t)g * A + lane];
+        } else {
+            const double gm = lane < A ? philox_gamma(a.seed, gid, mv, lane, a.noise_alpha) : 0.0;
+            double sum = gm;
+            const unsigned m = LaneGroup<G>::mask();
+            for (int off = G >> 1; off > 0; off >>= 1) sum += shfl_xor_f64(m, sum, off, G);
+            nz = gm / sum;
+        }
+        if (lane < A) {
+            if (a.trace.noise) a.trace.noise[(size_t)g * A + lane] = nz;
+            double* rp = p.root_prior + (size_t)g * A + lane;
+            *rp = __dadd_rn(__dmul_rn(*rp, __dsub_rn(1.0, a.noise_frac)), __dmul_rn(nz, a.noise_frac));
+        }
+    }
+}
+
+cudaError_t launch_tree_adopt_root(const TreeStepArgs& a, cudaStream_t stream) {
+    int G = 4;
+    while (G < a.A) G <<= 1;
+    const int grid = (a.n * G + 127) / 128;
+    switch (G) {
+        case 4: tree_adopt_root_kernel<4><<<grid, 128, 0, stream>>>(a); break;
+        case 8: tree_adopt_root_kernel<8><<<grid, 128, 0, stream>>>(a); break;
+        case 16: tree_adopt_root_kernel<16><<<grid, 128, 0, stream>>>(a); break;
+        case 32: tree_adopt_root_kernel<32><<<grid, 128, 0, stream>>>(a); break;
+        default: return cudaErrorInvalidValue;
+    }
+    return cudaGetLastError();
+}
+
 cudaError_t launch_tree_step(const TreeStepArgs& a, cudaStream_t stream) {
     int G = 4;
     while (G < a.A) G <<= 1;
     const int threads = 128;
     const int games_per_cta = threads / G;
     const int grid = (a.n + games_per_cta - 1) / games_per_cta;
-    // below ~4 resident warps per scheduler the kernel is latency-bound
-    const bool latency = (long)a.n * G <= 148L * 512;
+    // below ~4 resident warps per scheduler the kernel is latency-bound (MZ_TREE_LATENCY = 0 / 1 forces a variant: A/B switch)
+    static const int forced = getenv("MZ_TREE_LATENCY") ? atoi(getenv("MZ_TREE_LATENCY")) : -1;
+    const bool latency = forced >= 0 ? forced != 0 : (long)a.n * G <= 148L * 512;
     cudaError_t e = cudaSuccess;
 #define MZ_TREE(GG)                                                                                 \
     case GG:                                                                                        \
