@@ -30,7 +30,8 @@ extern "C" {
 
 #define MZ_ABI_VERSION 2
 #define MZ_MAX_LAYERS 8          /* hidden layers per MLP head */
-#define MZ_MAX_ACTIONS 32        /* |action_space| supported by the tree kernels */
+#define MZ_MAX_ACTIONS 128       /* |action_space| supported by the tree kernels (one lane per action up to 32,
+                                    four actions per lane above: csrc/tree_wide.cu) */
 
 enum { MZ_OK = 0, MZ_EINVAL = -1, MZ_ECUDA = -2, MZ_EUNSUPPORTED = -3, MZ_ESTATE = -4, MZ_ENOMEM = -5 };
 enum { MZ_NET_FC = 0, MZ_NET_RESNET = 1 };

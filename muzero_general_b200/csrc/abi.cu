@@ -60,7 +60,7 @@ extern "C" int mz_create(const MzNetDesc* net, const MzSearchDesc* search, int d
     if (search->num_players < 1 || search->max_games < 1 || search->num_simulations < 0)
         return fail(nullptr, MZ_EINVAL, "mz_create: bad search descriptor");
     if (net->action_space < 1 || net->action_space > MZ_MAX_ACTIONS)
-        return fail(nullptr, MZ_EUNSUPPORTED, "mz_create: action_space must be in [1, 32]");
+        return fail(nullptr, MZ_EUNSUPPORTED, "mz_create: action_space must be in [1, 128]");
     if (net->kind != MZ_NET_FC && net->kind != MZ_NET_RESNET)
         return fail(nullptr, MZ_EUNSUPPORTED, "The network parameter should be \"fullyconnected\" or \"resnet\".");
     if (net->kind == MZ_NET_RESNET && net->downsample > 1)
@@ -151,7 +151,7 @@ extern "C" int mz_create(const MzNetDesc* net, const MzSearchDesc* search, int d
     MZ_CREATE_CUDA(dev_alloc(&p.n_expanded, B));
     MZ_CREATE_CUDA(dev_alloc(&p.ties, B));
     MZ_CREATE_CUDA(dev_alloc(&p.max_depth, B));
-    MZ_CREATE_CUDA(dev_alloc(&p.legal, B));
+    MZ_CREATE_CUDA(dev_alloc(&p.legal, (size_t)B * (MZ_MAX_ACTIONS / 32)));     // one word per game (|A| <= 32) or four (tree_wide.cu)
     MZ_CREATE_CUDA(dev_alloc(&p.path, (size_t)B * (N + 2)));
     MZ_CREATE_CUDA(dev_alloc(&p.path_reward, (size_t)B * (N + 2)));
     MZ_CREATE_CUDA(dev_alloc(&p.leaf_depth, B));
@@ -175,14 +175,14 @@ extern "C" int mz_create(const MzNetDesc* net, const MzSearchDesc* search, int d
     if (genv) h->fc_group = atoi(genv);
     else {
         int g = 8;
-        while (g < A) g <<= 1;
+        while (g < A && g < 32) g <<= 1;
         if (g < 16) g = 16;
-        h->fc_group = g;
+        h->fc_group = g;                     // |A| > 32: 32 lanes stride over the outputs; the search itself is step-wise
     }
     const char* tenv = getenv("MZ_FC_THREADS");
     if (tenv) h->fc_threads = atoi(tenv);
     if (h->fc_threads < 32 || h->fc_threads > kFcMaxThreads || h->fc_threads % 32) h->fc_threads = 64;
-    if (h->fc_group < A || (h->fc_group != 4 && h->fc_group != 8 && h->fc_group != 16 && h->fc_group != 32)) {
+    if ((h->fc_group < A && A <= 32) || (h->fc_group != 4 && h->fc_group != 8 && h->fc_group != 16 && h->fc_group != 32)) {
         fail(nullptr, MZ_EINVAL, "mz_create: MZ_FC_GROUP must be 4, 8, 16 or 32 and >= action_space");
         mz_destroy(h);
         return MZ_EINVAL;
@@ -384,7 +384,7 @@ void mz_switch_to_strict(MzHandle* h) {
 int mz_dispatch_search(MzHandle* h, const SearchCall& call, bool teacher, bool trace, int flags) {
     const int n = call.n, N = h->search.num_simulations, A = h->net.action_space;
     int rc;
-    if (h->search.extra_expansions > 0) flags |= MZ_FLAG_STEPWISE;     // the fused FC kernel lays its tree out for N + 1 expansions
+    if (h->search.extra_expansions > 0 || A > 32) flags |= MZ_FLAG_STEPWISE;     // the fused FC kernel: N + 1 expansions, one lane per action
     SearchCall cont = call;
     cont.continue_from = (flags & MZ_FLAG_CONTINUE) ? h->imported_expansions : 0;
     const SearchCall& call_ = cont;
@@ -706,10 +706,20 @@ extern "C" int mz_import_tree(MzHandle* h, int32_t game, const MzTreeExport* t) 
     MZ_CUDA(h, cudaMemcpy(p.prior + base, prior.data(), used * 4, cudaMemcpyHostToDevice));
     MZ_CUDA(h, cudaMemcpy(p.expansion + base, t->child_expansion, used * 4, cudaMemcpyHostToDevice));
     MZ_CUDA(h, cudaMemcpy(p.root_prior + (size_t)game * A, rp.data(), A * 8, cudaMemcpyHostToDevice));
-    const unsigned legal = A >= 32 ? 0xffffffffu : ((1u << A) - 1u);       // children of a non-root node: the whole action space
+    // children of a non-root node: the whole action space (one mask word per game, four for |A| > 32)
     const double range[2] = {INFINITY, -INFINITY};
     const int zero = 0;
-    MZ_CUDA(h, cudaMemcpy(p.legal + game, &legal, 4, cudaMemcpyHostToDevice));
+    if (A > 32) {
+        unsigned words[MZ_MAX_ACTIONS / 32];
+        for (int j = 0; j < MZ_MAX_ACTIONS / 32; ++j) {
+            const int left = A - 32 * j;
+            words[j] = left >= 32 ? 0xffffffffu : (left > 0 ? ((1u << left) - 1u) : 0u);
+        }
+        MZ_CUDA(h, cudaMemcpy(p.legal + (size_t)game * (MZ_MAX_ACTIONS / 32), words, sizeof(words), cudaMemcpyHostToDevice));
+    } else {
+        const unsigned legal = A >= 32 ? 0xffffffffu : ((1u << A) - 1u);
+        MZ_CUDA(h, cudaMemcpy(p.legal + game, &legal, 4, cudaMemcpyHostToDevice));
+    }
     MZ_CUDA(h, cudaMemcpy(p.root_visit + game, &t->root_visit, 4, cudaMemcpyHostToDevice));
     MZ_CUDA(h, cudaMemcpy(p.root_vsum + game, &t->root_value_sum, 8, cudaMemcpyHostToDevice));
     MZ_CUDA(h, cudaMemcpy(p.root_reward + game, &t->root_reward, 4, cudaMemcpyHostToDevice));

@@ -155,21 +155,18 @@ __global__ void __launch_bounds__(128) tree_adopt_root_kernel(const __grid_const
         p.max_depth[g] = 0;
     }
     if (a.add_noise) {
-        double nz = 0.0;
         const int64_t gid = a.game_id ? a.game_id[g] : (int64_t)g;
         const int mv = a.move_index ? a.move_index[g] : 0;
-        if (a.noise) {
-            if (lane < A) nz = a.noise[(size_t)g * A + lane];
-        } else {
-            const double gm = lane < A ? philox_gamma(a.seed, gid, mv, lane, a.noise_alpha) : 0.0;
-            double sum = gm;
+        double sum = 0.0;
+        if (!a.noise) {                               // drawn here: normalised Gamma(alpha) draws over the whole action space
+            for (int k = lane; k < A; k += G) sum += philox_gamma(a.seed, gid, mv, k, a.noise_alpha);
             const unsigned m = LaneGroup<G>::mask();
             for (int off = G >> 1; off > 0; off >>= 1) sum += shfl_xor_f64(m, sum, off, G);
-            nz = gm / sum;
         }
-        if (lane < A) {
-            if (a.trace.noise) a.trace.noise[(size_t)g * A + lane] = nz;
-            double* rp = p.root_prior + (size_t)g * A + lane;
+        for (int k = lane; k < A; k += G) {           // lane l owns the actions l, l + G, ...
+            const double nz = a.noise ? a.noise[(size_t)g * A + k] : philox_gamma(a.seed, gid, mv, k, a.noise_alpha) / sum;
+            if (a.trace.noise) a.trace.noise[(size_t)g * A + k] = nz;
+            double* rp = p.root_prior + (size_t)g * A + k;
             *rp = __dadd_rn(__dmul_rn(*rp, __dsub_rn(1.0, a.noise_frac)), __dmul_rn(nz, a.noise_frac));
         }
     }
@@ -177,7 +174,7 @@ __global__ void __launch_bounds__(128) tree_adopt_root_kernel(const __grid_const
 
 cudaError_t launch_tree_adopt_root(const TreeStepArgs& a, cudaStream_t stream) {
     int G = 4;
-    while (G < a.A) G <<= 1;
+    while (G < a.A && G < 32) G <<= 1;
     const int grid = (a.n * G + 127) / 128;
     switch (G) {
         case 4: tree_adopt_root_kernel<4><<<grid, 128, 0, stream>>>(a); break;
@@ -190,6 +187,7 @@ cudaError_t launch_tree_adopt_root(const TreeStepArgs& a, cudaStream_t stream) {
 }
 
 cudaError_t launch_tree_step(const TreeStepArgs& a, cudaStream_t stream) {
+    if (a.A > 32) return launch_tree_step_wide(a, stream);
     int G = 4;
     while (G < a.A) G <<= 1;
     const int threads = 128;

@@ -28,6 +28,7 @@ class BoardVector(VectorGame):
     GRAVITY = False            # Connect4: a move names a column and the stone drops
     OBS_DTYPE = numpy.float64
     REWARD_SCALE = 1
+    REWARD_WHEN_FULL = False   # games/gomoku.py:243-247 pays the mover whenever the game ends, a full board included
 
     def __init__(self, num_games, seed=None):
         self.num_games = int(num_games)
@@ -77,7 +78,7 @@ class BoardVector(VectorGame):
         mine = self.board == self.player[:, None]
         won = mine[:, self.lines].all(axis=2).any(axis=1)
         full = ~(self.legal_mask().any(axis=1))
-        reward = numpy.where(won, 1, 0) * self.REWARD_SCALE
+        reward = numpy.where(won | full if self.REWARD_WHEN_FULL else won, 1, 0) * self.REWARD_SCALE
         self.player = -self.player
         return self.observations(), reward, won | full
 

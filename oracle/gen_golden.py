@@ -232,7 +232,7 @@ def gen_net(models, name, ref_cfg, spec, weights, batch, seed):
     net.set_weights(to_torch_sd(weights))
     net.eval()
     rs = numpy.random.RandomState(seed)
-    if name in ("tictactoe", "connect4"):
+    if name in ("tictactoe", "connect4", "gomoku"):
         obs = rs.randint(0, 2, size=(batch, spec.in_channels) + spec.obs_shape[1:]).astype(numpy.float32)
         obs[:, -1] = rs.choice([-1.0, 1.0], size=(batch, 1, 1))
     else:
@@ -457,6 +457,23 @@ def main_round2():
     cfg.num_simulations = 30
     json.dump(runs, open(os.path.join(OUT, "mcts_breakout_n50.json"), "w"))
     print("BASELINE-size closed-loop fixtures written")
+
+    # ---- the wide-action-space game: environment trajectories and a network + search fixture for games/gomoku.py
+    import muzero_general_b200.games as mygames2
+    go_ref = load_reference_game("gomoku")
+    fx = gen_env_fixture(go_ref, mygames2.load_game_module("gomoku"), "gomoku", 6, seed=13)
+    json.dump(fx, open(os.path.join(OUT, "env_gomoku.json"), "w"))
+    go_cfg = go_ref.MuZeroConfig()
+    go_spec = check_config_and_spec(models, "gomoku", go_cfg, mygames2.load_game_module("gomoku").MuZeroConfig())
+    go_net = gen_net(models, "gomoku", go_cfg, go_spec, synthetic_weights(go_spec, 0), 3, seed=5)
+    runs = []
+    for moves, n_sim, seed in (((), 60, 0), ((60, 61, 49, 71, 38), 90, 1)):
+        go_cfg.num_simulations = n_sim
+        o, legal, tp = board_obs(go_ref, moves)
+        runs.append(run_traced_search(sp, go_cfg, go_net, o, legal, tp, True, seed))
+    go_cfg.num_simulations = 400
+    json.dump(runs, open(os.path.join(OUT, "mcts_gomoku.json"), "w"))
+    print("gomoku fixtures written")
 
     # ---- hard-coded opponents (expert_agent): reference choice at every position of random playouts
     experts = {}

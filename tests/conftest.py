@@ -27,7 +27,7 @@ def golden_npz(name):
 @pytest.fixture(scope="session")
 def game_configs():
     from muzero_general_b200.games import load_game_module
-    return {n: load_game_module(n).MuZeroConfig() for n in ("cartpole", "tictactoe", "connect4", "breakout", "atari")}
+    return {n: load_game_module(n).MuZeroConfig() for n in ("cartpole", "tictactoe", "connect4", "breakout", "atari", "gomoku")}
 
 
 def weights_for(name, spec):

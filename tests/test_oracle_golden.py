@@ -22,7 +22,7 @@ def _net(name, cfgs):
     return spec, OracleNet(spec, weights_for(name, spec))
 
 
-@pytest.mark.parametrize("name", ["cartpole", "cartpole_pretrained", "tictactoe", "connect4", "breakout", "connect4_b64",
+@pytest.mark.parametrize("name", ["cartpole", "cartpole_pretrained", "tictactoe", "connect4", "breakout", "gomoku", "connect4_b64",
                                   "connect4_stress_large", "connect4_stress_overflow", "connect4_stress_tiny"])
 def test_network_matches_reference_outputs(name, game_configs):
     spec, net = _net(name, game_configs)
@@ -102,7 +102,7 @@ def test_stacked_observations_and_statistics_kat():
     assert om.child_visit_policy(list(range(9)), [0, 4, 8], [6, 18, 1]) == st["child_visits"][0]
 
 
-SEARCH_FILES = ["cartpole_synth", "cartpole_pretrained", "tictactoe", "connect4", "breakout", "connect4_n200", "breakout_n50"]
+SEARCH_FILES = ["cartpole_synth", "cartpole_pretrained", "tictactoe", "connect4", "breakout", "connect4_n200", "breakout_n50", "gomoku"]
 
 
 @pytest.mark.parametrize("name", SEARCH_FILES)

@@ -71,7 +71,7 @@ def _report(name, got, want):
     print(f"{name}: max abs err {err.max():.3e}, max rel err {(err / (numpy.abs(want) + 1e-3)).max():.3e}")
 
 
-@pytest.mark.parametrize("name", ["tictactoe", "connect4", "breakout", "connect4_b64"])
+@pytest.mark.parametrize("name", ["tictactoe", "connect4", "breakout", "connect4_b64", "gomoku"])
 def test_resnet_network_matches_reference(name, numerics, game_configs):
     _skip_redundant(name, numerics)
     cfg = game_configs[name.split("_")[0]]
@@ -185,7 +185,7 @@ def test_tower_range_guard_on_stress_weights(mode, game_configs, monkeypatch):
     eng.close()
 
 
-@pytest.mark.parametrize("name,N,n", [("tictactoe", 50, 24), ("connect4", 40, 12), ("breakout", 12, 4)])
+@pytest.mark.parametrize("name,N,n", [("tictactoe", 50, 24), ("connect4", 40, 12), ("breakout", 12, 4), ("gomoku", 30, 6)])
 def test_resnet_student_forced(name, N, n, numerics, game_configs):
     """Device search with its own residual networks, replayed through the oracle tree."""
     _skip_redundant(name, numerics)
@@ -223,7 +223,7 @@ def test_resnet_student_forced(name, N, n, numerics, game_configs):
     eng.close()
 
 
-@pytest.mark.parametrize("name", ["tictactoe", "connect4", "breakout", "connect4_n200", "breakout_n50"])
+@pytest.mark.parametrize("name", ["tictactoe", "connect4", "breakout", "connect4_n200", "breakout_n50", "gomoku"])
 def test_resnet_closed_loop_matches_reference_counts(name, numerics, game_configs):
     """Own networks + the reference's noise and first pick.  "off" and "x3": the reference's visit counts EXACTLY, at the
     BASELINE simulation counts too (Connect4 N=200, Breakout N=50).  "fp16": counts may move where two children are

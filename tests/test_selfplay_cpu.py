@@ -43,7 +43,7 @@ def _assert_history_equals(gh, ref):
 
 def test_env_fixtures():
     """Our board environments replay the reference's recorded trajectories."""
-    for name in ("tictactoe", "connect4"):
+    for name in ("tictactoe", "connect4", "gomoku"):
         fx = golden_json(f"env_{name}.json")
         mod = load_game_module(name)
         for steps in fx["games"]:

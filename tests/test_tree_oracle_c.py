@@ -9,7 +9,7 @@ from oracle import mcts as om
 
 
 @pytest.mark.parametrize("name", ["cartpole_synth", "cartpole_pretrained", "tictactoe", "connect4", "breakout",
-                                  "connect4_n200", "breakout_n50"])
+                                  "connect4_n200", "breakout_n50", "gomoku"])
 def test_c_oracle_reproduces_reference_traces(name, game_configs):
     cfg = game_configs[name.split("_")[0]]
     A = len(cfg.action_space)
@@ -24,7 +24,7 @@ def test_c_oracle_reproduces_reference_traces(name, game_configs):
         assert [[int(a) for a in r["actions"][0, s, :r["depth"][0, s]]] for s in range(N)] == [s["actions"] for s in c["sims"]]
 
 
-@pytest.mark.parametrize("game,N,n", [("cartpole", 50, 40), ("tictactoe", 30, 24), ("connect4", 40, 12)])
+@pytest.mark.parametrize("game,N,n", [("cartpole", 50, 40), ("tictactoe", 30, 24), ("connect4", 40, 12), ("gomoku", 40, 6)])
 def test_c_oracle_matches_python_oracle(game, N, n, game_configs):
     cfg = game_configs[game]
     A, P = len(cfg.action_space), len(cfg.players)

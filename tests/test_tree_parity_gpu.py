@@ -14,7 +14,7 @@ from oracle import mcts as om
 
 pytestmark = pytest.mark.gpu
 
-SEARCH_FILES = ["cartpole_synth", "cartpole_pretrained", "tictactoe", "connect4", "breakout", "connect4_n200", "breakout_n50"]
+SEARCH_FILES = ["cartpole_synth", "cartpole_pretrained", "tictactoe", "connect4", "breakout", "connect4_n200", "breakout_n50", "gomoku"]
 
 
 def _engine(cfg, max_games, N):
@@ -48,7 +48,7 @@ def test_teacher_forced_reference_traces(name, stepwise, game_configs):
 
 
 @pytest.mark.parametrize("stepwise", [False, True])
-@pytest.mark.parametrize("game,N,n", [("cartpole", 50, 48), ("tictactoe", 50, 32), ("connect4", 64, 16), ("breakout", 30, 16)])
+@pytest.mark.parametrize("game,N,n", [("cartpole", 50, 48), ("tictactoe", 50, 32), ("connect4", 64, 16), ("breakout", 30, 16), ("gomoku", 60, 24)])
 def test_teacher_forced_synthetic_vs_oracle(game, N, n, stepwise, game_configs):
     """Random per-simulation tables, restricted legal sets, both player modes, Philox ties."""
     cfg = game_configs[game]
@@ -208,7 +208,7 @@ def test_full_size_invariants(game_configs):
 
 
 @pytest.mark.parametrize("stepwise", [False, True])
-@pytest.mark.parametrize("game,n,N", [("cartpole", 4096, 50), ("tictactoe", 2048, 50), ("connect4", 1024, 200)])
+@pytest.mark.parametrize("game,n,N", [("cartpole", 4096, 50), ("tictactoe", 2048, 50), ("connect4", 1024, 200), ("gomoku", 256, 120)])
 def test_teacher_forced_full_size_vs_c_oracle(game, n, N, stepwise, game_configs):
     """BASELINE-sized batches, injected outputs: every game's visit counts, root value, depth,
     tie count, value range and every selected path equal the C oracle's, bit for bit."""
