@@ -223,7 +223,7 @@ def test_teacher_forced_full_size_vs_c_oracle(game, n, N, stepwise, game_configs
     to_play = rs.randint(0, P, n).astype(numpy.int32)
     gid = rs.randint(0, 1 << 40, n).astype(numpy.int64)
     mv = rs.randint(0, 400, n).astype(numpy.int32)
-    D = 64
+    D = 64 if A <= 32 else 160              # wide, flat action spaces search deep
     ref = build_c.tree_search(n, N, A, P, cfg.discount, cfg.pb_c_base, cfg.pb_c_init, cfg.root_exploration_fraction,
                               legal, to_play, noise, None, cfg.seed, gid, mv, t, D=D)
     eng = _engine(cfg, n, N)
