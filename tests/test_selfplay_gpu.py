@@ -203,3 +203,19 @@ def test_batched_reanalyse_on_device(monkeypatch):
     actor.reanalyse(buf, st)
     assert buf.updated and st.d["num_reanalysed_games"] > len(games)
     actor.close(); worker.model.engine.close()
+
+
+def test_wide_action_space_game_through_the_host_loop():
+    """games/gomoku.py (121 actions: four actions per lane in the tree kernels) through SelfPlay.play_moves on the host
+    loop: every move is legal (one new stone per move on a free cell), visit counts sum to N over legal actions only."""
+    worker, cfg, sp = _worker("gomoku", 0, num_parallel_games=4, num_simulations=20)
+    assert worker.loop_path == "host"
+    worker.play_moves(10, 1.0)
+    env = worker._batched.env
+    assert (numpy.abs(env.board).sum(1) == 10).all() and (env.board.sum(1) == 0).all()     # 5 stones each, all on distinct cells
+    rec = worker._batched.records[-1]
+    assert (rec["visits"].sum(1) == 20).all() and (rec["visits"][rec["legal"] == 0] == 0).all()
+    # single-game MCTS.run returns a Node graph over the legal actions
+    root, info = sp.MCTS(cfg).run(worker.model, numpy.zeros(cfg.observation_shape, numpy.float32), list(range(0, 121, 3)), 0, True)
+    assert list(root.children) == list(range(0, 121, 3)) and root.visit_count == 20
+    worker.model.engine.close()
