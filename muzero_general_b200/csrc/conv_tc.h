@@ -35,6 +35,8 @@ struct TowerArgs {
     int debug_skip;               // profiling only: 1 = no MMA, 2 = no A-tile loads, 4 = no global stores, 8 = no residual loads
     int g0;                       // x3 mode: first board of this launch (a batch is split into launches of <= 4 boards per SM)
     int* sat_count;               // x3 mode: bumped when a stored activation exceeds the fp16 range (accuracy contract left)
+    long long* timeline;          // x3 mode, profiling only (MZ_X3_TIMELINE): CTA 0 records clock64 per (layer, tile):
+                                  // [0] MMA issue starts, [1] issued, [2] epilogue sees the accumulator, [3] tile rewritten
 };
 
 cudaError_t launch_conv_tower_tc(const TowerArgs& a, int sm_count, cudaStream_t stream);

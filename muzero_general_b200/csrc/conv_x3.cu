@@ -124,6 +124,8 @@ MZ_DEVINL const unsigned char* x3_board(const TowerArgs& a, int buf, int g) {
 __global__ void __launch_bounds__(kThreads, 1) conv_tower_x3_kernel(const __grid_constant__ TowerArgs a) {
     extern __shared__ __align__(1024) unsigned char smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    constexpr int kStampBase = kTowerMaxLayers * kTiles * 4;     // timeline: [+0] kernel entry, [+1] setup done, [+2] outputs stored
+    if (a.timeline && blockIdx.x == 0 && threadIdx.x == 0) a.timeline[kStampBase] = clock64();
     const uint32_t s_base = smem_u32(smem);
     const uint32_t s_w = s_base + SmemX::w, s_hi = s_base + SmemX::hi, s_lo = s_base + SmemX::lo;
     float* s_bias = reinterpret_cast<float*>(smem + SmemX::bias);
@@ -181,6 +183,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tower_x3_kernel(const __grid
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    if (a.timeline && blockIdx.x == 0 && threadIdx.x == 0) a.timeline[kStampBase + 1] = clock64();
 
     if (warp == 0) {
         // ================= producer: weights of every layer, input boards once =================
@@ -221,6 +224,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tower_x3_kernel(const __grid
                 else mbar_wait(bar_tile_ready(k), (uint32_t)((l - 1) & 1));
                 tc_fence_after();
                 if (elect_one()) {
+                    if (a.timeline && blockIdx.x == 0) a.timeline[(l * kTiles + k) * 4 + 0] = clock64();
                     const uint32_t d = tmem_base + (uint32_t)(k * kAccCols);
                     const uint32_t row0 = (uint32_t)((kHalo + k * kBoards * kPos) * kRowBytes);
                     const uint32_t ah16 = ((s_hi + row0) >> 4) | kDescLoFlags;
@@ -243,6 +247,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tower_x3_kernel(const __grid
                         if (k == my_tiles - 1) umma_commit(bar_w_empty(tap));
                     }
                     umma_commit(bar_acc_full(k));
+                    if (a.timeline && blockIdx.x == 0) a.timeline[(l * kTiles + k) * 4 + 1] = clock64();
                 }
                 __syncwarp();
             }
@@ -264,6 +269,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tower_x3_kernel(const __grid
                 asm volatile("cp.async.bulk.commit_group;" ::: "memory");
             }
             asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+            if (a.timeline && blockIdx.x == 0) a.timeline[kStampBase + 2] = clock64();
         }
     } else if (warp >= 4) {
         // ================= epilogue: warps 4..7 own tile 0, warps 8..11 tile 1, for the whole tower =================
@@ -327,9 +333,22 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tower_x3_kernel(const __grid
                 const bool keep = l + 2 < L && a.layer[l + 2].res_buf >= 0;     // this output is the input of a block
                 float act_scale = 0.0f;
                 if (live && ly.action_table) act_scale = __fdiv_rn((float)a.action[g], (float)a.A);
-                const float* atab = ly.action_table ? ly.action_table + (size_t)p * kC : nullptr;
+                // the action table row of this position (dynamics stem): fetched into the idle residual registers while the
+                // MMAs of the layer run - 64 dependent L2 loads after the accumulator wait cost 20 k cycles per launch
+                // (profiles/r02_x3_timeline.md).  The table sits on the stem, before the first block: the registers are free.
+                // (the launcher rejects a table anywhere else)
+                const bool table = ly.action_table != nullptr;
+                if (table) {
+                    const float4* atab4 = reinterpret_cast<const float4*>(ly.action_table + (size_t)p * kC);
+#pragma unroll
+                    for (int j = 0; j < kC / 4; ++j) {
+                        const float4 t4 = __ldg(atab4 + j);
+                        res[4 * j] = t4.x; res[4 * j + 1] = t4.y; res[4 * j + 2] = t4.z; res[4 * j + 3] = t4.w;
+                    }
+                }
                 mbar_wait(bar_acc_full(k), (uint32_t)(l & 1));
                 tc_fence_after();
+                if (a.timeline && blockIdx.x == 0 && q == 0 && lane == 0) a.timeline[(l * kTiles + k) * 4 + 2] = clock64();
                 const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(k * kAccCols);
 #pragma unroll
                 for (int c4 = 0; c4 < 4; ++c4) {
@@ -344,7 +363,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tower_x3_kernel(const __grid
                         const int c = 16 * c4 + e;
                         float v = fmaf(__uint_as_float(vl[e]), kLoUnscale, __uint_as_float(vm[e]) + __uint_as_float(vc[e])) * scale[c] + bias[c];
                         if (add_res) v += res[c];
-                        if (atab) v = fmaf(act_scale, atab[c], v);
+                        if (table) v = fmaf(act_scale, res[c], v);
                         if (ly.relu) v = fmaxf(v, 0.0f);
                         if (!live) v = 0.0f;               // padding rows and missing boards stay zero
                         if (keep) res[c] = v;
@@ -370,6 +389,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tower_x3_kernel(const __grid
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic smem writes -> tcgen05 / bulk-copy readers
                 __syncwarp();
                 if (lane == 0) mbar_arrive(last ? bar_out_ready(k) : bar_tile_ready(k));
+                if (a.timeline && blockIdx.x == 0 && q == 0 && lane == 0) a.timeline[(l * kTiles + k) * 4 + 3] = clock64();
             }
             if (peak > 65504.0f && a.sat_count) atomicAdd(a.sat_count, 1);
         }
@@ -394,7 +414,17 @@ cudaError_t launch_conv_tower_x3(const TowerArgs& args, int sm_count, cudaStream
         const TowerLayer& t = args.layer[l];
         if (l > 0 && t.in_buf != args.layer[l - 1].out_buf) return cudaErrorInvalidValue;
         if (l > 0 && t.res_buf >= 0 && t.res_buf != args.layer[l - 1].in_buf) return cudaErrorInvalidValue;
+        // an action table belongs to a stem: first layer, no residual, not the first conv of a block (the kernel parks the
+        // table row in the residual registers, which must be idle)
+        if (t.action_table && (l > 0 || t.res_buf >= 0 || (args.n_layers >= 2 && args.layer[1].res_buf >= 0))) return cudaErrorInvalidValue;
     }
+    // profiling: MZ_X3_TIMELINE=<file> appends CTA 0's per-layer clock64 stamps of every launch (synchronous; never
+    // set inside a graph capture - use MZ_NO_GRAPH=1)
+    static const char* timeline_path = getenv("MZ_X3_TIMELINE");
+    static long long* d_timeline = nullptr;
+    constexpr int kTimelineWords = kTowerMaxLayers * kTiles * 4 + 4;
+    if (timeline_path && !d_timeline && cudaMalloc(&d_timeline, kTimelineWords * sizeof(long long)) != cudaSuccess)
+        return cudaErrorMemoryAllocation;
     const int per_launch = sm_count * kTiles * kBoards;
     const int chunks = (args.n + per_launch - 1) / per_launch;
     int per = (args.n + chunks - 1) / chunks;
@@ -405,8 +435,24 @@ cudaError_t launch_conv_tower_x3(const TowerArgs& args, int sm_count, cudaStream
         a.n = (args.n - g0 < per) ? args.n - g0 : per;
         const int n_tiles = (a.n + kBoards - 1) / kBoards;
         const int grid = (n_tiles + kTiles - 1) / kTiles;
+        a.timeline = timeline_path ? d_timeline : nullptr;
         cudaError_t e = launch_chained(conv_tower_x3_kernel, dim3(grid), dim3(kThreads), SmemX::total, stream, a);
         if (e != cudaSuccess) return e;
+        if (timeline_path) {
+            long long h[kTimelineWords];
+            if ((e = cudaStreamSynchronize(stream)) != cudaSuccess) return e;
+            if ((e = cudaMemcpy(h, d_timeline, sizeof(h), cudaMemcpyDeviceToHost)) != cudaSuccess) return e;
+            if (FILE* f = fopen(timeline_path, "a")) {
+                const long long* st = h + kTowerMaxLayers * kTiles * 4;
+                fprintf(f, "launch boards=%d layers=%d entry=%lld setup=%lld stored=%lld\n", a.n, a.n_layers, st[0] - h[0], st[1] - h[0], st[2] - h[0]);
+                for (int l = 0; l < a.n_layers; ++l)
+                    for (int k = 0; k < kTiles; ++k) {
+                        const long long* t = h + (l * kTiles + k) * 4;
+                        fprintf(f, "%d %d %lld %lld %lld %lld\n", l, k, t[0] - h[0], t[1] - h[0], t[2] - h[0], t[3] - h[0]);
+                    }
+                fclose(f);
+            }
+        }
     }
     return cudaGetLastError();
 }

@@ -278,16 +278,21 @@ __global__ void __launch_bounds__(kHeadThreads) heads_kernel(const __grid_consta
     float* s_sc = s_lo + C;                                          // [C] channel scale
     float* s_part = s_sc + C;                                        // [2][2][C] partial extrema
     float* s_act = s_part + 4 * C;                                   // per head: ping | pong
+    // board layout only (C = 64): padded row of dense position p, looked up instead of two runtime divisions per chunk
+    __shared__ unsigned char s_pos[64];
     pdl_launch_dependents();
     {
         const float4* src = reinterpret_cast<const float4*>(a.blob + a.w_lo);
         float4* dst = reinterpret_cast<float4*>(s_w);
         for (int i = threadIdx.x; i < a.w_floats / 4; i += blockDim.x) dst[i] = src[i];
+        if (a.p64c4 && threadIdx.x < HW && threadIdx.x < 64)
+            s_pos[threadIdx.x] = (unsigned char)((threadIdx.x / a.W + 1) * 8 + (threadIdx.x % a.W));
     }
     __syncthreads();
     pdl_wait();                                                      // the weights are constants; x comes from the previous kernel
     const float* blob = s_w - a.w_lo;                                // blob[off] addresses the staged copy
-    const int cj = C >> 3;                                           // 8-channel chunks per position (P64S path)
+    constexpr int cj = 8;                                            // 8-channel chunks per position (board layout: C = 64)
+    const int c_shift = (C & (C - 1)) == 0 ? 31 - __clz(C) : -1;     // C is a power of two for every bundled network
 
     for (int g = blockIdx.x * ngroups + group; g < a.n; g += gridDim.x * ngroups) {
         // ---- stage x[p][c]
@@ -296,7 +301,7 @@ __global__ void __launch_bounds__(kHeadThreads) heads_kernel(const __grid_consta
             const uint4* x8 = reinterpret_cast<const uint4*>(reinterpret_cast<const __half*>(a.x) + (size_t)g * (split ? 8192 : 4096));
             for (int i = t; i < cj * HW; i += kHeadGroup) {
                 const int j = i % cj, p = i / cj;
-                const int pos = (p / a.W + 1) * 8 + (p % a.W);
+                const int pos = s_pos[p];
                 const uint4 v = x8[pos * 8 + (j ^ (pos & 7))];
                 const __half2* h2 = reinterpret_cast<const __half2*>(&v);
                 float2 f0 = __half22float2(h2[0]), f1 = __half22float2(h2[1]);
@@ -326,7 +331,7 @@ __global__ void __launch_bounds__(kHeadThreads) heads_kernel(const __grid_consta
             // Phase A: channel extrema (two threads per channel when the group is wide enough).
             const int parts = (2 * C <= kHeadGroup) ? 2 : 1;
             for (int i = t; i < parts * C; i += kHeadGroup) {
-                const int c = i % C, part = i / C;
+                const int c = c_shift >= 0 ? (i & (C - 1)) : i % C, part = c_shift >= 0 ? (i >> c_shift) : i / C;
                 const int p0 = (part * HW) / parts, p1 = ((part + 1) * HW) / parts;
                 float lo = INFINITY, hi = -INFINITY;
                 for (int p = p0; p < p1; ++p) { const float v = s_x[p * CP + c]; lo = fminf(lo, v); hi = fmaxf(hi, v); }
@@ -346,7 +351,7 @@ __global__ void __launch_bounds__(kHeadThreads) heads_kernel(const __grid_consta
             if (a.p64c4) {
                 for (int i = t; i < cj * HW; i += kHeadGroup) {
                     const int j = i % cj, p = i / cj;
-                    const int pos = (p / a.W + 1) * 8 + (p % a.W);
+                    const int pos = s_pos[p];
                     const float4* xr = reinterpret_cast<const float4*>(s_x + p * CP + 8 * j);
                     const float4* lr = reinterpret_cast<const float4*>(s_lo + 8 * j);
                     const float4* sr = reinterpret_cast<const float4*>(s_sc + 8 * j);
@@ -1240,7 +1245,8 @@ struct Runner {
         const bool narrow = a.C * a.HW <= 1024 && n_heads <= 2;
         const int group = narrow ? 32 : 128;
         int groups = kHeadThreads / group;
-        if (narrow) groups = std::max(1, std::min(groups, (n + r->sm_count - 1) / r->sm_count));
+        // only as many groups per CTA as it takes to give every SM work (1024 Connect4 boards: 147 CTAs x 7 groups, not 128 x 8)
+        groups = std::max(1, std::min(groups, (n + r->sm_count - 1) / r->sm_count));
         size_t smem = ((size_t)a.w_floats + (size_t)groups * a.warp_floats) * 4;
         while (groups > 1 && smem > 227 * 1024) { --groups; smem = ((size_t)a.w_floats + (size_t)groups * a.warp_floats) * 4; }
         if (smem > 227 * 1024) {

@@ -1,0 +1,9 @@
+#!/bin/bash
+mkdir -p gpurun_out
+./scripts/mma_rate 40 > gpurun_out/r2_21_mma_rate.md 2>&1; cat gpurun_out/r2_21_mma_rate.md
+rm -f gpurun_out/x3_timeline.txt
+MZ_NO_GRAPH=1 MZ_X3_TIMELINE=gpurun_out/x3_timeline.txt timeout 600 python scripts/x3_timeline.py > gpurun_out/r2_21_timeline.md 2>&1; cat gpurun_out/r2_21_timeline.md
+timeout 900 python -m pytest tests/test_resnet_gpu.py tests/test_conv_gpu.py -m gpu -q -x 2>&1 | tail -3
+timeout 300 python bench.py --workload connect4_b1024_n200 --no-extras --no-loop --no-saturation --no-cpu-baseline --steps 10 --warmup 3 2>/dev/null | python -c "
+import json,sys
+d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('connect4 x3:', round(d['value']), 'env-steps/s', d['ms_per_search']['median'], 'ms', d.get('kernel_split'))"

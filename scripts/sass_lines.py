@@ -1,6 +1,7 @@
 #!/usr/bin/env python
 """Join an ncu SASS-level source page with nvdisasm line info: executed warp-instructions and stall
-samples per CUDA source line.  usage: sass_lines.py report.ncu-rep cubin mangled_kernel_name [top]"""
+samples per CUDA source line.  usage: sass_lines.py report.ncu-rep cubin mangled_kernel_name [top] [substring of the demangled kernel name]
+(the first launch of the report whose name contains the substring is used; default: the first launch)"""
 import collections
 import csv
 import re
@@ -9,6 +10,7 @@ import sys
 
 rep, cubin, kernel = sys.argv[1:4]
 top = int(sys.argv[4]) if len(sys.argv) > 4 else 40
+want = sys.argv[5] if len(sys.argv) > 5 else ""
 dis = subprocess.run(["nvdisasm", "-g", cubin], capture_output=True, text=True).stdout
 line_of = {}
 cur = None
@@ -33,11 +35,15 @@ raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_ou
 rows = list(csv.reader(raw.splitlines()))
 hdr = None
 base = None
+skipping = False
 ex = collections.Counter(); samples = collections.Counter(); total = 0
 for r in rows:
     if r and r[0] == "Kernel Name":
         if hdr is not None and base is not None:
-            break                      # first launch only
+            break                      # one launch only
+        skipping = want not in r[1]
+        continue
+    if skipping:
         continue
     if r and r[0] == "Address":
         hdr = r; continue
