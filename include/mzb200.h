@@ -206,6 +206,9 @@ int64_t mz_hidden_elems(const MzHandle* h);
 int64_t mz_obs_elems(const MzHandle* h);
 /* number of kernels this handle has launched so far (bench.py's gpu_launches) */
 int64_t mz_launch_count(const MzHandle* h);
+/* parallel branches of the CUDA graph the step-wise search is replayed from: the simulations of disjoint game ranges
+ * overlap (towers of one range with the heads / tree steps of the others); 1 = a single chain.  MZ_PARTS=1..4 overrides. */
+int32_t mz_graph_partitions(const MzHandle* h);
 /* device time of the search kernels of the last mz_search call, ms (CUDA events on the library stream) */
 double mz_last_search_ms(const MzHandle* h);
 
@@ -213,8 +216,9 @@ double mz_last_search_ms(const MzHandle* h);
  * pipeline runs launch by launch with a CUDA event pair around every kernel instead of replaying its CUDA graph.
  * mz_kernel_times synchronises and returns the accumulated milliseconds / launch counts since the last call:
  * [0] tree_step_kernel, [1] conv_tower_tc_kernel (tcgen05 towers, resident or streaming), [2] heads_kernel,
- * [3] conv3x3_kernel (CUDA cores, one conv per launch), [4] other, [5] small_tower_kernel (fused CUDA-core towers). */
-#define MZ_KERNEL_CLASSES 6
+ * [3] conv3x3_kernel (CUDA cores, one conv per launch), [4] other, [5] small_tower_kernel (fused CUDA-core towers),
+ * [6] small_search_kernel (small residual networks: all simulations of a search in one launch). */
+#define MZ_KERNEL_CLASSES 7
 int mz_kernel_timing(MzHandle* h, int32_t enable);
 int mz_kernel_times(MzHandle* h, double* ms, int64_t* count);
 

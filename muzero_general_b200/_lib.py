@@ -126,6 +126,7 @@ SYMBOLS = [
     ("mz_hidden_elems", C.c_int64, [C.c_void_p]),
     ("mz_obs_elems", C.c_int64, [C.c_void_p]),
     ("mz_launch_count", C.c_int64, [C.c_void_p]),
+    ("mz_graph_partitions", C.c_int32, [C.c_void_p]),
     ("mz_last_search_ms", C.c_double, [C.c_void_p]),
     ("mz_kernel_timing", C.c_int, [C.c_void_p, C.c_int32]),
     ("mz_kernel_times", C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),

@@ -11,6 +11,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
 #include <map>
 #include <string>
 #include <vector>
@@ -204,10 +205,15 @@ extern "C" int mz_destroy(MzHandle* h) {
     for (auto& kv : h->named) cudaFree(kv.second.first);
     if (h->h_in) cudaFreeHost(h->h_in);
     if (h->h_out) cudaFreeHost(h->h_out);
-    if (h->graph_exec) cudaGraphExecDestroy(h->graph_exec);
+    mz_drop_graphs(h);
     if (h->res) resnet_destroy(h->res);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
+    if (h->part_fork) cudaEventDestroy(h->part_fork);
+    for (int p = 0; p < MzHandle::kMaxParts; ++p) {
+        if (h->part_join[p]) cudaEventDestroy(h->part_join[p]);
+        if (h->part_stream[p]) cudaStreamDestroy(h->part_stream[p]);
+    }
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
     return MZ_OK;
@@ -222,6 +228,7 @@ extern "C" int64_t mz_hidden_elems(const MzHandle* h) { return h ? h->hidden_ele
 extern "C" int64_t mz_obs_elems(const MzHandle* h) { return h ? h->obs_elems : 0; }
 extern "C" int64_t mz_launch_count(const MzHandle* h) { return h ? h->launches : 0; }
 extern "C" double mz_last_search_ms(const MzHandle* h) { return h ? h->last_ms : 0.0; }
+extern "C" int32_t mz_graph_partitions(const MzHandle* h) { return h ? h->graph_parts : 1; }
 
 // ------------------------------------------------------------------------------------------
 // weights
@@ -303,8 +310,7 @@ extern "C" int mz_load_weights(MzHandle* h, const MzTensor* tensors, int32_t n) 
     if (!h || !tensors || n <= 0) return fail(h, MZ_EINVAL, "mz_load_weights: null argument");
     MZ_CUDA(h, cudaSetDevice(h->device));
     MZ_CUDA(h, cudaStreamSynchronize(h->stream));
-    if (h->graph_exec) { cudaGraphExecDestroy(h->graph_exec); h->graph_exec = nullptr; }   // weight buffers move
-    h->graph_key = 0; h->graph_seen = 0;
+    mz_drop_graphs(h);                 // weight buffers move
     int rc;
     if (h->net.kind == MZ_NET_FC) {
         rc = load_fc_weights(h, tensors, n);
@@ -373,9 +379,32 @@ void mz_switch_to_strict(MzHandle* h) {
     if (!h->res) return;
     resnet_use_strict(h->res);
     h->pool_state_elems = resnet_state_elems(h->res);
-    if (h->graph_exec) { cudaGraphExecDestroy(h->graph_exec); h->graph_exec = nullptr; }
-    h->graph_key = 0; h->graph_seen = 0;
+    mz_drop_graphs(h);
     h->range_fallbacks += 1;
+}
+
+void mz_drop_graphs(MzHandle* h) {
+    for (auto& e : h->graphs) if (e.exec) cudaGraphExecDestroy(e.exec);
+    h->graphs.clear();
+}
+
+// Number of parallel branches the captured graph of a search over n games is split into (1 = no split).
+// MZ_PARTS = 1 switches the partitioned replay off, 2..4 forces that many branches wherever the kernels allow it.
+static int search_partitions(MzHandle* h, int n, int continue_from) {
+    const char* penv = getenv("MZ_PARTS");
+    const int forced = penv ? atoi(penv) : 0;
+    if (forced == 1 || continue_from > 0 || h->net.kind != MZ_NET_RESNET || h->net.action_space > 32 || !h->res) return 1;
+    if (!resnet_can_partition(h->res)) return 1;
+    int parts = forced > 1 ? std::min(forced, (int)MzHandle::kMaxParts) : 2;
+    if (forced <= 1 && !resnet_uses_tensor_cores(h->res)) return 1;          // default: the tensor-core towers only
+    while (parts > 1 && n < parts * 64) --parts;
+    if (parts < 2) return 1;
+    for (int p = 1; p < parts; ++p) {
+        if (!h->part_stream[p] && cudaStreamCreateWithFlags(&h->part_stream[p], cudaStreamNonBlocking) != cudaSuccess) return 1;
+        if (!h->part_join[p] && cudaEventCreateWithFlags(&h->part_join[p], cudaEventDisableTiming) != cudaSuccess) return 1;
+    }
+    if (!h->part_fork && cudaEventCreateWithFlags(&h->part_fork, cudaEventDisableTiming) != cudaSuccess) return 1;
+    return parts;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -427,37 +456,82 @@ int mz_dispatch_search(MzHandle* h, const SearchCall& call, bool teacher, bool t
                               call.max_tree_depth, call.tie_count, call.root_priors, call.value_range};
         for (const void* q : ptrs) mix((uint64_t)(uintptr_t)q);
         mix((uint64_t)n); mix((uint64_t)call.add_noise); mix((uint64_t)call.keep_tree); mix((uint64_t)call_.continue_from);
-        auto eager = [&]() {
-            return run_stepwise_search(h->net, h->search, h->pool_n, h->pool, h->d_pbc, h->d_sqrt, h->d_ucb, h->fc, h->d_fc_blob, h->res, call_,
-                                       h->fc_group, h->sm_count, h->stream, &h->launches, &h->err);
+        auto run = [&](const SearchCall& sc, cudaStream_t st) {
+            return run_stepwise_search(h->net, h->search, h->pool_n, h->pool, h->d_pbc, h->d_sqrt, h->d_ucb, h->fc, h->d_fc_blob, h->res, sc,
+                                       h->fc_group, h->sm_count, st, &h->launches, &h->err);
         };
-        if (graphable && h->graph_exec && h->graph_key == key) {
-            MZ_CUDA(h, cudaGraphLaunch(h->graph_exec, h->stream));
-            h->launches += h->graph_launches;
-        } else if (graphable && h->graph_key == key && h->graph_seen >= 1) {
-            if (h->graph_exec) { cudaGraphExecDestroy(h->graph_exec); h->graph_exec = nullptr; }
+        auto eager = [&]() { return run(call_, h->stream); };
+        // Partitioned replay.  A simulation is a chain of dependent kernels (tower -> heads -> tower -> heads -> tree step) and
+        // the tensor-core towers leave the SMs they do not fill - and every SM during the heads / tree kernels - idle.  Games
+        // are independent, so the captured graph runs the simulations of P disjoint game ranges as P parallel branches: the
+        // towers of one range overlap the heads and tree steps of the others.  Every array stays addressed by the global
+        // game index, so the arithmetic per game - and every result - is exactly that of the whole-batch call.
+        const int parts = search_partitions(h, n, call_.continue_from);
+        auto partitioned = [&]() -> int {
+            SearchCall root = call_;
+            root.phases = kPhaseRoot;
+            int rc2 = run(root, h->stream);
+            if (rc2) return rc2;
+            if (cudaEventRecord(h->part_fork, h->stream) != cudaSuccess) return fail(h, MZ_ECUDA, "partitioned replay: fork");
+            const int per = ((n + parts - 1) / parts + 7) & ~7;
+            for (int p = 0; p < parts; ++p) {
+                SearchCall sc = call_;
+                sc.phases = kPhaseSims;
+                sc.g0 = p * per;
+                sc.n = std::min(per, n - sc.g0);
+                if (sc.n <= 0) continue;
+                cudaStream_t st = p == 0 ? h->stream : h->part_stream[p];
+                if (p > 0 && cudaStreamWaitEvent(st, h->part_fork, 0) != cudaSuccess) return fail(h, MZ_ECUDA, "partitioned replay: fork wait");
+                if ((rc2 = run(sc, st))) return rc2;
+                if (p > 0) {
+                    if (cudaEventRecord(h->part_join[p], st) != cudaSuccess || cudaStreamWaitEvent(h->stream, h->part_join[p], 0) != cudaSuccess)
+                        return fail(h, MZ_ECUDA, "partitioned replay: join");
+                }
+            }
+            return MZ_OK;
+        };
+        MzHandle::SearchGraph* gr = nullptr;
+        if (graphable) {
+            h->graph_tick += 1;
+            for (auto& e : h->graphs) if (e.key == key) gr = &e;
+            if (!gr) {
+                if ((int)h->graphs.size() < MzHandle::kMaxGraphs) {
+                    h->graphs.emplace_back();
+                    gr = &h->graphs.back();
+                } else {
+                    gr = &h->graphs[0];
+                    for (auto& e : h->graphs) if (e.used < gr->used) gr = &e;
+                    if (gr->exec) cudaGraphExecDestroy(gr->exec);
+                    *gr = MzHandle::SearchGraph{};
+                }
+                gr->key = key;
+            }
+            gr->used = h->graph_tick;
+        }
+        if (gr && gr->exec) {
+            MZ_CUDA(h, cudaGraphLaunch(gr->exec, h->stream));
+            h->launches += gr->launches;
+            h->graph_parts = gr->parts;
+        } else if (gr && gr->seen >= 1) {
             const int64_t l0 = h->launches;
             MZ_CUDA(h, cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
-            rc = eager();
+            rc = parts > 1 ? partitioned() : eager();
             cudaGraph_t graph = nullptr;
             cudaError_t ce = cudaStreamEndCapture(h->stream, &graph);
             if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
             if (ce != cudaSuccess) return fail(h, MZ_ECUDA, std::string("graph capture: ") + cudaGetErrorString(ce));
-            ce = cudaGraphInstantiate(&h->graph_exec, graph, 0);
+            ce = cudaGraphInstantiate(&gr->exec, graph, 0);
             cudaGraphDestroy(graph);
-            if (ce != cudaSuccess) { h->graph_exec = nullptr; return fail(h, MZ_ECUDA, std::string("graph instantiate: ") + cudaGetErrorString(ce)); }
-            h->graph_launches = h->launches - l0;
-            MZ_CUDA(h, cudaGraphLaunch(h->graph_exec, h->stream));
+            if (ce != cudaSuccess) { gr->exec = nullptr; return fail(h, MZ_ECUDA, std::string("graph instantiate: ") + cudaGetErrorString(ce)); }
+            gr->launches = h->launches - l0;
+            gr->parts = parts;
+            h->graph_parts = parts;
+            MZ_CUDA(h, cudaGraphLaunch(gr->exec, h->stream));
         } else {
             rc = eager();
             if (rc) return rc;
-            if (graphable) {
-                if (h->graph_key != key) {
-                    if (h->graph_exec) { cudaGraphExecDestroy(h->graph_exec); h->graph_exec = nullptr; }
-                    h->graph_key = key; h->graph_seen = 0;
-                }
-                h->graph_seen += 1;
-            }
+            if (gr) gr->seen += 1;
+            h->graph_parts = 1;
         }
     }
     return MZ_OK;

@@ -44,11 +44,25 @@ struct MzHandle {
     unsigned char* h_in = nullptr;
     unsigned char* h_out = nullptr;
     size_t in_cap = 0, out_cap = 0;
-    // CUDA graph of the step-wise pipeline for the last seen argument set (launch-bound inner loop)
-    uint64_t graph_key = 0;
-    int graph_seen = 0;
-    cudaGraphExec_t graph_exec = nullptr;
-    int64_t graph_launches = 0;
+    // CUDA graphs of the step-wise pipeline, one per argument set (callers that rotate a few input buffers - double
+    // buffering, bench.py's four batches - keep replaying): a set seen twice is captured, the least recently used of
+    // kMaxGraphs entries makes room
+    struct SearchGraph {
+        uint64_t key = 0;
+        int seen = 0;
+        cudaGraphExec_t exec = nullptr;
+        int64_t launches = 0;
+        int parts = 1;
+        uint64_t used = 0;             // tick of the last use
+    };
+    static constexpr int kMaxGraphs = 8;
+    std::vector<SearchGraph> graphs;
+    uint64_t graph_tick = 0;
+    // partitioned replay: the simulations of disjoint game ranges run as parallel branches of the graph (abi.cu)
+    static constexpr int kMaxParts = 4;
+    cudaStream_t part_stream[kMaxParts] = {nullptr, nullptr, nullptr, nullptr};     // [0] unused (= stream)
+    cudaEvent_t part_fork = nullptr, part_join[kMaxParts] = {nullptr, nullptr, nullptr, nullptr};
+    int graph_parts = 1;               // branches of the graph replayed last (mz_graph_partitions)
     // lazily allocated debug buffers
     std::vector<void*> debug_allocs;
     std::map<std::string, std::pair<void*, size_t>> named;
@@ -74,3 +88,4 @@ static inline int fail(MzHandle* h, int code, const std::string& msg) { return m
 int mz_dispatch_search(MzHandle* h, const mz::SearchCall& call, bool teacher, bool trace, int flags);
 void mz_selfplay_destroy(MzHandle* h);
 void mz_switch_to_strict(MzHandle* h);
+void mz_drop_graphs(MzHandle* h);             // captured graphs refer to buffers or kernels that are about to change

@@ -7,7 +7,7 @@
 
 namespace mz {
 
-enum KernelClass { KT_TREE = 0, KT_TOWER = 1, KT_HEADS = 2, KT_CONV = 3, KT_OTHER = 4, KT_SMALL = 5, KT_CLASSES = 6 };
+enum KernelClass { KT_TREE = 0, KT_TOWER = 1, KT_HEADS = 2, KT_CONV = 3, KT_OTHER = 4, KT_SMALL = 5, KT_SEARCH = 6, KT_CLASSES = 7 };
 
 void kt_enable(bool on);
 bool kt_enabled();

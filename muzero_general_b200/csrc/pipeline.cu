@@ -28,7 +28,10 @@ int run_stepwise_search(const MzNetDesc& net, const MzSearchDesc& search, int po
         return resnet_inference(res, c, stream, launches, err);
     };
 
+    const bool run_root = call.phases == kPhaseAll || (call.phases & kPhaseRoot);
+    const bool run_sims = call.phases == kPhaseAll || (call.phases & kPhaseSims);
     TreeStepArgs a{};
+    a.g0 = call.g0;
     a.n = n; a.N = NP; a.A = A; a.P = search.num_players;
     a.discount = search.discount; a.noise_frac = search.root_exploration_fraction; a.noise_alpha = search.root_dirichlet_alpha; a.seed = search.seed;
     a.pbc = d_pbc; a.sqrtn = d_sqrt; a.ucb = d_ucb; a.pool = pool;
@@ -39,6 +42,8 @@ int run_stepwise_search(const MzNetDesc& net, const MzSearchDesc& search, int po
     a.value_range = call.value_range; a.trace = call.trace;
 
     // ---- root
+    cudaError_t e = cudaSuccess;
+    if (run_root) {
     if (K0 > 0) {
         a.net_value = pool.net_value; a.net_reward = nullptr; a.net_policy = pool.net_policy;     // unused by do_root == 2
         a.value_stride = 1; a.policy_stride = A; a.policy_is_prior = 0;
@@ -47,7 +52,7 @@ int run_stepwise_search(const MzNetDesc& net, const MzSearchDesc& search, int po
         a.value_stride = 1; a.policy_stride = A; a.policy_is_prior = 1;
     } else {
         InferCall c{};
-        c.n = n; c.recurrent = 0; c.in = call.obs;
+        c.n = n; c.g0 = call.g0; c.recurrent = 0; c.in = call.obs;
         c.pool_hidden = pool.hidden; c.pool_stride = NP + 1; c.out_slot = 0;
         c.value = pool.net_value; c.policy_logits = pool.net_policy;
         int rc = infer(c);
@@ -57,14 +62,25 @@ int run_stepwise_search(const MzNetDesc& net, const MzSearchDesc& search, int po
     }
     a.sim = 0; a.do_root = K0 > 0 ? 0 : 1; a.do_update = 0; a.do_select = N > 0; a.do_final = N == 0;
     kt_begin(KT_TREE, stream);
-    cudaError_t e = cudaSuccess;
     if (K0 > 0) { e = launch_tree_adopt_root(a, stream); *launches += 1; }
     if (e == cudaSuccess) e = launch_tree_step(a, stream);
     kt_end(stream);
     if (e != cudaSuccess) return cuda_fail("tree_step(root)", e);
     *launches += 1;
+    }
+    if (!run_sims) return MZ_OK;
 
     // ---- simulations
+    if (!teacher && net.kind == MZ_NET_RESNET && K0 == 0 && N > 0 && !call.trace.depth) {
+        // small residual networks: ONE launch runs every simulation of every game (small_search.cu)
+        InferCall c{};
+        c.n = n; c.g0 = call.g0; c.recurrent = 1; c.action = pool.leaf_action; c.gather_parent = pool.leaf_parent;
+        c.pool_hidden = pool.hidden; c.pool_stride = NP + 1; c.out_slot = 1;
+        c.value = pool.net_value; c.reward = pool.net_reward; c.policy_logits = pool.net_policy;
+        a.net_value = pool.net_value; a.net_reward = pool.net_reward; a.net_policy = pool.net_policy;
+        a.value_stride = 1; a.policy_stride = A; a.policy_is_prior = 0;
+        if (resnet_small_search_supported(res, c, a, N)) return resnet_small_search(res, c, a, N, stream, launches, err);
+    }
     for (int sim = 0; sim < N; ++sim) {
         if (teacher) {
             a.net_value = call.teacher.value + sim; a.net_reward = call.teacher.reward + sim;
@@ -72,7 +88,7 @@ int run_stepwise_search(const MzNetDesc& net, const MzSearchDesc& search, int po
             a.value_stride = N; a.policy_stride = N * A; a.policy_is_prior = 1;
         } else {
             InferCall c{};
-            c.n = n; c.recurrent = 1; c.action = pool.leaf_action; c.gather_parent = pool.leaf_parent;
+            c.n = n; c.g0 = call.g0; c.recurrent = 1; c.action = pool.leaf_action; c.gather_parent = pool.leaf_parent;
             c.pool_hidden = pool.hidden; c.pool_stride = NP + 1; c.out_slot = (K0 > 0 ? K0 : 1) + sim;
             c.value = pool.net_value; c.reward = pool.net_reward; c.policy_logits = pool.net_policy;
             int rc = infer(c);

@@ -29,13 +29,19 @@ struct SearchCall {
     bool keep_tree;
     size_t out_bytes;
     int continue_from;             // > 0: MZ_FLAG_CONTINUE, the pool already holds this many expansions of every game
+    // Partitioned replay (abi.cu): the games [g0, g0 + n) of the batch, every array still addressed by the GLOBAL game
+    // index, and only some phases of the search.  g0 = 0, phases = kPhaseAll is the plain whole-batch call.
+    int g0;
+    int phases;
 };
+constexpr int kPhaseRoot = 1, kPhaseSims = 2, kPhaseAll = 0;      // 0 = both (so a zero-initialised call is a whole search)
 
 // One batched network call. Plain mode: sample g reads in[g*in_elems...] and writes hidden[g*H...].
 // Pool mode (gather_parent != nullptr): sample g reads pool_hidden[(g*pool_stride + gather_parent[g])*H...]
 // and writes its new state to pool_hidden[(g*pool_stride + out_slot)*H...].
 struct InferCall {
     int n, recurrent;
+    int g0;                        // first game of the call: every per-game array is addressed by g0 + local index
     const float* in;
     const int32_t* action;
     const int32_t* gather_parent;
@@ -47,6 +53,7 @@ struct InferCall {
 // One launch of the step-wise tree kernel (tree_kernels.cu).
 struct TreeStepArgs {
     int n, N, A, P;
+    int g0;                        // games [g0, g0 + n), arrays addressed by the global index
     int sim;                       // simulation selected by this launch (do_select); do_update handles sim-1
     int do_root, do_update, do_select, do_final;
     double discount, noise_frac, noise_alpha;
@@ -84,6 +91,12 @@ int resnet_debug_conv(int n, int C, int H, int W, const float* x, const float* w
                       const float* residual, int relu, int use_tc, float* out, int sm_count, std::string* err);
 const char* resnet_numerics(const ResNetDevice* r);
 int resnet_take_saturations(ResNetDevice* r, cudaStream_t stream);   // x3 range guard (synchronises)
+bool resnet_can_partition(const ResNetDevice* r);
+// fused search of small residual networks: all simulations in one launch (small_search.cu); MZ_SMALL_SEARCH=0 / 1 switches it off / on
+bool resnet_small_search_supported(ResNetDevice* r, const InferCall& first_recurrent, const TreeStepArgs& tree, int n_sims);
+int resnet_small_search(ResNetDevice* r, const InferCall& first_recurrent, const TreeStepArgs& tree, int n_sims, cudaStream_t stream,
+                        int64_t* launches, std::string* err);
+bool resnet_uses_tensor_cores(const ResNetDevice* r);                    // recurrent inference honours InferCall::g0 (x3 towers / fused small towers)
 void resnet_use_strict(ResNetDevice* r);                             // fp32 CUDA-core towers from now on   // arithmetic of the residual towers (bench.py dtype)
 int resnet_state_elems(const ResNetDevice* r);        // floats per stored hidden state in the pool
 int resnet_states_to_nchw(ResNetDevice* r, const float* states, int count, float* out, cudaStream_t stream);

@@ -26,18 +26,15 @@
 #include <cuda_fp16.h>
 
 #include "common.cuh"
+#include "heads.cuh"
 #include "ktimer.h"
 #include "small_tower.h"
+#include "small_search.h"
 #include "launch.h"
 #include "conv_tc.h"
 #include "pipeline.h"
 
 namespace mz {
-
-// Board layouts of the tensor-core towers (conv_tc.cu / conv_x3.cu): kLayoutF16 = one fp16 plane of 4096 halves,
-// kLayoutSplit = two fp16 planes, x_h then x_l with x ~ x_h + x_l / 2^11 (8192 halves = 4096 float slots per board).
-enum { kLayoutDense = 0, kLayoutF16 = 1, kLayoutSplit = 2 };
-constexpr float kSplitLoScale = 2048.0f, kSplitLoUnscale = 1.0f / 2048.0f;
 
 __device__ __forceinline__ float sat_f16_range(float v) { return fminf(fmaxf(v, -65504.0f), 65504.0f); }
 __device__ __forceinline__ void split_f32(float v, __half* hi, __half* lo) {
@@ -209,75 +206,12 @@ __global__ void avgpool3x3s2_kernel(const float* in, float* out, int planes, int
     out[i] = __fdiv_rn(s, 9.0f);
 }
 
-// ------------------------------------------------------------------------------------------
-// Heads: conv1x1(+bias) -> flatten (c,h,w) -> MLP -> logits (-> support_to_scalar), plus the
-// per-(sample, channel) min-max rescale of the state (models.py:530-553).  One CTA per sample.
-// ------------------------------------------------------------------------------------------
-struct HeadDesc {
-    int rc;                    // reduced channels
-    int w1_off, b1_off;        // conv1x1 weight [rc][C], bias [rc]
-    MlpDesc mlp;               // transposed layers in the same blob
-    int n_out;                 // logits
-};
-
-struct HeadsArgs {
-    const float* x;            // [n, C, HW] input state (raw trunk output)
-    const float* blob;
-    int n, C, HW, S;
-    int n_heads;
-    HeadDesc head[2];
-    float* logits[2];          // [n, n_out] or nullptr
-    float* scalar[2];          // [n] support_to_scalar or nullptr
-    // optional rescale of x into the hidden pool / a plain buffer
-    float* rescaled;           // [n, C*HW] or nullptr
-    float* pool_hidden;        // pool mode target
-    int pool_stride, out_slot;
-    int smem_floats;
-    int p64c4, W;              // kLayoutF16 / kLayoutSplit: input (and pool target) use the tensor-core board layout
-    float* state_p64c4;        // [n, 4096 fp16] rescaled state in P64C8 (input of the prediction tower), or nullptr
-    int w_lo, w_floats;        // slice of the head blob this launch needs (staged in shared memory)
-    int warp_floats;           // per-warp scratch: x tile + two activation vectors
-};
-
-// offset (in fp16 elements) of (channel c, dense position p) inside one P64S state of 4096 halves: position-major
-// rows of 64 channels, the 8-channel chunks of a row XOR-ed with (padded position % 8) (conv_tc.cu)
-__device__ __forceinline__ int p64c4_index(int c, int p, int W) {
-    const int pos = (p / W + 1) * 8 + (p % W);
-    return pos * 64 + ((((c >> 3) ^ (pos & 7))) << 3) + (c & 7);
-}
-
-// Persistent CTAs (one per SM), 1024 threads = 8 groups of 128: the head weights of this launch are staged
-// in shared memory once per CTA, then every GROUP takes one sample at a time (named barriers, groups never
-// wait for each other).  x is staged as a [position][channel] tile with 16-byte aligned rows (row stride C+4:
-// conflict-free for 128-bit row reads and for per-channel column scans).  Everything that touches global
-// memory or the weights moves 16 bytes per instruction: the P64S state is read and written as whole 8-channel
-// chunks, conv1x1 reads x rows and weight rows as float4, the FC layers read packed [in/4][out][4] weights and
-// float4 activations; index arithmetic with runtime divisors happens once per chunk, not per element.
-// The accumulation order of every dot product is ascending input index (as torch's reference loops are
-// compared with a tolerance anyway, this only keeps results independent of the vector width).
-// GROUP = 128 threads per sample for wide states (Connect4: 64 x 42), GROUP = 32 (one warp per sample, __syncwarp
-// instead of named barriers, 4x the samples in flight) when a sample is only a few hundred values (TicTacToe 16 x 9,
-// Breakout's 16 x 36 hidden board).
-constexpr int kHeadThreads = 1024;
-
-template <int GROUP>
-__device__ __forceinline__ void group_bar(int group) {
-    if constexpr (GROUP == 32) __syncwarp();
-    else asm volatile("bar.sync %0, %1;" ::"r"(group + 1), "r"(GROUP) : "memory");
-}
-
 template <int GROUP>
 __global__ void __launch_bounds__(kHeadThreads) heads_kernel(const __grid_constant__ HeadsArgs a) {
-    constexpr int kHeadGroup = GROUP;
     extern __shared__ __align__(16) float sm[];
-    const int C = a.C, HW = a.HW, CP = C + 4;
-    const int group = threadIdx.x / kHeadGroup, t = threadIdx.x % kHeadGroup, ngroups = blockDim.x / kHeadGroup;
+    const int group = threadIdx.x / GROUP, t = threadIdx.x % GROUP, ngroups = blockDim.x / GROUP;
     float* s_w = sm;                                                 // head blob slice [w_lo, w_lo + w_floats)
-    float* s_x = s_w + a.w_floats + (size_t)group * a.warp_floats;   // [HW][C+4]
-    float* s_lo = s_x + HW * CP;                                     // [C] channel minimum
-    float* s_sc = s_lo + C;                                          // [C] channel scale
-    float* s_part = s_sc + C;                                        // [2][2][C] partial extrema
-    float* s_act = s_part + 4 * C;                                   // per head: ping | pong
+    float* scratch = s_w + a.w_floats + (size_t)group * a.warp_floats;
     // board layout only (C = 64): padded row of dense position p, looked up instead of two runtime divisions per chunk
     __shared__ unsigned char s_pos[64];
     pdl_launch_dependents();
@@ -285,202 +219,14 @@ __global__ void __launch_bounds__(kHeadThreads) heads_kernel(const __grid_consta
         const float4* src = reinterpret_cast<const float4*>(a.blob + a.w_lo);
         float4* dst = reinterpret_cast<float4*>(s_w);
         for (int i = threadIdx.x; i < a.w_floats / 4; i += blockDim.x) dst[i] = src[i];
-        if (a.p64c4 && threadIdx.x < HW && threadIdx.x < 64)
+        if (a.p64c4 && threadIdx.x < a.HW && threadIdx.x < 64)
             s_pos[threadIdx.x] = (unsigned char)((threadIdx.x / a.W + 1) * 8 + (threadIdx.x % a.W));
     }
     __syncthreads();
     pdl_wait();                                                      // the weights are constants; x comes from the previous kernel
     const float* blob = s_w - a.w_lo;                                // blob[off] addresses the staged copy
-    constexpr int cj = 8;                                            // 8-channel chunks per position (board layout: C = 64)
-    const int c_shift = (C & (C - 1)) == 0 ? 31 - __clz(C) : -1;     // C is a power of two for every bundled network
-
-    for (int g = blockIdx.x * ngroups + group; g < a.n; g += gridDim.x * ngroups) {
-        // ---- stage x[p][c]
-        if (a.p64c4) {
-            const bool split = a.p64c4 == kLayoutSplit;
-            const uint4* x8 = reinterpret_cast<const uint4*>(reinterpret_cast<const __half*>(a.x) + (size_t)g * (split ? 8192 : 4096));
-            for (int i = t; i < cj * HW; i += kHeadGroup) {
-                const int j = i % cj, p = i / cj;
-                const int pos = s_pos[p];
-                const uint4 v = x8[pos * 8 + (j ^ (pos & 7))];
-                const __half2* h2 = reinterpret_cast<const __half2*>(&v);
-                float2 f0 = __half22float2(h2[0]), f1 = __half22float2(h2[1]);
-                float2 f2 = __half22float2(h2[2]), f3 = __half22float2(h2[3]);
-                if (split) {                                   // x = x_h + x_l / 2^11 (second plane)
-                    const uint4 w = x8[512 + pos * 8 + (j ^ (pos & 7))];
-                    const __half2* l2 = reinterpret_cast<const __half2*>(&w);
-                    const float2 g0 = __half22float2(l2[0]), g1 = __half22float2(l2[1]);
-                    const float2 g2 = __half22float2(l2[2]), g3 = __half22float2(l2[3]);
-                    f0.x = fmaf(g0.x, kSplitLoUnscale, f0.x); f0.y = fmaf(g0.y, kSplitLoUnscale, f0.y);
-                    f1.x = fmaf(g1.x, kSplitLoUnscale, f1.x); f1.y = fmaf(g1.y, kSplitLoUnscale, f1.y);
-                    f2.x = fmaf(g2.x, kSplitLoUnscale, f2.x); f2.y = fmaf(g2.y, kSplitLoUnscale, f2.y);
-                    f3.x = fmaf(g3.x, kSplitLoUnscale, f3.x); f3.y = fmaf(g3.y, kSplitLoUnscale, f3.y);
-                }
-                float4* d = reinterpret_cast<float4*>(s_x + p * CP + 8 * j);
-                d[0] = make_float4(f0.x, f0.y, f1.x, f1.y);
-                d[1] = make_float4(f2.x, f2.y, f3.x, f3.y);
-            }
-        } else {
-            const float* x = a.x + (size_t)g * C * HW;
-            for (int i = t; i < C * HW; i += kHeadGroup) s_x[(i % HW) * CP + i / HW] = x[i];
-        }
-        group_bar<GROUP>(group);
-
-        if (a.rescaled || a.pool_hidden || a.state_p64c4) {
-            // (x - min) / scale per channel over the positions (models.py:530-553).
-            // Phase A: channel extrema (two threads per channel when the group is wide enough).
-            const int parts = (2 * C <= kHeadGroup) ? 2 : 1;
-            for (int i = t; i < parts * C; i += kHeadGroup) {
-                const int c = c_shift >= 0 ? (i & (C - 1)) : i % C, part = c_shift >= 0 ? (i >> c_shift) : i / C;
-                const int p0 = (part * HW) / parts, p1 = ((part + 1) * HW) / parts;
-                float lo = INFINITY, hi = -INFINITY;
-                for (int p = p0; p < p1; ++p) { const float v = s_x[p * CP + c]; lo = fminf(lo, v); hi = fmaxf(hi, v); }
-                s_part[(part * 2) * C + c] = lo;
-                s_part[(part * 2 + 1) * C + c] = hi;
-            }
-            group_bar<GROUP>(group);
-            for (int c = t; c < C; c += kHeadGroup) {
-                float lo = s_part[c], hi = s_part[C + c];
-                if (parts == 2) { lo = fminf(lo, s_part[2 * C + c]); hi = fmaxf(hi, s_part[3 * C + c]); }
-                float sc = __fsub_rn(hi, lo);
-                if (sc < 1e-5f) sc = __fadd_rn(sc, 1e-5f);
-                s_lo[c] = lo; s_sc[c] = sc;
-            }
-            group_bar<GROUP>(group);
-            // Phase B: normalise and store
-            if (a.p64c4) {
-                for (int i = t; i < cj * HW; i += kHeadGroup) {
-                    const int j = i % cj, p = i / cj;
-                    const int pos = s_pos[p];
-                    const float4* xr = reinterpret_cast<const float4*>(s_x + p * CP + 8 * j);
-                    const float4* lr = reinterpret_cast<const float4*>(s_lo + 8 * j);
-                    const float4* sr = reinterpret_cast<const float4*>(s_sc + 8 * j);
-                    float v[8];
-#pragma unroll
-                    for (int q = 0; q < 2; ++q) {
-                        const float4 x4 = xr[q], l4 = lr[q], c4 = sr[q];
-                        v[4 * q + 0] = div_pos_or_zero(__fsub_rn(x4.x, l4.x), c4.x);
-                        v[4 * q + 1] = div_pos_or_zero(__fsub_rn(x4.y, l4.y), c4.y);
-                        v[4 * q + 2] = div_pos_or_zero(__fsub_rn(x4.z, l4.z), c4.z);
-                        v[4 * q + 3] = div_pos_or_zero(__fsub_rn(x4.w, l4.w), c4.w);
-                    }
-                    if (a.rescaled) {
-#pragma unroll
-                        for (int e = 0; e < 8; ++e) a.rescaled[(size_t)g * C * HW + (8 * j + e) * HW + p] = v[e];
-                    }
-                    uint4 packed, packed_lo;                        // 16-bit operands of the tensor-core convs
-                    __half2* h2 = reinterpret_cast<__half2*>(&packed);
-                    __half2* l2 = reinterpret_cast<__half2*>(&packed_lo);
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) {                   // values are in [0, 1]: no range concerns
-                        h2[e] = __floats2half2_rn(v[2 * e], v[2 * e + 1]);
-                        const float2 back = __half22float2(h2[e]);
-                        l2[e] = __floats2half2_rn((v[2 * e] - back.x) * kSplitLoScale, (v[2 * e + 1] - back.y) * kSplitLoScale);
-                    }
-                    const bool split = a.p64c4 == kLayoutSplit;
-                    const int off8 = pos * 8 + (j ^ (pos & 7));     // in 16-byte units inside the state's first plane
-                    const size_t board16 = split ? 1024 : 512;      // 16-byte units per stored state
-                    if (a.pool_hidden) {
-                        uint4* dst = reinterpret_cast<uint4*>(a.pool_hidden) + ((size_t)g * a.pool_stride + a.out_slot) * board16;
-                        dst[off8] = packed;
-                        if (split) dst[512 + off8] = packed_lo;
-                    }
-                    if (a.state_p64c4) {
-                        uint4* dst = reinterpret_cast<uint4*>(a.state_p64c4) + (size_t)g * board16;
-                        dst[off8] = packed;
-                        if (split) dst[512 + off8] = packed_lo;
-                    }
-                }
-            } else {
-                for (int i = t; i < C * HW; i += kHeadGroup) {
-                    const int c = i / HW, p = i % HW;
-                    const float v = div_pos_or_zero(__fsub_rn(s_x[p * CP + c], s_lo[c]), s_sc[c]);
-                    if (a.rescaled) a.rescaled[(size_t)g * C * HW + i] = v;
-                    if (a.pool_hidden) a.pool_hidden[((size_t)g * a.pool_stride + a.out_slot) * C * HW + i] = v;
-                }
-            }
-        }
-
-        if (a.n_heads > 0) {
-            // the heads of this launch side by side: head h owns threads [h*span, (h+1)*span)
-            const int span = kHeadGroup / a.n_heads;
-            const int h = t / span, u = t % span;
-            const HeadDesc& d = a.head[h];
-            float* cur = s_act + (size_t)h * 2 * a.smem_floats;
-            float* nxt = cur + a.smem_floats;
-            // conv1x1: r[c][p] = b[c] + sum_k W[c][k] x[p][k]; one thread per position, 4 channels at a time
-            for (int p = u; p < HW; p += span) {
-                const float4* xr = reinterpret_cast<const float4*>(s_x + p * CP);
-                for (int c0 = 0; c0 < d.rc; c0 += 4) {
-                    const int nc = min(4, d.rc - c0);
-                    float acc[4];
-#pragma unroll
-                    for (int cc = 0; cc < 4; ++cc) acc[cc] = cc < nc ? blob[d.b1_off + c0 + cc] : 0.0f;
-                    const float4* w0 = reinterpret_cast<const float4*>(blob + d.w1_off + (size_t)c0 * C);
-                    for (int k4 = 0; k4 < C / 4; ++k4) {
-                        const float4 x4 = xr[k4];
-#pragma unroll
-                        for (int cc = 0; cc < 4; ++cc) {
-                            if (cc < nc) {
-                                const float4 w4 = w0[cc * (C / 4) + k4];
-                                acc[cc] = fmaf(w4.x, x4.x, acc[cc]);
-                                acc[cc] = fmaf(w4.y, x4.y, acc[cc]);
-                                acc[cc] = fmaf(w4.z, x4.z, acc[cc]);
-                                acc[cc] = fmaf(w4.w, x4.w, acc[cc]);
-                            }
-                        }
-                    }
-#pragma unroll
-                    for (int cc = 0; cc < 4; ++cc)
-                        if (cc < nc) cur[(c0 + cc) * HW + p] = acc[cc];      // flatten order (c, h, w) = NCHW view(-1, ...)
-                }
-            }
-            if (u < 4) { const int i = d.rc * HW + u; if (i < ((d.rc * HW + 3) & ~3)) cur[i] = 0.0f; }   // zero the padding
-            group_bar<GROUP>(group);
-            const int max_layers = max(a.head[0].mlp.n, a.head[a.n_heads - 1].mlp.n);
-            for (int l = 0; l < max_layers; ++l) {
-                if (l < d.mlp.n) {
-                    const int in4 = (d.mlp.in[l] + 3) >> 2, out = d.mlp.out[l];
-                    const float4* W4 = reinterpret_cast<const float4*>(blob + d.mlp.w_off[l]);      // [in/4][out][4]
-                    const float4* a4 = reinterpret_cast<const float4*>(cur);
-                    const float* b = blob + d.mlp.b_off[l];
-                    const bool last = l == d.mlp.n - 1;
-                    for (int o = u; o < ((out + 3) & ~3); o += span) {
-                        if (o < out) {
-                            float acc = b[o];
-#pragma unroll 4
-                            for (int i = 0; i < in4; ++i) {
-                                const float4 x4 = a4[i], w4 = W4[(size_t)i * out + o];
-                                acc = fmaf(x4.x, w4.x, acc);
-                                acc = fmaf(x4.y, w4.y, acc);
-                                acc = fmaf(x4.z, w4.z, acc);
-                                acc = fmaf(x4.w, w4.w, acc);
-                            }
-                            nxt[o] = last ? acc : elu1(acc);
-                        } else {
-                            nxt[o] = 0.0f;                          // padding read by the next layer's float4 loads
-                        }
-                    }
-                    float* tmp = cur; cur = nxt; nxt = tmp;
-                }
-                group_bar<GROUP>(group);
-            }
-            if (a.logits[h])
-                for (int o = u; o < d.n_out; o += span) a.logits[h][(size_t)g * d.n_out + o] = cur[o];
-            if (a.scalar[h]) {
-                if (span >= 32) {                          // span is a multiple of 32: the head's first warp
-                    if (u < 32) {
-                        const float v = support_to_scalar_group<32>(cur, a.S);
-                        if (u == 0) a.scalar[h][g] = v;
-                    }
-                } else {                                   // two heads share a warp: 16 lanes each
-                    const float v = support_to_scalar_group<16>(cur, a.S);
-                    if (u == 0) a.scalar[h][g] = v;
-                }
-            }
-        }
-        group_bar<GROUP>(group);
-    }
+    for (int g = a.g0 + blockIdx.x * ngroups + group; g < a.g0 + a.n; g += gridDim.x * ngroups)
+        heads_one_sample<GROUP>(a, blob, scratch, s_pos, g, group, t, a.out_slot);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -959,6 +705,7 @@ int resnet_load_weights(ResNetDevice* r, const MzTensor* tensors, int n, std::st
 namespace {
 struct Runner {
     ResNetDevice* r; cudaStream_t stream; int64_t* launches; std::string* err; int n;
+    int g0 = 0;                // games [g0, g0 + n) of the batch (partitioned replay); buffers are addressed by the global index
     bool fail(const char* what, cudaError_t e) { *err = std::string(what) + ": " + cudaGetErrorString(e); return false; }
 
     // conv: in -> out. `in` may be gathered from the pool; action adds the constant plane.
@@ -976,7 +723,7 @@ struct Runner {
         a.n = n; a.H = r->hh; a.W = r->hw; a.A = r->net.action_space;
         static const int dbg = getenv("MZ_TC_DEBUG_SKIP") ? atoi(getenv("MZ_TC_DEBUG_SKIP")) : 0;
         a.debug_skip = dbg;
-        a.g0 = 0; a.sat_count = r->d_sat;
+        a.g0 = g0; a.sat_count = r->d_sat;
         kt_begin(KT_TOWER, stream);
         cudaError_t e = r->split ? launch_conv_tower_x3(a, r->sm_count, stream) : launch_conv_tower_tc(a, r->sm_count, stream);
         kt_end(stream);
@@ -1077,6 +824,7 @@ struct Runner {
     bool conv(const ConvLayer& l, const float* in, float* out, const float* residual, bool relu, int Hin, int Win,
               const int32_t* gather_parent = nullptr, int pool_stride = 0, const int32_t* action = nullptr,
               bool out_p64c4 = false) {
+        if (g0 != 0) { *err = "conv3x3: partitioned calls are not supported on the per-layer route"; return false; }
         ConvArgs a{};
         a.out_p64c4 = out_p64c4 ? (r->split ? kLayoutSplit : kLayoutF16) : 0;
         a.in = in; a.out = out; a.residual = residual; a.w = r->d_conv + l.w_off;
@@ -1133,23 +881,32 @@ struct Runner {
 
     // [optional stem conv] + `count` residual blocks as ONE fused CUDA-core launch (small_tower.cu).
     // Returns 1 = launched, 0 = shape not supported (caller falls back to one launch per conv), -1 = error.
-    int small_tower(const std::vector<ConvLayer>& layers, size_t first, bool stem, size_t count, const float* in, float* out,
-                    int in_channels, int H, int W, const int32_t* gather_parent = nullptr, int pool_stride = 0,
-                    const int32_t* action = nullptr) {
-        const bool off = !r->fuse_small;
+    // arguments of a fused CUDA-core tower; false when the layers are not of the supported kind
+    bool small_tower_args(SmallTowerArgs& a, const std::vector<ConvLayer>& layers, size_t first, bool stem, size_t count, const float* in,
+                          float* out, int in_channels, int H, int W, const int32_t* gather_parent, int pool_stride, const int32_t* action) {
         const size_t nl = (stem ? 1 : 0) + 2 * count;
-        if (off || nl == 0 || nl > (size_t)kSmallTowerMaxLayers) return 0;
-        SmallTowerArgs a{};
+        if (nl == 0 || nl > (size_t)kSmallTowerMaxLayers) return false;
+        a = SmallTowerArgs{};
         a.in = in; a.out = out; a.blob = r->d_conv; a.gather_parent = gather_parent; a.action = action; a.pool_stride = pool_stride;
-        a.n = n; a.C = r->C; a.H = H; a.W = W; a.A = r->net.action_space; a.in_channels = in_channels; a.n_layers = (int)nl;
+        a.n = n; a.g0 = g0; a.C = r->C; a.H = H; a.W = W; a.A = r->net.action_space; a.in_channels = in_channels; a.n_layers = (int)nl;
         for (size_t i = 0; i < nl; ++i) {
             const ConvLayer& l = layers[first + i];
-            if (l.stride != 1 || l.cout != r->C) return 0;
+            if (l.stride != 1 || l.cout != r->C) return false;
             SmallTowerLayer& t = a.layer[i];
             t.w_off = (int)l.w_off; t.b_off = (int)l.b_off; t.cin = l.cin; t.relu = 1;
             t.residual = (i >= (stem ? 1u : 0u) && ((i - (stem ? 1 : 0)) & 1)) ? 1 : 0;     // second conv of a block
         }
+        return true;
+    }
+
+    int small_tower(const std::vector<ConvLayer>& layers, size_t first, bool stem, size_t count, const float* in, float* out,
+                    int in_channels, int H, int W, const int32_t* gather_parent = nullptr, int pool_stride = 0,
+                    const int32_t* action = nullptr, bool dry_run = false) {
+        if (!r->fuse_small) return 0;
+        SmallTowerArgs a{};
+        if (!small_tower_args(a, layers, first, stem, count, in, out, in_channels, H, W, gather_parent, pool_stride, action)) return 0;
         if (!small_tower_supported(a)) return 0;
+        if (dry_run) return 1;
         kt_begin(KT_SMALL, stream);
         cudaError_t e = launch_small_tower(a, r->sm_count, stream);
         kt_end(stream);
@@ -1172,6 +929,7 @@ struct Runner {
     bool heads_big(const float* x, int n_heads, const HeadDesc* const* hs, float* l0, float* l1, float* s0, float* s1,
                    float* rescaled, float* pool_hidden, int pool_stride, int out_slot) {
         const int C = r->C, HW = r->hh * r->hw, S = r->net.support_size;
+        if (g0 != 0) { *err = "heads (generic route): partitioned calls are not supported"; return false; }
         kt_begin(KT_HEADS, stream);
         if (rescaled || pool_hidden) {
             big_rescale_kernel<<<(n * C + 127) / 128, 128, 0, stream>>>(x, n, C, HW, rescaled, pool_hidden, pool_stride, out_slot);
@@ -1213,11 +971,12 @@ struct Runner {
         return true;
     }
 
-    bool heads(const float* x, int n_heads, const HeadDesc* h0, const HeadDesc* h1, float* l0, float* l1, float* s0, float* s1,
-               float* rescaled, float* pool_hidden, int pool_stride, int out_slot, bool p64c4 = false, float* state_p64c4 = nullptr) {
+    // arguments of one heads launch (everything but the launch geometry)
+    HeadsArgs heads_args(const float* x, int n_heads, const HeadDesc* h0, const HeadDesc* h1, float* l0, float* l1, float* s0, float* s1,
+                         float* rescaled, float* pool_hidden, int pool_stride, int out_slot, bool p64c4 = false, float* state_p64c4 = nullptr) {
         HeadsArgs a{};
         a.p64c4 = p64c4 ? (r->split ? kLayoutSplit : kLayoutF16) : 0; a.W = r->hw; a.state_p64c4 = state_p64c4;
-        a.x = x; a.blob = r->d_head; a.n = n; a.C = r->C; a.HW = r->hh * r->hw; a.S = r->net.support_size;
+        a.x = x; a.blob = r->d_head; a.n = n; a.g0 = g0; a.C = r->C; a.HW = r->hh * r->hw; a.S = r->net.support_size;
         a.n_heads = n_heads;
         int maxw = 32;
         const HeadDesc* hs[2] = {h0, h1};
@@ -1240,6 +999,13 @@ struct Runner {
         if (n_heads == 0) { lo = 0; hi = 0; }
         a.w_lo = lo; a.w_floats = ((hi - lo) + 3) & ~3;
         a.warp_floats = (a.HW * (a.C + 4) + 6 * a.C + 4 * a.smem_floats + 3) & ~3;   // x tile + channel stats + (ping, pong) per head
+        return a;
+    }
+
+    bool heads(const float* x, int n_heads, const HeadDesc* h0, const HeadDesc* h1, float* l0, float* l1, float* s0, float* s1,
+               float* rescaled, float* pool_hidden, int pool_stride, int out_slot, bool p64c4 = false, float* state_p64c4 = nullptr) {
+        HeadsArgs a = heads_args(x, n_heads, h0, h1, l0, l1, s0, s1, rescaled, pool_hidden, pool_stride, out_slot, p64c4, state_p64c4);
+        const HeadDesc* hs[2] = {h0, h1};
         // one warp per sample when a sample is small (and, for small batches, only as many groups per CTA as it takes
         // to give every SM work); 128 threads per sample otherwise
         const bool narrow = a.C * a.HW <= 1024 && n_heads <= 2;
@@ -1280,7 +1046,8 @@ struct Runner {
 static int resnet_inference_tc(ResNetDevice* r, const InferCall& c, cudaStream_t stream, int64_t* launches, std::string* err) {
     const MzNetDesc& nd = r->net;
     const int n = c.n, C = r->C, hh = r->hh, hw = r->hw, F = 2 * nd.support_size + 1;
-    Runner R{r, stream, launches, err, n};
+    Runner R{r, stream, launches, err, n, c.g0};
+    if (c.g0 != 0 && (!r->split || !c.recurrent || !c.gather_parent)) { *err = "resnet: partitioned calls need the x3 towers in pool mode"; return MZ_EINVAL; }
     float *cur = r->ws[0], *tmp = r->ws[1], *spare = r->ws[2];
     float* state = r->scratch_state;                   // rescaled state, P64C4, input of the prediction tower
     if (!c.recurrent) {
@@ -1323,6 +1090,32 @@ static int resnet_inference_tc(ResNetDevice* r, const InferCall& c, cudaStream_t
 }
 
 int resnet_state_elems(const ResNetDevice* r) { return r->state_elems; }
+bool resnet_uses_tensor_cores(const ResNetDevice* r) { return r->use_tc; }
+
+// Partitioned replay (abi.cu) needs every kernel of a recurrent inference to honour a first-game offset: the x3 towers,
+// the fused small towers and heads_kernel do; the per-layer convs, the fp16-mode towers and the generic heads route do not.
+bool resnet_can_partition(const ResNetDevice* r0) {
+    ResNetDevice* r = const_cast<ResNetDevice*>(r0);
+    if (!r->loaded) return false;
+    if (r->use_tc) return r->split;
+    std::string err; int64_t launches = 0;
+    Runner R{r, nullptr, &launches, &err, r->max_batch, 0};
+    const int nb = r->net.blocks;
+    if (nb < 1) return false;
+    if (R.small_tower(r->dyn, 0, true, nb, nullptr, nullptr, r->C, r->hh, r->hw, nullptr, 0, reinterpret_cast<const int32_t*>(r), true) != 1) return false;
+    if (R.small_tower(r->pred, 0, false, nb, nullptr, nullptr, r->C, r->hh, r->hw, nullptr, 0, nullptr, true) != 1) return false;
+    // heads_kernel route (not heads_big): the head weights plus one group's tile fit in shared memory
+    const int HW = r->hh * r->hw;
+    int hi = 0, lo = 1 << 30, maxw = 32;
+    for (const HeadDesc* d : {&r->reward_head, &r->value_head, &r->policy_head}) {
+        lo = std::min(lo, d->w1_off);
+        hi = std::max(hi, d->mlp.b_off[d->mlp.n - 1] + d->mlp.out[d->mlp.n - 1]);
+        maxw = std::max(maxw, d->rc * HW + 4);
+        for (int l = 0; l < d->mlp.n; ++l) maxw = std::max(maxw, d->mlp.out[l] + 4);
+    }
+    const size_t warp_floats = (size_t)HW * (r->C + 4) + 6 * r->C + 4 * ((maxw + 3) & ~3);
+    return ((size_t)(hi - lo) + warp_floats) * 4 <= 227 * 1024;
+}
 const char* resnet_numerics(const ResNetDevice* r) {
     if (!r->use_tc) return r->fell_back ? "f32 nets + f64 tree statistics (tensor-core towers left after an activation exceeded the fp16 range)"
                                         : "f32 nets + f64 tree statistics";
@@ -1440,13 +1233,79 @@ int resnet_states_from_nchw(ResNetDevice* r, const float* dense, int count, floa
     return cudaGetLastError() == cudaSuccess ? MZ_OK : MZ_ECUDA;
 }
 
+// Fused search for small residual networks (small_search.cu): all the simulations of the games [c.g0, c.g0 + c.n) in ONE
+// launch.  `c` is the recurrent call of the first simulation (pool mode), `tree` the tree step that follows it; the
+// arguments of the towers and the heads are the ones resnet_inference would launch with, simulation after simulation.
+static bool small_search_build(ResNetDevice* r, const InferCall& c, const TreeStepArgs& tree, int n_sims, SmallSearchArgs* out,
+                               int* P, int* CO, int* G, int* threads, size_t* smem) {
+    if (r->use_tc || !r->loaded || !r->fuse_small || !c.recurrent || !c.gather_parent || c.hidden || r->net.blocks < 1) return false;
+    if (c.value_logits || c.reward_logits) return false;
+    std::string err; int64_t launches = 0;
+    Runner R{r, nullptr, &launches, &err, c.n, c.g0};
+    const int C = r->C, hh = r->hh, hw = r->hw, nb = r->net.blocks;
+    SmallSearchArgs a{};
+    float* raw = r->ws[0];                 // dynamics tower output
+    float* pred_out = r->ws[1];            // prediction tower output
+    float* hidden = r->scratch_hidden;     // rescaled state, dense (input of the prediction tower)
+    if (!R.small_tower_args(a.dyn, r->dyn, 0, true, nb, c.pool_hidden, raw, C, hh, hw, c.gather_parent, c.pool_stride, c.action)) return false;
+    if (!R.small_tower_args(a.pred, r->pred, 0, false, nb, hidden, pred_out, C, hh, hw, nullptr, 0, nullptr)) return false;
+    if (!small_tower_layout(a.dyn) || !small_tower_layout(a.pred)) return false;
+    const int cap = std::max(a.dyn.cap_channels, a.pred.cap_channels);
+    a.dyn.cap_channels = a.pred.cap_channels = cap;
+    a.heads_dyn = R.heads_args(raw, 1, &r->reward_head, nullptr, nullptr, nullptr, c.reward, nullptr, hidden, c.pool_hidden, c.pool_stride, c.out_slot);
+    a.heads_pred = R.heads_args(pred_out, 2, &r->value_head, &r->policy_head, nullptr, c.policy_logits, c.value, nullptr, nullptr, nullptr, 0, 0);
+    if (!(a.heads_dyn.C * a.heads_dyn.HW <= 1024)) return false;                   // one warp per sample (heads_kernel<32>)
+    const int lo = std::min(a.heads_dyn.w_lo, a.heads_pred.w_lo);
+    const int hi = std::max(a.heads_dyn.w_lo + a.heads_dyn.w_floats, a.heads_pred.w_lo + a.heads_pred.w_floats);
+    a.heads_lo = lo & ~3; a.heads_floats = ((hi - a.heads_lo) + 3) & ~3;
+    a.scratch_floats = std::max(a.heads_dyn.warp_floats, a.heads_pred.warp_floats);
+    a.tree = tree;
+    a.n = c.n; a.g0 = c.g0; a.n_sims = n_sims; a.first_slot = c.out_slot;
+    int tile = 0;
+    const int tower_floats = ((a.dyn.w_floats + 3) & ~3) + ((a.pred.w_floats + 3) & ~3);
+    if (!small_search_shape(hh, hw, C, r->net.action_space, c.n, r->sm_count, tower_floats, a.heads_floats, a.scratch_floats, cap,
+                            P, CO, G, &tile, threads, smem))
+        return false;
+    a.tile = tile;
+    a.dyn.boards_per_cta = a.pred.boards_per_cta = tile;
+    a.off_wd = 0;
+    a.off_wp = (a.dyn.w_floats + 3) & ~3;
+    a.off_wh = tower_floats;
+    a.off_scratch = a.off_wh + a.heads_floats;
+    a.off_act = a.off_scratch + (*threads / 32) * a.scratch_floats;
+    *out = a;
+    return true;
+}
+
+bool resnet_small_search_supported(ResNetDevice* r, const InferCall& c, const TreeStepArgs& tree, int n_sims) {
+    // A/B switch: MZ_SMALL_SEARCH=0 keeps the step-wise pipeline, =1 uses the fused kernel wherever the shape allows
+    constexpr bool kDefaultOn = false;
+    const char* sw = getenv("MZ_SMALL_SEARCH");
+    if (sw ? sw[0] != '1' : !kDefaultOn) return false;
+    SmallSearchArgs a; int P, CO, G, threads; size_t smem;
+    return small_search_build(r, c, tree, n_sims, &a, &P, &CO, &G, &threads, &smem);
+}
+
+int resnet_small_search(ResNetDevice* r, const InferCall& c, const TreeStepArgs& tree, int n_sims, cudaStream_t stream, int64_t* launches,
+                        std::string* err) {
+    SmallSearchArgs a; int P, CO, G, threads; size_t smem;
+    if (!small_search_build(r, c, tree, n_sims, &a, &P, &CO, &G, &threads, &smem)) { *err = "small_search: shape not supported"; return MZ_EINVAL; }
+    kt_begin(KT_SEARCH, stream);
+    cudaError_t e = launch_small_search(a, P, CO, G, threads, smem, stream);
+    kt_end(stream);
+    if (e != cudaSuccess) { *err = std::string("small_search launch: ") + cudaGetErrorString(e); return MZ_ECUDA; }
+    *launches += 1;
+    return MZ_OK;
+}
+
 int resnet_inference(ResNetDevice* r, const InferCall& c, cudaStream_t stream, int64_t* launches, std::string* err) {
     if (!r->loaded) { *err = "weights not loaded"; return MZ_ESTATE; }
-    if (c.n > r->max_batch) { *err = "batch larger than max_games"; return MZ_EINVAL; }
+    if (c.g0 < 0 || c.g0 + c.n > r->max_batch) { *err = "batch larger than max_games"; return MZ_EINVAL; }
     if (r->use_tc) return resnet_inference_tc(r, c, stream, launches, err);
     const MzNetDesc& nd = r->net;
     const int n = c.n, C = r->C, hh = r->hh, hw = r->hw, F = 2 * nd.support_size + 1;
-    Runner R{r, stream, launches, err, n};
+    Runner R{r, stream, launches, err, n, c.g0};
+    if (c.g0 != 0 && !c.recurrent) { *err = "resnet: partitioned calls are recurrent only"; return MZ_EINVAL; }
     float *cur = r->ws[0], *tmp = r->ws[1], *spare = r->ws[2];
     float* hidden_out = c.hidden ? c.hidden : r->scratch_hidden;
 

@@ -13,6 +13,7 @@
 // that row for CO channels (P x CO accumulators; P = W, or W/2 for small latency-bound batches); CO = 4 when the batch is large enough to fill the GPU that way (float4
 // weight loads, 4.5+ FMAs per shared-memory load), CO = 1 for small batches (4x the threads, lower latency).
 #include "small_tower.h"
+#include "small_tower.cuh"
 #include "launch.h"
 
 #include <algorithm>
@@ -25,133 +26,43 @@ constexpr int kMaxThreads = 704;      // 22 warps: one CTA can hold a whole SM's
 template <int P, int CO>
 __global__ void __launch_bounds__(kMaxThreads) small_tower_kernel(const __grid_constant__ SmallTowerArgs a) {
     extern __shared__ __align__(16) float smem[];
-    const int H = a.H, W = a.W, C = a.C;
-    const int Wp = W + 2;
-    const int plane = (H + 2) * Wp;
-    const int segs = W / P;                                 // row segments: a thread owns P consecutive pixels of a row
-    const int nb = a.boards_per_cta, cap = a.cap_channels;
-    const int bufsz = nb * cap * plane;
     float* s_w = smem;
     float* s_act = smem + a.w_floats;
-
     // ---- once per CTA: weights + biases of every layer, zeroed activation buffers (padding stays zero)
     pdl_launch_dependents();
-    for (int l = 0; l < a.n_layers; ++l) {
-        const int count = a.layer[l].cin * 9 * C;
-        const float4* src = reinterpret_cast<const float4*>(a.blob + a.layer[l].w_off);
-        float4* dst = reinterpret_cast<float4*>(s_w + a.w_smem_off[l]);
-        for (int i = threadIdx.x; i < count / 4; i += blockDim.x) dst[i] = src[i];
-        for (int i = threadIdx.x; i < C; i += blockDim.x)
-            s_w[a.b_smem_off[l] + i] = a.layer[l].b_off >= 0 ? a.blob[a.layer[l].b_off + i] : 0.0f;
-    }
-    for (int i = threadIdx.x; i < 2 * bufsz; i += blockDim.x) s_act[i] = 0.0f;
+    small_tower_stage(a, s_w, s_act, threadIdx.x, blockDim.x);
     pdl_wait();                                            // weights are constants; the input comes from the previous kernel
-
-    const int cgs = C / CO;
-    const int items_per_board = cgs * H * segs;
-    const int item = threadIdx.x;
-    const int cgi = item % cgs;
-    const int seg = (item / cgs) % segs;
-    const int y = (item / (cgs * segs)) % H;
-    const int b = item / items_per_board;
-    const int HW = H * W;
-    const int cin0 = a.layer[0].cin;
-    const size_t sample_elems = (size_t)a.in_channels * HW;
-
-    for (int tile = blockIdx.x; tile * nb < a.n; tile += gridDim.x) {
-        const int b0 = tile * nb;
-        const int nbt = min(nb, a.n - b0);
-        __syncthreads();                                   // previous tile fully consumed / initial fill visible
-        // ---- stage the tower input (interior only) into buffer 0
-        for (int i = threadIdx.x; i < nbt * cin0 * HW; i += blockDim.x) {
-            const int x = i % W, yy = (i / W) % H, ci = (i / HW) % cin0, bb = i / (HW * cin0);
-            const int g = b0 + bb;
-            float v;
-            if (ci < a.in_channels) {
-                const float* src = a.gather_parent ? a.in + ((size_t)g * a.pool_stride + a.gather_parent[g]) * sample_elems
-                                                   : a.in + (size_t)g * sample_elems;
-                v = src[ci * HW + yy * W + x];
-            } else {
-                v = __fdiv_rn((float)a.action[g], (float)a.A);        // action / |A| plane (models.py:586-600)
-            }
-            s_act[(bb * cap + ci) * plane + (yy + 1) * Wp + x + 1] = v;
-        }
-        __syncthreads();
-
-        const bool active = b < nbt;
-        int cur = 0;
-        for (int l = 0; l < a.n_layers; ++l) {
-            const float* sin = s_act + cur * bufsz;
-            float* sout = s_act + (cur ^ 1) * bufsz;
-            if (active) {
-                float acc[CO][P];
-#pragma unroll
-                for (int c = 0; c < CO; ++c)
-#pragma unroll
-                    for (int p = 0; p < P; ++p) acc[c][p] = 0.0f;
-                const float* ib = sin + b * cap * plane + y * Wp + seg * P;
-                const float* wb = s_w + a.w_smem_off[l] + cgi * CO;
-                const int cin = a.layer[l].cin;
-                for (int ci = 0; ci < cin; ++ci) {
-#pragma unroll
-                    for (int dy = 0; dy < 3; ++dy) {
-                        float v[P + 2];
-#pragma unroll
-                        for (int j = 0; j < P + 2; ++j) v[j] = ib[ci * plane + dy * Wp + j];
-#pragma unroll
-                        for (int dx = 0; dx < 3; ++dx) {
-                            float w[CO];
-                            if constexpr (CO == 4) {
-                                const float4 w4 = *reinterpret_cast<const float4*>(wb + (ci * 9 + dy * 3 + dx) * C);
-                                w[0] = w4.x; w[1] = w4.y; w[2] = w4.z; w[3] = w4.w;
-                            } else {
-#pragma unroll
-                                for (int c = 0; c < CO; ++c) w[c] = wb[(ci * 9 + dy * 3 + dx) * C + c];
-                            }
-#pragma unroll
-                            for (int p = 0; p < P; ++p)
-#pragma unroll
-                                for (int c = 0; c < CO; ++c) acc[c][p] = fmaf(v[p + dx], w[c], acc[c][p]);
-                        }
-                    }
-                }
-                const bool last = l == a.n_layers - 1;
-                const int g = b0 + b;
-#pragma unroll
-                for (int c = 0; c < CO; ++c) {
-                    const int co = cgi * CO + c;
-                    const float bias = s_w[a.b_smem_off[l] + co];
-                    float* so = sout + (b * cap + co) * plane + (y + 1) * Wp + 1 + seg * P;
-#pragma unroll
-                    for (int p = 0; p < P; ++p) {
-                        float r = acc[c][p] + bias;
-                        if (a.layer[l].residual) r += so[p];
-                        if (a.layer[l].relu) r = fmaxf(r, 0.0f);
-                        if (last) a.out[(((size_t)g * C + co) * H + y) * W + seg * P + p] = r;
-                        else so[p] = r;
-                    }
-                }
-            }
-            __syncthreads();
-            cur ^= 1;
-        }
-    }
+    const int nb = a.boards_per_cta;
+    for (int tile = blockIdx.x; tile * nb < a.n; tile += gridDim.x)
+        small_tower_tile<P, CO>(a, s_w, s_act, tile * nb, min(nb, a.n - tile * nb), threadIdx.x, blockDim.x);
 }
 
 struct Plan { int P, CO, nb, threads, grid; size_t smem; bool ok; };
+}  // namespace
 
-Plan make_plan(SmallTowerArgs& a, int sm_count) {
-    Plan pl{};
-    pl.ok = false;
-    if (a.n < 1 || a.n_layers < 1 || a.n_layers > kSmallTowerMaxLayers) return pl;
-    if (a.W < 2 || a.W > 8 || a.H < 1 || a.H > 16 || a.C % 4 != 0 || a.C < 4) return pl;
+// Shared-memory layout of the tower's weights (w_smem_off / b_smem_off / w_floats) and the channel capacity of its
+// activation buffers; false when the shape is outside what the kernels handle.
+bool small_tower_layout(SmallTowerArgs& a) {
+    if (a.n_layers < 1 || a.n_layers > kSmallTowerMaxLayers) return false;
+    if (a.W < 2 || a.W > 8 || a.H < 1 || a.H > 16 || a.C % 4 != 0 || a.C < 4) return false;
     int cap = a.C, w_floats = 0;
     for (int l = 0; l < a.n_layers; ++l) {
         cap = std::max(cap, a.layer[l].cin);
         a.w_smem_off[l] = w_floats; w_floats += a.layer[l].cin * 9 * a.C;
         a.b_smem_off[l] = w_floats; w_floats += a.C;
     }
-    if (a.layer[0].cin != a.in_channels + (a.action ? 1 : 0)) return pl;
+    if (a.layer[0].cin != a.in_channels + (a.action ? 1 : 0)) return false;
+    a.cap_channels = cap; a.w_floats = w_floats;
+    return true;
+}
+
+namespace {
+
+Plan make_plan(SmallTowerArgs& a, int sm_count) {
+    Plan pl{};
+    pl.ok = false;
+    if (a.n < 1 || !small_tower_layout(a)) return pl;
+    const int cap = a.cap_channels, w_floats = a.w_floats;
     const int plane = (a.H + 2) * (a.W + 2);
     // CO = 4 only when that still gives every SM a few hundred threads
     int CO = ((long)a.n * (a.C / 4) * a.H >= (long)sm_count * 384) ? 4 : 1;

@@ -24,6 +24,7 @@ struct SmallTowerArgs {
     const int32_t* action;   // [n]: constant plane action/A appended as channel in_channels (dynamics stem), or nullptr
     int pool_stride;
     int n, C, H, W, A;
+    int g0;                  // boards [g0, g0 + n): in / out / action / gather_parent are addressed by the global index
     int in_channels;         // channels of `in` as stored (without the action plane)
     int n_layers;
     SmallTowerLayer layer[kSmallTowerMaxLayers];
@@ -32,6 +33,8 @@ struct SmallTowerArgs {
     int w_smem_off[kSmallTowerMaxLayers], b_smem_off[kSmallTowerMaxLayers];
 };
 
+// fills cap_channels, w_floats, w_smem_off, b_smem_off; false when the shape is outside what the kernels handle
+bool small_tower_layout(SmallTowerArgs& a);
 // true when the whole tower (all weights + two activation buffers of a board tile) fits on chip
 bool small_tower_supported(const SmallTowerArgs& a);
 cudaError_t launch_small_tower(SmallTowerArgs a, int sm_count, cudaStream_t stream);

@@ -36,8 +36,9 @@ MZ_DEVINL int nth_action(const unsigned (&w)[kJ], int n) {
 __global__ void __launch_bounds__(128) tree_step_wide_kernel(const __grid_constant__ TreeStepArgs a) {
     pdl_launch_dependents();
     pdl_wait();
-    const int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (g >= a.n) return;
+    const int local = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (local >= a.n) return;
+    const int g = a.g0 + local;
     const int lane = threadIdx.x & 31;
     const int N = a.N, A = a.A;
     const size_t slots = (size_t)(N + 1) * A;

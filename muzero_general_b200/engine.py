@@ -141,6 +141,11 @@ class SearchEngine:
         return int(self.lib.mz_launch_count(self._h))
 
     @property
+    def graph_partitions(self):
+        """Parallel branches of the replayed search graph (1 = one chain of kernels)."""
+        return int(self.lib.mz_graph_partitions(self._h))
+
+    @property
     def last_search_ms(self):
         return float(self.lib.mz_last_search_ms(self._h))
 
@@ -149,7 +154,8 @@ class SearchEngine:
         """Arithmetic of the search path (bench.py's dtype)."""
         return self.lib.mz_numerics(self._h).decode()
 
-    KERNEL_CLASSES = ("tree_step_kernel", "conv_tower_tc_kernel", "heads_kernel", "conv3x3_kernel", "other", "small_tower_kernel")
+    KERNEL_CLASSES = ("tree_step_kernel", "conv_tower_tc_kernel", "heads_kernel", "conv3x3_kernel", "other", "small_tower_kernel",
+                      "small_search_kernel")
 
     def kernel_timing(self, enable):
         """Bracket every kernel of the step-wise pipeline with CUDA events (no graph replay while enabled)."""

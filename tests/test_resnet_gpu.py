@@ -371,3 +371,76 @@ def test_tower_modes_agree_across_batch_sizes(mode, game_configs, monkeypatch):
         for k in ("hidden", "value_logits", "policy_logits", "reward_logits", "value", "reward"):
             assert numpy.array_equal(part1[k], whole1[k][lo:hi]), (k, lo)
     eng.close()
+
+
+@pytest.mark.parametrize("name,n,N,parts", [("connect4", 300, 24, 2), ("connect4", 520, 12, 4), ("tictactoe", 400, 25, 3)])
+def test_partitioned_replay_does_not_change_results(name, n, N, parts, game_configs, monkeypatch):
+    """The replayed graph runs the simulations of disjoint game ranges as parallel branches (MZ_PARTS; default 2 for the
+    tensor-core towers): the towers of one range overlap the heads and tree steps of the others.  Every game is still
+    evaluated by the same arithmetic: visit counts, root values, value ranges and tree depths of the eager, captured
+    and replayed searches equal those of a single-chain handle, bit for bit."""
+    cfg = game_configs[name]
+    spec = netspec_from_config(cfg)
+    rs = numpy.random.RandomState(11)
+    obs = rs.random_sample((n, spec.obs_elems)).astype(numpy.float32)
+    noise = rs.dirichlet([cfg.root_dirichlet_alpha] * spec.action_space, size=n)
+    monkeypatch.setenv("MZ_TC_MODE", "x3")
+    results = []
+    for p in (1, parts):
+        monkeypatch.setenv("MZ_PARTS", str(p))
+        eng = _engine(cfg, n, N)
+        eng.load_weights(weights_for(name, spec))
+        runs = [eng.search(obs=obs, add_exploration_noise=True, noise=noise) for _ in range(4)]
+        assert eng.graph_partitions == p
+        for r in runs[1:]:
+            assert numpy.array_equal(r.visit_counts, runs[0].visit_counts)
+            assert numpy.array_equal(r.root_value, runs[0].root_value)
+        results.append(runs[-1])
+        eng.close()
+    a, b = results
+    assert numpy.array_equal(a.visit_counts, b.visit_counts)
+    assert numpy.array_equal(a.root_value, b.root_value)
+    assert numpy.array_equal(a.value_range, b.value_range)
+    assert numpy.array_equal(a.max_tree_depth, b.max_tree_depth)
+    assert (b.visit_counts.sum(1) == N).all()
+
+
+@pytest.mark.parametrize("name,n,N", [("tictactoe", 1, 25), ("tictactoe", 700, 50), ("tictactoe", 8192, 10), ("breakout", 5, 20), ("breakout", 300, 12)])
+def test_fused_small_search_equals_stepwise_pipeline(name, n, N, game_configs, monkeypatch):
+    """Small residual networks run ALL simulations of a search in one launch (csrc/small_search.cu): a CTA takes its
+    games through dynamics tower -> reward head + rescale -> prediction tower -> value / policy heads -> tree step with the
+    very device functions of the stand-alone kernels.  Visit counts, root values, value ranges, tree depths and the
+    exported trees (hidden states included) equal the step-wise pipeline's (MZ_SMALL_SEARCH=0), bit for bit."""
+    cfg = game_configs[name]
+    spec = netspec_from_config(cfg)
+    A = spec.action_space
+    rs = numpy.random.RandomState(5)
+    obs = rs.random_sample((n, spec.obs_elems)).astype(numpy.float32)
+    noise = rs.dirichlet([cfg.root_dirichlet_alpha] * A, size=n)
+    legal = (rs.uniform(size=(n, A)) < 0.7).astype(numpy.uint8)
+    legal[numpy.arange(n), rs.randint(0, A, n)] = 1
+    results, trees = [], []
+    for on in ("0", "1"):
+        monkeypatch.setenv("MZ_SMALL_SEARCH", on)
+        eng = _engine(cfg, n, N)
+        eng.load_weights(weights_for(name, spec))
+        launches0 = eng.launch_count
+        runs = [eng.search(obs=obs, legal_mask=legal, add_exploration_noise=True, noise=noise, keep_tree=True) for _ in range(3)]
+        per_search = (eng.launch_count - launches0) // 3
+        for r in runs[1:]:
+            assert numpy.array_equal(r.visit_counts, runs[0].visit_counts)
+            assert numpy.array_equal(r.root_value, runs[0].root_value)
+        results.append((runs[-1], per_search))
+        trees.append([eng.export_tree(i, with_hidden=True) for i in (0, n // 2, n - 1)])
+        eng.close()
+    (a, la), (b, lb) = results
+    assert la - lb == 5 * N - 1, (la, lb)          # ONE search launch instead of 5 launches per simulation
+    assert numpy.array_equal(a.visit_counts, b.visit_counts)
+    assert numpy.array_equal(a.root_value, b.root_value)
+    assert numpy.array_equal(a.value_range, b.value_range)
+    assert numpy.array_equal(a.max_tree_depth, b.max_tree_depth)
+    assert numpy.array_equal(a.root_predicted_value, b.root_predicted_value)
+    assert (b.visit_counts.sum(1) == N).all()
+    for ta, tb in zip(*trees):
+        for k in ta:
+            assert numpy.array_equal(numpy.asarray(ta[k]), numpy.asarray(tb[k])), k
