@@ -76,9 +76,14 @@ __device__ __forceinline__ void group_bar(int group) {
 // (optional), conv1x1 + MLP + scalarisation of the launch's heads.  `blob` addresses the staged head weights
 // (blob[off] = head blob offset off), `scratch` is the group's private shared memory (HeadsArgs::warp_floats floats),
 // s_pos the padded-row table of the board layouts (unused for dense states), out_slot the pool slot of the rescaled state.  Shared by heads_kernel and the fused small-network search kernel.
+// Resident mode (fused search kernel): `tile` connects the sample to the padded shared-memory board buffers of the towers -
+// src: the board's raw state is read from there instead of a.x, dst: the rescaled state is ALSO written there (the
+// prediction tower's input), map: dense element c * HW + pos -> offset inside a board buffer, xmap: -> offset inside s_x.
+struct HeadsTile { const float* src; float* dst; const int* map; const int* xmap; };
+
 template <int GROUP>
 __device__ __forceinline__ void heads_one_sample(const HeadsArgs& a, const float* blob, float* scratch, const unsigned char* s_pos,
-                                                 int g, int group, int t, int out_slot) {
+                                                 int g, int group, int t, int out_slot, HeadsTile tile = HeadsTile{nullptr, nullptr, nullptr, nullptr}) {
     constexpr int kHeadGroup = GROUP;
     const int C = a.C, HW = a.HW, CP = C + 4;
     float* s_x = scratch;                                            // [HW][C+4]
@@ -114,8 +119,12 @@ __device__ __forceinline__ void heads_one_sample(const HeadsArgs& a, const float
             d[1] = make_float4(f2.x, f2.y, f3.x, f3.y);
         }
     } else {
-        const float* x = a.x + (size_t)g * C * HW;
-        for (int i = t; i < C * HW; i += kHeadGroup) s_x[(i % HW) * CP + i / HW] = x[i];
+        if (tile.src) {
+            for (int i = t; i < C * HW; i += kHeadGroup) s_x[tile.xmap[i]] = tile.src[tile.map[i]];
+        } else {
+            const float* x = a.x + (size_t)g * C * HW;
+            for (int i = t; i < C * HW; i += kHeadGroup) s_x[(i % HW) * CP + i / HW] = x[i];
+        }
     }
     group_bar<GROUP>(group);
 
@@ -190,6 +199,7 @@ __device__ __forceinline__ void heads_one_sample(const HeadsArgs& a, const float
                 const float v = div_pos_or_zero(__fsub_rn(s_x[p * CP + c], s_lo[c]), s_sc[c]);
                 if (a.rescaled) a.rescaled[(size_t)g * C * HW + i] = v;
                 if (a.pool_hidden) a.pool_hidden[((size_t)g * a.pool_stride + out_slot) * C * HW + i] = v;
+                if (tile.dst) tile.dst[tile.map[i]] = v;
             }
         }
     }
@@ -201,32 +211,34 @@ __device__ __forceinline__ void heads_one_sample(const HeadsArgs& a, const float
         const HeadDesc& d = a.head[h];
         float* cur = s_act + (size_t)h * 2 * a.smem_floats;
         float* nxt = cur + a.smem_floats;
-        // conv1x1: r[c][p] = b[c] + sum_k W[c][k] x[p][k]; one thread per position, 4 channels at a time
-        for (int p = u; p < HW; p += span) {
+        // conv1x1: r[c][p] = b[c] + sum_k W[c][k] x[p][k]; one item = (position, group of 4 channels), items spread over the
+        // head's threads (a small board with many reduced channels - TicTacToe: 9 positions x 16 channels - keeps every lane
+        // busy that way; Connect4's 2-4 reduced channels are one group: one thread per position as before)
+        const int n_cgroups = (d.rc + 3) >> 2;
+        for (int it = u; it < HW * n_cgroups; it += span) {
+            const int p = it % HW, c0 = (it / HW) << 2;
             const float4* xr = reinterpret_cast<const float4*>(s_x + p * CP);
-            for (int c0 = 0; c0 < d.rc; c0 += 4) {
-                const int nc = min(4, d.rc - c0);
-                float acc[4];
+            const int nc = min(4, d.rc - c0);
+            float acc[4];
 #pragma unroll
-                for (int cc = 0; cc < 4; ++cc) acc[cc] = cc < nc ? blob[d.b1_off + c0 + cc] : 0.0f;
-                const float4* w0 = reinterpret_cast<const float4*>(blob + d.w1_off + (size_t)c0 * C);
-                for (int k4 = 0; k4 < C / 4; ++k4) {
-                    const float4 x4 = xr[k4];
+            for (int cc = 0; cc < 4; ++cc) acc[cc] = cc < nc ? blob[d.b1_off + c0 + cc] : 0.0f;
+            const float4* w0 = reinterpret_cast<const float4*>(blob + d.w1_off + (size_t)c0 * C);
+            for (int k4 = 0; k4 < C / 4; ++k4) {
+                const float4 x4 = xr[k4];
 #pragma unroll
-                    for (int cc = 0; cc < 4; ++cc) {
-                        if (cc < nc) {
-                            const float4 w4 = w0[cc * (C / 4) + k4];
-                            acc[cc] = fmaf(w4.x, x4.x, acc[cc]);
-                            acc[cc] = fmaf(w4.y, x4.y, acc[cc]);
-                            acc[cc] = fmaf(w4.z, x4.z, acc[cc]);
-                            acc[cc] = fmaf(w4.w, x4.w, acc[cc]);
-                        }
+                for (int cc = 0; cc < 4; ++cc) {
+                    if (cc < nc) {
+                        const float4 w4 = w0[cc * (C / 4) + k4];
+                        acc[cc] = fmaf(w4.x, x4.x, acc[cc]);
+                        acc[cc] = fmaf(w4.y, x4.y, acc[cc]);
+                        acc[cc] = fmaf(w4.z, x4.z, acc[cc]);
+                        acc[cc] = fmaf(w4.w, x4.w, acc[cc]);
                     }
                 }
-#pragma unroll
-                for (int cc = 0; cc < 4; ++cc)
-                    if (cc < nc) cur[(c0 + cc) * HW + p] = acc[cc];      // flatten order (c, h, w) = NCHW view(-1, ...)
             }
+#pragma unroll
+            for (int cc = 0; cc < 4; ++cc)
+                if (cc < nc) cur[(c0 + cc) * HW + p] = acc[cc];          // flatten order (c, h, w) = NCHW view(-1, ...)
         }
         if (u < 4) { const int i = d.rc * HW + u; if (i < ((d.rc * HW + 3) & ~3)) cur[i] = 0.0f; }   // zero the padding
         group_bar<GROUP>(group);
@@ -238,20 +250,50 @@ __device__ __forceinline__ void heads_one_sample(const HeadsArgs& a, const float
                 const float4* a4 = reinterpret_cast<const float4*>(cur);
                 const float* b = blob + d.mlp.b_off[l];
                 const bool last = l == d.mlp.n - 1;
-                for (int o = u; o < ((out + 3) & ~3); o += span) {
+                const int out4 = (out + 3) & ~3;
+                // one warp per sample (GROUP == 32): a long dot product with few outputs (TicTacToe's 144 -> 8) would keep 8
+                // lanes busy for 36 steps; K is split over `ks` adjacent lanes instead (strided partial sums, a shuffle
+                // tree, then the bias).  A different summation order than the one-lane loop - both are fp32 sums compared
+                // with the reference under the tolerance of tests/test_resnet_gpu.py.
+                int ks = 1;
+                if constexpr (GROUP == 32) {
+                    while (ks < 8 && 2 * ks * out4 <= span && in4 >= 16 * ks) ks <<= 1;
+                }
+                if (ks > 1) {
+                    const int o = u / ks, part = u % ks;             // out4 * ks <= span: every thread of the head has a slot
+                    float acc = 0.0f;
                     if (o < out) {
-                        float acc = b[o];
 #pragma unroll 4
-                        for (int i = 0; i < in4; ++i) {
+                        for (int i = part; i < in4; i += ks) {
                             const float4 x4 = a4[i], w4 = W4[(size_t)i * out + o];
                             acc = fmaf(x4.x, w4.x, acc);
                             acc = fmaf(x4.y, w4.y, acc);
                             acc = fmaf(x4.z, w4.z, acc);
                             acc = fmaf(x4.w, w4.w, acc);
                         }
-                        nxt[o] = last ? acc : elu1(acc);
-                    } else {
-                        nxt[o] = 0.0f;                          // padding read by the next layer's float4 loads
+                    }
+                    const unsigned hmask = span >= 32 ? 0xffffffffu : (((1u << span) - 1u) << (h * span));
+                    for (int off = ks >> 1; off > 0; off >>= 1) acc += __shfl_xor_sync(hmask, acc, off);
+                    if (part == 0 && o < out4) {
+                        const float r = acc + (o < out ? b[o] : 0.0f);
+                        nxt[o] = o < out ? (last ? r : elu1(r)) : 0.0f;
+                    }
+                } else {
+                    for (int o = u; o < out4; o += span) {
+                        if (o < out) {
+                            float acc = b[o];
+#pragma unroll 4
+                            for (int i = 0; i < in4; ++i) {
+                                const float4 x4 = a4[i], w4 = W4[(size_t)i * out + o];
+                                acc = fmaf(x4.x, w4.x, acc);
+                                acc = fmaf(x4.y, w4.y, acc);
+                                acc = fmaf(x4.z, w4.z, acc);
+                                acc = fmaf(x4.w, w4.w, acc);
+                            }
+                            nxt[o] = last ? acc : elu1(acc);
+                        } else {
+                            nxt[o] = 0.0f;                          // padding read by the next layer's float4 loads
+                        }
                     }
                 }
                 float* tmp = cur; cur = nxt; nxt = tmp;

@@ -1252,7 +1252,7 @@ static bool small_search_build(ResNetDevice* r, const InferCall& c, const TreeSt
     if (!small_tower_layout(a.dyn) || !small_tower_layout(a.pred)) return false;
     const int cap = std::max(a.dyn.cap_channels, a.pred.cap_channels);
     a.dyn.cap_channels = a.pred.cap_channels = cap;
-    a.heads_dyn = R.heads_args(raw, 1, &r->reward_head, nullptr, nullptr, nullptr, c.reward, nullptr, hidden, c.pool_hidden, c.pool_stride, c.out_slot);
+    a.heads_dyn = R.heads_args(raw, 1, &r->reward_head, nullptr, nullptr, nullptr, c.reward, nullptr, nullptr, c.pool_hidden, c.pool_stride, c.out_slot);
     a.heads_pred = R.heads_args(pred_out, 2, &r->value_head, &r->policy_head, nullptr, c.policy_logits, c.value, nullptr, nullptr, nullptr, 0, 0);
     if (!(a.heads_dyn.C * a.heads_dyn.HW <= 1024)) return false;                   // one warp per sample (heads_kernel<32>)
     const int lo = std::min(a.heads_dyn.w_lo, a.heads_pred.w_lo);
@@ -1261,25 +1261,28 @@ static bool small_search_build(ResNetDevice* r, const InferCall& c, const TreeSt
     a.scratch_floats = std::max(a.heads_dyn.warp_floats, a.heads_pred.warp_floats);
     a.tree = tree;
     a.n = c.n; a.g0 = c.g0; a.n_sims = n_sims; a.first_slot = c.out_slot;
-    int tile = 0;
+    int tile = 0, row_stride = 0, board_stride = 0;
     const int tower_floats = ((a.dyn.w_floats + 3) & ~3) + ((a.pred.w_floats + 3) & ~3);
     if (!small_search_shape(hh, hw, C, r->net.action_space, c.n, r->sm_count, tower_floats, a.heads_floats, a.scratch_floats, cap,
-                            P, CO, G, &tile, threads, smem))
+                            P, CO, G, &tile, threads, smem, &row_stride, &board_stride))
         return false;
     a.tile = tile;
     a.dyn.boards_per_cta = a.pred.boards_per_cta = tile;
+    a.dyn.row_stride = a.pred.row_stride = row_stride;
+    a.dyn.board_stride = a.pred.board_stride = board_stride;
     a.off_wd = 0;
     a.off_wp = (a.dyn.w_floats + 3) & ~3;
     a.off_wh = tower_floats;
     a.off_scratch = a.off_wh + a.heads_floats;
-    a.off_act = a.off_scratch + (*threads / 32) * a.scratch_floats;
+    a.off_map = a.off_scratch + (*threads / 32) * a.scratch_floats;
+    a.off_act = a.off_map + 2 * C * hh * hw;
     *out = a;
     return true;
 }
 
 bool resnet_small_search_supported(ResNetDevice* r, const InferCall& c, const TreeStepArgs& tree, int n_sims) {
     // A/B switch: MZ_SMALL_SEARCH=0 keeps the step-wise pipeline, =1 uses the fused kernel wherever the shape allows
-    constexpr bool kDefaultOn = false;
+    constexpr bool kDefaultOn = true;
     const char* sw = getenv("MZ_SMALL_SEARCH");
     if (sw ? sw[0] != '1' : !kDefaultOn) return false;
     SmallSearchArgs a; int P, CO, G, threads; size_t smem;

@@ -21,12 +21,12 @@ struct SmallSearchArgs {
     int first_slot;                  // pool slot receiving the state of the first simulation
     int heads_lo, heads_floats;      // slice of the head blob staged in shared memory (covers the three heads)
     int scratch_floats;              // per-warp scratch of the heads
-    int off_wd, off_wp, off_wh, off_scratch, off_act;   // shared-memory layout (float offsets)
+    int off_wd, off_wp, off_wh, off_scratch, off_map, off_act;   // shared-memory layout (float offsets)
 };
 
 // P x CO: thread mapping of the towers (small_tower.cuh), G: lanes per game of the tree step (>= |A|)
 bool small_search_shape(int H, int W, int C, int A, int n, int sm_count, int tower_floats, int heads_floats, int scratch_floats,
-                        int cap_channels, int* P, int* CO, int* G, int* tile, int* threads, size_t* smem);
+                        int cap_channels, int* P, int* CO, int* G, int* tile, int* threads, size_t* smem, int* row_stride, int* board_stride);
 cudaError_t launch_small_search(SmallSearchArgs a, int P, int CO, int G, int threads, size_t smem, cudaStream_t stream);
 
 }  // namespace mz

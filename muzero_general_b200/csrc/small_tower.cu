@@ -34,7 +34,7 @@ __global__ void __launch_bounds__(kMaxThreads) small_tower_kernel(const __grid_c
     pdl_wait();                                            // weights are constants; the input comes from the previous kernel
     const int nb = a.boards_per_cta;
     for (int tile = blockIdx.x; tile * nb < a.n; tile += gridDim.x)
-        small_tower_tile<P, CO>(a, s_w, s_act, tile * nb, min(nb, a.n - tile * nb), threadIdx.x, blockDim.x);
+        small_tower_tile<P, CO, false>(a, s_w, s_act, tile * nb, min(nb, a.n - tile * nb), threadIdx.x, blockDim.x);
 }
 
 struct Plan { int P, CO, nb, threads, grid; size_t smem; bool ok; };
@@ -53,6 +53,7 @@ bool small_tower_layout(SmallTowerArgs& a) {
     }
     if (a.layer[0].cin != a.in_channels + (a.action ? 1 : 0)) return false;
     a.cap_channels = cap; a.w_floats = w_floats;
+    a.row_stride = a.W + 2; a.board_stride = cap * (a.H + 2) * (a.W + 2);
     return true;
 }
 

@@ -30,10 +30,13 @@ struct SmallTowerArgs {
     SmallTowerLayer layer[kSmallTowerMaxLayers];
     // filled by the launcher
     int boards_per_cta, cap_channels, w_floats;
+    int row_stride;          // floats between the rows of a padded plane (W + 2, or W + 3 to make it odd: see small_tower.cuh)
+    int board_stride;        // floats between the boards of an activation buffer (>= cap_channels * (H + 2) * row_stride)
     int w_smem_off[kSmallTowerMaxLayers], b_smem_off[kSmallTowerMaxLayers];
 };
 
-// fills cap_channels, w_floats, w_smem_off, b_smem_off; false when the shape is outside what the kernels handle
+// fills cap_channels, w_floats, w_smem_off, b_smem_off and the plain strides (row W + 2, board cap * plane); false when
+// the shape is outside what the kernels handle
 bool small_tower_layout(SmallTowerArgs& a);
 // true when the whole tower (all weights + two activation buffers of a board tile) fits on chip
 bool small_tower_supported(const SmallTowerArgs& a);

@@ -67,3 +67,10 @@ byfile = collections.Counter()
 for loc, n in ex.items():
     byfile[loc[0] if loc else None] += n
 print({k: f"{100*v/total:.1f}%" for k, v in byfile.most_common()})
+sbyfile = collections.Counter()
+for loc, n in samples.items():
+    sbyfile[loc[0] if loc else None] += n
+print("samples by file:", {k: f"{100*v/max(ts,1):.1f}%" for k, v in sbyfile.most_common()})
+print("top lines by samples:")
+for loc, n in samples.most_common(25):
+    print(f"{100*n/max(ts,1):5.1f}% samples  {100*ex[loc]/total:5.1f}% inst  {loc}")
