@@ -341,6 +341,7 @@ def run_workload(name, args, D, rank, local_rank, world, with_loop, headline):
     # n_batches input buffers, so its warm-up covers every buffer three times (eager, eager, capture) - untimed, like W
     dv = timed(search_device, args.steps, max(args.warmup, 3 * n_batches))
     launches = eng.launch_count - launches0
+    graph_parts = eng.graph_partitions
     clk = clocks.stop() if clocks else None
     hv = timed(search_host, args.steps, args.warmup)
     assert int(numpy.asarray(hv["visits"]).sum()) == B * N
@@ -407,6 +408,7 @@ def run_workload(name, args, D, rank, local_rank, world, with_loop, headline):
         "workload": name, "value": value, "unit": "env-steps/s", "sims_per_sec": value * N,
         "value_is": "search only (no environment step); see loop",
         "dtype": numerics, "games_per_gpu": B, "num_simulations": N,
+        "graph_branches": graph_parts,        # parallel branches of the replayed search graph (partitioned replay); 1 = one chain
         "steps": args.steps, "searches_per_step": dv["inner"], "ms_per_step": 1000.0 * wall / args.steps,
         "ms_per_search": percentiles(dv["per_search"]), "timed_seconds": wall,
         "kernel_ms_per_search": kern_ms / dv["searches"],

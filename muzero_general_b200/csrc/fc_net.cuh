@@ -220,4 +220,139 @@ MZ_DEVINL void support_to_scalar_group2(const float* la, const float* lb, int S,
     rb = inverse_value_transform(__fdiv_rn(nb, db));
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Fixed-shape recurrent inference (the fused search kernel's per-simulation network call).
+//
+// The generic code above walks run-time layer descriptors: for CartPole's 8 -> 16 -> {8, 21, 2, 21} networks seven of eight
+// instructions it executes are loop control, predicates and address arithmetic (profiles/r02_fc_search_ncu.md: FMAs are 13 %
+// of the network code).  When the five MLPs have the common shape
+//     dynamics  [E | one_hot(A)] -> H -> E          reward / value  E -> H -> F = 2S+1          policy  E -> H -> A
+// with compile-time E, H, F, A, everything unrolls: per four inputs one broadcast 128-bit load of x, one 128-bit load of
+// the packed weights and four FMAs; the next state, the 2 x F value / reward logits and the policy logit never leave
+// registers (no store + barrier + reload between the last layer, the rescale and support_to_scalar).  Every accumulator
+// sees the operations of linear_layer / rescale_unit_range / support_to_scalar_group2 in the same order: bit-identical to
+// the generic path (tests/test_tree_parity_gpu.py::test_full_size_invariants compares the two on 4096 games).
+template <int E_, int H_, int S_, int A_>
+struct FcFixedShape {
+    static constexpr bool kEnabled = true;
+    static constexpr int E = E_, H = H_, S = S_, F = 2 * S_ + 1, A = A_;
+    static_assert(E % 4 == 0 && H % 4 == 0, "vector widths");
+};
+struct FcGenericShape { static constexpr bool kEnabled = false; };
+
+// does the network have the fixed shape SH ?
+template <typename SH>
+inline bool fc_matches_fixed(const FcNet& n) {
+    auto two = [](const MlpDesc& d, int in, int hid, int out) {
+        return d.n == 2 && d.in_dense[0] == in && d.out[0] == hid && d.in_dense[1] == hid && d.out[1] == out && d.x_off[1] < 0;
+    };
+    return n.E == SH::E && n.S == SH::S && n.A == SH::A && two(n.dyn, SH::E, SH::H, SH::E) && n.dyn.x_off[0] >= 0 &&
+           two(n.rew, SH::E, SH::H, SH::F) && n.rew.x_off[0] < 0 && two(n.val, SH::E, SH::H, SH::F) && n.val.x_off[0] < 0 &&
+           two(n.pol, SH::E, SH::H, SH::A) && n.pol.x_off[0] < 0;
+}
+
+// acc = b[o] + sum_i x[i] W[i][o], i ascending, four inputs per step (the accumulation order of linear_layer)
+template <int IN>
+MZ_DEVINL float dot_packed(const float* __restrict__ W, int out, int o, float bias, const float* x) {
+    const float4* W4 = reinterpret_cast<const float4*>(W) + o;
+    const float4* x4 = reinterpret_cast<const float4*>(x);
+    float acc = bias;
+#pragma unroll
+    for (int i = 0; i < IN / 4; ++i) {
+        const float4 xv = x4[i];
+        const float4 wv = W4[i * out];
+        acc = fmaf(xv.x, wv.x, acc);
+        acc = fmaf(xv.y, wv.y, acc);
+        acc = fmaf(xv.z, wv.z, acc);
+        acc = fmaf(xv.w, wv.w, acc);
+    }
+    return acc;
+}
+
+// One recurrent inference (models.py:147-170, 128-131) of the group's game.  h: parent state (shared, E floats); hn: where
+// the rescaled next state goes (shared); s0, s1, sr, sp, sv: shared scratch vectors of >= max(E, H) floats.
+// Returns this lane's policy logit (lanes < A), the scalarised value and reward.
+template <int G, typename SH>
+MZ_DEVINL void fc_recurrent_fixed(const FcNet& net, const float* blob, const float* h, int action, float* hn,
+                                  float* s0, float* s1, float* sr, float* sp, float* sv, float& logit, float& value, float& reward) {
+    constexpr int E = SH::E, H = SH::H, F = SH::F, A = SH::A, S = SH::S;
+    static_assert(E <= G && A <= G, "one lane per state element / action");
+    const int lane = LaneGroup<G>::lane();
+    const MlpDesc &dy = net.dyn, &rw = net.rew, &vl = net.val, &pl = net.pol;
+    // ---- dynamics layer 1: [h | one_hot(action)] -> H, ELU
+#pragma unroll
+    for (int o = lane; o < H; o += G) {
+        float acc = dot_packed<E>(blob + dy.w_off[0], H, o, blob[dy.b_off[0] + o], h);
+        acc += blob[dy.x_off[0] + action * H + o];
+        s0[o] = elu1(acc);
+    }
+    LaneGroup<G>::sync();
+    // ---- dynamics layer 2: H -> E (identity); the raw next state stays in a register of lane o and goes to s1 for the reward head
+    float raw = 0.0f;
+    if (lane < E) {
+        raw = dot_packed<H>(blob + dy.w_off[1], E, lane, blob[dy.b_off[1] + lane], s0);
+        s1[lane] = raw;
+    }
+    // ---- min-max rescale over the E values (rescale_unit_range: same extrema, same subtraction and division)
+    float lo = lane < E ? raw : INFINITY, hi = lane < E ? raw : -INFINITY;
+    lo = -group_max_f32<G>(-lo);
+    hi = group_max_f32<G>(hi);
+    float sc = __fsub_rn(hi, lo);
+    if (sc < 1e-5f) sc = __fadd_rn(sc, 1e-5f);
+    if (lane < E) hn[lane] = div_pos_or_zero(__fsub_rn(raw, lo), sc);
+    LaneGroup<G>::sync();
+    // ---- first layers of the three heads side by side: reward on the raw state, policy and value on the rescaled one
+#pragma unroll
+    for (int o = lane; o < H; o += G) {
+        const float ar = dot_packed<E>(blob + rw.w_off[0], H, o, blob[rw.b_off[0] + o], s1);
+        const float ap = dot_packed<E>(blob + pl.w_off[0], H, o, blob[pl.b_off[0] + o], hn);
+        const float av = dot_packed<E>(blob + vl.w_off[0], H, o, blob[vl.b_off[0] + o], hn);
+        sr[o] = elu1(ar); sp[o] = elu1(ap); sv[o] = elu1(av);
+    }
+    LaneGroup<G>::sync();
+    // ---- second layers: logits in registers (lane l holds elements l, l + G, ...)
+    constexpr int R = (F + G - 1) / G;
+    float lr[R], lv[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const int o = lane + r * G;
+        lr[r] = 0.0f; lv[r] = 0.0f;
+        if (o < F) {
+            lr[r] = dot_packed<H>(blob + rw.w_off[1], F, o, blob[rw.b_off[1] + o], sr);
+            lv[r] = dot_packed<H>(blob + vl.w_off[1], F, o, blob[vl.b_off[1] + o], sv);
+        }
+    }
+    logit = 0.0f;
+    if (lane < A) logit = dot_packed<H>(blob + pl.w_off[1], A, lane, blob[pl.b_off[1] + lane], sp);
+    // ---- support_to_scalar of value and reward (support_to_scalar_group2 on registers: same maxima, sums and order)
+    const unsigned m = LaneGroup<G>::mask();
+    float ma = -INFINITY, mb = -INFINITY;
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+        if (lane + r * G < F) { ma = fmaxf(ma, lv[r]); mb = fmaxf(mb, lr[r]); }
+#pragma unroll
+    for (int off = G >> 1; off > 0; off >>= 1) {
+        ma = fmaxf(ma, __shfl_xor_sync(m, ma, off, G));
+        mb = fmaxf(mb, __shfl_xor_sync(m, mb, off, G));
+    }
+    float da = 0.0f, na = 0.0f, db = 0.0f, nb = 0.0f;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const int i = lane + r * G;
+        if (i < F) {
+            const float ea = expf(lv[r] - ma), eb = expf(lr[r] - mb);
+            da += ea; na = fmaf((float)(i - S), ea, na);
+            db += eb; nb = fmaf((float)(i - S), eb, nb);
+        }
+    }
+#pragma unroll
+    for (int off = G >> 1; off > 0; off >>= 1) {
+        da += __shfl_xor_sync(m, da, off, G); db += __shfl_xor_sync(m, db, off, G);
+        na += __shfl_xor_sync(m, na, off, G); nb += __shfl_xor_sync(m, nb, off, G);
+    }
+    value = inverse_value_transform(__fdiv_rn(na, da));
+    reward = inverse_value_transform(__fdiv_rn(nb, db));
+    LaneGroup<G>::sync();                              // sr / sp / sv / s0 / s1 are free again
+}
+
 }  // namespace mz

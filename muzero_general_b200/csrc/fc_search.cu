@@ -11,6 +11,8 @@
 #include "tree.cuh"
 #include "kernels.h"
 
+#include <stdlib.h>
+
 namespace mz {
 
 struct GameSmem {
@@ -40,7 +42,9 @@ __host__ __device__ inline GameSmem game_smem_layout(int N, int A, int E, int ma
     return L;
 }
 
-template <int G, bool kTeacher>
+// SH: FcFixedShape<E, H, S, A> runs the per-simulation network call through the fully unrolled fixed-shape code
+// (fc_net.cuh::fc_recurrent_fixed, bit-identical to the generic descriptors walk), FcGenericShape through the latter.
+template <int G, bool kTeacher, typename SH>
 __global__ void __launch_bounds__(kFcMaxThreads) fc_search_kernel(const __grid_constant__ FcSearchArgs a) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int N = a.N, A = a.A;
@@ -135,8 +139,11 @@ __global__ void __launch_bounds__(kFcMaxThreads) fc_search_kernel(const __grid_c
             } else {
                 // dynamics (models.py:147-170)
                 const float* h = s_hidden + (size_t)leaf.parent_exp * Epad;
-                float* raw = mlp_forward<G>(a.net.dyn, s_blob, h, s0, s1, s2, leaf.action);
                 float* hn = s_hidden + (size_t)t.n_expanded * Epad;
+                if constexpr (SH::kEnabled) {
+                    fc_recurrent_fixed<G, SH>(a.net, s_blob, h, leaf.action, hn, s0, s1, hb[0][0], hb[1][0], hb[2][0], logit, value, reward);
+                } else {
+                float* raw = mlp_forward<G>(a.net.dyn, s_blob, h, s0, s1, s2, leaf.action);
                 if (fused_heads) {
                     // rescale first, then reward (raw state), policy and value (rescaled state) side by side
                     rescale_unit_range<G>(raw, hn, E);
@@ -159,6 +166,7 @@ __global__ void __launch_bounds__(kFcMaxThreads) fc_search_kernel(const __grid_c
                     float* vl = mlp_forward<G>(a.net.val, s_blob, hn, s0, s1, s2);
                     value = support_to_scalar_group<G>(vl, S);
                     LaneGroup<G>::sync();
+                }
                 }
                 prior = group_softmax_masked<G>(logit, lane < A);
             }
@@ -215,7 +223,7 @@ __global__ void __launch_bounds__(kFcMaxThreads) fc_search_kernel(const __grid_c
 // ------------------------------------------------------------------------------------------
 // host launcher
 // ------------------------------------------------------------------------------------------
-template <int G, bool T>
+template <int G, bool T, typename SH>
 static cudaError_t launch_one(const FcSearchArgs& a, int sm_count, size_t smem_cap, cudaStream_t stream, FcLaunchInfo* info) {
     const GameSmem L = game_smem_layout(a.N, a.A, a.net.E, a.net.maxw, !T);
     const size_t shared_bytes = ((2 * (size_t)(a.N + 2) * 8 + (T ? 0 : (size_t)a.net.blob_floats) * 4) + 15) & ~(size_t)15;
@@ -224,7 +232,7 @@ static cudaError_t launch_one(const FcSearchArgs& a, int sm_count, size_t smem_c
     if (groups < 1) return cudaErrorInvalidValue;
     const size_t smem = shared_bytes + (size_t)groups * L.bytes;
     if (smem > smem_cap) return cudaErrorInvalidConfiguration;
-    auto kern = fc_search_kernel<G, T>;
+    auto kern = fc_search_kernel<G, T, SH>;
     cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (err != cudaSuccess) return err;
     int per_sm = 0;
@@ -238,12 +246,20 @@ static cudaError_t launch_one(const FcSearchArgs& a, int sm_count, size_t smem_c
     return cudaGetLastError();
 }
 
+// shapes with a fully unrolled network path: games/cartpole.py (encoding 8, hidden 16, support 10, 2 actions)
+using CartPoleShape = FcFixedShape<8, 16, 10, 2>;
+
 cudaError_t launch_fc_search(const FcSearchArgs& a, int group, bool teacher, int sm_count, size_t smem_cap,
                              cudaStream_t stream, FcLaunchInfo* info) {
-#define MZ_CASE(GG)                                                                     \
-    case GG:                                                                            \
-        return teacher ? launch_one<GG, true>(a, sm_count, smem_cap, stream, info)      \
-                       : launch_one<GG, false>(a, sm_count, smem_cap, stream, info);
+    const char* generic = getenv("MZ_FC_GENERIC");             // A/B switch: always walk the layer descriptors
+    if (!teacher && !(generic && generic[0] == '1') && fc_matches_fixed<CartPoleShape>(a.net)) {
+        if (group == 16) return launch_one<16, false, CartPoleShape>(a, sm_count, smem_cap, stream, info);
+        if (group == 32) return launch_one<32, false, CartPoleShape>(a, sm_count, smem_cap, stream, info);
+    }
+#define MZ_CASE(GG)                                                                                     \
+    case GG:                                                                                            \
+        return teacher ? launch_one<GG, true, FcGenericShape>(a, sm_count, smem_cap, stream, info)      \
+                       : launch_one<GG, false, FcGenericShape>(a, sm_count, smem_cap, stream, info);
     switch (group) {
         MZ_CASE(4)
         MZ_CASE(8)

@@ -223,6 +223,7 @@ __device__ __forceinline__ void heads_one_sample(const HeadsArgs& a, const float
 #pragma unroll
             for (int cc = 0; cc < 4; ++cc) acc[cc] = cc < nc ? blob[d.b1_off + c0 + cc] : 0.0f;
             const float4* w0 = reinterpret_cast<const float4*>(blob + d.w1_off + (size_t)c0 * C);
+#pragma unroll 4
             for (int k4 = 0; k4 < C / 4; ++k4) {
                 const float4 x4 = xr[k4];
 #pragma unroll

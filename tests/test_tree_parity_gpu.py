@@ -276,3 +276,32 @@ def test_device_drawn_dirichlet_noise(game_configs):
                                [nz[i, k] for k in acts], None, seed=cfg.seed, game=int(gid[i]))
         assert [int(a.visit_counts[i, k]) for k in acts] == res.root_visits and a.root_value[i] == res.root_value
     eng.close()
+
+
+def test_fixed_shape_network_path_is_bit_identical_to_the_generic_one(game_configs, monkeypatch):
+    """The fused FC kernel evaluates CartPole's networks through fully unrolled fixed-shape code (fc_net.cuh::
+    fc_recurrent_fixed); MZ_FC_GENERIC=1 walks the layer descriptors instead.  Same operations in the same order: visit
+    counts, root values, value ranges and every hidden state of the exported trees are equal bit for bit."""
+    cfg = game_configs["cartpole"]
+    spec = netspec_from_config(cfg)
+    n, N, A = 1500, 50, 2
+    rs = numpy.random.RandomState(17)
+    obs = rs.uniform(-0.05, 0.05, size=(n, 4)).astype(numpy.float32)
+    noise = rs.dirichlet([0.25] * A, size=n)
+    outs, trees = [], []
+    for generic in ("1", "0"):
+        monkeypatch.setenv("MZ_FC_GENERIC", generic)
+        for wname in ("cartpole", "cartpole_pretrained"):
+            eng = _engine(cfg, n, N)
+            eng.load_weights(weights_for(wname, spec))
+            outs.append(eng.search(obs=obs, add_exploration_noise=True, noise=noise, keep_tree=True))
+            trees.append([eng.export_tree(i, with_hidden=True) for i in (0, 1, n // 3, n - 1)])
+            eng.close()
+    for a, b in ((outs[0], outs[2]), (outs[1], outs[3])):
+        assert numpy.array_equal(a.visit_counts, b.visit_counts)
+        assert numpy.array_equal(a.root_value, b.root_value)
+        assert numpy.array_equal(a.value_range, b.value_range)
+        assert numpy.array_equal(a.root_predicted_value, b.root_predicted_value)
+    for ta, tb in list(zip(trees[0], trees[2])) + list(zip(trees[1], trees[3])):
+        for k in ta:
+            assert numpy.array_equal(numpy.asarray(ta[k]), numpy.asarray(tb[k])), k
