@@ -77,6 +77,24 @@ MZ_DEVINL float group_max_f32(float v) {
     for (int off = G >> 1; off > 0; off >>= 1) v = fmaxf(v, __shfl_xor_sync(m, v, off, G));
     return v;
 }
+// The same reductions over the first W lanes of the group only (W a power of two <= G): valid in lanes < W.  With the lanes
+// >= W holding the neutral element the full-width reduction returns the same bits (max is exact, x + 0 is exact): these
+// just skip the steps that cannot change the result.
+constexpr int pow2_ceil_c(int n) { return n <= 1 ? 1 : 2 * pow2_ceil_c((n + 1) / 2); }
+template <int G, int W>
+MZ_DEVINL float group_max_f32_w(float v) {
+    const unsigned m = LaneGroup<G>::mask();
+#pragma unroll
+    for (int off = W >> 1; off > 0; off >>= 1) v = fmaxf(v, __shfl_xor_sync(m, v, off, G));
+    return v;
+}
+template <int G, int W>
+MZ_DEVINL float group_sum_f32_w(float v) {
+    const unsigned m = LaneGroup<G>::mask();
+#pragma unroll
+    for (int off = W >> 1; off > 0; off >>= 1) v += __shfl_xor_sync(m, v, off, G);
+    return v;
+}
 template <int G>
 MZ_DEVINL float group_sum_f32(float v) {
     const unsigned m = LaneGroup<G>::mask();

@@ -294,9 +294,10 @@ MZ_DEVINL void fc_recurrent_fixed(const FcNet& net, const float* blob, const flo
         s1[lane] = raw;
     }
     // ---- min-max rescale over the E values (rescale_unit_range: same extrema, same subtraction and division)
+    constexpr int WE = pow2_ceil_c(E);                 // lanes >= E hold the neutral elements: reduce over the first WE lanes
     float lo = lane < E ? raw : INFINITY, hi = lane < E ? raw : -INFINITY;
-    lo = -group_max_f32<G>(-lo);
-    hi = group_max_f32<G>(hi);
+    lo = -group_max_f32_w<G, WE>(-lo);
+    hi = group_max_f32_w<G, WE>(hi);
     float sc = __fsub_rn(hi, lo);
     if (sc < 1e-5f) sc = __fadd_rn(sc, 1e-5f);
     if (lane < E) hn[lane] = div_pos_or_zero(__fsub_rn(raw, lo), sc);

@@ -168,7 +168,8 @@ __global__ void __launch_bounds__(kFcMaxThreads) fc_search_kernel(const __grid_c
                     LaneGroup<G>::sync();
                 }
                 }
-                prior = group_softmax_masked<G>(logit, lane < A);
+                if constexpr (SH::kEnabled) prior = group_softmax_masked_w<G, pow2_ceil_c(SH::A)>(logit, lane < A);
+                else prior = group_softmax_masked<G>(logit, lane < A);
             }
             if (a.trace.depth) {
                 const size_t ti = (size_t)g * N + sim;

@@ -90,6 +90,15 @@ MZ_DEVINL float group_softmax_masked(float logit, bool valid) {
     return div_pos_or_zero(e, s);          // masked lanes (e = 0) must not drag the warp through the division slow path
 }
 
+// the same over the first W lanes only (W = pow2 >= |A|, compile time): valid in lanes < W, same bits
+template <int G, int W>
+MZ_DEVINL float group_softmax_masked_w(float logit, bool valid) {
+    const float m = group_max_f32_w<G, W>(valid ? logit : -INFINITY);
+    const float e = valid ? expf(logit - m) : 0.0f;
+    const float s = group_sum_f32_w<G, W>(e);
+    return div_pos_or_zero(e, s);
+}
+
 template <int G>
 MZ_DEVINL void tree_init_root(const TreeConst& c, GameTree& t, float prior_f32, float root_reward,
                               const double* noise /* [A] by action or nullptr */, bool generate_noise = false,
@@ -266,7 +275,8 @@ MZ_DEVINL int tree_expand(const TreeConst& c, GameTree& t, const Leaf& leaf, flo
 // ------------------------------------------------------------------------------------------
 // Backup along path[0..depth] (self_play.py:406-430).  The discounted value recurrence is a
 // serial chain (2 fp64 ops per level, run redundantly by every lane); the per-node updates
-// (value_sum, visit, running min/max) are independent and spread over the lanes.
+// (value_sum, visit, running min/max) are independent: lane j updates node j, all at once, after
+// the recurrence handed every lane the value its node saw.
 // ------------------------------------------------------------------------------------------
 template <int G>
 MZ_DEVINL void tree_backup(const TreeConst& c, GameTree& t, const Leaf& leaf, float leaf_value) {
@@ -281,16 +291,40 @@ MZ_DEVINL void tree_backup(const TreeConst& c, GameTree& t, const Leaf& leaf, fl
     int my_slot = -1;
     float my_reward = 0.0f;
     if (packed && k <= L) { my_slot = t.path[k]; my_reward = t.path_reward[k]; }
-    for (int j = L; j >= 0; --j) {
-        int slot;
-        float rf;
-        if (packed) {
-            slot = LaneGroup<G>::bcast(my_slot, j);
-            rf = LaneGroup<G>::bcast(my_reward, j);
-        } else {
-            slot = t.path[j];
-            rf = t.path_reward[j];
+    if (packed) {
+        // The recurrence runs on shuffles and every lane keeps the value its own node saw; the node updates then happen
+        // ONCE, all lanes in parallel (a divergent owner block inside the loop would be issued L + 1 times, one lane each).
+        double myv = 0.0;
+        for (int j = L; j >= 0; --j) {
+            const double r = (double)LaneGroup<G>::bcast(my_reward, j);
+            const bool same = (c.P == 1) || (((L - j) & 1) == 0);
+            if (j == k) myv = v;
+            const double rr = (c.P == 1) ? r : (same ? -r : r);
+            v = __dadd_rn(rr, __dmul_rn(c.discount, v));
         }
+        if (k <= L) {
+            const bool same = (c.P == 1) || (((L - k) & 1) == 0);
+            const double add = same ? myv : -myv;
+            double q;
+            if (k == 0) {
+                root_vsum = __dadd_rn(t.root_vsum, add);
+                q = __ddiv_rn(root_vsum, (double)(t.root_visit + 1));
+            } else {
+                const double s = __dadd_rn(t.vsum[my_slot], add);
+                const int n = t.visit[my_slot] + 1;
+                t.vsum[my_slot] = s;
+                t.visit[my_slot] = n;
+                q = __ddiv_rn(s, (double)n);
+            }
+            const double m = __dadd_rn((double)my_reward, __dmul_rn(c.discount, (c.P == 1) ? q : -q));
+            if (k > 0) t.mval[my_slot] = m;           // what the next selection will normalise for this child
+            lo = m;
+            hi = m;
+        }
+    } else {
+    for (int j = L; j >= 0; --j) {
+        const int slot = t.path[j];
+        const float rf = t.path_reward[j];
         const double r = (double)rf;
         // node.to_play == to_play  <=>  (L - j) even (players alternate every level)
         const bool same = (c.P == 1) || (((L - j) & 1) == 0);
@@ -316,6 +350,7 @@ MZ_DEVINL void tree_backup(const TreeConst& c, GameTree& t, const Leaf& leaf, fl
         // value = reward + discount * value                        (P == 1)
         const double rr = (c.P == 1) ? r : (same ? -r : r);
         v = __dadd_rn(rr, __dmul_rn(c.discount, v));
+    }
     }
     // only lanes 0..L hold candidates: reduce over the smallest power of two covering them,
     // then broadcast lane 0's result (lanes beyond the reduced width hold partial values)
