@@ -13,6 +13,7 @@
 
 #include <algorithm>
 #include <map>
+#include <type_traits>
 #include <string>
 #include <vector>
 
@@ -449,11 +450,38 @@ int mz_dispatch_search(MzHandle* h, const SearchCall& call, bool teacher, bool t
         // same argument set has been seen twice (first call runs eagerly so lazy attribute setup and
         // allocations happen outside capture).  Debug modes (teacher / trace) always run eagerly.
         const bool graphable = !teacher && !trace && !kt_enabled() && getenv("MZ_NO_GRAPH") == nullptr;
+        // Result pointers must not be part of a graph's identity: a caller that allocates its result arrays per call (the
+        // Python engine with device memory does) would never hit the cache.  The pipeline writes into the handle's own
+        // output arena and a few small device-to-device copies behind the graph hand the results over.
+        struct ResultCopy { void* dst; const void* src; size_t bytes; };
+        ResultCopy copies[8];
+        int n_copies = 0;
+        if (graphable) {
+            Arena ar;
+            const unsigned char* lo = h->d_out;
+            const unsigned char* hi = h->d_out + h->out_cap;
+            auto redirect = [&](auto*& ptr, size_t count) {
+                using T = std::remove_reference_t<decltype(*ptr)>;
+                const unsigned char* p8 = reinterpret_cast<const unsigned char*>(ptr);
+                if (!ptr || (p8 >= lo && p8 < hi)) return;               // absent, or already in the arena (host-memory calls)
+                const size_t o = ar.take(count * sizeof(T));
+                if (ar.off > h->out_cap) { ar.off = o; return; }         // (cannot happen: the arena is sized for max_games)
+                copies[n_copies++] = {ptr, h->d_out + o, count * sizeof(T)};
+                ptr = reinterpret_cast<T*>(h->d_out + o);
+            };
+            redirect(cont.visit_counts, (size_t)n * A);
+            redirect(cont.root_value, (size_t)n);
+            redirect(cont.root_predicted_value, (size_t)n);
+            redirect(cont.max_tree_depth, (size_t)n);
+            redirect(cont.tie_count, (size_t)n);
+            redirect(cont.root_priors, (size_t)n * A);
+            redirect(cont.value_range, (size_t)n * 2);
+        }
         uint64_t key = 1469598103934665603ull;
         auto mix = [&](uint64_t v) { key = (key ^ v) * 1099511628211ull; };
-        const void* ptrs[] = {call.obs, call.legal_mask, call.to_play, call.noise, call.first_index, call.game_id,
-                              call.move_index, call.visit_counts, call.root_value, call.root_predicted_value,
-                              call.max_tree_depth, call.tie_count, call.root_priors, call.value_range};
+        const void* ptrs[] = {call_.obs, call_.legal_mask, call_.to_play, call_.noise, call_.first_index, call_.game_id,
+                              call_.move_index, call_.visit_counts, call_.root_value, call_.root_predicted_value,
+                              call_.max_tree_depth, call_.tie_count, call_.root_priors, call_.value_range};
         for (const void* q : ptrs) mix((uint64_t)(uintptr_t)q);
         mix((uint64_t)n); mix((uint64_t)call.add_noise); mix((uint64_t)call.keep_tree); mix((uint64_t)call_.continue_from);
         auto run = [&](const SearchCall& sc, cudaStream_t st) {
@@ -533,6 +561,8 @@ int mz_dispatch_search(MzHandle* h, const SearchCall& call, bool teacher, bool t
             if (gr) gr->seen += 1;
             h->graph_parts = 1;
         }
+        for (int i = 0; i < n_copies; ++i)
+            MZ_CUDA(h, cudaMemcpyAsync(copies[i].dst, copies[i].src, copies[i].bytes, cudaMemcpyDeviceToDevice, h->stream));
     }
     return MZ_OK;
 }

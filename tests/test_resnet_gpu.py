@@ -444,3 +444,29 @@ def test_fused_small_search_equals_stepwise_pipeline(name, n, N, game_configs, m
     for ta, tb in zip(*trees):
         for k in ta:
             assert numpy.array_equal(numpy.asarray(ta[k]), numpy.asarray(tb[k])), k
+
+
+def test_graph_replay_does_not_depend_on_result_addresses(game_configs, monkeypatch):
+    """Device-memory callers get freshly allocated result arrays from the engine on every call; the replayed graph is keyed
+    by the INPUT addresses only (results go through the handle's arena and are copied behind the graph), so such a caller
+    still replays - seen here as the partitioned graph (2 branches) being in use although every call had new result arrays."""
+    import torch
+    cfg = game_configs["connect4"]
+    spec = netspec_from_config(cfg)
+    monkeypatch.setenv("MZ_TC_MODE", "x3")
+    monkeypatch.delenv("MZ_PARTS", raising=False)
+    n, N = 160, 6
+    rs = numpy.random.RandomState(2)
+    obs_host = rs.random_sample((n, spec.obs_elems)).astype(numpy.float32)
+    obs = torch.from_numpy(obs_host).cuda()
+    eng = _engine(cfg, n, N)
+    eng.load_weights(weights_for("connect4", spec))
+    ref = eng.search(obs=obs_host, add_exploration_noise=False)
+    keep = []
+    for _ in range(5):
+        out = eng.search(obs=obs, add_exploration_noise=False)
+        keep.append(out)                                  # keeps the result tensors alive: the next call gets new addresses
+        assert numpy.array_equal(out.visit_counts.cpu().numpy(), ref.visit_counts)
+        assert numpy.array_equal(out.root_value.cpu().numpy(), ref.root_value)
+    assert eng.graph_partitions == 2
+    eng.close()
