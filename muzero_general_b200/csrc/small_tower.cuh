@@ -106,7 +106,7 @@ __device__ __forceinline__ int small_tower_tile(const SmallTowerArgs& a, const f
             s_act[bb * bstride + ci * plane + (yy + 1) * Wp + x + 1] = v;
         }
     }
-    __syncthreads();
+    if (!(flags & kTileInputStaged)) __syncthreads();      // (a staged input became visible with the barrier above)
 
     const bool active = b < nbt;
     int cur = 0;
