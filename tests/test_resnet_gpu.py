@@ -405,7 +405,7 @@ def test_partitioned_replay_does_not_change_results(name, n, N, parts, game_conf
     assert (b.visit_counts.sum(1) == N).all()
 
 
-@pytest.mark.parametrize("name,n,N", [("tictactoe", 1, 25), ("tictactoe", 700, 50), ("tictactoe", 8192, 10), ("breakout", 5, 20), ("breakout", 300, 12)])
+@pytest.mark.parametrize("name,n,N", [("tictactoe", 1, 25), ("tictactoe", 700, 50), ("tictactoe", 3001, 12), ("tictactoe", 8192, 10), ("breakout", 5, 20), ("breakout", 300, 12)])
 def test_fused_small_search_equals_stepwise_pipeline(name, n, N, game_configs, monkeypatch):
     """Small residual networks run ALL simulations of a search in one launch (csrc/small_search.cu): a CTA takes its
     games through dynamics tower -> reward head + rescale -> prediction tower -> value / policy heads -> tree step with the
