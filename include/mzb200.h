@@ -222,6 +222,14 @@ double mz_last_search_ms(const MzHandle* h);
 int mz_kernel_timing(MzHandle* h, int32_t enable);
 int mz_kernel_times(MzHandle* h, double* ms, int64_t* count);
 
+/* Debug / tests (host only, no device needed): launch plan of the fused small-network search (csrc/small_search.cu) for a
+ * hidden board H x W x C, |A| actions, n games on sm_count SMs, with tower_floats + heads_floats of weights and scratch_floats
+ * of per-warp scratch in shared memory and cap_channels channels per activation buffer.  Returns 1 and fills
+ * plan[8] = {P, CO, G, games per CTA, threads per CTA, shared-memory bytes, row stride, board stride}, or 0 when the shape
+ * is not handled (the step-wise pipeline is used then). */
+int mz_debug_small_search_plan(int32_t H, int32_t W, int32_t C, int32_t A, int32_t n, int32_t sm_count, int32_t tower_floats,
+                               int32_t heads_floats, int32_t scratch_floats, int32_t cap_channels, int64_t* plan);
+
 /* Debug / parity: one conv3x3 (C -> C, stride 1, pad 1; models.py:206-209) with optional bias, residual and
  * ReLU on host NCHW fp32 data, through the CUDA-core kernel (use_tensor_cores = 0) or the tcgen05 implicit
  * GEMM (C = 64, H <= 6, W <= 7): 1 = fp16 operands, 2 = split fp16+bf16 operands with three partial products

@@ -18,6 +18,7 @@
 #include <vector>
 
 #include "handle.h"
+#include "small_search.h"
 
 using namespace mz;
 
@@ -863,6 +864,19 @@ extern "C" int mz_kernel_times(MzHandle* h, double* ms, int64_t* count) {
     cudaError_t e = kt_collect(ms, count);
     if (e != cudaSuccess) return fail(h, MZ_ECUDA, std::string("mz_kernel_times: ") + cudaGetErrorString(e));
     return MZ_OK;
+}
+
+extern "C" int mz_debug_small_search_plan(int32_t H, int32_t W, int32_t C, int32_t A, int32_t n, int32_t sm_count, int32_t tower_floats,
+                                          int32_t heads_floats, int32_t scratch_floats, int32_t cap_channels, int64_t* plan) {
+    if (!plan) return 0;
+    int P, CO, G, tile, threads, row_stride, board_stride;
+    size_t smem;
+    if (!small_search_shape(H, W, C, A, n, sm_count, tower_floats, heads_floats, scratch_floats, cap_channels, &P, &CO, &G, &tile, &threads,
+                            &smem, &row_stride, &board_stride))
+        return 0;
+    const int64_t out[8] = {P, CO, G, tile, threads, (int64_t)smem, row_stride, board_stride};
+    for (int i = 0; i < 8; ++i) plan[i] = out[i];
+    return 1;
 }
 
 // debug: one conv3x3 through either implementation (host NCHW in / out)

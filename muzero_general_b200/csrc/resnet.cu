@@ -1094,6 +1094,7 @@ bool resnet_uses_tensor_cores(const ResNetDevice* r) { return r->use_tc; }
 
 // Partitioned replay (abi.cu) needs every kernel of a recurrent inference to honour a first-game offset: the x3 towers,
 // the fused small towers and heads_kernel do; the per-layer convs, the fp16-mode towers and the generic heads route do not.
+static const int32_t kDryRunAction = 0;        // stands for the action array in dry runs (only its presence matters)
 bool resnet_can_partition(const ResNetDevice* r0) {
     ResNetDevice* r = const_cast<ResNetDevice*>(r0);
     if (!r->loaded) return false;
@@ -1102,7 +1103,7 @@ bool resnet_can_partition(const ResNetDevice* r0) {
     Runner R{r, nullptr, &launches, &err, r->max_batch, 0};
     const int nb = r->net.blocks;
     if (nb < 1) return false;
-    if (R.small_tower(r->dyn, 0, true, nb, nullptr, nullptr, r->C, r->hh, r->hw, nullptr, 0, reinterpret_cast<const int32_t*>(r), true) != 1) return false;
+    if (R.small_tower(r->dyn, 0, true, nb, nullptr, nullptr, r->C, r->hh, r->hw, nullptr, 0, &kDryRunAction, true) != 1) return false;
     if (R.small_tower(r->pred, 0, false, nb, nullptr, nullptr, r->C, r->hh, r->hw, nullptr, 0, nullptr, true) != 1) return false;
     // heads_kernel route (not heads_big): the head weights plus one group's tile fit in shared memory
     const int HW = r->hh * r->hw;

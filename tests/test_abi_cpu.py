@@ -131,3 +131,43 @@ def test_bench_conv_flops_agree_with_survey_table():
         conv = bench.conv3x3_flops(ns, N)
         total = f0 + N * f1
         assert 0.85 * total < conv <= total, (game, conv, total)
+
+
+def test_small_search_launch_plan():
+    """Host-side planner of the fused small-network search (csrc/small_search.cu::small_search_shape): tile sizes fill
+    whole waves of SMs, shared memory stays inside the 227 KB a CTA may use, the uniform-weight mapping gets the strides
+    that spread 32 rows over 32 banks, and shapes without an instantiated kernel are refused."""
+    import ctypes as C
+    from muzero_general_b200 import _lib
+    lib = _lib.load_library()
+
+    def plan(H, W, Cc, A, n, tower=11664, heads=5000, scratch=868, cap=17, sms=148):
+        out = (C.c_int64 * 8)()
+        ok = lib.mz_debug_small_search_plan(H, W, Cc, A, n, sms, tower, heads, scratch, cap, out)
+        return dict(zip(("P", "CO", "G", "tile", "threads", "smem", "row_stride", "board_stride"), out)) if ok else None
+
+    # TicTacToe, BASELINE batch: 8192 games -> two even waves of CTAs, one lane group per game, four output channels per thread
+    p = plan(3, 3, 16, 9, 8192)
+    assert (p["P"], p["CO"], p["G"]) == (3, 4, 16)
+    ctas = -(-8192 // p["tile"])
+    assert 1.9 < ctas / 148 <= 2.0 and p["tile"] * 16 <= p["threads"] <= 512 and p["threads"] % 32 == 0
+    assert p["smem"] <= 227 * 1024
+    # bank spreading of the uniform-weight mapping: odd row stride, 32 consecutive rows (board, y) hit 32 different banks
+    assert p["row_stride"] % 2 == 1 and p["board_stride"] >= 17 * 5 * p["row_stride"]
+    banks = {((r // 3) * p["board_stride"] + (r % 3) * p["row_stride"]) % 32 for r in range(32)}
+    assert len(banks) == 32
+    # a handful of games: one channel per thread (more threads per board), still one CTA per tile
+    q = plan(3, 3, 16, 9, 5)
+    assert q["CO"] == 1 and q["tile"] == 1
+    # the Breakout configuration's hidden board: 6 x 6 x 16, 4 actions, 128 games on 148 SMs -> one game per CTA
+    b = plan(6, 6, 16, 4, 128, tower=21024, heads=8600, scratch=1408)
+    assert b["G"] == 4 and b["tile"] == 1 and b["smem"] <= 227 * 1024
+    # same board, a large batch: uniform weights with P = W = 6
+    b2 = plan(6, 6, 16, 4, 4096, tower=21024, heads=8600, scratch=1408)
+    assert (b2["P"], b2["CO"]) == (6, 4) and b2["row_stride"] == 9 and b2["smem"] <= 227 * 1024
+    banks = {((r // 6) * b2["board_stride"] + (r % 6) * b2["row_stride"]) % 32 for r in range(32)}
+    assert len(banks) == 32
+    # not handled: 7 actions (no lane-group instantiation), a 7-wide board, weights beyond shared memory
+    assert plan(3, 3, 16, 7, 100) is None
+    assert plan(6, 7, 16, 4, 100) is None
+    assert plan(3, 3, 16, 9, 100, tower=70000) is None
