@@ -351,8 +351,12 @@ MZ_DEVINL void fc_recurrent_fixed(const FcNet& net, const float* blob, const flo
         da += __shfl_xor_sync(m, da, off, G); db += __shfl_xor_sync(m, db, off, G);
         na += __shfl_xor_sync(m, na, off, G); nb += __shfl_xor_sync(m, nb, off, G);
     }
-    value = inverse_value_transform(__fdiv_rn(na, da));
-    reward = inverse_value_transform(__fdiv_rn(nb, db));
+    // every lane holds the four sums: the lower half of the group scalarises the value, the upper half the reward - one
+    // division and one inverse transform per instruction stream instead of two - and two shuffles share the results
+    const bool upper = lane >= G / 2;
+    const float tr = inverse_value_transform(__fdiv_rn(upper ? nb : na, upper ? db : da));
+    value = __shfl_sync(m, tr, 0, G);
+    reward = __shfl_sync(m, tr, G / 2, G);
     LaneGroup<G>::sync();                              // sr / sp / sv / s0 / s1 are free again
 }
 

@@ -355,11 +355,26 @@ MZ_DEVINL void tree_backup(const TreeConst& c, GameTree& t, const Leaf& leaf, fl
     // only lanes 0..L hold candidates: reduce over the smallest power of two covering them,
     // then broadcast lane 0's result (lanes beyond the reduced width hold partial values)
     const int width = (L + 1 >= G) ? G : pow2_ceil(L + 1);
-    lo = group_min_f64<G>(lo, width);
-    hi = group_max_f64<G>(hi, width);
     const unsigned gm = LaneGroup<G>::mask();
+    if (width >= 2) {
+        // minimum and maximum in ONE butterfly: after the first exchange the lower half of the `width` lanes carries minimum
+        // candidates and the upper half maximum candidates (each lane sends the one it does not keep), the remaining steps
+        // stay inside the halves; lane 0 ends with the minimum, lane width/2 with the maximum (exact: no rounding involved)
+        const int half = width >> 1;
+        const bool up = (k & half) != 0;
+        const double got = shfl_xor_f64(gm, up ? lo : hi, half, G);
+        double val = up ? fmax(hi, got) : fmin(lo, got);
+        for (int off = half >> 1; off > 0; off >>= 1) {
+            const double r = shfl_xor_f64(gm, val, off, G);
+            val = up ? fmax(val, r) : fmin(val, r);
+        }
+        lo = shfl_f64(gm, val, 0, G);
+        hi = shfl_f64(gm, val, half, G);
+    } else {
+        lo = shfl_f64(gm, lo, 0, G);
+        hi = shfl_f64(gm, hi, 0, G);
+    }
     root_vsum = shfl_f64(gm, root_vsum, 0, G);
-    if (width < G) { lo = shfl_f64(gm, lo, 0, G); hi = shfl_f64(gm, hi, 0, G); }
     t.root_vsum = root_vsum;
     t.root_visit += 1;
     t.lo = fmin(t.lo, lo);
