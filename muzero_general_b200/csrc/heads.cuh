@@ -29,6 +29,7 @@ struct HeadsArgs {
     const float* x;            // [n, C, HW] input state (raw trunk output)
     const float* blob;
     int n, C, HW, S;
+    unsigned hw_inv;           // ceil(2^32 / HW) (0 when HW == 1): divisions by HW become a multiply-high
     int g0;                    // samples [g0, g0 + n), arrays addressed by the global index
     int n_heads;
     HeadDesc head[2];
@@ -92,6 +93,9 @@ __device__ __forceinline__ void heads_one_sample(const HeadsArgs& a, const float
     float* s_part = s_sc + C;                                        // [2][2][C] partial extrema
     float* s_act = s_part + 4 * C;                                   // per head: ping | pong
     constexpr int cj = 8;                                            // 8-channel chunks per position (board layout: C = 64)
+    // i / HW without a division: __umulhi(i, ceil(2^32 / HW)) is exact for 2 <= HW <= 1024 and i < 2^17 (checked exhaustively)
+    const unsigned hw_inv = a.hw_inv;                                // filled by the host (0: HW == 1)
+    auto div_hw = [&](int i) { return hw_inv ? (int)__umulhi((unsigned)i, hw_inv) : i; };
     const int c_shift = (C & (C - 1)) == 0 ? 31 - __clz(C) : -1;     // C is a power of two for every bundled network
     // ---- stage x[p][c]
     if (a.p64c4) {
@@ -123,7 +127,7 @@ __device__ __forceinline__ void heads_one_sample(const HeadsArgs& a, const float
             for (int i = t; i < C * HW; i += kHeadGroup) s_x[tile.xmap[i]] = tile.src[tile.map[i]];
         } else {
             const float* x = a.x + (size_t)g * C * HW;
-            for (int i = t; i < C * HW; i += kHeadGroup) s_x[(i % HW) * CP + i / HW] = x[i];
+            for (int i = t; i < C * HW; i += kHeadGroup) { const int c = div_hw(i); s_x[(i - c * HW) * CP + c] = x[i]; }
         }
     }
     group_bar<GROUP>(group);
@@ -195,7 +199,7 @@ __device__ __forceinline__ void heads_one_sample(const HeadsArgs& a, const float
             }
         } else {
             for (int i = t; i < C * HW; i += kHeadGroup) {
-                const int c = i / HW, p = i % HW;
+                const int c = div_hw(i), p = i - c * HW;
                 const float v = div_pos_or_zero(__fsub_rn(s_x[p * CP + c], s_lo[c]), s_sc[c]);
                 if (a.rescaled) a.rescaled[(size_t)g * C * HW + i] = v;
                 if (a.pool_hidden) a.pool_hidden[((size_t)g * a.pool_stride + out_slot) * C * HW + i] = v;
@@ -216,7 +220,7 @@ __device__ __forceinline__ void heads_one_sample(const HeadsArgs& a, const float
         // busy that way; Connect4's 2-4 reduced channels are one group: one thread per position as before)
         const int n_cgroups = (d.rc + 3) >> 2;
         for (int it = u; it < HW * n_cgroups; it += span) {
-            const int p = it % HW, c0 = (it / HW) << 2;
+            const int cg = div_hw(it), p = it - cg * HW, c0 = cg << 2;
             const float4* xr = reinterpret_cast<const float4*>(s_x + p * CP);
             const int nc = min(4, d.rc - c0);
             float acc[4];

@@ -977,6 +977,7 @@ struct Runner {
         HeadsArgs a{};
         a.p64c4 = p64c4 ? (r->split ? kLayoutSplit : kLayoutF16) : 0; a.W = r->hw; a.state_p64c4 = state_p64c4;
         a.x = x; a.blob = r->d_head; a.n = n; a.g0 = g0; a.C = r->C; a.HW = r->hh * r->hw; a.S = r->net.support_size;
+        a.hw_inv = a.HW >= 2 ? (unsigned)((0x100000000ull + (unsigned)a.HW - 1u) / (unsigned)a.HW) : 0u;
         a.n_heads = n_heads;
         int maxw = 32;
         const HeadDesc* hs[2] = {h0, h1};
