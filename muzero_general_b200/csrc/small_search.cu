@@ -7,7 +7,9 @@
 // dynamics call the leaf that tree step selected.  So a CTA takes a tile of games through ALL N simulations by itself:
 // tower weights, head weights and the activation buffers stay in shared memory for the whole search, the phases of a
 // simulation are separated by __syncthreads() instead of kernel boundaries, and nothing is launched or re-staged in
-// between.  The phases ARE the device functions of the stand-alone kernels (small_tower.cuh, heads.cuh,
+// between; the raw next state goes from the dynamics tower to the reward head, and the rescaled state from there to the
+// prediction tower, through the padded shared-memory board buffers (HeadsTile) - global memory only sees the gathered
+// parent state, the new pool state, the three network outputs per game and the tree.  The phases ARE the device functions of the stand-alone kernels (small_tower.cuh, heads.cuh,
 // tree_step.cuh) applied to the CTA's games, so every value - hidden states, logits, tree statistics, visit counts - is
 // bit-identical to the step-wise pipeline (tests/test_resnet_gpu.py::test_fused_small_search_equals_stepwise_pipeline).
 #include "small_search.h"
